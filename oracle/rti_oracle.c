@@ -1,0 +1,674 @@
+/*
+ * rti_oracle.c -- CPU ORACLE (test infrastructure; NOT part of the shipped product path).
+ *
+ * Straightforward dense C restatement of one SQP-RTI iteration of the reference controller.  Written for clarity,
+ * not speed: dense 7x7 / 9x9 loops, no structure exploitation.  The CUDA product (ad_mpc_b200/csrc) is an
+ * independent implementation that must reproduce these numbers.
+ *
+ * What each block follows (paths under /root/reference/data_driven_mpc/ros_gp_mpc/src/):
+ *   orc_ode / orc_model_jac : ad_mpc/ad_3d_optimizer.py:268-310 (CasADi model), generated C
+ *                             ad_mpc/c_generated_code/sim_car_model/sim_car_expl_ode_fun.c:51-291 and
+ *                             sim_car_expl_vde_forw.c:120-2371 (checked against the compiled originals, oracle/_ref)
+ *   orc_gp_predict          : model_fitting/gp.py:117-138 (kernel), :426-430 / :446-460 (mean), :140-165 (d/dz)
+ *   GP injection            : quad_mpc/quad_3d_optimizer.py:289-327,548-552 ; utils/utils.py:773-808
+ *   orc_rk4_sens            : acados sim_erk [EXT], options at acados_solver_sim_car.c:657-665 (4 stages, 1 step)
+ *   orc_prepare             : acados LINEAR_LS cost / BGH bounds [EXT], data at acados_solver_sim_car.c:378-605
+ *   orc_qp_solve            : HPIPM-style Mehrotra predictor-corrector IPM [EXT]; OCP-structured (Riccati) instead of
+ *                             the reference's FULL_CONDENSING (acados_solver_sim_car.c:145) -- same QP, same solution
+ *   orc_rti_step            : acados ocp_nlp_sqp_rti [EXT], options at acados_solver_sim_car.c:647-681
+ * [EXT] = acados@91a01d4 / HPIPM / BLASFEO, pinned in requirements.txt:1 but not vendored; algorithm restated from
+ * its published description and pinned by ad_mpc/sim_car_iterate.json (see tests/test_golden_iterate.py).
+ */
+#define _GNU_SOURCE
+#include "rti_oracle.h"
+#include <dlfcn.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NX ORC_NX
+#define NU ORC_NU
+#define NC ORC_NC
+
+void orc_default_opts(orc_opts *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->N = 20;
+    o->iter_max = 50;
+    o->dt = 0.05;
+    const double W[9] = {10, 10, 100, 0, 0, 0, 0, 1, 100};
+    const double We[7] = {1e-5, 1e-5, 1e-4, 0, 0, 0, 0};
+    memcpy(o->W, W, sizeof W);
+    memcpy(o->We, We, sizeof We);
+    for (int j = 0; j < 2; j++) { o->zl[j] = 10; o->zu[j] = 10; o->Zl[j] = 0; o->Zu[j] = 0; }
+    o->lbu[0] = -10; o->ubu[0] = 5; o->lbu[1] = -3; o->ubu[1] = 3;
+    o->lbx = -0.52; o->ubx = 0.52;
+    /* ad_3d.py:47-60, evaluated literally (note the reference's 3.14195) */
+    double mass = 1500, f_mass = 900, r_mass = mass - f_mass, L = 2.7;
+    o->mass = mass;
+    o->lf = L * (1 - f_mass / mass);
+    o->lr = L * (1 - r_mass / mass);
+    o->iz = o->lf * o->lr * (r_mass + f_mass);
+    o->cf2 = 2 * (f_mass * 0.5 * 9.81 * 0.165 * 180 / 3.14195);
+    o->cr2 = 2 * (r_mass * 0.5 * 9.81 * 0.165 * 180 / 3.14195);
+    /* HPIPM BALANCE-like settings [EXT]; design choice, see DESIGN.md */
+    o->mu0 = 10.0;
+    o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-8;
+    o->alpha_min = 1e-12;
+    o->lam_min = 1e-16;
+    o->t_min = 1e-16;
+    o->thr0 = 0.1;
+    o->reg = 1e-15;
+    o->gp_row[0] = 4; o->gp_row[1] = 5;
+    o->gp_feat[0] = 3; o->gp_feat[1] = 4; o->gp_feat[2] = 5; o->gp_feat[3] = 6;
+}
+
+/* ------------------------------------------------------------------ reference CasADi model (oracle/_ref) --- */
+typedef int (*casadi_fn)(const double **, double **, int *, double *, int);
+static casadi_fn ref_vde = 0, ref_ode = 0;
+
+int orc_load_ref_model(const char *path)
+{
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return -1;
+    ref_vde = (casadi_fn)dlsym(h, "sim_car_expl_vde_forw");
+    ref_ode = (casadi_fn)dlsym(h, "sim_car_expl_ode_fun");
+    return (ref_vde && ref_ode) ? 0 : -2;
+}
+
+/* ------------------------------------------------------------------------------------------ GP (gp.py) ----- */
+void orc_gp_predict(const orc_opts *o, const orc_gp *gp, const double *z, double *mu, double *dmu)
+{
+    const int M = o->gp_M, dz = o->gp_dz;
+    for (int j = 0; j < o->gp_nout; j++) {
+        const double *X = gp->X + (size_t)j * M * dz;
+        const double *al = gp->alpha + (size_t)j * M;
+        const double *ell = gp->ell + j * dz;
+        double m = 0.0, g[ORC_DZMAX] = {0};
+        for (int i = 0; i < M; i++) {
+            double d2 = 0.0, diff[ORC_DZMAX];
+            for (int d = 0; d < dz; d++) {
+                diff[d] = z[d] - X[i * dz + d];
+                d2 += diff[d] * diff[d] / (ell[d] * ell[d]);    /* gp.py:131-134 */
+            }
+            double k = gp->sigma_f[j] * exp(-0.5 * d2);         /* gp.py:138 (sigma_f, not squared) */
+            double ka = k * al[i];
+            m += ka;                                            /* gp.py:453 k_s^T K^-1 y */
+            for (int d = 0; d < dz; d++) g[d] += -ka * diff[d] / (ell[d] * ell[d]);   /* gp.py:165 */
+        }
+        mu[j] = m + gp->y_mean[j];
+        for (int d = 0; d < dz; d++) dmu[j * dz + d] = g[d];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ model ---------- */
+void orc_model_jac(const orc_opts *o, const orc_gp *gp, const double *x, const double *u, double p,
+                   const double *gp_state, double trigger, double *f, double *Jx, double *Ju)
+{
+    const double psi = x[2], vx = x[3], vy = x[4], r = x[5], dl = x[6];
+    const double u0 = u[0], u1 = u[1];
+    const double m = o->mass, lf = o->lf, lr = o->lr, iz = o->iz, cf2 = o->cf2, cr2 = o->cr2;
+    const double L = lr + lf, c = lr / L, q = 1.0 - p;
+    const double D = vx + 1e-99;                                   /* ad_3d_optimizer.py:290 */
+    const double sp = sin(psi), cp = cos(psi), sd = sin(dl), cd = cos(dl);
+    const double Ff = cf2 * (dl - (vy + lf * r) / D);              /* :290 */
+    const double Fr = cr2 * (lr * r - vy) / D;                     /* :296 */
+
+    f[0] = vx * cp - vy * sp;                                      /* :277 */
+    f[1] = vx * sp + vy * cp;                                      /* :280 */
+    f[2] = r;                                                      /* :283 */
+    f[3] = p * (u0 - (1.0 / m) * Ff * sd + vy * r) + q * u0;       /* :291-293 */
+    f[4] = p * ((1.0 / m) * (Fr + Ff * cd) - vx * r) + q * ((u1 * vx + dl * u0) * c);           /* :298-300 */
+    f[5] = p * ((1.0 / iz) * (lf * Ff * cd - lr * Fr)) + q * ((u1 * vx + dl * u0) / L);         /* :305-307 */
+    f[6] = u1;                                                     /* :310 */
+
+    memset(Jx, 0, 49 * sizeof(double));
+    memset(Ju, 0, 14 * sizeof(double));
+    const double Ff_vx = cf2 * (vy + lf * r) / (D * D), Ff_vy = -cf2 / D, Ff_r = -cf2 * lf / D, Ff_d = cf2;
+    const double Fr_vx = -Fr / D, Fr_vy = -cr2 / D, Fr_r = cr2 * lr / D;
+#define JX(i, j) Jx[(i) * 7 + (j)]
+#define JU(i, j) Ju[(i) * 2 + (j)]
+    JX(0, 2) = -vx * sp - vy * cp; JX(0, 3) = cp;  JX(0, 4) = -sp;
+    JX(1, 2) = vx * cp - vy * sp;  JX(1, 3) = sp;  JX(1, 4) = cp;
+    JX(2, 5) = 1.0;
+    JX(3, 3) = p * (-sd * Ff_vx / m);
+    JX(3, 4) = p * (-sd * Ff_vy / m + r);
+    JX(3, 5) = p * (-sd * Ff_r / m + vy);
+    JX(3, 6) = -p * (Ff_d * sd + Ff * cd) / m;
+    JU(3, 0) = 1.0;
+    JX(4, 3) = p * ((Fr_vx + cd * Ff_vx) / m - r) + q * u1 * c;
+    JX(4, 4) = p * (Fr_vy + cd * Ff_vy) / m;
+    JX(4, 5) = p * ((Fr_r + cd * Ff_r) / m - vx);
+    JX(4, 6) = p * (Ff_d * cd - Ff * sd) / m + q * u0 * c;
+    JU(4, 0) = q * dl * c;  JU(4, 1) = q * vx * c;
+    JX(5, 3) = p * (lf * cd * Ff_vx - lr * Fr_vx) / iz + q * u1 / L;
+    JX(5, 4) = p * (lf * cd * Ff_vy - lr * Fr_vy) / iz;
+    JX(5, 5) = p * (lf * cd * Ff_r - lr * Fr_r) / iz;
+    JX(5, 6) = p * lf * (Ff_d * cd - Ff * sd) / iz + q * u0 / L;
+    JU(5, 0) = q * dl / L;  JU(5, 1) = q * vx / L;
+    JU(6, 1) = 1.0;
+
+    if (o->gp_enabled && gp) {
+        /* gp_x = gp_state*trigger + x*(1-trigger)   quad_3d_optimizer.py:295 ; z = B_z [x;u]  gp.py:609-630 */
+        double z[ORC_DZMAX], mu[ORC_GPOUT_MAX], dmu[ORC_GPOUT_MAX * ORC_DZMAX];
+        for (int d = 0; d < o->gp_dz; d++) {
+            int fi = o->gp_feat[d];
+            if (fi < 7) z[d] = (gp_state ? gp_state[fi] : x[fi]) * trigger + x[fi] * (1.0 - trigger);
+            else z[d] = u[fi - 7];
+        }
+        orc_gp_predict(o, gp, z, mu, dmu);
+        for (int j = 0; j < o->gp_nout; j++) {
+            int row = o->gp_row[j];
+            f[row] += mu[j];                                       /* f + B_x mu   quad_3d_optimizer.py:315 */
+            for (int d = 0; d < o->gp_dz; d++) {
+                int fi = o->gp_feat[d];
+                if (fi < 7) JX(row, fi) += (1.0 - trigger) * dmu[j * o->gp_dz + d];
+                else JU(row, fi - 7) += dmu[j * o->gp_dz + d];
+            }
+        }
+    }
+#undef JX
+#undef JU
+}
+
+void orc_ode(const orc_opts *o, const orc_gp *gp, const double *x, const double *u, double p,
+             const double *gp_state, double trigger, double *xdot)
+{
+    double Jx[49], Ju[14];
+    orc_model_jac(o, gp, x, u, p, gp_state, trigger, xdot, Jx, Ju);
+}
+
+/* variational differential equation: xdot = f, dSx = Jx Sx, dSu = Jx Su + Ju   (row-major dense)
+ * mirrors the signature of sim_car_expl_vde_forw (sim_car_expl_vde_forw.c:120) */
+static void vde_forw(const orc_opts *o, const orc_gp *gp, const double *x, const double *Sx, const double *Su,
+                     const double *u, double p, const double *gp_state, double trigger, double *xdot,
+                     double *dSx, double *dSu)
+{
+    if (o->model_backend == 1 && ref_vde && !o->gp_enabled) {
+        /* the reference's own generated code: column-major dense inputs, CCS-sparse outputs
+         * (sparsity tables sim_car_expl_vde_forw.c:107-118: dSx 42 nz = rows 0..5 of each column,
+         *  dSu 13 nz = col 0 rows 0..5, col 1 rows 0..6) */
+        double Sxc[49], Suc[14], o1[42], o2[13], w[244];
+        int iw[3];
+        for (int i = 0; i < 7; i++) for (int j = 0; j < 7; j++) Sxc[j * 7 + i] = Sx[i * 7 + j];
+        for (int i = 0; i < 7; i++) for (int j = 0; j < 2; j++) Suc[j * 7 + i] = Su[i * 2 + j];
+        const double *arg[12] = {x, Sxc, Suc, u, &p};
+        double *res[10] = {xdot, o1, o2};
+        ref_vde(arg, res, iw, w, 0);
+        memset(dSx, 0, 49 * sizeof(double));
+        memset(dSu, 0, 14 * sizeof(double));
+        for (int j = 0; j < 7; j++) for (int i = 0; i < 6; i++) dSx[i * 7 + j] = o1[j * 6 + i];
+        for (int i = 0; i < 6; i++) dSu[i * 2 + 0] = o2[i];
+        for (int i = 0; i < 7; i++) dSu[i * 2 + 1] = o2[6 + i];
+        return;
+    }
+    double Jx[49], Ju[14];
+    orc_model_jac(o, gp, x, u, p, gp_state, trigger, xdot, Jx, Ju);
+    for (int i = 0; i < 7; i++) {
+        for (int j = 0; j < 7; j++) {
+            double s = 0;
+            for (int l = 0; l < 7; l++) s += Jx[i * 7 + l] * Sx[l * 7 + j];
+            dSx[i * 7 + j] = s;
+        }
+        for (int j = 0; j < 2; j++) {
+            double s = Ju[i * 2 + j];
+            for (int l = 0; l < 7; l++) s += Jx[i * 7 + l] * Su[l * 2 + j];
+            dSu[i * 2 + j] = s;
+        }
+    }
+}
+
+int orc_rk4_sens(const orc_opts *o, const orc_gp *gp, const double *x, const double *u, double p,
+                 const double *gp_state, double trigger, double *xn, double *A, double *B)
+{
+    /* classic RK4 on [x; Sx; Su], S(0) = [I 0]   (verified against the golden iterate) */
+    const double h = o->dt;
+    const double a[4] = {0.0, 0.5, 0.5, 1.0}, bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+    double Sx0[49] = {0}, Su0[14] = {0};
+    for (int i = 0; i < 7; i++) Sx0[i * 7 + i] = 1.0;
+    double kx[7] = {0}, kSx[49] = {0}, kSu[14] = {0};
+    double ax[7] = {0}, aSx[49] = {0}, aSu[14] = {0};
+    for (int s = 0; s < 4; s++) {
+        double xs[7], Sxs[49], Sus[14];
+        for (int i = 0; i < 7; i++) xs[i] = x[i] + h * a[s] * kx[i];
+        for (int i = 0; i < 49; i++) Sxs[i] = Sx0[i] + h * a[s] * kSx[i];
+        for (int i = 0; i < 14; i++) Sus[i] = Su0[i] + h * a[s] * kSu[i];
+        vde_forw(o, gp, xs, Sxs, Sus, u, p, gp_state, trigger, kx, kSx, kSu);
+        for (int i = 0; i < 7; i++) ax[i] += bw[s] * kx[i];
+        for (int i = 0; i < 49; i++) aSx[i] += bw[s] * kSx[i];
+        for (int i = 0; i < 14; i++) aSu[i] += bw[s] * kSu[i];
+    }
+    int bad = 0;
+    for (int i = 0; i < 7; i++) { xn[i] = x[i] + h * ax[i]; if (!isfinite(xn[i])) bad = 1; }
+    for (int i = 0; i < 49; i++) { A[i] = Sx0[i] + h * aSx[i]; if (!isfinite(A[i])) bad = 1; }
+    for (int i = 0; i < 14; i++) { B[i] = Su0[i] + h * aSu[i]; if (!isfinite(B[i])) bad = 1; }
+    return bad;
+}
+
+/* ------------------------------------------------------------------------------------------ prepare -------- */
+int orc_prepare(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, const double *yref,
+                const double *p, const double *gp_state, orc_lin *lin)
+{
+    const int N = o->N;
+    const double Ts = o->dt;
+    int bad = 0;
+    for (int k = 0; k < N; k++) {
+        const double *xk = it->x + k * 7, *uk = it->u + k * 2;
+        double xn[7];
+        double trig = (o->gp_enabled && o->gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
+        bad |= orc_rk4_sens(o, gp, xk, uk, p[k], gp_state, trig, xn, lin->A + k * 49, lin->B + k * 14);
+        for (int i = 0; i < 7; i++) lin->b[k * 7 + i] = xn[i] - it->x[(k + 1) * 7 + i];
+        /* LINEAR_LS, Vx=[I;0], Vu=[0;I], scaling Ts: grad = Ts * W (y - yref) */
+        for (int i = 0; i < 7; i++) lin->q[k * 7 + i] = Ts * o->W[i] * (xk[i] - yref[k * 9 + i]);
+        for (int j = 0; j < 2; j++) lin->r[k * 2 + j] = Ts * o->W[7 + j] * (uk[j] - yref[k * 9 + 7 + j]);
+    }
+    /* terminal: scaling 1 */
+    for (int i = 0; i < 7; i++) lin->q[N * 7 + i] = o->We[i] * (it->x[N * 7 + i] - yref[N * 9 + i]);
+    return bad;
+}
+
+/* ------------------------------------------------------------------------------------------ QP (IPM) ------- */
+typedef struct {
+    /* Newton-step right-hand sides */
+    double rgu[ORC_NMAX][2], rgx[ORC_NMAX + 1][7], rgsl[ORC_NMAX][2], rgsu[ORC_NMAX][2];
+    double rb[ORC_NMAX][7], rd[ORC_NMAX][NC], rm[ORC_NMAX][NC];
+    /* factorisation */
+    double Rt[ORC_NMAX][2], Qt6[ORC_NMAX + 1];
+    double K[ORC_NMAX][14], Luu[ORC_NMAX][3], P[ORC_NMAX + 1][49];
+    /* step */
+    double ddu[ORC_NMAX][2], ddx[ORC_NMAX + 1][7], dpi[ORC_NMAX][7], dlam[ORC_NMAX][NC], dt[ORC_NMAX][NC],
+        dsl[ORC_NMAX][2], dsu[ORC_NMAX][2];
+} ipm_ws;
+
+/* constraint activity mask: stage 0 has no state bound (x0 is eliminated, nbxe_0 = 7) */
+static inline int con_on(int k, int c) { return !((c == 2 || c == 5) && k == 0); }
+
+static void ipm_residuals(const orc_opts *o, const orc_lin *lin, const double *dlu, const double *duu,
+                          const double *dlx, const double *dux, const orc_qpsol *s, ipm_ws *w, double res[4],
+                          double *mu)
+{
+    const int N = o->N;
+    const double Ts = o->dt;
+    double ng = 0, nb = 0, nd = 0, nm = 0, summ = 0;
+    int nc = 0;
+    for (int k = 0; k <= N; k++) {
+        const double *dx = s->dx + k * 7;
+        if (k < N) {
+            const double *A = lin->A + k * 49, *B = lin->B + k * 14;
+            const double *du = s->du + k * 2, *pi = s->pi + k * 7, *lam = s->lam + k * NC, *t = s->t + k * NC;
+            for (int j = 0; j < 2; j++) {
+                double g = Ts * o->W[7 + j] * du[j] + lin->r[k * 2 + j];
+                for (int l = 0; l < 7; l++) g += B[l * 2 + j] * pi[l];
+                g += -lam[j] + lam[3 + j];
+                w->rgu[k][j] = g;
+                w->rgsl[k][j] = Ts * o->zl[j] + Ts * o->Zl[j] * s->sl[k * 2 + j] - lam[j] - lam[6 + j];
+                w->rgsu[k][j] = Ts * o->zu[j] + Ts * o->Zu[j] * s->su[k * 2 + j] - lam[3 + j] - lam[8 + j];
+                w->rd[k][j] = t[j] - (du[j] - dlu[k * 2 + j] + s->sl[k * 2 + j]);
+                w->rd[k][3 + j] = t[3 + j] - (duu[k * 2 + j] - du[j] + s->su[k * 2 + j]);
+                w->rd[k][6 + j] = t[6 + j] - s->sl[k * 2 + j];
+                w->rd[k][8 + j] = t[8 + j] - s->su[k * 2 + j];
+                ng = fmax(ng, fmax(fabs(g), fmax(fabs(w->rgsl[k][j]), fabs(w->rgsu[k][j]))));
+            }
+            if (k >= 1) {
+                w->rd[k][2] = t[2] - (dx[6] - dlx[k]);
+                w->rd[k][5] = t[5] - (dux[k] - dx[6]);
+            } else {
+                w->rd[k][2] = w->rd[k][5] = 0.0;
+            }
+            for (int i = 0; i < 7; i++) {
+                double v = lin->b[k * 7 + i] - s->dx[(k + 1) * 7 + i];
+                for (int l = 0; l < 7; l++) v += A[i * 7 + l] * dx[l];
+                for (int j = 0; j < 2; j++) v += B[i * 2 + j] * du[j];
+                w->rb[k][i] = v;
+                nb = fmax(nb, fabs(v));
+            }
+            for (int c = 0; c < NC; c++) {
+                if (!con_on(k, c)) { w->rm[k][c] = 0; continue; }
+                w->rm[k][c] = lam[c] * t[c];
+                nd = fmax(nd, fabs(w->rd[k][c]));
+                nm = fmax(nm, fabs(w->rm[k][c]));
+                summ += w->rm[k][c];
+                nc++;
+            }
+        }
+        if (k >= 1) {
+            const double Qk6 = (k < N) ? Ts * o->W[6] : o->We[6];
+            (void)Qk6;
+            for (int i = 0; i < 7; i++) {
+                double Qd = (k < N) ? Ts * o->W[i] : o->We[i];
+                double g = Qd * dx[i] + lin->q[k * 7 + i] - s->pi[(k - 1) * 7 + i];
+                if (k < N) {
+                    const double *A = lin->A + k * 49, *pi = s->pi + k * 7;
+                    for (int l = 0; l < 7; l++) g += A[l * 7 + i] * pi[l];
+                    if (i == 6) g += -s->lam[k * NC + 2] + s->lam[k * NC + 5];
+                }
+                w->rgx[k][i] = g;
+                ng = fmax(ng, fabs(g));
+            }
+        }
+    }
+    res[0] = ng; res[1] = nb; res[2] = nd; res[3] = nm;
+    *mu = summ / nc;
+}
+
+/* Riccati factorisation for the barrier-modified Hessian (matrix part only). */
+static void ipm_factor(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
+{
+    const int N = o->N;
+    const double Ts = o->dt;
+    /* barrier terms with soft-bound slacks eliminated */
+    for (int k = 0; k < N; k++) {
+        const double *lam = s->lam + k * NC, *t = s->t + k * NC;
+        for (int j = 0; j < 2; j++) {
+            double Sl = lam[j] / t[j], Su = lam[3 + j] / t[3 + j], Ssl = lam[6 + j] / t[6 + j],
+                   Ssu = lam[8 + j] / t[8 + j];
+            double Dl = Ts * o->Zl[j] + Sl + Ssl, Du = Ts * o->Zu[j] + Su + Ssu;
+            w->Rt[k][j] = Ts * o->W[7 + j] + Sl * (1.0 - Sl / Dl) + Su * (1.0 - Su / Du);
+        }
+        w->Qt6[k] = Ts * o->W[6] + (k >= 1 ? lam[2] / t[2] + lam[5] / t[5] : 0.0);
+    }
+    w->Qt6[N] = o->We[6];
+    double *P = w->P[N];
+    memset(P, 0, 49 * sizeof(double));
+    for (int i = 0; i < 7; i++) P[i * 7 + i] = (i == 6) ? w->Qt6[N] : o->We[i];
+    for (int k = N - 1; k >= 0; k--) {
+        const double *A = lin->A + k * 49, *B = lin->B + k * 14;
+        const double *Pn = w->P[k + 1];
+        double BA[7][9], PBA[7][9], G[9][9];
+        for (int i = 0; i < 7; i++) {
+            BA[i][0] = B[i * 2]; BA[i][1] = B[i * 2 + 1];
+            for (int j = 0; j < 7; j++) BA[i][2 + j] = A[i * 7 + j];
+        }
+        for (int i = 0; i < 7; i++) for (int c = 0; c < 9; c++) {
+            double v = 0;
+            for (int l = 0; l < 7; l++) v += Pn[i * 7 + l] * BA[l][c];
+            PBA[i][c] = v;
+        }
+        for (int a = 0; a < 9; a++) for (int c = 0; c < 9; c++) {
+            double v = 0;
+            for (int l = 0; l < 7; l++) v += BA[l][a] * PBA[l][c];
+            G[a][c] = v;
+        }
+        G[0][0] += w->Rt[k][0]; G[1][1] += w->Rt[k][1];
+        for (int i = 0; i < 7; i++) G[2 + i][2 + i] += (i == 6) ? w->Qt6[k] : Ts * o->W[i];
+        /* Cholesky of the 2x2 input block */
+        double l00 = sqrt(G[0][0] + o->reg), l10 = G[1][0] / l00, l11 = sqrt(G[1][1] + o->reg - l10 * l10);
+        w->Luu[k][0] = l00; w->Luu[k][1] = l10; w->Luu[k][2] = l11;
+        /* K = -Guu^-1 Gux */
+        for (int j = 0; j < 7; j++) {
+            double y0 = G[0][2 + j] / l00, y1 = (G[1][2 + j] - l10 * y0) / l11;
+            double k1 = y1 / l11, k0 = (y0 - l10 * k1) / l00;
+            w->K[k][j] = -k0; w->K[k][7 + j] = -k1;
+        }
+        double *Pk = w->P[k];
+        for (int i = 0; i < 7; i++) for (int j = 0; j < 7; j++)
+            Pk[i * 7 + j] = G[2 + i][2 + j] + G[2 + i][0] * w->K[k][j] + G[2 + i][1] * w->K[k][7 + j];
+        for (int i = 0; i < 7; i++) for (int j = 0; j < i; j++) {    /* symmetrise */
+            double m = 0.5 * (Pk[i * 7 + j] + Pk[j * 7 + i]);
+            Pk[i * 7 + j] = Pk[j * 7 + i] = m;
+        }
+    }
+}
+
+/* Solve for the Newton step given the complementarity right-hand side w->rm (vector part of the Riccati). */
+static void ipm_solve(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
+{
+    const int N = o->N;
+    const double Ts = o->dt;
+    double gl[ORC_NMAX][NC], rt[ORC_NMAX][2], qt6[ORC_NMAX], cl[ORC_NMAX][2], cu[ORC_NMAX][2],
+        Dl[ORC_NMAX][2], Du[ORC_NMAX][2];
+    for (int k = 0; k < N; k++) {
+        const double *lam = s->lam + k * NC, *t = s->t + k * NC;
+        for (int c = 0; c < NC; c++) gl[k][c] = con_on(k, c) ? (w->rm[k][c] - lam[c] * w->rd[k][c]) / t[c] : 0.0;
+        for (int j = 0; j < 2; j++) {
+            double Sl = lam[j] / t[j], Su = lam[3 + j] / t[3 + j], Ssl = lam[6 + j] / t[6 + j],
+                   Ssu = lam[8 + j] / t[8 + j];
+            Dl[k][j] = Ts * o->Zl[j] + Sl + Ssl;
+            Du[k][j] = Ts * o->Zu[j] + Su + Ssu;
+            cl[k][j] = w->rgsl[k][j] + gl[k][j] + gl[k][6 + j];
+            cu[k][j] = w->rgsu[k][j] + gl[k][3 + j] + gl[k][8 + j];
+            rt[k][j] = w->rgu[k][j] + (gl[k][j] - Sl * cl[k][j] / Dl[k][j]) - (gl[k][3 + j] - Su * cu[k][j] / Du[k][j]);
+        }
+        qt6[k] = (k >= 1) ? w->rgx[k][6] + gl[k][2] - gl[k][5] : 0.0;
+    }
+    /* backward vector recursion */
+    double pv[ORC_NMAX + 1][7], kf[ORC_NMAX][2];
+    for (int i = 0; i < 7; i++) pv[N][i] = w->rgx[N][i];
+    for (int k = N - 1; k >= 0; k--) {
+        const double *A = lin->A + k * 49, *B = lin->B + k * 14, *Pn = w->P[k + 1];
+        double h[7], gu[2], gx[7];
+        for (int i = 0; i < 7; i++) {
+            double v = pv[k + 1][i];
+            for (int l = 0; l < 7; l++) v += Pn[i * 7 + l] * w->rb[k][l];
+            h[i] = v;
+        }
+        for (int j = 0; j < 2; j++) {
+            double v = rt[k][j];
+            for (int l = 0; l < 7; l++) v += B[l * 2 + j] * h[l];
+            gu[j] = v;
+        }
+        for (int i = 0; i < 7; i++) {
+            double v = (k >= 1) ? ((i == 6) ? qt6[k] : w->rgx[k][i]) : 0.0;
+            for (int l = 0; l < 7; l++) v += A[l * 7 + i] * h[l];
+            gx[i] = v;
+        }
+        const double l00 = w->Luu[k][0], l10 = w->Luu[k][1], l11 = w->Luu[k][2];
+        double y0 = gu[0] / l00, y1 = (gu[1] - l10 * y0) / l11;
+        double k1 = y1 / l11, k0 = (y0 - l10 * k1) / l00;
+        kf[k][0] = -k0; kf[k][1] = -k1;
+        /* p_k = g_x + K^T g_u   (G_xu kf = -G_xu Guu^-1 g_u = K^T g_u) */
+        for (int i = 0; i < 7; i++) pv[k][i] = gx[i] + w->K[k][i] * gu[0] + w->K[k][7 + i] * gu[1];
+    }
+    /* forward rollout */
+    for (int i = 0; i < 7; i++) w->ddx[0][i] = 0.0;
+    for (int k = 0; k < N; k++) {
+        const double *A = lin->A + k * 49, *B = lin->B + k * 14, *Pn = w->P[k + 1];
+        for (int j = 0; j < 2; j++) {
+            double v = kf[k][j];
+            for (int l = 0; l < 7; l++) v += w->K[k][j * 7 + l] * w->ddx[k][l];
+            w->ddu[k][j] = v;
+        }
+        for (int i = 0; i < 7; i++) {
+            double v = w->rb[k][i];
+            for (int l = 0; l < 7; l++) v += A[i * 7 + l] * w->ddx[k][l];
+            for (int j = 0; j < 2; j++) v += B[i * 2 + j] * w->ddu[k][j];
+            w->ddx[k + 1][i] = v;
+        }
+        for (int i = 0; i < 7; i++) {
+            double v = pv[k + 1][i];
+            for (int l = 0; l < 7; l++) v += Pn[i * 7 + l] * w->ddx[k + 1][l];
+            w->dpi[k][i] = v;
+        }
+    }
+    /* recover slack, t and lambda steps */
+    for (int k = 0; k < N; k++) {
+        const double *lam = s->lam + k * NC, *t = s->t + k * NC;
+        for (int j = 0; j < 2; j++) {
+            double Sl = lam[j] / t[j], Su = lam[3 + j] / t[3 + j];
+            w->dsl[k][j] = -(cl[k][j] + Sl * w->ddu[k][j]) / Dl[k][j];
+            w->dsu[k][j] = -(cu[k][j] - Su * w->ddu[k][j]) / Du[k][j];
+            w->dt[k][j] = w->ddu[k][j] + w->dsl[k][j] - w->rd[k][j];
+            w->dt[k][3 + j] = -w->ddu[k][j] + w->dsu[k][j] - w->rd[k][3 + j];
+            w->dt[k][6 + j] = w->dsl[k][j] - w->rd[k][6 + j];
+            w->dt[k][8 + j] = w->dsu[k][j] - w->rd[k][8 + j];
+        }
+        if (k >= 1) {
+            w->dt[k][2] = w->ddx[k][6] - w->rd[k][2];
+            w->dt[k][5] = -w->ddx[k][6] - w->rd[k][5];
+        } else {
+            w->dt[k][2] = w->dt[k][5] = 0.0;
+        }
+        for (int c = 0; c < NC; c++)
+            w->dlam[k][c] = con_on(k, c) ? -(w->rm[k][c] + lam[c] * w->dt[k][c]) / t[c] : 0.0;
+    }
+}
+
+static double ipm_alpha(const orc_opts *o, const orc_qpsol *s, const ipm_ws *w)
+{
+    double a = 1.0;
+    for (int k = 0; k < o->N; k++) for (int c = 0; c < NC; c++) {
+        if (!con_on(k, c)) continue;
+        double l = s->lam[k * NC + c], t = s->t[k * NC + c], dl = w->dlam[k][c], dt = w->dt[k][c];
+        if (dl < 0 && -l / dl < a) a = -l / dl;
+        if (dt < 0 && -t / dt < a) a = -t / dt;
+    }
+    return a;
+}
+
+int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0,
+                 orc_qpsol *s, orc_stats *st)
+{
+    const int N = o->N;
+    ipm_ws *w = (ipm_ws *)malloc(sizeof(ipm_ws));
+    double dlu[ORC_NMAX * 2], duu[ORC_NMAX * 2], dlx[ORC_NMAX], dux[ORC_NMAX];
+    memset(s, 0, sizeof(*s));
+    /* bounds in delta form around the iterate */
+    for (int k = 0; k < N; k++) {
+        for (int j = 0; j < 2; j++) {
+            dlu[k * 2 + j] = o->lbu[j] - it->u[k * 2 + j];
+            duu[k * 2 + j] = o->ubu[j] - it->u[k * 2 + j];
+        }
+        dlx[k] = o->lbx - it->x[k * 7 + 6];
+        dux[k] = o->ubx - it->x[k * 7 + 6];
+    }
+    /* cold start (qp_solver_warm_start 0, sim_car_acados_ocp.json:885): primal 0 pushed thr0 inside its box */
+    for (int i = 0; i < 7; i++) s->dx[i] = x0[i] - it->x[i];     /* lbx_0 = ubx_0 = x0, eliminated (nbxe_0) */
+    for (int k = 0; k < N; k++) {
+        double *t = s->t + k * NC, *lam = s->lam + k * NC;
+        for (int j = 0; j < 3; j++) {
+            if (j == 2 && k == 0) { t[2] = t[5] = 1.0; lam[2] = lam[5] = 0.0; continue; }
+            double lo = (j < 2) ? dlu[k * 2 + j] : dlx[k], hi = (j < 2) ? duu[k * 2 + j] : dux[k];
+            double v = 0.0;
+            if (v - lo < o->thr0) {
+                if (hi - v < o->thr0) v = 0.5 * (lo + hi);
+                else v = lo + o->thr0;
+            } else if (hi - v < o->thr0) v = hi - o->thr0;
+            if (j < 2) s->du[k * 2 + j] = v; else s->dx[k * 7 + 6] = v;
+            t[j] = fmax(o->thr0, v - lo);
+            t[3 + j] = fmax(o->thr0, hi - v);
+        }
+        for (int j = 0; j < 2; j++) { t[6 + j] = o->thr0; t[8 + j] = o->thr0; }
+        for (int c = 0; c < NC; c++) if (con_on(k, c)) lam[c] = o->mu0 / t[c];
+    }
+    int status = 1, iter = 0;
+    double res[4] = {0}, mu = 0;
+    for (iter = 0;; iter++) {
+        ipm_residuals(o, lin, dlu, duu, dlx, dux, s, w, res, &mu);
+        if (!(isfinite(res[0]) && isfinite(res[1]) && isfinite(res[2]) && isfinite(res[3]))) { status = 3; break; }
+        if (res[0] < o->tol_stat && res[1] < o->tol_eq && res[2] < o->tol_ineq && res[3] < o->tol_comp) {
+            status = 0; break;
+        }
+        if (iter >= o->iter_max) { status = 1; break; }
+        /* predictor (affine scaling) */
+        ipm_factor(o, lin, s, w);
+        ipm_solve(o, lin, s, w);
+        double a_aff = ipm_alpha(o, s, w);
+        double mu_aff = 0; int nc = 0;
+        for (int k = 0; k < N; k++) for (int c = 0; c < NC; c++) if (con_on(k, c)) {
+            mu_aff += (s->lam[k * NC + c] + a_aff * w->dlam[k][c]) * (s->t[k * NC + c] + a_aff * w->dt[k][c]);
+            nc++;
+        }
+        mu_aff /= nc;
+        double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
+        /* corrector */
+        for (int k = 0; k < N; k++) for (int c = 0; c < NC; c++) if (con_on(k, c))
+            w->rm[k][c] = s->lam[k * NC + c] * s->t[k * NC + c] + w->dlam[k][c] * w->dt[k][c] - sigma * mu;
+        ipm_solve(o, lin, s, w);
+        double alpha = ipm_alpha(o, s, w);
+        if (alpha < o->alpha_min) { status = 2; break; }
+        if (alpha < 1.0) alpha *= 0.995;
+        for (int k = 0; k < N; k++) {
+            for (int j = 0; j < 2; j++) {
+                s->du[k * 2 + j] += alpha * w->ddu[k][j];
+                s->sl[k * 2 + j] += alpha * w->dsl[k][j];
+                s->su[k * 2 + j] += alpha * w->dsu[k][j];
+            }
+            for (int i = 0; i < 7; i++) {
+                s->dx[(k + 1) * 7 + i] += alpha * w->ddx[k + 1][i];
+                s->pi[k * 7 + i] += alpha * w->dpi[k][i];
+            }
+            for (int c = 0; c < NC; c++) if (con_on(k, c)) {
+                s->lam[k * NC + c] = fmax(s->lam[k * NC + c] + alpha * w->dlam[k][c], o->lam_min);
+                s->t[k * NC + c] = fmax(s->t[k * NC + c] + alpha * w->dt[k][c], o->t_min);
+            }
+        }
+    }
+    free(w);
+    /* hpipm {0 ok,1 maxiter,2 minstep,3 nan} -> acados {0,2,3,1}   [EXT]; SURVEY 8 A7 */
+    static const int map[4] = {0, 2, 3, 1};
+    if (st) {
+        st->qp_status = map[status];
+        st->qp_iter = iter;
+        memcpy(st->res, res, sizeof res);
+        double m = 0;
+        for (int i = 0; i < (N + 1) * 7; i++) m = fmax(m, fabs(s->dx[i]));
+        for (int i = 0; i < N * 2; i++) m = fmax(m, fabs(s->du[i]));
+        st->step_inf = m;
+    }
+    return status;
+}
+
+/* ------------------------------------------------------------------------------------------ RTI step ------- */
+int orc_rti_step(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref,
+                 const double *p, const double *gp_state, orc_iterate *it, orc_stats *st)
+{
+    const int N = o->N;
+    orc_lin *lin = (orc_lin *)malloc(sizeof(orc_lin));
+    orc_qpsol *sol = (orc_qpsol *)malloc(sizeof(orc_qpsol));
+    orc_stats local;
+    if (!st) st = &local;
+    memset(st, 0, sizeof(*st));
+    const double *gps = gp_state ? gp_state : x0;          /* quad_3d_optimizer.py:549 */
+    int bad = orc_prepare(o, gp, it, yref, p, gps, lin);
+    if (bad) { st->status = 1; free(lin); free(sol); return 1; }     /* ACADOS_FAILURE: NaN in linearisation */
+    orc_qp_solve(o, lin, it, x0, sol, st);
+    /* RTI tolerates QP maxiter; anything else is ACADOS_QP_FAILURE (4)  [EXT] */
+    st->status = (st->qp_status == 0 || st->qp_status == 2) ? 0 : 4;
+    if (st->status == 0) {
+        /* full step (step_length 1, fixed_step): primal += delta; duals <- QP duals */
+        for (int i = 0; i < (N + 1) * 7; i++) it->x[i] += sol->dx[i];
+        for (int i = 0; i < N * 2; i++) it->u[i] += sol->du[i];
+        memcpy(it->pi, sol->pi, sizeof(double) * N * 7);
+        memcpy(it->lam, sol->lam, sizeof(double) * N * NC);
+        memcpy(it->t, sol->t, sizeof(double) * N * NC);
+        memcpy(it->sl, sol->sl, sizeof(double) * N * 2);
+        memcpy(it->su, sol->su, sizeof(double) * N * 2);
+    }
+    free(lin); free(sol);
+    return st->status;
+}
+
+int orc_rti_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                  const double *p, const double *gp_state, double *xit, double *uit, double *piout,
+                  int *status, int *qp_status, int *qp_iter, int nthreads)
+{
+    const int N = o->N;
+    const size_t ny = (size_t)N * 9 + 7;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        orc_iterate *it = (orc_iterate *)malloc(sizeof(orc_iterate));
+#pragma omp for schedule(dynamic, 16)
+        for (int b = 0; b < B; b++) {
+            memset(it, 0, sizeof(*it));
+            memcpy(it->x, xit + (size_t)b * (N + 1) * 7, sizeof(double) * (N + 1) * 7);
+            memcpy(it->u, uit + (size_t)b * N * 2, sizeof(double) * N * 2);
+            orc_stats st;
+            orc_rti_step(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N,
+                         gp_state ? gp_state + (size_t)b * 7 : 0, it, &st);
+            memcpy(xit + (size_t)b * (N + 1) * 7, it->x, sizeof(double) * (N + 1) * 7);
+            memcpy(uit + (size_t)b * N * 2, it->u, sizeof(double) * N * 2);
+            if (piout) memcpy(piout + (size_t)b * N * 7, it->pi, sizeof(double) * N * 7);
+            if (status) status[b] = st.status;
+            if (qp_status) qp_status[b] = st.qp_status;
+            if (qp_iter) qp_iter[b] = st.qp_iter;
+        }
+        free(it);
+    }
+    return 0;
+}

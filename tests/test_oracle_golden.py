@@ -1,0 +1,151 @@
+"""Pins the CPU oracle against the reference's own artefacts:
+
+  * tests/golden/vde_vectors.npz   outputs of the reference's CasADi-generated sim_car_expl_vde_forw / _ode_fun
+  * tests/golden/sim_car_iterate.npz  converged acados iterate (N=40, p=0): dynamics gap, KKT relations, multiplier
+    conventions, and an RTI fixed-point test.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+TS = 0.05
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_model_matches_reference_vde_vectors(golden_dir):
+    """analytic f, Jx, Ju of the oracle == reference CasADi VDE (rows 0..5 of dSx; dSu pattern of the generated code)."""
+    g = _load(golden_dir, "vde_vectors.npz")
+    o = orc.default_opts()
+    worst = 0.0
+    for i in range(g["x"].shape[0]):
+        f, Jx, Ju = orc.model_jac(o, g["x"][i], g["u"][i], g["p"][i])
+        dSx = Jx @ g["Sx"][i]
+        dSu = Jx @ g["Su"][i] + Ju
+        scale = lambda a: np.maximum(1.0, np.abs(a))
+        worst = max(worst, (np.abs(f - g["xdot"][i]) / scale(g["xdot"][i])).max())
+        worst = max(worst, (np.abs(f - g["ode"][i]) / scale(g["ode"][i])).max())
+        worst = max(worst, (np.abs(dSx[:6] - g["dSx"][i][:6]) / scale(g["dSx"][i][:6])).max())
+        worst = max(worst, (np.abs(dSu[:6, 0] - g["dSu"][i][:6, 0]) / scale(g["dSu"][i][:6, 0])).max())
+        worst = max(worst, (np.abs(dSu[:, 1] - g["dSu"][i][:, 1]) / scale(g["dSu"][i][:, 1])).max())
+        # structural zeros of the generated code: row 6 of dSx, dSu[6,0]
+        assert np.all(dSx[6] == 0.0) and dSu[6, 0] == 0.0
+    assert worst < 1e-12, worst
+
+
+def test_ref_backend_equals_analytic_backend():
+    """RK4+sensitivities driven by the compiled reference VDE == driven by the analytic restatement."""
+    if not orc.load_ref_model():
+        pytest.skip("oracle/_ref not built (reference tree absent at build time)")
+    rng = np.random.default_rng(1)
+    o = orc.default_opts()
+    for p in (0.0, 1.0, 0.4):
+        for _ in range(40):
+            x = rng.normal(size=7) * np.array([10, 10, 1, 1, 0.5, 0.3, 0.2])
+            x[3] = rng.uniform(1, 15)
+            u = rng.normal(size=2)
+            o.model_backend = 0
+            xa, Aa, Ba, _ = orc.rk4_sens(o, x, u, p)
+            o.model_backend = 1
+            xr, Ar, Br, _ = orc.rk4_sens(o, x, u, p)
+            for a, r in ((xa, xr), (Aa, Ar), (Ba, Br)):
+                assert np.all(np.abs(a - r) <= 1e-12 * np.maximum(1.0, np.abs(r)))
+
+
+def _golden_lin(g, o):
+    N = g["u"].shape[0]
+    A, B, gap = [], [], 0.0
+    for k in range(N):
+        xn, Ak, Bk, bad = orc.rk4_sens(o, g["x"][k], g["u"][k], 0.0)
+        assert not bad
+        gap = max(gap, np.abs(xn - g["x"][k + 1]).max())
+        A.append(Ak)
+        B.append(Bk)
+    return np.array(A), np.array(B), gap
+
+
+def _golden_lam(g):
+    """[lbu0 lbu1 lbx | ubu0 ubu1 ubx | ls | us] for every stage; stage 0 has 7 state bounds (x0) instead of 1."""
+    l0, t0 = g["lam0"], g["t0"]
+    pick = lambda v: np.r_[v[0:2], 0.0, v[9:11], 0.0, v[18:22]]
+    return np.vstack([pick(l0)[None], g["lam"]]), np.vstack([pick(t0)[None], g["t"]])
+
+
+def test_golden_dynamics_gap(golden_dir):
+    g = _load(golden_dir, "sim_car_iterate.npz")
+    o = orc.default_opts(N=40)
+    _, _, gap = _golden_lin(g, o)
+    assert gap < 1e-12, gap          # 5.7e-14: pins f, RK4, dt=0.05, 1 step x 4 stages
+
+
+def test_golden_kkt_relations(golden_dir):
+    g = _load(golden_dir, "sim_car_iterate.npz")
+    o = orc.default_opts(N=40)
+    A, B, _ = _golden_lin(g, o)
+    lam, t = _golden_lam(g)
+    N = 40
+    R = np.array([o.W[7], o.W[8]])
+    for k in range(N):
+        # u-stationarity: Ts R u + B^T pi - lam_lbu + lam_ubu = 0  (u_ref = 0)  -> pins B_k, Ts scaling, sign of pi
+        s = TS * R * g["u"][k] + B[k].T @ g["pi"][k] - lam[k][0:2] + lam[k][3:5]
+        assert np.abs(s).max() < 2e-10
+        # slack stationarity: Ts z - lam_bound - lam_slack = 0
+        assert np.abs(TS * 10.0 - lam[k][0:2] - lam[k][6:8]).max() < 1e-9
+        assert np.abs(TS * 10.0 - lam[k][3:5] - lam[k][8:10]).max() < 1e-9
+        # t definitions
+        assert np.abs(t[k][0:2] - (g["u"][k] - np.array([-10, -3.0]) + g["sl"][k])).max() < 1e-12
+        assert np.abs(t[k][3:5] - (np.array([5, 3.0]) - g["u"][k] + g["su"][k])).max() < 1e-12
+        if k >= 1:
+            assert abs(t[k][2] - (g["x"][k][6] + 0.52)) < 1e-12 and abs(t[k][5] - (0.52 - g["x"][k][6])) < 1e-12
+    for k in range(1, N):
+        # x-stationarity rows with zero weight (v_x, v_y, r, delta): A^T pi_k - pi_{k-1} -/+ lam_x = 0 -> pins A_k
+        s = A[k].T @ g["pi"][k] - g["pi"][k - 1]
+        s[6] += -lam[k][2] + lam[k][5]
+        assert np.abs(s[3:]).max() < 1e-9
+    # stage-0 multiplier of the eliminated x0 bound: lam_lbx0 - lam_ubx0 = q_0 + A_0^T pi_0 (here on rows 3..6, W=0)
+    nu0 = g["lam0"][2:9] - g["lam0"][11:18]
+    assert np.abs((A[0].T @ g["pi"][0])[3:] - nu0[3:]).max() < 1e-9
+
+
+def _recover_yref(g, o, A, lam, We):
+    """positions/heading reference from x-stationarity rows 0..2 (W>0); other rows copy the iterate (W=0)."""
+    N = 40
+    yref = np.zeros(N * 9 + 7)
+    W = np.array(o.W[:7])
+    for k in range(N):
+        xr = g["x"][k].copy()
+        if k >= 1:
+            s = A[k].T @ g["pi"][k] - g["pi"][k - 1]
+            xr[:3] = g["x"][k][:3] + s[:3] / (TS * W[:3])
+        yref[k * 9:k * 9 + 7] = xr
+    xr = g["x"][N].copy()
+    xr[:3] = g["x"][N][:3] - g["pi"][N - 1][:3] / We[:3]
+    yref[N * 9:] = xr
+    return yref
+
+
+def test_golden_rti_fixed_point(golden_dir):
+    """One RTI step started AT the converged acados iterate must return (numerically) zero step and the golden duals."""
+    g = _load(golden_dir, "sim_car_iterate.npz")
+    We = np.array([10.0, 10.0, 100.0, 0, 0, 0, 0])   # the dump's W_e is not the in-tree one; any W_e with
+    o = orc.default_opts(N=40, We=We)               # a consistent terminal reference gives the same fixed point
+    A, B, _ = _golden_lin(g, o)
+    lam, t = _golden_lam(g)
+    yref = _recover_yref(g, o, A, lam, We)
+    # recovered reference is a smooth path near the iterate
+    ref_xy = yref[:40 * 9].reshape(40, 9)[:, :2]
+    assert np.abs(ref_xy - g["x"][:40, :2]).max() < 2.0
+    it = orc.make_iterate(o, g["x"], g["u"])
+    st = orc.rti_step(o, it, g["x"][0], yref, np.zeros(40))
+    assert st["status"] == 0 and st["qp_status"] == 0
+    assert st["step_inf"] < 5e-7, st
+    arr = orc.iterate_arrays(o, it)
+    assert np.abs(arr["x"] - g["x"]).max() < 5e-7 and np.abs(arr["u"] - g["u"]).max() < 5e-7
+    assert np.abs(arr["pi"] - g["pi"]).max() < 1e-5
+    act = lam > 1e-3          # active multipliers (input bound at stage 0, slack multipliers 0.5 = Ts*z)
+    assert np.abs(arr["lam"][act] - lam[act]).max() < 1e-5
