@@ -1,0 +1,813 @@
+// api.cu -- C ABI of libadmpc_b200.so (include/admpc.h): batched handle + the acados-shim twin.
+// Host side only orchestrates: device memory, one stream per handle, layout kernels, the three solver kernels.
+// No CPU fallback exists: without a usable CUDA device every entry point returns ADMPC_E_CUDA.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+void admpc_set_error(const char *what, const char *msg) { snprintf(g_err, sizeof g_err, "%s: %s", what, msg); }
+extern "C" const char *admpc_last_error(void) { return g_err; }
+
+extern "C" int admpc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void admpc_default_opts(admpc_opts *o)
+{
+    memset(o, 0, sizeof *o);
+    o->N = 20;
+    o->iter_max = 50;
+    o->dt = 0.05;
+    const double W[9] = {10, 10, 100, 0, 0, 0, 0, 1, 100};     // acados_solver_sim_car.c:393-399
+    const double We[7] = {1e-5, 1e-5, 1e-4, 0, 0, 0, 0};       // acados_solver_sim_car.c:481-485
+    memcpy(o->W, W, sizeof W);
+    memcpy(o->We, We, sizeof We);
+    for (int j = 0; j < 2; j++) { o->zl[j] = o->zu[j] = 10.0; o->Zl[j] = o->Zu[j] = 0.0; }
+    o->lbu[0] = -10; o->ubu[0] = 5; o->lbu[1] = -3; o->ubu[1] = 3;
+    o->lbx = -0.52; o->ubx = 0.52;
+    // ad_3d.py:47-60 evaluated literally (the reference's pi literal is 3.14195)
+    const double mass = 1500, f_mass = 900, r_mass = mass - f_mass, L = 2.7;
+    o->mass = mass;
+    o->lf = L * (1 - f_mass / mass);
+    o->lr = L * (1 - r_mass / mass);
+    o->iz = o->lf * o->lr * (r_mass + f_mass);
+    o->cf2 = 2 * (f_mass * 0.5 * 9.81 * 0.165 * 180 / 3.14195);
+    o->cr2 = 2 * (r_mass * 0.5 * 9.81 * 0.165 * 180 / 3.14195);
+    o->mu0 = 10.0;
+    o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-8;
+    o->alpha_min = 1e-12;
+    o->lam_min = o->t_min = 1e-16;
+    o->thr0 = 0.1;
+    o->reg = 1e-15;
+    o->gp_feat[0] = 3; o->gp_feat[1] = 4; o->gp_feat[2] = 5; o->gp_feat[3] = 6;
+    o->gp_row[0] = 4; o->gp_row[1] = 5;
+}
+
+// ---------------------------------------------------------------------------------------------- NCCL (dlopen) ---
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(nccl_uid *) = nullptr;
+    int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.lib) return 0;
+    const char *cands[] = {getenv("ADMPC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *l = nullptr;
+    for (const char *c : cands) {
+        if (!c) continue;
+        l = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (l) break;
+    }
+    if (!l) { admpc_set_error("dlopen(libnccl)", dlerror()); return ADMPC_E_NCCL; }
+#define LOAD(name)                                                                                 \
+    *(void **)(&g_nccl.name) = dlsym(l, "nccl" #name);                                             \
+    if (!g_nccl.name) { admpc_set_error("dlsym", "nccl" #name); return ADMPC_E_NCCL; }
+    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Broadcast) LOAD(AllReduce) LOAD(Send) LOAD(Recv)
+    LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
+#undef LOAD
+    g_nccl.lib = l;
+    return 0;
+}
+#define NCCL_CHECK_RET(call)                                                                              \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0) { admpc_set_error(#call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); return ADMPC_E_NCCL; } \
+    } while (0)
+enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+// ---------------------------------------------------------------------------------------------- batch handle ----
+struct admpc_batch {
+    Params P;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    double *pool = nullptr;      // one allocation for every double array
+    int *ipool = nullptr;
+    double *stage_in = nullptr, *stage_u = nullptr, *stage_x = nullptr, *stage_misc = nullptr;
+    int *stage_status = nullptr;
+    double *gp_blob = nullptr;
+    size_t gp_blob_cap = 0;
+    double *l2_scratch = nullptr;
+    size_t l2_bytes = 0;
+    cudaEvent_t ev[8];
+    cudaEvent_t tm0, tm1;
+    bool profiling = false;
+    bool gps_set = false;
+    long long launches = 0;
+    float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
+    nccl_comm comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+static size_t rup(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, admpc_batch **out)
+{
+    if (!opts || !out || B <= 0 || opts->N < 2 || opts->N > ADMPC_NMAX) { admpc_set_error("admpc_batch_create", "bad argument"); return ADMPC_E_ARG; }
+    int ndev = 0;
+    CUDA_CHECK_RET(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { admpc_set_error("admpc_batch_create", "no such CUDA device"); return ADMPC_E_CUDA; }
+    CUDA_CHECK_RET(cudaSetDevice(device));
+    admpc_batch *h = new admpc_batch();
+    h->device = device;
+    Params &P = h->P;
+    memset(&P, 0, sizeof P);
+    P.o = *opts;
+    P.o.gp_enabled = 0;
+    const int N = opts->N;
+    P.B = B;
+    P.Bp = (int)rup((size_t)B, 32);
+    const size_t Bp = P.Bp;
+    CUDA_CHECK_RET(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev) CUDA_CHECK_RET(cudaEventCreate(&e));
+    CUDA_CHECK_RET(cudaEventCreate(&h->tm0));
+    CUDA_CHECK_RET(cudaEventCreate(&h->tm1));
+
+    // carve the pool
+    struct Item { double **p; size_t rows; };
+    const size_t nX = (size_t)(N + 1) * 7, nU = (size_t)N * 2, nPi = (size_t)N * 7, nC = (size_t)N * NC;
+    double *x0, *yref, *pp, *gps;
+    std::vector<Item> items = {
+        {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
+        {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
+        {&P.lin, (size_t)(N + 1) * LIN_ROWS},
+        {&P.dx, nX}, {&P.du, nU}, {&P.pi, nPi}, {&P.lam, nC}, {&P.t, nC}, {&P.sl, nU}, {&P.su, nU},
+        {&P.rgu, nU}, {&P.rgx, nX}, {&P.rgsl, nU}, {&P.rgsu, nU}, {&P.rb, nPi}, {&P.rd, nC}, {&P.rm, nC},
+        {&P.K, (size_t)N * 14}, {&P.Ginv, (size_t)N * 3}, {&P.P, (size_t)(N + 1) * 28}, {&P.Pb, nPi}, {&P.kf, nU}, {&P.pv, nX},
+        {&P.ddu, nU}, {&P.ddx, nX}, {&P.dpi, nPi}, {&P.dlam, nC}, {&P.dt, nC}, {&P.dsl, nU}, {&P.dsu, nU},
+        {&P.res_out, 4},
+    };
+    size_t rows = 0;
+    for (auto &it : items) rows += it.rows;
+    CUDA_CHECK_RET(cudaMalloc(&h->pool, rows * Bp * sizeof(double)));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->pool, 0, rows * Bp * sizeof(double), h->stream));
+    size_t off = 0;
+    for (auto &it : items) { *it.p = h->pool + off * Bp; off += it.rows; }
+    P.x0 = x0; P.yref = yref; P.p = pp; P.gps = gps;
+    CUDA_CHECK_RET(cudaMalloc(&h->ipool, 4 * Bp * sizeof(int)));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->ipool, 0, 4 * Bp * sizeof(int), h->stream));
+    P.status = h->ipool; P.qp_status = h->ipool + Bp; P.qp_iter = h->ipool + 2 * Bp; P.lin_bad = h->ipool + 3 * Bp;
+    // instance-major staging areas
+    const size_t in_rows = (size_t)N * 49 > (size_t)N * 9 + 7 ? (size_t)N * 49 : (size_t)N * 9 + 7;
+    CUDA_CHECK_RET(cudaMalloc(&h->stage_in, in_rows * Bp * sizeof(double)));
+    CUDA_CHECK_RET(cudaMalloc(&h->stage_u, nU * Bp * sizeof(double)));
+    CUDA_CHECK_RET(cudaMalloc(&h->stage_x, nX * Bp * sizeof(double)));
+    CUDA_CHECK_RET(cudaMalloc(&h->stage_misc, (size_t)N * 49 * Bp * sizeof(double)));
+    CUDA_CHECK_RET(cudaMalloc(&h->stage_status, 3 * Bp * sizeof(int)));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+extern "C" int admpc_batch_free(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
+    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch);
+    for (auto &e : h->ev) cudaEventDestroy(e);
+    cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int admpc_batch_size(const admpc_batch *h) { return h ? h->P.B : ADMPC_E_ARG; }
+extern "C" int admpc_batch_horizon(const admpc_batch *h) { return h ? h->P.o.N : ADMPC_E_ARG; }
+extern "C" long long admpc_batch_kernel_launches(const admpc_batch *h) { return h ? h->launches : 0; }
+
+// packs the GP model into the TMA-friendly blob (see GpDev) and uploads it
+static int upload_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, const int *rows, const double *X,
+                     const double *alpha, const double *ell, const double *sigma_f, const double *y_mean, int trig)
+{
+    Params &P = h->P;
+    if (nout == 0) { P.o.gp_enabled = 0; return 0; }
+    if (nout < 0 || nout > ADMPC_GPOUT_MAX || M <= 0 || dz <= 0 || dz > ADMPC_DZMAX || !feat || !rows || !X || !alpha || !ell || !sigma_f || !y_mean) {
+        admpc_set_error("admpc_batch_set_gp", "bad argument");
+        return ADMPC_E_ARG;
+    }
+    for (int d = 0; d < dz; d++)
+        if (feat[d] < 2 || feat[d] > 8) { admpc_set_error("admpc_batch_set_gp", "GP features must be in [psi..delta,u0,u1] (indices 2..8)"); return ADMPC_E_UNSUPPORTED; }
+    for (int j = 0; j < nout; j++)
+        if (rows[j] < 3 || rows[j] > 5) { admpc_set_error("admpc_batch_set_gp", "GP outputs must map to state rows 3..5"); return ADMPC_E_UNSUPPORTED; }
+    const size_t stride = rup((size_t)M * (dz + 1) + dz + 1, 2);
+    const size_t bytes = stride * nout * sizeof(double);
+    if (bytes > 220 * 1024) { admpc_set_error("admpc_batch_set_gp", "GP model exceeds the shared-memory staging budget (220 KB)"); return ADMPC_E_UNSUPPORTED; }
+    std::vector<double> blob(stride * nout, 0.0);
+    for (int j = 0; j < nout; j++) {
+        double *b = blob.data() + stride * j;
+        for (int i = 0; i < M; i++) {
+            for (int d = 0; d < dz; d++) b[(size_t)i * (dz + 1) + d] = X[((size_t)j * M + i) * dz + d];
+            b[(size_t)i * (dz + 1) + dz] = sigma_f[j] * alpha[(size_t)j * M + i];
+        }
+        double *w = b + (size_t)M * (dz + 1);
+        for (int d = 0; d < dz; d++) w[d] = 1.0 / (ell[j * dz + d] * ell[j * dz + d]);
+        w[dz] = y_mean[j];
+    }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    if (bytes > h->gp_blob_cap) {
+        cudaFree(h->gp_blob);
+        CUDA_CHECK_RET(cudaMalloc(&h->gp_blob, bytes));
+        h->gp_blob_cap = bytes;
+    }
+    CUDA_CHECK_RET(cudaMemcpyAsync(h->gp_blob, blob.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    P.gp.blob = h->gp_blob;
+    P.gp.bytes = (int)bytes;
+    P.gp.stride_out = (int)stride;
+    P.o.gp_enabled = 1;
+    P.o.gp_nout = nout; P.o.gp_M = M; P.o.gp_dz = dz; P.o.gp_stage0_trigger = trig;
+    for (int d = 0; d < dz; d++) P.o.gp_feat[d] = feat[d];
+    for (int j = 0; j < nout; j++) P.o.gp_row[j] = rows[j];
+    return 0;
+}
+
+extern "C" int admpc_batch_set_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, const int *rows,
+                                  const double *X, const double *alpha, const double *ell, const double *sigma_f,
+                                  const double *y_mean, int stage0_trigger)
+{
+    if (!h) return ADMPC_E_ARG;
+    return upload_gp(h, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, stage0_trigger);
+}
+
+// host instance-major [B][F] -> device SoA rows
+static int put_rows(admpc_batch *h, const double *host, double *dst, int F)
+{
+    if (!h || !host) { admpc_set_error("admpc set", "null pointer"); return ADMPC_E_ARG; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaMemcpyAsync(h->stage_in, host, (size_t)h->P.B * F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_transpose_in(h->stage_in, dst, h->P.B, h->P.Bp, F, h->stream);
+    h->launches++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int admpc_batch_set_x0(admpc_batch *h, const double *x0)
+{
+    int r = put_rows(h, x0, (double *)h->P.x0, 7);
+    if (r == 0 && !h->gps_set) {   // gp_state defaults to the initial state (quad_3d_optimizer.py:549)
+        CUDA_CHECK_RET(cudaMemcpyAsync((void *)h->P.gps, h->P.x0, (size_t)7 * h->P.Bp * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return r;
+}
+extern "C" int admpc_batch_set_yref(admpc_batch *h, const double *yref) { return put_rows(h, yref, (double *)h->P.yref, h->P.o.N * 9 + 7); }
+extern "C" int admpc_batch_set_p(admpc_batch *h, const double *p) { return put_rows(h, p, (double *)h->P.p, h->P.o.N); }
+extern "C" int admpc_batch_set_p_scalar(admpc_batch *h, const double *p)
+{
+    if (!h || !p) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->stage_in, 0, (size_t)h->P.Bp * sizeof(double), h->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(h->stage_in, p, (size_t)h->P.B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_bcast_rows(h->stage_in, (double *)h->P.p, h->P.Bp, h->P.o.N, h->stream);
+    h->launches++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+extern "C" int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state)
+{
+    if (!h) return ADMPC_E_ARG;
+    if (!gp_state) { h->gps_set = false; return 0; }
+    h->gps_set = true;
+    return put_rows(h, gp_state, (double *)h->P.gps, 7);
+}
+extern "C" int admpc_batch_set_iterate(admpc_batch *h, const double *x, const double *u)
+{
+    int r = 0;
+    if (x) r = put_rows(h, x, h->P.xb, (h->P.o.N + 1) * 7);
+    if (r == 0 && u) r = put_rows(h, u, h->P.ub, h->P.o.N * 2);
+    return r;
+}
+extern "C" int admpc_batch_reset(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const Params &P = h->P;
+    // iterate arrays are contiguous in the pool: xb .. sub
+    const size_t n = (size_t)((P.sub + (size_t)P.o.N * 2 * P.Bp) - P.xb);
+    CUDA_CHECK_RET(cudaMemsetAsync(P.xb, 0, n * sizeof(double), h->stream));
+    return 0;
+}
+
+extern "C" int admpc_batch_solve(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const Params &P = h->P;
+    CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
+    CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
+    if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
+    launch_prepare(P, h->stream);
+    if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
+    launch_qp(P, h->stream);
+    if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
+    launch_update(P, h->stream);
+    CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
+    h->launches += 3;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int admpc_batch_wait(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int get_rows_async(admpc_batch *h, const double *src, double *stage, double *host, int F)
+{
+    launch_transpose_out(src, stage, h->P.B, h->P.Bp, F, h->stream);
+    h->launches++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    CUDA_CHECK_RET(cudaMemcpyAsync(host, stage, (size_t)h->P.B * F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+static int get_rows(admpc_batch *h, const double *src, double *host, int F)
+{
+    if (!h || !host) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    int r = get_rows_async(h, src, h->stage_misc, host, F);
+    if (r) return r;
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int admpc_batch_get_u(admpc_batch *h, double *u) { return get_rows(h, h->P.ub, u, h->P.o.N * 2); }
+extern "C" int admpc_batch_get_x(admpc_batch *h, double *x) { return get_rows(h, h->P.xb, x, (h->P.o.N + 1) * 7); }
+extern "C" int admpc_batch_get_pi(admpc_batch *h, double *pi) { return get_rows(h, h->P.pib, pi, h->P.o.N * 7); }
+extern "C" int admpc_batch_get_lam(admpc_batch *h, double *lam) { return get_rows(h, h->P.lamb, lam, h->P.o.N * NC); }
+extern "C" int admpc_batch_get_t(admpc_batch *h, double *t) { return get_rows(h, h->P.tb, t, h->P.o.N * NC); }
+extern "C" int admpc_batch_get_slacks(admpc_batch *h, double *sl, double *su)
+{
+    int r = 0;
+    if (sl) r = get_rows(h, h->P.slb, sl, h->P.o.N * 2);
+    if (r == 0 && su) r = get_rows(h, h->P.sub, su, h->P.o.N * 2);
+    return r;
+}
+extern "C" int admpc_batch_get_status(admpc_batch *h, int *status, int *qp_status, int *qp_iter)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->P.B * sizeof(int);
+    if (status) CUDA_CHECK_RET(cudaMemcpyAsync(status, h->P.status, n, cudaMemcpyDeviceToHost, h->stream));
+    if (qp_status) CUDA_CHECK_RET(cudaMemcpyAsync(qp_status, h->P.qp_status, n, cudaMemcpyDeviceToHost, h->stream));
+    if (qp_iter) CUDA_CHECK_RET(cudaMemcpyAsync(qp_iter, h->P.qp_iter, n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// expands the structured linearisation to dense row-major A[7x7], B[7x2] per stage (parity tests)
+__global__ void expand_lin_kernel(const Params P, double *A, double *Bm, double *b, double *q, double *r)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    const int N = P.o.N, Bp = P.Bp;
+    if (i >= P.B) return;
+    const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp + i;
+    if (k < N) {
+        double *Ao = A + ((size_t)i * N + k) * 49, *Bo = Bm + ((size_t)i * N + k) * 14;
+        for (int rr = 0; rr < 7; rr++)
+            for (int c = 0; c < 7; c++) {
+                double v;
+                if (c < 2) v = (rr == c) ? 1.0 : 0.0;
+                else if (rr == 6) v = (c == 6) ? 1.0 : 0.0;
+                else v = lin[(size_t)(LIN_A + rr * 5 + (c - 2)) * Bp];
+                Ao[rr * 7 + c] = v;
+            }
+        for (int rr = 0; rr < 7; rr++)
+            for (int c = 0; c < 2; c++) Bo[rr * 2 + c] = (rr == 6) ? ((c == 1) ? P.o.dt : 0.0) : lin[(size_t)(LIN_B + rr * 2 + c) * Bp];
+        for (int c = 0; c < 7; c++) b[((size_t)i * N + k) * 7 + c] = lin[(size_t)(LIN_b + c) * Bp];
+        for (int c = 0; c < 2; c++) r[((size_t)i * N + k) * 2 + c] = lin[(size_t)(LIN_r + c) * Bp];
+    }
+    for (int c = 0; c < 7; c++) q[((size_t)i * (N + 1) + k) * 7 + c] = lin[(size_t)(LIN_q + c) * Bp];
+}
+
+extern "C" int admpc_batch_get_lin(admpc_batch *h, double *A, double *Bm, double *b, double *q, double *r)
+{
+    if (!h || !A || !Bm || !b || !q || !r) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const int N = h->P.o.N, B = h->P.B;
+    const size_t nA = (size_t)B * N * 49, nB = (size_t)B * N * 14, nb = (size_t)B * N * 7, nq = (size_t)B * (N + 1) * 7, nr = (size_t)B * N * 2;
+    double *d = nullptr;
+    CUDA_CHECK_RET(cudaMalloc(&d, (nA + nB + nb + nq + nr) * sizeof(double)));
+    dim3 grid((B + 127) / 128, N + 1);
+    expand_lin_kernel<<<grid, 128, 0, h->stream>>>(h->P, d, d + nA, d + nA + nB, d + nA + nB + nb, d + nA + nB + nb + nq);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(A, d, nA * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Bm, d + nA, nB * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b, d + nA + nB, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q, d + nA + nB + nb, nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r, d + nA + nB + nb + nq, nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { admpc_set_error("admpc_batch_get_lin", cudaGetErrorString(e)); return ADMPC_E_CUDA; }
+    return 0;
+}
+
+extern "C" int admpc_batch_solve_host(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
+                                      double *u_out, double *x_out, int *status_out)
+{
+    if (!h) return ADMPC_E_ARG;
+    int r = 0;
+    if (x0 && (r = admpc_batch_set_x0(h, x0))) return r;
+    if (yref && (r = admpc_batch_set_yref(h, yref))) return r;
+    if (p_scalar && (r = admpc_batch_set_p_scalar(h, p_scalar))) return r;
+    if ((r = admpc_batch_solve(h))) return r;
+    if (u_out && (r = get_rows_async(h, h->P.ub, h->stage_u, u_out, h->P.o.N * 2))) return r;
+    if (x_out && (r = get_rows_async(h, h->P.xb, h->stage_x, x_out, (h->P.o.N + 1) * 7))) return r;
+    if (status_out) CUDA_CHECK_RET(cudaMemcpyAsync(status_out, h->P.status, (size_t)h->P.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int admpc_batch_set_profiling(admpc_batch *h, int on) { if (!h) return ADMPC_E_ARG; h->profiling = on != 0; return 0; }
+
+extern "C" int admpc_batch_last_ms(admpc_batch *h, const char *name, float *ms)
+{
+    if (!h || !name || !ms) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaEventSynchronize(h->ev[4]));
+    if (!strcmp(name, "solve")) { CUDA_CHECK_RET(cudaEventElapsedTime(ms, h->ev[0], h->ev[4])); return 0; }
+    if (!h->profiling) { admpc_set_error("admpc_batch_last_ms", "profiling is off"); return ADMPC_E_STATE; }
+    if (!strcmp(name, "prepare")) { CUDA_CHECK_RET(cudaEventElapsedTime(ms, h->ev[1], h->ev[2])); return 0; }
+    if (!strcmp(name, "qp")) { CUDA_CHECK_RET(cudaEventElapsedTime(ms, h->ev[2], h->ev[3])); return 0; }
+    if (!strcmp(name, "update")) { CUDA_CHECK_RET(cudaEventElapsedTime(ms, h->ev[3], h->ev[4])); return 0; }
+    admpc_set_error("admpc_batch_last_ms", "unknown timer");
+    return ADMPC_E_ARG;
+}
+
+extern "C" int admpc_batch_timer_start(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    CUDA_CHECK_RET(cudaEventRecord(h->tm0, h->stream));
+    return 0;
+}
+extern "C" int admpc_batch_timer_stop(admpc_batch *h, float *ms)
+{
+    if (!h || !ms) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaEventRecord(h->tm1, h->stream));
+    CUDA_CHECK_RET(cudaEventSynchronize(h->tm1));
+    CUDA_CHECK_RET(cudaEventElapsedTime(ms, h->tm0, h->tm1));
+    return 0;
+}
+extern "C" int admpc_batch_flush_l2(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    if (!h->l2_scratch) {
+        h->l2_bytes = (size_t)256 << 20;   // 256 MiB > 126 MB L2
+        CUDA_CHECK_RET(cudaMalloc(&h->l2_scratch, h->l2_bytes));
+    }
+    launch_fill(h->l2_scratch, h->l2_bytes / sizeof(double), 0.0, h->stream);
+    h->launches++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+
+extern "C" void *admpc_host_alloc(unsigned long long bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { admpc_set_error("cudaHostAlloc", "failed"); cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" int admpc_host_free(void *p) { CUDA_CHECK_RET(cudaFreeHost(p)); return 0; }
+
+extern "C" int admpc_measure_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return ADMPC_E_ARG;
+    const double v = run_fp64_peak(device);
+    if (v <= 0) { admpc_set_error("admpc_measure_fp64_peak", "CUDA failure"); return ADMPC_E_CUDA; }
+    *tflops = v;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- multi-GPU -------
+extern "C" int admpc_nccl_unique_id(void *id128)
+{
+    int r = nccl_load();
+    if (r) return r;
+    NCCL_CHECK_RET(g_nccl.GetUniqueId((nccl_uid *)id128));
+    return 0;
+}
+extern "C" int admpc_batch_comm_init(admpc_batch *h, const void *id128, int rank, int nranks)
+{
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return ADMPC_E_ARG;
+    int r = nccl_load();
+    if (r) return r;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    nccl_uid id;
+    memcpy(&id, id128, sizeof id);
+    NCCL_CHECK_RET(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank; h->nranks = nranks;
+    return 0;
+}
+extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, const int *feat, const int *rows,
+                                    const double *X, const double *alpha, const double *ell, const double *sigma_f,
+                                    const double *y_mean, int stage0_trigger)
+{
+    if (!h || !h->comm) { admpc_set_error("admpc_batch_bcast_gp", "communicator not initialised"); return ADMPC_E_STATE; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    // header (sizes, feature map) first, then the packed blob, both over NCCL on the handle's stream
+    int hdr[4 + ADMPC_DZMAX + ADMPC_GPOUT_MAX] = {0};
+    if (h->rank == root) {
+        int r = upload_gp(h, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, stage0_trigger);
+        if (r) return r;
+        hdr[0] = nout; hdr[1] = M; hdr[2] = dz; hdr[3] = stage0_trigger;
+        for (int d = 0; d < dz; d++) hdr[4 + d] = feat[d];
+        for (int j = 0; j < nout; j++) hdr[4 + ADMPC_DZMAX + j] = rows[j];
+    }
+    int *dh = h->stage_status;
+    CUDA_CHECK_RET(cudaMemcpyAsync(dh, hdr, sizeof hdr, cudaMemcpyHostToDevice, h->stream));
+    NCCL_CHECK_RET(g_nccl.Broadcast(dh, dh, sizeof hdr / sizeof(int), NCCL_INT32, root, h->comm, h->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(hdr, dh, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    Params &P = h->P;
+    if (h->rank != root) {
+        nout = hdr[0]; M = hdr[1]; dz = hdr[2];
+        const size_t stride = rup((size_t)M * (dz + 1) + dz + 1, 2);
+        const size_t bytes = stride * nout * sizeof(double);
+        if (bytes > h->gp_blob_cap) {
+            cudaFree(h->gp_blob);
+            CUDA_CHECK_RET(cudaMalloc(&h->gp_blob, bytes));
+            h->gp_blob_cap = bytes;
+        }
+        P.gp.blob = h->gp_blob; P.gp.bytes = (int)bytes; P.gp.stride_out = (int)stride;
+        P.o.gp_enabled = nout > 0; P.o.gp_nout = nout; P.o.gp_M = M; P.o.gp_dz = dz; P.o.gp_stage0_trigger = hdr[3];
+        for (int d = 0; d < dz; d++) P.o.gp_feat[d] = hdr[4 + d];
+        for (int j = 0; j < nout; j++) P.o.gp_row[j] = hdr[4 + ADMPC_DZMAX + j];
+    }
+    if (P.gp.bytes > 0)
+        NCCL_CHECK_RET(g_nccl.Broadcast(h->gp_blob, h->gp_blob, (size_t)P.gp.bytes / sizeof(double), NCCL_FLOAT64, root, h->comm, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, double *x_all, int *status_all)
+{
+    if (!h || !h->comm) { admpc_set_error("admpc_batch_gather", "communicator not initialised"); return ADMPC_E_STATE; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const Params &P = h->P;
+    const int N = P.o.N, B = P.B;
+    const size_t nu = (size_t)B * N * 2, nx = (size_t)B * (N + 1) * 7;
+    // instance-major blocks on every rank
+    launch_transpose_out(P.ub, h->stage_u, B, P.Bp, N * 2, h->stream);
+    launch_transpose_out(P.xb, h->stage_x, B, P.Bp, (N + 1) * 7, h->stream);
+    h->launches += 2;
+    CUDA_CHECK_RET(cudaGetLastError());
+    static double *gu = nullptr, *gx = nullptr;
+    static int *gs = nullptr;
+    static size_t cap = 0;
+    if (h->rank == root && cap < (size_t)h->nranks * (nu + nx)) {
+        cudaFree(gu); cudaFree(gx); cudaFree(gs);
+        CUDA_CHECK_RET(cudaMalloc(&gu, (size_t)h->nranks * nu * sizeof(double)));
+        CUDA_CHECK_RET(cudaMalloc(&gx, (size_t)h->nranks * nx * sizeof(double)));
+        CUDA_CHECK_RET(cudaMalloc(&gs, (size_t)h->nranks * B * sizeof(int)));
+        cap = (size_t)h->nranks * (nu + nx);
+    }
+    NCCL_CHECK_RET(g_nccl.GroupStart());
+    NCCL_CHECK_RET(g_nccl.Send(h->stage_u, nu, NCCL_FLOAT64, root, h->comm, h->stream));
+    NCCL_CHECK_RET(g_nccl.Send(h->stage_x, nx, NCCL_FLOAT64, root, h->comm, h->stream));
+    NCCL_CHECK_RET(g_nccl.Send(P.status, (size_t)B, NCCL_INT32, root, h->comm, h->stream));
+    if (h->rank == root) {
+        for (int r = 0; r < h->nranks; r++) {
+            NCCL_CHECK_RET(g_nccl.Recv(gu + (size_t)r * nu, nu, NCCL_FLOAT64, r, h->comm, h->stream));
+            NCCL_CHECK_RET(g_nccl.Recv(gx + (size_t)r * nx, nx, NCCL_FLOAT64, r, h->comm, h->stream));
+            NCCL_CHECK_RET(g_nccl.Recv(gs + (size_t)r * B, (size_t)B, NCCL_INT32, r, h->comm, h->stream));
+        }
+    }
+    NCCL_CHECK_RET(g_nccl.GroupEnd());
+    if (h->rank == root) {
+        if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all, gu, (size_t)h->nranks * nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all, gx, (size_t)h->nranks * nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all, gs, (size_t)h->nranks * B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int admpc_batch_barrier(admpc_batch *h)
+{
+    if (!h || !h->comm) return ADMPC_E_STATE;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    int *d = h->stage_status;
+    NCCL_CHECK_RET(g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_SUM, h->comm, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- acados shim -----
+struct sim_car_solver_capsule {
+    admpc_opts opts;
+    bool opts_set = false;
+    admpc_batch *h = nullptr;
+    int N = 0;
+    std::vector<double> x0, yref, p, x, u, pi, lam, t, sl, su;
+    bool iterate_dirty = false;
+    int status = 0, qp_status = 0, qp_iter = 0;
+    double time_tot = 0.0;
+    double res[4] = {0, 0, 0, 0};
+};
+
+extern "C" sim_car_solver_capsule *sim_car_acados_create_capsule(void)
+{
+    sim_car_solver_capsule *c = new sim_car_solver_capsule();
+    admpc_default_opts(&c->opts);
+    c->opts.N = 40;     // SIM_CAR_N, acados_solver_sim_car.h:66
+    return c;
+}
+extern "C" int sim_car_acados_free_capsule(sim_car_solver_capsule *c) { delete c; return 0; }
+extern "C" int sim_car_acados_set_opts(sim_car_solver_capsule *c, const admpc_opts *o)
+{
+    if (!c || !o) return ADMPC_E_ARG;
+    if (c->h) { admpc_set_error("sim_car_acados_set_opts", "solver already created"); return ADMPC_E_STATE; }
+    c->opts = *o;
+    c->opts_set = true;
+    return 0;
+}
+extern "C" int sim_car_acados_create_with_discretization(sim_car_solver_capsule *c, int N, double *ts)
+{
+    if (!c) return ADMPC_E_ARG;
+    if (c->h) { admpc_set_error("sim_car_acados_create", "already created"); return ADMPC_E_STATE; }
+    admpc_opts o = c->opts;
+    o.N = N;
+    if (ts) {
+        for (int k = 1; k < N; k++)
+            if (fabs(ts[k] - ts[0]) > 1e-12 * fabs(ts[0])) { admpc_set_error("create_with_discretization", "non-uniform time steps are not supported"); return ADMPC_E_UNSUPPORTED; }
+        o.dt = ts[0];
+    }
+    int r = admpc_batch_create(&o, 1, 0, &c->h);
+    if (r) return r;
+    c->opts = o;
+    c->N = N;
+    c->x0.assign(7, 0.0); c->yref.assign((size_t)N * 9 + 7, 0.0); c->p.assign(N, 0.0);
+    c->x.assign((size_t)(N + 1) * 7, 0.0); c->u.assign((size_t)N * 2, 0.0); c->pi.assign((size_t)N * 7, 0.0);
+    c->lam.assign((size_t)N * NC, 0.0); c->t.assign((size_t)N * NC, 0.0); c->sl.assign((size_t)N * 2, 0.0); c->su.assign((size_t)N * 2, 0.0);
+    return 0;
+}
+extern "C" int sim_car_acados_create(sim_car_solver_capsule *c) { return c ? sim_car_acados_create_with_discretization(c, c->opts.N, nullptr) : ADMPC_E_ARG; }
+extern "C" int sim_car_acados_update_time_steps(sim_car_solver_capsule *c, int N, double *ts)
+{
+    if (!c || !c->h || !ts) return ADMPC_E_ARG;
+    if (N != c->N) { admpc_set_error("update_time_steps", "N must equal the created horizon"); return ADMPC_E_ARG; }   // .h:131-133
+    for (int k = 1; k < N; k++)
+        if (fabs(ts[k] - ts[0]) > 1e-12 * fabs(ts[0])) return ADMPC_E_UNSUPPORTED;
+    c->h->P.o.dt = ts[0];
+    c->opts.dt = ts[0];
+    return 0;
+}
+extern "C" int sim_car_acados_update_params(sim_car_solver_capsule *c, int stage, double *value, int np)
+{
+    if (!c || !c->h || !value) return ADMPC_E_ARG;
+    if (np != ADMPC_NP) { admpc_set_error("sim_car_acados_update_params", "wrong number of parameters (expected 1)"); return ADMPC_E_ARG; }  // .c:862-866
+    if (stage < 0 || stage > c->N) return ADMPC_E_ARG;
+    if (stage < c->N) c->p[stage] = value[0];     // the parameter of the terminal node does not enter the problem
+    return 0;
+}
+extern "C" int sim_car_acados_reset(sim_car_solver_capsule *c, int)
+{
+    if (!c || !c->h) return ADMPC_E_STATE;
+    std::fill(c->x.begin(), c->x.end(), 0.0); std::fill(c->u.begin(), c->u.end(), 0.0);
+    std::fill(c->pi.begin(), c->pi.end(), 0.0); std::fill(c->lam.begin(), c->lam.end(), 0.0);
+    std::fill(c->t.begin(), c->t.end(), 0.0); std::fill(c->sl.begin(), c->sl.end(), 0.0); std::fill(c->su.begin(), c->su.end(), 0.0);
+    c->iterate_dirty = false;
+    return admpc_batch_reset(c->h);
+}
+extern "C" int sim_car_acados_free(sim_car_solver_capsule *c)
+{
+    if (!c) return ADMPC_E_ARG;
+    int r = c->h ? admpc_batch_free(c->h) : 0;
+    c->h = nullptr;
+    return r;
+}
+
+extern "C" int sim_car_acados_set(sim_car_solver_capsule *c, int stage, const char *field, const double *v, int n)
+{
+    if (!c || !c->h || !field || !v) return ADMPC_E_ARG;
+    const int N = c->N;
+    if (stage < 0 || stage > N) { admpc_set_error("sim_car_acados_set", "stage out of range"); return ADMPC_E_ARG; }
+    if (!strcmp(field, "yref")) {
+        const int need = stage < N ? 9 : 7;
+        if (n != need) { admpc_set_error("sim_car_acados_set", "yref has wrong length"); return ADMPC_E_ARG; }
+        memcpy(&c->yref[(size_t)stage * 9], v, sizeof(double) * need);
+        return 0;
+    }
+    if (!strcmp(field, "lbx") || !strcmp(field, "ubx")) {
+        if (stage == 0 && n == 7) { memcpy(c->x0.data(), v, sizeof(double) * 7); return 0; }   // x0 via lbx=ubx (ad_3d_optimizer.py:441-442)
+        admpc_set_error("sim_car_acados_set", "only the stage-0 state bound (x0, 7 values) can be changed per solve");
+        return ADMPC_E_UNSUPPORTED;
+    }
+    if (!strcmp(field, "p")) { return sim_car_acados_update_params(c, stage, (double *)v, n); }
+    if (!strcmp(field, "x")) {
+        if (n != 7) return ADMPC_E_ARG;
+        memcpy(&c->x[(size_t)stage * 7], v, sizeof(double) * 7); c->iterate_dirty = true; return 0;
+    }
+    if (!strcmp(field, "u")) {
+        if (n != 2 || stage >= N) return ADMPC_E_ARG;
+        memcpy(&c->u[(size_t)stage * 2], v, sizeof(double) * 2); c->iterate_dirty = true; return 0;
+    }
+    admpc_set_error("sim_car_acados_set", "unknown field");
+    return ADMPC_E_ARG;
+}
+
+extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
+{
+    if (!c || !c->h) { admpc_set_error("sim_car_acados_solve", "solver not created"); return ADMPC_E_STATE; }
+    admpc_batch *h = c->h;
+    int r;
+    if ((r = admpc_batch_timer_start(h))) return r;
+    if ((r = admpc_batch_set_x0(h, c->x0.data()))) return r;
+    if ((r = admpc_batch_set_yref(h, c->yref.data()))) return r;
+    if ((r = admpc_batch_set_p(h, c->p.data()))) return r;
+    if (c->iterate_dirty) { if ((r = admpc_batch_set_iterate(h, c->x.data(), c->u.data()))) return r; c->iterate_dirty = false; }
+    if ((r = admpc_batch_solve(h))) return r;
+    float ms = 0;
+    if ((r = admpc_batch_timer_stop(h, &ms))) return r;
+    c->time_tot = ms * 1e-3;
+    if ((r = admpc_batch_get_x(h, c->x.data()))) return r;
+    if ((r = admpc_batch_get_u(h, c->u.data()))) return r;
+    if ((r = admpc_batch_get_pi(h, c->pi.data()))) return r;
+    if ((r = admpc_batch_get_lam(h, c->lam.data()))) return r;
+    if ((r = admpc_batch_get_t(h, c->t.data()))) return r;
+    if ((r = admpc_batch_get_slacks(h, c->sl.data(), c->su.data()))) return r;
+    if ((r = admpc_batch_get_status(h, &c->status, &c->qp_status, &c->qp_iter))) return r;
+    CUDA_CHECK_RET(cudaMemcpy2D(c->res, sizeof(double), h->P.res_out, (size_t)h->P.Bp * sizeof(double), sizeof(double), 4, cudaMemcpyDeviceToHost));
+    return c->status;
+}
+
+extern "C" int sim_car_acados_get(sim_car_solver_capsule *c, int stage, const char *field, double *out, int n)
+{
+    if (!c || !c->h || !field || !out) return ADMPC_E_ARG;
+    const int N = c->N;
+    if (stage < 0 || stage > N) return ADMPC_E_ARG;
+    if (!strcmp(field, "x")) { if (n != 7) return ADMPC_E_ARG; memcpy(out, &c->x[(size_t)stage * 7], 56); return 0; }
+    if (stage >= N) { admpc_set_error("sim_car_acados_get", "field has no entry at the terminal node"); return ADMPC_E_ARG; }
+    if (!strcmp(field, "u")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->u[(size_t)stage * 2], 16); return 0; }
+    if (!strcmp(field, "pi")) { if (n != 7) return ADMPC_E_ARG; memcpy(out, &c->pi[(size_t)stage * 7], 56); return 0; }
+    if (!strcmp(field, "sl")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->sl[(size_t)stage * 2], 16); return 0; }
+    if (!strcmp(field, "su")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->su[(size_t)stage * 2], 16); return 0; }
+    if (!strcmp(field, "lam") || !strcmp(field, "t")) {
+        const std::vector<double> &src = (field[0] == 'l') ? c->lam : c->t;
+        const double *s = &src[(size_t)stage * NC];
+        if (stage >= 1) { if (n != NC) return ADMPC_E_ARG; memcpy(out, s, sizeof(double) * NC); return 0; }
+        // stage 0 in acados layout: [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(2) | us(2)]  (sim_car_iterate.json lam_0)
+        if (n != 22) return ADMPC_E_ARG;
+        for (int j = 0; j < 22; j++) out[j] = 1e-16;
+        out[0] = s[0]; out[1] = s[1]; out[9] = s[3]; out[10] = s[4];
+        for (int j = 0; j < 4; j++) out[18 + j] = s[6 + j];
+        return 0;
+    }
+    admpc_set_error("sim_car_acados_get", "unknown field");
+    return ADMPC_E_ARG;
+}
+
+extern "C" int sim_car_acados_get_stat(sim_car_solver_capsule *c, const char *name, void *out)
+{
+    if (!c || !name || !out) return ADMPC_E_ARG;
+    if (!strcmp(name, "sqp_iter")) { *(int *)out = 1; return 0; }          // RTI: exactly one SQP iteration
+    if (!strcmp(name, "qp_iter")) { *(int *)out = c->qp_iter; return 0; }
+    if (!strcmp(name, "qp_stat")) { *(int *)out = c->qp_status; return 0; }
+    if (!strcmp(name, "status")) { *(int *)out = c->status; return 0; }
+    if (!strcmp(name, "time_tot")) { *(double *)out = c->time_tot; return 0; }
+    if (!strcmp(name, "kkt_norm_inf")) {
+        double m = 0;
+        for (double r : c->res) m = r > m ? r : m;
+        *(double *)out = m;
+        return 0;
+    }
+    admpc_set_error("sim_car_acados_get_stat", "unknown statistic");
+    return ADMPC_E_ARG;
+}
+
+extern "C" void sim_car_acados_print_stats(sim_car_solver_capsule *c)
+{
+    if (!c) return;
+    // same columns as acados_solver_sim_car.c:950-977
+    printf("\niter\tqp_stat\tqp_iter\n");
+    printf("%d\t%d\t%d\n", 1, c->qp_status, c->qp_iter);
+}

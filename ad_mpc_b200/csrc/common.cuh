@@ -1,0 +1,68 @@
+// common.cuh -- shared definitions of the B200 batched SQP-RTI solver (device layouts, parameter block).
+//
+// HBM layout: every per-instance quantity is stored structure-of-arrays, "row-major over instances":
+//     value(row, i) at base[row * Bp + i],   i = instance (fastest), Bp = batch padded to a multiple of 32.
+// A warp therefore always touches 32 consecutive doubles (256 B, two full 128-B lines) per row.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/admpc.h"
+
+#define NX 7
+#define NU 2
+#define NC 10
+
+// rows of one stage of the linearisation block (written by prepare, read by the QP kernel)
+//   A: rows 0..5 x cols 2..6 of A_k (cols 0,1 are e0,e1 and row 6 is e6 for this model: SURVEY Appendix B)
+//   B: rows 0..5 x 2 of B_k (row 6 is [0, dt])
+#define LIN_A 0
+#define LIN_B 30
+#define LIN_b 42
+#define LIN_q 49
+#define LIN_r 56
+#define LIN_ROWS 58
+
+struct GpDev {
+    // packed, 16-byte aligned GP block in HBM, staged to shared memory by one TMA bulk copy per CTA:
+    //   per output j: pts[M][dz+1] = {X_i0..X_i(dz-1), sigma_f*alpha_i}, then w[dz] = 1/ell^2, then y_mean (padded)
+    const double *blob;
+    int bytes;          // multiple of 16
+    int stride_out;     // doubles per output block
+};
+
+struct Params {
+    admpc_opts o;
+    GpDev gp;
+    int B, Bp;
+    // inputs
+    const double *x0, *yref, *p, *gps;
+    // iterate
+    double *xb, *ub, *pib, *lamb, *tb, *slb, *sub;
+    // linearisation
+    double *lin;
+    // QP solution (delta form) + workspace
+    double *dx, *du, *pi, *lam, *t, *sl, *su;
+    double *rgu, *rgx, *rgsl, *rgsu, *rb, *rd, *rm;
+    double *K, *Ginv, *P, *Pb, *kf, *pv;
+    double *ddu, *ddx, *dpi, *dlam, *dt, *dsl, *dsu;
+    int *status, *qp_status, *qp_iter, *lin_bad;
+    double *res_out;     // [4][Bp] final residual norms
+};
+
+#define CUDA_CHECK_RET(call)                                                         \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) { admpc_set_error(#call, cudaGetErrorString(e_)); return ADMPC_E_CUDA; } \
+    } while (0)
+
+void admpc_set_error(const char *what, const char *msg);
+
+// kernel launchers (defined in the .cu files)
+void launch_prepare(const Params &P, cudaStream_t s);
+void launch_qp(const Params &P, cudaStream_t s);
+void launch_transpose_in(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);   // [B][F] -> [F][Bp]
+void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);  // [F][Bp] -> [B][F]
+void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]
+void launch_update(const Params &P, cudaStream_t s);
+void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
+double run_fp64_peak(int device);

@@ -1,0 +1,336 @@
+// prepare.cu -- preparation phase of the SQP-RTI step: one thread per (instance, shooting interval).
+//
+// Replaces, for a whole batch, what acados does per stage on the CPU:
+//   * ERK4 (4 stages x 1 step) of the bicycle model WITH forward sensitivities -- the reference runs the CasADi
+//     generated sim_car_expl_vde_forw (c_generated_code/sim_car_model/sim_car_expl_vde_forw.c:120) 4x per interval;
+//     here the Jacobian is hand-derived and only its structurally non-zero entries are touched:
+//     columns p_x,p_y of J_x are zero and row delta is trivial, so S keeps [e0 e1 | 6x5 block] + 6x2 input block.
+//   * optional GP residual f + B_x mu(z) and its Jacobian (model_fitting/gp.py:117-165,446-460;
+//     quad_mpc/quad_3d_optimizer.py:295,315): training set staged into shared memory once per CTA with a TMA bulk
+//     copy (cp.async.bulk + mbarrier), every thread then sweeps the M points with broadcast LDS.
+//   * LINEAR_LS gradient and multiple-shooting residual (acados_solver_sim_car.c:378-485).
+// Output: lin[k][58][Bp] (A 6x5, B 6x2, b 7, q 7, r 2), SoA, coalesced.
+#include "common.cuh"
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct Jac {
+    // d f / d x : rows 0,1 x cols {psi,vx,vy}; row 2 = e_r; rows 3..5 x cols 2..6 ; row 6 = 0
+    double j0[3], j1[3];
+    double jr[3][5];
+    // d f / d u : rows 3..5 x 2 ; row 6 = [0 1]
+    double ju[3][2];
+};
+
+template <bool GP>
+__device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__restrict__ gpsm, int gp_stride,
+                                           const double x[7], const double u[2], double p, const double gpx[7],
+                                           double trig, double f[7], Jac &J)
+{
+    const double psi = x[2], vx = x[3], vy = x[4], r = x[5], dl = x[6];
+    const double u0 = u[0], u1 = u[1];
+    const double im = 1.0 / o.mass, iiz = 1.0 / o.iz, L = o.lr + o.lf, c = o.lr / L, iL = 1.0 / L, q = 1.0 - p;
+    double sp, cp, sd, cd;
+    sincos(psi, &sp, &cp);
+    sincos(dl, &sd, &cd);
+    const double D = vx + 1e-99;
+    const double iD = 1.0 / D;
+    const double a = (vy + o.lf * r) * iD;
+    const double Ff = o.cf2 * (dl - a);
+    const double Fr = o.cr2 * (o.lr * r - vy) * iD;
+    const double kin = u1 * vx + dl * u0;
+
+    f[0] = vx * cp - vy * sp;
+    f[1] = vx * sp + vy * cp;
+    f[2] = r;
+    f[3] = p * (u0 - im * Ff * sd + vy * r) + q * u0;
+    f[4] = p * (im * (Fr + Ff * cd) - vx * r) + q * (kin * c);
+    f[5] = p * (iiz * (o.lf * Ff * cd - o.lr * Fr)) + q * (kin * iL);
+    f[6] = u1;
+
+    J.j0[0] = -f[1]; J.j0[1] = cp; J.j0[2] = -sp;
+    J.j1[0] = f[0];  J.j1[1] = sp; J.j1[2] = cp;
+
+    const double Ff_vx = o.cf2 * a * iD, Ff_vy = -o.cf2 * iD, Ff_r = -o.cf2 * o.lf * iD, Ff_d = o.cf2;
+    const double Fr_vx = -Fr * iD, Fr_vy = -o.cr2 * iD, Fr_r = o.cr2 * o.lr * iD;
+    const double t1 = Ff_d * cd - Ff * sd;
+    // row 3 (v_x)
+    J.jr[0][0] = 0.0;
+    J.jr[0][1] = p * (-sd * Ff_vx * im);
+    J.jr[0][2] = p * (-sd * Ff_vy * im + r);
+    J.jr[0][3] = p * (-sd * Ff_r * im + vy);
+    J.jr[0][4] = -p * (Ff_d * sd + Ff * cd) * im;
+    J.ju[0][0] = 1.0; J.ju[0][1] = 0.0;
+    // row 4 (v_y)
+    J.jr[1][0] = 0.0;
+    J.jr[1][1] = p * ((Fr_vx + cd * Ff_vx) * im - r) + q * u1 * c;
+    J.jr[1][2] = p * (Fr_vy + cd * Ff_vy) * im;
+    J.jr[1][3] = p * ((Fr_r + cd * Ff_r) * im - vx);
+    J.jr[1][4] = p * t1 * im + q * u0 * c;
+    J.ju[1][0] = q * dl * c; J.ju[1][1] = q * vx * c;
+    // row 5 (yaw rate)
+    J.jr[2][0] = 0.0;
+    J.jr[2][1] = p * (o.lf * cd * Ff_vx - o.lr * Fr_vx) * iiz + q * u1 * iL;
+    J.jr[2][2] = p * (o.lf * cd * Ff_vy - o.lr * Fr_vy) * iiz;
+    J.jr[2][3] = p * (o.lf * cd * Ff_r - o.lr * Fr_r) * iiz;
+    J.jr[2][4] = p * o.lf * t1 * iiz + q * u0 * iL;
+    J.ju[2][0] = q * dl * iL; J.ju[2][1] = q * vx * iL;
+
+    if (GP) {
+        const int dz = o.gp_dz, M = o.gp_M;
+        double z[ADMPC_DZMAX];
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) {
+            if (d < dz) {
+                const int fi = o.gp_feat[d];
+                double v = 0.0;
+                // feature select without dynamic register indexing
+#pragma unroll
+                for (int s = 2; s < 7; s++) if (fi == s) v = gpx[s] * trig + x[s] * (1.0 - trig);
+                if (fi == 7) v = u0;
+                if (fi == 8) v = u1;
+                z[d] = v;
+            }
+        }
+        for (int j = 0; j < o.gp_nout; j++) {
+            const double *blk = gpsm + (size_t)j * gp_stride;
+            const double *w = blk + (size_t)M * (dz + 1);
+            double wv[ADMPC_DZMAX];
+#pragma unroll
+            for (int d = 0; d < ADMPC_DZMAX; d++) wv[d] = (d < dz) ? w[d] : 0.0;
+            double m = 0.0, g[ADMPC_DZMAX];
+#pragma unroll
+            for (int d = 0; d < ADMPC_DZMAX; d++) g[d] = 0.0;
+            if (dz == 4) {
+                // hot case: 4 features -> {X0..X3, a} = 40 B per point
+#pragma unroll 2
+                for (int i = 0; i < M; i++) {
+                    const double *pt = blk + (size_t)i * 5;
+                    const double d0 = z[0] - pt[0], d1 = z[1] - pt[1], d2 = z[2] - pt[2], d3 = z[3] - pt[3];
+                    const double e0 = d0 * wv[0], e1 = d1 * wv[1], e2 = d2 * wv[2], e3 = d3 * wv[3];
+                    const double s = fma(d3, e3, fma(d2, e2, fma(d1, e1, d0 * e0)));
+                    const double ka = exp(-0.5 * s) * pt[4];
+                    m += ka;
+                    g[0] = fma(-ka, e0, g[0]); g[1] = fma(-ka, e1, g[1]);
+                    g[2] = fma(-ka, e2, g[2]); g[3] = fma(-ka, e3, g[3]);
+                }
+            } else {
+                for (int i = 0; i < M; i++) {
+                    const double *pt = blk + (size_t)i * (dz + 1);
+                    double s = 0.0, e[ADMPC_DZMAX];
+#pragma unroll
+                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) { const double dd = z[d] - pt[d]; e[d] = dd * wv[d]; s = fma(dd, e[d], s); }
+                    const double ka = exp(-0.5 * s) * pt[dz];
+                    m += ka;
+#pragma unroll
+                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) g[d] = fma(-ka, e[d], g[d]);
+                }
+            }
+            m += w[dz];   // y_mean
+            const int row = o.gp_row[j] - 3;       // 0..2
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+                if (rr == row) {
+                    f[3 + rr] += m;
+#pragma unroll
+                    for (int d = 0; d < ADMPC_DZMAX; d++) {
+                        if (d < dz) {
+                            const int fi = o.gp_feat[d];
+#pragma unroll
+                            for (int s = 2; s < 7; s++) if (fi == s) J.jr[rr][s - 2] += (1.0 - trig) * g[d];
+                            if (fi == 7) J.ju[rr][0] += g[d];
+                            if (fi == 8) J.ju[rr][1] += g[d];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One RK4 step with forward sensitivities. Sensitivity state: rows 0..5 x 7 columns [x2..x6 | u0 u1];
+// row 6 (delta) is analytic: d delta / d delta = 1, d delta / d u1 = t.
+template <bool GP>
+__global__ void __launch_bounds__(128) prepare_kernel(const Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const double *gpsm = nullptr;
+    if (GP) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, (uint32_t)P.gp.bytes);
+            // TMA bulk copies, <= 64 KB each
+            uint32_t off = 0;
+            while (off < (uint32_t)P.gp.bytes) {
+                uint32_t n = min((uint32_t)P.gp.bytes - off, 65536u);
+                tma_bulk_g2s(smem_raw + off, (const unsigned char *)P.gp.blob + off, n, &bar);
+                off += n;
+            }
+        }
+        gpsm = reinterpret_cast<const double *>(smem_raw);
+    }
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    const double h = o.dt;
+    const bool active = (i < P.B);
+
+    double x[7], u[2], xn[7], yr[9];
+    double pk = 0.0;
+    if (active) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) x[c] = P.xb[(size_t)(k * 7 + c) * Bp + i];
+        if (k < N) {
+#pragma unroll
+            for (int c = 0; c < 7; c++) xn[c] = P.xb[(size_t)((k + 1) * 7 + c) * Bp + i];
+#pragma unroll
+            for (int c = 0; c < 2; c++) u[c] = P.ub[(size_t)(k * 2 + c) * Bp + i];
+#pragma unroll
+            for (int c = 0; c < 9; c++) yr[c] = P.yref[(size_t)(k * 9 + c) * Bp + i];
+            pk = P.p[(size_t)k * Bp + i];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 7; c++) yr[c] = P.yref[(size_t)(N * 9 + c) * Bp + i];
+        }
+    }
+    double *lin = P.lin + (size_t)k * LIN_ROWS * Bp + i;
+    if (k == N) {
+        // terminal cost gradient, scaling 1
+        if (active) {
+#pragma unroll
+            for (int c = 0; c < 7; c++) lin[(size_t)(LIN_q + c) * Bp] = o.We[c] * (x[c] - yr[c]);
+        }
+        if (GP) mbar_wait(&bar, 0);   // do not exit with the bulk copy in flight
+        return;
+    }
+    double gpx[7];
+    double trig = 0.0;
+    if (GP) {
+        trig = (o.gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; c++) gpx[c] = (active && k == 0 && o.gp_stage0_trigger) ? P.gps[(size_t)c * Bp + i] : 0.0;
+        mbar_wait(&bar, 0);
+    }
+    if (!active) return;
+
+    // K = current stage derivative of the sensitivity block, acc = weighted sum (rows 0..5 x 7 cols)
+    double K[6][7], acc[6][7];
+    double kx[7], ax[7];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 7; c++) { K[r][c] = 0.0; acc[r][c] = 0.0; }
+#pragma unroll
+    for (int c = 0; c < 7; c++) { kx[c] = 0.0; ax[c] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
+        const double bs = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
+        const double ha = h * as;
+        double xs[7], f[7];
+#pragma unroll
+        for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
+        Jac J;
+        model_eval<GP>(o, gpsm, P.gp.stride_out, xs, u, pk, gpx, trig, f, J);
+#pragma unroll
+        for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
+        // sensitivity columns: c = 0..4 <-> x2..x6, c = 5,6 <-> u0,u1
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            // stage input S_in[:,c] = S0[:,c] + ha * K[:,c]; S0 = e_(2+c) for state columns, 0 for input columns
+            double sv[7];   // rows 0..6
+#pragma unroll
+            for (int r = 0; r < 6; r++) sv[r] = ha * K[r][c] + ((c < 5 && r == 2 + c) ? 1.0 : 0.0);
+            sv[6] = (c == 4) ? 1.0 : ((c == 6) ? ha : 0.0);
+            double kn[6];
+            kn[0] = fma(J.j0[0], sv[2], fma(J.j0[1], sv[3], J.j0[2] * sv[4]));
+            kn[1] = fma(J.j1[0], sv[2], fma(J.j1[1], sv[3], J.j1[2] * sv[4]));
+            kn[2] = sv[5];
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+                double v = (c >= 5) ? J.ju[rr][c - 5] : 0.0;
+#pragma unroll
+                for (int l = 0; l < 5; l++) v = fma(J.jr[rr][l], sv[2 + l], v);
+                kn[3 + rr] = v;
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) { K[r][c] = kn[r]; acc[r][c] = fma(bs, kn[r], acc[r][c]); }
+        }
+    }
+    bool bad = false;
+    // x+ = x + h * sum b_s k_s ; b = x+ - x_{k+1}
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+        const double xp = fma(h, ax[c], x[c]);
+        bad |= !isfinite(xp);
+        lin[(size_t)(LIN_b + c) * Bp] = xp - xn[c];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const double v = h * acc[r][c] + ((r == 2 + c) ? 1.0 : 0.0);
+            bad |= !isfinite(v);
+            lin[(size_t)(LIN_A + r * 5 + c) * Bp] = v;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const double v = h * acc[r][5 + c];
+            bad |= !isfinite(v);
+            lin[(size_t)(LIN_B + r * 2 + c) * Bp] = v;
+        }
+    }
+    const double Ts = o.dt;
+#pragma unroll
+    for (int c = 0; c < 7; c++) lin[(size_t)(LIN_q + c) * Bp] = Ts * o.W[c] * (x[c] - yr[c]);
+#pragma unroll
+    for (int c = 0; c < 2; c++) lin[(size_t)(LIN_r + c) * Bp] = Ts * o.W[7 + c] * (u[c] - yr[7 + c]);
+    if (bad) P.lin_bad[i] = 1;
+}
+
+void launch_prepare(const Params &P, cudaStream_t s)
+{
+    dim3 grid((P.Bp + 127) / 128, P.o.N + 1);
+    if (P.o.gp_enabled) {
+        size_t sm = (size_t)P.gp.bytes;
+        static size_t configured = 0;
+        if (sm > configured) {
+            cudaFuncSetAttribute(prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            configured = sm;
+        }
+        prepare_kernel<true><<<grid, 128, sm, s>>>(P);
+    } else {
+        prepare_kernel<false><<<grid, 128, 0, s>>>(P);
+    }
+}

@@ -1,0 +1,110 @@
+// util.cu -- layout kernels (instance-major host layout <-> SoA device layout) and the FP64 peak probe.
+#include "common.cuh"
+
+// [B][F] (instance-major, what the host hands over) -> [F][Bp] (SoA). 32x32 tiles through shared memory so both
+// sides are coalesced.  HBM-bound byte shuffling; grid = tiles.
+__global__ void transpose_in_kernel(const double *__restrict__ src, double *__restrict__ dst, int B, int Bp, int F)
+{
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, f = f0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < B && f < F) ? src[(size_t)i * F + f] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int f = f0 + r, i = i0 + threadIdx.x;
+        if (f < F && i < Bp) dst[(size_t)f * Bp + i] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void transpose_out_kernel(const double *__restrict__ src, double *__restrict__ dst, int B, int Bp, int F)
+{
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int f = f0 + r, i = i0 + threadIdx.x;
+        tile[r][threadIdx.x] = (f < F && i < Bp) ? src[(size_t)f * Bp + i] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, f = f0 + threadIdx.x;
+        if (i < B && f < F) dst[(size_t)i * F + f] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void bcast_rows_kernel(const double *__restrict__ src, double *__restrict__ dst, int Bp, int F)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Bp) return;
+    const double v = src[i];
+    for (int f = blockIdx.y; f < F; f += gridDim.y) dst[(size_t)f * Bp + i] = v;
+}
+
+__global__ void fill_kernel(double *dst, size_t n, double v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = v;
+}
+
+void launch_transpose_in(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s)
+{
+    dim3 grid((Bp + 31) / 32, (F + 31) / 32), block(32, 8);
+    transpose_in_kernel<<<grid, block, 0, s>>>(src, dst, B, Bp, F);
+}
+void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s)
+{
+    dim3 grid((Bp + 31) / 32, (F + 31) / 32), block(32, 8);
+    transpose_out_kernel<<<grid, block, 0, s>>>(src, dst, B, Bp, F);
+}
+void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s)
+{
+    dim3 grid((Bp + 255) / 256, F < 64 ? F : 64);
+    bcast_rows_kernel<<<grid, 256, 0, s>>>(src, dst, Bp, F);
+}
+void launch_fill(double *dst, size_t n, double v, cudaStream_t s)
+{
+    fill_kernel<<<148 * 8, 256, 0, s>>>(dst, n, v);
+}
+
+// ---- FP64 peak probe: 8 independent DFMA chains per thread, full occupancy -------------------------------
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+            r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+}
+
+double run_fp64_peak(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        dfma_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}

@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's solver interface, on top of the C ABI (include/admpc.h).
+
+* ``AcadosOcpSolverB200`` has the methods the reference calls on ``acados_template.AcadosOcpSolver``
+  (data_driven_mpc/ros_gp_mpc/src/ad_mpc/ad_3d_optimizer.py:209,430,438,441-442,450,456,462-465):
+  ``set(stage, field, value)``, ``solve() -> int``, ``get(stage, field) -> ndarray``, ``get_stats``,
+  ``store_iterate/load_iterate`` -- so ``AD3DOptimizer.run_optimization`` runs unchanged against it.
+* ``BatchSolver`` is the batched twin: one call solves B instances.
+
+numpy + ctypes only; no torch, no CPU fallback (``_lib.load`` raises when the CUDA library is missing).
+"""
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib
+from ._lib import AdmpcOpts, check
+
+NC = 10
+
+
+def default_opts(N=20, **kw):
+    L = _lib.load()
+    o = AdmpcOpts()
+    L.admpc_default_opts(C.byref(o))
+    o.N = N
+    for k, v in kw.items():
+        cur = getattr(o, k)
+        if hasattr(cur, "__len__"):
+            for i, vi in enumerate(v):
+                cur[i] = vi
+        else:
+            setattr(o, k, v)
+    return o
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class PinnedArray:
+    """float64/int32 numpy view over cudaHostAlloc'ed memory (truly asynchronous H2D/D2H)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        L = _lib.load()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = L.admpc_host_alloc(max(n, 16))
+        if not self._ptr:
+            raise _lib.AdmpcError("cudaHostAlloc failed: " + L.admpc_last_error().decode())
+        buf = (C.c_char * max(n, 16)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            _lib.load().admpc_host_free(self._ptr)
+            self._ptr = None
+
+
+class BatchSolver:
+    """B independent SQP-RTI NMPC instances on one GPU."""
+
+    def __init__(self, B, opts=None, device=0, N=None):
+        self.L = _lib.load()
+        self.opts = opts if opts is not None else default_opts(N or 20)
+        if N is not None:
+            self.opts.N = N
+        self.B, self.N = int(B), int(self.opts.N)
+        h = C.c_void_p()
+        check(self.L.admpc_batch_create(C.byref(self.opts), self.B, int(device), C.byref(h)), "admpc_batch_create")
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.admpc_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- model / inputs -------------------------------------------------------------------------------------
+    def set_gp(self, model, stage0_trigger=1):
+        """model: dict X[nout,M,dz] alpha[nout,M] ell[nout,dz] sigma_f[nout] y_mean[nout] feat rows (or None)."""
+        if model is None:
+            check(self.L.admpc_batch_set_gp(self.h, 0, 0, 0, None, None, None, None, None, None, None, 0), "set_gp")
+            return
+        X = _f64(model["X"])
+        nout, M, dz = X.shape
+        feat = np.ascontiguousarray(model.get("feat", (3, 4, 5, 6)[:dz]), dtype=np.int32)
+        rows = np.ascontiguousarray(model.get("rows", (4, 5)[:nout]), dtype=np.int32)
+        check(self.L.admpc_batch_set_gp(self.h, nout, M, dz, _ip(feat), _ip(rows), _dp(X), _dp(_f64(model["alpha"])),
+                                        _dp(_f64(model["ell"])), _dp(_f64(model["sigma_f"])), _dp(_f64(model["y_mean"])),
+                                        int(stage0_trigger)), "admpc_batch_set_gp")
+
+    def set_x0(self, x0):
+        check(self.L.admpc_batch_set_x0(self.h, _dp(_f64(x0, (self.B, 7)))), "set_x0")
+
+    def set_yref(self, yref):
+        check(self.L.admpc_batch_set_yref(self.h, _dp(_f64(yref, (self.B, self.N * 9 + 7)))), "set_yref")
+
+    def set_p(self, p):
+        p = np.asarray(p, dtype=np.float64)
+        if p.size == self.B:
+            check(self.L.admpc_batch_set_p_scalar(self.h, _dp(_f64(p, (self.B,)))), "set_p")
+        else:
+            check(self.L.admpc_batch_set_p(self.h, _dp(_f64(p, (self.B, self.N)))), "set_p")
+
+    def set_gp_state(self, gp_state):
+        check(self.L.admpc_batch_set_gp_state(self.h, None if gp_state is None else _dp(_f64(gp_state, (self.B, 7)))), "set_gp_state")
+
+    def set_iterate(self, x=None, u=None):
+        check(self.L.admpc_batch_set_iterate(self.h, None if x is None else _dp(_f64(x, (self.B, (self.N + 1) * 7))),
+                                             None if u is None else _dp(_f64(u, (self.B, self.N * 2)))), "set_iterate")
+
+    def reset(self):
+        check(self.L.admpc_batch_reset(self.h), "reset")
+
+    # ---- solve / outputs ------------------------------------------------------------------------------------
+    def solve(self):
+        check(self.L.admpc_batch_solve(self.h), "solve")
+
+    def wait(self):
+        check(self.L.admpc_batch_wait(self.h), "wait")
+
+    def _get(self, fn, width):
+        out = np.empty((self.B, width))
+        check(fn(self.h, _dp(out)), "get")
+        return out
+
+    def get_u(self):
+        return self._get(self.L.admpc_batch_get_u, self.N * 2).reshape(self.B, self.N, 2)
+
+    def get_x(self):
+        return self._get(self.L.admpc_batch_get_x, (self.N + 1) * 7).reshape(self.B, self.N + 1, 7)
+
+    def get_pi(self):
+        return self._get(self.L.admpc_batch_get_pi, self.N * 7).reshape(self.B, self.N, 7)
+
+    def get_lam(self):
+        return self._get(self.L.admpc_batch_get_lam, self.N * NC).reshape(self.B, self.N, NC)
+
+    def get_t(self):
+        return self._get(self.L.admpc_batch_get_t, self.N * NC).reshape(self.B, self.N, NC)
+
+    def get_slacks(self):
+        sl, su = np.empty((self.B, self.N * 2)), np.empty((self.B, self.N * 2))
+        check(self.L.admpc_batch_get_slacks(self.h, _dp(sl), _dp(su)), "get_slacks")
+        return sl.reshape(self.B, self.N, 2), su.reshape(self.B, self.N, 2)
+
+    def get_status(self):
+        st, qs, qi = (np.empty(self.B, dtype=np.int32) for _ in range(3))
+        check(self.L.admpc_batch_get_status(self.h, _ip(st), _ip(qs), _ip(qi)), "get_status")
+        return st, qs, qi
+
+    def get_lin(self):
+        B, N = self.B, self.N
+        A, Bm, b = np.empty((B, N, 7, 7)), np.empty((B, N, 7, 2)), np.empty((B, N, 7))
+        q, r = np.empty((B, N + 1, 7)), np.empty((B, N, 2))
+        check(self.L.admpc_batch_get_lin(self.h, _dp(A), _dp(Bm), _dp(b), _dp(q), _dp(r)), "get_lin")
+        return dict(A=A, B=Bm, b=b, q=q, r=r)
+
+    def solve_batch(self, x0, yref, p, u_out=None, x_out=None, status_out=None):
+        """One RTI step through host buffers: H2D(x0,yref,p) -> solve -> D2H(u,x,status).  Returns (u, x, status)."""
+        B, N = self.B, self.N
+        x0, yref = _f64(x0, (B, 7)), _f64(yref, (B, N * 9 + 7))
+        p = _f64(np.broadcast_to(np.asarray(p, dtype=np.float64).reshape(-1), (B,)) if np.size(p) in (1, B) else p)
+        if p.size != B:
+            self.set_p(p)
+            p = None
+        u = u_out if u_out is not None else np.empty((B, N, 2))
+        x = x_out if x_out is not None else np.empty((B, N + 1, 7))
+        st = status_out if status_out is not None else np.empty(B, dtype=np.int32)
+        check(self.L.admpc_batch_solve_host(self.h, _dp(x0), _dp(yref), None if p is None else _dp(p), _dp(u), _dp(x), _ip(st)), "solve_host")
+        return u, x, st
+
+    # ---- instrumentation ------------------------------------------------------------------------------------
+    def set_profiling(self, on=True):
+        check(self.L.admpc_batch_set_profiling(self.h, int(on)))
+
+    def last_ms(self, name="solve"):
+        ms = C.c_float()
+        check(self.L.admpc_batch_last_ms(self.h, name.encode(), C.byref(ms)), "last_ms")
+        return float(ms.value)
+
+    def timer_start(self):
+        check(self.L.admpc_batch_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.L.admpc_batch_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        check(self.L.admpc_batch_flush_l2(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.admpc_batch_kernel_launches(self.h))
+
+
+class AcadosOcpSolverB200:
+    """Drop-in for the ``AcadosOcpSolver`` object used by AD3DOptimizer (single instance, acados-shim symbols)."""
+
+    def __init__(self, opts=None, N=None):
+        self.L = _lib.load()
+        self.c = C.c_void_p(self.L.sim_car_acados_create_capsule())
+        if opts is not None:
+            check(self.L.sim_car_acados_set_opts(self.c, C.byref(opts)), "set_opts")
+        n = N if N is not None else (opts.N if opts is not None else 40)
+        check(self.L.sim_car_acados_create_with_discretization(self.c, int(n), None), "create")
+        self.N = int(n)
+        self.status = 0
+
+    def set(self, stage, field, value):
+        v = _f64(np.atleast_1d(value)).reshape(-1)
+        check(self.L.sim_car_acados_set(self.c, int(stage), field.encode(), _dp(v), v.size), "set(%s)" % field)
+
+    def solve(self):
+        self.status = self.L.sim_car_acados_solve(self.c)
+        check(self.status, "solve")
+        return self.status
+
+    def get(self, stage, field):
+        n = {"x": 7, "u": 2, "pi": 7, "sl": 2, "su": 2}.get(field, 22 if stage == 0 else NC)
+        out = np.empty(n)
+        check(self.L.sim_car_acados_get(self.c, int(stage), field.encode(), _dp(out), n), "get(%s)" % field)
+        return out
+
+    def get_stats(self, name):
+        if name in ("time_tot", "kkt_norm_inf"):
+            v = C.c_double()
+        else:
+            v = C.c_int()
+        check(self.L.sim_car_acados_get_stat(self.c, name.encode(), C.byref(v)), "get_stats")
+        return v.value
+
+    def print_statistics(self):
+        self.L.sim_car_acados_print_stats(self.c)
+
+    def reset(self):
+        check(self.L.sim_car_acados_reset(self.c, 1), "reset")
+
+    def store_iterate(self, filename="", overwrite=True):
+        """acados store_iterate JSON layout (sim_car_iterate.json): x_k,u_k,z_k,pi_k,lam_k,t_k,sl_k,su_k."""
+        d = {}
+        for k in range(self.N + 1):
+            d["x_%d" % k] = self.get(k, "x").tolist()
+            d["z_%d" % k] = []
+            for f in ("u", "lam", "t", "sl", "su"):
+                d["%s_%d" % (f, k)] = self.get(k, f).tolist() if k < self.N else []
+            if k < self.N:
+                d["pi_%d" % k] = self.get(k, "pi").tolist()
+        if filename:
+            with open(filename, "w") as fh:
+                json.dump(d, fh, indent=4, sort_keys=True)
+        return d
+
+    def load_iterate(self, filename):
+        with open(filename) as fh:
+            d = json.load(fh)
+        for k in range(self.N + 1):
+            self.set(k, "x", d["x_%d" % k])
+            if k < self.N:
+                self.set(k, "u", d["u_%d" % k])
+
+    def __del__(self):
+        try:
+            if self.c:
+                self.L.sim_car_acados_free(self.c)
+                self.L.sim_car_acados_free_capsule(self.c)
+                self.c = None
+        except Exception:
+            pass

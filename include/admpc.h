@@ -1,0 +1,176 @@
+/*
+ * admpc.h -- C ABI of libadmpc_b200.so: batched SQP-RTI NMPC solver for the AD_MPC bicycle model on NVIDIA B200.
+ *
+ * Drop-in boundary.  Paths cited below are under
+ *   /root/reference/data_driven_mpc/ros_gp_mpc/src/ad_mpc/            ($A)
+ *   /root/reference/data_driven_mpc/ros_gp_mpc/src/ad_mpc/c_generated_code/   ($G)
+ *
+ * Two layers are exported:
+ *   1. `sim_car_acados_*`  -- the acados-generated solver shim's lifecycle symbols, same names / argument meaning /
+ *      return convention as $G/acados_solver_sim_car.h:116-150, plus flat string-keyed set/get that replace the
+ *      libacados calls `ocp_nlp_cost_model_set / ocp_nlp_constraints_model_set / ocp_nlp_out_get / ocp_nlp_get`
+ *      the reference reaches through acados_template ($A/ad_3d_optimizer.py:430,438,441-442,450,456,462-465;
+ *      $G/main_sim_car.c:126-128,171-187,207-208).  One capsule == one MPC instance (a batch of 1 on the GPU).
+ *   2. `admpc_batch_*`     -- the batched twin: B independent instances solved by one call.
+ *
+ * Plain pointers and sizes only.  All setters copy from caller memory, all getters copy into caller memory
+ * ($G/main_sim_car.c:184-187 ownership rule).  Return value 0 == success everywhere; solve returns the acados
+ * status {0 success, 1 failure(NaN), 2 maxiter, 3 minstep, 4 QP failure} ($G/main_sim_car.c:190-197).  Negative
+ * values are library errors (ADMPC_E_*).  There is NO CPU fallback: every entry point that needs the device fails
+ * with ADMPC_E_CUDA when no CUDA device is usable.
+ */
+#ifndef ADMPC_H_
+#define ADMPC_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMPC_NX 7
+#define ADMPC_NU 2
+#define ADMPC_NP 1
+#define ADMPC_NY 9
+#define ADMPC_NYN 7
+#define ADMPC_NC 10        /* per-stage inequality rows [lbu0 lbu1 lbx | ubu0 ubu1 ubx | ls0 ls1 | us0 us1] */
+#define ADMPC_NMAX 128
+#define ADMPC_DZMAX 8
+#define ADMPC_GPOUT_MAX 2
+
+#define ADMPC_E_ARG (-1)       /* bad argument / unknown field / wrong length */
+#define ADMPC_E_CUDA (-2)      /* CUDA runtime error (message via admpc_last_error) */
+#define ADMPC_E_STATE (-3)     /* call order violated (e.g. solve before create) */
+#define ADMPC_E_NCCL (-4)      /* NCCL unavailable or failed */
+#define ADMPC_E_UNSUPPORTED (-5)
+
+/* Problem + solver options.  Defaults (admpc_default_opts) reproduce the shipped configuration:
+ * $G/acados_solver_sim_car.c:362 (dt), :393-399 (W), :481-485 (W_e), :455-473 (z,Z), :549-552 (lbu,ubu),
+ * :595-596 (lbx,ubx), :657-665 (ERK 4 stages x 1 step), :688-693 (HPIPM BALANCE, iter_max 50);
+ * $A/ad_3d.py:47-60 (vehicle). */
+typedef struct admpc_opts {
+    int N;                 /* shooting intervals (20 = $A/ad_3d_mpc.py:23-24 default; 40 = generated code) */
+    int iter_max;          /* QP iteration limit */
+    int gp_enabled;        /* set by admpc_batch_set_gp */
+    int gp_nout, gp_M, gp_dz;
+    int gp_stage0_trigger; /* 1: stage 0 evaluates the GP at gp_state (quad_mpc/quad_3d_optimizer.py:295,548-552) */
+    int reserved0;
+    int gp_feat[ADMPC_DZMAX];      /* feature indices into [x(7);u(2)] (B_z, model_fitting/gp.py:609-630); >= 2 */
+    int gp_row[ADMPC_GPOUT_MAX];   /* state rows receiving the GP outputs (B_x, utils/utils.py:773-786); in {3,4,5} */
+    double dt;
+    double W[9], We[7];
+    double zl[2], zu[2], Zl[2], Zu[2];
+    double lbu[2], ubu[2], lbx, ubx;
+    double mass, lf, lr, iz, cf2, cr2;
+    double mu0, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, lam_min, t_min, thr0, reg;
+} admpc_opts;
+
+void admpc_default_opts(admpc_opts *o);
+const char *admpc_last_error(void);
+int admpc_device_count(void);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * 1. single-instance shim: replaces $G/acados_solver_sim_car.h:116-150
+ * -------------------------------------------------------------------------------------------------------- */
+typedef struct sim_car_solver_capsule sim_car_solver_capsule;     /* opaque ($G/acados_solver_sim_car.h:78-114) */
+
+sim_car_solver_capsule *sim_car_acados_create_capsule(void);                      /* .h:116 */
+int sim_car_acados_free_capsule(sim_car_solver_capsule *capsule);                 /* .h:117 */
+int sim_car_acados_create(sim_car_solver_capsule *capsule);                       /* .h:119  N=40, dt=0.05 */
+int sim_car_acados_create_with_discretization(sim_car_solver_capsule *capsule, int n_time_steps,
+                                              double *new_time_steps);            /* .h:128 (uniform steps only) */
+int sim_car_acados_update_time_steps(sim_car_solver_capsule *capsule, int N, double *new_time_steps); /* .h:133 */
+int sim_car_acados_update_params(sim_car_solver_capsule *capsule, int stage, double *value, int np);  /* .h:138 */
+int sim_car_acados_solve(sim_car_solver_capsule *capsule);                        /* .h:139 */
+int sim_car_acados_reset(sim_car_solver_capsule *capsule, int reset_qp_solver_mem); /* .h:121 */
+int sim_car_acados_free(sim_car_solver_capsule *capsule);                         /* .h:140 */
+void sim_car_acados_print_stats(sim_car_solver_capsule *capsule);                 /* .h:141 */
+/* options used by the next create() on this capsule (the reference freezes them at code-generation time) */
+int sim_car_acados_set_opts(sim_car_solver_capsule *capsule, const admpc_opts *opts);
+/* flat field access replacing ocp_nlp_{cost_model,constraints_model,out}_set / ocp_nlp_out_get / ocp_nlp_get.
+ * set fields: "yref" (9, or 7 at stage N), "lbx"/"ubx" (stage 0: 7 = x0; stages 1..N-1: 1), "p" (1), "x" (7), "u" (2)
+ * get fields: "x" (7), "u" (2), "pi" (7), "lam" (10, stage 0: 22), "t" (same), "sl" (2), "su" (2)
+ * stats: "sqp_iter"(int) "qp_iter"(int) "qp_stat"(int) "status"(int) "time_tot"(double, s) "kkt_norm_inf"(double) */
+int sim_car_acados_set(sim_car_solver_capsule *capsule, int stage, const char *field, const double *value, int n);
+int sim_car_acados_get(sim_car_solver_capsule *capsule, int stage, const char *field, double *out, int n);
+int sim_car_acados_get_stat(sim_car_solver_capsule *capsule, const char *name, void *out);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * 2. batched solver: B independent instances, SoA-resident in HBM
+ *    Host layouts are instance-major (AoS), i.e. what numpy gives for x0[B,7], yref[B,N*9+7], ...
+ * -------------------------------------------------------------------------------------------------------- */
+typedef struct admpc_batch admpc_batch;
+
+int admpc_batch_create(const admpc_opts *opts, int B, int device, admpc_batch **out);
+int admpc_batch_free(admpc_batch *h);
+int admpc_batch_size(const admpc_batch *h);
+int admpc_batch_horizon(const admpc_batch *h);
+
+/* GP model (model_fitting/gp.py:495-508 schema): X[nout][M][dz], alpha[nout][M] (=K^-1 y), ell[nout][dz],
+ * sigma_f[nout], y_mean[nout]; feat[dz], rows[nout].  Pass nout = 0 to disable the GP again. */
+int admpc_batch_set_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, const int *rows,
+                       const double *X, const double *alpha, const double *ell, const double *sigma_f,
+                       const double *y_mean, int stage0_trigger);
+
+/* per-solve inputs ($A/ad_3d_optimizer.py:420-450).  Asynchronous on the handle's stream; pinned host memory
+ * (admpc_host_alloc) makes the copies truly asynchronous. */
+int admpc_batch_set_x0(admpc_batch *h, const double *x0 /*[B][7]*/);
+int admpc_batch_set_yref(admpc_batch *h, const double *yref /*[B][N*9+7]*/);
+int admpc_batch_set_p(admpc_batch *h, const double *p /*[B][N]*/);
+int admpc_batch_set_p_scalar(admpc_batch *h, const double *p /*[B]*/);      /* same switch on all stages (:449-450) */
+int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state /*[B][7] or NULL = x0*/);
+/* iterate (initial guess / warm start).  reset zeroes it like $G/acados_solver_sim_car.c:819-852. */
+int admpc_batch_set_iterate(admpc_batch *h, const double *x /*[B][(N+1)*7]*/, const double *u /*[B][N*2]*/);
+int admpc_batch_reset(admpc_batch *h);
+
+int admpc_batch_solve(admpc_batch *h);   /* one SQP-RTI iteration for all B instances (async launch) */
+int admpc_batch_wait(admpc_batch *h);    /* block until everything queued on the handle has finished */
+
+/* results (each waits for the solve, then copies D2H) */
+int admpc_batch_get_u(admpc_batch *h, double *u /*[B][N*2]*/);
+int admpc_batch_get_x(admpc_batch *h, double *x /*[B][(N+1)*7]*/);
+int admpc_batch_get_pi(admpc_batch *h, double *pi /*[B][N*7]*/);
+int admpc_batch_get_lam(admpc_batch *h, double *lam /*[B][N*10]*/);
+int admpc_batch_get_t(admpc_batch *h, double *t /*[B][N*10]*/);
+int admpc_batch_get_slacks(admpc_batch *h, double *sl /*[B][N*2]*/, double *su /*[B][N*2]*/);
+int admpc_batch_get_status(admpc_batch *h, int *status /*[B]*/, int *qp_status /*[B] or NULL*/, int *qp_iter /*[B] or NULL*/);
+/* linearisation of the last solve, for kernel-level parity tests: A[B][N][49] B[B][N][14] b[B][N][7] q[B][(N+1)*7] r[B][N*2] */
+int admpc_batch_get_lin(admpc_batch *h, double *A, double *Bm, double *b, double *q, double *r);
+
+/* whole RTI step through host buffers in ONE call: H2D(x0,yref,p) -> solve -> D2H(u,x,status).  This is the
+ * replacement of the 3N+5 ctypes calls of $A/ad_3d_optimizer.py:420-465. Any output pointer may be NULL. */
+int admpc_batch_solve_host(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
+                           double *u_out, double *x_out, int *status_out);
+
+/* instrumentation: device time (CUDA events on the handle's stream) of the last solve and of its kernels.
+ * name: "solve" | "prepare" | "qp" | "h2d" | "d2h" ; returns milliseconds in *ms. Needs admpc_batch_set_profiling(1)
+ * for the per-kernel entries. */
+int admpc_batch_set_profiling(admpc_batch *h, int on);
+int admpc_batch_last_ms(admpc_batch *h, const char *name, float *ms);
+long long admpc_batch_kernel_launches(const admpc_batch *h);   /* kernels launched by this handle so far */
+/* stream-ordered event pair for external timing of a region on the handle's stream */
+int admpc_batch_timer_start(admpc_batch *h);
+int admpc_batch_timer_stop(admpc_batch *h, float *ms);   /* records, synchronises and returns elapsed ms */
+int admpc_batch_flush_l2(admpc_batch *h);                /* writes a >L2-sized scratch buffer (bench hygiene) */
+
+/* pinned host memory helpers */
+void *admpc_host_alloc(unsigned long long bytes);
+int admpc_host_free(void *p);
+
+/* multi-GPU plumbing (one process per GPU).  The NCCL library is dlopen'ed; unique id bytes (128) are exchanged by
+ * the caller's launcher (torch.distributed / MPI / file).  Broadcast ships the GP model from root to every rank's
+ * handle; gather collects [u | x | status] blocks on root. */
+int admpc_nccl_unique_id(void *id128);
+int admpc_batch_comm_init(admpc_batch *h, const void *id128, int rank, int nranks);
+int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, const int *feat, const int *rows,
+                         const double *X, const double *alpha, const double *ell, const double *sigma_f,
+                         const double *y_mean, int stage0_trigger);
+int admpc_batch_gather(admpc_batch *h, int root, double *u_all /*[nranks*B][N*2]*/, double *x_all, int *status_all);
+int admpc_batch_barrier(admpc_batch *h);
+
+/* FP64 peak probe: runs a dependent-free DFMA loop and returns achieved TFLOP/s (roofline denominator; there is
+ * no FP64 entry in MEASURED_PEAKS.json). */
+int admpc_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

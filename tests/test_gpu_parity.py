@@ -1,0 +1,259 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): 1e-8 relative in FP64, measured as |a-b| <= 1e-8*max(1,|b|); status codes and
+QP iteration counts must be identical.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from ad_mpc_b200 import BatchSolver, AcadosOcpSolverB200, default_opts, workload as wl
+from oracle import oracle as orc
+from util_parity import mirror_opts, mixed_err, oracle_batch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _gpu_step(s, batch, gp_state=None):
+    s.set_iterate(batch["x_init"], batch["u_init"])
+    s.set_x0(batch["x0"])
+    s.set_yref(batch["yref"])
+    s.set_p(batch["p"])
+    if gp_state is not None:
+        s.set_gp_state(gp_state)
+    s.solve()
+    st, qs, qi = s.get_status()
+    return dict(u=s.get_u(), x=s.get_x(), pi=s.get_pi(), status=st, qp_status=qs, qp_iter=qi)
+
+
+def _compare(g, r, tol=TOL):
+    assert np.array_equal(g["status"], r["status"])
+    assert np.array_equal(g["qp_status"], r["qp_status"])
+    assert np.array_equal(g["qp_iter"], r["qp_iter"]), (g["qp_iter"][:16], r["qp_iter"][:16])
+    ok = r["status"] == 0
+    assert mixed_err(g["u"][ok], r["u"][ok]) <= tol
+    assert mixed_err(g["x"][ok], r["x"][ok]) <= tol
+    assert mixed_err(g["pi"][ok], r["pi"][ok]) <= 1e-6      # duals: looser (scaled by 1/t near active bounds)
+
+
+@pytest.mark.parametrize("p", [0.0, 1.0, 0.35])
+@pytest.mark.parametrize("N", [20, 40])
+def test_prepare_parity_nominal(p, N):
+    B = 96
+    batch = wl.make_batch(B, N, seed=11, p=p)
+    rng = np.random.default_rng(5)
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([1.0, 0.2])      # exercise the u-dependent Jacobian
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    s.set_iterate(batch["x_init"], batch["u_init"]); s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"])
+    s.solve()
+    lin = s.get_lin()
+    o = mirror_opts(opts)
+    for i in range(0, B, 7):
+        it = orc.make_iterate(o, batch["x_init"][i], batch["u_init"][i])
+        ref = orc.prepare(o, it, batch["yref"][i], batch["p"][i])
+        for key in ("A", "B", "b", "q", "r"):
+            assert mixed_err(lin[key][i], ref[key]) <= 1e-12, key
+    s.close()
+
+
+@pytest.mark.parametrize("p,trigger", [(1.0, 1), (0.0, 0), (0.6, 1)])
+def test_prepare_parity_gp(p, trigger):
+    B, N, M = 64, 20, 60
+    batch = wl.make_batch(B, N, seed=12, p=p)
+    rng = np.random.default_rng(6)
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([1.0, 0.2])
+    model = wl.make_gp(M=M, seed=3)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    s.set_gp(model, stage0_trigger=trigger)
+    gps = batch["x0"] + 0.01
+    s.set_iterate(batch["x_init"], batch["u_init"]); s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"])
+    s.set_gp_state(gps)
+    s.solve()
+    lin = s.get_lin()
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"], stage0_trigger=trigger)
+    for i in range(0, B, 5):
+        it = orc.make_iterate(o, batch["x_init"][i], batch["u_init"][i])
+        ref = orc.prepare(o, it, batch["yref"][i], batch["p"][i], gp=gp, gp_state=gps[i])
+        for key in ("A", "B", "b", "q", "r"):
+            assert mixed_err(lin[key][i], ref[key]) <= 1e-10, key
+    s.close()
+
+
+@pytest.mark.parametrize("p", [0.0, 1.0])
+@pytest.mark.parametrize("B,N", [(1, 20), (33, 20), (512, 20), (100, 40)])
+def test_rti_step_parity_nominal(p, B, N):
+    batch = wl.make_batch(B, N, seed=20262, p=p)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    g = _gpu_step(s, batch)
+    r = oracle_batch(mirror_opts(opts), batch)
+    assert (r["status"] == 0).all()
+    _compare(g, r)
+    s.close()
+
+
+def test_rti_step_parity_active_bounds():
+    """large initial-state errors: acceleration / steering-rate soft bounds and the steering bound become active."""
+    B, N = 256, 20
+    batch = wl.make_batch(B, N, seed=99, p=0.0, perturb=6.0)
+    batch["x0"][:, 6] = np.clip(batch["x0"][:, 6] * 4, -0.6, 0.6)        # some start outside the steering bound
+    batch["x_init"][:, :, 6] = np.clip(batch["x0"][:, None, 6], -0.5, 0.5)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    g = _gpu_step(s, batch)
+    r = oracle_batch(mirror_opts(opts), batch)
+    lam_active = (np.abs(g["u"][..., 0] - 5.0) < 1e-6).any() or (np.abs(g["u"][..., 0] + 10.0) < 1e-6).any()
+    assert lam_active, "test does not exercise an active input bound"
+    _compare(g, r)
+    s.close()
+
+
+def test_rti_step_parity_gp():
+    B, N, M = 128, 20, 200
+    batch = wl.make_batch(B, N, seed=20263, p=1.0)
+    model = wl.make_gp(M=M, seed=20263)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    s.set_gp(model)
+    g = _gpu_step(s, batch)
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    r = oracle_batch(o, batch, gp=gp)
+    _compare(g, r)
+    s.close()
+
+
+def test_closed_loop_warm_start_parity():
+    """5 consecutive RTI steps (iterate carried, unshifted, like the reference) stay in parity."""
+    B, N = 64, 20
+    batch = wl.make_batch(B, N, seed=7, p=1.0)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    o = mirror_opts(opts)
+    xo, uo = batch["x_init"].copy(), batch["u_init"].copy()
+    s.set_iterate(xo, uo)
+    x0 = batch["x0"].copy()
+    for step in range(5):
+        u, x, st = s.solve_batch(x0, batch["yref"], batch["p"][:, 0])
+        r = orc.rti_batch(o, x0, batch["yref"], batch["p"], xo, uo)
+        assert np.array_equal(st, r["status"])
+        assert mixed_err(u, r["u"]) <= TOL and mixed_err(x, r["x"]) <= TOL
+        xo, uo = r["x"], r["u"]
+        x0 = r["x"][:, 1, :].copy()          # plant = model prediction
+    s.close()
+
+
+def test_golden_fixed_point_on_gpu(golden_dir):
+    """The converged acados iterate (sim_car_iterate.json) is a fixed point of the CUDA RTI step as well."""
+    from test_oracle_golden import _golden_lam, _golden_lin, _recover_yref
+    g = np.load(os.path.join(golden_dir, "sim_car_iterate.npz"))
+    We = np.array([10.0, 10.0, 100.0, 0, 0, 0, 0])
+    opts = default_opts(40, We=We)
+    o = mirror_opts(opts)
+    A, B, _ = _golden_lin(g, o)
+    lam, t = _golden_lam(g)
+    yref = _recover_yref(g, o, A, lam, We)
+    s = BatchSolver(1, opts)
+    s.set_iterate(g["x"][None], g["u"][None])
+    u, x, st = s.solve_batch(g["x"][0][None], yref[None], np.zeros(1))
+    assert st[0] == 0
+    assert np.abs(x[0] - g["x"]).max() < 5e-7 and np.abs(u[0] - g["u"]).max() < 5e-7
+    assert np.abs(s.get_pi()[0] - g["pi"]).max() < 1e-5
+    lam_g = s.get_lam()[0]
+    act = lam > 1e-3
+    assert np.abs(lam_g[act] - lam[act]).max() < 1e-5
+    s.close()
+
+
+def test_nan_linearisation_status():
+    """NaN in the iterate -> ACADOS_FAILURE (1) for that instance only; others unaffected."""
+    B, N = 40, 20
+    batch = wl.make_batch(B, N, seed=3)
+    batch["x_init"][5, 3, 3] = np.nan
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    g = _gpu_step(s, batch)
+    r = oracle_batch(mirror_opts(opts), batch)
+    assert g["status"][5] == 1 and r["status"][5] == 1
+    assert np.array_equal(g["status"], r["status"])
+    s.close()
+
+
+def test_iter_max_status():
+    """QP iteration limit: qp_status 2 (ACADOS_MAXITER), RTI status 0 (tolerated), same on both sides."""
+    B, N = 32, 20
+    batch = wl.make_batch(B, N, seed=4)
+    opts = default_opts(N, iter_max=2)
+    s = BatchSolver(B, opts)
+    g = _gpu_step(s, batch)
+    r = oracle_batch(mirror_opts(opts), batch)
+    assert (g["qp_status"] == 2).all() and (g["qp_iter"] == 2).all()
+    _compare(g, r, tol=1e-7)
+    s.close()
+
+
+def test_acados_shim_single_instance():
+    """The acados-shim symbols reproduce AD3DOptimizer.run_optimization's call sequence (ad_3d_optimizer.py:420-465)."""
+    N = 20
+    batch = wl.make_batch(1, N, seed=8, p=0.0)
+    opts = default_opts(N)
+    solver = AcadosOcpSolverB200(opts)
+    yref = batch["yref"][0]
+    for j in range(N):
+        solver.set(j, "yref", yref[j * 9:(j + 1) * 9])
+    solver.set(N, "yref", yref[N * 9:])
+    solver.set(0, "lbx", batch["x0"][0])
+    solver.set(0, "ubx", batch["x0"][0])
+    for j in range(N + 1):
+        solver.set(j, "p", np.array([0.0]))
+    for j in range(N + 1):
+        solver.set(j, "x", batch["x_init"][0, j])
+    status = solver.solve()
+    assert status == 0
+    u = np.array([solver.get(i, "u") for i in range(N)])
+    x = np.array([solver.get(i, "x") for i in range(N + 1)])
+    r = oracle_batch(mirror_opts(opts), batch)
+    assert mixed_err(u, r["u"][0]) <= TOL and mixed_err(x, r["x"][0]) <= TOL
+    assert solver.get_stats("sqp_iter") == 1 and solver.get_stats("qp_iter") == r["qp_iter"][0]
+    assert solver.get(0, "lam").shape == (22,) and solver.get(1, "lam").shape == (10,)
+    assert solver.get_stats("kkt_norm_inf") < 1e-8
+    d = solver.store_iterate()
+    assert len(d) == 8 * (N + 1) - 1
+    # second solve from the carried iterate changes less than the first
+    x_prev = x.copy()
+    solver.solve()
+    x2 = np.array([solver.get(i, "x") for i in range(N + 1)])
+    assert np.abs(x2 - x_prev).max() < 0.5
+
+
+def test_scale_invariance_full_size():
+    """BASELINE cfg-3 size (B=16384, GP M=200): size-independent properties instead of a 16k-instance oracle run --
+    (i) duplicated instances give bit-identical results wherever they sit in the batch, (ii) a 256-instance sample
+    matches the oracle, (iii) every status is 0 and every QP converged."""
+    B, N = 16384, 20
+    base = wl.make_batch(256, N, seed=20263, p=1.0)
+    reps = B // 256
+    batch = {k: np.concatenate([v] * reps, axis=0) for k, v in base.items()}
+    model = wl.make_gp(M=200, seed=20263)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    s.set_gp(model)
+    g = _gpu_step(s, batch)
+    assert (g["status"] == 0).all() and (g["qp_status"] == 0).all()
+    u = g["u"].reshape(reps, 256, N, 2)
+    assert np.array_equal(u[0], u[-1]) and np.array_equal(u[0], u[reps // 2])
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    r = oracle_batch(o, base, gp=gp)
+    assert mixed_err(u[0], r["u"]) <= TOL
+    assert np.array_equal(g["qp_iter"][:256], r["qp_iter"])
+    s.close()
