@@ -114,6 +114,7 @@ struct admpc_batch {
     cudaEvent_t tm0, tm1;
     bool profiling = false;
     bool gps_set = false;
+    int qp_variant = 0;      // 0 auto(=3), 1 thread-per-instance (qp_ipm.cu), 2 octet (qp_octet.cu), 3 smem octet (qp_smem.cu)
     long long launches = 0;
     float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
     nccl_comm comm = nullptr;
@@ -131,6 +132,7 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     CUDA_CHECK_RET(cudaSetDevice(device));
     admpc_batch *h = new admpc_batch();
     h->device = device;
+    if (const char *v = getenv("ADMPC_QP_VARIANT")) h->qp_variant = atoi(v);
     Params &P = h->P;
     memset(&P, 0, sizeof P);
     P.o = *opts;
@@ -154,9 +156,9 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
         {&P.lin, (size_t)(N + 1) * LIN_ROWS},
         {&P.dx, nX}, {&P.du, nU}, {&P.pi, nPi}, {&P.lam, nC}, {&P.t, nC}, {&P.sl, nU}, {&P.su, nU},
         {&P.rgu, nU}, {&P.rgx, nX}, {&P.rgsl, nU}, {&P.rgsu, nU}, {&P.rb, nPi}, {&P.rd, nC}, {&P.rm, nC},
-        {&P.K, (size_t)N * 14}, {&P.Ginv, (size_t)N * 3}, {&P.P, (size_t)(N + 1) * 28}, {&P.Pb, nPi}, {&P.kf, nU}, {&P.pv, nX},
+        {&P.K, (size_t)N * 14}, {&P.Ginv, (size_t)N * 3}, {&P.P, (size_t)(N + 1) * 28}, {&P.Pb, nPi}, {&P.kf, nU}, {&P.pv, nX}, {&P.bar, (size_t)N * 6},
         {&P.ddu, nU}, {&P.ddx, nX}, {&P.dpi, nPi}, {&P.dlam, nC}, {&P.dt, nC}, {&P.dsl, nU}, {&P.dsu, nU},
-        {&P.res_out, 4},
+        {&P.res_out, 4}, {&P.ws, (size_t)qp_smem_ws_rows(N)},
     };
     size_t rows = 0;
     for (auto &it : items) rows += it.rows;
@@ -321,11 +323,16 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
     launch_prepare(P, h->stream);
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
-    launch_qp(P, h->stream);
+    // QP variant: 3 (default) shared-memory-resident octets with fused update; 2 octets on global scratch;
+    // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
+    const int variant = h->qp_variant ? h->qp_variant : 3;
+    bool fused = false;
+    if (variant == 3) fused = launch_qp_smem(P, h->stream);
+    if (!fused) { if (variant == 2) launch_qp_octet(P, h->stream); else launch_qp(P, h->stream); }
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
-    launch_update(P, h->stream);
+    if (!fused) launch_update(P, h->stream);
     CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
-    h->launches += 3;
+    h->launches += fused ? 2 : 3;
     CUDA_CHECK_RET(cudaGetLastError());
     return 0;
 }

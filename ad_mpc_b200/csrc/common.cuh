@@ -43,8 +43,9 @@ struct Params {
     // QP solution (delta form) + workspace
     double *dx, *du, *pi, *lam, *t, *sl, *su;
     double *rgu, *rgx, *rgsl, *rgsu, *rb, *rd, *rm;
-    double *K, *Ginv, *P, *Pb, *kf, *pv;
+    double *K, *Ginv, *P, *Pb, *kf, *pv, *bar;
     double *ddu, *ddx, *dpi, *dlam, *dt, *dsl, *dsu;
+    double *ws;          // qp_smem.cu: per-warp scratch tiles [Bp/4][rows][4]
     int *status, *qp_status, *qp_iter, *lin_bad;
     double *res_out;     // [4][Bp] final residual norms
 };
@@ -60,6 +61,9 @@ void admpc_set_error(const char *what, const char *msg);
 // kernel launchers (defined in the .cu files)
 void launch_prepare(const Params &P, cudaStream_t s);
 void launch_qp(const Params &P, cudaStream_t s);
+void launch_qp_octet(const Params &P, cudaStream_t s);
+bool launch_qp_smem(const Params &P, cudaStream_t s);   // false: horizon too long for the shared-memory variant
+int qp_smem_ws_rows(int N);
 void launch_transpose_in(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);   // [B][F] -> [F][Bp]
 void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);  // [F][Bp] -> [B][F]
 void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]

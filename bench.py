@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- SQP-RTI MPC solves/sec (N=20, GP-augmented) on 1/2/4/8 B200, roofline + CPU baseline.
+
+  python bench.py [--gpus N --steps K --warmup W]                 our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [...]                          reference arm: CPU restatement on all host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU (weak scaling: B per GPU fixed)
+
+One "step" = one SQP-RTI iteration (prepare -> QP -> update) over one batch of B instances per GPU.
+Workload (BASELINE.json configs[2], SURVEY 8d cfg 3): GP-augmented bicycle NMPC, N=20, dt=0.05, RBF GP with M=200
+training points on (v_y, yaw-rate), B=16384 instances per GPU, dynamic tyre model (p=1), circular track, synthetic.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(N=20, dt=0.05, M=200, B=16384, p=1.0, dz=4, n_out=2)
+
+
+def algorithmic_ops(N, M, dz, n_out, n_ipm, gp=True):
+    """SURVEY.md 8(d) op model (sin/cos/exp/div = 1 op): per solve, split by kernel."""
+    f_sim = 4848.0 * N + 60.0 * N
+    f_gp = 4.0 * N * (n_out * M * (6 * dz + 4) + 144) if gp else 0.0
+    f_qp = 3200.0 * N * n_ipm
+    return dict(prepare=f_sim + f_gp, qp=f_qp)
+
+
+def algorithmic_bytes(N):
+    """x0(7)+yref(9N+7)+p(1) in, u(2N)+x(7N+7) out, 8 B status/iter."""
+    return 8 * (7 + 9 * N + 7 + 1 + 2 * N + 7 * N + 7) + 8
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        # median over the busiest half of the samples (the region also contains host-side gaps)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return dict(sm_mhz=statistics.median(load) if load else None, sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_workload(rank, B=None):
+    from ad_mpc_b200 import workload as wl
+    B = B or CFG["B"]
+    batch = wl.make_batch(B, CFG["N"], dt=CFG["dt"], seed=20263 + 1000 * rank, p=CFG["p"])
+    model = wl.make_gp(M=CFG["M"], seed=20263, n_out=CFG["n_out"], dz=CFG["dz"])
+    return batch, model
+
+
+def config_dict(world):
+    return {"workload": "cfg3: GP-augmented bicycle NMPC (in-tree Cartesian-pose model), SQP-RTI, N=20, dt=0.05, RBF GP M=200 (d_z=4, "
+                        "2 outputs on v_y/yaw-rate), dynamic tyre model p=1, B=16384 instances per GPU, circular track R=50 m",
+            "N": CFG["N"], "gp_points": CFG["M"], "batch_per_gpu": CFG["B"], "global_batch": CFG["B"] * world,
+            "parallelism": "dp%d (independent instances, weak scaling)" % world,
+            "l2": "flushed between timed steps (256 MiB fill, untimed); per-step working set ~0.6 GB > 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline -------
+def cpu_oracle_rate(sample, nthreads=0, gp=True, reps=1):
+    """Times the oracle port (CPU restatement of the reference path; acados itself is not buildable here) on a
+    bounded sample of the same workload.  Returns (solves/s, seconds, threads)."""
+    from oracle import oracle as orc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util_parity import mirror_opts
+    from ad_mpc_b200 import default_opts
+    batch, model = make_workload(0, B=sample)
+    po = default_opts(CFG["N"])
+    po.dt = CFG["dt"]
+    o = mirror_opts(po)             # same options as the CUDA arm, field by field
+    g = None
+    if gp:
+        g = orc.Gp(model)
+        g.apply(o, feat=model["feat"], rows=model["rows"])
+    cores = nthreads or (os.cpu_count() or 1)
+    orc.rti_batch(o, batch["x0"][:64], batch["yref"][:64], batch["p"][:64], batch["x_init"][:64], batch["u_init"][:64],
+                  gp=g, nthreads=cores)   # warm-up (page-in, thread pool)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = orc.rti_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=g, nthreads=cores)
+    dt = time.perf_counter() - t0
+    assert (r["status"] == 0).all()
+    return sample * reps / dt, dt, cores
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    sample = 2048
+    cores = os.cpu_count() or 1
+    times = []
+    for s in range(args.warmup + args.steps):
+        rate, dt, cores = cpu_oracle_rate(sample)
+        if s >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms * 1e-3)
+    line = {"impl": "reference", "metric": "SQP-RTI MPC solves/sec (N=20, GP-augmented)", "value": value, "unit": "solves/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config_dict(world), reference_note="CPU restatement of the acados path (acados/HPIPM are "
+                           "un-vendored dependencies and cannot be built here); each step = %d-instance sample" % sample),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": "%d instances of the cfg3 workload per step, OpenMP over instances" % sample},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm ------------
+def run_ours(args):
+    rank, world, local = dist_env()
+    from ad_mpc_b200 import BatchSolver, PinnedArray, default_opts, _lib
+    import ctypes as C
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist          # plumbing only: rendezvous, barrier, max over ranks
+        dist.init_process_group(backend="gloo")
+    L = _lib.load()
+    B, N = CFG["B"], CFG["N"]
+    opts = default_opts(N)
+    opts.dt = CFG["dt"]
+    s = BatchSolver(B, opts, device=local)
+    batch, model = make_workload(rank)
+
+    if world > 1:
+        # NCCL communicator of the library itself: unique id from rank 0, shipped through the launcher's store
+        uid = (C.c_char * 128)()
+        if rank == 0:
+            _lib.check(L.admpc_nccl_unique_id(uid), "nccl_unique_id")
+        obj = [bytes(uid.raw)]
+        dist.broadcast_object_list(obj, src=0)
+        uid = (C.c_char * 128).from_buffer_copy(obj[0])
+        _lib.check(L.admpc_batch_comm_init(s.h, uid, rank, world), "comm_init")
+        # GP model lives on rank 0 and is broadcast over NVLink
+        X = np.ascontiguousarray(model["X"]); al = np.ascontiguousarray(model["alpha"]); ell = np.ascontiguousarray(model["ell"])
+        sf = np.ascontiguousarray(model["sigma_f"]); ym = np.ascontiguousarray(model["y_mean"])
+        feat = np.ascontiguousarray(model["feat"], dtype=np.int32); rows = np.ascontiguousarray(model["rows"], dtype=np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        _lib.check(L.admpc_batch_bcast_gp(s.h, 0, X.shape[0], X.shape[1], X.shape[2], feat.ctypes.data_as(ip),
+                                          rows.ctypes.data_as(ip), X.ctypes.data_as(dp), al.ctypes.data_as(dp),
+                                          ell.ctypes.data_as(dp), sf.ctypes.data_as(dp), ym.ctypes.data_as(dp), 1), "bcast_gp")
+    else:
+        s.set_gp(model)
+
+    def barrier():
+        s.wait()
+        if dist is not None:
+            dist.barrier()
+
+    def gather_device():
+        if world > 1:
+            _lib.check(L.admpc_batch_gather(s.h, 0, None, None, None), "gather")
+
+    # resident inputs
+    s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"][:, 0])
+    x_init, u_init = batch["x_init"], batch["u_init"]
+
+    def device_step():
+        s.solve()
+        gather_device()
+
+    # ---- device-resident throughput ("value") -----------------------------------------------------------------
+    s.set_profiling(True)
+    for _ in range(max(args.warmup, 3)):
+        s.set_iterate(x_init, u_init)
+        device_step()
+    s.wait()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    step_ms, prep_ms, qp_ms = [], [], []
+    launches0 = s.kernel_launches()
+    counted = 0
+    for _ in range(args.steps):
+        s.set_iterate(x_init, u_init)       # same warm start every step (untimed restore of the iterate)
+        s.flush_l2()
+        l0 = s.kernel_launches()
+        s.timer_start()
+        device_step()
+        step_ms.append(s.timer_stop())
+        counted += s.kernel_launches() - l0
+        prep_ms.append(s.last_ms("prepare"))
+        qp_ms.append(s.last_ms("qp"))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    st, qs, qi = s.get_status()
+    assert (st == 0).all(), "solver failures in the benchmark batch"
+    n_ipm = float(qi.mean())
+    t_local = sum(step_ms)
+    if dist is not None:
+        import torch
+        tt = torch.tensor([t_local], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_all = float(tt.item())
+    else:
+        t_all = t_local
+    ms_per_step = t_all / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with pinned HOST buffers ("e2e") --------------------------------
+    pin = {k: PinnedArray(v.shape) for k, v in (("x0", batch["x0"]), ("yref", batch["yref"]))}
+    pin["x0"].array[:] = batch["x0"]; pin["yref"].array[:] = batch["yref"]
+    pin_p = PinnedArray((B,)); pin_p.array[:] = batch["p"][:, 0]
+    out_u, out_x = PinnedArray((B, N, 2)), PinnedArray((B, N + 1, 7))
+    out_st = PinnedArray((B,), dtype=np.int32)
+    e2e_ms = []
+    for it in range(max(args.warmup, 3) + args.steps):
+        s.set_iterate(x_init, u_init)
+        s.wait()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        s.timer_start()
+        s.solve_batch(pin["x0"].array, pin["yref"].array, pin_p.array, out_u.array, out_x.array, out_st.array)
+        ms = s.timer_stop()
+        if it >= max(args.warmup, 3):
+            e2e_ms.append(ms)
+    e_local = sum(e2e_ms)
+    if dist is not None:
+        tt = torch.tensor([e_local], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e_all = float(tt.item())
+    else:
+        e_all = e_local
+    e2e_value = B * world / (e_all / args.steps * 1e-3)
+    h2d = int(batch["x0"].nbytes + batch["yref"].nbytes + B * 8)
+    d2h = int(B * N * 2 * 8 + B * (N + 1) * 7 * 8 + B * 4)
+    assert np.array_equal(out_st.array, st)
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (FP64 DFMA pipe) ------------------------------------
+        peak = C.c_double()
+        _lib.check(L.admpc_measure_fp64_peak(local, C.byref(peak)), "fp64 peak")
+        ops = algorithmic_ops(N, CFG["M"], CFG["dz"], CFG["n_out"], n_ipm)
+        kern = {"prepare": statistics.mean(prep_ms), "qp": statistics.mean(qp_ms)}
+        dom = max(kern, key=kern.get)
+        achieved = ops[dom] * B / (kern[dom] * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dom)
+            except Exception:
+                traffic = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "fp64", "kernel": {"prepare": "prepare_kernel<GP>", "qp": "qp_ipm_kernel"}[dom],
+                    "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
+                    "traffic": traffic,
+                    "peak_source": "DFMA microbenchmark admpc_measure_fp64_peak run in this process (MEASURED_PEAKS.json "
+                                   "has no FP64 entry; the path is FP64-CUDA-core bound, neither hbm nor tensor)",
+                    "flops_per_solve": ops[dom], "n_ipm_mean": n_ipm,
+                    "kernels_ms": kern,
+                    "all_kernels_tflops": (ops["prepare"] + ops["qp"]) * B / ((kern["prepare"] + kern["qp"]) * 1e-3) / 1e12,
+                    "hbm": {"algorithmic_GBps": algorithmic_bytes(N) * B / (ms_per_step * 1e-3) / 1e9, "peak_GBps": hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+        # ---- CPU baseline on this box's host cores ----------------------------------------------------------
+        sample = 2048
+        rate, secs, cores = cpu_oracle_rate(sample, reps=2)
+        cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": "%d instances of the cfg3 workload x2, OpenMP over instances, %.1f s" % (sample, secs),
+               "note": "CPU restatement of the acados path (oracle/); acados itself cannot be built here"}
+        e2e_sorted = sorted(e2e_ms)
+        line = {"metric": "SQP-RTI MPC solves/sec (N=20, GP-augmented)", "value": value, "unit": "solves/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(world),
+                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "p50_ms_per_batch_call": e2e_sorted[len(e2e_sorted) // 2]},
+                "gpu_launches": counted, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "wall_s_timed_region": wall,
+                "latency": {"p50_ms_per_batch_solve": sorted(step_ms)[len(step_ms) // 2], "batch": B}}
+        print(json.dumps(line), flush=True)
+    barrier()
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
