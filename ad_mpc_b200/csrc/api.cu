@@ -323,11 +323,13 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
     launch_prepare(P, h->stream);
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
-    // QP variant: 3 (default) shared-memory-resident octets with fused update; 2 octets on global scratch;
+    // QP variant: 4 (default) warp per instance, register-resident IPM state; 3 shared-memory-resident octets
+    // (horizons 32..80); 2 octets on global scratch;
     // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
-    const int variant = h->qp_variant ? h->qp_variant : 3;
+    const int variant = h->qp_variant ? h->qp_variant : 4;
     bool fused = false;
-    if (variant == 3) fused = launch_qp_smem(P, h->stream);
+    if (variant == 4) fused = launch_qp_warp(P, h->stream);        // one warp per instance, N <= 31
+    if (!fused && variant >= 3) fused = launch_qp_smem(P, h->stream);
     if (!fused) { if (variant == 2) launch_qp_octet(P, h->stream); else launch_qp(P, h->stream); }
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
     if (!fused) launch_update(P, h->stream);

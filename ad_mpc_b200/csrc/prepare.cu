@@ -38,6 +38,36 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  : "memory");
 }
 
+// exp(x) for x <= 0 (RBF kernel argument -0.5 * squared distance): Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2,
+// degree-13 Taylor/Horner (truncation 4e-18 relative), exponent-field scaling.  ~20 FP64-pipe instructions against
+// ~30 for the generic libdevice exp (no special cases needed here); arguments below -700 are clamped
+// (result 1e-304 instead of a denormal/zero: absolute difference < 1e-300).
+__device__ __forceinline__ double exp_neg(double x)
+{
+    x = fmax(x, -700.0);
+    const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest integer in the low bits
+    const double t = fma(x, 1.4426950408889634, SHIFT);
+    const int n = __double2loint(t);
+    const double nf = t - SHIFT;
+    double r = fma(nf, -6.93147180369123816490e-01, x);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                       // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                     // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                    // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                    // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                   // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                     // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                    // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                    // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                    // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                   // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                   // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 struct Jac {
     // d f / d x : rows 0,1 x cols {psi,vx,vy}; row 2 = e_r; rows 3..5 x cols 2..6 ; row 6 = 0
     double j0[3], j1[3];
@@ -127,13 +157,13 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
             for (int d = 0; d < ADMPC_DZMAX; d++) g[d] = 0.0;
             if (dz == 4) {
                 // hot case: 4 features -> {X0..X3, a} = 40 B per point
-#pragma unroll 2
+#pragma unroll 4
                 for (int i = 0; i < M; i++) {
                     const double *pt = blk + (size_t)i * 5;
                     const double d0 = z[0] - pt[0], d1 = z[1] - pt[1], d2 = z[2] - pt[2], d3 = z[3] - pt[3];
                     const double e0 = d0 * wv[0], e1 = d1 * wv[1], e2 = d2 * wv[2], e3 = d3 * wv[3];
                     const double s = fma(d3, e3, fma(d2, e2, fma(d1, e1, d0 * e0)));
-                    const double ka = exp(-0.5 * s) * pt[4];
+                    const double ka = exp_neg(-0.5 * s) * pt[4];
                     m += ka;
                     g[0] = fma(-ka, e0, g[0]); g[1] = fma(-ka, e1, g[1]);
                     g[2] = fma(-ka, e2, g[2]); g[3] = fma(-ka, e3, g[3]);
@@ -144,7 +174,7 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
                     double s = 0.0, e[ADMPC_DZMAX];
 #pragma unroll
                     for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) { const double dd = z[d] - pt[d]; e[d] = dd * wv[d]; s = fma(dd, e[d], s); }
-                    const double ka = exp(-0.5 * s) * pt[dz];
+                    const double ka = exp_neg(-0.5 * s) * pt[dz];
                     m += ka;
 #pragma unroll
                     for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) g[d] = fma(-ka, e[d], g[d]);
@@ -174,8 +204,8 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
 
 // One RK4 step with forward sensitivities. Sensitivity state: rows 0..5 x 7 columns [x2..x6 | u0 u1];
 // row 6 (delta) is analytic: d delta / d delta = 1, d delta / d u1 = t.
-template <bool GP>
-__global__ void __launch_bounds__(128) prepare_kernel(const Params P)
+template <bool GP, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
@@ -321,16 +351,30 @@ __global__ void __launch_bounds__(128) prepare_kernel(const Params P)
 
 void launch_prepare(const Params &P, cudaStream_t s)
 {
-    dim3 grid((P.Bp + 127) / 128, P.o.N + 1);
     if (P.o.gp_enabled) {
-        size_t sm = (size_t)P.gp.bytes;
-        static size_t configured = 0;
-        if (sm > configured) {
-            cudaFuncSetAttribute(prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            configured = sm;
+        // register budget capped at 128 so that 16 warps/SM are resident; the RK4 sensitivity state is spilled around
+        // the GP sweep (once per RK4 stage, negligible against the M-point loop).  Small models: 4 CTAs x 128 threads
+        // per SM; large models (one CTA per SM by shared memory): 512 threads.
+        const size_t sm = (size_t)P.gp.bytes;
+        if (sm <= 54 * 1024) {
+            static size_t configured = 0;
+            if (sm > configured) {
+                cudaFuncSetAttribute(prepare_kernel<true, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                configured = sm;
+            }
+            dim3 grid((P.Bp + 127) / 128, P.o.N + 1);
+            prepare_kernel<true, 128, 4><<<grid, 128, sm, s>>>(P);
+        } else {
+            static size_t configured = 0;
+            if (sm > configured) {
+                cudaFuncSetAttribute(prepare_kernel<true, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                configured = sm;
+            }
+            dim3 grid((P.Bp + 511) / 512, P.o.N + 1);
+            prepare_kernel<true, 512, 1><<<grid, 512, sm, s>>>(P);
         }
-        prepare_kernel<true><<<grid, 128, sm, s>>>(P);
     } else {
-        prepare_kernel<false><<<grid, 128, 0, s>>>(P);
+        dim3 grid((P.Bp + 127) / 128, P.o.N + 1);
+        prepare_kernel<false, 128, 1><<<grid, 128, 0, s>>>(P);
     }
 }

@@ -1,0 +1,616 @@
+// qp_warp.cu -- feedback phase, v4: ONE WARP PER MPC INSTANCE (N <= 31).
+//
+// Two lane roles alternate inside the interior-point iteration:
+//   * stage role  : lane k owns shooting node k (lane N the terminal node).  Its slice of the IPM iterate
+//                   (du, dx, pi, lam, t, slacks), the stage's cost gradient / dynamics residual data and the bounds
+//                   stay IN REGISTERS for the whole solve; residuals, barrier terms, slack / multiplier steps, step
+//                   length and the update are pure register maths + warp shuffles (neighbour nodes, reductions).
+//   * matrix role : in the horizon-sequential sweeps the 32 lanes spread over the entries of the 7x8 / 9x9 stage
+//                   matrices (P [M|rb], the Gram block M^T P M, gains, Schur complement), operands broadcast from
+//                   SHARED MEMORY, where the Riccati working set of the instance lives for the whole solve
+//                   (M=[B|A(:,2:7)], rb, K, Guu^-1, P rb, k_ff, barrier diagonals, r_x: 91 doubles per stage).
+// No global-memory traffic inside the iteration: HBM is touched once to stage the linearisation in and once to
+// write the updated iterate back (fused RTI update).
+//
+// Algorithm: HPIPM-style Mehrotra predictor-corrector IPM on the OCP-structured QP [EXT], replacing
+// FULL_CONDENSING_HPIPM (acados_solver_sim_car.c:145,688-693).  Same maths as qp_smem.cu / qp_ipm.cu; divisions by
+// t are done as multiplications by 1/t and the ratio test keeps (num, den) pairs, so results differ from the other
+// variants by rounding only.
+#include "common.cuh"
+
+#define FULL 0xffffffffu
+#define ATS(arr, row) (arr)[(size_t)(row) * Bp + i]      // SoA interface arrays [row][Bp]
+
+// stage record in shared memory (doubles)
+#define R_M 0       // 42: column c (0,1 = u0,u1 ; 2..6 = x2..x6) at c*6 + r, r < 6
+#define R_RB 42     // 7   dynamics residual ; corrector roll-out leaves ddx_{k+1} here
+#define R_K 49      // 14  K0[0..6], K1[0..6]
+#define R_GI 63     // 3
+#define R_PB 66     // 7   P_{k+1} rb_k ; the adjoint sweep leaves dpi_k here
+#define R_KF 73     // 2
+#define R_BAR 75    // 5   Rt0 Rt1 Qt6 rt0 rt1
+#define R_GX 80     // 7   rgx0..rgx5, qt6 ; corrector roll-out leaves the adjoint base vector here
+#define R_DD 87     // 3   ddu0 ddu1 ddx_k[6]
+#define R_STRIDE 91
+// scratch after the N stage records and the 8-double terminal record
+#define PSS 9       // row stride of P and column stride of W (odd: conflict-free across the 7 rows / 8 columns)
+#define X_PS 0      // 64  P_{k+1}, full symmetric, row a at a*PSS
+#define X_WS 64     // 72  W = P [M | rb], column c at c*PSS + a
+#define X_GS 136    // 32  M^T P M packed lower over the 7 M-indices (+ diagonal terms)
+#define X_PV 168    // 8   p_{k+1}
+#define X_HV 176    // 8   h = P rb + p
+#define X_GV 184    // 12  g vector: [gu0 gu1 gx2..gx6 | gx0 gx1]
+#define X_SIZE 196
+
+__device__ __forceinline__ constexpr int tri(int a, int b) { return (a >= b) ? (a * (a + 1) / 2 + b) : (b * (b + 1) / 2 + a); }
+__device__ __forceinline__ int tri_rt(int a, int b) { return (a >= b) ? (a * (a + 1) / 2 + b) : (b * (b + 1) / 2 + a); }
+__device__ __forceinline__ double sel7(const double *a, int idx)
+{
+    double v = 0.0;
+#pragma unroll
+    for (int c = 0; c < 7; c++) if (c == idx) v = a[c];
+    return v;
+}
+__device__ __forceinline__ double wsum(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double nmaxw(double a, double b) { return (a > b || a != a) ? a : b; }   // NaN-propagating
+__device__ __forceinline__ double wmax(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = nmaxw(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+struct StageState {            // registers of lane k
+    double du[2], dx[7], pi[7], lam[NC], t[NC], sl[2], su[2];
+    double lo[2], hi[2], lox, hix;     // bounds around the iterate (delta form)
+    double rd[NC], rm[NC], rgu[2], rgsl[2], rgsu[2], rgx6;
+};
+
+// barrier-modified Hessian diagonal / gradient of one stage (soft-bound slacks eliminated), it = 1/t
+__device__ __forceinline__ void barrier_w(const admpc_opts &o, bool k_ge1, const StageState &S, const double it[NC],
+                                          double Rt[2], double &Qt6, double rt[2], double &qt6)
+{
+    const double Ts = o.dt;
+    double g[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) g[c] = (S.rm[c] - S.lam[c] * S.rd[c]) * it[c];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const double Sl = S.lam[j] * it[j], Su = S.lam[3 + j] * it[3 + j];
+        const double Ssl = S.lam[6 + j] * it[6 + j], Ssu = S.lam[8 + j] * it[8 + j];
+        const double iDl = 1.0 / (Ts * o.Zl[j] + Sl + Ssl), iDu = 1.0 / (Ts * o.Zu[j] + Su + Ssu);
+        Rt[j] = Ts * o.W[7 + j] + Sl * (1.0 - Sl * iDl) + Su * (1.0 - Su * iDu);
+        const double cl = S.rgsl[j] + g[j] + g[6 + j];
+        const double cu = S.rgsu[j] + g[3 + j] + g[8 + j];
+        rt[j] = S.rgu[j] + (g[j] - Sl * cl * iDl) - (g[3 + j] - Su * cu * iDu);
+    }
+    if (k_ge1) {
+        Qt6 = Ts * o.W[6] + S.lam[2] * it[2] + S.lam[5] * it[5];
+        qt6 = S.rgx6 + g[2] - g[5];
+    } else {
+        Qt6 = Ts * o.W[6];
+        qt6 = 0.0;
+    }
+}
+
+// ---- sequential backward sweep (matrix role) -----------------------------------------------------------------------
+// Uniform instruction stream: every lane runs the same code on per-lane smem pointers set up once before the horizon
+// loop; lanes without a role in a phase recompute a neighbour's entry (same value, same address) or have their
+// store predicated off.  No divergent branches inside the loop.
+template <bool FACTOR>
+__device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, double *xs, int N, int l)
+{
+    const double Ts = o.dt, hdt = o.dt;
+    // ---- per-lane role constants ------------------------------------------------------------------------------------
+    // phase 1: entries e = cc*7 + a of W = P [M | rb]
+    int e0 = l, e1 = (l + 32 < 56) ? l + 32 : 55;
+    const int cc0 = e0 / 7, a0 = e0 - cc0 * 7, cc1 = e1 / 7, a1 = e1 - cc1 * 7;
+    const double *p1P0 = xs + X_PS + a0 * PSS, *p1P1 = xs + X_PS + a1 * PSS;
+    const int p1c0 = (cc0 < 7) ? R_M + cc0 * 6 : R_RB, p1c1 = (cc1 < 7) ? R_M + cc1 * 6 : R_RB;
+    const double m6c0 = (cc0 == 1) ? hdt : (cc0 == 6) ? 1.0 : 0.0, m6r0 = (cc0 == 7) ? 1.0 : 0.0;
+    const double m6c1 = (cc1 == 1) ? hdt : (cc1 == 6) ? 1.0 : 0.0, m6r1 = (cc1 == 7) ? 1.0 : 0.0;
+    double *p1o0 = xs + X_WS + cc0 * PSS + a0, *p1o1 = xs + X_WS + cc1 * PSS + a1;
+    const bool v70 = (cc0 == 7), v71 = (cc1 == 7);
+    // phases 2 and 4: packed lower-triangle pair (ta >= tb); lanes 28..31 shadow lane 27
+    const int lt = (l < 28) ? l : 27;
+    const int ta = (lt >= 21) ? 6 : (lt >= 15) ? 5 : (lt >= 10) ? 4 : (lt >= 6) ? 3 : (lt >= 3) ? 2 : (lt >= 1) ? 1 : 0;
+    const int tb = lt - ta * (ta + 1) / 2;
+    const int p2M = R_M + ta * 6;
+    const double *p2W = xs + X_WS + tb * PSS;
+    const double p2m6 = (ta == 1) ? hdt : (ta == 6) ? 1.0 : 0.0;
+    const bool dg = (ta == tb);
+    const double p2dm = (dg && (ta < 2 || ta == 6)) ? 1.0 : 0.0;                 // diagonal term read from the record
+    const double p2dc = (dg && ta >= 2 && ta < 6) ? Ts * sel7(o.W, ta) : 0.0;    // or a constant weight
+    const int p2dOff = R_BAR + ((ta == 6) ? 2 : (ta == 1) ? 1 : 0);
+    // phase 3: gains (lanes 0..13: j = l/7, x = l%7) and gradient vector (lanes 14..22: v = l-14)
+    const int lk = (l < 14) ? l : 13, kj = lk / 7, kx = lk - 7 * kj;
+    const double *p3a0 = (kx < 2) ? xs + X_WS + 0 * PSS + kx : xs + X_GS + tri_rt(kx, 0);
+    const double *p3a1 = (kx < 2) ? xs + X_WS + 1 * PSS + kx : xs + X_GS + tri_rt(kx, 1);
+    const bool isK = (l < 14), isG = (l >= 14 && l < 23);
+    const int gv = isG ? l - 14 : 0;
+    const int p3gb = (gv < 2) ? R_BAR + 3 + gv : (gv < 7) ? R_GX + gv : R_GX + (gv - 7);
+    const int p3M = R_M + ((gv < 7) ? gv : 0) * 6;
+    const double p3m6 = (gv == 1) ? hdt : (gv == 6) ? 1.0 : 0.0;
+    const double p3gm = (gv < 7) ? 1.0 : 0.0, p3gh = (gv < 7) ? 0.0 : 1.0;
+    const double *p3h = xs + X_HV + ((gv < 7) ? 0 : gv - 7);
+    // phase 4: Schur complement entry (ta, tb) as state indices
+    const double *p4g = (tb >= 2) ? xs + X_GS + lt : (ta >= 2) ? xs + X_WS + ta * PSS + tb : xs + X_PS + ta * PSS + tb;
+    const double p4add = (ta < 2 && dg) ? Ts * sel7(o.W, ta) : 0.0;
+    const double *p4a0 = (ta >= 2) ? xs + X_GS + tri_rt(ta, 0) : xs + X_WS + 0 * PSS + ta;
+    const double *p4a1 = (ta >= 2) ? xs + X_GS + tri_rt(ta, 1) : xs + X_WS + 1 * PSS + ta;
+    double *p4o0 = xs + X_PS + ta * PSS + tb, *p4o1 = xs + X_PS + tb * PSS + ta;
+    const int l7 = (l < 7) ? l : 6;
+    const double *p4gx = xs + X_GV + ((l7 < 2) ? 7 + l7 : l7);
+    const bool kfj = (l == 29);
+
+    // terminal: P_N = diag(We), p_N = r_x,N
+    if (FACTOR) { xs[X_PS + l] = 0.0; xs[X_PS + 32 + l] = 0.0; }
+    if (l < 7) xs[X_PV + l] = sm[N * R_STRIDE + l];
+    __syncwarp();
+    if (FACTOR && l < 7) xs[X_PS + l * PSS + l] = sel7(o.We, l);
+    __syncwarp();
+    double *st = sm + (N - 1) * R_STRIDE;
+    for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
+        if (FACTOR) {
+            // ---- phase 1: W = P_{k+1} [M | rb] ; h = W(:,7) + p ----------------------------------------------------------
+            const double rb6 = st[R_RB + 6];
+            {
+                const double *col = st + p1c0;
+                double v = p1P0[6] * fma(m6r0, rb6, m6c0), v2 = p1P0[0] * col[0];
+                v = fma(p1P0[1], col[1], v); v2 = fma(p1P0[2], col[2], v2);
+                v = fma(p1P0[3], col[3], v); v2 = fma(p1P0[4], col[4], v2);
+                v = fma(p1P0[5], col[5], v) + v2;
+                *p1o0 = v;
+                if (v70) { st[R_PB + a0] = v; xs[X_HV + a0] = v + xs[X_PV + a0]; }
+            }
+            {
+                const double *col = st + p1c1;
+                double v = p1P1[6] * fma(m6r1, rb6, m6c1), v2 = p1P1[0] * col[0];
+                v = fma(p1P1[1], col[1], v); v2 = fma(p1P1[2], col[2], v2);
+                v = fma(p1P1[3], col[3], v); v2 = fma(p1P1[4], col[4], v2);
+                v = fma(p1P1[5], col[5], v) + v2;
+                *p1o1 = v;
+                if (v71) { st[R_PB + a1] = v; xs[X_HV + a1] = v + xs[X_PV + a1]; }
+            }
+            __syncwarp();
+            // ---- phase 2: Gram block G[ta][tb] = M(:,ta)^T W(:,tb) + diagonal --------------------------------------------
+            {
+                const double *mc = st + p2M;
+                double v = p2m6 * p2W[6], v2 = mc[0] * p2W[0];
+                v = fma(mc[1], p2W[1], v); v2 = fma(mc[2], p2W[2], v2);
+                v = fma(mc[3], p2W[3], v); v2 = fma(mc[4], p2W[4], v2);
+                v = fma(mc[5], p2W[5], v) + v2;
+                v += fma(p2dm, st[p2dOff], p2dc);
+                xs[X_GS + lt] = v;
+            }
+            __syncwarp();
+        } else {
+            if (l < 7) xs[X_HV + l] = st[R_PB + l] + xs[X_PV + l];
+            __syncwarp();
+        }
+        // ---- phase 3: 2x2 pivot, gains K, gradient vector g -----------------------------------------------------------------
+        double gi00, gi01, gi11;
+        if (FACTOR) {
+            const double g00 = xs[X_GS + 0] + o.reg, g01 = xs[X_GS + 1], g11 = xs[X_GS + 2] + o.reg;
+            const double idet = 1.0 / (g00 * g11 - g01 * g01);
+            gi00 = g11 * idet; gi01 = -g01 * idet; gi11 = g00 * idet;
+            const double c0 = kj ? gi01 : gi00, c1 = kj ? gi11 : gi01;
+            const double kval = -(c0 * (*p3a0) + c1 * (*p3a1));
+            if (isK) st[R_K + l] = kval;
+            if (l == 31) { st[R_GI + 0] = gi00; st[R_GI + 1] = gi01; st[R_GI + 2] = gi11; }
+        } else {
+            gi00 = st[R_GI + 0]; gi01 = st[R_GI + 1]; gi11 = st[R_GI + 2];
+        }
+        {
+            const double *mc = st + p3M;
+            double d = p3m6 * xs[X_HV + 6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) d = fma(mc[r], xs[X_HV + r], d);
+            const double g = st[p3gb] + fma(p3gm, d, p3gh * (*p3h));
+            if (isG) xs[X_GV + gv] = g;
+        }
+        __syncwarp();
+        // ---- phase 4: Schur complement, k_ff, p_k -----------------------------------------------------------------------------
+        if (FACTOR) {
+            const double pn = (*p4g + p4add) + (*p4a0) * st[R_K + tb] + (*p4a1) * st[R_K + 7 + tb];
+            *p4o0 = pn; *p4o1 = pn;
+        }
+        {
+            const double gu0 = xs[X_GV + 0], gu1 = xs[X_GV + 1];
+            const double c0 = kfj ? gi01 : gi00, c1 = kfj ? gi11 : gi01;
+            const double kf = -(c0 * gu0 + c1 * gu1);
+            if (l == 28 || l == 29) st[R_KF + (l - 28)] = kf;
+            const double pvv = *p4gx + st[R_K + l7] * gu0 + st[R_K + 7 + l7] * gu1;
+            if (l < 7) xs[X_PV + l] = pvv;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- sequential forward roll-out (matrix role: lane r < 7 carries ddx_k[r]) -------------------------------------------
+template <bool ADJ>
+__device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, int N, int l)
+{
+    const double hdt = o.dt, Ts = o.dt;
+    const int l7 = (l < 7) ? l : 6, l6 = (l < 6) ? l : 5;
+    const double wq_l = Ts * sel7(o.W, l7), we_l = sel7(o.We, l7);
+    const double cself = (l < 2 || l == 6) ? 1.0 : 0.0, cdt = (l == 6) ? hdt : 0.0, mB = (l < 6) ? 1.0 : 0.0;
+    const double is6 = (l == 6) ? 1.0 : 0.0;
+    double dxr = 0.0;
+    double *st = sm;
+    for (int k = 0; k < N; k++, st += R_STRIDE) {
+        double dxv[7];
+#pragma unroll
+        for (int a = 0; a < 7; a++) dxv[a] = __shfl_sync(FULL, dxr, a);
+        double du0 = st[R_KF + 0], du1 = st[R_KF + 1];
+#pragma unroll
+        for (int a = 0; a < 7; a++) { du0 = fma(st[R_K + a], dxv[a], du0); du1 = fma(st[R_K + 7 + a], dxv[a], du1); }
+        if (l == 7) { st[R_DD + 0] = du0; st[R_DD + 1] = du1; st[R_DD + 2] = dxv[6]; }
+        if (ADJ && k >= 1) {
+            const double Qd = fma(is6, st[R_BAR + 2] - wq_l, wq_l);
+            const double nb = fma(Qd, dxr, st[R_GX + l7]);
+            if (l < 7) st[R_GX + l] = nb;
+        }
+        const double *mr = st + R_M + l6;        // row l of M: element (l, c) at c*6
+        double d = mr[0] * du0;
+        d = fma(mr[6], du1, d);
+#pragma unroll
+        for (int cc = 0; cc < 5; cc++) d = fma(mr[(2 + cc) * 6], dxv[2 + cc], d);
+        double v = st[R_RB + l7] + fma(cself, dxr, cdt * du1);
+        v = fma(mB, d, v);
+        dxr = (l < 7) ? v : 0.0;
+        if (ADJ && l < 7) st[R_RB + l] = dxr;           // ddx_{k+1}
+    }
+    if (ADJ && l < 7) sm[N * R_STRIDE + l] = fma(we_l, dxr, sm[N * R_STRIDE + l]);
+    __syncwarp();
+}
+
+// ---- sequential adjoint sweep: dpi_{k-1} = base_k + A_k^T dpi_k ; leaves dpi_k in the P rb slot ----------------------
+__device__ __forceinline__ void w_adjoint(double *sm, int N, int l)
+{
+    const int l7 = (l < 7) ? l : 6;
+    const int lc = (l >= 2 && l < 7) ? l : 2;
+    const double cself = (l < 2 || l == 6) ? 1.0 : 0.0, mA = (l >= 2 && l < 7) ? 1.0 : 0.0;
+    double dpr = (l < 7) ? sm[N * R_STRIDE + l] : 0.0;       // dpi_{N-1} = We dx_N + r_x,N
+    double *st = sm + (N - 1) * R_STRIDE;
+    for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
+        if (l < 7) st[R_PB + l] = dpr;
+        if (k == 0) break;
+        const double *mc = st + R_M + lc * 6;
+        double d = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) d = fma(mc[r], __shfl_sync(FULL, dpr, r), d);
+        const double v = st[R_GX + l7] + fma(cself, dpr, mA * d);     // A(:,0..1) = e0,e1 ; A[6][6] = 1
+        dpr = (l < 7) ? v : 0.0;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
+{
+    extern __shared__ __align__(16) double smw[];
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const int l = threadIdx.x;
+    const int i = blockIdx.x;                    // one instance per warp
+    double *sm = smw;
+    double *xs = smw + N * R_STRIDE + 8;
+    const double Ts = o.dt, hdt = o.dt;
+    if (P.lin_bad[i]) {                          // NaN/Inf in the linearisation: ACADOS_FAILURE, iterate untouched
+        if (l == 0) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+        return;
+    }
+    // ---- stage M into shared memory ------------------------------------------------------------------------------------
+    for (int e = l; e < 42 * N; e += 32) {
+        const int k = e / 42, w = e - k * 42;
+        const int cc = w / 6, r = w - cc * 6;
+        const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp;
+        sm[k * R_STRIDE + R_M + w] = (cc < 2) ? ATS(lin, LIN_B + r * 2 + cc) : ATS(lin, LIN_A + r * 5 + (cc - 2));
+    }
+    // ---- stage role: load this node's data, cold start ---------------------------------------------------------------------
+    const int k = l;
+    const bool isst = k < N, isterm = (k == N);
+    StageState S;
+#pragma unroll
+    for (int a = 0; a < 7; a++) { S.dx[a] = 0.0; S.pi[a] = 0.0; }
+#pragma unroll
+    for (int c = 0; c < NC; c++) { S.lam[c] = 0.0; S.t[c] = 1.0; S.rd[c] = 0.0; S.rm[c] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 2; j++) { S.du[j] = 0.0; S.sl[j] = 0.0; S.su[j] = 0.0; S.lo[j] = -1.0; S.hi[j] = 1.0; S.rgu[j] = S.rgsl[j] = S.rgsu[j] = 0.0; }
+    S.lox = -1.0; S.hix = 1.0; S.rgx6 = 0.0;
+    if (isst || isterm) {
+        if (isst) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const double cur = ATS(P.ub, k * 2 + j);
+                S.lo[j] = o.lbu[j] - cur; S.hi[j] = o.ubu[j] - cur;
+            }
+            const double cur6 = ATS(P.xb, k * 7 + 6);
+            S.lox = o.lbx - cur6; S.hix = o.ubx - cur6;
+        }
+        if (k == 0) {
+#pragma unroll
+            for (int a = 0; a < 7; a++) S.dx[a] = ATS(P.x0, a) - ATS(P.xb, a);     // x0 eliminated (nbxe_0 = 7)
+        }
+    }
+    if (isst) {
+        // cold start: primal 0 pushed thr0 inside its box, t from the box, lam = mu0 / t
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            if (j == 2 && k == 0) continue;
+            const double lo = (j < 2) ? S.lo[j] : S.lox, hi = (j < 2) ? S.hi[j] : S.hix;
+            double v = 0.0;
+            if (v - lo < o.thr0) {
+                if (hi - v < o.thr0) v = 0.5 * (lo + hi);
+                else v = lo + o.thr0;
+            } else if (hi - v < o.thr0) v = hi - o.thr0;
+            if (j < 2) S.du[j] = v; else S.dx[6] = v;
+            const double tl = fmax(o.thr0, v - lo), tu = fmax(o.thr0, hi - v);
+            S.t[j] = tl; S.t[3 + j] = tu;
+            S.lam[j] = o.mu0 / tl; S.lam[3 + j] = o.mu0 / tu;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            S.t[6 + j] = o.thr0; S.t[8 + j] = o.thr0;
+            S.lam[6 + j] = o.mu0 / o.thr0; S.lam[8 + j] = o.mu0 / o.thr0;
+        }
+    }
+    __syncwarp();
+
+    const double inv_nc = 1.0 / (double)(NC * N - 2);
+    int status = 1, iter = 0;
+    double res0 = 0, res1 = 0, res2 = 0, res3 = 0;
+    for (iter = 0;; iter++) {
+        // ================= residuals of the current point (stage role) ===================================================
+        double pim[7], dxn[7], it[NC];
+        // b_k, q_k, r_k are re-read each iteration (L2-resident) instead of occupying 32 registers for the whole solve
+        double lb[7], lq[7], lr[2];
+        {
+            const double *lin = P.lin + (size_t)((isst || isterm) ? k : 0) * LIN_ROWS * Bp;
+#pragma unroll
+            for (int a = 0; a < 7; a++) { lq[a] = ATS(lin, LIN_q + a); lb[a] = ATS(lin, LIN_b + a); }
+            lr[0] = ATS(lin, LIN_r + 0); lr[1] = ATS(lin, LIN_r + 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            const double up = __shfl_up_sync(FULL, S.pi[a], 1);
+            pim[a] = (k >= 1) ? up : 0.0;
+            dxn[a] = __shfl_down_sync(FULL, S.dx[a], 1);
+        }
+        double ng = 0, nb = 0, nd = 0, nm = 0, summ = 0;
+        double *st = sm + (isst ? k : 0) * R_STRIDE;
+        if (isst) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) it[c] = 1.0 / S.t[c];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                double g = Ts * o.W[7 + j] * S.du[j] + lr[j] - S.lam[j] + S.lam[3 + j];
+#pragma unroll
+                for (int r = 0; r < 6; r++) g = fma(st[R_M + j * 6 + r], S.pi[r], g);
+                if (j == 1) g = fma(hdt, S.pi[6], g);
+                S.rgu[j] = g;
+                S.rgsl[j] = Ts * o.zl[j] + Ts * o.Zl[j] * S.sl[j] - S.lam[j] - S.lam[6 + j];
+                S.rgsu[j] = Ts * o.zu[j] + Ts * o.Zu[j] * S.su[j] - S.lam[3 + j] - S.lam[8 + j];
+                ng = nmaxw(ng, nmaxw(fabs(g), nmaxw(fabs(S.rgsl[j]), fabs(S.rgsu[j]))));
+                S.rd[j] = S.t[j] - (S.du[j] - S.lo[j] + S.sl[j]);
+                S.rd[3 + j] = S.t[3 + j] - (S.hi[j] - S.du[j] + S.su[j]);
+                S.rd[6 + j] = S.t[6 + j] - S.sl[j];
+                S.rd[8 + j] = S.t[8 + j] - S.su[j];
+                nd = nmaxw(nd, nmaxw(nmaxw(fabs(S.rd[j]), fabs(S.rd[3 + j])), nmaxw(fabs(S.rd[6 + j]), fabs(S.rd[8 + j]))));
+            }
+            if (k >= 1) {
+                S.rd[2] = S.t[2] - (S.dx[6] - S.lox);
+                S.rd[5] = S.t[5] - (S.hix - S.dx[6]);
+                nd = nmaxw(nd, nmaxw(fabs(S.rd[2]), fabs(S.rd[5])));
+            } else {
+                S.rd[2] = 0.0; S.rd[5] = 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                double v = lb[r] - dxn[r] + ((r < 2) ? S.dx[r] : 0.0);
+                v = fma(st[R_M + 0 * 6 + r], S.du[0], v);
+                v = fma(st[R_M + 1 * 6 + r], S.du[1], v);
+#pragma unroll
+                for (int cc = 0; cc < 5; cc++) v = fma(st[R_M + (2 + cc) * 6 + r], S.dx[2 + cc], v);
+                st[R_RB + r] = v;
+                nb = nmaxw(nb, fabs(v));
+            }
+            {
+                const double v = lb[6] - dxn[6] + S.dx[6] + hdt * S.du[1];
+                st[R_RB + 6] = v;
+                nb = nmaxw(nb, fabs(v));
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const bool on = !((c == 2 || c == 5) && k == 0);
+                S.rm[c] = on ? S.lam[c] * S.t[c] : 0.0;
+                nm = nmaxw(nm, fabs(S.rm[c]));
+                summ += S.rm[c];
+            }
+            S.rgx6 = 0.0;
+            if (k >= 1) {
+#pragma unroll
+                for (int a = 0; a < 7; a++) {
+                    double g = Ts * o.W[a] * S.dx[a] + lq[a] - pim[a];
+                    if (a < 2) g += S.pi[a];
+                    else {
+#pragma unroll
+                        for (int r = 0; r < 6; r++) g = fma(st[R_M + a * 6 + r], S.pi[r], g);
+                        if (a == 6) g += S.pi[6] - S.lam[2] + S.lam[5];
+                    }
+                    if (a < 6) st[R_GX + a] = g; else S.rgx6 = g;
+                    ng = nmaxw(ng, fabs(g));
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 6; a++) st[R_GX + a] = 0.0;
+            }
+            double Rt[2], Qt6, rt[2], qt6;
+            barrier_w(o, k >= 1, S, it, Rt, Qt6, rt, qt6);
+            st[R_BAR + 0] = Rt[0]; st[R_BAR + 1] = Rt[1]; st[R_BAR + 2] = Qt6;
+            st[R_BAR + 3] = rt[0]; st[R_BAR + 4] = rt[1]; st[R_GX + 6] = qt6;
+        } else if (isterm) {
+#pragma unroll
+            for (int a = 0; a < 7; a++) {
+                const double g = o.We[a] * S.dx[a] + lq[a] - pim[a];
+                sm[N * R_STRIDE + a] = g;
+                ng = nmaxw(ng, fabs(g));
+            }
+        }
+        ng = wmax(ng); nb = wmax(nb); nd = wmax(nd); nm = wmax(nm); summ = wsum(summ);
+        res0 = ng; res1 = nb; res2 = nd; res3 = nm;
+        if (!(isfinite(ng) && isfinite(nb) && isfinite(nd) && isfinite(nm))) { status = 3; break; }
+        if (ng < o.tol_stat && nb < o.tol_eq && nd < o.tol_ineq && nm < o.tol_comp) { status = 0; break; }
+        if (iter >= o.iter_max) { status = 1; break; }
+        const double mu = summ * inv_nc;
+        __syncwarp();
+
+        // ================= predictor ===================================================================================
+        w_backward<true>(o, sm, xs, N, l);
+        w_forward<false>(o, sm, N, l);
+        double dsl[2], dsu[2], dtv[NC], dlv[NC];
+        double an = 1.0, ad = 1.0;          // step length as a ratio an/ad (<= 1)
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            // pass 0: affine step -> mu_aff, sigma, corrected rhs ; pass 1: final step -> alpha
+            an = 1.0; ad = 1.0; s1 = 0.0; s2 = 0.0;
+            if (isst) {
+                const double du0 = st[R_DD + 0], du1 = st[R_DD + 1], dx6 = st[R_DD + 2];
+                double gq[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++) gq[c] = (S.rm[c] - S.lam[c] * S.rd[c]) * it[c];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const double duj = (j == 0) ? du0 : du1;
+                    const double Sl = S.lam[j] * it[j], Su = S.lam[3 + j] * it[3 + j];
+                    const double Ssl = S.lam[6 + j] * it[6 + j], Ssu = S.lam[8 + j] * it[8 + j];
+                    const double iDl = 1.0 / (Ts * o.Zl[j] + Sl + Ssl), iDu = 1.0 / (Ts * o.Zu[j] + Su + Ssu);
+                    const double cl = S.rgsl[j] + gq[j] + gq[6 + j];
+                    const double cu = S.rgsu[j] + gq[3 + j] + gq[8 + j];
+                    dsl[j] = -(cl + Sl * duj) * iDl;
+                    dsu[j] = -(cu - Su * duj) * iDu;
+                    dtv[j] = duj + dsl[j] - S.rd[j];
+                    dtv[3 + j] = -duj + dsu[j] - S.rd[3 + j];
+                    dtv[6 + j] = dsl[j] - S.rd[6 + j];
+                    dtv[8 + j] = dsu[j] - S.rd[8 + j];
+                }
+                if (k >= 1) { dtv[2] = dx6 - S.rd[2]; dtv[5] = -dx6 - S.rd[5]; }
+                else { dtv[2] = 0.0; dtv[5] = 0.0; }
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const bool on = !((c == 2 || c == 5) && k == 0);
+                    dlv[c] = on ? -(S.rm[c] + S.lam[c] * dtv[c]) * it[c] : 0.0;
+                    if (on) {
+                        // ratio test without divisions: keep the smallest lam/(-dlam), t/(-dt) as a pair
+                        if (dlv[c] < 0.0 && S.lam[c] * ad < an * (-dlv[c])) { an = S.lam[c]; ad = -dlv[c]; }
+                        if (dtv[c] < 0.0 && S.t[c] * ad < an * (-dtv[c])) { an = S.t[c]; ad = -dtv[c]; }
+                        s1 += S.lam[c] * dtv[c] + S.t[c] * dlv[c];
+                        s2 += dlv[c] * dtv[c];
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                const double bn = __shfl_xor_sync(FULL, an, off), bd = __shfl_xor_sync(FULL, ad, off);
+                if (bn * ad < an * bd) { an = bn; ad = bd; }
+            }
+            an = __shfl_sync(FULL, an, 0); ad = __shfl_sync(FULL, ad, 0);     // one representative pair for all lanes
+            if (pass == 0) {
+                s1 = wsum(s1); s2 = wsum(s2);
+                const double a_aff = an / ad;
+                const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
+                double sigma = mu_aff / mu;
+                sigma = sigma * sigma * sigma;
+                const double sigmu = sigma * mu;
+                if (isst) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        const bool on = !((c == 2 || c == 5) && k == 0);
+                        S.rm[c] = on ? S.rm[c] + dlv[c] * dtv[c] - sigmu : 0.0;
+                    }
+                    double Rt[2], Qt6, rt[2], qt6;
+                    barrier_w(o, k >= 1, S, it, Rt, Qt6, rt, qt6);
+                    st[R_BAR + 3] = rt[0]; st[R_BAR + 4] = rt[1]; st[R_GX + 6] = qt6;
+                }
+                __syncwarp();
+                // ================= corrector ===========================================================================
+                w_backward<false>(o, sm, xs, N, l);
+                w_forward<true>(o, sm, N, l);
+            }
+        }
+        double alpha = an / ad;
+        if (alpha < o.alpha_min) { status = 2; break; }
+        if (alpha < 1.0) alpha *= 0.995;
+        // ================= update (stage role); pi and dx wait for the adjoint sweep ==========================================
+        if (isst) {
+            const double du0 = st[R_DD + 0], du1 = st[R_DD + 1];
+            S.du[0] += alpha * du0; S.du[1] += alpha * du1;
+#pragma unroll
+            for (int j = 0; j < 2; j++) { S.sl[j] += alpha * dsl[j]; S.su[j] += alpha * dsu[j]; }
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                if ((c == 2 || c == 5) && k == 0) continue;
+                S.lam[c] = fmax(S.lam[c] + alpha * dlv[c], o.lam_min);
+                S.t[c] = fmax(S.t[c] + alpha * dtv[c], o.t_min);
+            }
+        }
+        w_adjoint(sm, N, l);
+        if (isst) {
+#pragma unroll
+            for (int a = 0; a < 7; a++) S.pi[a] += alpha * st[R_PB + a];
+        }
+        if ((isst || isterm) && k >= 1) {
+            const double *prev = sm + (k - 1) * R_STRIDE;      // ddx_k was left in record k-1
+#pragma unroll
+            for (int a = 0; a < 7; a++) S.dx[a] += alpha * prev[R_RB + a];
+        }
+        __syncwarp();
+    }
+    // ---- epilogue: statuses + fused RTI update (full step; duals <- QP duals) --------------------------------------------
+    const int qps = (status == 0) ? 0 : ((status == 1) ? 2 : ((status == 2) ? 3 : 1));   // hpipm -> acados numbering
+    const int nlp_status = (qps == 0 || qps == 2) ? 0 : 4;
+    if (l == 0) {
+        P.qp_status[i] = qps; P.qp_iter[i] = iter; P.status[i] = nlp_status;
+        ATS(P.res_out, 0) = res0; ATS(P.res_out, 1) = res1; ATS(P.res_out, 2) = res2; ATS(P.res_out, 3) = res3;
+    }
+    if (nlp_status == 0 && (isst || isterm)) {
+#pragma unroll
+        for (int a = 0; a < 7; a++) ATS(P.xb, k * 7 + a) += S.dx[a];
+        if (isst) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                ATS(P.ub, k * 2 + j) += S.du[j];
+                ATS(P.slb, k * 2 + j) = S.sl[j];
+                ATS(P.sub, k * 2 + j) = S.su[j];
+            }
+#pragma unroll
+            for (int a = 0; a < 7; a++) ATS(P.pib, k * 7 + a) = S.pi[a];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const bool on = !((c == 2 || c == 5) && k == 0);
+                ATS(P.lamb, k * NC + c) = on ? S.lam[c] : 0.0;
+                ATS(P.tb, k * NC + c) = on ? S.t[c] : 1.0;
+            }
+        }
+    }
+}
+
+bool launch_qp_warp(const Params &P, cudaStream_t s)
+{
+    const int N = P.o.N;
+    if (N > 31) return false;
+    const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE) * sizeof(double);
+    static size_t configured = 0;
+    if (sm > configured) {
+        cudaFuncSetAttribute(qp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        configured = sm;
+    }
+    qp_warp_kernel<<<P.B, 32, sm, s>>>(P);
+    return true;
+}
