@@ -4,4 +4,4 @@ Host side: numpy + ctypes over the C ABI in include/admpc.h.  The compute path i
 libadmpc_b200.so (ad_mpc_b200/csrc); nothing here falls back to the CPU.
 """
 from . import _lib  # noqa: F401
-from .solver import AcadosOcpSolverB200, BatchSolver, PinnedArray, default_opts  # noqa: F401
+from .solver import AcadosOcpSolverB200, BatchSolver, PinnedArray, PipelinedSolver, default_opts  # noqa: F401

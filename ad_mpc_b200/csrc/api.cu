@@ -436,8 +436,26 @@ extern "C" int admpc_batch_get_lin(admpc_batch *h, double *A, double *Bm, double
     return 0;
 }
 
+static int solve_host_enqueue(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
+                              double *u_out, double *x_out, int *status_out);
+
+extern "C" int admpc_batch_solve_host_async(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
+                                            double *u_out, double *x_out, int *status_out)
+{
+    return solve_host_enqueue(h, x0, yref, p_scalar, u_out, x_out, status_out);
+}
+
 extern "C" int admpc_batch_solve_host(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
                                       double *u_out, double *x_out, int *status_out)
+{
+    int r = solve_host_enqueue(h, x0, yref, p_scalar, u_out, x_out, status_out);
+    if (r) return r;
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int solve_host_enqueue(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
+                              double *u_out, double *x_out, int *status_out)
 {
     if (!h) return ADMPC_E_ARG;
     int r = 0;
@@ -448,7 +466,6 @@ extern "C" int admpc_batch_solve_host(admpc_batch *h, const double *x0, const do
     if (u_out && (r = get_rows_async(h, h->P.ub, h->stage_u, u_out, h->P.o.N * 2))) return r;
     if (x_out && (r = get_rows_async(h, h->P.xb, h->stage_x, x_out, (h->P.o.N + 1) * 7))) return r;
     if (status_out) CUDA_CHECK_RET(cudaMemcpyAsync(status_out, h->P.status, (size_t)h->P.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

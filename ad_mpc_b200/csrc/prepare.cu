@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
 #pragma unroll
     for (int c = 0; c < 7; c++) { kx[c] = 0.0; ax[c] = 0.0; }
 
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {          // not unrolled: 4 copies of the GP sweep would not fit the instruction cache
         const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
         const double bs = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
         const double ha = h * as;

@@ -211,6 +211,46 @@ class BatchSolver:
         return int(self.L.admpc_batch_kernel_launches(self.h))
 
 
+class PipelinedSolver:
+    """B instances split into `chunks` BatchSolver handles (one CUDA stream each): the H2D copy of chunk c+1, the solve
+    of chunk c and the D2H copy of chunk c-1 overlap.  Host buffers should be pinned (PinnedArray) for real overlap."""
+
+    def __init__(self, B, opts=None, device=0, N=None, chunks=4):
+        from .shard import shard_range
+        self.B = int(B)
+        self.ranges = [shard_range(self.B, c, chunks) for c in range(chunks) if shard_range(self.B, c, chunks)[1] > shard_range(self.B, c, chunks)[0]]
+        self.parts = [BatchSolver(hi - lo, opts=opts, device=device, N=N) for lo, hi in self.ranges]
+        self.N = self.parts[0].N
+        self.L = self.parts[0].L
+
+    def set_gp(self, model, stage0_trigger=1):
+        for s in self.parts:
+            s.set_gp(model, stage0_trigger)
+
+    def set_iterate(self, x=None, u=None):
+        for s, (lo, hi) in zip(self.parts, self.ranges):
+            s.set_iterate(None if x is None else x[lo:hi], None if u is None else u[lo:hi])
+
+    def wait(self):
+        for s in self.parts:
+            s.wait()
+
+    def solve_batch(self, x0, yref, p, u_out, x_out, status_out):
+        """x0[B,7] yref[B,N*9+7] p[B] -> u_out[B,N,2] x_out[B,N+1,7] status_out[B] (all C-contiguous float64/int32)."""
+        for s, (lo, hi) in zip(self.parts, self.ranges):
+            check(self.L.admpc_batch_solve_host_async(s.h, _dp(x0[lo:hi]), _dp(yref[lo:hi]), _dp(p[lo:hi]), _dp(u_out[lo:hi]),
+                                                     _dp(x_out[lo:hi]), _ip(status_out[lo:hi])), "solve_host_async")
+        self.wait()
+        return u_out, x_out, status_out
+
+    def kernel_launches(self):
+        return sum(s.kernel_launches() for s in self.parts)
+
+    def close(self):
+        for s in self.parts:
+            s.close()
+
+
 class AcadosOcpSolverB200:
     """Drop-in for the ``AcadosOcpSolver`` object used by AD3DOptimizer (single instance, acados-shim symbols)."""
 

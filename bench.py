@@ -141,7 +141,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    sample = 2048
+    sample = 4096
     cores = os.cpu_count() or 1
     times = []
     for s in range(args.warmup + args.steps):
@@ -257,6 +257,11 @@ def run_ours(args):
     value = B * world / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with pinned HOST buffers ("e2e") --------------------------------
+    # PipelinedSolver = the public batched call: 4 chunks on 4 streams so that H2D / solve / D2H overlap.
+    from ad_mpc_b200 import PipelinedSolver
+    s.set_profiling(False)
+    ps = PipelinedSolver(B, opts, device=local, chunks=4)
+    ps.set_gp(model)
     pin = {k: PinnedArray(v.shape) for k, v in (("x0", batch["x0"]), ("yref", batch["yref"]))}
     pin["x0"].array[:] = batch["x0"]; pin["yref"].array[:] = batch["yref"]
     pin_p = PinnedArray((B,)); pin_p.array[:] = batch["p"][:, 0]
@@ -264,14 +269,13 @@ def run_ours(args):
     out_st = PinnedArray((B,), dtype=np.int32)
     e2e_ms = []
     for it in range(max(args.warmup, 3) + args.steps):
-        s.set_iterate(x_init, u_init)
-        s.wait()
+        ps.set_iterate(x_init, u_init)
+        ps.wait()
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        s.timer_start()
-        s.solve_batch(pin["x0"].array, pin["yref"].array, pin_p.array, out_u.array, out_x.array, out_st.array)
-        ms = s.timer_stop()
+        ps.solve_batch(pin["x0"].array, pin["yref"].array, pin_p.array, out_u.array, out_x.array, out_st.array)
+        ms = (time.perf_counter() - t0) * 1e3          # host clock around the blocking public call (4 streams inside)
         if it >= max(args.warmup, 3):
             e2e_ms.append(ms)
     e_local = sum(e2e_ms)
@@ -285,6 +289,30 @@ def run_ours(args):
     h2d = int(batch["x0"].nbytes + batch["yref"].nbytes + B * 8)
     d2h = int(B * N * 2 * 8 + B * (N + 1) * 7 * 8 + B * 4)
     assert np.array_equal(out_st.array, st)
+    ref_u = s.get_u()
+    assert np.array_equal(out_u.array, ref_u), "pipelined e2e result differs from the resident-input result"
+    ps.close()
+
+    # ---- single-instance latency through the acados-shim symbols (cfg 1: nominal, N=20, B=1) ---------------------
+    single_ms = []
+    if rank == 0:
+        from ad_mpc_b200 import AcadosOcpSolverB200
+        from ad_mpc_b200 import workload as wl
+        b1 = wl.make_batch(1, N, seed=20261, p=0.0)
+        cap = AcadosOcpSolverB200(default_opts(N))
+        for j in range(N):
+            cap.set(j, "yref", b1["yref"][0][j * 9:(j + 1) * 9])
+        cap.set(N, "yref", b1["yref"][0][N * 9:])
+        for j in range(N + 1):
+            cap.set(j, "x", b1["x_init"][0, j])
+        x0c = b1["x0"][0].copy()
+        for it in range(30):
+            cap.set(0, "lbx", x0c); cap.set(0, "ubx", x0c)
+            t0 = time.perf_counter()
+            cap.solve()
+            single_ms.append((time.perf_counter() - t0) * 1e3)
+            x0c = cap.get(1, "x")
+        single_ms = sorted(single_ms[5:])
 
     if rank == 0:
         # ---- roofline of the dominant kernel (FP64 DFMA pipe) ------------------------------------
@@ -307,7 +335,7 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        roofline = {"bound": "fp64", "kernel": {"prepare": "prepare_kernel<GP>", "qp": "qp_ipm_kernel"}[dom],
+        roofline = {"bound": "fp64", "kernel": {"prepare": "prepare_kernel<GP>", "qp": "qp_warp_kernel"}[dom],
                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,
                     "peak_source": "DFMA microbenchmark admpc_measure_fp64_peak run in this process (MEASURED_PEAKS.json "
@@ -318,10 +346,12 @@ def run_ours(args):
                     "hbm": {"algorithmic_GBps": algorithmic_bytes(N) * B / (ms_per_step * 1e-3) / 1e9, "peak_GBps": hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
         # ---- CPU baseline on this box's host cores ----------------------------------------------------------
-        sample = 2048
-        rate, secs, cores = cpu_oracle_rate(sample, reps=2)
+        sample = 8192
+        rate0, secs0, cores = cpu_oracle_rate(1024)                      # calibrate, then size the sample to ~12 s
+        reps = max(1, min(40, int(12.0 * rate0 / sample)))
+        rate, secs, cores = cpu_oracle_rate(sample, reps=reps)
         cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": "%d instances of the cfg3 workload x2, OpenMP over instances, %.1f s" % (sample, secs),
+               "sample": "%d instances of the cfg3 workload x%d, OpenMP over instances, %.1f s" % (sample, reps, secs),
                "note": "CPU restatement of the acados path (oracle/); acados itself cannot be built here"}
         e2e_sorted = sorted(e2e_ms)
         line = {"metric": "SQP-RTI MPC solves/sec (N=20, GP-augmented)", "value": value, "unit": "solves/s",
@@ -332,7 +362,10 @@ def run_ours(args):
                         "p50_ms_per_batch_call": e2e_sorted[len(e2e_sorted) // 2]},
                 "gpu_launches": counted, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_s_timed_region": wall,
-                "latency": {"p50_ms_per_batch_solve": sorted(step_ms)[len(step_ms) // 2], "batch": B}}
+                "latency": {"p50_ms_per_batch_solve": sorted(step_ms)[len(step_ms) // 2], "batch": B,
+                            "single_instance_p50_ms": single_ms[len(single_ms) // 2] if single_ms else None,
+                            "single_instance_note": "cfg1: nominal N=20, B=1 through sim_car_acados_solve (host clock, "
+                                                    "includes H2D/D2H of the one instance)"}}
         print(json.dumps(line), flush=True)
     barrier()
     s.close()

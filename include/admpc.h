@@ -139,6 +139,10 @@ int admpc_batch_get_lin(admpc_batch *h, double *A, double *Bm, double *b, double
  * replacement of the 3N+5 ctypes calls of $A/ad_3d_optimizer.py:420-465. Any output pointer may be NULL. */
 int admpc_batch_solve_host(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
                            double *u_out, double *x_out, int *status_out);
+/* same, but returns as soon as everything is enqueued on the handle's stream (pinned host buffers required for true
+ * asynchrony); complete with admpc_batch_wait.  Several handles (one stream each) pipeline H2D / solve / D2H. */
+int admpc_batch_solve_host_async(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
+                                 double *u_out, double *x_out, int *status_out);
 
 /* instrumentation: device time (CUDA events on the handle's stream) of the last solve and of its kernels.
  * name: "solve" | "prepare" | "qp" | "h2d" | "d2h" ; returns milliseconds in *ms. Needs admpc_batch_set_profiling(1)
