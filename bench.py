@@ -168,6 +168,7 @@ def run_ours(args):
     from ad_mpc_b200 import BatchSolver, PinnedArray, default_opts, _lib
     import ctypes as C
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
     dist = None
     if world > 1:
         import torch.distributed as dist          # plumbing only: rendezvous, barrier, max over ranks
@@ -346,13 +347,15 @@ def run_ours(args):
                     "hbm": {"algorithmic_GBps": algorithmic_bytes(N) * B / (ms_per_step * 1e-3) / 1e9, "peak_GBps": hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
         # ---- CPU baseline on this box's host cores ----------------------------------------------------------
-        sample = 8192
-        rate0, secs0, cores = cpu_oracle_rate(1024)                      # calibrate, then size the sample to ~12 s
-        reps = max(1, min(40, int(12.0 * rate0 / sample)))
-        rate, secs, cores = cpu_oracle_rate(sample, reps=reps)
-        cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": "%d instances of the cfg3 workload x%d, OpenMP over instances, %.1f s" % (sample, reps, secs),
-               "note": "CPU restatement of the acados path (oracle/); acados itself cannot be built here"}
+        cpu = None
+        if world == 1:                                                       # reported at N=1 only
+            sample = 8192
+            rate0, secs0, cores = cpu_oracle_rate(1024)                      # calibrate, then size the sample to ~12 s
+            reps = max(1, min(40, int(12.0 * rate0 / sample)))
+            rate, secs, cores = cpu_oracle_rate(sample, reps=reps)
+            cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+                   "sample": "%d instances of the cfg3 workload x%d, OpenMP over instances, %.1f s" % (sample, reps, secs),
+                   "note": "CPU restatement of the acados path (oracle/); acados itself cannot be built here"}
         e2e_sorted = sorted(e2e_ms)
         line = {"metric": "SQP-RTI MPC solves/sec (N=20, GP-augmented)", "value": value, "unit": "solves/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
