@@ -21,26 +21,29 @@
 #define FULL 0xffffffffu
 #define ATS(arr, row) (arr)[(size_t)(row) * Bp + i]      // SoA interface arrays [row][Bp]
 
-// stage record in shared memory (doubles)
+// stage record in shared memory (doubles).  Every vector-loaded block starts at an even offset and the stride is
+// even, so 16-byte LDS.128 (double2) loads are legal everywhere.
 #define R_M 0       // 42: column c (0,1 = u0,u1 ; 2..6 = x2..x6) at c*6 + r, r < 6
 #define R_RB 42     // 7   dynamics residual ; corrector roll-out leaves ddx_{k+1} here
-#define R_K 49      // 14  K0[0..6], K1[0..6]
-#define R_GI 63     // 3
-#define R_PB 66     // 7   P_{k+1} rb_k ; the adjoint sweep leaves dpi_k here
-#define R_KF 73     // 2
-#define R_BAR 75    // 5   Rt0 Rt1 Qt6 rt0 rt1
-#define R_GX 80     // 7   rgx0..rgx5, qt6 ; corrector roll-out leaves the adjoint base vector here
-#define R_DD 87     // 3   ddu0 ddu1 ddx_k[6]
-#define R_STRIDE 91
+#define R_K0 50     // 7   first row of the gain K
+#define R_K1 58     // 7   second row
+#define R_GI 66     // 3   Guu^-1
+#define R_PB 70     // 7   P_{k+1} rb_k ; the adjoint sweep leaves dpi_k here
+#define R_KF 78     // 2
+#define R_BAR 80    // 5   Rt0 Rt1 Qt6 rt0 rt1
+#define R_GX 86     // 7   rgx0..rgx5, qt6 ; corrector roll-out leaves the adjoint base vector here
+#define R_DD 94     // 3   ddu0 ddu1 ddx_k[6]
+#define R_STRIDE 98
 // scratch after the N stage records and the 8-double terminal record
-#define PSS 9       // row stride of P and column stride of W (odd: conflict-free across the 7 rows / 8 columns)
-#define X_PS 0      // 64  P_{k+1}, full symmetric, row a at a*PSS
-#define X_WS 64     // 72  W = P [M | rb], column c at c*PSS + a
-#define X_GS 136    // 32  M^T P M packed lower over the 7 M-indices (+ diagonal terms)
-#define X_PV 168    // 8   p_{k+1}
-#define X_HV 176    // 8   h = P rb + p
-#define X_GV 184    // 12  g vector: [gu0 gu1 gx2..gx6 | gx0 gx1]
-#define X_SIZE 196
+#define PSS 10      // row stride of P / column stride of W: even (LDS.128) and conflict-free over 7 rows (80 B)
+#define X_PS 0      // 72  P_{k+1}, full symmetric, row a at a*PSS
+#define X_WS 72     // 80  W = P [M | rb], column c at c*PSS + a
+#define X_GS 152    // 32  M^T P M packed lower over the 7 M-indices (+ diagonal terms)
+#define X_PV 184    // 8   p_{k+1}
+#define X_HV 192    // 8   h = P rb + p
+#define X_GV 200    // 12  g vector: [gu0 gu1 gx2..gx6 | gx0 gx1]
+#define X_DX 212    // 16  double-buffered broadcast of the roll-out / adjoint state
+#define X_SIZE 228
 
 __device__ __forceinline__ constexpr int tri(int a, int b) { return (a >= b) ? (a * (a + 1) / 2 + b) : (b * (b + 1) / 2 + a); }
 __device__ __forceinline__ int tri_rt(int a, int b) { return (a >= b) ? (a * (a + 1) / 2 + b) : (b * (b + 1) / 2 + a); }
@@ -98,17 +101,28 @@ __device__ __forceinline__ void barrier_w(const admpc_opts &o, bool k_ge1, const
     }
 }
 
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+// 7-term dot product a[0..6] . b[0..6] with a, b 16-byte aligned, two accumulation chains, b6 scaled separately
+__device__ __forceinline__ double dot6(const double *a, const double *b)
+{
+    const double2 a0 = ld2(a), a1 = ld2(a + 2), a2 = ld2(a + 4);
+    const double2 b0 = ld2(b), b1 = ld2(b + 2), b2 = ld2(b + 4);
+    double v = a0.x * b0.x, w = a0.y * b0.y;
+    v = fma(a1.x, b1.x, v); w = fma(a1.y, b1.y, w);
+    v = fma(a2.x, b2.x, v); w = fma(a2.y, b2.y, w);
+    return v + w;
+}
+
 // ---- sequential backward sweep (matrix role) -----------------------------------------------------------------------
-// Uniform instruction stream: every lane runs the same code on per-lane smem pointers set up once before the horizon
-// loop; lanes without a role in a phase recompute a neighbour's entry (same value, same address) or have their
-// store predicated off.  No divergent branches inside the loop.
+// Uniform instruction stream: every lane runs the same code on per-lane shared-memory pointers set up once before the
+// horizon loop; lanes without a role in a phase shadow a neighbour (same value, same address) or have their store
+// predicated off.  Three __syncwarp phases per stage when factorising, two in the vector-only (corrector) sweep.
 template <bool FACTOR>
 __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
     const double Ts = o.dt, hdt = o.dt;
-    // ---- per-lane role constants ------------------------------------------------------------------------------------
     // phase 1: entries e = cc*7 + a of W = P [M | rb]
-    int e0 = l, e1 = (l + 32 < 56) ? l + 32 : 55;
+    const int e0 = l, e1 = (l + 32 < 56) ? l + 32 : 55;
     const int cc0 = e0 / 7, a0 = e0 - cc0 * 7, cc1 = e1 / 7, a1 = e1 - cc1 * 7;
     const double *p1P0 = xs + X_PS + a0 * PSS, *p1P1 = xs + X_PS + a1 * PSS;
     const int p1c0 = (cc0 < 7) ? R_M + cc0 * 6 : R_RB, p1c1 = (cc1 < 7) ? R_M + cc1 * 6 : R_RB;
@@ -116,7 +130,7 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     const double m6c1 = (cc1 == 1) ? hdt : (cc1 == 6) ? 1.0 : 0.0, m6r1 = (cc1 == 7) ? 1.0 : 0.0;
     double *p1o0 = xs + X_WS + cc0 * PSS + a0, *p1o1 = xs + X_WS + cc1 * PSS + a1;
     const bool v70 = (cc0 == 7), v71 = (cc1 == 7);
-    // phases 2 and 4: packed lower-triangle pair (ta >= tb); lanes 28..31 shadow lane 27
+    // phases 2 and 3: packed lower-triangle pair (ta >= tb); lanes 28..31 shadow lane 27
     const int lt = (l < 28) ? l : 27;
     const int ta = (lt >= 21) ? 6 : (lt >= 15) ? 5 : (lt >= 10) ? 4 : (lt >= 6) ? 3 : (lt >= 3) ? 2 : (lt >= 1) ? 1 : 0;
     const int tb = lt - ta * (ta + 1) / 2;
@@ -127,114 +141,113 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     const double p2dm = (dg && (ta < 2 || ta == 6)) ? 1.0 : 0.0;                 // diagonal term read from the record
     const double p2dc = (dg && ta >= 2 && ta < 6) ? Ts * sel7(o.W, ta) : 0.0;    // or a constant weight
     const int p2dOff = R_BAR + ((ta == 6) ? 2 : (ta == 1) ? 1 : 0);
-    // phase 3: gains (lanes 0..13: j = l/7, x = l%7) and gradient vector (lanes 14..22: v = l-14)
-    const int lk = (l < 14) ? l : 13, kj = lk / 7, kx = lk - 7 * kj;
-    const double *p3a0 = (kx < 2) ? xs + X_WS + 0 * PSS + kx : xs + X_GS + tri_rt(kx, 0);
-    const double *p3a1 = (kx < 2) ? xs + X_WS + 1 * PSS + kx : xs + X_GS + tri_rt(kx, 1);
-    const bool isK = (l < 14), isG = (l >= 14 && l < 23);
-    const int gv = isG ? l - 14 : 0;
+    // gradient vector g (lanes 0..8 as a second job of phase 2): v < 7 -> M-column v ; v = 7,8 -> x0, x1
+    const bool isG = (l < 9);
+    const int gv = isG ? l : 0;
     const int p3gb = (gv < 2) ? R_BAR + 3 + gv : (gv < 7) ? R_GX + gv : R_GX + (gv - 7);
     const int p3M = R_M + ((gv < 7) ? gv : 0) * 6;
     const double p3m6 = (gv == 1) ? hdt : (gv == 6) ? 1.0 : 0.0;
     const double p3gm = (gv < 7) ? 1.0 : 0.0, p3gh = (gv < 7) ? 0.0 : 1.0;
-    const double *p3h = xs + X_HV + ((gv < 7) ? 0 : gv - 7);
-    // phase 4: Schur complement entry (ta, tb) as state indices
+    const int p3h = (gv < 7) ? 0 : gv - 7;
+    // phase 3: gains (lanes 0..13: j = l/7, x = l%7), Schur entry (ta, tb), k_ff (lanes 28, 29), p_k (lanes 0..6)
+    const int lk = (l < 14) ? l : 13, kj = lk / 7, kx = lk - 7 * kj;
+    const double *p3a0 = (kx < 2) ? xs + X_WS + 0 * PSS + kx : xs + X_GS + tri_rt(kx, 0);
+    const double *p3a1 = (kx < 2) ? xs + X_WS + 1 * PSS + kx : xs + X_GS + tri_rt(kx, 1);
+    const bool isK = (l < 14);
     const double *p4g = (tb >= 2) ? xs + X_GS + lt : (ta >= 2) ? xs + X_WS + ta * PSS + tb : xs + X_PS + ta * PSS + tb;
     const double p4add = (ta < 2 && dg) ? Ts * sel7(o.W, ta) : 0.0;
-    const double *p4a0 = (ta >= 2) ? xs + X_GS + tri_rt(ta, 0) : xs + X_WS + 0 * PSS + ta;
-    const double *p4a1 = (ta >= 2) ? xs + X_GS + tri_rt(ta, 1) : xs + X_WS + 1 * PSS + ta;
+    const double *p4a0 = (ta >= 2) ? xs + X_GS + tri_rt(ta, 0) : xs + X_WS + 0 * PSS + ta;   // G[x_ta][u0]
+    const double *p4a1 = (ta >= 2) ? xs + X_GS + tri_rt(ta, 1) : xs + X_WS + 1 * PSS + ta;   // G[x_ta][u1]
+    const double *p4b0 = (tb >= 2) ? xs + X_GS + tri_rt(tb, 0) : xs + X_WS + 0 * PSS + tb;   // G[u0][x_tb]
+    const double *p4b1 = (tb >= 2) ? xs + X_GS + tri_rt(tb, 1) : xs + X_WS + 1 * PSS + tb;   // G[u1][x_tb]
     double *p4o0 = xs + X_PS + ta * PSS + tb, *p4o1 = xs + X_PS + tb * PSS + ta;
     const int l7 = (l < 7) ? l : 6;
     const double *p4gx = xs + X_GV + ((l7 < 2) ? 7 + l7 : l7);
+    const double *p5c0 = (l7 < 2) ? xs + X_WS + 0 * PSS + l7 : xs + X_GS + tri_rt(l7, 0);   // G[u0][x_l]
+    const double *p5c1 = (l7 < 2) ? xs + X_WS + 1 * PSS + l7 : xs + X_GS + tri_rt(l7, 1);
     const bool kfj = (l == 29);
 
     // terminal: P_N = diag(We), p_N = r_x,N
-    if (FACTOR) { xs[X_PS + l] = 0.0; xs[X_PS + 32 + l] = 0.0; }
+    if (FACTOR) { xs[X_PS + l] = 0.0; xs[X_PS + 32 + l] = 0.0; if (l < 8) xs[X_PS + 64 + l] = 0.0; }
     if (l < 7) xs[X_PV + l] = sm[N * R_STRIDE + l];
     __syncwarp();
     if (FACTOR && l < 7) xs[X_PS + l * PSS + l] = sel7(o.We, l);
     __syncwarp();
     double *st = sm + (N - 1) * R_STRIDE;
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
+        double gi00, gi01, gi11;
         if (FACTOR) {
-            // ---- phase 1: W = P_{k+1} [M | rb] ; h = W(:,7) + p ----------------------------------------------------------
+            // ---- phase 1: W = P_{k+1} [M | rb] ; P rb ; h = P rb + p ------------------------------------------------------
             const double rb6 = st[R_RB + 6];
             {
-                const double *col = st + p1c0;
-                double v = p1P0[6] * fma(m6r0, rb6, m6c0), v2 = p1P0[0] * col[0];
-                v = fma(p1P0[1], col[1], v); v2 = fma(p1P0[2], col[2], v2);
-                v = fma(p1P0[3], col[3], v); v2 = fma(p1P0[4], col[4], v2);
-                v = fma(p1P0[5], col[5], v) + v2;
+                const double v = fma(p1P0[6], fma(m6r0, rb6, m6c0), dot6(p1P0, st + p1c0));
                 *p1o0 = v;
                 if (v70) { st[R_PB + a0] = v; xs[X_HV + a0] = v + xs[X_PV + a0]; }
             }
             {
-                const double *col = st + p1c1;
-                double v = p1P1[6] * fma(m6r1, rb6, m6c1), v2 = p1P1[0] * col[0];
-                v = fma(p1P1[1], col[1], v); v2 = fma(p1P1[2], col[2], v2);
-                v = fma(p1P1[3], col[3], v); v2 = fma(p1P1[4], col[4], v2);
-                v = fma(p1P1[5], col[5], v) + v2;
+                const double v = fma(p1P1[6], fma(m6r1, rb6, m6c1), dot6(p1P1, st + p1c1));
                 *p1o1 = v;
                 if (v71) { st[R_PB + a1] = v; xs[X_HV + a1] = v + xs[X_PV + a1]; }
             }
             __syncwarp();
-            // ---- phase 2: Gram block G[ta][tb] = M(:,ta)^T W(:,tb) + diagonal --------------------------------------------
+            // ---- phase 2: Gram block G[ta][tb] = M(:,ta)^T W(:,tb) + diagonal ; gradient vector g ---------------------------
             {
-                const double *mc = st + p2M;
-                double v = p2m6 * p2W[6], v2 = mc[0] * p2W[0];
-                v = fma(mc[1], p2W[1], v); v2 = fma(mc[2], p2W[2], v2);
-                v = fma(mc[3], p2W[3], v); v2 = fma(mc[4], p2W[4], v2);
-                v = fma(mc[5], p2W[5], v) + v2;
+                double v = fma(p2m6, p2W[6], dot6(st + p2M, p2W));
                 v += fma(p2dm, st[p2dOff], p2dc);
                 xs[X_GS + lt] = v;
             }
-            __syncwarp();
         } else {
             if (l < 7) xs[X_HV + l] = st[R_PB + l] + xs[X_PV + l];
             __syncwarp();
         }
-        // ---- phase 3: 2x2 pivot, gains K, gradient vector g -----------------------------------------------------------------
-        double gi00, gi01, gi11;
+        {
+            const double d = fma(p3m6, xs[X_HV + 6], dot6(st + p3M, xs + X_HV));
+            const double g = st[p3gb] + fma(p3gm, d, p3gh * xs[X_HV + p3h]);
+            if (isG) xs[X_GV + gv] = g;
+        }
+        __syncwarp();
+        // ---- phase 3: 2x2 pivot, gains, Schur complement, k_ff, p_k -----------------------------------------------------------
+        const double gu0 = xs[X_GV + 0], gu1 = xs[X_GV + 1];
         if (FACTOR) {
             const double g00 = xs[X_GS + 0] + o.reg, g01 = xs[X_GS + 1], g11 = xs[X_GS + 2] + o.reg;
             const double idet = 1.0 / (g00 * g11 - g01 * g01);
             gi00 = g11 * idet; gi01 = -g01 * idet; gi11 = g00 * idet;
-            const double c0 = kj ? gi01 : gi00, c1 = kj ? gi11 : gi01;
-            const double kval = -(c0 * (*p3a0) + c1 * (*p3a1));
-            if (isK) st[R_K + l] = kval;
+            {
+                const double c0 = kj ? gi01 : gi00, c1 = kj ? gi11 : gi01;
+                const double kval = -(c0 * (*p3a0) + c1 * (*p3a1));
+                if (isK) st[(kj ? R_K1 : R_K0) + kx] = kval;
+            }
             if (l == 31) { st[R_GI + 0] = gi00; st[R_GI + 1] = gi01; st[R_GI + 2] = gi11; }
+            {   // P_k[ta][tb] = Gxx + G[x_ta][u] K(:, x_tb)
+                const double b0 = *p4b0, b1 = *p4b1;
+                const double kb0 = -(gi00 * b0 + gi01 * b1), kb1 = -(gi01 * b0 + gi11 * b1);
+                const double pn = (*p4g + p4add) + (*p4a0) * kb0 + (*p4a1) * kb1;
+                *p4o0 = pn; *p4o1 = pn;
+            }
+            {   // p_k[l] = g_x[l] + K(:, x_l) . g_u
+                const double c0 = *p5c0, c1 = *p5c1;
+                const double k0 = -(gi00 * c0 + gi01 * c1), k1 = -(gi01 * c0 + gi11 * c1);
+                const double pvv = *p4gx + k0 * gu0 + k1 * gu1;
+                if (l < 7) xs[X_PV + l] = pvv;
+            }
         } else {
             gi00 = st[R_GI + 0]; gi01 = st[R_GI + 1]; gi11 = st[R_GI + 2];
+            const double pvv = *p4gx + st[R_K0 + l7] * gu0 + st[R_K1 + l7] * gu1;
+            if (l < 7) xs[X_PV + l] = pvv;
         }
         {
-            const double *mc = st + p3M;
-            double d = p3m6 * xs[X_HV + 6];
-#pragma unroll
-            for (int r = 0; r < 6; r++) d = fma(mc[r], xs[X_HV + r], d);
-            const double g = st[p3gb] + fma(p3gm, d, p3gh * (*p3h));
-            if (isG) xs[X_GV + gv] = g;
-        }
-        __syncwarp();
-        // ---- phase 4: Schur complement, k_ff, p_k -----------------------------------------------------------------------------
-        if (FACTOR) {
-            const double pn = (*p4g + p4add) + (*p4a0) * st[R_K + tb] + (*p4a1) * st[R_K + 7 + tb];
-            *p4o0 = pn; *p4o1 = pn;
-        }
-        {
-            const double gu0 = xs[X_GV + 0], gu1 = xs[X_GV + 1];
             const double c0 = kfj ? gi01 : gi00, c1 = kfj ? gi11 : gi01;
             const double kf = -(c0 * gu0 + c1 * gu1);
             if (l == 28 || l == 29) st[R_KF + (l - 28)] = kf;
-            const double pvv = *p4gx + st[R_K + l7] * gu0 + st[R_K + 7 + l7] * gu1;
-            if (l < 7) xs[X_PV + l] = pvv;
         }
         __syncwarp();
     }
 }
 
 // ---- sequential forward roll-out (matrix role: lane r < 7 carries ddx_k[r]) -------------------------------------------
+// The state is broadcast through a double-buffered 8-double slot (1 STS + LDS.128s + one __syncwarp per stage).
 template <bool ADJ>
-__device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, int N, int l)
+__device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
     const double hdt = o.dt, Ts = o.dt;
     const int l7 = (l < 7) ? l : 6, l6 = (l < 6) ? l : 5;
@@ -244,23 +257,33 @@ __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, int N
     double dxr = 0.0;
     double *st = sm;
     for (int k = 0; k < N; k++, st += R_STRIDE) {
-        double dxv[7];
-#pragma unroll
-        for (int a = 0; a < 7; a++) dxv[a] = __shfl_sync(FULL, dxr, a);
-        double du0 = st[R_KF + 0], du1 = st[R_KF + 1];
-#pragma unroll
-        for (int a = 0; a < 7; a++) { du0 = fma(st[R_K + a], dxv[a], du0); du1 = fma(st[R_K + 7 + a], dxv[a], du1); }
-        if (l == 7) { st[R_DD + 0] = du0; st[R_DD + 1] = du1; st[R_DD + 2] = dxv[6]; }
+        double *bx = xs + X_DX + (k & 1) * 8;
+        if (l < 8) bx[l] = dxr;                        // lane 7 writes the zero pad
+        __syncwarp();
+        const double2 x01 = ld2(bx), x23 = ld2(bx + 2), x45 = ld2(bx + 4);
+        const double x6 = bx[6];
+        const double2 ka = ld2(st + R_K0), kb = ld2(st + R_K0 + 2), kc = ld2(st + R_K0 + 4);
+        const double2 kd = ld2(st + R_K1), ke = ld2(st + R_K1 + 2), kg = ld2(st + R_K1 + 4);
+        const double2 kf = ld2(st + R_KF);
+        double du0 = fma(ka.x, x01.x, kf.x), t0 = ka.y * x01.y;
+        du0 = fma(kb.x, x23.x, du0); t0 = fma(kb.y, x23.y, t0);
+        du0 = fma(kc.x, x45.x, du0); t0 = fma(kc.y, x45.y, t0);
+        du0 = fma(st[R_K0 + 6], x6, du0) + t0;
+        double du1 = fma(kd.x, x01.x, kf.y), t1 = kd.y * x01.y;
+        du1 = fma(ke.x, x23.x, du1); t1 = fma(ke.y, x23.y, t1);
+        du1 = fma(kg.x, x45.x, du1); t1 = fma(kg.y, x45.y, t1);
+        du1 = fma(st[R_K1 + 6], x6, du1) + t1;
+        if (l == 7) { st[R_DD + 0] = du0; st[R_DD + 1] = du1; st[R_DD + 2] = x6; }
         if (ADJ && k >= 1) {
             const double Qd = fma(is6, st[R_BAR + 2] - wq_l, wq_l);
             const double nb = fma(Qd, dxr, st[R_GX + l7]);
             if (l < 7) st[R_GX + l] = nb;
         }
         const double *mr = st + R_M + l6;        // row l of M: element (l, c) at c*6
-        double d = mr[0] * du0;
-        d = fma(mr[6], du1, d);
-#pragma unroll
-        for (int cc = 0; cc < 5; cc++) d = fma(mr[(2 + cc) * 6], dxv[2 + cc], d);
+        double d = mr[0] * du0, d2 = mr[6] * du1;
+        d = fma(mr[12], x23.x, d); d2 = fma(mr[18], x23.y, d2);
+        d = fma(mr[24], x45.x, d); d2 = fma(mr[30], x45.y, d2);
+        d = fma(mr[36], x6, d) + d2;
         double v = st[R_RB + l7] + fma(cself, dxr, cdt * du1);
         v = fma(mB, d, v);
         dxr = (l < 7) ? v : 0.0;
@@ -271,7 +294,7 @@ __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, int N
 }
 
 // ---- sequential adjoint sweep: dpi_{k-1} = base_k + A_k^T dpi_k ; leaves dpi_k in the P rb slot ----------------------
-__device__ __forceinline__ void w_adjoint(double *sm, int N, int l)
+__device__ __forceinline__ void w_adjoint(double *sm, double *xs, int N, int l)
 {
     const int l7 = (l < 7) ? l : 6;
     const int lc = (l >= 2 && l < 7) ? l : 2;
@@ -281,11 +304,9 @@ __device__ __forceinline__ void w_adjoint(double *sm, int N, int l)
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
         if (l < 7) st[R_PB + l] = dpr;
         if (k == 0) break;
-        const double *mc = st + R_M + lc * 6;
-        double d = 0.0;
-#pragma unroll
-        for (int r = 0; r < 6; r++) d = fma(mc[r], __shfl_sync(FULL, dpr, r), d);
-        const double v = st[R_GX + l7] + fma(cself, dpr, mA * d);     // A(:,0..1) = e0,e1 ; A[6][6] = 1
+        __syncwarp();
+        const double d = dot6(st + R_M + lc * 6, st + R_PB);      // rows 0..5 of dpi_k, just published in the record
+        const double v = st[R_GX + l7] + fma(cself, dpr, mA * d);  // A(:,0..1) = e0,e1 ; A[6][6] = 1
         dpr = (l < 7) ? v : 0.0;
     }
     __syncwarp();
@@ -472,7 +493,7 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
 
         // ================= predictor ===================================================================================
         w_backward<true>(o, sm, xs, N, l);
-        w_forward<false>(o, sm, N, l);
+        w_forward<false>(o, sm, xs, N, l);
         double dsl[2], dsu[2], dtv[NC], dlv[NC];
         double an = 1.0, ad = 1.0;          // step length as a ratio an/ad (<= 1)
         double s1 = 0.0, s2 = 0.0;
@@ -541,7 +562,7 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
                 __syncwarp();
                 // ================= corrector ===========================================================================
                 w_backward<false>(o, sm, xs, N, l);
-                w_forward<true>(o, sm, N, l);
+                w_forward<true>(o, sm, xs, N, l);
             }
         }
         double alpha = an / ad;
@@ -560,7 +581,7 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
                 S.t[c] = fmax(S.t[c] + alpha * dtv[c], o.t_min);
             }
         }
-        w_adjoint(sm, N, l);
+        w_adjoint(sm, xs, N, l);
         if (isst) {
 #pragma unroll
             for (int a = 0; a < 7; a++) S.pi[a] += alpha * st[R_PB + a];
