@@ -114,7 +114,7 @@ struct admpc_batch {
     cudaEvent_t tm0, tm1;
     bool profiling = false;
     bool gps_set = false;
-    int qp_variant = 0;      // 0 auto(=3), 1 thread-per-instance (qp_ipm.cu), 2 octet (qp_octet.cu), 3 smem octet (qp_smem.cu)
+    int qp_variant = 0;      // 0 auto(=4), 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu)
     long long launches = 0;
     float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
     nccl_comm comm = nullptr;
@@ -122,6 +122,8 @@ struct admpc_batch {
 };
 
 static size_t rup(size_t v, size_t m) { return (v + m - 1) / m * m; }
+// doubles per GP output in the packed blob: M points x (dz + 2) + tail (dz inverse squared length scales, y_mean)
+static size_t gp_stride(int M, int dz) { return rup((size_t)M * (dz + 2) + dz + 1, 2); }
 
 extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, admpc_batch **out)
 {
@@ -156,7 +158,7 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
         {&P.lin, (size_t)(N + 1) * LIN_ROWS},
         {&P.dx, nX}, {&P.du, nU}, {&P.pi, nPi}, {&P.lam, nC}, {&P.t, nC}, {&P.sl, nU}, {&P.su, nU},
         {&P.rgu, nU}, {&P.rgx, nX}, {&P.rgsl, nU}, {&P.rgsu, nU}, {&P.rb, nPi}, {&P.rd, nC}, {&P.rm, nC},
-        {&P.K, (size_t)N * 14}, {&P.Ginv, (size_t)N * 3}, {&P.P, (size_t)(N + 1) * 28}, {&P.Pb, nPi}, {&P.kf, nU}, {&P.pv, nX}, {&P.bar, (size_t)N * 6},
+        {&P.K, (size_t)N * 14}, {&P.Ginv, (size_t)N * 3}, {&P.P, (size_t)(N + 1) * 28}, {&P.Pb, nPi}, {&P.kf, nU}, {&P.pv, nX},
         {&P.ddu, nU}, {&P.ddx, nX}, {&P.dpi, nPi}, {&P.dlam, nC}, {&P.dt, nC}, {&P.dsl, nU}, {&P.dsu, nU},
         {&P.res_out, 4}, {&P.ws, (size_t)qp_smem_ws_rows(N)},
     };
@@ -215,17 +217,24 @@ static int upload_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, c
         if (feat[d] < 2 || feat[d] > 8) { admpc_set_error("admpc_batch_set_gp", "GP features must be in [psi..delta,u0,u1] (indices 2..8)"); return ADMPC_E_UNSUPPORTED; }
     for (int j = 0; j < nout; j++)
         if (rows[j] < 3 || rows[j] > 5) { admpc_set_error("admpc_batch_set_gp", "GP outputs must map to state rows 3..5"); return ADMPC_E_UNSUPPORTED; }
-    const size_t stride = rup((size_t)M * (dz + 1) + dz + 1, 2);
+    const size_t stride = gp_stride(M, dz);
     const size_t bytes = stride * nout * sizeof(double);
     if (bytes > 220 * 1024) { admpc_set_error("admpc_batch_set_gp", "GP model exceeds the shared-memory staging budget (220 KB)"); return ADMPC_E_UNSUPPORTED; }
     std::vector<double> blob(stride * nout, 0.0);
     for (int j = 0; j < nout; j++) {
         double *b = blob.data() + stride * j;
+        const double L2E = 1.4426950408889634;
         for (int i = 0; i < M; i++) {
-            for (int d = 0; d < dz; d++) b[(size_t)i * (dz + 1) + d] = X[((size_t)j * M + i) * dz + d];
-            b[(size_t)i * (dz + 1) + dz] = sigma_f[j] * alpha[(size_t)j * M + i];
+            double c = 0.0;
+            for (int d = 0; d < dz; d++) {
+                const double x = X[((size_t)j * M + i) * dz + d], wd = 1.0 / (ell[j * dz + d] * ell[j * dz + d]);
+                b[(size_t)i * (dz + 2) + d] = L2E * wd * x;
+                c += wd * x * x;
+            }
+            b[(size_t)i * (dz + 2) + dz] = -0.5 * L2E * c;
+            b[(size_t)i * (dz + 2) + dz + 1] = sigma_f[j] * alpha[(size_t)j * M + i];
         }
-        double *w = b + (size_t)M * (dz + 1);
+        double *w = b + (size_t)M * (dz + 2);
         for (int d = 0; d < dz; d++) w[d] = 1.0 / (ell[j * dz + d] * ell[j * dz + d]);
         w[dz] = y_mean[j];
     }
@@ -324,13 +333,13 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     launch_prepare(P, h->stream);
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
     // QP variant: 4 (default) warp per instance, register-resident IPM state; 3 shared-memory-resident octets
-    // (horizons 32..80); 2 octets on global scratch;
+    // (horizons 32..80);
     // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
     const int variant = h->qp_variant ? h->qp_variant : 4;
     bool fused = false;
     if (variant == 4) fused = launch_qp_warp(P, h->stream);        // one warp per instance, N <= 31
     if (!fused && variant >= 3) fused = launch_qp_smem(P, h->stream);
-    if (!fused) { if (variant == 2) launch_qp_octet(P, h->stream); else launch_qp(P, h->stream); }
+    if (!fused) launch_qp(P, h->stream);
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
     if (!fused) launch_update(P, h->stream);
     CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
@@ -576,7 +585,7 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
     Params &P = h->P;
     if (h->rank != root) {
         nout = hdr[0]; M = hdr[1]; dz = hdr[2];
-        const size_t stride = rup((size_t)M * (dz + 1) + dz + 1, 2);
+        const size_t stride = gp_stride(M, dz);
         const size_t bytes = stride * nout * sizeof(double);
         if (bytes > h->gp_blob_cap) {
             cudaFree(h->gp_blob);

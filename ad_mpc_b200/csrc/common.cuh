@@ -24,7 +24,8 @@
 
 struct GpDev {
     // packed, 16-byte aligned GP block in HBM, staged to shared memory by one TMA bulk copy per CTA:
-    //   per output j: pts[M][dz+1] = {X_i0..X_i(dz-1), sigma_f*alpha_i}, then w[dz] = 1/ell^2, then y_mean (padded)
+    //   per output j: pts[M][dz+2] = {log2e*X_id/ell_d^2 (dz), -0.5*log2e*sum_d X_id^2/ell_d^2, sigma_f*alpha_i},
+    //   then w[dz] = 1/ell^2, then y_mean (padded to an even count)
     const double *blob;
     int bytes;          // multiple of 16
     int stride_out;     // doubles per output block
@@ -43,7 +44,7 @@ struct Params {
     // QP solution (delta form) + workspace
     double *dx, *du, *pi, *lam, *t, *sl, *su;
     double *rgu, *rgx, *rgsl, *rgsu, *rb, *rd, *rm;
-    double *K, *Ginv, *P, *Pb, *kf, *pv, *bar;
+    double *K, *Ginv, *P, *Pb, *kf, *pv;
     double *ddu, *ddx, *dpi, *dlam, *dt, *dsl, *dsu;
     double *ws;          // qp_smem.cu: per-warp scratch tiles [Bp/4][rows][4]
     int *status, *qp_status, *qp_iter, *lin_bad;
@@ -61,7 +62,6 @@ void admpc_set_error(const char *what, const char *msg);
 // kernel launchers (defined in the .cu files)
 void launch_prepare(const Params &P, cudaStream_t s);
 void launch_qp(const Params &P, cudaStream_t s);
-void launch_qp_octet(const Params &P, cudaStream_t s);
 bool launch_qp_smem(const Params &P, cudaStream_t s);   // false: horizon too long for the shared-memory variant
 int qp_smem_ws_rows(int N);
 bool launch_qp_warp(const Params &P, cudaStream_t s);   // false: N > 31

@@ -68,6 +68,33 @@ __device__ __forceinline__ double exp_neg(double x)
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// 2^t for t <= 0 (RBF argument pre-scaled by -0.5*log2(e) on the host): n = rint(t), r = t - n exactly, |r| <= 1/2,
+// 2^r by degree-13 Horner in r with coefficients ln2^k/k! (truncation 4e-18), exponent-field scaling.
+// 17 FP64-pipe instructions; arguments below -1000 are clamped (2^-1000 = 1e-301 instead of a denormal/zero).
+__device__ __forceinline__ double exp2_neg(double t)
+{
+    t = fmax(t, -1000.0);
+    const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52
+    const double tt = t + SHIFT;
+    const int n = __double2loint(tt);
+    const double r = t - (tt - SHIFT);
+    double p = 1.3691488853904128e-12;
+    p = fma(p, r, 2.5678435993488206e-11);
+    p = fma(p, r, 4.4455382718708116e-10);
+    p = fma(p, r, 7.054911620801123e-09);
+    p = fma(p, r, 1.01780860092397e-07);
+    p = fma(p, r, 1.321548679014431e-06);
+    p = fma(p, r, 1.5252733804059841e-05);
+    p = fma(p, r, 0.0001540353039338161);
+    p = fma(p, r, 0.0013333558146428443);
+    p = fma(p, r, 0.009618129107628477);
+    p = fma(p, r, 0.05550410866482158);
+    p = fma(p, r, 0.24022650695910072);
+    p = fma(p, r, 0.6931471805599453);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 struct Jac {
     // d f / d x : rows 0,1 x cols {psi,vx,vy}; row 2 = e_r; rows 3..5 x cols 2..6 ; row 6 = 0
     double j0[3], j1[3];
@@ -147,39 +174,49 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
             }
         }
         for (int j = 0; j < o.gp_nout; j++) {
+            // blob per output: M points of {a_0..a_{dz-1}, c, sigma_f*alpha} with a_d = log2(e) X_d / ell_d^2 and
+            // c = -0.5 log2(e) sum_d X_d^2/ell_d^2, so that  log2 k(z, X_i) = q + c_i + a_i . z,
+            // q = -0.5 log2(e) sum_d z_d^2/ell_d^2  (expanded square: 4 FMAs per point instead of 12 ops; the
+            // cancellation costs ~1e-15 absolute in the exponent).  Tail: 1/ell_d^2 (dz values), y_mean.
             const double *blk = gpsm + (size_t)j * gp_stride;
-            const double *w = blk + (size_t)M * (dz + 1);
+            const double *w = blk + (size_t)M * (dz + 2);
             double wv[ADMPC_DZMAX];
 #pragma unroll
             for (int d = 0; d < ADMPC_DZMAX; d++) wv[d] = (d < dz) ? w[d] : 0.0;
-            double m = 0.0, g[ADMPC_DZMAX];
+            double q = 0.0;
 #pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) g[d] = 0.0;
+            for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) q = fma(z[d] * wv[d], z[d], q);
+            q *= -0.5 * 1.4426950408889634;
+            double m = 0.0, g[ADMPC_DZMAX], G2[ADMPC_DZMAX];
+#pragma unroll
+            for (int d = 0; d < ADMPC_DZMAX; d++) { g[d] = 0.0; G2[d] = 0.0; }
             if (dz == 4) {
-                // hot case: 4 features -> {X0..X3, a} = 40 B per point
+                // hot case: 4 features -> 48 B per point, three LDS.128
 #pragma unroll 4
                 for (int i = 0; i < M; i++) {
-                    const double *pt = blk + (size_t)i * 5;
-                    const double d0 = z[0] - pt[0], d1 = z[1] - pt[1], d2 = z[2] - pt[2], d3 = z[3] - pt[3];
-                    const double e0 = d0 * wv[0], e1 = d1 * wv[1], e2 = d2 * wv[2], e3 = d3 * wv[3];
-                    const double s = fma(d3, e3, fma(d2, e2, fma(d1, e1, d0 * e0)));
-                    const double ka = exp_neg(-0.5 * s) * pt[4];
+                    const double2 *pt = reinterpret_cast<const double2 *>(blk + (size_t)i * 6);
+                    const double2 a01 = pt[0], a23 = pt[1], ca = pt[2];
+                    const double t = fma(a23.y, z[3], fma(a23.x, z[2], fma(a01.y, z[1], fma(a01.x, z[0], q + ca.x))));
+                    const double ka = exp2_neg(t) * ca.y;
                     m += ka;
-                    g[0] = fma(-ka, e0, g[0]); g[1] = fma(-ka, e1, g[1]);
-                    g[2] = fma(-ka, e2, g[2]); g[3] = fma(-ka, e3, g[3]);
+                    G2[0] = fma(ka, a01.x, G2[0]); G2[1] = fma(ka, a01.y, G2[1]);
+                    G2[2] = fma(ka, a23.x, G2[2]); G2[3] = fma(ka, a23.y, G2[3]);
                 }
             } else {
                 for (int i = 0; i < M; i++) {
-                    const double *pt = blk + (size_t)i * (dz + 1);
-                    double s = 0.0, e[ADMPC_DZMAX];
+                    const double *pt = blk + (size_t)i * (dz + 2);
+                    double t = q + pt[dz];
 #pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) { const double dd = z[d] - pt[d]; e[d] = dd * wv[d]; s = fma(dd, e[d], s); }
-                    const double ka = exp_neg(-0.5 * s) * pt[dz];
+                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) t = fma(pt[d], z[d], t);
+                    const double ka = exp2_neg(t) * pt[dz + 1];
                     m += ka;
 #pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) g[d] = fma(-ka, e[d], g[d]);
+                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G2[d] = fma(ka, pt[d], G2[d]);
                 }
             }
+            // d mu / d z_d = -sum_i ka_i (z_d - X_id)/ell_d^2 = -(z_d/ell_d^2 * m - ln2 * G2_d)
+#pragma unroll
+            for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) g[d] = fma(0.6931471805599453, G2[d], -(z[d] * wv[d]) * m);
             m += w[dz];   // y_mean
             const int row = o.gp_row[j] - 3;       // 0..2
 #pragma unroll

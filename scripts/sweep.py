@@ -24,7 +24,7 @@ def run(B, N, gpM, variant, p=1.0, reps=5):
         B, N, gpM, variant, np.mean(tp), np.mean(tq), np.mean(ts), B / np.mean(ts) / 1e3, qi.mean(), (st == 0).all()), flush=True)
 
 if __name__ == "__main__":
-    variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [3]
+    variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [4]
     for B in (1, 4096, 16384, 131072):
         for v in variants:
             run(B, 20, 0, v)
