@@ -110,6 +110,9 @@ struct admpc_batch {
     size_t gp_blob_cap = 0;
     double *l2_scratch = nullptr;
     size_t l2_bytes = 0;
+    double *track = nullptr, *track_info = nullptr;
+    size_t track_cap = 0;
+    int track_L = 0, track_H = 0, track_stop = 0;
     cudaEvent_t ev[8];
     cudaEvent_t tm0, tm1;
     bool profiling = false;
@@ -191,7 +194,7 @@ extern "C" int admpc_batch_free(admpc_batch *h)
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
-    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch);
+    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info);
     for (auto &e : h->ev) cudaEventDestroy(e);
     cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
     cudaStreamDestroy(h->stream);
@@ -539,6 +542,58 @@ extern "C" int admpc_measure_fp64_peak(int device, double *tflops)
     const double v = run_fp64_peak(device);
     if (v <= 0) { admpc_set_error("admpc_measure_fp64_peak", "CUDA failure"); return ADMPC_E_CUDA; }
     *tflops = v;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- reference generation ---
+struct TrackHost { std::vector<double> dev; int L = 0, H = 0, stop = 0; };
+int refgen_build_track(int L, const double *traj, int H, double dt, TrackHost &T);
+void launch_refgen(const Params &P, const double *trk, int L, int H, double *info, cudaStream_t s);
+
+extern "C" int admpc_batch_set_track(admpc_batch *h, int L, const double *traj, int H, double traj_dt)
+{
+    if (!h) return ADMPC_E_ARG;
+    if (H < h->P.o.N) { admpc_set_error("admpc_batch_set_track", "reference horizon H must be >= N (gp_ad_mpc_node.py:172-175 single-point branch is not supported)"); return ADMPC_E_UNSUPPORTED; }
+    TrackHost T;
+    int r = refgen_build_track(L, traj, H, traj_dt, T);
+    if (r) { admpc_set_error("admpc_batch_set_track", "bad track (need L >= 2 rows of [vel,x,y,psi,cdist,curv], H >= 4)"); return r; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const size_t bytes = T.dev.size() * sizeof(double);
+    if (bytes > h->track_cap) {
+        cudaFree(h->track);
+        CUDA_CHECK_RET(cudaMalloc(&h->track, bytes));
+        h->track_cap = bytes;
+    }
+    if (!h->track_info) CUDA_CHECK_RET(cudaMalloc(&h->track_info, (size_t)3 * h->P.Bp * sizeof(double)));
+    CUDA_CHECK_RET(cudaMemcpyAsync(h->track, T.dev.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    h->track_L = L; h->track_H = H; h->track_stop = T.stop;
+    return 0;
+}
+
+extern "C" int admpc_batch_make_yref(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    if (!h->track) { admpc_set_error("admpc_batch_make_yref", "no track set"); return ADMPC_E_STATE; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    launch_refgen(h->P, h->track, h->track_L, h->track_H, h->track_info, h->stream);
+    h->launches++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int admpc_batch_get_yref(admpc_batch *h, double *yref) { return get_rows(h, h->P.yref, yref, h->P.o.N * 9 + 7); }
+
+extern "C" int admpc_batch_get_waypoint_info(admpc_batch *h, double *s0, double *e_y0, double *e_psi0, int *stop)
+{
+    if (!h || !h->track_info) return ADMPC_E_STATE;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->P.B * sizeof(double);
+    if (s0) CUDA_CHECK_RET(cudaMemcpyAsync(s0, h->track_info, n, cudaMemcpyDeviceToHost, h->stream));
+    if (e_y0) CUDA_CHECK_RET(cudaMemcpyAsync(e_y0, h->track_info + h->P.Bp, n, cudaMemcpyDeviceToHost, h->stream));
+    if (e_psi0) CUDA_CHECK_RET(cudaMemcpyAsync(e_psi0, h->track_info + 2 * (size_t)h->P.Bp, n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    if (stop) *stop = h->track_stop;
     return 0;
 }
 

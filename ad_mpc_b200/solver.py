@@ -129,6 +129,26 @@ class BatchSolver:
     def reset(self):
         check(self.L.admpc_batch_reset(self.h), "reset")
 
+    # ---- reference generation on the device (RefTrajectory.get_waypoints for the whole batch) -----------------------
+    def set_track(self, traj, H=None, traj_dt=None):
+        """traj[L,6] = [vel, x, y, psi, cdist, curv] (the table RefTrajectory.set_traj builds); H >= N reference points."""
+        traj = _f64(traj)
+        H = int(H if H is not None else self.N)
+        dt = float(traj_dt if traj_dt is not None else self.opts.dt)
+        check(self.L.admpc_batch_set_track(self.h, traj.shape[0], _dp(traj), H, dt), "set_track")
+
+    def make_yref(self):
+        check(self.L.admpc_batch_make_yref(self.h), "make_yref")
+
+    def get_yref(self):
+        return self._get(self.L.admpc_batch_get_yref, self.N * 9 + 7)
+
+    def get_waypoint_info(self):
+        s0, ey, ep = (np.empty(self.B) for _ in range(3))
+        stop = C.c_int()
+        check(self.L.admpc_batch_get_waypoint_info(self.h, _dp(s0), _dp(ey), _dp(ep), C.byref(stop)), "get_waypoint_info")
+        return s0, ey, ep, bool(stop.value)
+
     # ---- solve / outputs ------------------------------------------------------------------------------------
     def solve(self):
         check(self.L.admpc_batch_solve(self.h), "solve")

@@ -144,6 +144,15 @@ int admpc_batch_solve_host(admpc_batch *h, const double *x0, const double *yref,
 int admpc_batch_solve_host_async(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
                                  double *u_out, double *x_out, int *status_out);
 
+/* Reference generation on the device (ad_mpc/ref_traj.py:89-171 + nodes/gp_ad_mpc_node.py:180-187 +
+ * ad_mpc/ad_3d_optimizer.py:343-345,420-438): set_track takes the table RefTrajectory.set_traj builds
+ * (traj[L][6] rows = [vel, x, y, psi, cdist, curv], ref_traj.py:84) with the generator's horizon H (>= N) and time step;
+ * make_yref turns the CURRENT x0 of every instance (pose = x0[0..2]) into its yref, in place on the device. */
+int admpc_batch_set_track(admpc_batch *h, int L, const double *traj /*[L][6]*/, int H, double traj_dt);
+int admpc_batch_make_yref(admpc_batch *h);
+int admpc_batch_get_yref(admpc_batch *h, double *yref /*[B][N*9+7]*/);
+int admpc_batch_get_waypoint_info(admpc_batch *h, double *s0 /*[B]*/, double *e_y0 /*[B]*/, double *e_psi0 /*[B]*/, int *stop);
+
 /* instrumentation: device time (CUDA events on the handle's stream) of the last solve and of its kernels.
  * name: "solve" | "prepare" | "qp" | "h2d" | "d2h" ; returns milliseconds in *ms. Needs admpc_batch_set_profiling(1)
  * for the per-kernel entries. */
