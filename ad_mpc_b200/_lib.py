@@ -71,9 +71,13 @@ SYMBOLS = {
     "admpc_batch_solve_host": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip]),
     "admpc_batch_solve_host_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip]),
     "admpc_batch_set_track": (C.c_int, [_vp, C.c_int, _dp, C.c_int, C.c_double]),
+    "admpc_batch_set_track_anchor": (C.c_int, [_vp, C.c_int]),
     "admpc_batch_make_yref": (C.c_int, [_vp]),
     "admpc_batch_get_yref": (C.c_int, [_vp, _dp]),
     "admpc_batch_get_waypoint_info": (C.c_int, [_vp, _dp, _dp, _dp, _ip]),
+    "admpc_batch_postsolve": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "admpc_batch_closed_loop": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp]),
+    "admpc_batch_get_loop_info": (C.c_int, [_vp, _ip, _ip, _ip, _dp, _dp]),
     "admpc_batch_set_profiling": (C.c_int, [_vp, C.c_int]),
     "admpc_batch_last_ms": (C.c_int, [_vp, _cp, C.POINTER(C.c_float)]),
     "admpc_batch_kernel_launches": (C.c_longlong, [_vp]),

@@ -110,9 +110,12 @@ struct admpc_batch {
     size_t gp_blob_cap = 0;
     double *l2_scratch = nullptr;
     size_t l2_bytes = 0;
+    double *loop_prev_u = nullptr;      // [2N prev_u | 2 u_apply | 7 x_next][Bp]
+    int *loop_i = nullptr;              // [has_prev | safe_count | valid | cmd_ok][Bp]
     double *track = nullptr, *track_info = nullptr;
     size_t track_cap = 0;
-    int track_L = 0, track_H = 0, track_stop = 0;
+    int track_L = 0, track_H = 0, track_stop = 0, track_anchor = 0;
+    double track_dt = 0.0;
     cudaEvent_t ev[8];
     cudaEvent_t tm0, tm1;
     bool profiling = false;
@@ -194,7 +197,7 @@ extern "C" int admpc_batch_free(admpc_batch *h)
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
-    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info);
+    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i);
     for (auto &e : h->ev) cudaEventDestroy(e);
     cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
     cudaStreamDestroy(h->stream);
@@ -548,7 +551,7 @@ extern "C" int admpc_measure_fp64_peak(int device, double *tflops)
 // ---------------------------------------------------------------------------------------------- reference generation ---
 struct TrackHost { std::vector<double> dev; int L = 0, H = 0, stop = 0; };
 int refgen_build_track(int L, const double *traj, int H, double dt, TrackHost &T);
-void launch_refgen(const Params &P, const double *trk, int L, int H, double *info, cudaStream_t s);
+void launch_refgen(const Params &P, const double *trk, int L, int H, double dt, int anchor, double *info, cudaStream_t s);
 
 extern "C" int admpc_batch_set_track(admpc_batch *h, int L, const double *traj, int H, double traj_dt)
 {
@@ -567,7 +570,15 @@ extern "C" int admpc_batch_set_track(admpc_batch *h, int L, const double *traj, 
     if (!h->track_info) CUDA_CHECK_RET(cudaMalloc(&h->track_info, (size_t)3 * h->P.Bp * sizeof(double)));
     CUDA_CHECK_RET(cudaMemcpyAsync(h->track, T.dev.data(), bytes, cudaMemcpyHostToDevice, h->stream));
     CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
-    h->track_L = L; h->track_H = H; h->track_stop = T.stop;
+    h->track_L = L; h->track_H = H; h->track_stop = T.stop; h->track_dt = traj_dt;
+    return 0;
+}
+
+extern "C" int admpc_batch_set_track_anchor(admpc_batch *h, int anchor_at_closest)
+{
+    if (!h) return ADMPC_E_ARG;
+    if (anchor_at_closest && h->track_H > 64) { admpc_set_error("admpc_batch_set_track_anchor", "anchored mode supports H <= 64"); return ADMPC_E_UNSUPPORTED; }
+    h->track_anchor = anchor_at_closest ? 1 : 0;
     return 0;
 }
 
@@ -576,7 +587,7 @@ extern "C" int admpc_batch_make_yref(admpc_batch *h)
     if (!h) return ADMPC_E_ARG;
     if (!h->track) { admpc_set_error("admpc_batch_make_yref", "no track set"); return ADMPC_E_STATE; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
-    launch_refgen(h->P, h->track, h->track_L, h->track_H, h->track_info, h->stream);
+    launch_refgen(h->P, h->track, h->track_L, h->track_H, h->track_dt, h->track_anchor, h->track_info, h->stream);
     h->launches++;
     CUDA_CHECK_RET(cudaGetLastError());
     return 0;
@@ -595,6 +606,80 @@ extern "C" int admpc_batch_get_waypoint_info(admpc_batch *h, double *s0, double 
     CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     if (stop) *stop = h->track_stop;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- closed loop ------------
+void launch_postsolve(const Params &P, double *prev_u, int *ibuf, double *u_apply, double *x_next, int threshold, int advance, cudaStream_t s);
+
+static int loop_alloc(admpc_batch *h)
+{
+    if (h->loop_prev_u) return 0;
+    const size_t Bp = h->P.Bp, N = h->P.o.N;
+    CUDA_CHECK_RET(cudaMalloc(&h->loop_prev_u, (2 * N + 2 + 7) * Bp * sizeof(double)));
+    CUDA_CHECK_RET(cudaMalloc(&h->loop_i, 4 * Bp * sizeof(int)));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->loop_prev_u, 0, (2 * N + 2 + 7) * Bp * sizeof(double), h->stream));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->loop_i, 0, 4 * Bp * sizeof(int), h->stream));
+    return 0;
+}
+
+// validity check + backup control + safety counter (+ plant step when advance != 0) for the last solve
+extern "C" int admpc_batch_postsolve(admpc_batch *h, int advance, int safe_threshold)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    int r = loop_alloc(h);
+    if (r) return r;
+    const size_t Bp = h->P.Bp, N = h->P.o.N;
+    launch_postsolve(h->P, h->loop_prev_u, h->loop_i, h->loop_prev_u + 2 * N * Bp, h->loop_prev_u + (2 * N + 2) * Bp, safe_threshold, advance, h->stream);
+    h->launches++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+
+// `steps` closed-loop control steps entirely on the device: [make_yref] -> solve -> postsolve(advance) ...
+// log_x: optional host buffer [steps+1][B][7] receiving the plant state before every step and after the last one.
+extern "C" int admpc_batch_closed_loop(admpc_batch *h, int steps, int use_track, int safe_threshold, double *log_x)
+{
+    if (!h || steps < 1) return ADMPC_E_ARG;
+    if (use_track && !h->track) { admpc_set_error("admpc_batch_closed_loop", "no track set"); return ADMPC_E_STATE; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    int r = loop_alloc(h);
+    if (r) return r;
+    const size_t Bp = h->P.Bp, B = h->P.B;
+    double *dlog = nullptr;
+    if (log_x) CUDA_CHECK_RET(cudaMalloc(&dlog, (size_t)(steps + 1) * B * 7 * sizeof(double)));
+    for (int t = 0; t < steps; t++) {
+        if (dlog) { launch_transpose_out(h->P.x0, dlog + (size_t)t * B * 7, (int)B, (int)Bp, 7, h->stream); h->launches++; }
+        if (use_track && (r = admpc_batch_make_yref(h))) break;
+        if ((r = admpc_batch_solve(h))) break;
+        if ((r = admpc_batch_postsolve(h, 1, safe_threshold))) break;
+    }
+    if (!r && dlog) {
+        launch_transpose_out(h->P.x0, dlog + (size_t)steps * B * 7, (int)B, (int)Bp, 7, h->stream);
+        h->launches++;
+        cudaError_t e = cudaMemcpyAsync(log_x, dlog, (size_t)(steps + 1) * B * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) { admpc_set_error("closed_loop log copy", cudaGetErrorString(e)); r = ADMPC_E_CUDA; }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (dlog) cudaFree(dlog);
+    if (r) return r;
+    if (e != cudaSuccess) { admpc_set_error("admpc_batch_closed_loop", cudaGetErrorString(e)); return ADMPC_E_CUDA; }
+    return 0;
+}
+
+extern "C" int admpc_batch_get_loop_info(admpc_batch *h, int *valid, int *safe_count, int *cmd_ok, double *u_apply, double *x0)
+{
+    if (!h || !h->loop_prev_u) return ADMPC_E_STATE;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const size_t Bp = h->P.Bp, N = h->P.o.N, n = (size_t)h->P.B * sizeof(int);
+    if (safe_count) CUDA_CHECK_RET(cudaMemcpyAsync(safe_count, h->loop_i + Bp, n, cudaMemcpyDeviceToHost, h->stream));
+    if (valid) CUDA_CHECK_RET(cudaMemcpyAsync(valid, h->loop_i + 2 * Bp, n, cudaMemcpyDeviceToHost, h->stream));
+    if (cmd_ok) CUDA_CHECK_RET(cudaMemcpyAsync(cmd_ok, h->loop_i + 3 * Bp, n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    int r = 0;
+    if (u_apply) r = get_rows(h, h->loop_prev_u + 2 * N * Bp, u_apply, 2);
+    if (!r && x0) r = get_rows(h, h->P.x0, x0, 7);
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------- multi-GPU -------

@@ -38,206 +38,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  : "memory");
 }
 
-// exp(x) for x <= 0 (RBF kernel argument -0.5 * squared distance): Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2,
-// degree-13 Taylor/Horner (truncation 4e-18 relative), exponent-field scaling.  ~20 FP64-pipe instructions against
-// ~30 for the generic libdevice exp (no special cases needed here); arguments below -700 are clamped
-// (result 1e-304 instead of a denormal/zero: absolute difference < 1e-300).
-__device__ __forceinline__ double exp_neg(double x)
-{
-    x = fmax(x, -700.0);
-    const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest integer in the low bits
-    const double t = fma(x, 1.4426950408889634, SHIFT);
-    const int n = __double2loint(t);
-    const double nf = t - SHIFT;
-    double r = fma(nf, -6.93147180369123816490e-01, x);
-    r = fma(nf, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;                       // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                     // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                    // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                    // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                   // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                     // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                    // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);                    // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                    // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                   // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                   // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
-
-// 2^t for t <= 0 (RBF argument pre-scaled by -0.5*log2(e) on the host): n = rint(t), r = t - n exactly, |r| <= 1/2,
-// 2^r by degree-13 Horner in r with coefficients ln2^k/k! (truncation 4e-18), exponent-field scaling.
-// 17 FP64-pipe instructions; arguments below -1000 are clamped (2^-1000 = 1e-301 instead of a denormal/zero).
-__device__ __forceinline__ double exp2_neg(double t)
-{
-    t = fmax(t, -1000.0);
-    const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52
-    const double tt = t + SHIFT;
-    const int n = __double2loint(tt);
-    const double r = t - (tt - SHIFT);
-    double p = 1.3691488853904128e-12;
-    p = fma(p, r, 2.5678435993488206e-11);
-    p = fma(p, r, 4.4455382718708116e-10);
-    p = fma(p, r, 7.054911620801123e-09);
-    p = fma(p, r, 1.01780860092397e-07);
-    p = fma(p, r, 1.321548679014431e-06);
-    p = fma(p, r, 1.5252733804059841e-05);
-    p = fma(p, r, 0.0001540353039338161);
-    p = fma(p, r, 0.0013333558146428443);
-    p = fma(p, r, 0.009618129107628477);
-    p = fma(p, r, 0.05550410866482158);
-    p = fma(p, r, 0.24022650695910072);
-    p = fma(p, r, 0.6931471805599453);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
-
-struct Jac {
-    // d f / d x : rows 0,1 x cols {psi,vx,vy}; row 2 = e_r; rows 3..5 x cols 2..6 ; row 6 = 0
-    double j0[3], j1[3];
-    double jr[3][5];
-    // d f / d u : rows 3..5 x 2 ; row 6 = [0 1]
-    double ju[3][2];
-};
-
-template <bool GP>
-__device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__restrict__ gpsm, int gp_stride,
-                                           const double x[7], const double u[2], double p, const double gpx[7],
-                                           double trig, double f[7], Jac &J)
-{
-    const double psi = x[2], vx = x[3], vy = x[4], r = x[5], dl = x[6];
-    const double u0 = u[0], u1 = u[1];
-    const double im = 1.0 / o.mass, iiz = 1.0 / o.iz, L = o.lr + o.lf, c = o.lr / L, iL = 1.0 / L, q = 1.0 - p;
-    double sp, cp, sd, cd;
-    sincos(psi, &sp, &cp);
-    sincos(dl, &sd, &cd);
-    const double D = vx + 1e-99;
-    const double iD = 1.0 / D;
-    const double a = (vy + o.lf * r) * iD;
-    const double Ff = o.cf2 * (dl - a);
-    const double Fr = o.cr2 * (o.lr * r - vy) * iD;
-    const double kin = u1 * vx + dl * u0;
-
-    f[0] = vx * cp - vy * sp;
-    f[1] = vx * sp + vy * cp;
-    f[2] = r;
-    f[3] = p * (u0 - im * Ff * sd + vy * r) + q * u0;
-    f[4] = p * (im * (Fr + Ff * cd) - vx * r) + q * (kin * c);
-    f[5] = p * (iiz * (o.lf * Ff * cd - o.lr * Fr)) + q * (kin * iL);
-    f[6] = u1;
-
-    J.j0[0] = -f[1]; J.j0[1] = cp; J.j0[2] = -sp;
-    J.j1[0] = f[0];  J.j1[1] = sp; J.j1[2] = cp;
-
-    const double Ff_vx = o.cf2 * a * iD, Ff_vy = -o.cf2 * iD, Ff_r = -o.cf2 * o.lf * iD, Ff_d = o.cf2;
-    const double Fr_vx = -Fr * iD, Fr_vy = -o.cr2 * iD, Fr_r = o.cr2 * o.lr * iD;
-    const double t1 = Ff_d * cd - Ff * sd;
-    // row 3 (v_x)
-    J.jr[0][0] = 0.0;
-    J.jr[0][1] = p * (-sd * Ff_vx * im);
-    J.jr[0][2] = p * (-sd * Ff_vy * im + r);
-    J.jr[0][3] = p * (-sd * Ff_r * im + vy);
-    J.jr[0][4] = -p * (Ff_d * sd + Ff * cd) * im;
-    J.ju[0][0] = 1.0; J.ju[0][1] = 0.0;
-    // row 4 (v_y)
-    J.jr[1][0] = 0.0;
-    J.jr[1][1] = p * ((Fr_vx + cd * Ff_vx) * im - r) + q * u1 * c;
-    J.jr[1][2] = p * (Fr_vy + cd * Ff_vy) * im;
-    J.jr[1][3] = p * ((Fr_r + cd * Ff_r) * im - vx);
-    J.jr[1][4] = p * t1 * im + q * u0 * c;
-    J.ju[1][0] = q * dl * c; J.ju[1][1] = q * vx * c;
-    // row 5 (yaw rate)
-    J.jr[2][0] = 0.0;
-    J.jr[2][1] = p * (o.lf * cd * Ff_vx - o.lr * Fr_vx) * iiz + q * u1 * iL;
-    J.jr[2][2] = p * (o.lf * cd * Ff_vy - o.lr * Fr_vy) * iiz;
-    J.jr[2][3] = p * (o.lf * cd * Ff_r - o.lr * Fr_r) * iiz;
-    J.jr[2][4] = p * o.lf * t1 * iiz + q * u0 * iL;
-    J.ju[2][0] = q * dl * iL; J.ju[2][1] = q * vx * iL;
-
-    if (GP) {
-        const int dz = o.gp_dz, M = o.gp_M;
-        double z[ADMPC_DZMAX];
-#pragma unroll
-        for (int d = 0; d < ADMPC_DZMAX; d++) {
-            if (d < dz) {
-                const int fi = o.gp_feat[d];
-                double v = 0.0;
-                // feature select without dynamic register indexing
-#pragma unroll
-                for (int s = 2; s < 7; s++) if (fi == s) v = gpx[s] * trig + x[s] * (1.0 - trig);
-                if (fi == 7) v = u0;
-                if (fi == 8) v = u1;
-                z[d] = v;
-            }
-        }
-        for (int j = 0; j < o.gp_nout; j++) {
-            // blob per output: M points of {a_0..a_{dz-1}, c, sigma_f*alpha} with a_d = log2(e) X_d / ell_d^2 and
-            // c = -0.5 log2(e) sum_d X_d^2/ell_d^2, so that  log2 k(z, X_i) = q + c_i + a_i . z,
-            // q = -0.5 log2(e) sum_d z_d^2/ell_d^2  (expanded square: 4 FMAs per point instead of 12 ops; the
-            // cancellation costs ~1e-15 absolute in the exponent).  Tail: 1/ell_d^2 (dz values), y_mean.
-            const double *blk = gpsm + (size_t)j * gp_stride;
-            const double *w = blk + (size_t)M * (dz + 2);
-            double wv[ADMPC_DZMAX];
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) wv[d] = (d < dz) ? w[d] : 0.0;
-            double q = 0.0;
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) q = fma(z[d] * wv[d], z[d], q);
-            q *= -0.5 * 1.4426950408889634;
-            double m = 0.0, g[ADMPC_DZMAX], G2[ADMPC_DZMAX];
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) { g[d] = 0.0; G2[d] = 0.0; }
-            if (dz == 4) {
-                // hot case: 4 features -> 48 B per point, three LDS.128
-#pragma unroll 4
-                for (int i = 0; i < M; i++) {
-                    const double2 *pt = reinterpret_cast<const double2 *>(blk + (size_t)i * 6);
-                    const double2 a01 = pt[0], a23 = pt[1], ca = pt[2];
-                    const double t = fma(a23.y, z[3], fma(a23.x, z[2], fma(a01.y, z[1], fma(a01.x, z[0], q + ca.x))));
-                    const double ka = exp2_neg(t) * ca.y;
-                    m += ka;
-                    G2[0] = fma(ka, a01.x, G2[0]); G2[1] = fma(ka, a01.y, G2[1]);
-                    G2[2] = fma(ka, a23.x, G2[2]); G2[3] = fma(ka, a23.y, G2[3]);
-                }
-            } else {
-                for (int i = 0; i < M; i++) {
-                    const double *pt = blk + (size_t)i * (dz + 2);
-                    double t = q + pt[dz];
-#pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) t = fma(pt[d], z[d], t);
-                    const double ka = exp2_neg(t) * pt[dz + 1];
-                    m += ka;
-#pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G2[d] = fma(ka, pt[d], G2[d]);
-                }
-            }
-            // d mu / d z_d = -sum_i ka_i (z_d - X_id)/ell_d^2 = -(z_d/ell_d^2 * m - ln2 * G2_d)
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) g[d] = fma(0.6931471805599453, G2[d], -(z[d] * wv[d]) * m);
-            m += w[dz];   // y_mean
-            const int row = o.gp_row[j] - 3;       // 0..2
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
-                if (rr == row) {
-                    f[3 + rr] += m;
-#pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) {
-                        if (d < dz) {
-                            const int fi = o.gp_feat[d];
-#pragma unroll
-                            for (int s = 2; s < 7; s++) if (fi == s) J.jr[rr][s - 2] += (1.0 - trig) * g[d];
-                            if (fi == 7) J.ju[rr][0] += g[d];
-                            if (fi == 8) J.ju[rr][1] += g[d];
-                        }
-                    }
-                }
-            }
-        }
-    }
-}
+#include "model.cuh"
 
 // One RK4 step with forward sensitivities. Sensitivity state: rows 0..5 x 7 columns [x2..x6 | u0 u1];
 // row 6 (delta) is analytic: d delta / d delta = 1, d delta / d u1 = t.

@@ -49,7 +49,7 @@ static double np_interp1(double x, const std::vector<double> &xp, const std::vec
 }
 
 struct TrackHost {
-    std::vector<double> dev;      // packed: x[L] y[L] psi[L] cdist[L] | tabx[H] taby[H] tabpsi[H] tabv[H]
+    std::vector<double> dev;      // packed: x[L] y[L] psi[L] cdist[L] psi_unwrapped[L] vel[L] | tabx[H] taby[H] tabpsi[H] tabv[H]
     int L = 0, H = 0, stop = 0;
 };
 
@@ -80,6 +80,8 @@ int refgen_build_track(int L, const double *traj, int H, double dt, TrackHost &T
     T.dev.insert(T.dev.end(), y.begin(), y.end());
     T.dev.insert(T.dev.end(), psi.begin(), psi.end());
     T.dev.insert(T.dev.end(), cd.begin(), cd.end());
+    T.dev.insert(T.dev.end(), psiu.begin(), psiu.end());
+    T.dev.insert(T.dev.end(), vel.begin(), vel.begin() + L);
     T.dev.insert(T.dev.end(), tx.begin(), tx.end());
     T.dev.insert(T.dev.end(), ty.begin(), ty.end());
     T.dev.insert(T.dev.end(), tp.begin(), tp.end());
@@ -88,15 +90,33 @@ int refgen_build_track(int L, const double *traj, int H, double dt, TrackHost &T
 }
 
 #define REF_TILE 1024
-// one thread per instance; the track polyline is swept through shared memory in tiles (broadcast reads)
-__global__ void __launch_bounds__(256) refgen_kernel(const Params P, const double *__restrict__ trk, int L, int H, double *info)
+#define REF_HMAX 64
+// numpy.interp on the device with a forward-moving bracket (abscissae are non-decreasing along the horizon)
+__device__ __forceinline__ double interp_fwd(double s, const double *__restrict__ xp, const double *__restrict__ fp, int L, int &j)
+{
+    if (s < xp[0]) return fp[0];
+    if (s >= xp[L - 1]) return fp[L - 1];
+    while (j + 1 < L - 1 && xp[j + 1] <= s) j++;
+    if (xp[j] == s) return fp[j];
+    const double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+    return __dadd_rn(__dmul_rn(slope, s - xp[j]), fp[j]);
+}
+
+// one thread per instance; the track polyline is swept through shared memory in tiles (broadcast reads).
+// ANCHOR = false: literal get_waypoints (abscissae measured from the start of the track window, ref_traj.py:128-131).
+// ANCHOR = true : extension for a shared global track: abscissae start at the closest waypoint of each vehicle
+//                 (what the reference gets implicitly because its planner publishes a window that starts at the car).
+template <bool ANCHOR>
+__global__ void __launch_bounds__(256) refgen_kernel(const Params P, const double *__restrict__ trk, int L, int H, double dt, double *info)
 {
     __shared__ double sx[REF_TILE], sy[REF_TILE];
     const int N = P.o.N, Bp = P.Bp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = i < P.B;
     const double *tx = trk, *ty = trk + L, *tpsi = trk + 2 * L, *tcd = trk + 3 * L;
-    const double *tabx = trk + 4 * (size_t)L, *taby = tabx + H, *tabp = taby + H, *tabv = tabp + H;
+    const double *tpsiu = trk + 4 * (size_t)L, *tvel = trk + 5 * (size_t)L;
+    const double *tabx = trk + 6 * (size_t)L, *taby = tabx + H, *tabp = taby + H, *tabv = tabp + H;
+    double lx_[ANCHOR ? REF_HMAX : 1], ly_[ANCHOR ? REF_HMAX : 1], lp_[ANCHOR ? REF_HMAX : 1], lv_[ANCHOR ? REF_HMAX : 1];
     const double X0 = act ? P.x0[(size_t)0 * Bp + i] : 0.0, Y0 = act ? P.x0[(size_t)1 * Bp + i] : 0.0;
     const double psi0 = act ? P.x0[(size_t)2 * Bp + i] : 0.0;
     // (1) closest waypoint: argmin of sqrt(dx^2 + dy^2), first minimum (ref_traj.py:101); no FMA contraction so that
@@ -123,6 +143,30 @@ __global__ void __launch_bounds__(256) refgen_kernel(const Params P, const doubl
         info[(size_t)0 * Bp + i] = tcd[ci];
         info[(size_t)1 * Bp + i] = __dadd_rn(__dmul_rn(-sin(pw), ex), __dmul_rn(cos(pw), ey));
         info[(size_t)2 * Bp + i] = bound_pi(psi_init - pw);
+    }
+    if (ANCHOR) {
+        // per-vehicle arc-length tables: s_h = cdist[ci] + sum_{m<=h} dt * vel[ci+m]   (0.01 beyond the end, :125-126)
+        double fit = 0.0, cprev = 0.0;
+        int jb = ci;
+        for (int hh = 0; hh < H; hh++) {
+            const int vi = ci + hh;
+            fit = __dadd_rn(fit, __dmul_rn(dt, (vi < L) ? tvel[vi] : 0.01));
+            const double sq = tcd[ci] + fit;
+            int j1 = jb, j2 = jb, j3 = jb, j4 = jb;
+            lx_[hh] = interp_fwd(sq, tcd, tx, L, j1);
+            ly_[hh] = interp_fwd(sq, tcd, ty, L, j2);
+            lp_[hh] = interp_fwd(sq, tcd, tpsiu, L, j3);
+            const double cq = interp_fwd(sq, tcd, tcd, L, j4);
+            jb = j1;
+            if (hh >= 1) lv_[hh - 1] = (cq - cprev) / dt;
+            cprev = cq;
+        }
+        lv_[H - 1] = lv_[H - 2];
+        // blended speed reference: [v2 v2 v2 | v[2..H-2]]  (in place, back to front)
+        for (int hh = H - 1; hh >= 3; hh--) lv_[hh] = lv_[hh - 1];
+        const double v2 = lv_[2];
+        lv_[0] = v2; lv_[1] = v2;
+        tabx = lx_; taby = ly_; tabp = lp_; tabv = lv_;
     }
     // (3) references: heading fixed relative to the vehicle heading (ref_traj.py:30-35,143-145), 3-point blend from the
     //     current pose (:157-167), padding to N+1, heading unwrap of run_optimization (ad_3d_optimizer.py:420-438)
@@ -159,7 +203,8 @@ __global__ void __launch_bounds__(256) refgen_kernel(const Params P, const doubl
     for (int j = H; j <= N; j++) put(j, lx, ly, lp, tabv[H - 1]);       // set_reference_trajectory padding
 }
 
-void launch_refgen(const Params &P, const double *trk, int L, int H, double *info, cudaStream_t s)
+void launch_refgen(const Params &P, const double *trk, int L, int H, double dt, int anchor, double *info, cudaStream_t s)
 {
-    refgen_kernel<<<(P.Bp + 255) / 256, 256, 0, s>>>(P, trk, L, H, info);
+    if (anchor) refgen_kernel<true><<<(P.Bp + 255) / 256, 256, 0, s>>>(P, trk, L, H, dt, info);
+    else refgen_kernel<false><<<(P.Bp + 255) / 256, 256, 0, s>>>(P, trk, L, H, dt, info);
 }

@@ -130,12 +130,15 @@ class BatchSolver:
         check(self.L.admpc_batch_reset(self.h), "reset")
 
     # ---- reference generation on the device (RefTrajectory.get_waypoints for the whole batch) -----------------------
-    def set_track(self, traj, H=None, traj_dt=None):
-        """traj[L,6] = [vel, x, y, psi, cdist, curv] (the table RefTrajectory.set_traj builds); H >= N reference points."""
+    def set_track(self, traj, H=None, traj_dt=None, anchor=False):
+        """traj[L,6] = [vel, x, y, psi, cdist, curv] (the table RefTrajectory.set_traj builds); H >= N reference points.
+        anchor=True measures arc length from each vehicle's closest waypoint (shared global track) instead of from the
+        start of the window (the reference's literal behaviour)."""
         traj = _f64(traj)
         H = int(H if H is not None else self.N)
         dt = float(traj_dt if traj_dt is not None else self.opts.dt)
         check(self.L.admpc_batch_set_track(self.h, traj.shape[0], _dp(traj), H, dt), "set_track")
+        check(self.L.admpc_batch_set_track_anchor(self.h, int(anchor)), "set_track_anchor")
 
     def make_yref(self):
         check(self.L.admpc_batch_make_yref(self.h), "make_yref")
@@ -148,6 +151,22 @@ class BatchSolver:
         stop = C.c_int()
         check(self.L.admpc_batch_get_waypoint_info(self.h, _dp(s0), _dp(ey), _dp(ep), C.byref(stop)), "get_waypoint_info")
         return s0, ey, ep, bool(stop.value)
+
+    # ---- after-solve logic and closed loops on the device ------------------------------------------------------------
+    def postsolve(self, advance=False, safe_threshold=10):
+        check(self.L.admpc_batch_postsolve(self.h, int(advance), int(safe_threshold)), "postsolve")
+
+    def closed_loop(self, steps, use_track=True, safe_threshold=10, log=False):
+        """`steps` control steps on the device. Returns the plant-state log [steps+1,B,7] when log=True."""
+        buf = np.empty((steps + 1, self.B, 7)) if log else None
+        check(self.L.admpc_batch_closed_loop(self.h, int(steps), int(use_track), int(safe_threshold), _dp(buf)), "closed_loop")
+        return buf
+
+    def get_loop_info(self):
+        valid, cnt, ok = (np.empty(self.B, dtype=np.int32) for _ in range(3))
+        ua, x0 = np.empty((self.B, 2)), np.empty((self.B, 7))
+        check(self.L.admpc_batch_get_loop_info(self.h, _ip(valid), _ip(cnt), _ip(ok), _dp(ua), _dp(x0)), "get_loop_info")
+        return dict(valid=valid, safe_count=cnt, cmd_ok=ok, u_apply=ua, x0=x0)
 
     # ---- solve / outputs ------------------------------------------------------------------------------------
     def solve(self):

@@ -149,9 +149,20 @@ int admpc_batch_solve_host_async(admpc_batch *h, const double *x0, const double 
  * (traj[L][6] rows = [vel, x, y, psi, cdist, curv], ref_traj.py:84) with the generator's horizon H (>= N) and time step;
  * make_yref turns the CURRENT x0 of every instance (pose = x0[0..2]) into its yref, in place on the device. */
 int admpc_batch_set_track(admpc_batch *h, int L, const double *traj /*[L][6]*/, int H, double traj_dt);
+/* 0 (default): literal get_waypoints, arc lengths measured from the start of the track window (ref_traj.py:128-131);
+ * 1: extension for a shared global track -- arc lengths start at each vehicle's closest waypoint (H <= 64). */
+int admpc_batch_set_track_anchor(admpc_batch *h, int anchor_at_closest);
 int admpc_batch_make_yref(admpc_batch *h);
 int admpc_batch_get_yref(admpc_batch *h, double *yref /*[B][N*9+7]*/);
 int admpc_batch_get_waypoint_info(admpc_batch *h, double *s0 /*[B]*/, double *e_y0 /*[B]*/, double *e_psi0 /*[B]*/, int *stop);
+
+/* After-solve logic of the reference, batched on the device: is_valid_command
+ * (ad_mpc/ad_3d_optimizer.py:385-394), backup control (:469-476), safety counter (nodes/gp_ad_mpc_node.py:206-216);
+ * advance != 0 also integrates the nominal model one step with the applied control and installs the result as the
+ * next x0.  closed_loop runs `steps` control steps ([make_yref] -> solve -> postsolve) without a host round trip. */
+int admpc_batch_postsolve(admpc_batch *h, int advance, int safe_threshold);
+int admpc_batch_closed_loop(admpc_batch *h, int steps, int use_track, int safe_threshold, double *log_x /*[steps+1][B][7] or NULL*/);
+int admpc_batch_get_loop_info(admpc_batch *h, int *valid, int *safe_count, int *cmd_ok, double *u_apply /*[B][2]*/, double *x0 /*[B][7]*/);
 
 /* instrumentation: device time (CUDA events on the handle's stream) of the last solve and of its kernels.
  * name: "solve" | "prepare" | "qp" | "h2d" | "d2h" ; returns milliseconds in *ms. Needs admpc_batch_set_profiling(1)

@@ -39,7 +39,28 @@ def track_tables(traj, H, dt):
     return tab
 
 
-def get_waypoints(traj, H, dt, X0, Y0, psi0):
+def track_tables_anchored(traj, H, dt, ci):
+    """Extension (not in the reference): the same tables with arc length measured from waypoint `ci` of a shared global
+    track and the speed profile taken from that waypoint on."""
+    vel = traj[ci:, 0]
+    cd = traj[:, 4]
+    while len(vel) < H + 1:
+        vel = np.concatenate((vel, [0.01]))
+    fit = [0.0 + dt * vel[0]]
+    for h in range(1, H):
+        fit.append(fit[-1] + dt * vel[h])
+    fit = traj[ci, 4] + np.array(fit)
+    tab = {}
+    for key, col in (("x", 1), ("y", 2), ("psi", 3), ("cdist", 4), ("curv", 5)):
+        src = np.unwrap(traj[:, col]) if key == "psi" else traj[:, col]
+        tab[key] = np.interp(fit, cd, src)
+    v = np.diff(tab["cdist"]) / dt
+    tab["v"] = np.insert(v, len(v), v[-1])
+    tab["stop"] = bool(tab["cdist"][-1] == cd[-1])
+    return tab
+
+
+def get_waypoints(traj, H, dt, X0, Y0, psi0, anchor=False):
     """One pose -> dict like the reference's waypoint_dict (x_ref, y_ref, psi_ref, v_ref, s0, e_y0, e_psi0, stop)."""
     psi_init = bound_angle_within_pi(psi0)
     xy = traj[:, 1:3]
@@ -47,7 +68,7 @@ def get_waypoints(traj, H, dt, X0, Y0, psi0):
     pw = traj[ci, 3]
     rot = np.array([[np.cos(pw), np.sin(pw)], [-np.sin(pw), np.cos(pw)]])
     ef = rot @ (np.array([X0, Y0]) - xy[ci])
-    tab = track_tables(traj, H, dt)
+    tab = track_tables_anchored(traj, H, dt, ci) if anchor else track_tables(traj, H, dt)
     psi = bound_angle_within_pi(fix_angle_reference(tab["psi"], psi_init))
     out = dict(s0=traj[ci, 4], e_y0=ef[1], e_psi0=bound_angle_within_pi(psi_init - pw), stop=tab["stop"],
                cdist_ref=tab["cdist"], curv_ref=tab["curv"])
@@ -58,13 +79,13 @@ def get_waypoints(traj, H, dt, X0, Y0, psi0):
     return out
 
 
-def make_yref(traj, H, dt, x0, N):
+def make_yref(traj, H, dt, x0, N, anchor=False):
     """Batched: x0[B,7] -> yref[B, N*9+7] exactly as the node + optimizer assemble it."""
     B = x0.shape[0]
     yref = np.zeros((B, N * 9 + 7))
     info = np.zeros((B, 3))
     for b in range(B):
-        w = get_waypoints(traj, H, dt, x0[b, 0], x0[b, 1], x0[b, 2])
+        w = get_waypoints(traj, H, dt, x0[b, 0], x0[b, 1], x0[b, 2], anchor=anchor)
         ref = np.zeros((H, 7))                                   # gp_ad_mpc_node.py:180-185
         ref[:, 0], ref[:, 1], ref[:, 2], ref[:, 3] = w["x_ref"], w["y_ref"], w["psi_ref"], w["v_ref"]
         while ref.shape[0] < N + 1:                              # ad_3d_optimizer.py:343-345

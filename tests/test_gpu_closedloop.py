@@ -1,0 +1,95 @@
+"""GPU parity of the after-solve logic and the on-device closed loop against the Python/C oracle."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from ad_mpc_b200 import BatchSolver, default_opts
+from oracle import closedloop_oracle as clo
+from oracle import oracle as orc
+from util_parity import mirror_opts
+
+pytestmark = pytest.mark.gpu
+
+
+def _track(L=900, ds=0.4, R=50.0):
+    s = np.arange(L) * ds
+    th = s / R
+    psi = (th + math.pi / 2 + math.pi) % (2 * math.pi) - math.pi
+    return np.stack([np.full(L, 8.0), R * np.cos(th), R * np.sin(th), psi, s, np.full(L, 1.0 / R)], axis=1)
+
+
+def _setup(B, N, seed, spread=0.5):
+    traj = _track()
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, 600, size=B)              # vehicles anywhere along the shared global track (anchored mode)
+    x0 = np.zeros((B, 7))
+    x0[:, 0] = traj[idx, 1] + rng.normal(size=B) * spread
+    x0[:, 1] = traj[idx, 2] + rng.normal(size=B) * spread
+    x0[:, 2] = traj[idx, 3] + rng.normal(size=B) * 0.05
+    x0[:, 3] = 8.0 + rng.normal(size=B) * 0.5
+    x_init = np.repeat(x0[:, None, :], N + 1, axis=1)
+    u_init = np.zeros((B, N, 2))
+    return traj, x0, x_init, u_init
+
+
+def test_postsolve_validity_backup_counter_match_oracle():
+    B, N = 96, 20
+    traj, x0, x_init, u_init = _setup(B, N, 5, spread=0.5)
+    x0[:24, 0] += 9.0                                # far from the path: prediction fails the geometric check
+    opts = default_opts(N)
+    o = mirror_opts(opts)
+    s = BatchSolver(B, opts)
+    s.set_track(traj, H=N, traj_dt=opts.dt, anchor=True)
+    s.set_iterate(x_init, u_init); s.set_x0(x0); s.set_p(np.zeros(B))
+    log = s.closed_loop(2, use_track=True, safe_threshold=2, log=True)
+    g = s.get_loop_info()
+    rlog, r = clo.closed_loop(o, traj, N, opts.dt, x0, np.zeros(B), x_init, u_init, 2, threshold=2, anchor=True)
+    assert np.array_equal(g["valid"], r["valid"]) and (g["valid"] == 0).any() and (g["valid"] == 1).any()
+    assert np.array_equal(g["safe_count"], r["safe_count"]) and np.array_equal(g["cmd_ok"], r["cmd_ok"])
+    assert np.abs(g["u_apply"] - r["u_apply"]).max() < 1e-8
+    assert np.abs(log - rlog).max() < 1e-8 * 300
+    s.close()
+
+
+def test_closed_loop_tracks_the_reference_and_matches_oracle():
+    """10 control steps on the device == 10 oracle steps; the vehicles converge onto the path."""
+    B, N, T = 48, 20, 10
+    traj, x0, x_init, u_init = _setup(B, N, 6, spread=0.3)
+    opts = default_opts(N)
+    o = mirror_opts(opts)
+    s = BatchSolver(B, opts)
+    s.set_track(traj, H=N, traj_dt=opts.dt, anchor=True)
+    s.set_iterate(x_init, u_init); s.set_x0(x0); s.set_p(np.zeros(B))
+    log = s.closed_loop(T, use_track=True, log=True)
+    rlog, r = clo.closed_loop(o, traj, N, opts.dt, x0, np.zeros(B), x_init, u_init, T, anchor=True)
+    err = np.abs(log - rlog) / np.maximum(1.0, np.abs(rlog))
+    assert err.max() < 1e-7, err.max()               # 10 chained solves: looser than the single-step 1e-8
+    g = s.get_loop_info()
+    assert (g["valid"] == 1).all() and np.array_equal(g["safe_count"], r["safe_count"])
+    # speed stays near the 8 m/s reference and nobody leaves the road
+    assert np.abs(log[-1][:, 3] - 8.0).max() < 1.5
+    rad = np.hypot(log[-1][:, 0], log[-1][:, 1])
+    assert np.abs(rad - 50.0).max() < 1.5
+    s.close()
+
+
+def test_closed_loop_full_size_runs_on_device():
+    """B = 16384 closed loops x 5 steps: no failures, all predictions healthy, timing printed."""
+    B, N, T = 16384, 20, 5
+    traj, x0, x_init, u_init = _setup(B, N, 7, spread=0.3)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    s.set_track(traj, H=N, traj_dt=opts.dt, anchor=True)
+    s.set_iterate(x_init, u_init); s.set_x0(x0); s.set_p(np.zeros(B))
+    s.closed_loop(2, use_track=True)                 # warm-up
+    s.set_iterate(x_init, u_init); s.set_x0(x0)
+    s.timer_start()
+    s.closed_loop(T, use_track=True)
+    ms = s.timer_stop()
+    g = s.get_loop_info()
+    st, _, _ = s.get_status()
+    assert (st == 0).all() and (g["valid"] == 1).all() and np.isfinite(g["x0"]).all()
+    print("closed loop B=%d: %.3f ms per control step (%.2f M vehicle-steps/s)" % (B, ms / T, B * T / ms / 1e3))
+    s.close()

@@ -45,6 +45,23 @@ def test_refgen_matches_oracle_and_reference(golden_dir, H, N):
     s.close()
 
 
+@pytest.mark.parametrize("H,N", [(20, 20), (40, 20)])
+def test_refgen_anchored_matches_oracle(golden_dir, H, N):
+    """Extension mode (arc length measured from each vehicle's closest waypoint) against its numpy restatement."""
+    g = np.load(os.path.join(golden_dir, "refgen.npz"))
+    traj, dt, pose = g["H%d_traj" % H], float(g["H%d_dt" % H]), g["H%d_pose" % H]
+    x0 = _x0_from_pose(pose, np.random.default_rng(3))
+    s = BatchSolver(pose.shape[0], default_opts(N))
+    s.set_track(traj, H=H, traj_dt=dt, anchor=True)
+    s.set_x0(x0)
+    s.make_yref()
+    yref = s.get_yref()
+    ref, info = ro.make_yref(traj, H, dt, x0, N, anchor=True)
+    assert np.abs(yref - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+    assert np.array_equal(s.get_waypoint_info()[0], info[:, 0])
+    s.close()
+
+
 def test_refgen_feeds_the_solver_without_host_round_trip(golden_dir):
     """x0 -> make_yref (device) -> solve  ==  x0, yref(host oracle) -> solve."""
     from ad_mpc_b200 import workload as wl
