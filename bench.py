@@ -168,7 +168,10 @@ def run_ours(args):
     from ad_mpc_b200 import BatchSolver, PinnedArray, default_opts, _lib
     import ctypes as C
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
+    # keep NCCL's banner / debug lines off stdout: rank 0 prints exactly one JSON line there
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist = None
     if world > 1:
         import torch.distributed as dist          # plumbing only: rendezvous, barrier, max over ranks
