@@ -10,14 +10,15 @@ import math
 import numpy as np
 
 
-def bound_angle_within_pi(a):                      # ref_traj.py:27-28
-    return (a + np.pi) % (2.0 * np.pi) - np.pi
+def wrap_pi(a):
+    """angle wrapped to [-pi, pi) with numpy's modulo convention (ref_traj.py:27-28)."""
+    two_pi = 2.0 * np.pi
+    return (a + np.pi) % two_pi - np.pi
 
 
-def fix_angle_reference(angle_ref, angle_init):    # ref_traj.py:30-35
-    diff = bound_angle_within_pi(angle_ref - angle_init)
-    diff = np.unwrap(diff)
-    return angle_init + diff
+def heading_relative_to(psi_ref, psi_vehicle):
+    """reference headings made continuous around the vehicle heading (ref_traj.py:30-35)."""
+    return psi_vehicle + np.unwrap(wrap_pi(psi_ref - psi_vehicle))
 
 
 def track_tables(traj, H, dt):
@@ -62,15 +63,15 @@ def track_tables_anchored(traj, H, dt, ci):
 
 def get_waypoints(traj, H, dt, X0, Y0, psi0, anchor=False):
     """One pose -> dict like the reference's waypoint_dict (x_ref, y_ref, psi_ref, v_ref, s0, e_y0, e_psi0, stop)."""
-    psi_init = bound_angle_within_pi(psi0)
+    psi_init = wrap_pi(psi0)
     xy = traj[:, 1:3]
     ci = int(np.argmin(np.linalg.norm(xy - np.array([[X0, Y0]]), axis=1)))
     pw = traj[ci, 3]
     rot = np.array([[np.cos(pw), np.sin(pw)], [-np.sin(pw), np.cos(pw)]])
     ef = rot @ (np.array([X0, Y0]) - xy[ci])
     tab = track_tables_anchored(traj, H, dt, ci) if anchor else track_tables(traj, H, dt)
-    psi = bound_angle_within_pi(fix_angle_reference(tab["psi"], psi_init))
-    out = dict(s0=traj[ci, 4], e_y0=ef[1], e_psi0=bound_angle_within_pi(psi_init - pw), stop=tab["stop"],
+    psi = wrap_pi(heading_relative_to(tab["psi"], psi_init))
+    out = dict(s0=traj[ci, 4], e_y0=ef[1], e_psi0=wrap_pi(psi_init - pw), stop=tab["stop"],
                cdist_ref=tab["cdist"], curv_ref=tab["curv"])
     out["x_ref"] = np.hstack([np.linspace(X0, tab["x"][1], 3), tab["x"][2:-1]])
     out["y_ref"] = np.hstack([np.linspace(Y0, tab["y"][1], 3), tab["y"][2:-1]])
