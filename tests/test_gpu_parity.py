@@ -257,3 +257,74 @@ def test_scale_invariance_full_size():
     assert mixed_err(u[0], r["u"]) <= TOL
     assert np.array_equal(g["qp_iter"][:256], r["qp_iter"])
     s.close()
+
+
+def test_long_horizon_fallback_variants():
+    """N = 40 runs the shared-memory octet kernel, N = 90 the one-thread-per-instance kernel: same parity bar."""
+    for N, B in ((40, 24), (90, 12)):
+        batch = wl.make_batch(B, N, seed=31, p=1.0)
+        opts = default_opts(N)
+        s = BatchSolver(B, opts)
+        g = _gpu_step(s, batch)
+        r = oracle_batch(mirror_opts(opts), batch)
+        _compare(g, r)
+        s.close()
+
+
+def test_qp_variants_agree(monkeypatch):
+    """The three QP kernels are independent implementations of the same algorithm: identical statuses / iteration
+    counts and 1e-8 agreement on a batch with active bounds."""
+    B, N = 128, 20
+    batch = wl.make_batch(B, N, seed=77, p=0.5, perturb=5.0)
+    out = {}
+    for v in (1, 3, 4):
+        monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
+        s = BatchSolver(B, default_opts(N))
+        out[v] = _gpu_step(s, batch)
+        s.close()
+    for v in (1, 3):
+        assert np.array_equal(out[v]["qp_iter"], out[4]["qp_iter"]) and np.array_equal(out[v]["status"], out[4]["status"])
+        assert mixed_err(out[v]["u"], out[4]["u"]) <= TOL and mixed_err(out[v]["x"], out[4]["x"]) <= TOL
+
+
+def test_non_default_weights_and_quadratic_slack_penalty():
+    """Python-default weights of AD3DOptimizer (ad_3d_optimizer.py:45-47: q = [10,10,50,0,0,0,1], r = [1,100]),
+    W_e = 1e-6 q (:151), plus a quadratic slack term (Zl, Zu > 0) and tighter input bounds."""
+    B, N = 96, 20
+    batch = wl.make_batch(B, N, seed=41, p=0.0, perturb=4.0)
+    q = [10, 10, 50, 0.0, 0.0, 0.0, 1]
+    opts = default_opts(N, W=q + [1.0, 100.0], We=[1e-6 * v for v in q], Zl=[0.5, 2.0], Zu=[0.5, 2.0],
+                        lbu=[-3.0, -1.0], ubu=[2.0, 1.0])
+    s = BatchSolver(B, opts)
+    g = _gpu_step(s, batch)
+    r = oracle_batch(mirror_opts(opts), batch)
+    assert (np.abs(g["u"][..., 0]) > 1.99).any()          # the tighter acceleration bound is exercised
+    _compare(g, r)
+    s.close()
+
+
+def test_error_paths():
+    from ad_mpc_b200 import _lib
+    import ctypes as C
+    L = _lib.load()
+    s = BatchSolver(8, default_opts(20))
+    model = wl.make_gp(M=8, seed=1)
+    bad = dict(model, feat=(0, 4, 5, 6))                   # p_x as a GP feature would break the A-structure
+    with pytest.raises(_lib.AdmpcError):
+        s.set_gp(bad)
+    with pytest.raises(_lib.AdmpcError):
+        s.make_yref()                                      # no track set
+    assert L.admpc_batch_set_x0(s.h, None) == -1
+    s.close()
+    cap = AcadosOcpSolverB200(default_opts(20))
+    with pytest.raises(_lib.AdmpcError):
+        cap.set(3, "yref", np.zeros(5))                    # wrong length
+    with pytest.raises(_lib.AdmpcError):
+        cap.set(2, "lbx", np.zeros(1))                     # per-stage bound changes are not supported
+    with pytest.raises(_lib.AdmpcError):
+        cap.set(0, "nonsense", np.zeros(1))
+    o = default_opts(20)
+    h = C.c_void_p()
+    assert L.admpc_batch_create(C.byref(o), 0, 0, C.byref(h)) == -1       # B must be positive
+    o.N = 1000
+    assert L.admpc_batch_create(C.byref(o), 4, 0, C.byref(h)) == -1       # N > ADMPC_NMAX
