@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
         with open(obj + ".ptxas.log", "w") as f:
             f.write(r.stderr)
         objs.append(obj)
-    cmd = [NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", SO] + objs + ["-ldl"]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", SO] + objs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
