@@ -73,6 +73,7 @@ SYMBOLS = {
     "admpc_batch_set_track": (C.c_int, [_vp, C.c_int, _dp, C.c_int, C.c_double]),
     "admpc_batch_set_track_anchor": (C.c_int, [_vp, C.c_int]),
     "admpc_batch_make_yref": (C.c_int, [_vp]),
+    "admpc_batch_solve_pose_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip]),
     "admpc_batch_get_yref": (C.c_int, [_vp, _dp]),
     "admpc_batch_get_waypoint_info": (C.c_int, [_vp, _dp, _dp, _dp, _ip]),
     "admpc_batch_postsolve": (C.c_int, [_vp, C.c_int, C.c_int]),

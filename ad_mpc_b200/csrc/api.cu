@@ -593,6 +593,18 @@ extern "C" int admpc_batch_make_yref(admpc_batch *h)
     return 0;
 }
 
+// pose-only variant of solve_host: H2D(x0, p) -> make_yref on the device -> solve -> D2H(u, x, status); async.
+extern "C" int admpc_batch_solve_pose_async(admpc_batch *h, const double *x0, const double *p_scalar, double *u_out,
+                                            double *x_out, int *status_out)
+{
+    if (!h || !x0) return ADMPC_E_ARG;
+    int r;
+    if ((r = admpc_batch_set_x0(h, x0))) return r;
+    if (p_scalar && (r = admpc_batch_set_p_scalar(h, p_scalar))) return r;
+    if ((r = admpc_batch_make_yref(h))) return r;
+    return solve_host_enqueue(h, nullptr, nullptr, nullptr, u_out, x_out, status_out);
+}
+
 extern "C" int admpc_batch_get_yref(admpc_batch *h, double *yref) { return get_rows(h, h->P.yref, yref, h->P.o.N * 9 + 7); }
 
 extern "C" int admpc_batch_get_waypoint_info(admpc_batch *h, double *s0, double *e_y0, double *e_psi0, int *stop)

@@ -282,6 +282,18 @@ class PipelinedSolver:
         self.wait()
         return u_out, x_out, status_out
 
+    def set_track(self, traj, H=None, traj_dt=None, anchor=False):
+        for s in self.parts:
+            s.set_track(traj, H=H, traj_dt=traj_dt, anchor=anchor)
+
+    def solve_from_pose(self, x0, p, u_out, x_out, status_out):
+        """Control step from vehicle states only: reference generation, solve and read-back per chunk, pipelined."""
+        for s, (lo, hi) in zip(self.parts, self.ranges):
+            check(self.L.admpc_batch_solve_pose_async(s.h, _dp(x0[lo:hi]), _dp(p[lo:hi]), _dp(u_out[lo:hi]), _dp(x_out[lo:hi]),
+                                                     _ip(status_out[lo:hi])), "solve_pose_async")
+        self.wait()
+        return u_out, x_out, status_out
+
     def kernel_launches(self):
         return sum(s.kernel_launches() for s in self.parts)
 

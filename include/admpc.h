@@ -153,6 +153,10 @@ int admpc_batch_set_track(admpc_batch *h, int L, const double *traj /*[L][6]*/, 
  * 1: extension for a shared global track -- arc lengths start at each vehicle's closest waypoint (H <= 64). */
 int admpc_batch_set_track_anchor(admpc_batch *h, int anchor_at_closest);
 int admpc_batch_make_yref(admpc_batch *h);
+/* pose-only step: H2D(x0, p) -> make_yref -> solve -> D2H(u, x, status), enqueued on the handle's stream (complete with
+ * admpc_batch_wait).  Replaces get_waypoints + set_reference + run_optimization of one control step for B vehicles. */
+int admpc_batch_solve_pose_async(admpc_batch *h, const double *x0, const double *p_scalar, double *u_out,
+                                 double *x_out, int *status_out);
 int admpc_batch_get_yref(admpc_batch *h, double *yref /*[B][N*9+7]*/);
 int admpc_batch_get_waypoint_info(admpc_batch *h, double *s0 /*[B]*/, double *e_y0 /*[B]*/, double *e_psi0 /*[B]*/, int *stop);
 

@@ -124,3 +124,27 @@ def test_refgen_full_size_properties():
         assert s0[b] == traj[int(np.argmin(dist)), 4]
     print("refgen B=%d L=%d: %.3f ms, %.1f GB/s written" % (B, L, ms, B * (N * 9 + 7) * 8 / ms / 1e6))
     s.close()
+
+
+def test_pipelined_pose_only_step_equals_two_stage_path(golden_dir):
+    """PipelinedSolver.solve_from_pose (H2D poses -> refgen -> solve -> D2H, 3 chunks) == make_yref + solve on one handle."""
+    from ad_mpc_b200 import PipelinedSolver
+    g = np.load(os.path.join(golden_dir, "refgen.npz"))
+    traj, dt, pose = g["H20_traj"], float(g["H20_dt"]), g["H20_pose"]
+    N = 20
+    x0 = _x0_from_pose(pose, np.random.default_rng(4))
+    B = x0.shape[0]
+    xin = np.repeat(x0[:, None, :], N + 1, axis=1)
+    p = np.zeros(B)
+    ps = PipelinedSolver(B, default_opts(N), chunks=3)
+    ps.set_track(traj, H=20, traj_dt=dt, anchor=True)
+    ps.set_iterate(xin, np.zeros((B, N, 2)))
+    u, x, st = np.empty((B, N, 2)), np.empty((B, N + 1, 7)), np.empty(B, dtype=np.int32)
+    ps.solve_from_pose(x0, p, u, x, st)
+    s = BatchSolver(B, default_opts(N))
+    s.set_track(traj, H=20, traj_dt=dt, anchor=True)
+    s.set_iterate(xin, np.zeros((B, N, 2))); s.set_x0(x0); s.set_p(p)
+    s.make_yref(); s.solve()
+    assert np.array_equal(st, s.get_status()[0])
+    assert np.array_equal(u, s.get_u()) and np.array_equal(x, s.get_x())
+    ps.close(); s.close()
