@@ -123,6 +123,7 @@ struct admpc_batch {
     int qp_variant = 0;      // 0 auto(=4), 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu)
     long long launches = 0;
     float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
+    char *pack = nullptr, *gpack = nullptr;     // packed [u | x | status] block of this rank / of all ranks (root)
     nccl_comm comm = nullptr;
     int rank = 0, nranks = 1;
 };
@@ -197,7 +198,7 @@ extern "C" int admpc_batch_free(admpc_batch *h)
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
-    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i);
+    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack);
     for (auto &e : h->ev) cudaEventDestroy(e);
     cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
     cudaStreamDestroy(h->stream);
@@ -762,40 +763,37 @@ extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, doubl
     const Params &P = h->P;
     const int N = P.o.N, B = P.B;
     const size_t nu = (size_t)B * N * 2, nx = (size_t)B * (N + 1) * 7;
-    // instance-major blocks on every rank
-    launch_transpose_out(P.ub, h->stage_u, B, P.Bp, N * 2, h->stream);
-    launch_transpose_out(P.xb, h->stage_x, B, P.Bp, (N + 1) * 7, h->stream);
+    const size_t bytes = (nu + nx) * sizeof(double) + (size_t)B * sizeof(int);      // one packed block per rank
+    if (!h->pack) CUDA_CHECK_RET(cudaMalloc(&h->pack, bytes));
+    if (h->rank == root && !h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, bytes * h->nranks));
+    // instance-major [u | x | status] block, then ONE send per rank and one receive per peer on the root
+    double *pu = (double *)h->pack, *px = pu + nu;
+    int *pst = (int *)(px + nx);
+    launch_transpose_out(P.ub, pu, B, P.Bp, N * 2, h->stream);
+    launch_transpose_out(P.xb, px, B, P.Bp, (N + 1) * 7, h->stream);
     h->launches += 2;
     CUDA_CHECK_RET(cudaGetLastError());
-    static double *gu = nullptr, *gx = nullptr;
-    static int *gs = nullptr;
-    static size_t cap = 0;
-    if (h->rank == root && cap < (size_t)h->nranks * (nu + nx)) {
-        cudaFree(gu); cudaFree(gx); cudaFree(gs);
-        CUDA_CHECK_RET(cudaMalloc(&gu, (size_t)h->nranks * nu * sizeof(double)));
-        CUDA_CHECK_RET(cudaMalloc(&gx, (size_t)h->nranks * nx * sizeof(double)));
-        CUDA_CHECK_RET(cudaMalloc(&gs, (size_t)h->nranks * B * sizeof(int)));
-        cap = (size_t)h->nranks * (nu + nx);
-    }
+    CUDA_CHECK_RET(cudaMemcpyAsync(pst, P.status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
     NCCL_CHECK_RET(g_nccl.GroupStart());
-    NCCL_CHECK_RET(g_nccl.Send(h->stage_u, nu, NCCL_FLOAT64, root, h->comm, h->stream));
-    NCCL_CHECK_RET(g_nccl.Send(h->stage_x, nx, NCCL_FLOAT64, root, h->comm, h->stream));
-    NCCL_CHECK_RET(g_nccl.Send(P.status, (size_t)B, NCCL_INT32, root, h->comm, h->stream));
-    if (h->rank == root) {
-        for (int r = 0; r < h->nranks; r++) {
-            NCCL_CHECK_RET(g_nccl.Recv(gu + (size_t)r * nu, nu, NCCL_FLOAT64, r, h->comm, h->stream));
-            NCCL_CHECK_RET(g_nccl.Recv(gx + (size_t)r * nx, nx, NCCL_FLOAT64, r, h->comm, h->stream));
-            NCCL_CHECK_RET(g_nccl.Recv(gs + (size_t)r * B, (size_t)B, NCCL_INT32, r, h->comm, h->stream));
-        }
+    if (h->rank != root) NCCL_CHECK_RET(g_nccl.Send(h->pack, bytes, NCCL_INT8, root, h->comm, h->stream));
+    else {
+        for (int r = 0; r < h->nranks; r++)
+            if (r != root) NCCL_CHECK_RET(g_nccl.Recv(h->gpack + (size_t)r * bytes, bytes, NCCL_INT8, r, h->comm, h->stream));
     }
     NCCL_CHECK_RET(g_nccl.GroupEnd());
     if (h->rank == root) {
-        if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all, gu, (size_t)h->nranks * nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all, gx, (size_t)h->nranks * nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all, gs, (size_t)h->nranks * B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK_RET(cudaMemcpyAsync(h->gpack + (size_t)root * bytes, h->pack, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        if (u_all || x_all || status_all) {
+            for (int r = 0; r < h->nranks; r++) {
+                const char *blk = h->gpack + (size_t)r * bytes;
+                if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all + (size_t)r * nu, blk, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all + (size_t)r * nx, blk + nu * sizeof(double), nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all + (size_t)r * B, blk + (nu + nx) * sizeof(double), (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            }
+            CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+        }
     }
-    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
-    return 0;
+    return 0;       // stream-ordered: admpc_batch_wait (or the next synchronising call) completes it
 }
 
 extern "C" int admpc_batch_barrier(admpc_batch *h)
