@@ -244,6 +244,48 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     }
 }
 
+// ---- corrector backward sweep: vector part only, ONE __syncwarp per stage --------------------------------------------
+// Every g-lane rebuilds h = P rb + p itself from the record and the published p_{k+1}; g_u reaches the p-lanes by two
+// shuffles; p_k is published in the other half of a double buffer for the next stage.
+__device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, double *xs, int N, int l)
+{
+    const double hdt = o.dt;
+    const int v = (l < 9) ? l : 0;                              // v < 7: M-column v ; v = 7, 8: x0, x1
+    const int gb = (v < 2) ? R_BAR + 3 + v : (v < 7) ? R_GX + v : R_GX + (v - 7);
+    const int mOff = R_M + ((v < 7) ? v : 0) * 6;
+    const double m6 = (v == 1) ? hdt : (v == 6) ? 1.0 : 0.0;
+    const double gm = (v < 7) ? 1.0 : 0.0, gh = (v < 7) ? 0.0 : 1.0;
+    const bool h1sel = (v == 8);
+    const int sx = (v >= 2 && v < 7) ? v : (v == 8) ? 1 : 0;    // state index of the p entry this lane produces
+    const bool isP = (l >= 2 && l < 9);
+    const bool kfj = (l == 10);
+    double *pva = xs + X_PV, *pvb = xs + X_HV;
+    if (l < 7) pva[l] = sm[N * R_STRIDE + l];
+    __syncwarp();
+    double *st = sm + (N - 1) * R_STRIDE;
+    for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
+        const double2 b01 = ld2(st + R_PB), b23 = ld2(st + R_PB + 2), b45 = ld2(st + R_PB + 4);
+        const double2 p01 = ld2(pva), p23 = ld2(pva + 2), p45 = ld2(pva + 4);
+        const double h0 = b01.x + p01.x, h1 = b01.y + p01.y, h2 = b23.x + p23.x, h3 = b23.y + p23.y;
+        const double h4 = b45.x + p45.x, h5 = b45.y + p45.y, h6 = st[R_PB + 6] + pva[6];
+        const double2 m01 = ld2(st + mOff), m23 = ld2(st + mOff + 2), m45 = ld2(st + mOff + 4);
+        double d = m6 * h6, d2 = m01.x * h0;
+        d = fma(m01.y, h1, d); d2 = fma(m23.x, h2, d2);
+        d = fma(m23.y, h3, d); d2 = fma(m45.x, h4, d2);
+        d = fma(m45.y, h5, d) + d2;
+        const double g = st[gb] + fma(gm, d, gh * (h1sel ? h1 : h0));
+        const double gu0 = __shfl_sync(FULL, g, 0), gu1 = __shfl_sync(FULL, g, 1);
+        const double gi00 = st[R_GI + 0], gi01 = st[R_GI + 1], gi11 = st[R_GI + 2];
+        const double c0 = kfj ? gi01 : gi00, c1 = kfj ? gi11 : gi01;
+        const double kf = -(c0 * gu0 + c1 * gu1);
+        if (l == 9 || l == 10) st[R_KF + (l - 9)] = kf;
+        const double pvv = g + st[R_K0 + sx] * gu0 + st[R_K1 + sx] * gu1;
+        if (isP) pvb[sx] = pvv;
+        __syncwarp();
+        double *t = pva; pva = pvb; pvb = t;
+    }
+}
+
 // ---- sequential forward roll-out (matrix role: lane r < 7 carries ddx_k[r]) -------------------------------------------
 // The state is broadcast through a double-buffered 8-double slot (1 STS + LDS.128s + one __syncwarp per stage).
 template <bool ADJ>
@@ -561,7 +603,7 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
                 }
                 __syncwarp();
                 // ================= corrector ===========================================================================
-                w_backward<false>(o, sm, xs, N, l);
+                w_backward_vec(o, sm, xs, N, l);
                 w_forward<true>(o, sm, xs, N, l);
             }
         }
