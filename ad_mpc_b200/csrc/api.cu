@@ -813,7 +813,7 @@ struct sim_car_solver_capsule {
     admpc_batch *h = nullptr;
     int N = 0;
     std::vector<double> x0, yref, p, x, u, pi, lam, t, sl, su;
-    bool iterate_dirty = false;
+    bool iterate_dirty = false, duals_stale = false;
     int status = 0, qp_status = 0, qp_iter = 0;
     double time_tot = 0.0;
     double res[4] = {0, 0, 0, 0};
@@ -934,13 +934,11 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
     float ms = 0;
     if ((r = admpc_batch_timer_stop(h, &ms))) return r;
     c->time_tot = ms * 1e-3;
+    // primal solution and statuses now; multipliers / slacks are fetched on first use (most callers only read x, u)
     if ((r = admpc_batch_get_x(h, c->x.data()))) return r;
     if ((r = admpc_batch_get_u(h, c->u.data()))) return r;
-    if ((r = admpc_batch_get_pi(h, c->pi.data()))) return r;
-    if ((r = admpc_batch_get_lam(h, c->lam.data()))) return r;
-    if ((r = admpc_batch_get_t(h, c->t.data()))) return r;
-    if ((r = admpc_batch_get_slacks(h, c->sl.data(), c->su.data()))) return r;
     if ((r = admpc_batch_get_status(h, &c->status, &c->qp_status, &c->qp_iter))) return r;
+    c->duals_stale = true;
     CUDA_CHECK_RET(cudaMemcpy2D(c->res, sizeof(double), h->P.res_out, (size_t)h->P.Bp * sizeof(double), sizeof(double), 4, cudaMemcpyDeviceToHost));
     return c->status;
 }
@@ -953,6 +951,14 @@ extern "C" int sim_car_acados_get(sim_car_solver_capsule *c, int stage, const ch
     if (!strcmp(field, "x")) { if (n != 7) return ADMPC_E_ARG; memcpy(out, &c->x[(size_t)stage * 7], 56); return 0; }
     if (stage >= N) { admpc_set_error("sim_car_acados_get", "field has no entry at the terminal node"); return ADMPC_E_ARG; }
     if (!strcmp(field, "u")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->u[(size_t)stage * 2], 16); return 0; }
+    if (c->duals_stale) {
+        int r;
+        if ((r = admpc_batch_get_pi(c->h, c->pi.data()))) return r;
+        if ((r = admpc_batch_get_lam(c->h, c->lam.data()))) return r;
+        if ((r = admpc_batch_get_t(c->h, c->t.data()))) return r;
+        if ((r = admpc_batch_get_slacks(c->h, c->sl.data(), c->su.data()))) return r;
+        c->duals_stale = false;
+    }
     if (!strcmp(field, "pi")) { if (n != 7) return ADMPC_E_ARG; memcpy(out, &c->pi[(size_t)stage * 7], 56); return 0; }
     if (!strcmp(field, "sl")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->sl[(size_t)stage * 2], 16); return 0; }
     if (!strcmp(field, "su")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->su[(size_t)stage * 2], 16); return 0; }
