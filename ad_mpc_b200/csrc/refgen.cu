@@ -119,21 +119,38 @@ __global__ void __launch_bounds__(256) refgen_kernel(const Params P, const doubl
     double lx_[ANCHOR ? REF_HMAX : 1], ly_[ANCHOR ? REF_HMAX : 1], lp_[ANCHOR ? REF_HMAX : 1], lv_[ANCHOR ? REF_HMAX : 1];
     const double X0 = act ? P.x0[(size_t)0 * Bp + i] : 0.0, Y0 = act ? P.x0[(size_t)1 * Bp + i] : 0.0;
     const double psi0 = act ? P.x0[(size_t)2 * Bp + i] : 0.0;
-    // (1) closest waypoint: argmin of sqrt(dx^2 + dy^2), first minimum (ref_traj.py:101); no FMA contraction so that
-    //     ties resolve exactly like numpy
-    double best = INFINITY;
-    int ci = 0;
+    // (1) closest waypoint: argmin_j sqrt(dx^2 + dy^2), first minimum, exactly as numpy resolves it (ref_traj.py:101).
+    //     sqrt is monotone, so min_j sqrt(d2_j) = sqrt(min_j d2_j): pass 1 finds the smallest squared distance without
+    //     any square root; pass 2 takes the first waypoint whose ROUNDED distance equals the rounded minimum (waypoints
+    //     within a few ulp of the minimum are the only ones that need a sqrt).  No FMA contraction in d2.
+    double m2 = INFINITY;
     for (int t0 = 0; t0 < L; t0 += REF_TILE) {
         const int n = min(REF_TILE, L - t0);
         __syncthreads();
         for (int j = threadIdx.x; j < n; j += blockDim.x) { sx[j] = tx[t0 + j]; sy[j] = ty[t0 + j]; }
         __syncthreads();
+#pragma unroll 4
         for (int j = 0; j < n; j++) {
             const double dx = sx[j] - X0, dy = sy[j] - Y0;
-            const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-            if (d < best) { best = d; ci = t0 + j; }
+            m2 = fmin(m2, __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
         }
     }
+    const double smin = sqrt(m2), thr = m2 * (1.0 + 2e-15);
+    int ci = -1;
+    for (int t0 = 0; t0 < L; t0 += REF_TILE) {
+        const int n = min(REF_TILE, L - t0);
+        if (L > REF_TILE) {
+            __syncthreads();
+            for (int j = threadIdx.x; j < n; j += blockDim.x) { sx[j] = tx[t0 + j]; sy[j] = ty[t0 + j]; }
+            __syncthreads();
+        }
+        for (int j = 0; j < n; j++) {
+            const double dx = sx[j] - X0, dy = sy[j] - Y0;
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (ci < 0 && d2 <= thr && sqrt(d2) == smin) ci = t0 + j;
+        }
+    }
+    if (ci < 0) ci = 0;
     if (!act) return;
     // (2) Frenet errors (ref_traj.py:104-117)
     const double pw = tpsi[ci];

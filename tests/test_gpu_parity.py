@@ -328,3 +328,16 @@ def test_error_paths():
     assert L.admpc_batch_create(C.byref(o), 0, 0, C.byref(h)) == -1       # B must be positive
     o.N = 1000
     assert L.admpc_batch_create(C.byref(o), 4, 0, C.byref(h)) == -1       # N > ADMPC_NMAX
+
+
+def test_c_example_runs():
+    """The plain-C example (reference main_sim_car.c sequence) links against libadmpc_b200.so and converges."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "main_sim_car_b200")
+    if not os.path.exists(exe):
+        subprocess.run(["/usr/bin/gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "main_sim_car_b200.c"),
+                        "-o", exe, "-L", os.path.join(root, "ad_mpc_b200"), "-ladmpc_b200",
+                        "-Wl,-rpath," + os.path.join(root, "ad_mpc_b200"), "-lm"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "EXAMPLE_OK" in out.stdout, out.stdout[-800:] + out.stderr[-400:]

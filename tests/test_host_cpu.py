@@ -247,3 +247,14 @@ def test_world_size_2_shard_broadcast_gather_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "SHARD_OK" in out.stdout
+
+
+def test_c_example_compiles_against_the_header():
+    """examples/main_sim_car_b200.c (the reference's main_sim_car.c call sequence) builds with plain gcc + the C ABI."""
+    import __graft_entry__ as g
+    g.build()
+    exe = os.path.join(ROOT, "examples", "main_sim_car_b200")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "main_sim_car_b200.c"),
+                    "-o", exe, "-L", os.path.join(ROOT, "ad_mpc_b200"), "-ladmpc_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "ad_mpc_b200"), "-lm"], check=True)
+    assert os.path.exists(exe)
