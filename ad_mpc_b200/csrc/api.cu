@@ -159,16 +159,27 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     struct Item { double **p; size_t rows; };
     const size_t nX = (size_t)(N + 1) * 7, nU = (size_t)N * 2, nPi = (size_t)N * 7, nC = (size_t)N * NC;
     double *x0, *yref, *pp, *gps;
+    // Interface arrays always; QP workspaces only for the kernel variant this handle will run: the warp-per-instance
+    // kernel (N <= 31) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
+    // thread-per-instance kernel streams a 35 KB/instance SoA workspace.
+    const int variant = h->qp_variant ? h->qp_variant : (N <= 31 ? 4 : 3);
+    const bool need_ws3 = (variant == 3 || (variant == 4 && N > 31)) && N <= 80;
+    const bool need_ws1 = (variant == 1) || N > 80;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
-        {&P.lin, (size_t)(N + 1) * LIN_ROWS},
-        {&P.dx, nX}, {&P.du, nU}, {&P.pi, nPi}, {&P.lam, nC}, {&P.t, nC}, {&P.sl, nU}, {&P.su, nU},
-        {&P.rgu, nU}, {&P.rgx, nX}, {&P.rgsl, nU}, {&P.rgsu, nU}, {&P.rb, nPi}, {&P.rd, nC}, {&P.rm, nC},
-        {&P.K, (size_t)N * 14}, {&P.Ginv, (size_t)N * 3}, {&P.P, (size_t)(N + 1) * 28}, {&P.Pb, nPi}, {&P.kf, nU}, {&P.pv, nX},
-        {&P.ddu, nU}, {&P.ddx, nX}, {&P.dpi, nPi}, {&P.dlam, nC}, {&P.dt, nC}, {&P.dsl, nU}, {&P.dsu, nU},
-        {&P.res_out, 4}, {&P.ws, (size_t)qp_smem_ws_rows(N)},
+        {&P.lin, (size_t)(N + 1) * LIN_ROWS}, {&P.res_out, 4},
     };
+    if (need_ws3) items.push_back({&P.ws, (size_t)qp_smem_ws_rows(N)});
+    if (need_ws1) {
+        std::vector<Item> w1 = {
+            {&P.dx, nX}, {&P.du, nU}, {&P.pi, nPi}, {&P.lam, nC}, {&P.t, nC}, {&P.sl, nU}, {&P.su, nU},
+            {&P.rgu, nU}, {&P.rgx, nX}, {&P.rgsl, nU}, {&P.rgsu, nU}, {&P.rb, nPi}, {&P.rd, nC}, {&P.rm, nC},
+            {&P.K, (size_t)N * 14}, {&P.Ginv, (size_t)N * 3}, {&P.P, (size_t)(N + 1) * 28}, {&P.Pb, nPi}, {&P.kf, nU}, {&P.pv, nX},
+            {&P.ddu, nU}, {&P.ddx, nX}, {&P.dpi, nPi}, {&P.dlam, nC}, {&P.dt, nC}, {&P.dsl, nU}, {&P.dsu, nU},
+        };
+        items.insert(items.end(), w1.begin(), w1.end());
+    }
     size_t rows = 0;
     for (auto &it : items) rows += it.rows;
     CUDA_CHECK_RET(cudaMalloc(&h->pool, rows * Bp * sizeof(double)));
@@ -345,8 +356,11 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     const int variant = h->qp_variant ? h->qp_variant : 4;
     bool fused = false;
     if (variant == 4) fused = launch_qp_warp(P, h->stream);        // one warp per instance, N <= 31
-    if (!fused && variant >= 3) fused = launch_qp_smem(P, h->stream);
-    if (!fused) launch_qp(P, h->stream);
+    if (!fused && variant >= 3 && P.ws) fused = launch_qp_smem(P, h->stream);
+    if (!fused) {
+        if (!P.dx) { admpc_set_error("admpc_batch_solve", "QP workspace for this kernel variant was not allocated at create"); return ADMPC_E_STATE; }
+        launch_qp(P, h->stream);
+    }
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
     if (!fused) launch_update(P, h->stream);
     CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
