@@ -10,8 +10,11 @@
  *   - model f / VDE          : pinned against the reference's own CasADi C (oracle/_ref/libsim_car_ref.so)
  *   - RK4+sensitivities, cost scaling, multiplier conventions: pinned against the acados golden iterate
  *                              src/ad_mpc/sim_car_iterate.json (tests/golden/)
- *   - IPM iterate path / iteration counts, GP numerics: UNPINNED by reference fixtures (acados/HPIPM are not
- *                              vendored in the reference; no GP fixture ships) -- pinned by formula only.
+ *   - GP posterior mean      : pinned against the reference's own numeric predict() (model_fitting/gp.py imported with
+ *                              its symbolic dependencies stubbed; tests/golden/gp_reference.npz); the Jacobian by finite
+ *                              differences of that mean
+ *   - IPM iterate path / iteration counts: UNPINNED by reference fixtures (acados/HPIPM are not vendored in the
+ *                              reference) -- restated from the published algorithm, design choices in DESIGN.md.
  */
 #ifndef RTI_ORACLE_H_
 #define RTI_ORACLE_H_

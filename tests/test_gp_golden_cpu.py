@@ -1,0 +1,44 @@
+"""GP numerics pinned against the reference's own model_fitting/gp.py (tests/golden/gp_reference.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gpfit_oracle as gf
+from oracle import oracle as orc
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_oracle_gp_mean_matches_reference_predict(golden_dir, tag):
+    """orc_gp_predict fed with the reference's fitted model (x_train, K^-1 y, l, sigma_f, y_mean) reproduces the
+    reference's numeric predict() (gp.py:426-430)."""
+    g = np.load(os.path.join(golden_dir, "gp_reference.npz"))
+    X, al, ell = g[tag + "_X"], g[tag + "_K_inv_y"], g[tag + "_ell"]
+    dz = X.shape[1]
+    model = dict(X=X[None], alpha=al[None], ell=ell[None], sigma_f=np.array([float(g[tag + "_sigma_f"])]),
+                 y_mean=np.array([float(g[tag + "_y_mean"])]))
+    o = orc.default_opts(20)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=tuple(range(3, 3 + dz)), rows=(4,))
+    for z, mu_ref in zip(g[tag + "_xtest"], g[tag + "_mu"]):
+        mu, _ = orc.gp_predict(o, gp, z)
+        # K^-1 y of a fitted GP is large (+-1e3) with heavy cancellation in the sum: compare at the cancellation scale
+        scale = np.abs(al).sum() * float(g[tag + "_sigma_f"])
+        assert abs(mu[0] - mu_ref) <= 1e-13 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_gpfit_oracle_matches_reference_nll_and_alpha(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "gp_reference.npz"))
+    X, y = g[tag + "_X"], g[tag + "_y"]
+    dz = X.shape[1]
+    for theta, ref in zip(g[tag + "_thetas"], g[tag + "_nll"]):
+        p = np.exp(theta)
+        v = gf.nll(X, y, p[:dz], p[dz], p[dz + 1])
+        assert abs(v - ref) <= 1e-9 * max(1.0, abs(ref))
+    a = gf.alpha(X, y, g[tag + "_ell"], float(g[tag + "_sigma_f"]), float(g[tag + "_sigma_n"]))
+    ref = g[tag + "_K_inv_y"]
+    # K is ill-conditioned (sigma_n ~ 1e-2): inv(K) @ y of the reference vs a Cholesky solve agree to cond * eps
+    assert np.abs(a - ref).max() <= 1e-6 * np.abs(ref).max()
+    K = gf.train_kernel(X, g[tag + "_ell"], float(g[tag + "_sigma_f"]), float(g[tag + "_sigma_n"]))
+    assert np.abs(K @ ref - y).max() <= 1e-8 * max(1.0, np.abs(y).max())
