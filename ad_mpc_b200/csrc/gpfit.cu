@@ -1,0 +1,242 @@
+// gpfit.cu -- GP model update on the device: the dense linear algebra of CustomGPRegression.fit /
+// _nll (reference: model_fitting/gp.py:283-289,305-311,361-363) for one output dimension:
+//     K = sigma_f exp(-1/2 |x_i/l - x_j/l|^2) + sigma_n^2 I        (two-argument kernel call, gp.py:103-105)
+//     L = chol(K)
+//     alpha = K^-1 y                  (the vector the inference kernels consume; the reference forms inv(K) explicitly)
+//     nll = sum log L_ii + 1/2 y^T alpha + M/2 log 2 pi
+// The hyper-parameter search stays a host loop (L-BFGS-B like the reference, ad_mpc_b200/gpfit.py); every NLL
+// evaluation and the final alpha run here.  FP64 throughout: K has condition ~ sigma_f M / sigma_n^2.
+//
+// Blocked right-looking Cholesky on 32x32 tiles of the padded matrix (row-major, lower triangle):
+//   potrf32 (one CTA)  ->  trsm32 (one CTA per tile below the diagonal)  ->  syrk32 (one CTA per trailing tile pair).
+// The trailing update is the dense GEMM of this path (M^3/3 flops, 2.7 GFLOP at M = 2000); B200 has no FP64 tcgen05
+// kind and its FP64 DMMA peak equals the DFMA peak, so the tile GEMM is register-tiled DFMA (2x2 outputs per thread).
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+#define TB 32
+
+// K build: one thread per (i, j) of the padded Mp x Mp matrix; padding = identity
+__global__ void gpfit_build_kernel(const double *__restrict__ Xs, int M, int Mp, int dz, double sigma_f, double sn2,
+                                   double *__restrict__ A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= Mp || j >= Mp) return;
+    double v;
+    if (i < M && j < M) {
+        double d2 = 0.0;
+        for (int d = 0; d < dz; d++) { const double t = Xs[(size_t)i * dz + d] - Xs[(size_t)j * dz + d]; d2 = fma(t, t, d2); }
+        v = sigma_f * exp(-0.5 * d2) + ((i == j) ? sn2 : 0.0);
+    } else {
+        v = (i == j) ? 1.0 : 0.0;
+    }
+    A[(size_t)i * Mp + j] = v;
+}
+
+// Cholesky of the diagonal tile (j, j): 32x32 threads, tile in shared memory
+__global__ void __launch_bounds__(TB * TB) gpfit_potrf32(double *A, int Mp, int jb, int *fail)
+{
+    __shared__ double T[TB][TB + 1];
+    const int r = threadIdx.y, c = threadIdx.x;
+    double *Ajj = A + (size_t)(jb * TB) * Mp + jb * TB;
+    T[r][c] = Ajj[(size_t)r * Mp + c];
+    __syncthreads();
+    for (int k = 0; k < TB; k++) {
+        if (r == k && c == k) {
+            const double d = T[k][k];
+            if (!(d > 0.0)) *fail = 1;           // not positive definite (np.linalg.LinAlgError in the reference)
+            T[k][k] = sqrt(d);
+        }
+        __syncthreads();
+        if (c == k && r > k) T[r][k] /= T[k][k];
+        __syncthreads();
+        if (c > k && r >= c) T[r][c] -= T[r][k] * T[c][k];
+        __syncthreads();
+    }
+    Ajj[(size_t)r * Mp + c] = (c <= r) ? T[r][c] : 0.0;
+}
+
+// X = A_ij L_jj^-T for the tiles below the diagonal: one thread per row of the tile (32 rows), 4 tiles per CTA
+__global__ void __launch_bounds__(128) gpfit_trsm32(double *A, int Mp, int jb, int nb)
+{
+    __shared__ double Lt[TB][TB + 1];
+    for (int e = threadIdx.x; e < TB * TB; e += blockDim.x) {
+        const int r = e / TB, c = e % TB;
+        Lt[r][c] = A[(size_t)(jb * TB + r) * Mp + jb * TB + c];
+    }
+    __syncthreads();
+    const int tile = jb + 1 + blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (tile >= nb) return;
+    const int r = threadIdx.x & 31;
+    double *row = A + (size_t)(tile * TB + r) * Mp + jb * TB;
+    double x[TB];
+#pragma unroll
+    for (int c = 0; c < TB; c++) x[c] = row[c];
+#pragma unroll
+    for (int c = 0; c < TB; c++) {
+        double v = x[c];
+#pragma unroll
+        for (int m = 0; m < c; m++) v = fma(-x[m], Lt[c][m], v);
+        x[c] = v / Lt[c][c];
+    }
+#pragma unroll
+    for (int c = 0; c < TB; c++) row[c] = x[c];
+}
+
+// trailing update C_ik -= A_ij A_kj^T for i >= k > j: one CTA (16x16 threads, 2x2 outputs each) per tile pair
+__global__ void __launch_bounds__(256) gpfit_syrk32(double *A, int Mp, int jb, int nb)
+{
+    const int ti = jb + 1 + blockIdx.y, tk = jb + 1 + blockIdx.x;
+    if (ti >= nb || tk > ti) return;
+    __shared__ double Ai[TB][TB + 1], Ak[TB][TB + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 16 + tx;
+    for (int e = t; e < TB * TB; e += 256) {
+        const int r = e / TB, c = e % TB;
+        Ai[r][c] = A[(size_t)(ti * TB + r) * Mp + jb * TB + c];
+        Ak[r][c] = A[(size_t)(tk * TB + r) * Mp + jb * TB + c];
+    }
+    __syncthreads();
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+    const int r0 = ty * 2, k0 = tx * 2;
+#pragma unroll 8
+    for (int m = 0; m < TB; m++) {
+        const double a0 = Ai[r0][m], a1 = Ai[r0 + 1][m], b0 = Ak[k0][m], b1 = Ak[k0 + 1][m];
+        c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01); c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
+    }
+    double *C = A + (size_t)(ti * TB + r0) * Mp + tk * TB + k0;
+    C[0] -= c00; C[1] -= c01; C[Mp] -= c10; C[Mp + 1] -= c11;
+}
+
+// y <- L^-1 y, then y <- L^-T y (blocked by 32, single CTA), plus log-determinant and y0^T alpha
+__global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restrict__ A, int M, int Mp, double *y,
+                                                            const double *__restrict__ y0, double *out2)
+{
+    __shared__ double xb[TB];
+    __shared__ double red[32];
+    const int nb = Mp / TB, t = threadIdx.x;
+    // forward: L z = y
+    for (int b = 0; b < nb; b++) {
+        if (t < 32) {
+            double v = y[b * TB + t];
+            for (int c = 0; c < TB; c++) {
+                const double lcc = A[(size_t)(b * TB + c) * Mp + b * TB + c];
+                const double xc = __shfl_sync(0xffffffffu, v, c) / lcc;
+                if (t == c) v = xc;
+                else if (t > c) v = fma(-A[(size_t)(b * TB + t) * Mp + b * TB + c], xc, v);
+            }
+            xb[t] = v;
+            y[b * TB + t] = v;
+        }
+        __syncthreads();
+        for (int i = (b + 1) * TB + t; i < Mp; i += blockDim.x) {
+            const double *row = A + (size_t)i * Mp + b * TB;
+            double s = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < TB; c++) s = fma(row[c], xb[c], s);
+            y[i] -= s;
+        }
+        __syncthreads();
+    }
+    // backward: L^T alpha = z
+    for (int b = nb - 1; b >= 0; b--) {
+        if (t < 32) {
+            double v = y[b * TB + t];
+            for (int c = TB - 1; c >= 0; c--) {
+                const double lcc = A[(size_t)(b * TB + c) * Mp + b * TB + c];
+                const double xc = __shfl_sync(0xffffffffu, v, c) / lcc;
+                if (t == c) v = xc;
+                else if (t < c) v = fma(-A[(size_t)(b * TB + c) * Mp + b * TB + t], xc, v);
+            }
+            xb[t] = v;
+            y[b * TB + t] = v;
+        }
+        __syncthreads();
+        for (int i = t; i < b * TB; i += blockDim.x) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < TB; r++) s = fma(A[(size_t)(b * TB + r) * Mp + i], xb[r], s);
+            y[i] -= s;
+        }
+        __syncthreads();
+    }
+    // reductions: sum_i log L_ii (i < M) and y0^T alpha
+    double ld = 0.0, qa = 0.0;
+    for (int i = t; i < M; i += blockDim.x) { ld += log(A[(size_t)i * Mp + i]); qa = fma(y0[i], y[i], qa); }
+    for (int pass = 0; pass < 2; pass++) {
+        double v = pass ? qa : ld;
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((t & 31) == 0) red[t >> 5] = v;
+        __syncthreads();
+        if (t < 32) {
+            v = red[t];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (t == 0) out2[pass] = v;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int admpc_gp_fit(int device, int M, int dz, const double *X, const double *y, const double *ell,
+                            double sigma_f, double sigma_n, double *alpha_out, double *nll_out, float *ms_out)
+{
+    if (M < 1 || dz < 1 || dz > ADMPC_DZMAX || !X || !y || !ell) { admpc_set_error("admpc_gp_fit", "bad argument"); return ADMPC_E_ARG; }
+    int ndev = 0;
+    CUDA_CHECK_RET(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { admpc_set_error("admpc_gp_fit", "no such CUDA device"); return ADMPC_E_CUDA; }
+    CUDA_CHECK_RET(cudaSetDevice(device));
+    const int Mp = (M + TB - 1) / TB * TB, nb = Mp / TB;
+    std::vector<double> Xs((size_t)M * dz), yp(Mp, 0.0);
+    for (int i = 0; i < M; i++)
+        for (int d = 0; d < dz; d++) Xs[(size_t)i * dz + d] = X[(size_t)i * dz + d] / ell[d];     // cdist(x/l, x/l), gp.py:103
+    for (int i = 0; i < M; i++) yp[i] = y[i];
+    double *dXs = nullptr, *dA = nullptr, *dy = nullptr, *dy0 = nullptr, *dout = nullptr;
+    int *dfail = nullptr;
+    cudaStream_t s;
+    CUDA_CHECK_RET(cudaStreamCreate(&s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = 0;
+    do {
+#define GP_TRY(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { admpc_set_error(#call, cudaGetErrorString(e_)); rc = ADMPC_E_CUDA; break; } }
+        GP_TRY(cudaMalloc(&dXs, Xs.size() * sizeof(double)));
+        GP_TRY(cudaMalloc(&dA, (size_t)Mp * Mp * sizeof(double)));
+        GP_TRY(cudaMalloc(&dy, Mp * sizeof(double)));
+        GP_TRY(cudaMalloc(&dy0, Mp * sizeof(double)));
+        GP_TRY(cudaMalloc(&dout, 2 * sizeof(double)));
+        GP_TRY(cudaMalloc(&dfail, sizeof(int)));
+        GP_TRY(cudaMemcpyAsync(dXs, Xs.data(), Xs.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        GP_TRY(cudaMemcpyAsync(dy, yp.data(), Mp * sizeof(double), cudaMemcpyHostToDevice, s));
+        GP_TRY(cudaMemcpyAsync(dy0, yp.data(), Mp * sizeof(double), cudaMemcpyHostToDevice, s));
+        GP_TRY(cudaMemsetAsync(dfail, 0, sizeof(int), s));
+        GP_TRY(cudaEventRecord(e0, s));
+        dim3 bb(16, 16), bg((Mp + 15) / 16, (Mp + 15) / 16);
+        gpfit_build_kernel<<<bg, bb, 0, s>>>(dXs, M, Mp, dz, sigma_f, sigma_n * sigma_n, dA);
+        for (int j = 0; j < nb; j++) {
+            gpfit_potrf32<<<1, dim3(TB, TB), 0, s>>>(dA, Mp, j, dfail);
+            const int rem = nb - j - 1;
+            if (rem > 0) {
+                gpfit_trsm32<<<(rem + 3) / 4, 128, 0, s>>>(dA, Mp, j, nb);
+                gpfit_syrk32<<<dim3(rem, rem), dim3(16, 16), 0, s>>>(dA, Mp, j, nb);
+            }
+        }
+        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, dy, dy0, dout);
+        GP_TRY(cudaEventRecord(e1, s));
+        GP_TRY(cudaGetLastError());
+        double out2[2];
+        int fail = 0;
+        GP_TRY(cudaMemcpyAsync(out2, dout, sizeof out2, cudaMemcpyDeviceToHost, s));
+        GP_TRY(cudaMemcpyAsync(&fail, dfail, sizeof fail, cudaMemcpyDeviceToHost, s));
+        if (alpha_out) GP_TRY(cudaMemcpyAsync(alpha_out, dy, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+        GP_TRY(cudaStreamSynchronize(s));
+        if (fail) { admpc_set_error("admpc_gp_fit", "kernel matrix is not positive definite"); rc = ADMPC_E_ARG; break; }
+        if (nll_out) *nll_out = out2[0] + 0.5 * out2[1] + 0.5 * M * log(2.0 * 3.141592653589793);
+        if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+#undef GP_TRY
+    } while (0);
+    cudaFree(dXs); cudaFree(dA); cudaFree(dy); cudaFree(dy0); cudaFree(dout); cudaFree(dfail);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    return rc;
+}

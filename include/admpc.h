@@ -194,6 +194,13 @@ int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, cons
 int admpc_batch_gather(admpc_batch *h, int root, double *u_all /*[nranks*B][N*2]*/, double *x_all, int *status_all);
 int admpc_batch_barrier(admpc_batch *h);
 
+/* GP model update on the device (model_fitting/gp.py:283-289,305-311,361-363): for ONE output dimension builds
+ * K = sigma_f exp(-1/2 |x_i/l - x_j/l|^2) + sigma_n^2 I, factorises it (blocked FP64 Cholesky) and returns
+ * alpha = K^-1 y (what admpc_batch_set_gp consumes) and the negative log likelihood the reference minimises.
+ * y must already have its mean removed (gp.py:343).  ADMPC_E_ARG when K is not positive definite. */
+int admpc_gp_fit(int device, int M, int dz, const double *X /*[M][dz]*/, const double *y /*[M]*/, const double *ell /*[dz]*/,
+                 double sigma_f, double sigma_n, double *alpha_out /*[M] or NULL*/, double *nll_out, float *ms_out);
+
 /* FP64 peak probe: runs a dependent-free DFMA loop and returns achieved TFLOP/s (roofline denominator; there is
  * no FP64 entry in MEASURED_PEAKS.json). */
 int admpc_measure_fp64_peak(int device, double *tflops);
