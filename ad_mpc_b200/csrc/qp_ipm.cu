@@ -11,6 +11,9 @@
 
 #define AT(arr, row) (arr)[(size_t)(row) * Bp + i]
 
+// NaN-propagating max for the residual norms (fmax would hide a diverged instance)
+__device__ __forceinline__ double nmax1(double a, double b) { return (a > b || a != a) ? a : b; }
+
 // symmetric 7x7 packed lower: idx(i,j), i>=j
 __device__ __forceinline__ constexpr int sidx(int i, int j) { return (i >= j) ? (i * (i + 1) / 2 + j) : (j * (j + 1) / 2 + i); }
 
@@ -376,19 +379,19 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const Params P)
                 const double gsu = Ts * o.zu[j] + Ts * o.Zu[j] * su - lam[3 + j] - lam[8 + j];
                 AT(P.rgsl, k * 2 + j) = gsl;
                 AT(P.rgsu, k * 2 + j) = gsu;
-                ng = fmax(ng, fmax(fabs(g), fmax(fabs(gsl), fabs(gsu))));
+                ng = nmax1(ng, nmax1(fabs(g), nmax1(fabs(gsl), fabs(gsu))));
                 const double lo = o.lbu[j] - AT(P.ub, k * 2 + j), hi = o.ubu[j] - AT(P.ub, k * 2 + j);
                 const double r0 = t[j] - (du[j] - lo + sl), r1 = t[3 + j] - (hi - du[j] + su);
                 const double r2 = t[6 + j] - sl, r3 = t[8 + j] - su;
                 AT(P.rd, k * NC + j) = r0; AT(P.rd, k * NC + 3 + j) = r1;
                 AT(P.rd, k * NC + 6 + j) = r2; AT(P.rd, k * NC + 8 + j) = r3;
-                nd = fmax(nd, fmax(fmax(fabs(r0), fabs(r1)), fmax(fabs(r2), fabs(r3))));
+                nd = nmax1(nd, nmax1(nmax1(fabs(r0), fabs(r1)), nmax1(fabs(r2), fabs(r3))));
             }
             if (k >= 1) {
                 const double cur = AT(P.xb, k * 7 + 6);
                 const double r0 = t[2] - (dxk[6] - (o.lbx - cur)), r1 = t[5] - ((o.ubx - cur) - dxk[6]);
                 AT(P.rd, k * NC + 2) = r0; AT(P.rd, k * NC + 5) = r1;
-                nd = fmax(nd, fmax(fabs(r0), fabs(r1)));
+                nd = nmax1(nd, nmax1(fabs(r0), fabs(r1)));
             } else {
                 AT(P.rd, 2) = 0.0; AT(P.rd, 5) = 0.0;
             }
@@ -401,19 +404,19 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const Params P)
 #pragma unroll
                 for (int c = 0; c < 5; c++) v = fma(Mx[r][2 + c], dxk[2 + c], v);
                 AT(P.rb, k * 7 + r) = v;
-                nb = fmax(nb, fabs(v));
+                nb = nmax1(nb, fabs(v));
             }
             {
                 const double v = AT(lin, LIN_b + 6) - dxn[6] + dxk[6] + hdt * du[1];
                 AT(P.rb, k * 7 + 6) = v;
-                nb = fmax(nb, fabs(v));
+                nb = nmax1(nb, fabs(v));
             }
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 const bool on = !((c == 2 || c == 5) && k == 0);
                 const double m = on ? lam[c] * t[c] : 0.0;
                 AT(P.rm, k * NC + c) = m;
-                nm = fmax(nm, fabs(m));
+                nm = nmax1(nm, fabs(m));
                 summ += m;
             }
             // stationarity wrt x_k (k >= 1): Q dx + q + A^T pi_k - pi_{k-1} -/+ lam_x
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const Params P)
                         if (a == 6) g += pik[6] - lam[2] + lam[5];
                     }
                     AT(P.rgx, k * 7 + a) = g;
-                    ng = fmax(ng, fabs(g));
+                    ng = nmax1(ng, fabs(g));
                 }
             }
 #pragma unroll
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const Params P)
             for (int a = 0; a < 7; a++) {
                 const double g = o.We[a] * dxk[a] + AT(lin, LIN_q + a) - pim[a];
                 AT(P.rgx, N * 7 + a) = g;
-                ng = fmax(ng, fabs(g));
+                ng = nmax1(ng, fabs(g));
             }
         }
         const double mu = summ * inv_nc;

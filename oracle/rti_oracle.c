@@ -17,7 +17,7 @@
  *                             the reference's FULL_CONDENSING (acados_solver_sim_car.c:145) -- same QP, same solution
  *   orc_rti_step            : acados ocp_nlp_sqp_rti [EXT], options at acados_solver_sim_car.c:647-681
  * [EXT] = acados@91a01d4 / HPIPM / BLASFEO, pinned in requirements.txt:1 but not vendored; algorithm restated from
- * its published description and pinned by ad_mpc/sim_car_iterate.json (see tests/test_golden_iterate.py).
+ * its published description and pinned by ad_mpc/sim_car_iterate.json (see tests/test_oracle_golden.py).
  */
 #define _GNU_SOURCE
 #include "rti_oracle.h"
@@ -28,6 +28,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+/* NaN-propagating max: a NaN residual must surface in the norms (fmax would drop it) */
+static inline double nanmax(double a, double b) { return (a > b || a != a) ? a : b; }
 
 #define NX ORC_NX
 #define NU ORC_NU
@@ -310,7 +313,7 @@ static void ipm_residuals(const orc_opts *o, const orc_lin *lin, const double *d
                 w->rd[k][3 + j] = t[3 + j] - (duu[k * 2 + j] - du[j] + s->su[k * 2 + j]);
                 w->rd[k][6 + j] = t[6 + j] - s->sl[k * 2 + j];
                 w->rd[k][8 + j] = t[8 + j] - s->su[k * 2 + j];
-                ng = fmax(ng, fmax(fabs(g), fmax(fabs(w->rgsl[k][j]), fabs(w->rgsu[k][j]))));
+                ng = nanmax(ng, nanmax(fabs(g), nanmax(fabs(w->rgsl[k][j]), fabs(w->rgsu[k][j]))));
             }
             if (k >= 1) {
                 w->rd[k][2] = t[2] - (dx[6] - dlx[k]);
@@ -323,13 +326,13 @@ static void ipm_residuals(const orc_opts *o, const orc_lin *lin, const double *d
                 for (int l = 0; l < 7; l++) v += A[i * 7 + l] * dx[l];
                 for (int j = 0; j < 2; j++) v += B[i * 2 + j] * du[j];
                 w->rb[k][i] = v;
-                nb = fmax(nb, fabs(v));
+                nb = nanmax(nb, fabs(v));
             }
             for (int c = 0; c < NC; c++) {
                 if (!con_on(k, c)) { w->rm[k][c] = 0; continue; }
                 w->rm[k][c] = lam[c] * t[c];
-                nd = fmax(nd, fabs(w->rd[k][c]));
-                nm = fmax(nm, fabs(w->rm[k][c]));
+                nd = nanmax(nd, fabs(w->rd[k][c]));
+                nm = nanmax(nm, fabs(w->rm[k][c]));
                 summ += w->rm[k][c];
                 nc++;
             }
@@ -346,7 +349,7 @@ static void ipm_residuals(const orc_opts *o, const orc_lin *lin, const double *d
                     if (i == 6) g += -s->lam[k * NC + 2] + s->lam[k * NC + 5];
                 }
                 w->rgx[k][i] = g;
-                ng = fmax(ng, fabs(g));
+                ng = nanmax(ng, fabs(g));
             }
         }
     }
