@@ -160,10 +160,10 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     const size_t nX = (size_t)(N + 1) * 7, nU = (size_t)N * 2, nPi = (size_t)N * 7, nC = (size_t)N * NC;
     double *x0, *yref, *pp, *gps;
     // Interface arrays always; QP workspaces only for the kernel variant this handle will run: the warp-per-instance
-    // kernel (N <= 31) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
+    // kernel (N <= 63) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
     // thread-per-instance kernel streams a 35 KB/instance SoA workspace.
-    const int variant = h->qp_variant ? h->qp_variant : (N <= 31 ? 4 : 3);
-    const bool need_ws3 = (variant == 3 || (variant == 4 && N > 31)) && N <= 80;
+    const int variant = h->qp_variant ? h->qp_variant : (N <= 63 ? 4 : 3);
+    const bool need_ws3 = (variant == 3 || (variant == 4 && N > 63)) && N <= 80;
     const bool need_ws1 = (variant == 1) || N > 80;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
@@ -355,7 +355,7 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
     const int variant = h->qp_variant ? h->qp_variant : 4;
     bool fused = false;
-    if (variant == 4) fused = launch_qp_warp(P, h->stream);        // one warp per instance, N <= 31
+    if (variant == 4) fused = launch_qp_warp(P, h->stream);        // one / two warps per instance, N <= 63
     if (!fused && variant >= 3 && P.ws) fused = launch_qp_smem(P, h->stream);
     if (!fused) {
         if (!P.dx) { admpc_set_error("admpc_batch_solve", "QP workspace for this kernel variant was not allocated at create"); return ADMPC_E_STATE; }

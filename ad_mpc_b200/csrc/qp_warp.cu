@@ -354,29 +354,40 @@ __device__ __forceinline__ void w_adjoint(double *sm, double *xs, int N, int l)
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
+// NW = 1: one warp per instance (N <= 31).  NW = 2: two warps per instance (N <= 63): stage k lives in thread k of a
+// 64-thread CTA, the horizon-sequential sweeps run on warp 0 only, neighbour exchange and reductions cross the warp
+// boundary through a small shared-memory window with CTA barriers.
+#define XCH_STRIDE 15   // odd: conflict-free 64-bit accesses over consecutive stages
+#define XCH_SIZE (64 * XCH_STRIDE + 48)
+template <int NW> __device__ __forceinline__ void cta_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params P)
 {
     extern __shared__ __align__(16) double smw[];
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
-    const int l = threadIdx.x;
-    const int i = blockIdx.x;                    // one instance per warp
+    const int l = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const bool sweeper = (NW == 1) || wrp == 0;
+    const int i = blockIdx.x;                    // one instance per CTA
     double *sm = smw;
     double *xs = smw + N * R_STRIDE + 8;
+    double *xc = xs + X_SIZE;                    // NW == 2 only: exchange window [64][XCH_STRIDE] + 48 reduction slots
+    double *red = xc + 64 * XCH_STRIDE;
     const double Ts = o.dt, hdt = o.dt;
     if (P.lin_bad[i]) {                          // NaN/Inf in the linearisation: ACADOS_FAILURE, iterate untouched
-        if (l == 0) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+        if (threadIdx.x == 0) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
         return;
     }
     // ---- stage M into shared memory ------------------------------------------------------------------------------------
-    for (int e = l; e < 42 * N; e += 32) {
+    for (int e = threadIdx.x; e < 42 * N; e += 32 * NW) {
         const int k = e / 42, w = e - k * 42;
         const int cc = w / 6, r = w - cc * 6;
         const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp;
         sm[k * R_STRIDE + R_M + w] = (cc < 2) ? ATS(lin, LIN_B + r * 2 + cc) : ATS(lin, LIN_A + r * 5 + (cc - 2));
     }
     // ---- stage role: load this node's data, cold start ---------------------------------------------------------------------
-    const int k = l;
+    const int k = threadIdx.x;
     const bool isst = k < N, isterm = (k == N);
     StageState S;
 #pragma unroll
@@ -423,7 +434,7 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
             S.lam[6 + j] = o.mu0 / o.thr0; S.lam[8 + j] = o.mu0 / o.thr0;
         }
     }
-    __syncwarp();
+    cta_sync<NW>();
 
     const double inv_nc = 1.0 / (double)(NC * N - 2);
     int status = 1, iter = 0;
@@ -439,11 +450,24 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
             for (int a = 0; a < 7; a++) { lq[a] = ATS(lin, LIN_q + a); lb[a] = ATS(lin, LIN_b + a); }
             lr[0] = ATS(lin, LIN_r + 0); lr[1] = ATS(lin, LIN_r + 1);
         }
+        if (NW == 1) {
 #pragma unroll
-        for (int a = 0; a < 7; a++) {
-            const double up = __shfl_up_sync(FULL, S.pi[a], 1);
-            pim[a] = (k >= 1) ? up : 0.0;
-            dxn[a] = __shfl_down_sync(FULL, S.dx[a], 1);
+            for (int a = 0; a < 7; a++) {
+                const double up = __shfl_up_sync(FULL, S.pi[a], 1);
+                pim[a] = (k >= 1) ? up : 0.0;
+                dxn[a] = __shfl_down_sync(FULL, S.dx[a], 1);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 7; a++) { xc[k * XCH_STRIDE + a] = S.pi[a]; xc[k * XCH_STRIDE + 7 + a] = S.dx[a]; }
+            __syncthreads();
+            const int km = (k >= 1) ? k - 1 : 0, kp = (k < 63) ? k + 1 : 63;
+#pragma unroll
+            for (int a = 0; a < 7; a++) {
+                const double up = xc[km * XCH_STRIDE + a];
+                pim[a] = (k >= 1) ? up : 0.0;
+                dxn[a] = xc[kp * XCH_STRIDE + 7 + a];
+            }
         }
         double ng = 0, nb = 0, nd = 0, nm = 0, summ = 0;
         double *st = sm + (isst ? k : 0) * R_STRIDE;
@@ -526,16 +550,25 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
             }
         }
         ng = wmax(ng); nb = wmax(nb); nd = wmax(nd); nm = wmax(nm); summ = wsum(summ);
+        if (NW == 2) {
+            if (l == 0) { double *r = red + wrp * 8; r[0] = ng; r[1] = nb; r[2] = nd; r[3] = nm; r[4] = summ; }
+            __syncthreads();
+            ng = nmaxw(red[0], red[8]); nb = nmaxw(red[1], red[9]); nd = nmaxw(red[2], red[10]);
+            nm = nmaxw(red[3], red[11]); summ = red[4] + red[12];
+        }
         res0 = ng; res1 = nb; res2 = nd; res3 = nm;
         if (!(isfinite(ng) && isfinite(nb) && isfinite(nd) && isfinite(nm))) { status = 3; break; }
         if (ng < o.tol_stat && nb < o.tol_eq && nd < o.tol_ineq && nm < o.tol_comp) { status = 0; break; }
         if (iter >= o.iter_max) { status = 1; break; }
         const double mu = summ * inv_nc;
-        __syncwarp();
+        cta_sync<NW>();
 
         // ================= predictor ===================================================================================
-        w_backward<true>(o, sm, xs, N, l);
-        w_forward<false>(o, sm, xs, N, l);
+        if (sweeper) {
+            w_backward<true>(o, sm, xs, N, l);
+            w_forward<false>(o, sm, xs, N, l);
+        }
+        if (NW == 2) __syncthreads();
         double dsl[2], dsu[2], dtv[NC], dlv[NC];
         double an = 1.0, ad = 1.0;          // step length as a ratio an/ad (<= 1)
         double s1 = 0.0, s2 = 0.0;
@@ -584,8 +617,16 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
                 if (bn * ad < an * bd) { an = bn; ad = bd; }
             }
             an = __shfl_sync(FULL, an, 0); ad = __shfl_sync(FULL, ad, 0);     // one representative pair for all lanes
+            if (pass == 0) { s1 = wsum(s1); s2 = wsum(s2); }
+            if (NW == 2) {
+                double *r = red + 16 + pass * 16;
+                if (l == 0) { r[wrp * 4 + 0] = an; r[wrp * 4 + 1] = ad; r[wrp * 4 + 2] = s1; r[wrp * 4 + 3] = s2; }
+                __syncthreads();
+                an = r[0]; ad = r[1];
+                if (r[4] * ad < an * r[5]) { an = r[4]; ad = r[5]; }
+                s1 = r[2] + r[6]; s2 = r[3] + r[7];
+            }
             if (pass == 0) {
-                s1 = wsum(s1); s2 = wsum(s2);
                 const double a_aff = an / ad;
                 const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
                 double sigma = mu_aff / mu;
@@ -601,10 +642,13 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
                     barrier_w(o, k >= 1, S, it, Rt, Qt6, rt, qt6);
                     st[R_BAR + 3] = rt[0]; st[R_BAR + 4] = rt[1]; st[R_GX + 6] = qt6;
                 }
-                __syncwarp();
+                cta_sync<NW>();
                 // ================= corrector ===========================================================================
-                w_backward_vec(o, sm, xs, N, l);
-                w_forward<true>(o, sm, xs, N, l);
+                if (sweeper) {
+                    w_backward_vec(o, sm, xs, N, l);
+                    w_forward<true>(o, sm, xs, N, l);
+                }
+                if (NW == 2) __syncthreads();
             }
         }
         double alpha = an / ad;
@@ -623,7 +667,8 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
                 S.t[c] = fmax(S.t[c] + alpha * dtv[c], o.t_min);
             }
         }
-        w_adjoint(sm, xs, N, l);
+        if (sweeper) w_adjoint(sm, xs, N, l);
+        if (NW == 2) __syncthreads();
         if (isst) {
 #pragma unroll
             for (int a = 0; a < 7; a++) S.pi[a] += alpha * st[R_PB + a];
@@ -633,12 +678,12 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
 #pragma unroll
             for (int a = 0; a < 7; a++) S.dx[a] += alpha * prev[R_RB + a];
         }
-        __syncwarp();
+        cta_sync<NW>();
     }
     // ---- epilogue: statuses + fused RTI update (full step; duals <- QP duals) --------------------------------------------
     const int qps = (status == 0) ? 0 : ((status == 1) ? 2 : ((status == 2) ? 3 : 1));   // hpipm -> acados numbering
     const int nlp_status = (qps == 0 || qps == 2) ? 0 : 4;
-    if (l == 0) {
+    if (threadIdx.x == 0) {
         P.qp_status[i] = qps; P.qp_iter[i] = iter; P.status[i] = nlp_status;
         ATS(P.res_out, 0) = res0; ATS(P.res_out, 1) = res1; ATS(P.res_out, 2) = res2; ATS(P.res_out, 3) = res3;
     }
@@ -667,13 +712,23 @@ __global__ void __launch_bounds__(32, 12) qp_warp_kernel(const Params P)
 bool launch_qp_warp(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
-    if (N > 31) return false;
-    const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE) * sizeof(double);
-    static size_t configured = 0;
-    if (sm > configured) {
-        cudaFuncSetAttribute(qp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        configured = sm;
+    if (N > 63) return false;
+    if (N <= 31) {
+        const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE) * sizeof(double);
+        static size_t configured = 0;
+        if (sm > configured) {
+            cudaFuncSetAttribute(qp_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            configured = sm;
+        }
+        qp_warp_kernel<1><<<P.B, 32, sm, s>>>(P);
+    } else {
+        const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE + XCH_SIZE) * sizeof(double);
+        static size_t configured2 = 0;
+        if (sm > configured2) {
+            cudaFuncSetAttribute(qp_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            configured2 = sm;
+        }
+        qp_warp_kernel<2><<<P.B, 64, sm, s>>>(P);
     }
-    qp_warp_kernel<<<P.B, 32, sm, s>>>(P);
     return true;
 }

@@ -260,15 +260,32 @@ def test_scale_invariance_full_size():
 
 
 def test_long_horizon_fallback_variants():
-    """N = 40 runs the shared-memory octet kernel, N = 90 the one-thread-per-instance kernel: same parity bar."""
-    for N, B in ((40, 24), (90, 12)):
-        batch = wl.make_batch(B, N, seed=31, p=1.0)
+    """Horizon dispatch of the feedback kernel: N <= 31 one warp per instance, 32..63 two warps per instance, 64..80 the
+    shared-memory octet kernel, above that one thread per instance -- same parity bar on both sides of every edge."""
+    for N, B in ((31, 16), (32, 16), (40, 24), (63, 12), (64, 12), (90, 12)):
+        batch = wl.make_batch(B, N, seed=31, p=1.0, perturb=3.0 if N in (32, 63) else 1.0)
         opts = default_opts(N)
         s = BatchSolver(B, opts)
         g = _gpu_step(s, batch)
         r = oracle_batch(mirror_opts(opts), batch)
         _compare(g, r)
         s.close()
+
+
+def test_two_warp_kernel_matches_octet_kernel(monkeypatch):
+    """N = 40 with active bounds: the two-warps-per-instance kernel (default) against the octet kernel (variant 3)."""
+    B, N = 96, 40
+    batch = wl.make_batch(B, N, seed=78, p=0.5, perturb=5.0)
+    out = {}
+    for v in (3, 4):
+        monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
+        s = BatchSolver(B, default_opts(N))
+        out[v] = _gpu_step(s, batch)
+        s.close()
+    assert np.array_equal(out[3]["qp_iter"], out[4]["qp_iter"]) and np.array_equal(out[3]["status"], out[4]["status"])
+    assert mixed_err(out[3]["u"], out[4]["u"]) <= TOL and mixed_err(out[3]["x"], out[4]["x"]) <= TOL
+    r = oracle_batch(mirror_opts(default_opts(N)), batch)
+    _compare(out[4], r)
 
 
 def test_qp_variants_agree(monkeypatch):
