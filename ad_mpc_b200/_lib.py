@@ -94,6 +94,7 @@ SYMBOLS = {
     "admpc_batch_barrier": (C.c_int, [_vp]),
     "admpc_gp_fit": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_float)]),
     "admpc_measure_fp64_peak": (C.c_int, [C.c_int, _dp]),
+    "admpc_measure_fp64_mix": (C.c_int, [C.c_int, C.c_int, _dp]),
 }
 
 _lib = None

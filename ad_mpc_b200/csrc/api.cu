@@ -131,6 +131,8 @@ struct admpc_batch {
 static size_t rup(size_t v, size_t m) { return (v + m - 1) / m * m; }
 // doubles per GP output in the packed blob: M points x (dz + 2) + tail (dz inverse squared length scales, y_mean)
 static size_t gp_stride(int M, int dz) { return rup((size_t)M * (dz + 2) + dz + 1, 2); }
+// whole blob: nout outputs, then the 2^(j/GP_TAB) table of the device exp2 (model.cuh)
+static size_t gp_blob_doubles(int nout, int M, int dz) { return gp_stride(M, dz) * nout + GP_TAB; }
 
 extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, admpc_batch **out)
 {
@@ -236,9 +238,10 @@ static int upload_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, c
     for (int j = 0; j < nout; j++)
         if (rows[j] < 3 || rows[j] > 5) { admpc_set_error("admpc_batch_set_gp", "GP outputs must map to state rows 3..5"); return ADMPC_E_UNSUPPORTED; }
     const size_t stride = gp_stride(M, dz);
-    const size_t bytes = stride * nout * sizeof(double);
+    const size_t bytes = gp_blob_doubles(nout, M, dz) * sizeof(double);
     if (bytes > 220 * 1024) { admpc_set_error("admpc_batch_set_gp", "GP model exceeds the shared-memory staging budget (220 KB)"); return ADMPC_E_UNSUPPORTED; }
-    std::vector<double> blob(stride * nout, 0.0);
+    std::vector<double> blob(gp_blob_doubles(nout, M, dz), 0.0);
+    for (int j = 0; j < GP_TAB; j++) blob[stride * nout + j] = exp2((double)j / GP_TAB);
     for (int j = 0; j < nout; j++) {
         double *b = blob.data() + stride * j;
         const double L2E = 1.4426950408889634;
@@ -557,8 +560,16 @@ extern "C" int admpc_host_free(void *p) { CUDA_CHECK_RET(cudaFreeHost(p)); retur
 extern "C" int admpc_measure_fp64_peak(int device, double *tflops)
 {
     if (!tflops) return ADMPC_E_ARG;
-    const double v = run_fp64_peak(device);
+    const double v = run_fp64_peak(device, 0);
     if (v <= 0) { admpc_set_error("admpc_measure_fp64_peak", "CUDA failure"); return ADMPC_E_CUDA; }
+    *tflops = v;
+    return 0;
+}
+extern "C" int admpc_measure_fp64_mix(int device, int int_ops_per_8_dfma, double *tflops)
+{
+    if (!tflops || int_ops_per_8_dfma < 0 || (int_ops_per_8_dfma > 8 && int_ops_per_8_dfma != 16)) return ADMPC_E_ARG;
+    const double v = run_fp64_peak(device, int_ops_per_8_dfma);
+    if (v <= 0) { admpc_set_error("admpc_measure_fp64_mix", "CUDA failure"); return ADMPC_E_CUDA; }
     *tflops = v;
     return 0;
 }
@@ -753,7 +764,7 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
     if (h->rank != root) {
         nout = hdr[0]; M = hdr[1]; dz = hdr[2];
         const size_t stride = gp_stride(M, dz);
-        const size_t bytes = stride * nout * sizeof(double);
+        const size_t bytes = gp_blob_doubles(nout, M, dz) * sizeof(double);
         if (bytes > h->gp_blob_cap) {
             cudaFree(h->gp_blob);
             CUDA_CHECK_RET(cudaMalloc(&h->gp_blob, bytes));

@@ -22,6 +22,11 @@
 #define LIN_r 56
 #define LIN_ROWS 58
 
+// entries of the 2^(j/GP_TAB) table of the device exp2 (model.cuh), stored behind the last GP output in the blob
+#ifndef GP_TAB_BITS
+#define GP_TAB_BITS 6
+#endif
+#define GP_TAB (1 << GP_TAB_BITS)
 struct GpDev {
     // packed, 16-byte aligned GP block in HBM, staged to shared memory by one TMA bulk copy per CTA:
     //   per output j: pts[M][dz+2] = {log2e*X_id/ell_d^2 (dz), -0.5*log2e*sum_d X_id^2/ell_d^2, sigma_f*alpha_i},
@@ -70,4 +75,4 @@ void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, 
 void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]
 void launch_update(const Params &P, cudaStream_t s);
 void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
-double run_fp64_peak(int device);
+double run_fp64_peak(int device, int nint);

@@ -61,6 +61,48 @@ __device__ __forceinline__ double exp2_neg(double t)
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// 2^t for t <= 0, table-driven: t = n + j/GP_TAB + f with |f| <= 1/(2 GP_TAB); 2^(j/GP_TAB) from a GP_TAB-entry
+// shared-memory table (appended to the GP blob by the host), 2^f - 1 by a short Taylor/Horner polynomial (truncation
+// < 4e-18 relative), 2^n through the exponent field.  10 FP64-pipe instructions against 17 for exp2_neg; the clamp
+// (t < -1000 -> 2^-1000 = 1e-301 instead of a denormal/zero) is an integer compare.  With GP_TAB = 32 two lanes
+// conflict on a bank only when their indices differ by exactly 16.
+struct Exp2Part { double f, T; int nsh; };
+// front half: range reduction, table fetch, exponent increment (already shifted into the high word)
+__device__ __forceinline__ Exp2Part exp2_front(double t, uint32_t tab)       // tab: shared-space address of the table
+{
+    Exp2Part e;
+    const bool far = (unsigned)__double2hiint(t) > 0xC08F4000u;      // t < -1000: off the FP64 dependency chain
+    const double SHIFT = 6755399441055744.0 / GP_TAB;                // 1.5 * 2^(52 - GP_TAB_BITS)
+    const double tt = t + SHIFT;
+    const int ti = __double2loint(tt);                               // rint(t * GP_TAB)
+    e.f = t - (tt - SHIFT);                                          // |f| <= 1/(2 GP_TAB) for every finite t
+    asm("ld.shared.f64 %0, [%1];" : "=d"(e.T) : "r"(tab + ((ti & (GP_TAB - 1)) << 3)));
+    e.nsh = far ? (-1000 << 20) : ((ti << (20 - GP_TAB_BITS)) & 0xfff00000);
+    return e;
+}
+// back half: 2^f - 1 polynomial, table factor, exponent field
+__device__ __forceinline__ double exp2_back(const Exp2Part &e)
+{
+    const double f = e.f;
+#if GP_TAB_BITS == 6
+    double p = 1.33335581464284434e-03;
+#elif GP_TAB_BITS == 5
+    double p = 1.54035303933816100e-04;
+    p = fma(p, f, 1.33335581464284434e-03);
+#else
+    double p = 1.52527338040598403e-05;
+    p = fma(p, f, 1.54035303933816100e-04);
+    p = fma(p, f, 1.33335581464284434e-03);
+#endif
+    p = fma(p, f, 9.61812910762847716e-03);
+    p = fma(p, f, 5.55041086648215800e-02);
+    p = fma(p, f, 2.40226506959100712e-01);
+    p = fma(p, f, 6.93147180559945309e-01);
+    const double r = fma(e.T, f * p, e.T);
+    return __hiloint2double(__double2hiint(r) + e.nsh, __double2loint(r));
+}
+__device__ __forceinline__ double exp2_neg_tab(double t, uint32_t tab) { return exp2_back(exp2_front(t, tab)); }
+
 struct Jac {
     // d f / d x : rows 0,1 x cols {psi,vx,vy}; row 2 = e_r; rows 3..5 x cols 2..6 ; row 6 = 0
     double j0[3], j1[3];
@@ -145,6 +187,8 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
             // q = -0.5 log2(e) sum_d z_d^2/ell_d^2  (expanded square: 4 FMAs per point instead of 12 ops; the
             // cancellation costs ~1e-15 absolute in the exponent).  Tail: 1/ell_d^2 (dz values), y_mean.
             const double *blk = gpsm + (size_t)j * gp_stride;
+            // 2^(j/GP_TAB) table behind the last output (32-bit shared-space address, fixed for the whole sweep)
+            const uint32_t tab = (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)o.gp_nout * gp_stride);
             const double *w = blk + (size_t)M * (dz + 2);
             double wv[ADMPC_DZMAX];
 #pragma unroll
@@ -157,13 +201,14 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
 #pragma unroll
             for (int d = 0; d < ADMPC_DZMAX; d++) { g[d] = 0.0; G2[d] = 0.0; }
             if (dz == 4) {
-                // hot case: 4 features -> 48 B per point, three LDS.128
+                // hot case: 4 features -> 48 B per point, three LDS.128.  (Two-point interleaving and software
+                // pipelining in the source were both tried: ptxas re-serialises the chains, no gain.)
 #pragma unroll 4
                 for (int i = 0; i < M; i++) {
                     const double2 *pt = reinterpret_cast<const double2 *>(blk + (size_t)i * 6);
                     const double2 a01 = pt[0], a23 = pt[1], ca = pt[2];
                     const double t = fma(a23.y, z[3], fma(a23.x, z[2], fma(a01.y, z[1], fma(a01.x, z[0], q + ca.x))));
-                    const double ka = exp2_neg(t) * ca.y;
+                    const double ka = exp2_neg_tab(t, tab) * ca.y;
                     m += ka;
                     G2[0] = fma(ka, a01.x, G2[0]); G2[1] = fma(ka, a01.y, G2[1]);
                     G2[2] = fma(ka, a23.x, G2[2]); G2[3] = fma(ka, a23.y, G2[3]);
@@ -174,7 +219,7 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
                     double t = q + pt[dz];
 #pragma unroll
                     for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) t = fma(pt[d], z[d], t);
-                    const double ka = exp2_neg(t) * pt[dz + 1];
+                    const double ka = exp2_neg_tab(t, tab) * pt[dz + 1];
                     m += ka;
 #pragma unroll
                     for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G2[d] = fma(ka, pt[d], G2[d]);

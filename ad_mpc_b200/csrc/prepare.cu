@@ -190,26 +190,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
 void launch_prepare(const Params &P, cudaStream_t s)
 {
     if (P.o.gp_enabled) {
-        // register budget capped at 128 so that 16 warps/SM are resident; the RK4 sensitivity state is spilled around
-        // the GP sweep (once per RK4 stage, negligible against the M-point loop).  Small models: 4 CTAs x 128 threads
-        // per SM; large models (one CTA per SM by shared memory): 512 threads.
+        // register budget capped at 80 (24 warps/SM) or 128 (16 warps/SM): the GP sweep itself needs ~60 registers, the
+        // RK4 sensitivity state is spilled around it (once per RK4 stage, negligible against the M-point loop).
+        // Small models: 6 CTAs x 128 threads per SM; large models (one CTA per SM by shared memory): 512 / 768 threads.
         const size_t sm = (size_t)P.gp.bytes;
-        if (sm <= 54 * 1024) {
-            static size_t configured = 0;
-            if (sm > configured) {
-                cudaFuncSetAttribute(prepare_kernel<true, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                configured = sm;
-            }
-            dim3 grid((P.Bp + 127) / 128, P.o.N + 1);
-            prepare_kernel<true, 128, 4><<<grid, 128, sm, s>>>(P);
+#define LAUNCH_PREP(BLK, MINB)                                                                                          \
+    do {                                                                                                                \
+        static size_t configured = 0;                                                                                   \
+        if (sm > configured) {                                                                                          \
+            cudaFuncSetAttribute(prepare_kernel<true, BLK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            configured = sm;                                                                                            \
+        }                                                                                                               \
+        dim3 grid((P.Bp + BLK - 1) / BLK, P.o.N + 1);                                                                   \
+        prepare_kernel<true, BLK, MINB><<<grid, BLK, sm, s>>>(P);                                                       \
+    } while (0)
+        if (sm <= 36 * 1024) {
+            LAUNCH_PREP(128, 6);            // 80 registers, 24 warps/SM
+        } else if (sm <= 54 * 1024) {
+            LAUNCH_PREP(128, 4);
         } else {
-            static size_t configured = 0;
-            if (sm > configured) {
-                cudaFuncSetAttribute(prepare_kernel<true, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                configured = sm;
-            }
-            dim3 grid((P.Bp + 511) / 512, P.o.N + 1);
-            prepare_kernel<true, 512, 1><<<grid, 512, sm, s>>>(P);
+            // one CTA per SM by shared memory: pick the CTA width with the fewest (weighted) waves over the 148 SMs
+            const long n512 = (long)((P.Bp + 511) / 512) * P.o.N, n768 = (long)((P.Bp + 767) / 768) * P.o.N;
+            const long w512 = (n512 + 147) / 148 * 512, w768 = (n768 + 147) / 148 * 768;
+            if (w768 * 100 <= w512 * 104) LAUNCH_PREP(768, 1);     // 80 registers: ~4 % more throughput per SM
+            else LAUNCH_PREP(512, 1);
         }
     } else {
         dim3 grid((P.Bp + 127) / 128, P.o.N + 1);

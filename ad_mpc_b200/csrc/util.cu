@@ -69,20 +69,50 @@ void launch_fill(double *dst, size_t n, double v, cudaStream_t s)
 }
 
 // ---- FP64 peak probe: 8 independent DFMA chains per thread, full occupancy -------------------------------
-__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b)
+// NINT > 0 adds NINT independent integer multiply-adds per 8 DFMAs (issue-slot pressure probe: how much FP64
+// throughput survives when the scheduler also has address / index arithmetic to issue).
+template <int NINT>
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b, int ia)
 {
     double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    int q[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) q[j] = threadIdx.x + j;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
             r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+#pragma unroll
+            for (int j = 0; j < NINT; j++) q[j] = q[j] * ia + u;
+        }
+    }
+    int qs = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) qs += q[j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7 + (double)qs;
+}
+
+// three distinct register operands per DFMA (the shape of the kernels' inner loops: operand-fetch pressure probe)
+__global__ void __launch_bounds__(256) dfma3_kernel(double *out, int iters, double a, double b)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    double s[8], t[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s[j] = a + 1e-9 * (threadIdx.x + j); t[j] = b * (1 + j + threadIdx.x); }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            r0 = fma(r0, s[(u + 0) & 7], t[(u + 1) & 7]); r1 = fma(r1, s[(u + 1) & 7], t[(u + 2) & 7]);
+            r2 = fma(r2, s[(u + 2) & 7], t[(u + 3) & 7]); r3 = fma(r3, s[(u + 3) & 7], t[(u + 4) & 7]);
+            r4 = fma(r4, s[(u + 4) & 7], t[(u + 5) & 7]); r5 = fma(r5, s[(u + 5) & 7], t[(u + 6) & 7]);
+            r6 = fma(r6, s[(u + 6) & 7], t[(u + 7) & 7]); r7 = fma(r7, s[(u + 7) & 7], t[(u + 0) & 7]);
         }
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
 }
 
-double run_fp64_peak(int device)
+double run_fp64_peak(int device, int nint)
 {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     const int blocks = 148 * 8, threads = 256, iters = 4096;
@@ -94,7 +124,11 @@ double run_fp64_peak(int device)
     double best = 0.0;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(e0);
-        dfma_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        if (nint == 16) dfma3_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        else if (nint <= 0) dfma_kernel<0><<<blocks, threads>>>(out, iters, 0.999999, 1e-9, 3);
+        else if (nint <= 2) dfma_kernel<2><<<blocks, threads>>>(out, iters, 0.999999, 1e-9, 3);
+        else if (nint <= 4) dfma_kernel<4><<<blocks, threads>>>(out, iters, 0.999999, 1e-9, 3);
+        else dfma_kernel<8><<<blocks, threads>>>(out, iters, 0.999999, 1e-9, 3);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
         float ms = 0;

@@ -204,6 +204,10 @@ int admpc_gp_fit(int device, int M, int dz, const double *X /*[M][dz]*/, const d
 /* FP64 peak probe: runs a dependent-free DFMA loop and returns achieved TFLOP/s (roofline denominator; there is
  * no FP64 entry in MEASURED_PEAKS.json). */
 int admpc_measure_fp64_peak(int device, double *tflops);
+/* Same loop with 0 / 2 / 4 / 8 independent integer multiply-adds issued per 8 DFMAs: the FP64 throughput that survives
+ * the issue-slot pressure of index / address arithmetic (diagnostic for DESIGN.md's attainable-roofline estimate).
+ * int_ops_per_8_dfma = 16 selects the operand-fetch probe instead: DFMAs with three distinct register operands. */
+int admpc_measure_fp64_mix(int device, int int_ops_per_8_dfma, double *tflops);
 
 #ifdef __cplusplus
 }
