@@ -71,25 +71,51 @@ __device__ __forceinline__ double wmax(double v)
 struct StageState {            // registers of lane k
     double du[2], dx[7], pi[7], lam[NC], t[NC], sl[2], su[2];
     double lo[2], hi[2], lox, hix;     // bounds around the iterate (delta form)
-    double rd[NC], rm[NC], rgu[2], rgsl[2], rgsu[2], rgx6;
+    double rm[NC], rgu[2], rgx6;
 };
 
+// Residual pieces that are cheap functions of the iterate are RECOMPUTED after every sweep instead of being kept live
+// in registers across it (the sweeps need those registers for their per-lane operand pointers): rd (bound residuals)
+// and the slack stationarity residuals.  The asm barrier keeps the compiler from carrying the values across.
+struct StageRes { double rd[NC], rgsl[2], rgsu[2]; };
+__device__ __forceinline__ void stage_res(const admpc_opts &o, bool k_ge1, StageState &S, StageRes &R)
+{
+    const double Ts = o.dt;
+#pragma unroll
+    for (int c = 0; c < NC; c++) asm volatile("" : "+d"(S.t[c]));
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        R.rgsl[j] = Ts * o.zl[j] + Ts * o.Zl[j] * S.sl[j] - S.lam[j] - S.lam[6 + j];
+        R.rgsu[j] = Ts * o.zu[j] + Ts * o.Zu[j] * S.su[j] - S.lam[3 + j] - S.lam[8 + j];
+        R.rd[j] = S.t[j] - (S.du[j] - S.lo[j] + S.sl[j]);
+        R.rd[3 + j] = S.t[3 + j] - (S.hi[j] - S.du[j] + S.su[j]);
+        R.rd[6 + j] = S.t[6 + j] - S.sl[j];
+        R.rd[8 + j] = S.t[8 + j] - S.su[j];
+    }
+    if (k_ge1) {
+        R.rd[2] = S.t[2] - (S.dx[6] - S.lox);
+        R.rd[5] = S.t[5] - (S.hix - S.dx[6]);
+    } else {
+        R.rd[2] = 0.0; R.rd[5] = 0.0;
+    }
+}
+
 // barrier-modified Hessian diagonal / gradient of one stage (soft-bound slacks eliminated), it = 1/t
-__device__ __forceinline__ void barrier_w(const admpc_opts &o, bool k_ge1, const StageState &S, const double it[NC],
-                                          double Rt[2], double &Qt6, double rt[2], double &qt6)
+__device__ __forceinline__ void barrier_w(const admpc_opts &o, bool k_ge1, const StageState &S, const StageRes &R,
+                                          const double it[NC], double Rt[2], double &Qt6, double rt[2], double &qt6)
 {
     const double Ts = o.dt;
     double g[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) g[c] = (S.rm[c] - S.lam[c] * S.rd[c]) * it[c];
+    for (int c = 0; c < NC; c++) g[c] = (S.rm[c] - S.lam[c] * R.rd[c]) * it[c];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         const double Sl = S.lam[j] * it[j], Su = S.lam[3 + j] * it[3 + j];
         const double Ssl = S.lam[6 + j] * it[6 + j], Ssu = S.lam[8 + j] * it[8 + j];
         const double iDl = 1.0 / (Ts * o.Zl[j] + Sl + Ssl), iDu = 1.0 / (Ts * o.Zu[j] + Su + Ssu);
         Rt[j] = Ts * o.W[7 + j] + Sl * (1.0 - Sl * iDl) + Su * (1.0 - Su * iDu);
-        const double cl = S.rgsl[j] + g[j] + g[6 + j];
-        const double cu = S.rgsu[j] + g[3 + j] + g[8 + j];
+        const double cl = R.rgsl[j] + g[j] + g[6 + j];
+        const double cu = R.rgsu[j] + g[3 + j] + g[8 + j];
         rt[j] = S.rgu[j] + (g[j] - Sl * cl * iDl) - (g[3 + j] - Su * cu * iDu);
     }
     if (k_ge1) {
@@ -120,6 +146,8 @@ __device__ __forceinline__ double dot6(const double *a, const double *b)
 template <bool FACTOR>
 __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
+    asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
+
     const double Ts = o.dt, hdt = o.dt;
     // phase 1: entries e = cc*7 + a of W = P [M | rb]
     const int e0 = l, e1 = (l + 32 < 56) ? l + 32 : 55;
@@ -249,6 +277,8 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
 // shuffles; p_k is published in the other half of a double buffer for the next stage.
 __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
+    asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
+
     const double hdt = o.dt;
     const int v = (l < 9) ? l : 0;                              // v < 7: M-column v ; v = 7, 8: x0, x1
     const int gb = (v < 2) ? R_BAR + 3 + v : (v < 7) ? R_GX + v : R_GX + (v - 7);
@@ -291,6 +321,8 @@ __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, 
 template <bool ADJ>
 __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
+    asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
+
     const double hdt = o.dt, Ts = o.dt;
     const int l7 = (l < 7) ? l : 6, l6 = (l < 6) ? l : 5;
     const double wq_l = Ts * sel7(o.W, l7), we_l = sel7(o.We, l7);
@@ -338,6 +370,8 @@ __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, doubl
 // ---- sequential adjoint sweep: dpi_{k-1} = base_k + A_k^T dpi_k ; leaves dpi_k in the P rb slot ----------------------
 __device__ __forceinline__ void w_adjoint(double *sm, double *xs, int N, int l)
 {
+    asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
+
     const int l7 = (l < 7) ? l : 6;
     const int lc = (l >= 2 && l < 7) ? l : 2;
     const double cself = (l < 2 || l == 6) ? 1.0 : 0.0, mA = (l >= 2 && l < 7) ? 1.0 : 0.0;
@@ -393,9 +427,9 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
 #pragma unroll
     for (int a = 0; a < 7; a++) { S.dx[a] = 0.0; S.pi[a] = 0.0; }
 #pragma unroll
-    for (int c = 0; c < NC; c++) { S.lam[c] = 0.0; S.t[c] = 1.0; S.rd[c] = 0.0; S.rm[c] = 0.0; }
+    for (int c = 0; c < NC; c++) { S.lam[c] = 0.0; S.t[c] = 1.0; S.rm[c] = 0.0; }
 #pragma unroll
-    for (int j = 0; j < 2; j++) { S.du[j] = 0.0; S.sl[j] = 0.0; S.su[j] = 0.0; S.lo[j] = -1.0; S.hi[j] = 1.0; S.rgu[j] = S.rgsl[j] = S.rgsu[j] = 0.0; }
+    for (int j = 0; j < 2; j++) { S.du[j] = 0.0; S.sl[j] = 0.0; S.su[j] = 0.0; S.lo[j] = -1.0; S.hi[j] = 1.0; S.rgu[j] = 0.0; }
     S.lox = -1.0; S.hix = 1.0; S.rgx6 = 0.0;
     if (isst || isterm) {
         if (isst) {
@@ -474,6 +508,8 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
         if (isst) {
 #pragma unroll
             for (int c = 0; c < NC; c++) it[c] = 1.0 / S.t[c];
+            StageRes R;
+            stage_res(o, k >= 1, S, R);
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 double g = Ts * o.W[7 + j] * S.du[j] + lr[j] - S.lam[j] + S.lam[3 + j];
@@ -481,22 +517,10 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
                 for (int r = 0; r < 6; r++) g = fma(st[R_M + j * 6 + r], S.pi[r], g);
                 if (j == 1) g = fma(hdt, S.pi[6], g);
                 S.rgu[j] = g;
-                S.rgsl[j] = Ts * o.zl[j] + Ts * o.Zl[j] * S.sl[j] - S.lam[j] - S.lam[6 + j];
-                S.rgsu[j] = Ts * o.zu[j] + Ts * o.Zu[j] * S.su[j] - S.lam[3 + j] - S.lam[8 + j];
-                ng = nmaxw(ng, nmaxw(fabs(g), nmaxw(fabs(S.rgsl[j]), fabs(S.rgsu[j]))));
-                S.rd[j] = S.t[j] - (S.du[j] - S.lo[j] + S.sl[j]);
-                S.rd[3 + j] = S.t[3 + j] - (S.hi[j] - S.du[j] + S.su[j]);
-                S.rd[6 + j] = S.t[6 + j] - S.sl[j];
-                S.rd[8 + j] = S.t[8 + j] - S.su[j];
-                nd = nmaxw(nd, nmaxw(nmaxw(fabs(S.rd[j]), fabs(S.rd[3 + j])), nmaxw(fabs(S.rd[6 + j]), fabs(S.rd[8 + j]))));
+                ng = nmaxw(ng, nmaxw(fabs(g), nmaxw(fabs(R.rgsl[j]), fabs(R.rgsu[j]))));
+                nd = nmaxw(nd, nmaxw(nmaxw(fabs(R.rd[j]), fabs(R.rd[3 + j])), nmaxw(fabs(R.rd[6 + j]), fabs(R.rd[8 + j]))));
             }
-            if (k >= 1) {
-                S.rd[2] = S.t[2] - (S.dx[6] - S.lox);
-                S.rd[5] = S.t[5] - (S.hix - S.dx[6]);
-                nd = nmaxw(nd, nmaxw(fabs(S.rd[2]), fabs(S.rd[5])));
-            } else {
-                S.rd[2] = 0.0; S.rd[5] = 0.0;
-            }
+            if (k >= 1) nd = nmaxw(nd, nmaxw(fabs(R.rd[2]), fabs(R.rd[5])));
 #pragma unroll
             for (int r = 0; r < 6; r++) {
                 double v = lb[r] - dxn[r] + ((r < 2) ? S.dx[r] : 0.0);
@@ -538,7 +562,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
                 for (int a = 0; a < 6; a++) st[R_GX + a] = 0.0;
             }
             double Rt[2], Qt6, rt[2], qt6;
-            barrier_w(o, k >= 1, S, it, Rt, Qt6, rt, qt6);
+            barrier_w(o, k >= 1, S, R, it, Rt, Qt6, rt, qt6);
             st[R_BAR + 0] = Rt[0]; st[R_BAR + 1] = Rt[1]; st[R_BAR + 2] = Qt6;
             st[R_BAR + 3] = rt[0]; st[R_BAR + 4] = rt[1]; st[R_GX + 6] = qt6;
         } else if (isterm) {
@@ -576,27 +600,29 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
         for (int pass = 0; pass < 2; pass++) {
             // pass 0: affine step -> mu_aff, sigma, corrected rhs ; pass 1: final step -> alpha
             an = 1.0; ad = 1.0; s1 = 0.0; s2 = 0.0;
+            StageRes R;
             if (isst) {
+                stage_res(o, k >= 1, S, R);
                 const double du0 = st[R_DD + 0], du1 = st[R_DD + 1], dx6 = st[R_DD + 2];
                 double gq[NC];
 #pragma unroll
-                for (int c = 0; c < NC; c++) gq[c] = (S.rm[c] - S.lam[c] * S.rd[c]) * it[c];
+                for (int c = 0; c < NC; c++) gq[c] = (S.rm[c] - S.lam[c] * R.rd[c]) * it[c];
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     const double duj = (j == 0) ? du0 : du1;
                     const double Sl = S.lam[j] * it[j], Su = S.lam[3 + j] * it[3 + j];
                     const double Ssl = S.lam[6 + j] * it[6 + j], Ssu = S.lam[8 + j] * it[8 + j];
                     const double iDl = 1.0 / (Ts * o.Zl[j] + Sl + Ssl), iDu = 1.0 / (Ts * o.Zu[j] + Su + Ssu);
-                    const double cl = S.rgsl[j] + gq[j] + gq[6 + j];
-                    const double cu = S.rgsu[j] + gq[3 + j] + gq[8 + j];
+                    const double cl = R.rgsl[j] + gq[j] + gq[6 + j];
+                    const double cu = R.rgsu[j] + gq[3 + j] + gq[8 + j];
                     dsl[j] = -(cl + Sl * duj) * iDl;
                     dsu[j] = -(cu - Su * duj) * iDu;
-                    dtv[j] = duj + dsl[j] - S.rd[j];
-                    dtv[3 + j] = -duj + dsu[j] - S.rd[3 + j];
-                    dtv[6 + j] = dsl[j] - S.rd[6 + j];
-                    dtv[8 + j] = dsu[j] - S.rd[8 + j];
+                    dtv[j] = duj + dsl[j] - R.rd[j];
+                    dtv[3 + j] = -duj + dsu[j] - R.rd[3 + j];
+                    dtv[6 + j] = dsl[j] - R.rd[6 + j];
+                    dtv[8 + j] = dsu[j] - R.rd[8 + j];
                 }
-                if (k >= 1) { dtv[2] = dx6 - S.rd[2]; dtv[5] = -dx6 - S.rd[5]; }
+                if (k >= 1) { dtv[2] = dx6 - R.rd[2]; dtv[5] = -dx6 - R.rd[5]; }
                 else { dtv[2] = 0.0; dtv[5] = 0.0; }
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
@@ -639,7 +665,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
                         S.rm[c] = on ? S.rm[c] + dlv[c] * dtv[c] - sigmu : 0.0;
                     }
                     double Rt[2], Qt6, rt[2], qt6;
-                    barrier_w(o, k >= 1, S, it, Rt, Qt6, rt, qt6);
+                    barrier_w(o, k >= 1, S, R, it, Rt, Qt6, rt, qt6);
                     st[R_BAR + 3] = rt[0]; st[R_BAR + 4] = rt[1]; st[R_GX + 6] = qt6;
                 }
                 cta_sync<NW>();
