@@ -106,6 +106,8 @@ struct admpc_batch {
     int *ipool = nullptr;
     double *stage_in = nullptr, *stage_u = nullptr, *stage_x = nullptr, *stage_misc = nullptr;
     int *stage_status = nullptr;
+    int *sqp_active = nullptr;       // device counters (one per SQP iteration parity), see admpc_batch_solve_sqp
+    int *sqp_active_host = nullptr;  // pinned
     double *gp_blob = nullptr;
     size_t gp_blob_cap = 0;
     double *l2_scratch = nullptr;
@@ -170,6 +172,7 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
+        {&P.nlp_res, 4},
         {&P.lin, (size_t)(N + 1) * LIN_ROWS}, {&P.res_out, 4},
     };
     if (need_ws3) items.push_back({&P.ws, (size_t)qp_smem_ws_rows(N)});
@@ -189,9 +192,11 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     size_t off = 0;
     for (auto &it : items) { *it.p = h->pool + off * Bp; off += it.rows; }
     P.x0 = x0; P.yref = yref; P.p = pp; P.gps = gps;
-    CUDA_CHECK_RET(cudaMalloc(&h->ipool, 4 * Bp * sizeof(int)));
-    CUDA_CHECK_RET(cudaMemsetAsync(h->ipool, 0, 4 * Bp * sizeof(int), h->stream));
+    CUDA_CHECK_RET(cudaMalloc(&h->ipool, (6 * Bp + 32) * sizeof(int)));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->ipool, 0, (6 * Bp + 32) * sizeof(int), h->stream));
     P.status = h->ipool; P.qp_status = h->ipool + Bp; P.qp_iter = h->ipool + 2 * Bp; P.lin_bad = h->ipool + 3 * Bp;
+    P.sqp_status = h->ipool + 4 * Bp; P.sqp_iter = h->ipool + 5 * Bp;
+    h->sqp_active = h->ipool + 6 * Bp;                       // per-iteration counters of still-running instances
     // instance-major staging areas
     const size_t in_rows = (size_t)N * 49 > (size_t)N * 9 + 7 ? (size_t)N * 49 : (size_t)N * 9 + 7;
     CUDA_CHECK_RET(cudaMalloc(&h->stage_in, in_rows * Bp * sizeof(double)));
@@ -211,7 +216,7 @@ extern "C" int admpc_batch_free(admpc_batch *h)
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
-    cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack);
+    cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack);
     for (auto &e : h->ev) cudaEventDestroy(e);
     cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
     cudaStreamDestroy(h->stream);
@@ -343,18 +348,12 @@ extern "C" int admpc_batch_reset(admpc_batch *h)
     return 0;
 }
 
-extern "C" int admpc_batch_solve(admpc_batch *h)
+// feedback phase + update of one iteration (shared by the RTI step and the full-SQP loop)
+static int launch_feedback(admpc_batch *h)
 {
-    if (!h) return ADMPC_E_ARG;
-    CUDA_CHECK_RET(cudaSetDevice(h->device));
     const Params &P = h->P;
-    CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
-    CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
-    if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
-    launch_prepare(P, h->stream);
-    if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
     // QP variant: 4 (default) warp per instance, register-resident IPM state; 3 shared-memory-resident octets
-    // (horizons 32..80);
+    // (horizons 64..80);
     // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
     const int variant = h->qp_variant ? h->qp_variant : 4;
     bool fused = false;
@@ -366,9 +365,81 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     }
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
     if (!fused) launch_update(P, h->stream);
+    h->launches += fused ? 1 : 2;
+    return 0;
+}
+
+extern "C" int admpc_batch_solve(admpc_batch *h)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const Params &P = h->P;
+    CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
+    CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
+    if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
+    launch_prepare(P, h->stream);
+    h->launches += 1;
+    if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
+    if (int r = launch_feedback(h)) return r;
     CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
-    h->launches += fused ? 2 : 3;
     CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+
+// Full SQP (nlp_solver_type "SQP", create_ros_ad_mpc.py:47-51): repeat { prepare; NLP residual check; QP; full step }
+// until every instance has converged / failed or max_iter is reached.  Synchronous: the host reads one counter per
+// iteration (how many instances are still running).  Per-instance results: admpc_batch_get_sqp_info.
+extern "C" int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double *tol4, int *iterations_run)
+{
+    if (!h || max_iter < 0) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const Params &P = h->P;
+    const double dflt[4] = {1e-6, 1e-6, 1e-6, 1e-6};            // sim_car_acados_ocp.json:870-873
+    const double *tol = tol4 ? tol4 : dflt;
+    if (!h->sqp_active_host) CUDA_CHECK_RET(cudaHostAlloc((void **)&h->sqp_active_host, 32 * sizeof(int), cudaHostAllocDefault));
+    CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
+    CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
+    CUDA_CHECK_RET(cudaMemsetAsync(P.status, 0, (size_t)P.Bp * sizeof(int), h->stream));
+    CUDA_CHECK_RET(cudaMemsetAsync(P.sqp_iter, 0, (size_t)P.Bp * sizeof(int), h->stream));
+    int it = 0, running = P.B;
+    for (it = 0; it < max_iter; it++) {
+        int *ctr = h->sqp_active + (it & 1);
+        CUDA_CHECK_RET(cudaMemsetAsync(ctr, 0, sizeof(int), h->stream));
+        launch_prepare(P, h->stream);
+        launch_nlp_res(P, it, tol, ctr, h->stream);
+        h->launches += 2;
+        CUDA_CHECK_RET(cudaMemcpyAsync(h->sqp_active_host, ctr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+        running = h->sqp_active_host[0];
+        if (running == 0) break;
+        if (int r = launch_feedback(h)) return r;
+    }
+    if (running != 0) {              // max_iter reached (or max_iter == 0): classify what is still running
+        launch_sqp_finalize(P, h->stream);
+        h->launches += 1;
+    }
+    CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    CUDA_CHECK_RET(cudaGetLastError());
+    if (iterations_run) *iterations_run = it;
+    return 0;
+}
+
+// per-instance outcome of the last admpc_batch_solve_sqp: acados status {0 converged, 1 NaN, 2 max_iter, 4 QP failure},
+// number of QPs solved, NLP residual norms (stat, eq, ineq, comp) of the last check.  Any pointer may be NULL.
+extern "C" int admpc_batch_get_sqp_info(admpc_batch *h, int *status, int *sqp_iter, double *res /*[B][4]*/)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const Params &P = h->P;
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    if (status) CUDA_CHECK_RET(cudaMemcpy(status, P.sqp_status, (size_t)P.B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (sqp_iter) CUDA_CHECK_RET(cudaMemcpy(sqp_iter, P.sqp_iter, (size_t)P.B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (res) {
+        launch_transpose_out(P.nlp_res, h->stage_misc, P.B, P.Bp, 4, h->stream);
+        CUDA_CHECK_RET(cudaMemcpyAsync(res, h->stage_misc, (size_t)P.B * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    }
     return 0;
 }
 
@@ -839,7 +910,10 @@ struct sim_car_solver_capsule {
     int N = 0;
     std::vector<double> x0, yref, p, x, u, pi, lam, t, sl, su;
     bool iterate_dirty = false, duals_stale = false;
-    int status = 0, qp_status = 0, qp_iter = 0;
+    int status = 0, qp_status = 0, qp_iter = 0, sqp_iter = 1;
+    bool nlp_sqp = false;            // nlp_solver_type: false "SQP_RTI" (shipped), true "SQP" (point-reference mode)
+    int nlp_max_iter = 100;          // sim_car_acados_ocp.json:868
+    double nlp_tol[4] = {1e-6, 1e-6, 1e-6, 1e-6};   // :870-873
     double time_tot = 0.0;
     double res[4] = {0, 0, 0, 0};
 };
@@ -858,6 +932,18 @@ extern "C" int sim_car_acados_set_opts(sim_car_solver_capsule *c, const admpc_op
     if (c->h) { admpc_set_error("sim_car_acados_set_opts", "solver already created"); return ADMPC_E_STATE; }
     c->opts = *o;
     c->opts_set = true;
+    return 0;
+}
+// nlp_solver_type of the capsule: "SQP_RTI" (what the reference ships) or "SQP" (its point-reference mode,
+// create_ros_ad_mpc.py:47-51); max_iter <= 0 / tol4 NULL keep the acados defaults (100, 1e-6).
+extern "C" int sim_car_acados_set_nlp_solver(sim_car_solver_capsule *c, const char *type, int max_iter, const double *tol4)
+{
+    if (!c || !type) return ADMPC_E_ARG;
+    if (!strcmp(type, "SQP")) c->nlp_sqp = true;
+    else if (!strcmp(type, "SQP_RTI")) c->nlp_sqp = false;
+    else { admpc_set_error("sim_car_acados_set_nlp_solver", "nlp_solver_type must be SQP_RTI or SQP"); return ADMPC_E_ARG; }
+    if (max_iter > 0) c->nlp_max_iter = max_iter;
+    if (tol4) memcpy(c->nlp_tol, tol4, sizeof c->nlp_tol);
     return 0;
 }
 extern "C" int sim_car_acados_create_with_discretization(sim_car_solver_capsule *c, int N, double *ts)
@@ -955,7 +1041,11 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
     if ((r = admpc_batch_set_yref(h, c->yref.data()))) return r;
     if ((r = admpc_batch_set_p(h, c->p.data()))) return r;
     if (c->iterate_dirty) { if ((r = admpc_batch_set_iterate(h, c->x.data(), c->u.data()))) return r; c->iterate_dirty = false; }
-    if ((r = admpc_batch_solve(h))) return r;
+    if (c->nlp_sqp) {
+        if ((r = admpc_batch_solve_sqp(h, c->nlp_max_iter, c->nlp_tol, nullptr))) return r;
+    } else {
+        if ((r = admpc_batch_solve(h))) return r;
+    }
     float ms = 0;
     if ((r = admpc_batch_timer_stop(h, &ms))) return r;
     c->time_tot = ms * 1e-3;
@@ -964,7 +1054,12 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
     if ((r = admpc_batch_get_u(h, c->u.data()))) return r;
     if ((r = admpc_batch_get_status(h, &c->status, &c->qp_status, &c->qp_iter))) return r;
     c->duals_stale = true;
-    CUDA_CHECK_RET(cudaMemcpy2D(c->res, sizeof(double), h->P.res_out, (size_t)h->P.Bp * sizeof(double), sizeof(double), 4, cudaMemcpyDeviceToHost));
+    c->sqp_iter = 1;
+    if (c->nlp_sqp) {
+        if ((r = admpc_batch_get_sqp_info(h, &c->status, &c->sqp_iter, c->res))) return r;
+    } else {
+        CUDA_CHECK_RET(cudaMemcpy2D(c->res, sizeof(double), h->P.res_out, (size_t)h->P.Bp * sizeof(double), sizeof(double), 4, cudaMemcpyDeviceToHost));
+    }
     return c->status;
 }
 
@@ -1005,7 +1100,7 @@ extern "C" int sim_car_acados_get(sim_car_solver_capsule *c, int stage, const ch
 extern "C" int sim_car_acados_get_stat(sim_car_solver_capsule *c, const char *name, void *out)
 {
     if (!c || !name || !out) return ADMPC_E_ARG;
-    if (!strcmp(name, "sqp_iter")) { *(int *)out = 1; return 0; }          // RTI: exactly one SQP iteration
+    if (!strcmp(name, "sqp_iter")) { *(int *)out = c->sqp_iter; return 0; }   // RTI: exactly one SQP iteration
     if (!strcmp(name, "qp_iter")) { *(int *)out = c->qp_iter; return 0; }
     if (!strcmp(name, "qp_stat")) { *(int *)out = c->qp_status; return 0; }
     if (!strcmp(name, "status")) { *(int *)out = c->status; return 0; }

@@ -54,6 +54,9 @@ struct Params {
     double *ws;          // qp_smem.cu: per-warp scratch tiles [Bp/4][rows][4]
     int *status, *qp_status, *qp_iter, *lin_bad;
     double *res_out;     // [4][Bp] final residual norms
+    // full SQP mode (sqp.cu): lin_bad == 2 marks an instance that has finished and is skipped by prepare / QP kernels
+    int *sqp_status, *sqp_iter;
+    double *nlp_res;     // [4][Bp] NLP KKT residual norms of the last check
 };
 
 #define CUDA_CHECK_RET(call)                                                         \
@@ -76,3 +79,5 @@ void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream
 void launch_update(const Params &P, cudaStream_t s);
 void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
 double run_fp64_peak(int device, int nint);
+void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
+void launch_sqp_finalize(const Params &P, cudaStream_t s);

@@ -77,7 +77,7 @@ __device__ __forceinline__ Exp2Part exp2_front(double t, uint32_t tab)       // 
     const int ti = __double2loint(tt);                               // rint(t * GP_TAB)
     e.f = t - (tt - SHIFT);                                          // |f| <= 1/(2 GP_TAB) for every finite t
     asm("ld.shared.f64 %0, [%1];" : "=d"(e.T) : "r"(tab + ((ti & (GP_TAB - 1)) << 3)));
-    e.nsh = far ? (-1000 << 20) : ((ti << (20 - GP_TAB_BITS)) & 0xfff00000);
+    e.nsh = far ? -1000 * (1 << 20) : (int)((unsigned)(ti << (20 - GP_TAB_BITS)) & 0xfff00000u);
     return e;
 }
 // back half: 2^f - 1 polynomial, table factor, exponent field

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     const double h = o.dt;
-    const bool active = (i < P.B);
+    const bool active = (i < P.B) && (P.lin_bad[i] != 2);      // 2: finished instance of the full-SQP loop (sqp.cu)
 
     double x[7], u[2], xn[7], yr[9];
     double pk = 0.0;

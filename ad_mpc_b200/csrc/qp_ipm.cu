@@ -302,9 +302,9 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const Params P)
     if (i >= P.B) return;
     const double Ts = o.dt, hdt = o.dt;
 
-    if (P.lin_bad[i]) {     // NaN/Inf in the linearisation: ACADOS_FAILURE, iterate untouched
-        P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0;
-        return;
+    if (const int flag = P.lin_bad[i]) {     // 1: NaN/Inf in the linearisation: ACADOS_FAILURE, iterate untouched
+        if (flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+        return;                              // 2: finished instance of the full-SQP loop
     }
     // ---- cold start: primal at 0 pushed thr0 inside its box, t from the box, lam = mu0/t -------------------
 #pragma unroll
@@ -502,7 +502,7 @@ __global__ void update_kernel(const Params P)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = blockIdx.y;
     if (i >= P.B) return;
-    if (P.status[i] != 0) return;
+    if (P.status[i] != 0 || P.lin_bad[i] == 2) return;     // failed QP, or finished instance of the full-SQP loop
     if (row < (N + 1) * 7) AT(P.xb, row) += AT(P.dx, row);
     if (row < N * 2) {
         AT(P.ub, row) += AT(P.du, row);

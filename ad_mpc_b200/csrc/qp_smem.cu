@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(32) qp_smem_kernel(const Params P)
     const bool valid = i < P.B;
     const bool bad = valid ? (P.lin_bad[i] != 0) : false;
     int status = (valid && !bad) ? -1 : 0;     // -1 running ; 0 ok, 1 maxiter, 2 minstep, 3 nan (hpipm numbering)
-    if (valid && bad && s == 0) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+    if (valid && bad && s == 0 && P.lin_bad[i] == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }   // 2: finished (full SQP)
 
     // ---- stage M into shared memory (lin is SoA [row][Bp]: 32-byte sector per row and warp) ----------------------
     for (int k = 0; k < N; k++) {

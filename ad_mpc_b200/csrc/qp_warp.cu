@@ -409,9 +409,9 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
     double *xc = xs + X_SIZE;                    // NW == 2 only: exchange window [64][XCH_STRIDE] + 48 reduction slots
     double *red = xc + 64 * XCH_STRIDE;
     const double Ts = o.dt, hdt = o.dt;
-    if (P.lin_bad[i]) {                          // NaN/Inf in the linearisation: ACADOS_FAILURE, iterate untouched
-        if (threadIdx.x == 0) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
-        return;
+    if (const int flag = P.lin_bad[i]) {         // 1: NaN/Inf in the linearisation: ACADOS_FAILURE, iterate untouched
+        if (threadIdx.x == 0 && flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+        return;                                  // 2: finished instance of the full-SQP loop, nothing to do
     }
     // ---- stage M into shared memory ------------------------------------------------------------------------------------
     for (int e = threadIdx.x; e < 42 * N; e += 32 * NW) {

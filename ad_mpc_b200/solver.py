@@ -172,6 +172,18 @@ class BatchSolver:
     def solve(self):
         check(self.L.admpc_batch_solve(self.h), "solve")
 
+    def solve_sqp(self, max_iter=100, tol=(1e-6, 1e-6, 1e-6, 1e-6)):
+        """Full SQP (nlp_solver_type "SQP", create_ros_ad_mpc.py:47-51): iterate every instance to convergence.
+        Returns dict(status[B] acados codes {0,1,2,4}, sqp_iter[B], res[B,4], iterations_run)."""
+        t = _f64(np.asarray(tol, dtype=np.float64).reshape(4))
+        n = C.c_int(0)
+        check(self.L.admpc_batch_solve_sqp(self.h, int(max_iter), _dp(t), C.byref(n)), "solve_sqp")
+        st, it = np.empty(self.B, dtype=np.int32), np.empty(self.B, dtype=np.int32)
+        res = np.empty((self.B, 4))
+        check(self.L.admpc_batch_get_sqp_info(self.h, st.ctypes.data_as(C.POINTER(C.c_int)),
+                                              it.ctypes.data_as(C.POINTER(C.c_int)), _dp(res)), "get_sqp_info")
+        return dict(status=st, sqp_iter=it, res=res, iterations_run=n.value)
+
     def wait(self):
         check(self.L.admpc_batch_wait(self.h), "wait")
 
@@ -305,11 +317,15 @@ class PipelinedSolver:
 class AcadosOcpSolverB200:
     """Drop-in for the ``AcadosOcpSolver`` object used by AD3DOptimizer (single instance, acados-shim symbols)."""
 
-    def __init__(self, opts=None, N=None):
+    def __init__(self, opts=None, N=None, nlp_solver_type="SQP_RTI", nlp_solver_max_iter=100, nlp_tol=None):
+        """nlp_solver_type mirrors ocp.solver_options.nlp_solver_type (ad_3d_optimizer.py:205): "SQP_RTI" or "SQP"."""
         self.L = _lib.load()
         self.c = C.c_void_p(self.L.sim_car_acados_create_capsule())
         if opts is not None:
             check(self.L.sim_car_acados_set_opts(self.c, C.byref(opts)), "set_opts")
+        tol = None if nlp_tol is None else _f64(np.asarray(nlp_tol, dtype=np.float64).reshape(4))
+        check(self.L.sim_car_acados_set_nlp_solver(self.c, nlp_solver_type.encode(), int(nlp_solver_max_iter),
+                                                   _dp(tol) if tol is not None else None), "set_nlp_solver")
         n = N if N is not None else (opts.N if opts is not None else 40)
         check(self.L.sim_car_acados_create_with_discretization(self.c, int(n), None), "create")
         self.N = int(n)

@@ -85,6 +85,10 @@ int sim_car_acados_free(sim_car_solver_capsule *capsule);                       
 void sim_car_acados_print_stats(sim_car_solver_capsule *capsule);                 /* .h:141 */
 /* options used by the next create() on this capsule (the reference freezes them at code-generation time) */
 int sim_car_acados_set_opts(sim_car_solver_capsule *capsule, const admpc_opts *opts);
+/* nlp_solver_type: "SQP_RTI" (shipped, $A/ad_3d_optimizer.py:205 default) or "SQP" (point-reference mode,
+ * $A/create_ros_ad_mpc.py:47-51); max_iter <= 0 and tol4 == NULL keep nlp_solver_max_iter 100 / tolerances 1e-6
+ * (acados_models/sim_car_acados_ocp.json:868-873).  solve() then iterates to convergence; get_stat "sqp_iter". */
+int sim_car_acados_set_nlp_solver(sim_car_solver_capsule *capsule, const char *type, int max_iter, const double *tol4);
 /* flat field access replacing ocp_nlp_{cost_model,constraints_model,out}_set / ocp_nlp_out_get / ocp_nlp_get.
  * set fields: "yref" (9, or 7 at stage N), "lbx"/"ubx" (stage 0: 7 = x0; stages 1..N-1: 1), "p" (1), "x" (7), "u" (2)
  * get fields: "x" (7), "u" (2), "pi" (7), "lam" (10, stage 0: 22), "t" (same), "sl" (2), "su" (2)
@@ -200,6 +204,16 @@ int admpc_batch_barrier(admpc_batch *h);
  * y must already have its mean removed (gp.py:343).  ADMPC_E_ARG when K is not positive definite. */
 int admpc_gp_fit(int device, int M, int dz, const double *X /*[M][dz]*/, const double *y /*[M]*/, const double *ell /*[dz]*/,
                  double sigma_f, double sigma_n, double *alpha_out /*[M] or NULL*/, double *nll_out, float *ms_out);
+
+/* Full SQP mode (nlp_solver_type "SQP": $A/create_ros_ad_mpc.py:47-51 -> $A/ad_3d_optimizer.py:205; defaults
+ * nlp_solver_max_iter 100 and tolerances 1e-6 from acados_models/sim_car_acados_ocp.json:868-873).  Repeats
+ * { linearise; NLP KKT residual check; QP; full step } on the device until every instance has converged, failed or
+ * used max_iter iterations; tol4 = {stat, eq, ineq, comp} (NULL: 1e-6 each).  Synchronous.  iterations_run (may be
+ * NULL) receives the number of batch iterations executed. */
+int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double *tol4, int *iterations_run);
+/* per-instance outcome of the last solve_sqp: acados status {0 converged, 1 NaN, 2 max_iter, 4 QP failure}, QPs
+ * solved, NLP residual norms [B][4] of the last check.  Any pointer may be NULL. */
+int admpc_batch_get_sqp_info(admpc_batch *h, int *status, int *sqp_iter, double *res);
 
 /* FP64 peak probe: runs a dependent-free DFMA loop and returns achieved TFLOP/s (roofline denominator; there is
  * no FP64 entry in MEASURED_PEAKS.json). */

@@ -644,6 +644,101 @@ int orc_rti_step(const orc_opts *o, const orc_gp *gp, const double *x0, const do
     return st->status;
 }
 
+/* ------------------------------------------------------------------------------------------ full SQP ------- */
+/* NLP KKT residual norms (stat, eq, ineq, comp) of the iterate against a fresh linearisation: the IPM residual
+ * function evaluated at a zero step with the iterate's own multipliers and slacks (acados ocp_nlp_res_compute [EXT]:
+ * res_ineq = constraint function + t, res_comp = lam .* t). */
+void orc_nlp_residuals(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0, double res[4])
+{
+    const int N = o->N;
+    ipm_ws *w = (ipm_ws *)malloc(sizeof(ipm_ws));
+    orc_qpsol *s = (orc_qpsol *)calloc(1, sizeof(orc_qpsol));
+    double dlu[ORC_NMAX * 2], duu[ORC_NMAX * 2], dlx[ORC_NMAX], dux[ORC_NMAX], mu;
+    for (int k = 0; k < N; k++) {
+        for (int j = 0; j < 2; j++) {
+            dlu[k * 2 + j] = o->lbu[j] - it->u[k * 2 + j];
+            duu[k * 2 + j] = o->ubu[j] - it->u[k * 2 + j];
+        }
+        dlx[k] = o->lbx - it->x[k * 7 + 6];
+        dux[k] = o->ubx - it->x[k * 7 + 6];
+    }
+    memcpy(s->pi, it->pi, sizeof(double) * N * 7);
+    memcpy(s->lam, it->lam, sizeof(double) * N * NC);
+    memcpy(s->t, it->t, sizeof(double) * N * NC);
+    memcpy(s->sl, it->sl, sizeof(double) * N * 2);
+    memcpy(s->su, it->su, sizeof(double) * N * 2);
+    ipm_residuals(o, lin, dlu, duu, dlx, dux, s, w, res, &mu);
+    /* the initial-state mismatch is an equality residual of the NLP (x_0 = x0 is a constraint of the OCP) */
+    for (int i = 0; i < 7; i++) res[1] = nanmax(res[1], fabs(x0[i] - it->x[i]));
+    free(w); free(s);
+}
+
+/* Full SQP (nlp_solver_type "SQP", create_ros_ad_mpc.py:47-51 point-reference mode; acados ocp_nlp_sqp [EXT]):
+ * repeat { linearise; stop with status 0 when the four NLP residuals are below tol; solve the QP; full step }.
+ * Returns the acados status: 0 converged, 1 NaN in the linearisation, 2 max_iter reached, 4 QP failure. */
+int orc_sqp_solve(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref, const double *p,
+                  const double *gp_state, orc_iterate *it, int max_iter, const double tol[4], int *sqp_iter,
+                  double res_out[4])
+{
+    const int N = o->N;
+    orc_lin *lin = (orc_lin *)malloc(sizeof(orc_lin));
+    orc_qpsol *sol = (orc_qpsol *)malloc(sizeof(orc_qpsol));
+    const double *gps = gp_state ? gp_state : x0;
+    int status = 2, iter = 0;
+    double res[4] = {0, 0, 0, 0};
+    for (iter = 0; iter < max_iter; iter++) {
+        if (orc_prepare(o, gp, it, yref, p, gps, lin)) { status = 1; break; }
+        orc_nlp_residuals(o, lin, it, x0, res);
+        if (res[0] < tol[0] && res[1] < tol[1] && res[2] < tol[2] && res[3] < tol[3]) { status = 0; break; }
+        orc_stats st;
+        orc_qp_solve(o, lin, it, x0, sol, &st);
+        if (!(st.qp_status == 0 || st.qp_status == 2)) { status = 4; break; }
+        for (int i = 0; i < (N + 1) * 7; i++) it->x[i] += sol->dx[i];
+        for (int i = 0; i < N * 2; i++) it->u[i] += sol->du[i];
+        memcpy(it->pi, sol->pi, sizeof(double) * N * 7);
+        memcpy(it->lam, sol->lam, sizeof(double) * N * NC);
+        memcpy(it->t, sol->t, sizeof(double) * N * NC);
+        memcpy(it->sl, sol->sl, sizeof(double) * N * 2);
+        memcpy(it->su, sol->su, sizeof(double) * N * 2);
+    }
+    if (sqp_iter) *sqp_iter = iter;
+    if (res_out) memcpy(res_out, res, sizeof res);
+    free(lin); free(sol);
+    return status;
+}
+
+int orc_sqp_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                  const double *p, const double *gp_state, double *xit, double *uit, int max_iter, const double *tol,
+                  int *status, int *sqp_iter, double *res, int nthreads)
+{
+    const int N = o->N;
+    const size_t ny = (size_t)N * 9 + 7;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        orc_iterate *it = (orc_iterate *)malloc(sizeof(orc_iterate));
+#pragma omp for schedule(dynamic, 4)
+        for (int b = 0; b < B; b++) {
+            memset(it, 0, sizeof(*it));
+            memcpy(it->x, xit + (size_t)b * (N + 1) * 7, sizeof(double) * (N + 1) * 7);
+            memcpy(it->u, uit + (size_t)b * N * 2, sizeof(double) * N * 2);
+            int si = 0;
+            double r4[4];
+            int stt = orc_sqp_solve(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N,
+                                    gp_state ? gp_state + (size_t)b * 7 : 0, it, max_iter, tol, &si, r4);
+            memcpy(xit + (size_t)b * (N + 1) * 7, it->x, sizeof(double) * (N + 1) * 7);
+            memcpy(uit + (size_t)b * N * 2, it->u, sizeof(double) * N * 2);
+            if (status) status[b] = stt;
+            if (sqp_iter) sqp_iter[b] = si;
+            if (res) memcpy(res + (size_t)b * 4, r4, sizeof r4);
+        }
+        free(it);
+    }
+    return 0;
+}
+
 int orc_rti_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
                   const double *p, const double *gp_state, double *xit, double *uit, double *piout,
                   int *status, int *qp_status, int *qp_iter, int nthreads)

@@ -124,6 +124,16 @@ int orc_rti_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, 
                   const double *p, const double *gp_state, double *xit, double *uit, double *piout,
                   int *status, int *qp_status, int *qp_iter, int nthreads);
 
+/* full SQP mode (nlp_solver_type "SQP": create_ros_ad_mpc.py:47-51; nlp_solver_max_iter 100, tolerances 1e-6:
+ * acados_models/sim_car_acados_ocp.json:868-873).  tol = {stat, eq, ineq, comp}. */
+void orc_nlp_residuals(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0, double res[4]);
+int orc_sqp_solve(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref, const double *p,
+                  const double *gp_state, orc_iterate *it, int max_iter, const double tol[4], int *sqp_iter,
+                  double res_out[4]);
+int orc_sqp_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                  const double *p, const double *gp_state, double *xit, double *uit, int max_iter, const double *tol,
+                  int *status, int *sqp_iter, double *res, int nthreads);
+
 int orc_load_ref_model(const char *path); /* dlopen oracle/_ref/libsim_car_ref.so; 0 on success */
 
 #ifdef __cplusplus

@@ -358,3 +358,79 @@ def test_c_example_runs():
                         "-Wl,-rpath," + os.path.join(root, "ad_mpc_b200"), "-lm"], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "EXAMPLE_OK" in out.stdout, out.stdout[-800:] + out.stderr[-400:]
+
+
+def _gpu_sqp(s, batch, **kw):
+    s.set_iterate(batch["x_init"], batch["u_init"])
+    s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"])
+    info = s.solve_sqp(**kw)
+    info.update(u=s.get_u(), x=s.get_x())
+    return info
+
+
+@pytest.mark.parametrize("B,N,p", [(200, 20, 1.0), (64, 40, 0.0)])
+def test_sqp_mode_parity(B, N, p):
+    """Full SQP (point-reference mode of the reference, create_ros_ad_mpc.py:47-51): identical acados statuses and SQP
+    iteration counts, 1e-8 agreement of the converged trajectories; instances finish at different iterations."""
+    batch = wl.make_batch(B, N, seed=90 + N, p=p, perturb=3.0)
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    g = _gpu_sqp(s, batch)
+    r = orc.sqp_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"])
+    assert np.array_equal(g["status"], r["status"]) and (r["status"] == 0).all()
+    assert np.array_equal(g["sqp_iter"], r["sqp_iter"]), (g["sqp_iter"][:16], r["sqp_iter"][:16])
+    assert len(set(r["sqp_iter"].tolist())) > 1 and g["iterations_run"] == r["sqp_iter"].max()
+    assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL
+    assert mixed_err(g["res"], r["res"]) <= 1e-6 and (g["res"] < 1e-6).all()
+    # iteration budget: MAXITER (2) for the instances that need more, same iterate as the oracle's truncated loop
+    g2 = _gpu_sqp(s, batch, max_iter=3)
+    r2 = orc.sqp_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], max_iter=3)
+    assert np.array_equal(g2["status"], r2["status"]) and (r2["status"] == 2).any()
+    assert np.array_equal(g2["sqp_iter"], r2["sqp_iter"])
+    assert mixed_err(g2["u"], r2["u"]) <= TOL and mixed_err(g2["x"], r2["x"]) <= TOL
+    # the plain RTI step still works on the same handle afterwards (finished-instance flags are reset per solve)
+    g3 = _gpu_step(s, batch)
+    _compare(g3, oracle_batch(mirror_opts(opts), batch))
+    s.close()
+
+
+def test_sqp_mode_with_gp_and_other_qp_kernels(monkeypatch):
+    """SQP loop on the GP-augmented model, and through the thread-per-instance / octet QP kernels (skip flags)."""
+    B, N = 48, 20
+    batch = wl.make_batch(B, N, seed=93, p=1.0, perturb=2.0)
+    model = wl.make_gp(M=40, seed=5)
+    opts = default_opts(N)
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    r = orc.sqp_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=gp, gp_state=batch["x0"])
+    for v in (4, 3, 1):
+        monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
+        s = BatchSolver(B, opts)
+        s.set_gp(model)
+        s.set_gp_state(batch["x0"])
+        g = _gpu_sqp(s, batch)
+        assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["sqp_iter"], r["sqp_iter"]), v
+        assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL, v
+        s.close()
+
+
+def test_acados_shim_sqp_mode():
+    """AcadosOcpSolverB200(nlp_solver_type="SQP"): solve() iterates to convergence, get_stats("sqp_iter") reports it."""
+    N = 20
+    b = wl.make_batch(1, N, seed=95, p=0.0, perturb=2.0)
+    opts = default_opts(N)
+    cap = AcadosOcpSolverB200(opts, nlp_solver_type="SQP")
+    for j in range(N):
+        cap.set(j, "yref", b["yref"][0][j * 9:(j + 1) * 9])
+        cap.set(j, "p", b["p"][0][j])
+    cap.set(N, "yref", b["yref"][0][N * 9:])
+    for j in range(N + 1):
+        cap.set(j, "x", b["x_init"][0, j])
+    cap.set(0, "lbx", b["x0"][0]); cap.set(0, "ubx", b["x0"][0])
+    assert cap.solve() == 0
+    r = orc.sqp_batch(mirror_opts(opts), b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"])
+    assert cap.get_stats("sqp_iter") == r["sqp_iter"][0] > 1
+    u = np.stack([cap.get(j, "u") for j in range(N)])
+    assert mixed_err(u, r["u"][0]) <= TOL
+    cap.free() if hasattr(cap, "free") else None

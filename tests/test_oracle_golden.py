@@ -149,3 +149,35 @@ def test_golden_rti_fixed_point(golden_dir):
     assert np.abs(arr["pi"] - g["pi"]).max() < 1e-5
     act = lam > 1e-3          # active multipliers (input bound at stage 0, slack multipliers 0.5 = Ts*z)
     assert np.abs(arr["lam"][act] - lam[act]).max() < 1e-5
+
+
+def test_sqp_mode_oracle_properties(golden_dir):
+    """Full SQP (nlp_solver_type "SQP", create_ros_ad_mpc.py:47-51): converges on the benchmark workload, a budget of k
+    iterations equals k chained RTI steps bit for bit, and the acados golden iterate (a converged solution) passes the
+    NLP residual check immediately (0 QPs)."""
+    from ad_mpc_b200 import workload as wl
+    N = 20
+    b = wl.make_batch(12, N, seed=9, p=1.0, perturb=2.0)
+    o = orc.default_opts(N)
+    r = orc.sqp_batch(o, b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"])
+    assert (r["status"] == 0).all() and (r["sqp_iter"] >= 2).all() and (r["sqp_iter"] <= 12).all()
+    assert (r["res"] < 1e-6).all()
+    # one more RTI step from the converged point is (numerically) a zero step
+    again = orc.rti_batch(o, b["x0"], b["yref"], b["p"], r["x"], r["u"])
+    assert np.abs(again["u"] - r["u"]).max() < 1e-5 and np.abs(again["x"] - r["x"]).max() < 1e-5
+    # budget of 2 iterations == 2 chained RTI steps, status MAXITER (2)
+    r2 = orc.sqp_batch(o, b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"], max_iter=2)
+    s1 = orc.rti_batch(o, b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"])
+    s2 = orc.rti_batch(o, b["x0"], b["yref"], b["p"], s1["x"], s1["u"])
+    assert (r2["status"] == 2).all() and (r2["sqp_iter"] == 2).all()
+    assert np.array_equal(r2["x"], s2["x"]) and np.array_equal(r2["u"], s2["u"])
+    # golden acados iterate: SQP from the converged point needs at most one QP
+    g = _load(golden_dir, "sim_car_iterate.npz")
+    We = np.array([10.0, 10.0, 100.0, 0, 0, 0, 0])
+    o40 = orc.default_opts(N=40, We=We)
+    A, B, _ = _golden_lin(g, o40)
+    lam, t = _golden_lam(g)
+    yref = _recover_yref(g, o40, A, lam, We)
+    rg = orc.sqp_batch(o40, g["x"][0][None], yref[None], np.zeros((1, 40)), g["x"][None], g["u"][None], tol=(1e-5,) * 4)
+    assert rg["status"][0] == 0 and rg["sqp_iter"][0] <= 1
+    assert np.abs(rg["x"][0] - g["x"]).max() < 5e-6 and np.abs(rg["u"][0] - g["u"]).max() < 5e-6
