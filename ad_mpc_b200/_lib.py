@@ -93,6 +93,8 @@ SYMBOLS = {
     "admpc_batch_gather": (C.c_int, [_vp, C.c_int, _dp, _dp, _ip]),
     "admpc_batch_barrier": (C.c_int, [_vp]),
     "admpc_gp_fit": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_float)]),
+    "admpc_gp_predict": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, _dp,
+                                   _dp, _dp, _dp]),
     "admpc_batch_solve_sqp": (C.c_int, [_vp, C.c_int, _dp, _ip]),
     "admpc_batch_get_sqp_info": (C.c_int, [_vp, _ip, _ip, _dp]),
     "sim_car_acados_set_nlp_solver": (C.c_int, [_vp, _cp, C.c_int, _dp]),

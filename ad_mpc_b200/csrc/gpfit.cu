@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) gpfit_syrk32(double *A, int Mp, int jb, i
 }
 
 // y <- L^-1 y, then y <- L^-T y (blocked by 32, single CTA), plus log-determinant and y0^T alpha
-__global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restrict__ A, int M, int Mp, double *y,
+// (the Mp x Mp factor may sit in the top-left corner of a larger matrix: row stride ldA)
+__global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restrict__ A, int M, int Mp, int ldA, double *y,
                                                             const double *__restrict__ y0, double *out2)
 {
     __shared__ double xb[TB];
@@ -121,17 +122,17 @@ __global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restr
         if (t < 32) {
             double v = y[b * TB + t];
             for (int c = 0; c < TB; c++) {
-                const double lcc = A[(size_t)(b * TB + c) * Mp + b * TB + c];
+                const double lcc = A[(size_t)(b * TB + c) * ldA + b * TB + c];
                 const double xc = __shfl_sync(0xffffffffu, v, c) / lcc;
                 if (t == c) v = xc;
-                else if (t > c) v = fma(-A[(size_t)(b * TB + t) * Mp + b * TB + c], xc, v);
+                else if (t > c) v = fma(-A[(size_t)(b * TB + t) * ldA + b * TB + c], xc, v);
             }
             xb[t] = v;
             y[b * TB + t] = v;
         }
         __syncthreads();
         for (int i = (b + 1) * TB + t; i < Mp; i += blockDim.x) {
-            const double *row = A + (size_t)i * Mp + b * TB;
+            const double *row = A + (size_t)i * ldA + b * TB;
             double s = 0.0;
 #pragma unroll 8
             for (int c = 0; c < TB; c++) s = fma(row[c], xb[c], s);
@@ -144,10 +145,10 @@ __global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restr
         if (t < 32) {
             double v = y[b * TB + t];
             for (int c = TB - 1; c >= 0; c--) {
-                const double lcc = A[(size_t)(b * TB + c) * Mp + b * TB + c];
+                const double lcc = A[(size_t)(b * TB + c) * ldA + b * TB + c];
                 const double xc = __shfl_sync(0xffffffffu, v, c) / lcc;
                 if (t == c) v = xc;
-                else if (t < c) v = fma(-A[(size_t)(b * TB + c) * Mp + b * TB + t], xc, v);
+                else if (t < c) v = fma(-A[(size_t)(b * TB + c) * ldA + b * TB + t], xc, v);
             }
             xb[t] = v;
             y[b * TB + t] = v;
@@ -156,14 +157,14 @@ __global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restr
         for (int i = t; i < b * TB; i += blockDim.x) {
             double s = 0.0;
 #pragma unroll 8
-            for (int r = 0; r < TB; r++) s = fma(A[(size_t)(b * TB + r) * Mp + i], xb[r], s);
+            for (int r = 0; r < TB; r++) s = fma(A[(size_t)(b * TB + r) * ldA + i], xb[r], s);
             y[i] -= s;
         }
         __syncthreads();
     }
     // reductions: sum_i log L_ii (i < M) and y0^T alpha
     double ld = 0.0, qa = 0.0;
-    for (int i = t; i < M; i += blockDim.x) { ld += log(A[(size_t)i * Mp + i]); qa = fma(y0[i], y[i], qa); }
+    for (int i = t; i < M; i += blockDim.x) { ld += log(A[(size_t)i * ldA + i]); qa = fma(y0[i], y[i], qa); }
     for (int pass = 0; pass < 2; pass++) {
         double v = pass ? qa : ld;
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -221,7 +222,7 @@ extern "C" int admpc_gp_fit(int device, int M, int dz, const double *X, const do
                 gpfit_syrk32<<<dim3(rem, rem), dim3(16, 16), 0, s>>>(dA, Mp, j, nb);
             }
         }
-        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, dy, dy0, dout);
+        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, Mp, dy, dy0, dout);
         GP_TRY(cudaEventRecord(e1, s));
         GP_TRY(cudaGetLastError());
         double out2[2];
@@ -237,6 +238,126 @@ extern "C" int admpc_gp_fit(int device, int M, int dz, const double *X, const do
     } while (0);
     cudaFree(dXs); cudaFree(dA); cudaFree(dy); cudaFree(dy0); cudaFree(dout); cudaFree(dfail);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------- posterior variance ---
+// GP posterior at n test points (reference: CustomGPRegression.predict(x, return_cov=True), gp.py:402-441):
+//     mu  = k_s K^-1 y + y_mean ,   cov = k(x*, x*) + 1e-8 I - k_s K^-1 k_s^T
+// computed WITHOUT forming K^-1: the blocked Cholesky above is run on the augmented matrix
+//     [ K      k_s^T        ]
+//     [ k_s    k_ss + 1e-8 I ]
+// for the first Mp/32 block columns only; what is left in the trailing n x n block is the Schur complement = cov
+// (same potrf32 / trsm32 / syrk32 kernels, the test rows are just more tiles below the diagonal).
+__global__ void gpfit_build_aug_kernel(const double *__restrict__ Xs, const double *__restrict__ Xt, int M, int Mp, int n,
+                                       int Mt, int dz, double sigma_f, double sn2, double *__restrict__ A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= Mt || j >= Mt) return;
+    const bool itr = i < M, jtr = j < M, its = i >= Mp && i < Mp + n, jts = j >= Mp && j < Mp + n;
+    double v = (i == j) ? 1.0 : 0.0;                       // padding rows / columns: identity
+    if ((itr || its) && (jtr || jts)) {
+        const double *pi = itr ? Xs + (size_t)i * dz : Xt + (size_t)(i - Mp) * dz;
+        const double *pj = jtr ? Xs + (size_t)j * dz : Xt + (size_t)(j - Mp) * dz;
+        double d2 = 0.0;
+        for (int d = 0; d < dz; d++) { const double t = pi[d] - pj[d]; d2 = fma(t, t, d2); }
+        v = sigma_f * exp(-0.5 * d2);
+        if (i == j) v += itr ? sn2 : 1e-8;
+    }
+    A[(size_t)i * Mt + j] = v;
+}
+
+// mu_i = sum_j k(x*_i, x_j) alpha_j + y_mean : one warp per test point
+__global__ void gpfit_mean_kernel(const double *__restrict__ Xs, const double *__restrict__ Xt, const double *__restrict__ alpha,
+                                  int M, int n, int dz, double sigma_f, double y_mean, double *__restrict__ mu)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (w >= n) return;
+    double s = 0.0;
+    for (int j = l; j < M; j += 32) {
+        double d2 = 0.0;
+        for (int d = 0; d < dz; d++) { const double t = Xt[(size_t)w * dz + d] - Xs[(size_t)j * dz + d]; d2 = fma(t, t, d2); }
+        s = fma(sigma_f * exp(-0.5 * d2), alpha[j], s);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (l == 0) mu[w] = s + y_mean;
+}
+
+// variance = diagonal of the Schur complement; optional full covariance (lower triangle mirrored)
+__global__ void gpfit_cov_out_kernel(const double *__restrict__ A, int Mp, int n, int Mt, double *__restrict__ var,
+                                     double *__restrict__ cov)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= n || j >= n) return;
+    const int r = i > j ? i : j, c = i > j ? j : i;
+    const double v = A[(size_t)(Mp + r) * Mt + Mp + c];
+    if (cov) cov[(size_t)i * n + j] = v;
+    if (i == j) var[i] = v;
+}
+
+extern "C" int admpc_gp_predict(int device, int M, int dz, const double *X, const double *y, const double *ell, double sigma_f,
+                                double sigma_n, double y_mean, int n, const double *Xtest, double *mu_out, double *var_out,
+                                double *cov_out)
+{
+    if (M < 1 || n < 1 || dz < 1 || dz > ADMPC_DZMAX || !X || !y || !ell || !Xtest) { admpc_set_error("admpc_gp_predict", "bad argument"); return ADMPC_E_ARG; }
+    int ndev = 0;
+    CUDA_CHECK_RET(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { admpc_set_error("admpc_gp_predict", "no such CUDA device"); return ADMPC_E_CUDA; }
+    CUDA_CHECK_RET(cudaSetDevice(device));
+    const int Mp = (M + TB - 1) / TB * TB, np_ = (n + TB - 1) / TB * TB, Mt = Mp + np_, nbM = Mp / TB, nb = Mt / TB;
+    std::vector<double> Xs((size_t)M * dz), Xt((size_t)n * dz), yp(Mp, 0.0);
+    for (int i = 0; i < M; i++)
+        for (int d = 0; d < dz; d++) Xs[(size_t)i * dz + d] = X[(size_t)i * dz + d] / ell[d];
+    for (int i = 0; i < n; i++)
+        for (int d = 0; d < dz; d++) Xt[(size_t)i * dz + d] = Xtest[(size_t)i * dz + d] / ell[d];
+    for (int i = 0; i < M; i++) yp[i] = y[i];
+    double *dXs = nullptr, *dXt = nullptr, *dA = nullptr, *dy = nullptr, *dy0 = nullptr, *dout = nullptr, *dmu = nullptr, *dvar = nullptr, *dcov = nullptr;
+    int *dfail = nullptr;
+    cudaStream_t s;
+    CUDA_CHECK_RET(cudaStreamCreate(&s));
+    int rc = 0;
+    do {
+#define GP_TRY(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { admpc_set_error(#call, cudaGetErrorString(e_)); rc = ADMPC_E_CUDA; break; } }
+        GP_TRY(cudaMalloc(&dXs, Xs.size() * sizeof(double)));
+        GP_TRY(cudaMalloc(&dXt, Xt.size() * sizeof(double)));
+        GP_TRY(cudaMalloc(&dA, (size_t)Mt * Mt * sizeof(double)));
+        GP_TRY(cudaMalloc(&dy, Mp * sizeof(double)));
+        GP_TRY(cudaMalloc(&dy0, Mp * sizeof(double)));
+        GP_TRY(cudaMalloc(&dout, 2 * sizeof(double)));
+        GP_TRY(cudaMalloc(&dmu, n * sizeof(double)));
+        GP_TRY(cudaMalloc(&dvar, n * sizeof(double)));
+        if (cov_out) GP_TRY(cudaMalloc(&dcov, (size_t)n * n * sizeof(double)));
+        GP_TRY(cudaMalloc(&dfail, sizeof(int)));
+        GP_TRY(cudaMemcpyAsync(dXs, Xs.data(), Xs.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        GP_TRY(cudaMemcpyAsync(dXt, Xt.data(), Xt.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        GP_TRY(cudaMemcpyAsync(dy, yp.data(), Mp * sizeof(double), cudaMemcpyHostToDevice, s));
+        GP_TRY(cudaMemcpyAsync(dy0, yp.data(), Mp * sizeof(double), cudaMemcpyHostToDevice, s));
+        GP_TRY(cudaMemsetAsync(dfail, 0, sizeof(int), s));
+        dim3 bb(16, 16), bg((Mt + 15) / 16, (Mt + 15) / 16);
+        gpfit_build_aug_kernel<<<bg, bb, 0, s>>>(dXs, dXt, M, Mp, n, Mt, dz, sigma_f, sigma_n * sigma_n, dA);
+        for (int j = 0; j < nbM; j++) {                      // eliminate the training block only
+            gpfit_potrf32<<<1, dim3(TB, TB), 0, s>>>(dA, Mt, j, dfail);
+            const int rem = nb - j - 1;
+            gpfit_trsm32<<<(rem + 3) / 4, 128, 0, s>>>(dA, Mt, j, nb);
+            gpfit_syrk32<<<dim3(rem, rem), dim3(16, 16), 0, s>>>(dA, Mt, j, nb);
+        }
+        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, Mt, dy, dy0, dout);        // alpha = K^-1 y
+        gpfit_mean_kernel<<<(n * 32 + 127) / 128, 128, 0, s>>>(dXs, dXt, dy, M, n, dz, sigma_f, y_mean, dmu);
+        dim3 cg((n + 15) / 16, (n + 15) / 16);
+        gpfit_cov_out_kernel<<<cg, bb, 0, s>>>(dA, Mp, n, Mt, dvar, dcov);
+        GP_TRY(cudaGetLastError());
+        int fail = 0;
+        GP_TRY(cudaMemcpyAsync(&fail, dfail, sizeof fail, cudaMemcpyDeviceToHost, s));
+        if (mu_out) GP_TRY(cudaMemcpyAsync(mu_out, dmu, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (var_out) GP_TRY(cudaMemcpyAsync(var_out, dvar, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (cov_out) GP_TRY(cudaMemcpyAsync(cov_out, dcov, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        GP_TRY(cudaStreamSynchronize(s));
+        if (fail) { admpc_set_error("admpc_gp_predict", "kernel matrix is not positive definite"); rc = ADMPC_E_ARG; break; }
+#undef GP_TRY
+    } while (0);
+    cudaFree(dXs); cudaFree(dXt); cudaFree(dA); cudaFree(dy); cudaFree(dy0); cudaFree(dout); cudaFree(dmu); cudaFree(dvar); cudaFree(dcov); cudaFree(dfail);
     cudaStreamDestroy(s);
     return rc;
 }

@@ -51,7 +51,27 @@ def fit(X, y, ell0=None, sigma_f0=1.0, sigma_n0=1e-2, device=0, optimise=True):
         theta = res.x
     p = np.exp(theta)
     nll, alpha, _ = nll_alpha(X, yc, p[:dz], p[dz], p[dz + 1], device=device)
-    return dict(X=X, alpha=alpha, ell=p[:dz].copy(), sigma_f=float(p[dz]), sigma_n=float(p[dz + 1]), y_mean=y_mean, nll=nll)
+    return dict(X=X, y=yc, alpha=alpha, ell=p[:dz].copy(), sigma_f=float(p[dz]), sigma_n=float(p[dz + 1]), y_mean=y_mean, nll=nll)
+
+
+def predict(model, x_test, y=None, device=0, return_cov=False, full_cov=False):
+    """Mirror of `CustomGPRegression.predict(x_test, return_std/return_cov)` (gp.py:402-441) for one fitted output
+    (dict from `fit`, plus the mean-removed training targets `y` if the dict does not carry them as model["y"]).
+    Returns mu, or (mu, var) / (mu, var, cov[n,n])."""
+    L = _lib.load()
+    X = np.ascontiguousarray(model["X"], dtype=np.float64)
+    yc = np.ascontiguousarray(model["y"] if y is None else y, dtype=np.float64).reshape(-1)
+    xt = np.ascontiguousarray(np.atleast_2d(np.asarray(x_test, dtype=np.float64)))
+    ell = np.ascontiguousarray(np.broadcast_to(np.asarray(model["ell"], dtype=np.float64).reshape(-1), (X.shape[1],)))
+    n = xt.shape[0]
+    mu, var = np.empty(n), np.empty(n)
+    cov = np.empty((n, n)) if full_cov else None
+    check(L.admpc_gp_predict(int(device), X.shape[0], X.shape[1], _dp(X), _dp(yc), _dp(ell), float(model["sigma_f"]),
+                             float(model["sigma_n"]), float(model["y_mean"]), n, _dp(xt), _dp(mu), _dp(var),
+                             _dp(cov) if full_cov else None), "admpc_gp_predict")
+    if full_cov:
+        return mu, var, cov
+    return (mu, var) if return_cov else mu
 
 
 def stack_models(models, feat=(3, 4, 5, 6), rows=(4, 5)):

@@ -205,6 +205,14 @@ int admpc_batch_barrier(admpc_batch *h);
 int admpc_gp_fit(int device, int M, int dz, const double *X /*[M][dz]*/, const double *y /*[M]*/, const double *ell /*[dz]*/,
                  double sigma_f, double sigma_n, double *alpha_out /*[M] or NULL*/, double *nll_out, float *ms_out);
 
+/* GP posterior at n test points (next-row f4; reference: CustomGPRegression.predict(x, return_cov=True),
+ * model_fitting/gp.py:402-441): mu = k_s K^-1 y + y_mean, cov = k(x*,x*) + 1e-8 I - k_s K^-1 k_s^T.  The reference forms
+ * inv(K); here the blocked Cholesky of admpc_gp_fit runs on the augmented matrix and the Schur complement is the
+ * covariance.  var_out [n] = diag(cov); cov_out [n][n] full covariance or NULL; y has its mean removed (gp.py:343). */
+int admpc_gp_predict(int device, int M, int dz, const double *X /*[M][dz]*/, const double *y /*[M]*/, const double *ell,
+                     double sigma_f, double sigma_n, double y_mean, int n, const double *Xtest /*[n][dz]*/,
+                     double *mu_out, double *var_out, double *cov_out);
+
 /* Full SQP mode (nlp_solver_type "SQP": $A/create_ros_ad_mpc.py:47-51 -> $A/ad_3d_optimizer.py:205; defaults
  * nlp_solver_max_iter 100 and tolerances 1e-6 from acados_models/sim_car_acados_ocp.json:868-873).  Repeats
  * { linearise; NLP KKT residual check; QP; full step } on the device until every instance has converged, failed or

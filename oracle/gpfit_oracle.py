@@ -27,3 +27,20 @@ def alpha(X, y, ell, sigma_f, sigma_n):
     K = train_kernel(X, ell, sigma_f, sigma_n)
     L = np.linalg.cholesky(K)
     return np.linalg.solve(L.T, np.linalg.solve(L, y))
+
+
+def predict(X, y, ell, sigma_f, sigma_n, y_mean, xt):
+    """Posterior mean and variance of `CustomGPRegression.predict(x_test, return_cov=True)` (gp.py:402-441):
+    k_s = k(x_test, X); mu = k_s K^-1 y + y_mean; cov = k(x_test, x_test) + 1e-8 I - k_s K^-1 k_s^T, diagonal returned.
+    K^-1 is formed explicitly like the reference does (gp.py:362)."""
+    X = np.asarray(X, dtype=np.float64); xt = np.atleast_2d(np.asarray(xt, dtype=np.float64))
+    K = train_kernel(X, ell, sigma_f, sigma_n)
+    K_inv = np.linalg.inv(K)
+    a, b = xt / ell, X / ell
+    d2 = ((a[:, None, :] - b[None, :, :]) ** 2).sum(axis=2)
+    k_s = sigma_f * np.exp(-0.5 * d2)
+    d2s = ((a[:, None, :] - a[None, :, :]) ** 2).sum(axis=2)
+    k_ss = sigma_f * np.exp(-0.5 * d2s) + 1e-8 * np.eye(xt.shape[0])
+    mu = k_s @ (K_inv @ y) + y_mean
+    cov = k_ss - k_s @ K_inv @ k_s.T
+    return mu, np.diag(cov).copy(), cov

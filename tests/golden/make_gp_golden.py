@@ -1,7 +1,7 @@
 """Golden vectors for the GP path, produced by the reference's OWN numeric code (model_fitting/gp.py), imported in the
 build container with its symbolic dependencies stubbed (casadi is only needed for the CasADi twins; utils.utils for
 two unrelated helpers).  Pins: NLL values (gp.py:292-316), the fitted K^-1 y (gp.py:361-363) and the posterior mean of
-`predict` (gp.py:426-430) on seeded data.
+`predict` (gp.py:426-430) and its posterior variance (return_cov, gp.py:425-441) on seeded data.
 
   python tests/golden/make_gp_golden.py   ->  tests/golden/gp_reference.npz
 """
@@ -69,6 +69,9 @@ def main():
         reg.fit(X.copy(), y.copy())                                   # L-BFGS-B on the NLL, then K, K^-1, K^-1 y
         xt = rng.uniform(lo, hi, size=(64, dz))
         mu = np.asarray(reg.predict(xt)).reshape(-1)
+        mu_c, cov = reg.predict(xt, return_cov=True)                  # posterior variance (gp.py:425-441)
+        assert np.allclose(np.asarray(mu_c).reshape(-1), mu)
+        out[tag + "_var"] = np.asarray(cov).reshape(-1)
         out[tag + "_X"] = np.asarray(reg.x_train)
         out[tag + "_y"] = np.asarray(reg.y_train)                     # mean-subtracted by fit (gp.py:343)
         out[tag + "_y_mean"] = np.array(y_mean)

@@ -42,3 +42,15 @@ def test_gpfit_oracle_matches_reference_nll_and_alpha(golden_dir, tag):
     assert np.abs(a - ref).max() <= 1e-6 * np.abs(ref).max()
     K = gf.train_kernel(X, g[tag + "_ell"], float(g[tag + "_sigma_f"]), float(g[tag + "_sigma_n"]))
     assert np.abs(K @ ref - y).max() <= 1e-8 * max(1.0, np.abs(y).max())
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_gp_posterior_variance_oracle_matches_reference_predict(golden_dir, tag):
+    """oracle predict (mean + variance) against CustomGPRegression.predict(x, return_cov=True) of the reference module."""
+    from oracle import gpfit_oracle as go
+    d = np.load(os.path.join(golden_dir, "gp_reference.npz"))
+    mu, var, cov = go.predict(d[tag + "_X"], d[tag + "_y"], d[tag + "_ell"], float(d[tag + "_sigma_f"]), float(d[tag + "_sigma_n"]),
+                              float(d[tag + "_y_mean"]), d[tag + "_xtest"])
+    assert np.abs(mu - d[tag + "_mu"]).max() <= 1e-12
+    assert np.abs(var - d[tag + "_var"]).max() <= 1e-14
+    assert (var > 0).all() and np.allclose(cov, cov.T, atol=1e-12)

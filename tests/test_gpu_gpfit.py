@@ -83,3 +83,32 @@ def test_hyperparameter_search_decreases_nll():
     ref = gf.nll(X, yc, m1["ell"], m1["sigma_f"], m1["sigma_n"])
     assert abs(ref - m1["nll"]) <= 1e-8 * max(1.0, abs(ref))
     assert np.all(m1["ell"] >= 1e-5 * (1 - 1e-9)) and np.all(m1["ell"] <= 10.0 * (1 + 1e-9)) and 1e-8 * (1 - 1e-9) <= m1["sigma_n"] <= 1.0 + 1e-9   # gp.py:336-338
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_posterior_mean_and_variance_match_reference_predict(golden_dir, tag):
+    """admpc_gp_predict (Schur complement of the blocked Cholesky) against CustomGPRegression.predict(return_cov=True).
+    The reference forms inv(K) (gp.py:362); the two routes agree to ~1e-12 absolute on variances of 1e-5."""
+    g = np.load(os.path.join(golden_dir, "gp_reference.npz"))
+    model = dict(X=g[tag + "_X"], y=g[tag + "_y"], ell=g[tag + "_ell"], sigma_f=float(g[tag + "_sigma_f"]),
+                 sigma_n=float(g[tag + "_sigma_n"]), y_mean=float(g[tag + "_y_mean"]))
+    mu, var, cov = gpfit.predict(model, g[tag + "_xtest"], full_cov=True)
+    assert np.abs(mu - g[tag + "_mu"]).max() <= 1e-8 * max(1.0, np.abs(g[tag + "_mu"]).max())
+    assert np.abs(var - g[tag + "_var"]).max() <= 1e-10
+    _, _, cov_o = gf.predict(model["X"], model["y"], model["ell"], model["sigma_f"], model["sigma_n"], model["y_mean"], g[tag + "_xtest"])
+    assert np.abs(cov - cov_o).max() <= 1e-10 and np.array_equal(cov, cov.T)
+    assert np.array_equal(np.diag(cov), var)
+
+
+@pytest.mark.parametrize("M,n", [(1, 1), (33, 70), (500, 257)])
+def test_posterior_sizes_against_oracle(M, n):
+    rng = np.random.default_rng(M + n)
+    X = rng.uniform(-1, 1, size=(M, 3))
+    y = np.sin(X[:, 0]) + 0.01 * rng.normal(size=M)
+    y = y - y.mean()
+    xt = rng.uniform(-1.5, 1.5, size=(n, 3))
+    model = dict(X=X, y=y, ell=np.array([0.7, 1.1, 2.0]), sigma_f=0.8, sigma_n=0.05, y_mean=0.3)
+    mu, var = gpfit.predict(model, xt, return_cov=True)
+    mu_o, var_o, _ = gf.predict(X, y, model["ell"], 0.8, 0.05, 0.3, xt)
+    assert np.abs(mu - mu_o).max() <= 1e-9 and np.abs(var - var_o).max() <= 1e-10
+    assert (var > 0).all() and (var <= 0.8 + 1e-8 + 1e-12).all()
