@@ -12,7 +12,7 @@ DZMAX, GPOUT_MAX = 8, 2
 class AdmpcOpts(C.Structure):
     _fields_ = [
         ("N", C.c_int), ("iter_max", C.c_int), ("gp_enabled", C.c_int), ("gp_nout", C.c_int), ("gp_M", C.c_int),
-        ("gp_dz", C.c_int), ("gp_stage0_trigger", C.c_int), ("reserved0", C.c_int),
+        ("gp_dz", C.c_int), ("gp_stage0_trigger", C.c_int), ("model_variant", C.c_int),
         ("gp_feat", C.c_int * DZMAX), ("gp_row", C.c_int * GPOUT_MAX),
         ("dt", C.c_double), ("W", C.c_double * 9), ("We", C.c_double * 7),
         ("zl", C.c_double * 2), ("zu", C.c_double * 2), ("Zl", C.c_double * 2), ("Zu", C.c_double * 2),
@@ -55,6 +55,7 @@ SYMBOLS = {
     "admpc_batch_set_yref": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_p": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_p_scalar": (C.c_int, [_vp, _dp]),
+    "admpc_batch_set_kappa": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_gp_state": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_iterate": (C.c_int, [_vp, _dp, _dp]),
     "admpc_batch_reset": (C.c_int, [_vp]),

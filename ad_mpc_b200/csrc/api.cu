@@ -139,6 +139,7 @@ static size_t gp_blob_doubles(int nout, int M, int dz) { return gp_stride(M, dz)
 extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, admpc_batch **out)
 {
     if (!opts || !out || B <= 0 || opts->N < 2 || opts->N > ADMPC_NMAX) { admpc_set_error("admpc_batch_create", "bad argument"); return ADMPC_E_ARG; }
+    if (opts->model_variant != 0 && opts->model_variant != 1) { admpc_set_error("admpc_batch_create", "model_variant must be 0 (Cartesian) or 1 (Frenet)"); return ADMPC_E_ARG; }
     int ndev = 0;
     CUDA_CHECK_RET(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { admpc_set_error("admpc_batch_create", "no such CUDA device"); return ADMPC_E_CUDA; }
@@ -162,17 +163,19 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     // carve the pool
     struct Item { double **p; size_t rows; };
     const size_t nX = (size_t)(N + 1) * 7, nU = (size_t)N * 2, nPi = (size_t)N * 7, nC = (size_t)N * NC;
-    double *x0, *yref, *pp, *gps;
+    double *x0, *yref, *pp, *gps, *kap = nullptr;
     // Interface arrays always; QP workspaces only for the kernel variant this handle will run: the warp-per-instance
     // kernel (N <= 63) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
     // thread-per-instance kernel streams a 35 KB/instance SoA workspace.
     const int variant = h->qp_variant ? h->qp_variant : (N <= 63 ? 4 : 3);
     const bool need_ws3 = (variant == 3 || (variant == 4 && N > 63)) && N <= 80;
-    const bool need_ws1 = (variant == 1) || N > 80;
+    const bool frenet = h->P.o.model_variant == 1;
+    const bool need_ws1 = (variant == 1) || N > 80 || frenet;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
         {&P.nlp_res, 4},
+        {&P.lin_d, frenet ? (size_t)(N + 1) * DL_ROWS : 0}, {&kap, frenet ? (size_t)N : 0},
         {&P.lin, (size_t)(N + 1) * LIN_ROWS}, {&P.res_out, 4},
     };
     if (need_ws3) items.push_back({&P.ws, (size_t)qp_smem_ws_rows(N)});
@@ -191,7 +194,7 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     CUDA_CHECK_RET(cudaMemsetAsync(h->pool, 0, rows * Bp * sizeof(double), h->stream));
     size_t off = 0;
     for (auto &it : items) { *it.p = h->pool + off * Bp; off += it.rows; }
-    P.x0 = x0; P.yref = yref; P.p = pp; P.gps = gps;
+    P.x0 = x0; P.yref = yref; P.p = pp; P.gps = gps; P.kappa = kap;
     CUDA_CHECK_RET(cudaMalloc(&h->ipool, (6 * Bp + 32) * sizeof(int)));
     CUDA_CHECK_RET(cudaMemsetAsync(h->ipool, 0, (6 * Bp + 32) * sizeof(int), h->stream));
     P.status = h->ipool; P.qp_status = h->ipool + Bp; P.qp_iter = h->ipool + 2 * Bp; P.lin_bad = h->ipool + 3 * Bp;
@@ -312,6 +315,12 @@ extern "C" int admpc_batch_set_x0(admpc_batch *h, const double *x0)
 }
 extern "C" int admpc_batch_set_yref(admpc_batch *h, const double *yref) { return put_rows(h, yref, (double *)h->P.yref, h->P.o.N * 9 + 7); }
 extern "C" int admpc_batch_set_p(admpc_batch *h, const double *p) { return put_rows(h, p, (double *)h->P.p, h->P.o.N); }
+extern "C" int admpc_batch_set_kappa(admpc_batch *h, const double *kappa)
+{
+    if (!h) return ADMPC_E_ARG;
+    if (h->P.o.model_variant != 1) { admpc_set_error("admpc_batch_set_kappa", "handle was not created with model_variant = 1 (Frenet)"); return ADMPC_E_STATE; }
+    return put_rows(h, kappa, (double *)h->P.kappa, h->P.o.N);
+}
 extern "C" int admpc_batch_set_p_scalar(admpc_batch *h, const double *p)
 {
     if (!h || !p) return ADMPC_E_ARG;
@@ -352,6 +361,13 @@ extern "C" int admpc_batch_reset(admpc_batch *h)
 static int launch_feedback(admpc_batch *h)
 {
     const Params &P = h->P;
+    if (P.o.model_variant == 1) {        // Frenet variant: dense stage matrices, generic kernel + separate update
+        launch_qp_dense(P, h->stream);
+        if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
+        launch_update(P, h->stream);
+        h->launches += 2;
+        return 0;
+    }
     // QP variant: 4 (default) warp per instance, register-resident IPM state; 3 shared-memory-resident octets
     // (horizons 64..80);
     // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
@@ -377,7 +393,8 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
     CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
-    launch_prepare(P, h->stream);
+    if (P.o.model_variant == 1) launch_prepare_dense(P, h->stream);
+    else launch_prepare(P, h->stream);
     h->launches += 1;
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
     if (int r = launch_feedback(h)) return r;
@@ -392,6 +409,7 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
 extern "C" int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double *tol4, int *iterations_run)
 {
     if (!h || max_iter < 0) return ADMPC_E_ARG;
+    if (h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_solve_sqp", "full SQP mode is implemented for the Cartesian model only"); return ADMPC_E_UNSUPPORTED; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     const Params &P = h->P;
     const double dflt[4] = {1e-6, 1e-6, 1e-6, 1e-6};            // sim_car_acados_ocp.json:870-873
@@ -652,6 +670,7 @@ void launch_refgen(const Params &P, const double *trk, int L, int H, double dt, 
 
 extern "C" int admpc_batch_set_track(admpc_batch *h, int L, const double *traj, int H, double traj_dt)
 {
+    if (h && h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_set_track", "Cartesian model only (the Frenet variant takes its reference in path coordinates)"); return ADMPC_E_UNSUPPORTED; }
     if (!h) return ADMPC_E_ARG;
     if (H < h->P.o.N) { admpc_set_error("admpc_batch_set_track", "reference horizon H must be >= N (gp_ad_mpc_node.py:172-175 single-point branch is not supported)"); return ADMPC_E_UNSUPPORTED; }
     TrackHost T;
@@ -734,6 +753,7 @@ static int loop_alloc(admpc_batch *h)
 // validity check + backup control + safety counter (+ plant step when advance != 0) for the last solve
 extern "C" int admpc_batch_postsolve(admpc_batch *h, int advance, int safe_threshold)
 {
+    if (h && h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_postsolve", "Cartesian model only (the Frenet variant takes its reference in path coordinates)"); return ADMPC_E_UNSUPPORTED; }
     if (!h) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     int r = loop_alloc(h);
@@ -749,6 +769,7 @@ extern "C" int admpc_batch_postsolve(admpc_batch *h, int advance, int safe_thres
 // log_x: optional host buffer [steps+1][B][7] receiving the plant state before every step and after the last one.
 extern "C" int admpc_batch_closed_loop(admpc_batch *h, int steps, int use_track, int safe_threshold, double *log_x)
 {
+    if (h && h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_closed_loop", "Cartesian model only (the Frenet variant takes its reference in path coordinates)"); return ADMPC_E_UNSUPPORTED; }
     if (!h || steps < 1) return ADMPC_E_ARG;
     if (use_track && !h->track) { admpc_set_error("admpc_batch_closed_loop", "no track set"); return ADMPC_E_STATE; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
@@ -908,7 +929,7 @@ struct sim_car_solver_capsule {
     bool opts_set = false;
     admpc_batch *h = nullptr;
     int N = 0;
-    std::vector<double> x0, yref, p, x, u, pi, lam, t, sl, su;
+    std::vector<double> x0, yref, p, kappa, x, u, pi, lam, t, sl, su;
     bool iterate_dirty = false, duals_stale = false;
     int status = 0, qp_status = 0, qp_iter = 0, sqp_iter = 1;
     bool nlp_sqp = false;            // nlp_solver_type: false "SQP_RTI" (shipped), true "SQP" (point-reference mode)
@@ -961,7 +982,7 @@ extern "C" int sim_car_acados_create_with_discretization(sim_car_solver_capsule 
     if (r) return r;
     c->opts = o;
     c->N = N;
-    c->x0.assign(7, 0.0); c->yref.assign((size_t)N * 9 + 7, 0.0); c->p.assign(N, 0.0);
+    c->x0.assign(7, 0.0); c->yref.assign((size_t)N * 9 + 7, 0.0); c->p.assign(N, 0.0); c->kappa.assign(N, 0.0);
     c->x.assign((size_t)(N + 1) * 7, 0.0); c->u.assign((size_t)N * 2, 0.0); c->pi.assign((size_t)N * 7, 0.0);
     c->lam.assign((size_t)N * NC, 0.0); c->t.assign((size_t)N * NC, 0.0); c->sl.assign((size_t)N * 2, 0.0); c->su.assign((size_t)N * 2, 0.0);
     return 0;
@@ -1019,6 +1040,11 @@ extern "C" int sim_car_acados_set(sim_car_solver_capsule *c, int stage, const ch
         return ADMPC_E_UNSUPPORTED;
     }
     if (!strcmp(field, "p")) { return sim_car_acados_update_params(c, stage, (double *)v, n); }
+    if (!strcmp(field, "kappa")) {       // Frenet variant: path curvature at this shooting node
+        if (n != 1 || stage >= N) return ADMPC_E_ARG;
+        if (c->opts.model_variant != 1) { admpc_set_error("sim_car_acados_set", "kappa needs model_variant = 1 (Frenet)"); return ADMPC_E_STATE; }
+        c->kappa[stage] = v[0]; return 0;
+    }
     if (!strcmp(field, "x")) {
         if (n != 7) return ADMPC_E_ARG;
         memcpy(&c->x[(size_t)stage * 7], v, sizeof(double) * 7); c->iterate_dirty = true; return 0;
@@ -1040,9 +1066,10 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
     if ((r = admpc_batch_set_x0(h, c->x0.data()))) return r;
     if ((r = admpc_batch_set_yref(h, c->yref.data()))) return r;
     if ((r = admpc_batch_set_p(h, c->p.data()))) return r;
+    if (c->opts.model_variant == 1 && (r = admpc_batch_set_kappa(h, c->kappa.data()))) return r;
     if (c->iterate_dirty) { if ((r = admpc_batch_set_iterate(h, c->x.data(), c->u.data()))) return r; c->iterate_dirty = false; }
     if (c->nlp_sqp) {
-        if ((r = admpc_batch_solve_sqp(h, c->nlp_max_iter, c->nlp_tol, nullptr))) return r;
+        if ((r = admpc_batch_solve_sqp(h, c->nlp_max_iter, c->nlp_tol, nullptr))) return r;     // Cartesian model only
     } else {
         if ((r = admpc_batch_solve(h))) return r;
     }

@@ -36,6 +36,7 @@ struct GpDev {
     int stride_out;     // doubles per output block
 };
 
+#define DL_ROWS 79
 struct Params {
     admpc_opts o;
     GpDev gp;
@@ -55,6 +56,9 @@ struct Params {
     int *status, *qp_status, *qp_iter, *lin_bad;
     double *res_out;     // [4][Bp] final residual norms
     // full SQP mode (sqp.cu): lin_bad == 2 marks an instance that has finished and is skipped by prepare / QP kernels
+    // Frenet variant (frenet.cu): dense linearisation [k][DL_ROWS][Bp] (A 49, B 14, b 7, q 7, r 2), curvature [N][Bp]
+    double *lin_d;
+    const double *kappa;
     int *sqp_status, *sqp_iter;
     double *nlp_res;     // [4][Bp] NLP KKT residual norms of the last check
 };
@@ -79,5 +83,7 @@ void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream
 void launch_update(const Params &P, cudaStream_t s);
 void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
 double run_fp64_peak(int device, int nint);
+void launch_prepare_dense(const Params &P, cudaStream_t s);
+void launch_qp_dense(const Params &P, cudaStream_t s);
 void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_sqp_finalize(const Params &P, cudaStream_t s);

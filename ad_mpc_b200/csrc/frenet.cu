@@ -1,0 +1,580 @@
+// frenet.cu -- Frenet-frame model variant (SURVEY.md 8a row A2'): preparation and feedback kernels for a model whose
+// linearisation has no exploitable structure beyond "dense 7x7 / 7x2".
+//
+// Reference: ad_mpc/__pycache__/fren_ad_3d_optimizer.cpython-36.pyc (bytecode only; equations recovered in SURVEY 8a):
+// state x = [s, e_y, e_psi, v_x, v_y, r, delta];  rows 3..6 are the Cartesian model's (ad_3d_optimizer.py:286-310),
+//     s'     = (v_x cos e_psi - v_y sin e_psi) / (1 - e_y kappa)
+//     e_y'   =  v_x sin e_psi + v_y cos e_psi
+//     e_psi' =  r - e_y kappa s'                         (literal bytecode form, including the e_y*kappa factor)
+// The reference evaluates a B-spline kappa(s) inside the model (compiled with placeholder knots); here kappa is a
+// per-instance, per-shooting-node parameter (admpc_batch_set_kappa), i.e. d/ds = 0 inside one linearisation.
+// With kappa = 0 the model IS the Cartesian one; tests pin this variant to the (reference-pinned) Cartesian path that
+// way.  The variant's own OCP (soft e_y bound, hard steering-rate bound) is not restated: the constraint set stays
+// the shipped one (both inputs soft, delta hard); weights / bounds / tyre factors are options.
+//
+// Kernels (first correct version, one thread per (instance, node) / per instance, no structure exploited):
+//   prepare_dense_kernel<GP>  RK4 + forward sensitivities with dense Jacobians, writes lin_d[k][79][Bp]
+//   qp_dense_kernel           the same Mehrotra / Riccati IPM as qp_ipm.cu on dense stage matrices
+// FP64-pipe bound like their structured twins; expect ~5-10x their run time.
+#include "common.cuh"
+
+#include "model.cuh"
+
+#define AT(arr, row) (arr)[(size_t)(row) * Bp + i]
+#define DL_A 0
+#define DL_B 49
+#define DL_b 63
+#define DL_q 70
+#define DL_r 77
+
+__device__ __forceinline__ double nmaxd(double a, double b) { return (a > b || a != a) ? a : b; }
+
+// dense f, Jx (7x7), Ju (7x2) of the Frenet variant at (x, u); rows 3..6 (+ GP) from the shared model code
+template <bool GP>
+__device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *gpsm, int gp_stride, const double x[7],
+                                            const double u[2], double p, double kap, const double gpx[7], double trig,
+                                            double f[7], double Jx[7][7], double Ju[7][2])
+{
+    Jac J;
+    model_eval<GP>(o, gpsm, gp_stride, x, u, p, gpx, trig, f, J);
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) Jx[r][c] = 0.0;
+        Ju[r][0] = 0.0; Ju[r][1] = 0.0;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+#pragma unroll
+        for (int l = 0; l < 5; l++) Jx[3 + rr][2 + l] = J.jr[rr][l];
+        Ju[3 + rr][0] = J.ju[rr][0]; Ju[3 + rr][1] = J.ju[rr][1];
+    }
+    Ju[6][1] = 1.0;
+    double sp, cp;
+    sincos(x[2], &sp, &cp);
+    const double ey = x[1], vx = x[3], vy = x[4], r = x[5];
+    const double vt = vx * cp - vy * sp, vn = vx * sp + vy * cp, den = 1.0 - ey * kap;
+    const double sd0 = vt / den;
+    f[0] = sd0; f[1] = vn; f[2] = r - ey * kap * sd0;
+    Jx[0][1] = sd0 * kap / den; Jx[0][2] = -vn / den; Jx[0][3] = cp / den; Jx[0][4] = -sp / den;
+    Jx[1][2] = vt; Jx[1][3] = sp; Jx[1][4] = cp;
+    Jx[2][1] = -kap * sd0 - ey * kap * Jx[0][1];
+    Jx[2][2] = -ey * kap * Jx[0][2];
+    Jx[2][3] = -ey * kap * Jx[0][3];
+    Jx[2][4] = -ey * kap * Jx[0][4];
+    Jx[2][5] = 1.0;
+}
+
+__device__ __forceinline__ uint32_t fr_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool GP>
+__global__ void __launch_bounds__(128) prepare_dense_kernel(const Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const double *gpsm = nullptr;
+    if (GP) {
+        // GP blob staged by TMA bulk copies exactly as in prepare.cu
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fr_smem_u32(&bar)), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fr_smem_u32(&bar)), "r"((uint32_t)P.gp.bytes) : "memory");
+            uint32_t off = 0;
+            while (off < (uint32_t)P.gp.bytes) {
+                const uint32_t n = min((uint32_t)P.gp.bytes - off, 65536u);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 fr_smem_u32(smem_raw + off)),
+                             "l"((const unsigned char *)P.gp.blob + off), "r"(n), "r"(fr_smem_u32(&bar))
+                             : "memory");
+                off += n;
+            }
+        }
+        gpsm = reinterpret_cast<const double *>(smem_raw);
+        asm volatile(
+            "{\n .reg .pred p;\n WAIT_%=:\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(fr_smem_u32(&bar)), "r"(0) : "memory");
+    }
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= P.B || P.lin_bad[i] == 2) return;
+    const double h = o.dt, Ts = o.dt;
+    double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+    double x[7];
+#pragma unroll
+    for (int c = 0; c < 7; c++) x[c] = AT(P.xb, k * 7 + c);
+    if (k == N) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = o.We[c] * (x[c] - AT(P.yref, N * 9 + c));
+        return;
+    }
+    double u[2], gpx[7];
+    u[0] = AT(P.ub, k * 2 + 0); u[1] = AT(P.ub, k * 2 + 1);
+    const double pk = AT(P.p, k), kap = AT(P.kappa, k);
+    const double trig = (GP && o.gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
+#pragma unroll
+    for (int c = 0; c < 7; c++) gpx[c] = (trig != 0.0) ? AT(P.gps, c) : 0.0;
+
+    // classic RK4 on [x | S], S = [S_x (7x7) | S_u (7x2)], S(0) = [I 0]
+    double K[7][9], acc[7][9], kx[7], ax[7];
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        kx[r] = 0.0; ax[r] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 9; c++) { K[r][c] = 0.0; acc[r][c] = 0.0; }
+    }
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {
+        const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
+        const double bs = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
+        const double ha = h * as;
+        double xs[7], f[7], Jx[7][7], Ju[7][2];
+#pragma unroll
+        for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
+        frenet_eval<GP>(o, gpsm, P.gp.stride_out, xs, u, pk, kap, gpx, trig, f, Jx, Ju);
+#pragma unroll
+        for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            double sv[7], kn[7];
+#pragma unroll
+            for (int r = 0; r < 7; r++) sv[r] = ha * K[r][c] + ((r == c) ? 1.0 : 0.0);
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+                double v = (c >= 7) ? Ju[r][c - 7] : 0.0;
+#pragma unroll
+                for (int l = 0; l < 7; l++) v = fma(Jx[r][l], sv[l], v);
+                kn[r] = v;
+            }
+#pragma unroll
+            for (int r = 0; r < 7; r++) { K[r][c] = kn[r]; acc[r][c] = fma(bs, kn[r], acc[r][c]); }
+        }
+    }
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+        const double xp = fma(h, ax[c], x[c]);
+        bad |= !isfinite(xp);
+        AT(lin, DL_b + c) = xp - AT(P.xb, (k + 1) * 7 + c);
+    }
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            const double v = h * acc[r][c] + ((r == c) ? 1.0 : 0.0);
+            bad |= !isfinite(v);
+            AT(lin, DL_A + r * 7 + c) = v;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const double v = h * acc[r][7 + c];
+            bad |= !isfinite(v);
+            AT(lin, DL_B + r * 2 + c) = v;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = Ts * o.W[c] * (x[c] - AT(P.yref, k * 9 + c));
+#pragma unroll
+    for (int c = 0; c < 2; c++) AT(lin, DL_r + c) = Ts * o.W[7 + c] * (u[c] - AT(P.yref, k * 9 + 7 + c));
+    if (bad) P.lin_bad[i] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------- dense IPM ---------
+__device__ __forceinline__ bool con_on(int k, int c) { return !((c == 2 || c == 5) && k == 0); }
+__device__ __forceinline__ constexpr int sy(int a, int b) { return (a >= b) ? (a * (a + 1) / 2 + b) : (b * (b + 1) / 2 + a); }
+
+// residuals of the current point: fills rgu, rgx, rgsl, rgsu, rb, rd, rm; returns the four norms and mu
+__device__ void dn_residuals(const Params &P, int i, double res[4], double &summ)
+{
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const double Ts = o.dt;
+    double ng = 0, nb = 0, nd = 0, nm = 0;
+    summ = 0;
+    for (int k = 0; k <= N; k++) {
+        const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+        double dx[7];
+#pragma unroll
+        for (int a = 0; a < 7; a++) dx[a] = AT(P.dx, k * 7 + a);
+        if (k < N) {
+            double du[2], pi[7], lam[NC], t[NC];
+            du[0] = AT(P.du, k * 2); du[1] = AT(P.du, k * 2 + 1);
+#pragma unroll
+            for (int a = 0; a < 7; a++) pi[a] = AT(P.pi, k * 7 + a);
+#pragma unroll
+            for (int c = 0; c < NC; c++) { lam[c] = AT(P.lam, k * NC + c); t[c] = AT(P.t, k * NC + c); }
+            double rd[NC];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                double g = Ts * o.W[7 + j] * du[j] + AT(lin, DL_r + j);
+#pragma unroll
+                for (int l = 0; l < 7; l++) g += AT(lin, DL_B + l * 2 + j) * pi[l];
+                g += -lam[j] + lam[3 + j];
+                const double sl = AT(P.sl, k * 2 + j), su = AT(P.su, k * 2 + j), ub = AT(P.ub, k * 2 + j);
+                const double gsl = Ts * o.zl[j] + Ts * o.Zl[j] * sl - lam[j] - lam[6 + j];
+                const double gsu = Ts * o.zu[j] + Ts * o.Zu[j] * su - lam[3 + j] - lam[8 + j];
+                AT(P.rgu, k * 2 + j) = g; AT(P.rgsl, k * 2 + j) = gsl; AT(P.rgsu, k * 2 + j) = gsu;
+                rd[j] = t[j] - (du[j] - (o.lbu[j] - ub) + sl);
+                rd[3 + j] = t[3 + j] - ((o.ubu[j] - ub) - du[j] + su);
+                rd[6 + j] = t[6 + j] - sl;
+                rd[8 + j] = t[8 + j] - su;
+                ng = nmaxd(ng, nmaxd(fabs(g), nmaxd(fabs(gsl), fabs(gsu))));
+            }
+            if (k >= 1) {
+                const double x6 = AT(P.xb, k * 7 + 6);
+                rd[2] = t[2] - (dx[6] - (o.lbx - x6));
+                rd[5] = t[5] - ((o.ubx - x6) - dx[6]);
+            } else { rd[2] = 0.0; rd[5] = 0.0; }
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+                double v = AT(lin, DL_b + r) - AT(P.dx, (k + 1) * 7 + r);
+#pragma unroll
+                for (int l = 0; l < 7; l++) v += AT(lin, DL_A + r * 7 + l) * dx[l];
+                v += AT(lin, DL_B + r * 2) * du[0];
+                v += AT(lin, DL_B + r * 2 + 1) * du[1];
+                AT(P.rb, k * 7 + r) = v;
+                nb = nmaxd(nb, fabs(v));
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                AT(P.rd, k * NC + c) = rd[c];
+                if (!con_on(k, c)) { AT(P.rm, k * NC + c) = 0.0; continue; }
+                const double rm = lam[c] * t[c];
+                AT(P.rm, k * NC + c) = rm;
+                nd = nmaxd(nd, fabs(rd[c]));
+                nm = nmaxd(nm, fabs(rm));
+                summ += rm;
+            }
+        }
+        if (k >= 1) {
+#pragma unroll
+            for (int a = 0; a < 7; a++) {
+                const double Qd = (k < N) ? Ts * o.W[a] : o.We[a];
+                double g = Qd * dx[a] + AT(lin, DL_q + a) - AT(P.pi, (k - 1) * 7 + a);
+                if (k < N) {
+#pragma unroll
+                    for (int l = 0; l < 7; l++) g += AT(lin, DL_A + l * 7 + a) * AT(P.pi, k * 7 + l);
+                    if (a == 6) g += -AT(P.lam, k * NC + 2) + AT(P.lam, k * NC + 5);
+                }
+                AT(P.rgx, k * 7 + a) = g;
+                ng = nmaxd(ng, fabs(g));
+            }
+        }
+    }
+    res[0] = ng; res[1] = nb; res[2] = nd; res[3] = nm;
+}
+
+// Riccati factorisation of the barrier-modified Hessian (matrix part): K, Luu (in Ginv), P (packed symmetric)
+__device__ void dn_factor(const Params &P, int i)
+{
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const double Ts = o.dt;
+    double Pn[28];
+#pragma unroll
+    for (int a = 0; a < 28; a++) Pn[a] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 7; a++) Pn[sy(a, a)] = o.We[a];
+#pragma unroll
+    for (int a = 0; a < 28; a++) AT(P.P, N * 28 + a) = Pn[a];
+    for (int k = N - 1; k >= 0; k--) {
+        const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+        double Rt[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const double Sl = AT(P.lam, k * NC + j) / AT(P.t, k * NC + j), Su = AT(P.lam, k * NC + 3 + j) / AT(P.t, k * NC + 3 + j);
+            const double Ssl = AT(P.lam, k * NC + 6 + j) / AT(P.t, k * NC + 6 + j), Ssu = AT(P.lam, k * NC + 8 + j) / AT(P.t, k * NC + 8 + j);
+            const double Dl = Ts * o.Zl[j] + Sl + Ssl, Du = Ts * o.Zu[j] + Su + Ssu;
+            Rt[j] = Ts * o.W[7 + j] + Sl * (1.0 - Sl / Dl) + Su * (1.0 - Su / Du);
+        }
+        const double Qt6 = Ts * o.W[6] + (k >= 1 ? AT(P.lam, k * NC + 2) / AT(P.t, k * NC + 2) + AT(P.lam, k * NC + 5) / AT(P.t, k * NC + 5) : 0.0);
+        double BA[7][9], PBA[7][9], G[45];
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            BA[r][0] = AT(lin, DL_B + r * 2); BA[r][1] = AT(lin, DL_B + r * 2 + 1);
+#pragma unroll
+            for (int c = 0; c < 7; c++) BA[r][2 + c] = AT(lin, DL_A + r * 7 + c);
+        }
+#pragma unroll
+        for (int r = 0; r < 7; r++)
+#pragma unroll
+            for (int c = 0; c < 9; c++) {
+                double v = 0.0;
+#pragma unroll
+                for (int l = 0; l < 7; l++) v += Pn[sy(r, l)] * BA[l][c];
+                PBA[r][c] = v;
+            }
+#pragma unroll
+        for (int a = 0; a < 9; a++)
+#pragma unroll
+            for (int c = 0; c <= a; c++) {
+                double v = 0.0;
+#pragma unroll
+                for (int l = 0; l < 7; l++) v += BA[l][a] * PBA[l][c];
+                G[sy(a, c)] = v;
+            }
+        G[sy(0, 0)] += Rt[0]; G[sy(1, 1)] += Rt[1];
+#pragma unroll
+        for (int a = 0; a < 7; a++) G[sy(2 + a, 2 + a)] += (a == 6) ? Qt6 : Ts * o.W[a];
+        const double l00 = sqrt(G[sy(0, 0)] + o.reg), l10 = G[sy(1, 0)] / l00, l11 = sqrt(G[sy(1, 1)] + o.reg - l10 * l10);
+        AT(P.Ginv, k * 3 + 0) = l00; AT(P.Ginv, k * 3 + 1) = l10; AT(P.Ginv, k * 3 + 2) = l11;
+        double K0[7], K1[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const double y0 = G[sy(2 + j, 0)] / l00, y1 = (G[sy(2 + j, 1)] - l10 * y0) / l11;
+            const double k1 = y1 / l11, k0 = (y0 - l10 * k1) / l00;
+            K0[j] = -k0; K1[j] = -k1;
+            AT(P.K, k * 14 + j) = -k0; AT(P.K, k * 14 + 7 + j) = -k1;
+        }
+#pragma unroll
+        for (int a = 0; a < 7; a++)
+#pragma unroll
+            for (int c = 0; c <= a; c++) {
+                // symmetrised Schur complement (the oracle averages the two triangles)
+                const double v1 = G[sy(2 + a, 2 + c)] + G[sy(2 + a, 0)] * K0[c] + G[sy(2 + a, 1)] * K1[c];
+                const double v2 = G[sy(2 + c, 2 + a)] + G[sy(2 + c, 0)] * K0[a] + G[sy(2 + c, 1)] * K1[a];
+                Pn[sy(a, c)] = (a == c) ? v1 : 0.5 * (v1 + v2);
+            }
+#pragma unroll
+        for (int a = 0; a < 28; a++) AT(P.P, k * 28 + a) = Pn[a];
+    }
+}
+
+// Newton step for the complementarity right-hand side in P.rm: ddu, ddx, dpi, dsl, dsu, dt, dlam; returns the
+// fraction-to-boundary step and the two sums of the Mehrotra centering estimate
+__device__ void dn_solve(const Params &P, int i, double &alpha, double &s1, double &s2)
+{
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const double Ts = o.dt;
+    double pv[7];
+#pragma unroll
+    for (int a = 0; a < 7; a++) { pv[a] = AT(P.rgx, N * 7 + a); AT(P.pv, N * 7 + a) = pv[a]; }
+    // backward vector recursion (stage barrier quantities recomputed, rt / qt6 not stored)
+    for (int k = N - 1; k >= 0; k--) {
+        const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+        double gl[NC], rt[2];
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+            gl[c] = con_on(k, c) ? (AT(P.rm, k * NC + c) - AT(P.lam, k * NC + c) * AT(P.rd, k * NC + c)) / AT(P.t, k * NC + c) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const double Sl = AT(P.lam, k * NC + j) / AT(P.t, k * NC + j), Su = AT(P.lam, k * NC + 3 + j) / AT(P.t, k * NC + 3 + j);
+            const double Ssl = AT(P.lam, k * NC + 6 + j) / AT(P.t, k * NC + 6 + j), Ssu = AT(P.lam, k * NC + 8 + j) / AT(P.t, k * NC + 8 + j);
+            const double Dl = Ts * o.Zl[j] + Sl + Ssl, Du = Ts * o.Zu[j] + Su + Ssu;
+            const double cl = AT(P.rgsl, k * 2 + j) + gl[j] + gl[6 + j], cu = AT(P.rgsu, k * 2 + j) + gl[3 + j] + gl[8 + j];
+            rt[j] = AT(P.rgu, k * 2 + j) + (gl[j] - Sl * cl / Dl) - (gl[3 + j] - Su * cu / Du);
+        }
+        const double qt6 = (k >= 1) ? AT(P.rgx, k * 7 + 6) + gl[2] - gl[5] : 0.0;
+        double Pn[28], hv[7], gu[2], gx[7];
+#pragma unroll
+        for (int a = 0; a < 28; a++) Pn[a] = AT(P.P, (k + 1) * 28 + a);
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            double v = pv[a];
+#pragma unroll
+            for (int l = 0; l < 7; l++) v += Pn[sy(a, l)] * AT(P.rb, k * 7 + l);
+            hv[a] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double v = rt[j];
+#pragma unroll
+            for (int l = 0; l < 7; l++) v += AT(lin, DL_B + l * 2 + j) * hv[l];
+            gu[j] = v;
+        }
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            double v = (k >= 1) ? ((a == 6) ? qt6 : AT(P.rgx, k * 7 + a)) : 0.0;
+#pragma unroll
+            for (int l = 0; l < 7; l++) v += AT(lin, DL_A + l * 7 + a) * hv[l];
+            gx[a] = v;
+        }
+        const double l00 = AT(P.Ginv, k * 3 + 0), l10 = AT(P.Ginv, k * 3 + 1), l11 = AT(P.Ginv, k * 3 + 2);
+        const double y0 = gu[0] / l00, y1 = (gu[1] - l10 * y0) / l11;
+        const double k1 = y1 / l11, k0 = (y0 - l10 * k1) / l00;
+        AT(P.kf, k * 2 + 0) = -k0; AT(P.kf, k * 2 + 1) = -k1;
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            pv[a] = gx[a] + AT(P.K, k * 14 + a) * gu[0] + AT(P.K, k * 14 + 7 + a) * gu[1];
+            AT(P.pv, k * 7 + a) = pv[a];
+        }
+    }
+    // forward roll-out + step recovery + ratio test
+    double ddx[7];
+#pragma unroll
+    for (int a = 0; a < 7; a++) { ddx[a] = 0.0; AT(P.ddx, a) = 0.0; }
+    alpha = 1.0; s1 = 0.0; s2 = 0.0;
+    for (int k = 0; k < N; k++) {
+        const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+        double ddu[2], nx[7];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double v = AT(P.kf, k * 2 + j);
+#pragma unroll
+            for (int l = 0; l < 7; l++) v += AT(P.K, k * 14 + j * 7 + l) * ddx[l];
+            ddu[j] = v;
+            AT(P.ddu, k * 2 + j) = v;
+        }
+        // slack / t / lambda steps of this stage (need ddu_k and ddx_k[6])
+        {
+            double gl[NC], dt[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+                gl[c] = con_on(k, c) ? (AT(P.rm, k * NC + c) - AT(P.lam, k * NC + c) * AT(P.rd, k * NC + c)) / AT(P.t, k * NC + c) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const double Sl = AT(P.lam, k * NC + j) / AT(P.t, k * NC + j), Su = AT(P.lam, k * NC + 3 + j) / AT(P.t, k * NC + 3 + j);
+                const double Ssl = AT(P.lam, k * NC + 6 + j) / AT(P.t, k * NC + 6 + j), Ssu = AT(P.lam, k * NC + 8 + j) / AT(P.t, k * NC + 8 + j);
+                const double Dl = Ts * o.Zl[j] + Sl + Ssl, Du = Ts * o.Zu[j] + Su + Ssu;
+                const double cl = AT(P.rgsl, k * 2 + j) + gl[j] + gl[6 + j], cu = AT(P.rgsu, k * 2 + j) + gl[3 + j] + gl[8 + j];
+                const double dsl = -(cl + Sl * ddu[j]) / Dl, dsu = -(cu - Su * ddu[j]) / Du;
+                AT(P.dsl, k * 2 + j) = dsl; AT(P.dsu, k * 2 + j) = dsu;
+                dt[j] = ddu[j] + dsl - AT(P.rd, k * NC + j);
+                dt[3 + j] = -ddu[j] + dsu - AT(P.rd, k * NC + 3 + j);
+                dt[6 + j] = dsl - AT(P.rd, k * NC + 6 + j);
+                dt[8 + j] = dsu - AT(P.rd, k * NC + 8 + j);
+            }
+            if (k >= 1) { dt[2] = ddx[6] - AT(P.rd, k * NC + 2); dt[5] = -ddx[6] - AT(P.rd, k * NC + 5); }
+            else { dt[2] = 0.0; dt[5] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const double lam = AT(P.lam, k * NC + c), t = AT(P.t, k * NC + c);
+                const double dl = con_on(k, c) ? -(AT(P.rm, k * NC + c) + lam * dt[c]) / t : 0.0;
+                AT(P.dt, k * NC + c) = dt[c]; AT(P.dlam, k * NC + c) = dl;
+                if (!con_on(k, c)) continue;
+                if (dl < 0 && -lam / dl < alpha) alpha = -lam / dl;
+                if (dt[c] < 0 && -t / dt[c] < alpha) alpha = -t / dt[c];
+                s1 += lam * dt[c] + t * dl;
+                s2 += dl * dt[c];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            double v = AT(P.rb, k * 7 + r);
+#pragma unroll
+            for (int l = 0; l < 7; l++) v += AT(lin, DL_A + r * 7 + l) * ddx[l];
+            v += AT(lin, DL_B + r * 2) * ddu[0];
+            v += AT(lin, DL_B + r * 2 + 1) * ddu[1];
+            nx[r] = v;
+        }
+#pragma unroll
+        for (int a = 0; a < 7; a++) { ddx[a] = nx[a]; AT(P.ddx, (k + 1) * 7 + a) = nx[a]; }
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            double v = AT(P.pv, (k + 1) * 7 + a);
+#pragma unroll
+            for (int l = 0; l < 7; l++) v += AT(P.P, (k + 1) * 28 + sy(a, l)) * ddx[l];
+            AT(P.dpi, k * 7 + a) = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) qp_dense_kernel(const Params P)
+{
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.B) return;
+    if (const int flag = P.lin_bad[i]) {
+        if (flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+        return;
+    }
+    // cold start (identical to qp_ipm.cu)
+#pragma unroll
+    for (int a = 0; a < 7; a++) AT(P.dx, a) = AT(P.x0, a) - AT(P.xb, a);
+    for (int k = 0; k < N; k++) {
+        for (int j = 0; j < 3; j++) {
+            if (j == 2 && k == 0) {
+                AT(P.t, 2) = 1.0; AT(P.t, 5) = 1.0; AT(P.lam, 2) = 0.0; AT(P.lam, 5) = 0.0;
+                continue;
+            }
+            const double cur = (j < 2) ? AT(P.ub, k * 2 + j) : AT(P.xb, k * 7 + 6);
+            const double lo = ((j < 2) ? o.lbu[j] : o.lbx) - cur, hi = ((j < 2) ? o.ubu[j] : o.ubx) - cur;
+            double v = 0.0;
+            if (v - lo < o.thr0) {
+                if (hi - v < o.thr0) v = 0.5 * (lo + hi);
+                else v = lo + o.thr0;
+            } else if (hi - v < o.thr0) v = hi - o.thr0;
+            if (j < 2) AT(P.du, k * 2 + j) = v; else AT(P.dx, k * 7 + 6) = v;
+            const double tl = fmax(o.thr0, v - lo), tu = fmax(o.thr0, hi - v);
+            AT(P.t, k * NC + j) = tl; AT(P.t, k * NC + 3 + j) = tu;
+            AT(P.lam, k * NC + j) = o.mu0 / tl; AT(P.lam, k * NC + 3 + j) = o.mu0 / tu;
+        }
+        for (int j = 0; j < 2; j++) {
+            AT(P.t, k * NC + 6 + j) = o.thr0; AT(P.t, k * NC + 8 + j) = o.thr0;
+            AT(P.lam, k * NC + 6 + j) = o.mu0 / o.thr0; AT(P.lam, k * NC + 8 + j) = o.mu0 / o.thr0;
+            AT(P.sl, k * 2 + j) = 0.0; AT(P.su, k * 2 + j) = 0.0;
+        }
+        for (int a = 0; a < 7; a++) AT(P.pi, k * 7 + a) = 0.0;
+        for (int a = 0; a < 6; a++) AT(P.dx, (k + 1) * 7 + a) = 0.0;
+        if (k + 1 == N) AT(P.dx, N * 7 + 6) = 0.0;
+    }
+    const double inv_nc = 1.0 / (double)(NC * N - 2);
+    int status = 1, iter = 0;
+    double res[4] = {0, 0, 0, 0};
+    for (iter = 0;; iter++) {
+        double summ;
+        dn_residuals(P, i, res, summ);
+        if (!(isfinite(res[0]) && isfinite(res[1]) && isfinite(res[2]) && isfinite(res[3]))) { status = 3; break; }
+        if (res[0] < o.tol_stat && res[1] < o.tol_eq && res[2] < o.tol_ineq && res[3] < o.tol_comp) { status = 0; break; }
+        if (iter >= o.iter_max) { status = 1; break; }
+        const double mu = summ * inv_nc;
+        double a_aff, s1, s2, alpha;
+        dn_factor(P, i);
+        dn_solve(P, i, a_aff, s1, s2);
+        const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
+        double sigma = mu_aff / mu;
+        sigma = sigma * sigma * sigma;
+        for (int k = 0; k < N; k++)
+            for (int c = 0; c < NC; c++)
+                if (con_on(k, c))
+                    AT(P.rm, k * NC + c) = AT(P.lam, k * NC + c) * AT(P.t, k * NC + c) + AT(P.dlam, k * NC + c) * AT(P.dt, k * NC + c) - sigma * mu;
+        dn_solve(P, i, alpha, s1, s2);
+        if (alpha < o.alpha_min) { status = 2; break; }
+        if (alpha < 1.0) alpha *= 0.995;
+        for (int k = 0; k < N; k++) {
+            for (int j = 0; j < 2; j++) {
+                AT(P.du, k * 2 + j) += alpha * AT(P.ddu, k * 2 + j);
+                AT(P.sl, k * 2 + j) += alpha * AT(P.dsl, k * 2 + j);
+                AT(P.su, k * 2 + j) += alpha * AT(P.dsu, k * 2 + j);
+            }
+            for (int a = 0; a < 7; a++) {
+                AT(P.dx, (k + 1) * 7 + a) += alpha * AT(P.ddx, (k + 1) * 7 + a);
+                AT(P.pi, k * 7 + a) += alpha * AT(P.dpi, k * 7 + a);
+            }
+            for (int c = 0; c < NC; c++) {
+                if (!con_on(k, c)) continue;
+                AT(P.lam, k * NC + c) = fmax(AT(P.lam, k * NC + c) + alpha * AT(P.dlam, k * NC + c), o.lam_min);
+                AT(P.t, k * NC + c) = fmax(AT(P.t, k * NC + c) + alpha * AT(P.dt, k * NC + c), o.t_min);
+            }
+        }
+    }
+    const int qps = (status == 0) ? 0 : ((status == 1) ? 2 : ((status == 2) ? 3 : 1));
+    P.qp_status[i] = qps;
+    P.qp_iter[i] = iter;
+    P.status[i] = (qps == 0 || qps == 2) ? 0 : 4;
+    AT(P.res_out, 0) = res[0]; AT(P.res_out, 1) = res[1]; AT(P.res_out, 2) = res[2]; AT(P.res_out, 3) = res[3];
+}
+
+void launch_prepare_dense(const Params &P, cudaStream_t s)
+{
+    dim3 grid((P.B + 127) / 128, P.o.N + 1);
+    if (P.o.gp_enabled) {
+        const size_t sm = (size_t)P.gp.bytes;
+        static size_t configured = 0;
+        if (sm > configured) {
+            cudaFuncSetAttribute(prepare_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            configured = sm;
+        }
+        prepare_dense_kernel<true><<<grid, 128, sm, s>>>(P);
+    } else {
+        prepare_dense_kernel<false><<<grid, 128, 0, s>>>(P);
+    }
+}
+void launch_qp_dense(const Params &P, cudaStream_t s) { qp_dense_kernel<<<(P.B + 63) / 64, 64, 0, s>>>(P); }

@@ -119,6 +119,13 @@ class BatchSolver:
         else:
             check(self.L.admpc_batch_set_p(self.h, _dp(_f64(p, (self.B, self.N)))), "set_p")
 
+    def set_kappa(self, kappa):
+        """Frenet variant (default_opts(model_variant=1)): path curvature at every shooting node, [B, N] or [B]."""
+        k = np.asarray(kappa, dtype=np.float64)
+        if k.size == self.B:
+            k = np.repeat(k.reshape(self.B, 1), self.N, axis=1)
+        check(self.L.admpc_batch_set_kappa(self.h, _dp(_f64(k, (self.B, self.N)))), "set_kappa")
+
     def set_gp_state(self, gp_state):
         check(self.L.admpc_batch_set_gp_state(self.h, None if gp_state is None else _dp(_f64(gp_state, (self.B, 7)))), "set_gp_state")
 

@@ -87,3 +87,21 @@ def make_gp(M=200, seed=20263, n_out=2, dz=4, sigma_f=0.5, sigma_n=0.01):
         alpha[j] = np.linalg.solve(L.T, np.linalg.solve(L, y - y_mean[j]))
     return dict(X=X, alpha=alpha, ell=ell, sigma_f=np.full(n_out, sigma_f), y_mean=y_mean,
                 feat=(3, 4, 5, 6)[:dz], rows=(4, 5)[:n_out])
+
+
+def make_batch_frenet(B, N, dt=0.05, seed=20270, p=1.0, perturb=1.0, radius=50.0, v_ref=8.0):
+    """Frenet-variant twin of make_batch (SURVEY 8a A2'): states [s, e_y, e_psi, v_x, v_y, r, delta] along a circular
+    path of the given radius (curvature 1/R at every node), reference = on the path at v_ref.
+    Returns the make_batch dict plus kappa[B, N]."""
+    rng = np.random.default_rng(seed)
+    s0 = rng.uniform(0.0, 2 * math.pi * radius, size=B)
+    ref = np.zeros((B, N + 1, 7))
+    ref[..., 0] = s0[:, None] + v_ref * dt * np.arange(N + 1)[None, :]
+    ref[..., 3] = v_ref
+    x0 = ref[:, 0, :] + perturb * rng.normal(size=(B, 7)) * X0_SIGMA
+    yref = np.zeros((B, N * 9 + 7))
+    yref[:, :N * 9].reshape(B, N, 9)[:, :, :7] = ref[:, :N, :]
+    yref[:, N * 9:] = ref[:, N, :]
+    pp = np.full((B, N), float(p))
+    kappa = np.full((B, N), 1.0 / radius) * (1.0 + 0.2 * rng.uniform(-1, 1, size=(B, 1)))
+    return dict(x0=x0, yref=yref, p=pp, x_init=ref.copy(), u_init=np.zeros((B, N, 2)), ref=ref, kappa=kappa)

@@ -52,7 +52,9 @@ typedef struct admpc_opts {
     int gp_enabled;        /* set by admpc_batch_set_gp */
     int gp_nout, gp_M, gp_dz;
     int gp_stage0_trigger; /* 1: stage 0 evaluates the GP at gp_state (quad_mpc/quad_3d_optimizer.py:295,548-552) */
-    int reserved0;
+    int model_variant;     /* 0: Cartesian-pose model ($A/ad_3d_optimizer.py:268-310, shipped); 1: Frenet-frame variant
+                              ($A/__pycache__/fren_ad_3d_optimizer.cpython-36.pyc; x = [s, e_y, e_psi, v_x, v_y, r, delta],
+                              path curvature per shooting node via admpc_batch_set_kappa) */
     int gp_feat[ADMPC_DZMAX];      /* feature indices into [x(7);u(2)] (B_z, model_fitting/gp.py:609-630); >= 2 */
     int gp_row[ADMPC_GPOUT_MAX];   /* state rows receiving the GP outputs (B_x, utils/utils.py:773-786); in {3,4,5} */
     double dt;
@@ -90,7 +92,8 @@ int sim_car_acados_set_opts(sim_car_solver_capsule *capsule, const admpc_opts *o
  * (acados_models/sim_car_acados_ocp.json:868-873).  solve() then iterates to convergence; get_stat "sqp_iter". */
 int sim_car_acados_set_nlp_solver(sim_car_solver_capsule *capsule, const char *type, int max_iter, const double *tol4);
 /* flat field access replacing ocp_nlp_{cost_model,constraints_model,out}_set / ocp_nlp_out_get / ocp_nlp_get.
- * set fields: "yref" (9, or 7 at stage N), "lbx"/"ubx" (stage 0: 7 = x0; stages 1..N-1: 1), "p" (1), "x" (7), "u" (2)
+ * set fields: "yref" (9, or 7 at stage N), "lbx"/"ubx" (stage 0: 7 = x0; stages 1..N-1: 1), "p" (1), "x" (7), "u" (2),
+ *             "kappa" (1; Frenet variant only: path curvature at the node)
  * get fields: "x" (7), "u" (2), "pi" (7), "lam" (10, stage 0: 22), "t" (same), "sl" (2), "su" (2)
  * stats: "sqp_iter"(int) "qp_iter"(int) "qp_stat"(int) "status"(int) "time_tot"(double, s) "kkt_norm_inf"(double) */
 int sim_car_acados_set(sim_car_solver_capsule *capsule, int stage, const char *field, const double *value, int n);
@@ -120,6 +123,11 @@ int admpc_batch_set_x0(admpc_batch *h, const double *x0 /*[B][7]*/);
 int admpc_batch_set_yref(admpc_batch *h, const double *yref /*[B][N*9+7]*/);
 int admpc_batch_set_p(admpc_batch *h, const double *p /*[B][N]*/);
 int admpc_batch_set_p_scalar(admpc_batch *h, const double *p /*[B]*/);      /* same switch on all stages (:449-450) */
+/* Frenet variant only (opts.model_variant == 1): path curvature kappa[B][N] at every shooting node (default 0; the
+ * reference evaluates a B-spline kappa(s) inside the model, fren_ad_3d_optimizer bytecode).  With kappa = 0 the variant
+ * coincides with the Cartesian model.  The variant runs dense, unstructured kernels (csrc/frenet.cu); full SQP mode,
+ * the device reference generator and the closed-loop plant are Cartesian-only (ADMPC_E_UNSUPPORTED). */
+int admpc_batch_set_kappa(admpc_batch *h, const double *kappa);
 int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state /*[B][7] or NULL = x0*/);
 /* iterate (initial guess / warm start).  reset zeroes it like $G/acados_solver_sim_car.c:819-852. */
 int admpc_batch_set_iterate(admpc_batch *h, const double *x /*[B][(N+1)*7]*/, const double *u /*[B][N*2]*/);

@@ -86,6 +86,9 @@ def lib():
         L.orc_qp_solve.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcLin), C.POINTER(OrcIterate), dp, C.POINTER(OrcQpSol), C.POINTER(OrcStats)]
         L.orc_rti_step.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, dp, dp, C.POINTER(OrcIterate), C.POINTER(OrcStats)]
         L.orc_rti_batch.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, dp, ip, ip, ip, C.c_int]
+        L.orc_set_kappa.argtypes = [C.c_double]
+        L.orc_rti_batch_frenet.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip,
+                                           ip, C.c_int]
         L.orc_sqp_batch.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, dp,
                                     ip, ip, dp, C.c_int]
         L.orc_load_ref_model.argtypes = [C.c_char_p]
@@ -149,8 +152,10 @@ class Gp:
         return o
 
 
-def model_jac(o, x, u, p, gp=None, gp_state=None, trigger=0.0):
+def model_jac(o, x, u, p, gp=None, gp_state=None, trigger=0.0, kappa=0.0):
+    """kappa: path curvature, used by the Frenet variant (o.model_backend == 2) only."""
     f, Jx, Ju = np.zeros(7), np.zeros((7, 7)), np.zeros((7, 2))
+    lib().orc_set_kappa(float(kappa))
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
     gs = None if gp_state is None else np.ascontiguousarray(gp_state, dtype=np.float64)
@@ -166,8 +171,9 @@ def gp_predict(o, gp, z):
     return mu, dmu
 
 
-def rk4_sens(o, x, u, p, gp=None, gp_state=None, trigger=0.0):
+def rk4_sens(o, x, u, p, gp=None, gp_state=None, trigger=0.0, kappa=0.0):
     xn, A, B = np.zeros(7), np.zeros((7, 7)), np.zeros((7, 2))
+    lib().orc_set_kappa(float(kappa))
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
     gs = None if gp_state is None else np.ascontiguousarray(gp_state, dtype=np.float64)
@@ -226,8 +232,9 @@ def rti_step(o, it, x0, yref, p, gp=None, gp_state=None):
     return dict(status=st.status, qp_status=st.qp_status, qp_iter=st.qp_iter, res=np.array(st.res[:]), step_inf=st.step_inf)
 
 
-def rti_batch(o, x0, yref, p, xit, uit, gp=None, gp_state=None, nthreads=0):
-    """x0[B,7] yref[B,N*9+7] p[B,N] xit[B,N+1,7] uit[B,N,2] -> dict(x,u,pi,status,qp_status,qp_iter); inputs not modified."""
+def rti_batch(o, x0, yref, p, xit, uit, gp=None, gp_state=None, nthreads=0, kappa=None):
+    """x0[B,7] yref[B,N*9+7] p[B,N] xit[B,N+1,7] uit[B,N,2] -> dict(x,u,pi,status,qp_status,qp_iter); inputs not modified.
+    kappa[B,N] (Frenet variant, o.model_backend == 2): path curvature at every shooting node."""
     B = x0.shape[0]
     N = o.N
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
@@ -238,8 +245,9 @@ def rti_batch(o, x0, yref, p, xit, uit, gp=None, gp_state=None, nthreads=0):
     pi = np.zeros((B, N, 7))
     gs = None if gp_state is None else np.ascontiguousarray(gp_state, dtype=np.float64)
     status, qps, qpi = (np.zeros(B, dtype=np.int32) for _ in range(3))
-    lib().orc_rti_batch(C.byref(o), C.byref(gp.c) if gp else None, B, _dp(x0), _dp(yref), _dp(p), _dp(gs), _dp(x), _dp(u),
-                        _dp(pi), _ip(status), _ip(qps), _ip(qpi), int(nthreads))
+    kap = None if kappa is None else np.ascontiguousarray(np.broadcast_to(np.asarray(kappa, dtype=np.float64).reshape(B, -1), (B, N)))
+    lib().orc_rti_batch_frenet(C.byref(o), C.byref(gp.c) if gp else None, B, _dp(x0), _dp(yref), _dp(p), _dp(kap), _dp(gs),
+                               _dp(x), _dp(u), _dp(pi), _ip(status), _ip(qps), _ip(qpi), int(nthreads))
     return dict(x=x, u=u, pi=pi, status=status, qp_status=qps, qp_iter=qpi)
 
 

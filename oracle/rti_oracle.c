@@ -108,6 +108,12 @@ void orc_gp_predict(const orc_opts *o, const orc_gp *gp, const double *z, double
 }
 
 /* ------------------------------------------------------------------------------------------ model ---------- */
+/* Frenet variant (model_backend == 2; SURVEY 8a A2': fren_ad_3d_optimizer, bytecode only): the curvature of the
+ * reference path at the stage is a per-stage model parameter, handed down through this thread-local slot by the
+ * preparation loop (the reference evaluates a B-spline kappa(s) inside the model). */
+static _Thread_local double tls_kappa = 0.0;
+void orc_set_kappa(double kappa) { tls_kappa = kappa; }
+
 void orc_model_jac(const orc_opts *o, const orc_gp *gp, const double *x, const double *u, double p,
                    const double *gp_state, double trigger, double *f, double *Jx, double *Ju)
 {
@@ -154,6 +160,25 @@ void orc_model_jac(const orc_opts *o, const orc_gp *gp, const double *x, const d
     JU(5, 0) = q * dl / L;  JU(5, 1) = q * vx / L;
     JU(6, 1) = 1.0;
 
+    if (o->model_backend == 2) {
+        /* rows 0..2 in curvilinear coordinates x = [s, e_y, e_psi, ...] (A2'; literal form of the bytecode, including
+         * the e_y*kappa factor in the heading-error rate):
+         *   s'     = (vx cos e_psi - vy sin e_psi) / (1 - e_y kappa)
+         *   e_y'   =  vx sin e_psi + vy cos e_psi
+         *   e_psi' =  r - e_y kappa s'                                                             */
+        const double kap = tls_kappa, ey = x[1];
+        const double vt = vx * cp - vy * sp, vn = vx * sp + vy * cp, den = 1.0 - ey * kap;
+        const double sd0 = vt / den;
+        f[0] = sd0; f[1] = vn; f[2] = r - ey * kap * sd0;
+        for (int j = 0; j < 7; j++) { JX(0, j) = 0.0; JX(1, j) = 0.0; JX(2, j) = 0.0; }
+        JX(0, 1) = sd0 * kap / den; JX(0, 2) = -vn / den; JX(0, 3) = cp / den; JX(0, 4) = -sp / den;
+        JX(1, 2) = vt; JX(1, 3) = sp; JX(1, 4) = cp;
+        JX(2, 1) = -kap * sd0 - ey * kap * JX(0, 1);
+        JX(2, 2) = -ey * kap * JX(0, 2);
+        JX(2, 3) = -ey * kap * JX(0, 3);
+        JX(2, 4) = -ey * kap * JX(0, 4);
+        JX(2, 5) = 1.0;
+    }
     if (o->gp_enabled && gp) {
         /* gp_x = gp_state*trigger + x*(1-trigger)   quad_3d_optimizer.py:295 ; z = B_z [x;u]  gp.py:609-630 */
         double z[ORC_DZMAX], mu[ORC_GPOUT_MAX], dmu[ORC_GPOUT_MAX * ORC_DZMAX];
@@ -252,8 +277,20 @@ int orc_rk4_sens(const orc_opts *o, const orc_gp *gp, const double *x, const dou
 }
 
 /* ------------------------------------------------------------------------------------------ prepare -------- */
+static int prepare_impl(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, const double *yref,
+                        const double *p, const double *kappa, const double *gp_state, orc_lin *lin);
 int orc_prepare(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, const double *yref,
                 const double *p, const double *gp_state, orc_lin *lin)
+{
+    return prepare_impl(o, gp, it, yref, p, 0, gp_state, lin);
+}
+int orc_prepare_frenet(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, const double *yref,
+                       const double *p, const double *kappa, const double *gp_state, orc_lin *lin)
+{
+    return prepare_impl(o, gp, it, yref, p, kappa, gp_state, lin);
+}
+static int prepare_impl(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, const double *yref,
+                        const double *p, const double *kappa, const double *gp_state, orc_lin *lin)
 {
     const int N = o->N;
     const double Ts = o->dt;
@@ -261,6 +298,7 @@ int orc_prepare(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, cons
     for (int k = 0; k < N; k++) {
         const double *xk = it->x + k * 7, *uk = it->u + k * 2;
         double xn[7];
+        tls_kappa = kappa ? kappa[k] : 0.0;
         double trig = (o->gp_enabled && o->gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
         bad |= orc_rk4_sens(o, gp, xk, uk, p[k], gp_state, trig, xn, lin->A + k * 49, lin->B + k * 14);
         for (int i = 0; i < 7; i++) lin->b[k * 7 + i] = xn[i] - it->x[(k + 1) * 7 + i];
@@ -615,8 +653,20 @@ int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, c
 }
 
 /* ------------------------------------------------------------------------------------------ RTI step ------- */
+static int rti_step_impl(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, orc_iterate *it, orc_stats *st);
 int orc_rti_step(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref,
                  const double *p, const double *gp_state, orc_iterate *it, orc_stats *st)
+{
+    return rti_step_impl(o, gp, x0, yref, p, 0, gp_state, it, st);
+}
+int orc_rti_step_frenet(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref,
+                        const double *p, const double *kappa, const double *gp_state, orc_iterate *it, orc_stats *st)
+{
+    return rti_step_impl(o, gp, x0, yref, p, kappa, gp_state, it, st);
+}
+static int rti_step_impl(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, orc_iterate *it, orc_stats *st)
 {
     const int N = o->N;
     orc_lin *lin = (orc_lin *)malloc(sizeof(orc_lin));
@@ -625,7 +675,7 @@ int orc_rti_step(const orc_opts *o, const orc_gp *gp, const double *x0, const do
     if (!st) st = &local;
     memset(st, 0, sizeof(*st));
     const double *gps = gp_state ? gp_state : x0;          /* quad_3d_optimizer.py:549 */
-    int bad = orc_prepare(o, gp, it, yref, p, gps, lin);
+    int bad = prepare_impl(o, gp, it, yref, p, kappa, gps, lin);
     if (bad) { st->status = 1; free(lin); free(sol); return 1; }     /* ACADOS_FAILURE: NaN in linearisation */
     orc_qp_solve(o, lin, it, x0, sol, st);
     /* RTI tolerates QP maxiter; anything else is ACADOS_QP_FAILURE (4)  [EXT] */
@@ -739,9 +789,19 @@ int orc_sqp_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, 
     return 0;
 }
 
+int orc_rti_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, double *xit, double *uit,
+                         double *piout, int *status, int *qp_status, int *qp_iter, int nthreads);
 int orc_rti_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
                   const double *p, const double *gp_state, double *xit, double *uit, double *piout,
                   int *status, int *qp_status, int *qp_iter, int nthreads)
+{
+    return orc_rti_batch_frenet(o, gp, B, x0, yref, p, 0, gp_state, xit, uit, piout, status, qp_status, qp_iter, nthreads);
+}
+/* kappa[B][N]: path curvature at every shooting node (Frenet variant), or NULL */
+int orc_rti_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, double *xit, double *uit,
+                         double *piout, int *status, int *qp_status, int *qp_iter, int nthreads)
 {
     const int N = o->N;
     const size_t ny = (size_t)N * 9 + 7;
@@ -757,8 +817,8 @@ int orc_rti_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, 
             memcpy(it->x, xit + (size_t)b * (N + 1) * 7, sizeof(double) * (N + 1) * 7);
             memcpy(it->u, uit + (size_t)b * N * 2, sizeof(double) * N * 2);
             orc_stats st;
-            orc_rti_step(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N,
-                         gp_state ? gp_state + (size_t)b * 7 : 0, it, &st);
+            rti_step_impl(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N, kappa ? kappa + (size_t)b * N : 0,
+                          gp_state ? gp_state + (size_t)b * 7 : 0, it, &st);
             memcpy(xit + (size_t)b * (N + 1) * 7, it->x, sizeof(double) * (N + 1) * 7);
             memcpy(uit + (size_t)b * N * 2, it->u, sizeof(double) * N * 2);
             if (piout) memcpy(piout + (size_t)b * N * 7, it->pi, sizeof(double) * N * 7);

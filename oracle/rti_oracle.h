@@ -38,7 +38,8 @@ typedef struct orc_opts {
     int gp_M;             /* training points per output */
     int gp_dz;            /* feature dimension (<= ORC_DZMAX) */
     int gp_stage0_trigger;/* 1: stage 0 evaluates the GP at gp_state (quad_3d_optimizer.py:295,548-552) */
-    int model_backend;    /* 0: analytic restatement, 1: reference CasADi C via oracle/_ref (nominal only) */
+    int model_backend;    /* 0: analytic restatement, 1: reference CasADi C via oracle/_ref (nominal only),
+                             2: Frenet variant (SURVEY 8a A2'), curvature per shooting node via the *_frenet entry points */
     int gp_feat[ORC_DZMAX];      /* indices into [x(7); u(2)] selected by B_z   gp.py:609-630 */
     int gp_row[ORC_GPOUT_MAX];   /* state row each GP output is added to (B_x)  utils.py:773-786 */
     double dt;            /* interval length = cost scaling Ts        acados_solver_sim_car.c:362-366 */
@@ -133,6 +134,16 @@ int orc_sqp_solve(const orc_opts *o, const orc_gp *gp, const double *x0, const d
 int orc_sqp_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
                   const double *p, const double *gp_state, double *xit, double *uit, int max_iter, const double *tol,
                   int *status, int *sqp_iter, double *res, int nthreads);
+
+/* Frenet variant (model_backend = 2): kappa[N] per instance = path curvature at every shooting node */
+void orc_set_kappa(double kappa);      /* for direct orc_model_jac / orc_rk4_sens calls (thread-local) */
+int orc_prepare_frenet(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, const double *yref,
+                       const double *p, const double *kappa, const double *gp_state, orc_lin *lin);
+int orc_rti_step_frenet(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref,
+                        const double *p, const double *kappa, const double *gp_state, orc_iterate *it, orc_stats *st);
+int orc_rti_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, double *xit, double *uit,
+                         double *piout, int *status, int *qp_status, int *qp_iter, int nthreads);
 
 int orc_load_ref_model(const char *path); /* dlopen oracle/_ref/libsim_car_ref.so; 0 on success */
 

@@ -1,0 +1,106 @@
+"""GPU parity of the Frenet-frame model variant (SURVEY 8a A2') against the oracle's Frenet restatement, and of the
+dense kernels against the structured Cartesian kernels at zero curvature (where both models coincide)."""
+import numpy as np
+import pytest
+
+from ad_mpc_b200 import BatchSolver, default_opts, workload as wl
+from oracle import oracle as orc
+from util_parity import mirror_opts, mixed_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _step(s, batch, kappa=None, gp_state=None):
+    s.set_iterate(batch["x_init"], batch["u_init"])
+    s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"])
+    if kappa is not None:
+        s.set_kappa(kappa)
+    if gp_state is not None:
+        s.set_gp_state(gp_state)
+    s.solve()
+    st, qs, qi = s.get_status()
+    return dict(u=s.get_u(), x=s.get_x(), pi=s.get_pi(), status=st, qp_status=qs, qp_iter=qi)
+
+
+@pytest.mark.parametrize("B,N,p", [(1, 20, 1.0), (70, 20, 1.0), (33, 40, 0.3)])
+def test_frenet_rti_step_parity(B, N, p):
+    batch = wl.make_batch_frenet(B, N, seed=300 + B, p=p, perturb=2.0)
+    opts = default_opts(N, model_variant=1)
+    s = BatchSolver(B, opts)
+    g = _step(s, batch, kappa=batch["kappa"])
+    r = orc.rti_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=batch["kappa"])
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_status"], r["qp_status"])
+    assert np.array_equal(g["qp_iter"], r["qp_iter"])
+    assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL
+    assert mixed_err(g["pi"], r["pi"]) <= 1e-6
+    # second (warm) step from the updated iterate
+    s.solve()
+    r2 = orc.rti_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], r["x"], r["u"], kappa=batch["kappa"])
+    assert mixed_err(s.get_u(), r2["u"]) <= TOL
+    s.close()
+
+
+def test_frenet_at_zero_curvature_equals_cartesian_kernels():
+    """kappa = 0: the dense Frenet kernels must reproduce the structured Cartesian kernels (independent code paths)."""
+    B, N = 96, 20
+    batch = wl.make_batch(B, N, seed=310, p=0.6, perturb=3.0)
+    sc = BatchSolver(B, default_opts(N))
+    gc = _step(sc, batch)
+    sf = BatchSolver(B, default_opts(N, model_variant=1))
+    gf = _step(sf, batch, kappa=np.zeros((B, N)))
+    assert np.array_equal(gc["status"], gf["status"]) and np.array_equal(gc["qp_iter"], gf["qp_iter"])
+    assert mixed_err(gf["u"], gc["u"]) <= TOL and mixed_err(gf["x"], gc["x"]) <= TOL
+    sc.close(); sf.close()
+
+
+def test_frenet_with_gp_and_nondefault_weights():
+    """GP residual on v_y / yaw rate in the Frenet variant + the variant's own weights (q = [0,10,10,10,10,1,0.1],
+    r = [10,10], W_e = 0.01 Q: fren_ad_3d_optimizer defaults, SURVEY 8a A2')."""
+    B, N = 40, 20
+    batch = wl.make_batch_frenet(B, N, seed=320, p=1.0, perturb=1.5)
+    q = [0.0, 10.0, 10.0, 10.0, 10.0, 1.0, 0.1]
+    opts = default_opts(N, model_variant=1, W=q + [10.0, 10.0], We=[0.01 * v for v in q])
+    model = wl.make_gp(M=50, seed=7)
+    s = BatchSolver(B, opts)
+    s.set_gp(model)
+    g = _step(s, batch, kappa=batch["kappa"], gp_state=batch["x0"])
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    r = orc.rti_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=gp, gp_state=batch["x0"],
+                      kappa=batch["kappa"])
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_iter"], r["qp_iter"])
+    assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL
+    s.close()
+
+
+def test_frenet_unsupported_calls_fail_loudly():
+    from ad_mpc_b200 import _lib
+    s = BatchSolver(4, default_opts(20, model_variant=1))
+    with pytest.raises(_lib.AdmpcError):
+        s.solve_sqp()
+    sc = BatchSolver(4, default_opts(20))
+    with pytest.raises(_lib.AdmpcError):
+        sc.set_kappa(np.zeros((4, 20)))
+    s.close(); sc.close()
+
+
+def test_frenet_through_the_acados_shim():
+    from ad_mpc_b200 import AcadosOcpSolverB200
+    N = 20
+    b = wl.make_batch_frenet(1, N, seed=330, p=1.0, perturb=2.0)
+    opts = default_opts(N, model_variant=1)
+    cap = AcadosOcpSolverB200(opts)
+    for j in range(N):
+        cap.set(j, "yref", b["yref"][0][j * 9:(j + 1) * 9])
+        cap.set(j, "p", b["p"][0][j])
+        cap.set(j, "kappa", b["kappa"][0][j])
+    cap.set(N, "yref", b["yref"][0][N * 9:])
+    for j in range(N + 1):
+        cap.set(j, "x", b["x_init"][0, j])
+    cap.set(0, "lbx", b["x0"][0]); cap.set(0, "ubx", b["x0"][0])
+    assert cap.solve() == 0
+    r = orc.rti_batch(mirror_opts(opts), b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"], kappa=b["kappa"])
+    u = np.stack([cap.get(j, "u") for j in range(N)])
+    assert mixed_err(u, r["u"][0]) <= TOL

@@ -181,3 +181,37 @@ def test_sqp_mode_oracle_properties(golden_dir):
     rg = orc.sqp_batch(o40, g["x"][0][None], yref[None], np.zeros((1, 40)), g["x"][None], g["u"][None], tol=(1e-5,) * 4)
     assert rg["status"][0] == 0 and rg["sqp_iter"][0] <= 1
     assert np.abs(rg["x"][0] - g["x"]).max() < 5e-6 and np.abs(rg["u"][0] - g["u"]).max() < 5e-6
+
+
+def test_frenet_variant_oracle_consistency():
+    """Frenet variant (SURVEY 8a A2', bytecode-only in the reference => no fixture): the analytic Jacobian matches central
+    differences, and with zero curvature the variant IS the Cartesian model -- model, RK4 sensitivities and a whole RTI
+    step reproduce the (reference-pinned) Cartesian oracle bit for bit."""
+    from ad_mpc_b200 import workload as wl
+    o, of = orc.default_opts(20), orc.default_opts(20, model_backend=2)
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        x = np.array([rng.uniform(0, 50), rng.uniform(-1.5, 1.5), rng.uniform(-0.5, 0.5), rng.uniform(3, 14),
+                      rng.uniform(-1, 1), rng.uniform(-0.6, 0.6), rng.uniform(-0.4, 0.4)])
+        u, p, kap = rng.uniform(-2, 2, 2), rng.uniform(0, 1), rng.uniform(-0.1, 0.1)
+        f, Jx, Ju = orc.model_jac(of, x, u, p, kappa=kap)
+        h = 1e-6
+        for j in range(7):
+            xp, xm = x.copy(), x.copy()
+            xp[j] += h; xm[j] -= h
+            fd = (orc.model_jac(of, xp, u, p, kappa=kap)[0] - orc.model_jac(of, xm, u, p, kappa=kap)[0]) / (2 * h)
+            assert np.abs(fd - Jx[:, j]).max() <= 1e-7 * max(1.0, np.abs(Jx[:, j]).max())
+        f0, Jx0, Ju0 = orc.model_jac(of, x, u, p, kappa=0.0)
+        fc, Jxc, Juc = orc.model_jac(o, x, u, p)
+        assert np.array_equal(f0, fc) and np.array_equal(Jx0, Jxc) and np.array_equal(Ju0, Juc)
+        # curvature enters rows 0 and 2 only
+        assert np.array_equal(f[[1, 3, 4, 5, 6]], fc[[1, 3, 4, 5, 6]]) and f[0] != fc[0]
+    b = wl.make_batch(8, 20, seed=3, p=1.0)
+    r0 = orc.rti_batch(o, b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"])
+    r1 = orc.rti_batch(of, b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"], kappa=np.zeros((8, 20)))
+    assert np.array_equal(r0["u"], r1["u"]) and np.array_equal(r0["x"], r1["x"]) and np.array_equal(r0["qp_iter"], r1["qp_iter"])
+    # curved path: the RTI step converges on the Frenet workload and tracks the path (e_y, e_psi shrink)
+    bf = wl.make_batch_frenet(8, 20, seed=4, p=1.0, perturb=2.0)
+    rf = orc.rti_batch(of, bf["x0"], bf["yref"], bf["p"], bf["x_init"], bf["u_init"], kappa=bf["kappa"])
+    assert (rf["status"] == 0).all() and (rf["qp_status"] == 0).all()
+    assert np.abs(rf["x"][:, -1, 1]).mean() < np.abs(bf["x0"][:, 1]).mean()

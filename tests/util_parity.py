@@ -18,6 +18,8 @@ def mirror_opts(gpu_opts):
                 getattr(o, f)[i] = v[i]
         else:
             setattr(o, f, v)
+    if getattr(gpu_opts, "model_variant", 0) == 1:
+        o.model_backend = 2                      # Frenet variant of the oracle
     return o
 
 
