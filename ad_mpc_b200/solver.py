@@ -273,7 +273,7 @@ class PipelinedSolver:
     """B instances split into `chunks` BatchSolver handles (one CUDA stream each): the H2D copy of chunk c+1, the solve
     of chunk c and the D2H copy of chunk c-1 overlap.  Host buffers should be pinned (PinnedArray) for real overlap."""
 
-    def __init__(self, B, opts=None, device=0, N=None, chunks=4):
+    def __init__(self, B, opts=None, device=0, N=None, chunks=8):
         from .shard import shard_range
         self.B = int(B)
         self.ranges = [shard_range(self.B, c, chunks) for c in range(chunks) if shard_range(self.B, c, chunks)[1] > shard_range(self.B, c, chunks)[0]]

@@ -261,10 +261,10 @@ def run_ours(args):
     value = B * world / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with pinned HOST buffers ("e2e") --------------------------------
-    # PipelinedSolver = the public batched call: 4 chunks on 4 streams so that H2D / solve / D2H overlap.
+    # PipelinedSolver = the public batched call: 8 chunks on 8 streams so that H2D / solve / D2H overlap.
     from ad_mpc_b200 import PipelinedSolver
     s.set_profiling(False)
-    ps = PipelinedSolver(B, opts, device=local, chunks=4)
+    ps = PipelinedSolver(B, opts, device=local, chunks=8)
     ps.set_gp(model)
     pin = {k: PinnedArray(v.shape) for k, v in (("x0", batch["x0"]), ("yref", batch["yref"]))}
     pin["x0"].array[:] = batch["x0"]; pin["yref"].array[:] = batch["yref"]
