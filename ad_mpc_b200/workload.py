@@ -79,7 +79,7 @@ def make_gp(M=200, seed=20263, n_out=2, dz=4, sigma_f=0.5, sigma_n=0.01):
     for j in range(n_out):
         X[j] = rng.uniform(lo, hi, size=(M, dz))
         ell[j] = rng.uniform(0.5, 2.0, size=dz) * 0.5 * (hi - lo)
-        vx, vy, dl = X[j][:, 0], X[j][:, 1], X[j][:, min(3, dz - 1)]
+        vx, vy, dl = X[j][:, 0], X[j][:, min(1, dz - 1)], X[j][:, min(3, dz - 1)]
         y = (0.3 * np.sin(vy) + 0.1 * dl * vx / 10.0) * (1.0 if j == 0 else 0.5) + rng.normal(size=M) * sigma_n
         y_mean[j] = y.mean()
         K = _sqexp(X[j], X[j], ell[j], sigma_f) + sigma_n ** 2 * np.eye(M)

@@ -86,6 +86,46 @@ def test_prepare_parity_gp(p, trigger):
     s.close()
 
 
+@pytest.mark.parametrize("dz,n_out,M,feat,rows", [
+    (1, 1, 37, (4,), (4,)),            # the reference's own 1-D models (README: --x 7 --y 7 style), odd M
+    (2, 2, 1, (3, 8), (5, 3)),         # an input feature (u1), outputs on yaw rate and v_x, a single training point
+    (3, 1, 130, (6, 7, 2), (5,)),      # steering angle, u0 and the heading as features
+    (7, 2, 33, (2, 3, 4, 5, 6, 7, 8), (3, 4)),   # every admissible feature
+])
+def test_prepare_parity_gp_shapes(dz, n_out, M, feat, rows):
+    """GP configurations off the benchmark's d_z = 4 fast path: generic feature loop, input features, 1..2 outputs."""
+    B, N = 40, 20
+    batch = wl.make_batch(B, N, seed=14, p=0.7)
+    rng = np.random.default_rng(8)
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([1.0, 0.2])
+    model = wl.make_gp(M=M, seed=4, n_out=n_out, dz=min(dz, 4))
+    if dz > 4:                                   # widen the synthetic model to dz features
+        model["X"] = np.concatenate([model["X"], rng.uniform(-1, 1, size=(n_out, M, dz - 4))], axis=2)
+        model["ell"] = np.concatenate([model["ell"], rng.uniform(1.0, 3.0, size=(n_out, dz - 4))], axis=1)
+    model["feat"], model["rows"] = feat, rows
+    opts = default_opts(N)
+    s = BatchSolver(B, opts)
+    s.set_gp(model, stage0_trigger=1)
+    gps = batch["x0"] + 0.02
+    s.set_iterate(batch["x_init"], batch["u_init"]); s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"])
+    s.set_gp_state(gps)
+    s.solve()
+    lin = s.get_lin()
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=feat, rows=rows, stage0_trigger=1)
+    for i in range(0, B, 7):
+        it = orc.make_iterate(o, batch["x_init"][i], batch["u_init"][i])
+        ref = orc.prepare(o, it, batch["yref"][i], batch["p"][i], gp=gp, gp_state=gps[i])
+        for key in ("A", "B", "b", "q", "r"):
+            assert mixed_err(lin[key][i], ref[key]) <= 1e-10, key
+    # and the whole step
+    g = dict(u=s.get_u(), x=s.get_x())
+    r = orc.rti_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=gp, gp_state=gps)
+    assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL
+    s.close()
+
+
 @pytest.mark.parametrize("p", [0.0, 1.0])
 @pytest.mark.parametrize("B,N", [(1, 20), (33, 20), (512, 20), (100, 40)])
 def test_rti_step_parity_nominal(p, B, N):
