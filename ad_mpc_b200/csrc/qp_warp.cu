@@ -354,10 +354,12 @@ __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, doubl
             if (l < 7) st[R_GX + l] = nb;
         }
         const double *mr = st + R_M + l6;        // row l of M: element (l, c) at c*6
-        double d = mr[0] * du0, d2 = mr[6] * du1;
-        d = fma(mr[12], x23.x, d); d2 = fma(mr[18], x23.y, d2);
+        // state terms first: they do not wait for the du dot products (shorter dependent chain per stage)
+        double d = mr[12] * x23.x, d2 = mr[18] * x23.y;
         d = fma(mr[24], x45.x, d); d2 = fma(mr[30], x45.y, d2);
-        d = fma(mr[36], x6, d) + d2;
+        d = fma(mr[36], x6, d);
+        d = fma(mr[0], du0, d); d2 = fma(mr[6], du1, d2);
+        d += d2;
         double v = st[R_RB + l7] + fma(cself, dxr, cdt * du1);
         v = fma(mB, d, v);
         dxr = (l < 7) ? v : 0.0;
