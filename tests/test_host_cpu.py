@@ -258,3 +258,45 @@ def test_c_example_compiles_against_the_header():
                     "-o", exe, "-L", os.path.join(ROOT, "ad_mpc_b200"), "-ladmpc_b200",
                     "-Wl,-rpath," + os.path.join(ROOT, "ad_mpc_b200"), "-lm"], check=True)
     assert os.path.exists(exe)
+
+
+def test_optimizer_marshalling_matches_the_reference_loops():
+    """AD3DOptimizerB200.marshal (vectorised) against the reference's per-node Python of run_optimization
+    (ad_3d_optimizer.py:417-443): heading unwrap relative to x0.psi on every node, in-place edit of the terminal
+    target, vel_switch blend."""
+    import math
+    from ad_mpc_b200.optimizer import AD3DOptimizerB200
+    rng = np.random.default_rng(11)
+    B, N = 64, 20
+    x_init = rng.normal(size=(B, 7))
+    x_init[:, 2] = rng.uniform(-math.pi, math.pi, size=B)
+    x_init[:8, 2] = 0.0                                            # psi == 0: neither branch
+    x_init[:, 3] = rng.uniform(0, 14, size=B)
+    target = rng.normal(size=(B, N + 1, 7))
+    target[..., 2] = rng.uniform(-math.pi, math.pi, size=(B, N + 1))
+    u_target = rng.normal(size=(B, N + 1, 2))
+    t_in = target.copy()
+    yref, vs = AD3DOptimizerB200.marshal(x_init, target, u_target, N, 3.0, 12.0)
+    for b in range(B):
+        stacked = t_in[b].copy()
+        for j in range(N):
+            ref = np.concatenate((stacked[j, :], u_target[b, j, :]))
+            if x_init[b, 2] < 0:
+                if x_init[b, 2] + math.pi < ref[2]:
+                    ref[2] = ref[2] - 2 * math.pi
+            elif x_init[b, 2] > 0:
+                if x_init[b, 2] - math.pi > ref[2]:
+                    ref[2] = ref[2] + 2 * math.pi
+            assert np.array_equal(yref[b, j * 9:(j + 1) * 9], ref)
+        if x_init[b, 2] < 0:
+            if x_init[b, 2] + math.pi < stacked[N, 2]:
+                stacked[N, 2] = stacked[N, 2] - 2 * math.pi
+        elif x_init[b, 2] > 0:
+            if x_init[b, 2] - math.pi > stacked[N, 2]:
+                stacked[N, 2] = stacked[N, 2] + 2 * math.pi
+        assert np.array_equal(yref[b, N * 9:], stacked[N, :]) and np.array_equal(target[b], stacked)
+        assert vs[b] == min(max((x_init[b, 3] - 3.0) / (12.0 - 3.0), 0.0), 1.0)
+    # backup control slice arithmetic of :472
+    prev = np.arange(40.0)
+    w = AD3DOptimizerB200._backup(prev)
+    assert w.shape == (40,) and np.array_equal(w[:39], np.concatenate((prev[2:-1], prev[-3:-1])))
