@@ -35,27 +35,33 @@ __global__ void gpfit_build_kernel(const double *__restrict__ Xs, int M, int Mp,
     A[(size_t)i * Mp + j] = v;
 }
 
-// Cholesky of the diagonal tile (j, j): 32x32 threads, tile in shared memory
-__global__ void __launch_bounds__(TB * TB) gpfit_potrf32(double *A, int Mp, int jb, int *fail)
+// Cholesky of the diagonal tile (j, j): ONE WARP, lane r owns row r of the tile in registers; the pivot column
+// travels by shuffles (no shared memory, no block barriers: the 32 column steps are the serial part of every block
+// step of the factorisation, so their latency is what matters).
+__global__ void __launch_bounds__(32) gpfit_potrf32(double *A, int Mp, int jb, int *fail)
 {
-    __shared__ double T[TB][TB + 1];
-    const int r = threadIdx.y, c = threadIdx.x;
+    const int r = threadIdx.x;
     double *Ajj = A + (size_t)(jb * TB) * Mp + jb * TB;
-    T[r][c] = Ajj[(size_t)r * Mp + c];
-    __syncthreads();
+    double row[TB];
+#pragma unroll
+    for (int c = 0; c < TB; c++) row[c] = Ajj[(size_t)r * Mp + c];
+    bool bad = false;
+#pragma unroll
     for (int k = 0; k < TB; k++) {
-        if (r == k && c == k) {
-            const double d = T[k][k];
-            if (!(d > 0.0)) *fail = 1;           // not positive definite (np.linalg.LinAlgError in the reference)
-            T[k][k] = sqrt(d);
+        const double piv = __shfl_sync(0xffffffffu, row[k], k);
+        bad |= !(piv > 0.0);                       // not positive definite (np.linalg.LinAlgError in the reference)
+        const double d = sqrt(piv);
+        const double lrk = (r == k) ? d : row[k] / d;          // column k of L (rows >= k)
+        row[k] = lrk;
+#pragma unroll
+        for (int c = k + 1; c < TB; c++) {
+            const double lck = __shfl_sync(0xffffffffu, lrk, c);
+            if (r >= c) row[c] = fma(-lrk, lck, row[c]);
         }
-        __syncthreads();
-        if (c == k && r > k) T[r][k] /= T[k][k];
-        __syncthreads();
-        if (c > k && r >= c) T[r][c] -= T[r][k] * T[c][k];
-        __syncthreads();
     }
-    Ajj[(size_t)r * Mp + c] = (c <= r) ? T[r][c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < TB; c++) Ajj[(size_t)r * Mp + c] = (c <= r) ? row[c] : 0.0;
+    if (bad && r == 0) *fail = 1;
 }
 
 // X = A_ij L_jj^-T for the tiles below the diagonal: one thread per row of the tile (32 rows), 4 tiles per CTA
@@ -215,7 +221,7 @@ extern "C" int admpc_gp_fit(int device, int M, int dz, const double *X, const do
         dim3 bb(16, 16), bg((Mp + 15) / 16, (Mp + 15) / 16);
         gpfit_build_kernel<<<bg, bb, 0, s>>>(dXs, M, Mp, dz, sigma_f, sigma_n * sigma_n, dA);
         for (int j = 0; j < nb; j++) {
-            gpfit_potrf32<<<1, dim3(TB, TB), 0, s>>>(dA, Mp, j, dfail);
+            gpfit_potrf32<<<1, 32, 0, s>>>(dA, Mp, j, dfail);
             const int rem = nb - j - 1;
             if (rem > 0) {
                 gpfit_trsm32<<<(rem + 3) / 4, 128, 0, s>>>(dA, Mp, j, nb);
@@ -338,7 +344,7 @@ extern "C" int admpc_gp_predict(int device, int M, int dz, const double *X, cons
         dim3 bb(16, 16), bg((Mt + 15) / 16, (Mt + 15) / 16);
         gpfit_build_aug_kernel<<<bg, bb, 0, s>>>(dXs, dXt, M, Mp, n, Mt, dz, sigma_f, sigma_n * sigma_n, dA);
         for (int j = 0; j < nbM; j++) {                      // eliminate the training block only
-            gpfit_potrf32<<<1, dim3(TB, TB), 0, s>>>(dA, Mt, j, dfail);
+            gpfit_potrf32<<<1, 32, 0, s>>>(dA, Mt, j, dfail);
             const int rem = nb - j - 1;
             gpfit_trsm32<<<(rem + 3) / 4, 128, 0, s>>>(dA, Mt, j, nb);
             gpfit_syrk32<<<dim3(rem, rem), dim3(16, 16), 0, s>>>(dA, Mt, j, nb);
