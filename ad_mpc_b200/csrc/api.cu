@@ -409,7 +409,6 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
 extern "C" int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double *tol4, int *iterations_run)
 {
     if (!h || max_iter < 0) return ADMPC_E_ARG;
-    if (h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_solve_sqp", "full SQP mode is implemented for the Cartesian model only"); return ADMPC_E_UNSUPPORTED; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     const Params &P = h->P;
     const double dflt[4] = {1e-6, 1e-6, 1e-6, 1e-6};            // sim_car_acados_ocp.json:870-873
@@ -423,8 +422,8 @@ extern "C" int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double 
     for (it = 0; it < max_iter; it++) {
         int *ctr = h->sqp_active + (it & 1);
         CUDA_CHECK_RET(cudaMemsetAsync(ctr, 0, sizeof(int), h->stream));
-        launch_prepare(P, h->stream);
-        launch_nlp_res(P, it, tol, ctr, h->stream);
+        if (P.o.model_variant == 1) { launch_prepare_dense(P, h->stream); launch_nlp_res_dense(P, it, tol, ctr, h->stream); }
+        else { launch_prepare(P, h->stream); launch_nlp_res(P, it, tol, ctr, h->stream); }
         h->launches += 2;
         CUDA_CHECK_RET(cudaMemcpyAsync(h->sqp_active_host, ctr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));

@@ -85,5 +85,6 @@ void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
 double run_fp64_peak(int device, int nint);
 void launch_prepare_dense(const Params &P, cudaStream_t s);
 void launch_qp_dense(const Params &P, cudaStream_t s);
+void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_sqp_finalize(const Params &P, cudaStream_t s);

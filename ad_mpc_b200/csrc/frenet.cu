@@ -562,6 +562,88 @@ __global__ void __launch_bounds__(64) qp_dense_kernel(const Params P)
     AT(P.res_out, 0) = res[0]; AT(P.res_out, 1) = res[1]; AT(P.res_out, 2) = res[2]; AT(P.res_out, 3) = res[3];
 }
 
+// NLP KKT residual check of the full-SQP loop on the dense linearisation (twin of nlp_res_kernel in sqp.cu)
+__global__ void __launch_bounds__(128) nlp_res_dense_kernel(const Params P, int it, double tol0, double tol1, double tol2, double tol3,
+                                                            int *active)
+{
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.B) return;
+    const int flag = P.lin_bad[i];
+    if (flag == 2) return;
+    if (it > 0 && P.status[i] != 0) { P.sqp_status[i] = P.status[i]; P.sqp_iter[i] = it - 1; P.lin_bad[i] = 2; return; }
+    if (flag == 1) { P.sqp_status[i] = 1; P.status[i] = 1; P.sqp_iter[i] = it; P.lin_bad[i] = 2; return; }
+    const double Ts = o.dt;
+    double ng = 0, nb = 0, nd = 0, nm = 0;
+    double pim[7];
+#pragma unroll
+    for (int a = 0; a < 7; a++) { pim[a] = 0.0; nb = nmaxd(nb, fabs(AT(P.x0, a) - AT(P.xb, a))); }
+    for (int k = 0; k < N; k++) {
+        const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+        double pi[7], lam[NC], t[NC];
+#pragma unroll
+        for (int a = 0; a < 7; a++) pi[a] = AT(P.pib, k * 7 + a);
+#pragma unroll
+        for (int c = 0; c < NC; c++) { lam[c] = AT(P.lamb, k * NC + c); t[c] = AT(P.tb, k * NC + c); }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double g = AT(lin, DL_r + j);
+#pragma unroll
+            for (int l = 0; l < 7; l++) g += AT(lin, DL_B + l * 2 + j) * pi[l];
+            g += -lam[j] + lam[3 + j];
+            const double sl = AT(P.slb, k * 2 + j), su = AT(P.sub, k * 2 + j), u = AT(P.ub, k * 2 + j);
+            const double gsl = Ts * o.zl[j] + Ts * o.Zl[j] * sl - lam[j] - lam[6 + j];
+            const double gsu = Ts * o.zu[j] + Ts * o.Zu[j] * su - lam[3 + j] - lam[8 + j];
+            ng = nmaxd(ng, nmaxd(fabs(g), nmaxd(fabs(gsl), fabs(gsu))));
+            nd = nmaxd(nd, fabs(t[j] - (0.0 - (o.lbu[j] - u) + sl)));
+            nd = nmaxd(nd, fabs(t[3 + j] - ((o.ubu[j] - u) - 0.0 + su)));
+            nd = nmaxd(nd, fabs(t[6 + j] - sl));
+            nd = nmaxd(nd, fabs(t[8 + j] - su));
+        }
+        if (k >= 1) {
+            const double x6 = AT(P.xb, k * 7 + 6);
+            nd = nmaxd(nd, fabs(t[2] - (0.0 - (o.lbx - x6))));
+            nd = nmaxd(nd, fabs(t[5] - ((o.ubx - x6) - 0.0)));
+        }
+#pragma unroll
+        for (int a = 0; a < 7; a++) nb = nmaxd(nb, fabs(AT(lin, DL_b + a)));
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            if (!con_on(k, c)) continue;
+            nm = nmaxd(nm, fabs(lam[c] * t[c]));
+        }
+        if (k >= 1) {
+#pragma unroll
+            for (int a = 0; a < 7; a++) {
+                double g = AT(lin, DL_q + a) - pim[a];
+#pragma unroll
+                for (int l = 0; l < 7; l++) g += AT(lin, DL_A + l * 7 + a) * pi[l];
+                if (a == 6) g += -lam[2] + lam[5];
+                ng = nmaxd(ng, fabs(g));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 7; a++) pim[a] = pi[a];
+    }
+    {
+        const double *lin = P.lin_d + (size_t)N * DL_ROWS * Bp;
+#pragma unroll
+        for (int a = 0; a < 7; a++) ng = nmaxd(ng, fabs(AT(lin, DL_q + a) - pim[a]));
+    }
+    AT(P.nlp_res, 0) = ng; AT(P.nlp_res, 1) = nb; AT(P.nlp_res, 2) = nd; AT(P.nlp_res, 3) = nm;
+    if (ng < tol0 && nb < tol1 && nd < tol2 && nm < tol3) {
+        P.sqp_status[i] = 0; P.sqp_iter[i] = it; P.status[i] = 0; P.lin_bad[i] = 2;
+        return;
+    }
+    P.sqp_iter[i] = it + 1;
+    atomicAdd(active, 1);
+}
+void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s)
+{
+    nlp_res_dense_kernel<<<(P.B + 127) / 128, 128, 0, s>>>(P, it, tol[0], tol[1], tol[2], tol[3], active);
+}
+
 void launch_prepare_dense(const Params &P, cudaStream_t s)
 {
     dim3 grid((P.B + 127) / 128, P.o.N + 1);

@@ -125,8 +125,8 @@ int admpc_batch_set_p(admpc_batch *h, const double *p /*[B][N]*/);
 int admpc_batch_set_p_scalar(admpc_batch *h, const double *p /*[B]*/);      /* same switch on all stages (:449-450) */
 /* Frenet variant only (opts.model_variant == 1): path curvature kappa[B][N] at every shooting node (default 0; the
  * reference evaluates a B-spline kappa(s) inside the model, fren_ad_3d_optimizer bytecode).  With kappa = 0 the variant
- * coincides with the Cartesian model.  The variant runs dense, unstructured kernels (csrc/frenet.cu); full SQP mode,
- * the device reference generator and the closed-loop plant are Cartesian-only (ADMPC_E_UNSUPPORTED). */
+ * coincides with the Cartesian model.  The variant runs dense, unstructured kernels (csrc/frenet.cu), full SQP mode
+ * included; the device reference generator and the closed-loop plant are Cartesian-only (ADMPC_E_UNSUPPORTED). */
 int admpc_batch_set_kappa(admpc_batch *h, const double *kappa);
 int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state /*[B][7] or NULL = x0*/);
 /* iterate (initial guess / warm start).  reset zeroes it like $G/acados_solver_sim_car.c:819-852. */

@@ -89,8 +89,8 @@ def lib():
         L.orc_set_kappa.argtypes = [C.c_double]
         L.orc_rti_batch_frenet.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip,
                                            ip, C.c_int]
-        L.orc_sqp_batch.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, dp,
-                                    ip, ip, dp, C.c_int]
+        L.orc_sqp_batch_frenet.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, dp, C.c_int, dp,
+                                           ip, ip, dp, C.c_int]
         L.orc_load_ref_model.argtypes = [C.c_char_p]
         _lib = L
     return _lib
@@ -251,7 +251,8 @@ def rti_batch(o, x0, yref, p, xit, uit, gp=None, gp_state=None, nthreads=0, kapp
     return dict(x=x, u=u, pi=pi, status=status, qp_status=qps, qp_iter=qpi)
 
 
-def sqp_batch(o, x0, yref, p, xit, uit, gp=None, gp_state=None, max_iter=100, tol=(1e-6, 1e-6, 1e-6, 1e-6), nthreads=0):
+def sqp_batch(o, x0, yref, p, xit, uit, gp=None, gp_state=None, max_iter=100, tol=(1e-6, 1e-6, 1e-6, 1e-6), nthreads=0,
+              kappa=None):
     """Full SQP (nlp_solver_type "SQP") on a batch -> dict(x,u,status,sqp_iter,res[B,4]); inputs not modified."""
     B = x0.shape[0]
     N = o.N
@@ -264,6 +265,7 @@ def sqp_batch(o, x0, yref, p, xit, uit, gp=None, gp_state=None, max_iter=100, to
     status, it = (np.zeros(B, dtype=np.int32) for _ in range(2))
     res = np.zeros((B, 4))
     tol = np.ascontiguousarray(tol, dtype=np.float64)
-    lib().orc_sqp_batch(C.byref(o), C.byref(gp.c) if gp else None, B, _dp(x0), _dp(yref), _dp(p), _dp(gs), _dp(x), _dp(u),
-                        int(max_iter), _dp(tol), _ip(status), _ip(it), _dp(res), int(nthreads))
+    kap = None if kappa is None else np.ascontiguousarray(np.broadcast_to(np.asarray(kappa, dtype=np.float64).reshape(B, -1), (B, N)))
+    lib().orc_sqp_batch_frenet(C.byref(o), C.byref(gp.c) if gp else None, B, _dp(x0), _dp(yref), _dp(p), _dp(kap), _dp(gs),
+                               _dp(x), _dp(u), int(max_iter), _dp(tol), _ip(status), _ip(it), _dp(res), int(nthreads))
     return dict(x=x, u=u, status=status, sqp_iter=it, res=res)

@@ -726,9 +726,18 @@ void orc_nlp_residuals(const orc_opts *o, const orc_lin *lin, const orc_iterate 
 /* Full SQP (nlp_solver_type "SQP", create_ros_ad_mpc.py:47-51 point-reference mode; acados ocp_nlp_sqp [EXT]):
  * repeat { linearise; stop with status 0 when the four NLP residuals are below tol; solve the QP; full step }.
  * Returns the acados status: 0 converged, 1 NaN in the linearisation, 2 max_iter reached, 4 QP failure. */
+static int sqp_solve_impl(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref, const double *p,
+                          const double *kappa, const double *gp_state, orc_iterate *it, int max_iter, const double tol[4],
+                          int *sqp_iter, double res_out[4]);
 int orc_sqp_solve(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref, const double *p,
                   const double *gp_state, orc_iterate *it, int max_iter, const double tol[4], int *sqp_iter,
                   double res_out[4])
+{
+    return sqp_solve_impl(o, gp, x0, yref, p, 0, gp_state, it, max_iter, tol, sqp_iter, res_out);
+}
+static int sqp_solve_impl(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref, const double *p,
+                          const double *kappa, const double *gp_state, orc_iterate *it, int max_iter, const double tol[4],
+                          int *sqp_iter, double res_out[4])
 {
     const int N = o->N;
     orc_lin *lin = (orc_lin *)malloc(sizeof(orc_lin));
@@ -737,7 +746,7 @@ int orc_sqp_solve(const orc_opts *o, const orc_gp *gp, const double *x0, const d
     int status = 2, iter = 0;
     double res[4] = {0, 0, 0, 0};
     for (iter = 0; iter < max_iter; iter++) {
-        if (orc_prepare(o, gp, it, yref, p, gps, lin)) { status = 1; break; }
+        if (prepare_impl(o, gp, it, yref, p, kappa, gps, lin)) { status = 1; break; }
         orc_nlp_residuals(o, lin, it, x0, res);
         if (res[0] < tol[0] && res[1] < tol[1] && res[2] < tol[2] && res[3] < tol[3]) { status = 0; break; }
         orc_stats st;
@@ -757,9 +766,18 @@ int orc_sqp_solve(const orc_opts *o, const orc_gp *gp, const double *x0, const d
     return status;
 }
 
+int orc_sqp_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, double *xit, double *uit, int max_iter,
+                         const double *tol, int *status, int *sqp_iter, double *res, int nthreads);
 int orc_sqp_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
                   const double *p, const double *gp_state, double *xit, double *uit, int max_iter, const double *tol,
                   int *status, int *sqp_iter, double *res, int nthreads)
+{
+    return orc_sqp_batch_frenet(o, gp, B, x0, yref, p, 0, gp_state, xit, uit, max_iter, tol, status, sqp_iter, res, nthreads);
+}
+int orc_sqp_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, double *xit, double *uit, int max_iter,
+                         const double *tol, int *status, int *sqp_iter, double *res, int nthreads)
 {
     const int N = o->N;
     const size_t ny = (size_t)N * 9 + 7;
@@ -776,8 +794,8 @@ int orc_sqp_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, 
             memcpy(it->u, uit + (size_t)b * N * 2, sizeof(double) * N * 2);
             int si = 0;
             double r4[4];
-            int stt = orc_sqp_solve(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N,
-                                    gp_state ? gp_state + (size_t)b * 7 : 0, it, max_iter, tol, &si, r4);
+            int stt = sqp_solve_impl(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N, kappa ? kappa + (size_t)b * N : 0,
+                                     gp_state ? gp_state + (size_t)b * 7 : 0, it, max_iter, tol, &si, r4);
             memcpy(xit + (size_t)b * (N + 1) * 7, it->x, sizeof(double) * (N + 1) * 7);
             memcpy(uit + (size_t)b * N * 2, it->u, sizeof(double) * N * 2);
             if (status) status[b] = stt;

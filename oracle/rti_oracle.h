@@ -145,6 +145,10 @@ int orc_rti_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const doubl
                          const double *p, const double *kappa, const double *gp_state, double *xit, double *uit,
                          double *piout, int *status, int *qp_status, int *qp_iter, int nthreads);
 
+int orc_sqp_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const double *x0, const double *yref,
+                         const double *p, const double *kappa, const double *gp_state, double *xit, double *uit, int max_iter,
+                         const double *tol, int *status, int *sqp_iter, double *res, int nthreads);
+
 int orc_load_ref_model(const char *path); /* dlopen oracle/_ref/libsim_car_ref.so; 0 on success */
 
 #ifdef __cplusplus

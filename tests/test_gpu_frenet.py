@@ -75,11 +75,26 @@ def test_frenet_with_gp_and_nondefault_weights():
     s.close()
 
 
+def test_frenet_full_sqp_parity():
+    B, N = 40, 20
+    batch = wl.make_batch_frenet(B, N, seed=340, p=1.0, perturb=2.5)
+    opts = default_opts(N, model_variant=1)
+    s = BatchSolver(B, opts)
+    s.set_iterate(batch["x_init"], batch["u_init"])
+    s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"]); s.set_kappa(batch["kappa"])
+    g = s.solve_sqp()
+    r = orc.sqp_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=batch["kappa"])
+    assert np.array_equal(g["status"], r["status"]) and (r["status"] == 0).all()
+    assert np.array_equal(g["sqp_iter"], r["sqp_iter"])
+    assert mixed_err(s.get_u(), r["u"]) <= TOL and mixed_err(s.get_x(), r["x"]) <= TOL
+    s.close()
+
+
 def test_frenet_unsupported_calls_fail_loudly():
     from ad_mpc_b200 import _lib
     s = BatchSolver(4, default_opts(20, model_variant=1))
     with pytest.raises(_lib.AdmpcError):
-        s.solve_sqp()
+        s.set_track(np.zeros((10, 6)), H=20, traj_dt=0.05)
     sc = BatchSolver(4, default_opts(20))
     with pytest.raises(_lib.AdmpcError):
         sc.set_kappa(np.zeros((4, 20)))
