@@ -194,26 +194,36 @@ void launch_prepare(const Params &P, cudaStream_t s)
         // RK4 sensitivity state is spilled around it (once per RK4 stage, negligible against the M-point loop).
         // Small models: 6 CTAs x 128 threads per SM; large models (one CTA per SM by shared memory): 512 / 768 threads.
         const size_t sm = (size_t)P.gp.bytes;
-#define LAUNCH_PREP(BLK, MINB)                                                                                          \
+#define LAUNCH_PREP(BOUND, MINB, BLK)                                                                                    \
     do {                                                                                                                \
         static size_t configured = 0;                                                                                   \
         if (sm > configured) {                                                                                          \
-            cudaFuncSetAttribute(prepare_kernel<true, BLK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
             configured = sm;                                                                                            \
         }                                                                                                               \
-        dim3 grid((P.Bp + BLK - 1) / BLK, P.o.N + 1);                                                                   \
-        prepare_kernel<true, BLK, MINB><<<grid, BLK, sm, s>>>(P);                                                       \
+        dim3 grid((P.Bp + (BLK) - 1) / (BLK), P.o.N + 1);                                                               \
+        prepare_kernel<true, BOUND, MINB><<<grid, (BLK), sm, s>>>(P);                                                   \
     } while (0)
         if (sm <= 36 * 1024) {
-            LAUNCH_PREP(128, 6);            // 80 registers, 24 warps/SM
+            LAUNCH_PREP(128, 6, 128);       // 80 registers, 24 warps/SM
         } else if (sm <= 54 * 1024) {
-            LAUNCH_PREP(128, 4);
+            LAUNCH_PREP(128, 4, 128);
         } else {
-            // one CTA per SM by shared memory: pick the CTA width with the fewest (weighted) waves over the 148 SMs
-            const long n512 = (long)((P.Bp + 511) / 512) * P.o.N, n768 = (long)((P.Bp + 767) / 768) * P.o.N;
-            const long w512 = (n512 + 147) / 148 * 512, w768 = (n768 + 147) / 148 * 768;
-            if (w768 * 100 <= w512 * 104) LAUNCH_PREP(768, 1);     // 80 registers: ~4 % more throughput per SM
-            else LAUNCH_PREP(512, 1);
+            // One CTA per SM by shared memory.  All CTAs of the N working grid rows take the same time, so the run time is
+            // (number of waves over the 148 SMs) x (CTA width): pick the width, in warps, that minimises it; wider CTAs
+            // run with a lower register cap (more resident warps, slightly better latency hiding).
+            int best = 512;
+            double best_cost = 1e300;
+            for (int blk = 1024; blk >= 256; blk -= 32) {
+                const long ctas = (long)((P.Bp + blk - 1) / blk) * P.o.N;
+                const double eff = blk > 768 ? 1.02 : blk > 640 ? 0.96 : blk > 512 ? 0.98 : 1.0;   // measured per-thread cost
+                const double cost = (double)((ctas + 147) / 148) * blk * eff;
+                if (cost < best_cost) { best_cost = cost; best = blk; }
+            }
+            if (best <= 512) LAUNCH_PREP(512, 1, best);
+            else if (best <= 640) LAUNCH_PREP(640, 1, best);
+            else if (best <= 768) LAUNCH_PREP(768, 1, best);
+            else LAUNCH_PREP(1024, 1, best);
         }
     } else {
         dim3 grid((P.Bp + 127) / 128, P.o.N + 1);
