@@ -51,6 +51,10 @@ SYMBOLS = {
     "admpc_batch_size": (C.c_int, [_vp]),
     "admpc_batch_horizon": (C.c_int, [_vp]),
     "admpc_batch_set_gp": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "admpc_batch_set_gp_ensemble": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "admpc_batch_select_gp": (C.c_int, [_vp, _dp, _dp]),
+    "admpc_batch_set_gp_index": (C.c_int, [_vp, _ip]),
+    "admpc_batch_get_gp_index": (C.c_int, [_vp, _ip]),
     "admpc_batch_set_x0": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_yref": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_p": (C.c_int, [_vp, _dp]),

@@ -106,6 +106,7 @@ struct admpc_batch {
     int *ipool = nullptr;
     double *stage_in = nullptr, *stage_u = nullptr, *stage_x = nullptr, *stage_misc = nullptr;
     int *stage_status = nullptr;
+    int *gp_sel = nullptr;           // [Bp] cluster model per instance (GP ensemble)
     int *sqp_active = nullptr;       // device counters (one per SQP iteration parity), see admpc_batch_solve_sqp
     int *sqp_active_host = nullptr;  // pinned
     double *gp_blob = nullptr;
@@ -195,11 +196,12 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     size_t off = 0;
     for (auto &it : items) { *it.p = h->pool + off * Bp; off += it.rows; }
     P.x0 = x0; P.yref = yref; P.p = pp; P.gps = gps; P.kappa = kap;
-    CUDA_CHECK_RET(cudaMalloc(&h->ipool, (6 * Bp + 32) * sizeof(int)));
-    CUDA_CHECK_RET(cudaMemsetAsync(h->ipool, 0, (6 * Bp + 32) * sizeof(int), h->stream));
+    CUDA_CHECK_RET(cudaMalloc(&h->ipool, (7 * Bp + 32) * sizeof(int)));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->ipool, 0, (7 * Bp + 32) * sizeof(int), h->stream));
     P.status = h->ipool; P.qp_status = h->ipool + Bp; P.qp_iter = h->ipool + 2 * Bp; P.lin_bad = h->ipool + 3 * Bp;
     P.sqp_status = h->ipool + 4 * Bp; P.sqp_iter = h->ipool + 5 * Bp;
-    h->sqp_active = h->ipool + 6 * Bp;                       // per-iteration counters of still-running instances
+    h->gp_sel = h->ipool + 6 * Bp; P.gp_sel = h->gp_sel;
+    h->sqp_active = h->ipool + 7 * Bp;                       // per-iteration counters of still-running instances
     // instance-major staging areas
     const size_t in_rows = (size_t)N * 49 > (size_t)N * 9 + 7 ? (size_t)N * 49 : (size_t)N * 9 + 7;
     CUDA_CHECK_RET(cudaMalloc(&h->stage_in, in_rows * Bp * sizeof(double)));
@@ -231,13 +233,16 @@ extern "C" int admpc_batch_size(const admpc_batch *h) { return h ? h->P.B : ADMP
 extern "C" int admpc_batch_horizon(const admpc_batch *h) { return h ? h->P.o.N : ADMPC_E_ARG; }
 extern "C" long long admpc_batch_kernel_launches(const admpc_batch *h) { return h ? h->launches : 0; }
 
-// packs the GP model into the TMA-friendly blob (see GpDev) and uploads it
-static int upload_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, const int *rows, const double *X,
-                     const double *alpha, const double *ell, const double *sigma_f, const double *y_mean, int trig)
+// packs K cluster models (K = 1: a plain GP) into the TMA-friendly blob (see GpDev) and uploads it.
+// Array layouts carry a leading model axis: X[K][nout][M][dz], alpha[K][nout][M], ell[K][nout][dz], sigma_f[K][nout],
+// y_mean[K][nout], centroids[K][dz] (NULL for K = 1).
+static int upload_gp(admpc_batch *h, int K, int nout, int M, int dz, const int *feat, const int *rows, const double *X,
+                     const double *alpha, const double *ell, const double *sigma_f, const double *y_mean,
+                     const double *centroids, int trig)
 {
     Params &P = h->P;
     if (nout == 0) { P.o.gp_enabled = 0; return 0; }
-    if (nout < 0 || nout > ADMPC_GPOUT_MAX || M <= 0 || dz <= 0 || dz > ADMPC_DZMAX || !feat || !rows || !X || !alpha || !ell || !sigma_f || !y_mean) {
+    if (K < 1 || nout < 0 || nout > ADMPC_GPOUT_MAX || M <= 0 || dz <= 0 || dz > ADMPC_DZMAX || !feat || !rows || !X || !alpha || !ell || !sigma_f || !y_mean || (K > 1 && !centroids)) {
         admpc_set_error("admpc_batch_set_gp", "bad argument");
         return ADMPC_E_ARG;
     }
@@ -246,38 +251,48 @@ static int upload_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, c
     for (int j = 0; j < nout; j++)
         if (rows[j] < 3 || rows[j] > 5) { admpc_set_error("admpc_batch_set_gp", "GP outputs must map to state rows 3..5"); return ADMPC_E_UNSUPPORTED; }
     const size_t stride = gp_stride(M, dz);
-    const size_t bytes = gp_blob_doubles(nout, M, dz) * sizeof(double);
-    if (bytes > 220 * 1024) { admpc_set_error("admpc_batch_set_gp", "GP model exceeds the shared-memory staging budget (220 KB)"); return ADMPC_E_UNSUPPORTED; }
-    std::vector<double> blob(gp_blob_doubles(nout, M, dz), 0.0);
-    for (int j = 0; j < GP_TAB; j++) blob[stride * nout + j] = exp2((double)j / GP_TAB);
-    for (int j = 0; j < nout; j++) {
-        double *b = blob.data() + stride * j;
-        const double L2E = 1.4426950408889634;
-        for (int i = 0; i < M; i++) {
-            double c = 0.0;
-            for (int d = 0; d < dz; d++) {
-                const double x = X[((size_t)j * M + i) * dz + d], wd = 1.0 / (ell[j * dz + d] * ell[j * dz + d]);
-                b[(size_t)i * (dz + 2) + d] = L2E * wd * x;
-                c += wd * x * x;
+    const size_t model_doubles = stride * nout;
+    const size_t total = model_doubles * K + GP_TAB;
+    const size_t bytes = total * sizeof(double);
+    if (bytes > 220 * 1024) { admpc_set_error("admpc_batch_set_gp", "GP model (all cluster models together) exceeds the shared-memory staging budget (220 KB)"); return ADMPC_E_UNSUPPORTED; }
+    std::vector<double> blob(total, 0.0);
+    for (int j = 0; j < GP_TAB; j++) blob[model_doubles * K + j] = exp2((double)j / GP_TAB);
+    const double L2E = 1.4426950408889634;
+    for (int c = 0; c < K; c++)
+        for (int j = 0; j < nout; j++) {
+            const size_t cj = (size_t)c * nout + j;
+            double *b = blob.data() + model_doubles * c + stride * j;
+            for (int i = 0; i < M; i++) {
+                double cs = 0.0;
+                for (int d = 0; d < dz; d++) {
+                    const double x = X[(cj * M + i) * dz + d], wd = 1.0 / (ell[cj * dz + d] * ell[cj * dz + d]);
+                    b[(size_t)i * (dz + 2) + d] = L2E * wd * x;
+                    cs += wd * x * x;
+                }
+                b[(size_t)i * (dz + 2) + dz] = -0.5 * L2E * cs;
+                b[(size_t)i * (dz + 2) + dz + 1] = sigma_f[cj] * alpha[cj * M + i];
             }
-            b[(size_t)i * (dz + 2) + dz] = -0.5 * L2E * c;
-            b[(size_t)i * (dz + 2) + dz + 1] = sigma_f[j] * alpha[(size_t)j * M + i];
+            double *w = b + (size_t)M * (dz + 2);
+            for (int d = 0; d < dz; d++) w[d] = 1.0 / (ell[cj * dz + d] * ell[cj * dz + d]);
+            w[dz] = y_mean[cj];
         }
-        double *w = b + (size_t)M * (dz + 2);
-        for (int d = 0; d < dz; d++) w[d] = 1.0 / (ell[j * dz + d] * ell[j * dz + d]);
-        w[dz] = y_mean[j];
-    }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
-    if (bytes > h->gp_blob_cap) {
+    const size_t cbytes = (size_t)K * dz * sizeof(double);
+    if (bytes + cbytes > h->gp_blob_cap) {
         cudaFree(h->gp_blob);
-        CUDA_CHECK_RET(cudaMalloc(&h->gp_blob, bytes));
-        h->gp_blob_cap = bytes;
+        CUDA_CHECK_RET(cudaMalloc(&h->gp_blob, bytes + cbytes));
+        h->gp_blob_cap = bytes + cbytes;
     }
     CUDA_CHECK_RET(cudaMemcpyAsync(h->gp_blob, blob.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+    if (K > 1) CUDA_CHECK_RET(cudaMemcpyAsync((char *)h->gp_blob + bytes, centroids, cbytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK_RET(cudaMemsetAsync(h->gp_sel, 0, (size_t)P.Bp * sizeof(int), h->stream));      // model 0 until a selection is made
     CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     P.gp.blob = h->gp_blob;
     P.gp.bytes = (int)bytes;
     P.gp.stride_out = (int)stride;
+    P.gp.n_models = K;
+    P.gp.model_doubles = (int)model_doubles;
+    P.gp.centroids = (const double *)((char *)h->gp_blob + bytes);
     P.o.gp_enabled = 1;
     P.o.gp_nout = nout; P.o.gp_M = M; P.o.gp_dz = dz; P.o.gp_stage0_trigger = trig;
     for (int d = 0; d < dz; d++) P.o.gp_feat[d] = feat[d];
@@ -290,7 +305,62 @@ extern "C" int admpc_batch_set_gp(admpc_batch *h, int nout, int M, int dz, const
                                   const double *y_mean, int stage0_trigger)
 {
     if (!h) return ADMPC_E_ARG;
-    return upload_gp(h, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, stage0_trigger);
+    return upload_gp(h, 1, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, nullptr, stage0_trigger);
+}
+
+// GP ensemble (GPEnsemble, gp.py:536-770; homogeneous case: the same K clusters for every output dimension):
+// K cluster models with their centroids in feature space; every instance uses ONE of them per solve, chosen by
+// admpc_batch_select_gp (nearest centroid, gp.py:738-770) or set explicitly (the reference's use_model argument).
+extern "C" int admpc_batch_set_gp_ensemble(admpc_batch *h, int K, int nout, int M, int dz, const int *feat, const int *rows,
+                                           const double *X, const double *alpha, const double *ell, const double *sigma_f,
+                                           const double *y_mean, const double *centroids, int stage0_trigger)
+{
+    if (!h) return ADMPC_E_ARG;
+    return upload_gp(h, K, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, centroids, stage0_trigger);
+}
+
+// nearest-centroid choice per instance from the query state xq [B][7] (NULL: the current x0) and input uq [B][2]
+// (NULL: zeros): argmin_c || z - centroid_c ||, z = B_z [x; u]; first minimum wins like np.argmin.
+extern "C" int admpc_batch_select_gp(admpc_batch *h, const double *xq, const double *uq)
+{
+    if (!h) return ADMPC_E_ARG;
+    Params &P = h->P;
+    if (!P.o.gp_enabled) { admpc_set_error("admpc_batch_select_gp", "no GP model set"); return ADMPC_E_STATE; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const double *dx = P.x0, *du = nullptr;
+    if (xq) {
+        CUDA_CHECK_RET(cudaMemcpyAsync(h->stage_in, xq, (size_t)P.B * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_transpose_in(h->stage_in, h->stage_x, P.B, P.Bp, 7, h->stream);
+        dx = h->stage_x;
+    }
+    if (uq) {
+        CUDA_CHECK_RET(cudaMemcpyAsync(h->stage_misc, uq, (size_t)P.B * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_transpose_in(h->stage_misc, h->stage_u, P.B, P.Bp, 2, h->stream);
+        du = h->stage_u;
+    }
+    launch_gp_select(P, dx, du, h->gp_sel, h->stream);
+    h->launches += 1 + (xq ? 1 : 0) + (uq ? 1 : 0);
+    CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+}
+extern "C" int admpc_batch_set_gp_index(admpc_batch *h, const int *idx)
+{
+    if (!h || !idx) return ADMPC_E_ARG;
+    const Params &P = h->P;
+    for (int i = 0; i < P.B; i++)
+        if (idx[i] < 0 || idx[i] >= (P.gp.n_models > 0 ? P.gp.n_models : 1)) { admpc_set_error("admpc_batch_set_gp_index", "model index out of range"); return ADMPC_E_ARG; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaMemcpyAsync(h->gp_sel, idx, (size_t)P.B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int admpc_batch_get_gp_index(admpc_batch *h, int *idx)
+{
+    if (!h || !idx) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    CUDA_CHECK_RET(cudaMemcpyAsync(idx, h->gp_sel, (size_t)h->P.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 // host instance-major [B][F] -> device SoA rows
@@ -840,7 +910,7 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
     // header (sizes, feature map) first, then the packed blob, both over NCCL on the handle's stream
     int hdr[4 + ADMPC_DZMAX + ADMPC_GPOUT_MAX] = {0};
     if (h->rank == root) {
-        int r = upload_gp(h, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, stage0_trigger);
+        int r = upload_gp(h, 1, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, nullptr, stage0_trigger);   // single model
         if (r) return r;
         hdr[0] = nout; hdr[1] = M; hdr[2] = dz; hdr[3] = stage0_trigger;
         for (int d = 0; d < dz; d++) hdr[4 + d] = feat[d];
@@ -862,6 +932,8 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
             h->gp_blob_cap = bytes;
         }
         P.gp.blob = h->gp_blob; P.gp.bytes = (int)bytes; P.gp.stride_out = (int)stride;
+        P.gp.n_models = 1; P.gp.model_doubles = (int)(stride * nout); P.gp.centroids = nullptr;
+        CUDA_CHECK_RET(cudaMemsetAsync(h->gp_sel, 0, (size_t)P.Bp * sizeof(int), h->stream));
         P.o.gp_enabled = nout > 0; P.o.gp_nout = nout; P.o.gp_M = M; P.o.gp_dz = dz; P.o.gp_stage0_trigger = hdr[3];
         for (int d = 0; d < dz; d++) P.o.gp_feat[d] = hdr[4 + d];
         for (int j = 0; j < nout; j++) P.o.gp_row[j] = hdr[4 + ADMPC_DZMAX + j];

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) postsolve_kernel(const Params P, const Lo
 #pragma unroll
         for (int c = 0; c < 7; c++) xs[c] = fma(h * as, kx[c], x[c]);
         Jac J;
-        model_eval<false>(o, nullptr, 0, xs, u, p, gz, 0.0, f, J);
+        model_eval<false>(o, nullptr, 0, 0u, xs, u, p, gz, 0.0, f, J);
 #pragma unroll
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
     }

@@ -34,6 +34,11 @@ struct GpDev {
     const double *blob;
     int bytes;          // multiple of 16
     int stride_out;     // doubles per output block
+    // ensemble (GPEnsemble, gp.py:536-770): n_models cluster models back to back, model_doubles apart; the table of the
+    // device exp2 follows the last model.  centroids [n_models][dz] in HBM for the per-instance nearest-centroid choice.
+    int n_models;
+    int model_doubles;
+    const double *centroids;
 };
 
 #define DL_ROWS 79
@@ -60,6 +65,7 @@ struct Params {
     double *lin_d;
     const double *kappa;
     int *sqp_status, *sqp_iter;
+    const int *gp_sel;   // [Bp] cluster model of every instance (GP ensemble; zeros for a single model)
     double *nlp_res;     // [4][Bp] NLP KKT residual norms of the last check
 };
 
@@ -84,6 +90,7 @@ void launch_update(const Params &P, cudaStream_t s);
 void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
 double run_fp64_peak(int device, int nint);
 void launch_prepare_dense(const Params &P, cudaStream_t s);
+void launch_gp_select(const Params &P, const double *xq, const double *uq, int *sel, cudaStream_t s);
 void launch_qp_dense(const Params &P, cudaStream_t s);
 void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);

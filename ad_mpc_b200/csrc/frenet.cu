@@ -31,12 +31,12 @@ __device__ __forceinline__ double nmaxd(double a, double b) { return (a > b || a
 
 // dense f, Jx (7x7), Ju (7x2) of the Frenet variant at (x, u); rows 3..6 (+ GP) from the shared model code
 template <bool GP>
-__device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *gpsm, int gp_stride, const double x[7],
+__device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *gpsm, int gp_stride, uint32_t tab, const double x[7],
                                             const double u[2], double p, double kap, const double gpx[7], double trig,
                                             double f[7], double Jx[7][7], double Ju[7][2])
 {
     Jac J;
-    model_eval<GP>(o, gpsm, gp_stride, x, u, p, gpx, trig, f, J);
+    model_eval<GP>(o, gpsm, gp_stride, tab, x, u, p, gpx, trig, f, J);
 #pragma unroll
     for (int r = 0; r < 7; r++) {
 #pragma unroll
@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(128) prepare_dense_kernel(const Params P)
     const int k = blockIdx.y;
     if (i >= P.B || P.lin_bad[i] == 2) return;
     const double h = o.dt, Ts = o.dt;
+    const double *gpm = GP ? gpsm + (size_t)P.gp_sel[i] * P.gp.model_doubles : nullptr;      // this instance's cluster model
+    const uint32_t tab = GP ? (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)P.gp.n_models * P.gp.model_doubles) : 0u;
     double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
     double x[7];
 #pragma unroll
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(128) prepare_dense_kernel(const Params P)
         double xs[7], f[7], Jx[7][7], Ju[7][2];
 #pragma unroll
         for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
-        frenet_eval<GP>(o, gpsm, P.gp.stride_out, xs, u, pk, kap, gpx, trig, f, Jx, Ju);
+        frenet_eval<GP>(o, gpm, P.gp.stride_out, tab, xs, u, pk, kap, gpx, trig, f, Jx, Ju);
 #pragma unroll
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
 #pragma unroll

@@ -112,7 +112,9 @@ struct Jac {
 };
 
 template <bool GP>
-__device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__restrict__ gpsm, int gp_stride,
+// gpsm: shared-memory copy of THIS instance's cluster model (nout output blocks); tab: shared-space address of the
+// 2^(j/GP_TAB) table of the device exp2
+__device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__restrict__ gpsm, int gp_stride, uint32_t tab,
                                            const double x[7], const double u[2], double p, const double gpx[7],
                                            double trig, double f[7], Jac &J)
 {
@@ -187,8 +189,6 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
             // q = -0.5 log2(e) sum_d z_d^2/ell_d^2  (expanded square: 4 FMAs per point instead of 12 ops; the
             // cancellation costs ~1e-15 absolute in the exponent).  Tail: 1/ell_d^2 (dz values), y_mean.
             const double *blk = gpsm + (size_t)j * gp_stride;
-            // 2^(j/GP_TAB) table behind the last output (32-bit shared-space address, fixed for the whole sweep)
-            const uint32_t tab = (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)o.gp_nout * gp_stride);
             const double *w = blk + (size_t)M * (dz + 2);
             double wv[ADMPC_DZMAX];
 #pragma unroll

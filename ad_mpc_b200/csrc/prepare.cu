@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
         mbar_wait(&bar, 0);
     }
     if (!active) return;
+    const double *gpm = GP ? gpsm + (size_t)P.gp_sel[i] * P.gp.model_doubles : nullptr;      // this instance's cluster model
+    const uint32_t tab = GP ? (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)P.gp.n_models * P.gp.model_doubles) : 0u;
 
     // K = current stage derivative of the sensitivity block, acc = weighted sum (rows 0..5 x 7 cols)
     double K[6][7], acc[6][7];
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
 #pragma unroll
         for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
         Jac J;
-        model_eval<GP>(o, gpsm, P.gp.stride_out, xs, u, pk, gpx, trig, f, J);
+        model_eval<GP>(o, gpm, P.gp.stride_out, tab, xs, u, pk, gpx, trig, f, J);
 #pragma unroll
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
         // sensitivity columns: c = 0..4 <-> x2..x6, c = 5,6 <-> u0,u1

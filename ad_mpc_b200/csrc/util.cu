@@ -68,6 +68,34 @@ void launch_fill(double *dst, size_t n, double v, cudaStream_t s)
     fill_kernel<<<148 * 8, 256, 0, s>>>(dst, n, v);
 }
 
+// ---- GP ensemble: nearest-centroid model choice per instance (GPEnsemble.select_gp, model_fitting/gp.py:738-770) -----
+// z = B_z [x; u] from the query state / input (SoA rows), distance sqrt(sum (z - c)^2) like the reference, first minimum
+__global__ void gp_select_kernel(const Params P, const double *__restrict__ xq, const double *__restrict__ uq, int *sel)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.B) return;
+    const int dz = P.o.gp_dz, K = P.gp.n_models, Bp = P.Bp;
+    double z[ADMPC_DZMAX];
+    for (int d = 0; d < dz; d++) {
+        const int f = P.o.gp_feat[d];
+        z[d] = (f < 7) ? xq[(size_t)f * Bp + i] : (uq ? uq[(size_t)(f - 7) * Bp + i] : 0.0);
+    }
+    int best = 0;
+    double bd = 0.0;
+    for (int c = 0; c < K; c++) {
+        double d2 = 0.0;
+        for (int d = 0; d < dz; d++) { const double t = z[d] - P.gp.centroids[c * dz + d]; d2 = d2 + t * t; }
+        const double dist = sqrt(d2);
+        if (c == 0 || dist < bd) { bd = dist; best = c; }
+    }
+    sel[i] = best;
+}
+void launch_gp_select(const Params &P, const double *xq, const double *uq, int *sel, cudaStream_t s)
+{
+    if (P.gp.n_models <= 1) { cudaMemsetAsync(sel, 0, (size_t)P.Bp * sizeof(int), s); return; }
+    gp_select_kernel<<<(P.B + 127) / 128, 128, 0, s>>>(P, xq, uq, sel);
+}
+
 // ---- FP64 peak probe: 8 independent DFMA chains per thread, full occupancy -------------------------------
 // NINT > 0 adds NINT independent integer multiply-adds per 8 DFMAs (issue-slot pressure probe: how much FP64
 // throughput survives when the scheduler also has address / index arithmetic to issue).

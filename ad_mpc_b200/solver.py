@@ -106,6 +106,42 @@ class BatchSolver:
                                         _dp(_f64(model["ell"])), _dp(_f64(model["sigma_f"])), _dp(_f64(model["y_mean"])),
                                         int(stage0_trigger)), "admpc_batch_set_gp")
 
+    def set_gp_ensemble(self, models, centroids=None, stage0_trigger=1):
+        """GP ensemble (GPEnsemble, gp.py:536-770): `models` = list of K model dicts of the set_gp schema (one per cluster,
+        same nout / M / dz / feat / rows), `centroids` [K, dz] cluster means in feature space (default: model["mean"]).
+        Clusters are sorted by the first centroid coordinate like GPEnsemble.add_model does (gp.py:592-595)."""
+        K = len(models)
+        cen = np.asarray([m["mean"] for m in models] if centroids is None else centroids, dtype=np.float64).reshape(K, -1)
+        order = np.argsort(cen[:, 0], kind="stable")
+        models = [models[i] for i in order]
+        cen = _f64(cen[order])
+        X = _f64(np.stack([m["X"] for m in models]))
+        _, nout, M, dz = X.shape
+        feat = np.ascontiguousarray(models[0].get("feat", (3, 4, 5, 6)[:dz]), dtype=np.int32)
+        rows = np.ascontiguousarray(models[0].get("rows", (4, 5)[:nout]), dtype=np.int32)
+        stack = lambda k: _f64(np.stack([np.asarray(m[k], dtype=np.float64) for m in models]))
+        check(self.L.admpc_batch_set_gp_ensemble(self.h, K, nout, M, dz, _ip(feat), _ip(rows), _dp(X), _dp(stack("alpha")),
+                                                 _dp(stack("ell")), _dp(stack("sigma_f")), _dp(stack("y_mean")), _dp(cen),
+                                                 int(stage0_trigger)), "admpc_batch_set_gp_ensemble")
+        return order
+
+    def select_gp(self, x=None, u=None):
+        """Nearest-centroid model choice per instance (GPEnsemble.select_gp, gp.py:738-770) from the query state x [B,7]
+        (default: the current x0) and input u [B,2] (default: zeros); returns the chosen indices [B]."""
+        check(self.L.admpc_batch_select_gp(self.h, None if x is None else _dp(_f64(x, (self.B, 7))),
+                                           None if u is None else _dp(_f64(u, (self.B, 2)))), "select_gp")
+        return self.get_gp_index()
+
+    def set_gp_index(self, idx):
+        """Explicit model choice per instance (the reference's use_model argument)."""
+        i = np.ascontiguousarray(np.broadcast_to(np.asarray(idx, dtype=np.int32).reshape(-1), (self.B,)))
+        check(self.L.admpc_batch_set_gp_index(self.h, _ip(i)), "set_gp_index")
+
+    def get_gp_index(self):
+        out = np.empty(self.B, dtype=np.int32)
+        check(self.L.admpc_batch_get_gp_index(self.h, _ip(out)), "get_gp_index")
+        return out
+
     def set_x0(self, x0):
         check(self.L.admpc_batch_set_x0(self.h, _dp(_f64(x0, (self.B, 7)))), "set_x0")
 

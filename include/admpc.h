@@ -117,6 +117,21 @@ int admpc_batch_set_gp(admpc_batch *h, int nout, int M, int dz, const int *feat,
                        const double *X, const double *alpha, const double *ell, const double *sigma_f,
                        const double *y_mean, int stage0_trigger);
 
+/* GP ensemble (GPEnsemble, model_fitting/gp.py:536-770, homogeneous case): K cluster models with a leading model axis,
+ * X[K][nout][M][dz], alpha[K][nout][M], ell[K][nout][dz], sigma_f[K][nout], y_mean[K][nout], centroids[K][dz] (cluster
+ * means in feature space, in the order the reference sorts them: ascending first coordinate, gp.py:592-595).  All
+ * models are staged in shared memory together (220 KB budget).  Every instance uses ONE model per solve:
+ *   admpc_batch_select_gp   nearest centroid to z = B_z [xq; uq] (select_gp, gp.py:738-770); xq NULL = the current x0,
+ *                           uq NULL = zeros (the reference queries with the reference state / target input,
+ *                           quad_mpc/quad_3d_optimizer.py:452,491)
+ *   admpc_batch_set_gp_index explicit choice (the reference's use_model argument); model 0 after set_gp_ensemble. */
+int admpc_batch_set_gp_ensemble(admpc_batch *h, int K, int nout, int M, int dz, const int *feat, const int *rows,
+                                const double *X, const double *alpha, const double *ell, const double *sigma_f,
+                                const double *y_mean, const double *centroids, int stage0_trigger);
+int admpc_batch_select_gp(admpc_batch *h, const double *xq /*[B][7] or NULL*/, const double *uq /*[B][2] or NULL*/);
+int admpc_batch_set_gp_index(admpc_batch *h, const int *idx /*[B]*/);
+int admpc_batch_get_gp_index(admpc_batch *h, int *idx /*[B]*/);
+
 /* per-solve inputs ($A/ad_3d_optimizer.py:420-450).  Asynchronous on the handle's stream; pinned host memory
  * (admpc_host_alloc) makes the copies truly asynchronous. */
 int admpc_batch_set_x0(admpc_batch *h, const double *x0 /*[B][7]*/);
