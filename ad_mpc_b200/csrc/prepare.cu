@@ -42,7 +42,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 // One RK4 step with forward sensitivities. Sensitivity state: rows 0..5 x 7 columns [x2..x6 | u0 u1];
 // row 6 (delta) is analytic: d delta / d delta = 1, d delta / d u1 = t.
-template <bool GP, int BLOCK, int MINB>
+// ENS: GP ensemble -- the cluster model is chosen per instance, so the training-set loads use per-thread addresses; a
+// single model keeps warp-uniform addresses (uniform-register LDS), which is measurably cheaper.
+template <bool GP, int BLOCK, int MINB, bool ENS = false>
 __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
         mbar_wait(&bar, 0);
     }
     if (!active) return;
-    const double *gpm = GP ? gpsm + (size_t)P.gp_sel[i] * P.gp.model_doubles : nullptr;      // this instance's cluster model
+    const double *gpm = (GP && ENS) ? gpsm + (size_t)P.gp_sel[i] * P.gp.model_doubles : gpsm;   // this instance's cluster model
     const uint32_t tab = GP ? (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)P.gp.n_models * P.gp.model_doubles) : 0u;
 
     // K = current stage derivative of the sensitivity block, acc = weighted sum (rows 0..5 x 7 cols)
@@ -200,11 +202,13 @@ void launch_prepare(const Params &P, cudaStream_t s)
     do {                                                                                                                \
         static size_t configured = 0;                                                                                   \
         if (sm > configured) {                                                                                          \
-            cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
             configured = sm;                                                                                            \
         }                                                                                                               \
         dim3 grid((P.Bp + (BLK) - 1) / (BLK), P.o.N + 1);                                                               \
-        prepare_kernel<true, BOUND, MINB><<<grid, (BLK), sm, s>>>(P);                                                   \
+        if (P.gp.n_models > 1) prepare_kernel<true, BOUND, MINB, true><<<grid, (BLK), sm, s>>>(P);                      \
+        else prepare_kernel<true, BOUND, MINB, false><<<grid, (BLK), sm, s>>>(P);                                       \
     } while (0)
         if (sm <= 36 * 1024) {
             LAUNCH_PREP(128, 6, 128);       // 80 registers, 24 warps/SM
