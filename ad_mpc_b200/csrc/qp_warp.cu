@@ -54,6 +54,17 @@ __device__ __forceinline__ double sel7(const double *a, int idx)
     for (int c = 0; c < 7; c++) if (c == idx) v = a[c];
     return v;
 }
+// 1/x for positive normal x without the out-of-line slow path of the IEEE division (the compiler keeps registers free
+// around that call): hardware seed (2^-20) + two Newton steps, <= 1 ulp; NaN propagates, x = 0 gives NaN instead of inf.
+__device__ __forceinline__ double rcp_nr(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 __device__ __forceinline__ double wsum(double v)
 {
 #pragma unroll
@@ -112,7 +123,7 @@ __device__ __forceinline__ void barrier_w(const admpc_opts &o, bool k_ge1, const
     for (int j = 0; j < 2; j++) {
         const double Sl = S.lam[j] * it[j], Su = S.lam[3 + j] * it[3 + j];
         const double Ssl = S.lam[6 + j] * it[6 + j], Ssu = S.lam[8 + j] * it[8 + j];
-        const double iDl = 1.0 / (Ts * o.Zl[j] + Sl + Ssl), iDu = 1.0 / (Ts * o.Zu[j] + Su + Ssu);
+        const double iDl = rcp_nr(Ts * o.Zl[j] + Sl + Ssl), iDu = rcp_nr(Ts * o.Zu[j] + Su + Ssu);
         Rt[j] = Ts * o.W[7 + j] + Sl * (1.0 - Sl * iDl) + Su * (1.0 - Su * iDu);
         const double cl = R.rgsl[j] + g[j] + g[6 + j];
         const double cu = R.rgsu[j] + g[3 + j] + g[8 + j];
@@ -238,7 +249,7 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
         const double gu0 = xs[X_GV + 0], gu1 = xs[X_GV + 1];
         if (FACTOR) {
             const double g00 = xs[X_GS + 0] + o.reg, g01 = xs[X_GS + 1], g11 = xs[X_GS + 2] + o.reg;
-            const double idet = 1.0 / (g00 * g11 - g01 * g01);
+            const double idet = rcp_nr(g00 * g11 - g01 * g01);
             gi00 = g11 * idet; gi01 = -g01 * idet; gi11 = g00 * idet;
             {
                 const double c0 = kj ? gi01 : gi00, c1 = kj ? gi11 : gi01;
@@ -509,7 +520,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
         double *st = sm + (isst ? k : 0) * R_STRIDE;
         if (isst) {
 #pragma unroll
-            for (int c = 0; c < NC; c++) it[c] = 1.0 / S.t[c];
+            for (int c = 0; c < NC; c++) it[c] = rcp_nr(S.t[c]);
             StageRes R;
             stage_res(o, k >= 1, S, R);
 #pragma unroll
@@ -614,7 +625,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
                     const double duj = (j == 0) ? du0 : du1;
                     const double Sl = S.lam[j] * it[j], Su = S.lam[3 + j] * it[3 + j];
                     const double Ssl = S.lam[6 + j] * it[6 + j], Ssu = S.lam[8 + j] * it[8 + j];
-                    const double iDl = 1.0 / (Ts * o.Zl[j] + Sl + Ssl), iDu = 1.0 / (Ts * o.Zu[j] + Su + Ssu);
+                    const double iDl = rcp_nr(Ts * o.Zl[j] + Sl + Ssl), iDu = rcp_nr(Ts * o.Zu[j] + Su + Ssu);
                     const double cl = R.rgsl[j] + gq[j] + gq[6 + j];
                     const double cu = R.rgsu[j] + gq[3 + j] + gq[8 + j];
                     dsl[j] = -(cl + Sl * duj) * iDl;
@@ -655,9 +666,9 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
                 s1 = r[2] + r[6]; s2 = r[3] + r[7];
             }
             if (pass == 0) {
-                const double a_aff = an / ad;
+                const double a_aff = an * rcp_nr(ad);
                 const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
-                double sigma = mu_aff / mu;
+                double sigma = mu_aff * rcp_nr(mu);
                 sigma = sigma * sigma * sigma;
                 const double sigmu = sigma * mu;
                 if (isst) {
@@ -679,7 +690,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
                 if (NW == 2) __syncthreads();
             }
         }
-        double alpha = an / ad;
+        double alpha = an * rcp_nr(ad);
         if (alpha < o.alpha_min) { status = 2; break; }
         if (alpha < 1.0) alpha *= 0.995;
         // ================= update (stage role); pi and dx wait for the adjoint sweep ==========================================
