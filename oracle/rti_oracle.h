@@ -13,6 +13,8 @@
  *   - GP posterior mean      : pinned against the reference's own numeric predict() (model_fitting/gp.py imported with
  *                              its symbolic dependencies stubbed; tests/golden/gp_reference.npz); the Jacobian by finite
  *                              differences of that mean
+ *   - QP SOLUTION            : certified solver-independently (tests/test_qp_certificate_cpu.py: the oracle's answer is
+ *                              the KKT point of its active set, by one dense numpy KKT solve -- sufficient for a convex QP)
  *   - IPM iterate path / iteration counts: UNPINNED by reference fixtures (acados/HPIPM are not vendored in the
  *                              reference) -- restated from the published algorithm, design choices in DESIGN.md.
  */
