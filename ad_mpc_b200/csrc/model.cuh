@@ -103,6 +103,48 @@ __device__ __forceinline__ double exp2_back(const Exp2Part &e)
 }
 __device__ __forceinline__ double exp2_neg_tab(double t, uint32_t tab) { return exp2_back(exp2_front(t, tab)); }
 
+// sin and cos for the heading / steering angles of the model (|x| far below 1e5): Cody-Waite reduction by pi/2 in three
+// parts + degree-13 / degree-14 polynomials, everything inline.  The libdevice sincos carries an out-of-line slow path
+// for huge arguments; a call inside the preparation kernel makes the register allocator spill around it.
+__device__ __forceinline__ void sincos_mid(double x, double *s, double *c)
+{
+    const double SHIFT = 6755399441055744.0;
+    const double kd = fma(x, 0.63661977236758134308, SHIFT);           // x * 2/pi, rounded to nearest integer
+    const int k = __double2loint(kd);
+    const double kf = kd - SHIFT;
+    double r = fma(kf, -1.57079632679489655800e+00, x);                // pi/2 split in three parts (53 + 53 + 53 bits)
+    r = fma(kf, -6.12323399573676603587e-17, r);
+    r = fma(kf, 1.49745833459802707e-33, r);
+    const double z = r * r;
+    double ps = 1.58962301576546568060e-10;
+    ps = fma(ps, z, -2.50507477628578072866e-08);
+    ps = fma(ps, z, 2.75573136213857245213e-06);
+    ps = fma(ps, z, -1.98412698295895385996e-04);
+    ps = fma(ps, z, 8.33333333332211858878e-03);
+    ps = fma(ps, z, -1.66666666666666307295e-01);
+    const double sn = fma(ps * z, r, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double cs = fma(fma(pc, z, -0.5), z, 1.0);
+    const double s0 = (k & 1) ? cs : sn, c0 = (k & 1) ? sn : cs;
+    *s = (k & 2) ? -s0 : s0;
+    *c = ((k + 1) & 2) ? -c0 : c0;
+}
+// 1/x for normal x without the IEEE division's out-of-line slow path (hardware seed + two Newton steps, <= 1 ulp)
+__device__ __forceinline__ double rcp_mid(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 struct Jac {
     // d f / d x : rows 0,1 x cols {psi,vx,vy}; row 2 = e_r; rows 3..5 x cols 2..6 ; row 6 = 0
     double j0[3], j1[3];
@@ -120,12 +162,12 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
 {
     const double psi = x[2], vx = x[3], vy = x[4], r = x[5], dl = x[6];
     const double u0 = u[0], u1 = u[1];
-    const double im = 1.0 / o.mass, iiz = 1.0 / o.iz, L = o.lr + o.lf, c = o.lr / L, iL = 1.0 / L, q = 1.0 - p;
+    const double im = rcp_mid(o.mass), iiz = rcp_mid(o.iz), L = o.lr + o.lf, iL = rcp_mid(L), c = o.lr * iL, q = 1.0 - p;
     double sp, cp, sd, cd;
-    sincos(psi, &sp, &cp);
-    sincos(dl, &sd, &cd);
+    sincos_mid(psi, &sp, &cp);
+    sincos_mid(dl, &sd, &cd);
     const double D = vx + 1e-99;
-    const double iD = 1.0 / D;
+    const double iD = rcp_mid(D);
     const double a = (vy + o.lf * r) * iD;
     const double Ff = o.cf2 * (dl - a);
     const double Fr = o.cr2 * (o.lr * r - vy) * iD;
