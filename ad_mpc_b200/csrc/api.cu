@@ -944,6 +944,24 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
     return 0;
 }
 
+// host copy of the blocks the last gather left on the root (rank-major, instance-major inside)
+extern "C" int admpc_batch_get_gathered(admpc_batch *h, double *u_all, double *x_all, int *status_all)
+{
+    if (!h || !h->gpack) { admpc_set_error("admpc_batch_get_gathered", "nothing gathered on this rank"); return ADMPC_E_STATE; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const Params &P = h->P;
+    const size_t nu = (size_t)P.B * P.o.N * 2, nx = (size_t)P.B * (P.o.N + 1) * 7;
+    const size_t bytes = (nu + nx) * sizeof(double) + (size_t)P.B * sizeof(int);
+    for (int r = 0; r < h->nranks; r++) {
+        const char *blk = h->gpack + (size_t)r * bytes;
+        if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all + (size_t)r * nu, blk, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all + (size_t)r * nx, blk + nu * sizeof(double), nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all + (size_t)r * P.B, blk + (nu + nx) * sizeof(double), (size_t)P.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, double *x_all, int *status_all)
 {
     if (!h || !h->comm) { admpc_set_error("admpc_batch_gather", "communicator not initialised"); return ADMPC_E_STATE; }

@@ -219,6 +219,8 @@ int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, cons
                          const double *X, const double *alpha, const double *ell, const double *sigma_f,
                          const double *y_mean, int stage0_trigger);
 int admpc_batch_gather(admpc_batch *h, int root, double *u_all /*[nranks*B][N*2]*/, double *x_all, int *status_all);
+/* host copy of what the last gather left on the root's device (rank-major blocks); root only */
+int admpc_batch_get_gathered(admpc_batch *h, double *u_all, double *x_all, int *status_all);
 int admpc_batch_barrier(admpc_batch *h);
 
 /* GP model update on the device (model_fitting/gp.py:283-289,305-311,361-363): for ONE output dimension builds

@@ -32,4 +32,10 @@ if rank == 0:
         assert np.array_equal(u_all[r * B:(r + 1) * B], blocks[r][0]) and np.array_equal(x_all[r * B:(r + 1) * B], blocks[r][1])
         assert np.array_equal(st_all[r * B:(r + 1) * B], blocks[r][2])
     print("GATHER_OK world=%d device-gather %.3f ms" % (world, ms))
+# the blocks left on the root's device can be fetched again without another transfer
+if rank == 0:
+    u2 = np.zeros_like(u_all); x2 = np.zeros_like(x_all); st2 = np.full_like(st_all, -1)
+    _lib.check(L.admpc_batch_get_gathered(s.h, u2.ctypes.data_as(dp), x2.ctypes.data_as(dp), st2.ctypes.data_as(ip)), "get_gathered")
+    assert np.array_equal(u2, u_all) and np.array_equal(x2, x_all) and np.array_equal(st2, st_all)
+    print("GET_GATHERED_OK")
 s.close(); dist.destroy_process_group()
