@@ -35,11 +35,13 @@ __global__ void gpfit_build_kernel(const double *__restrict__ Xs, int M, int Mp,
     A[(size_t)i * Mp + j] = v;
 }
 
-// Cholesky of the diagonal tile (j, j): ONE WARP, lane r owns row r of the tile in registers; the pivot column
-// travels by shuffles (no shared memory, no block barriers: the 32 column steps are the serial part of every block
-// step of the factorisation, so their latency is what matters).
+// Cholesky of the diagonal tile (j, j): ONE WARP, lane r owns row r of the tile in registers; the pivot column is
+// published through a 32-double shared-memory slot and read back as broadcast LDS.128 (no block barriers: the 32
+// column steps are the serial part of every block step of the factorisation, so their latency is what matters).
 __global__ void __launch_bounds__(32) gpfit_potrf32(double *A, int Mp, int jb, int *fail)
 {
+    __shared__ __align__(16) double col[2][TB];      // double-buffered: step k reads buffer k&1 while step k+1 fills the other
+    __shared__ double pv[2];
     const int r = threadIdx.x;
     double *Ajj = A + (size_t)(jb * TB) * Mp + jb * TB;
     double row[TB];
@@ -48,14 +50,18 @@ __global__ void __launch_bounds__(32) gpfit_potrf32(double *A, int Mp, int jb, i
     bool bad = false;
 #pragma unroll
     for (int k = 0; k < TB; k++) {
-        const double piv = __shfl_sync(0xffffffffu, row[k], k);
+        if (r == k) pv[k & 1] = row[k];
+        __syncwarp();
+        const double piv = pv[k & 1];
         bad |= !(piv > 0.0);                       // not positive definite (np.linalg.LinAlgError in the reference)
         const double d = sqrt(piv);
         const double lrk = (r == k) ? d : row[k] / d;          // column k of L (rows >= k)
         row[k] = lrk;
+        if (r > k) col[k & 1][r] = lrk;
+        __syncwarp();
 #pragma unroll
         for (int c = k + 1; c < TB; c++) {
-            const double lck = __shfl_sync(0xffffffffu, lrk, c);
+            const double lck = col[k & 1][c];
             if (r >= c) row[c] = fma(-lrk, lck, row[c]);
         }
     }
@@ -115,56 +121,73 @@ __global__ void __launch_bounds__(256) gpfit_syrk32(double *A, int Mp, int jb, i
     C[0] -= c00; C[1] -= c01; C[Mp] -= c10; C[Mp + 1] -= c11;
 }
 
-// y <- L^-1 y, then y <- L^-T y (blocked by 32, single CTA), plus log-determinant and y0^T alpha
-// (the Mp x Mp factor may sit in the top-left corner of a larger matrix: row stride ldA)
+// y <- L^-1 y, then y <- L^-T y (blocked by 32, single CTA of 32 warps, left-looking), plus log-determinant and
+// y0^T alpha.  Forward: warp w owns row w of the current block row and sweeps its already-solved columns with coalesced
+// 256-byte reads.  Backward: lane c owns column c of the current block column, the warps stride over the rows below it
+// (again one coalesced 256-byte read per row), partial sums meet in shared memory.  The 32x32 diagonal solves stay on
+// warp 0.  (the Mp x Mp factor may sit in the top-left corner of a larger matrix: row stride ldA)
 __global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restrict__ A, int M, int Mp, int ldA, double *y,
                                                             const double *__restrict__ y0, double *out2)
 {
     __shared__ double xb[TB];
+    __shared__ double part[TB][TB + 1];
     __shared__ double red[32];
-    const int nb = Mp / TB, t = threadIdx.x;
+    const int nb = Mp / TB, t = threadIdx.x, w = t >> 5, l = t & 31;
     // forward: L z = y
     for (int b = 0; b < nb; b++) {
-        if (t < 32) {
-            double v = y[b * TB + t];
-            for (int c = 0; c < TB; c++) {
-                const double lcc = A[(size_t)(b * TB + c) * ldA + b * TB + c];
-                const double xc = __shfl_sync(0xffffffffu, v, c) / lcc;
-                if (t == c) v = xc;
-                else if (t > c) v = fma(-A[(size_t)(b * TB + t) * ldA + b * TB + c], xc, v);
-            }
-            xb[t] = v;
-            y[b * TB + t] = v;
+        {
+            const double *row = A + (size_t)(b * TB + w) * ldA;
+            double s = 0.0;
+            for (int c = l; c < b * TB; c += 32) s = fma(row[c], y[c], s);
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (l == 0) xb[w] = y[b * TB + w] - s;
         }
         __syncthreads();
-        for (int i = (b + 1) * TB + t; i < Mp; i += blockDim.x) {
-            const double *row = A + (size_t)i * ldA + b * TB;
-            double s = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < TB; c++) s = fma(row[c], xb[c], s);
-            y[i] -= s;
+        if (t < 32) {
+            // diagonal block: row t in registers first (all 32 loads in flight at once), then 32 shuffle steps
+            double Lr[TB];
+#pragma unroll
+            for (int c = 0; c < TB; c++) Lr[c] = A[(size_t)(b * TB + t) * ldA + b * TB + c];
+            double dinv = 0.0;
+#pragma unroll
+            for (int c = 0; c < TB; c++) if (t == c) dinv = 1.0 / Lr[c];
+            double v = xb[t];
+#pragma unroll
+            for (int c = 0; c < TB; c++) {
+                const double xc = __shfl_sync(0xffffffffu, v * dinv, c);
+                if (t == c) v = xc;
+                else if (t > c) v = fma(-Lr[c], xc, v);
+            }
+            y[b * TB + t] = v;
         }
         __syncthreads();
     }
     // backward: L^T alpha = z
     for (int b = nb - 1; b >= 0; b--) {
-        if (t < 32) {
-            double v = y[b * TB + t];
-            for (int c = TB - 1; c >= 0; c--) {
-                const double lcc = A[(size_t)(b * TB + c) * ldA + b * TB + c];
-                const double xc = __shfl_sync(0xffffffffu, v, c) / lcc;
-                if (t == c) v = xc;
-                else if (t < c) v = fma(-A[(size_t)(b * TB + c) * ldA + b * TB + t], xc, v);
-            }
-            xb[t] = v;
-            y[b * TB + t] = v;
+        {
+            double s = 0.0;
+            for (int i = (b + 1) * TB + w; i < Mp; i += 32) s = fma(A[(size_t)i * ldA + b * TB + l], y[i], s);
+            part[w][l] = s;
         }
         __syncthreads();
-        for (int i = t; i < b * TB; i += blockDim.x) {
+        if (t < 32) {
             double s = 0.0;
 #pragma unroll 8
-            for (int r = 0; r < TB; r++) s = fma(A[(size_t)(b * TB + r) * ldA + i], xb[r], s);
-            y[i] -= s;
+            for (int q = 0; q < TB; q++) s += part[q][t];
+            double v = y[b * TB + t] - s;
+            double Lc[TB];                       // column t of the diagonal block (coalesced across lanes)
+#pragma unroll
+            for (int c = 0; c < TB; c++) Lc[c] = A[(size_t)(b * TB + c) * ldA + b * TB + t];
+            double dinv = 0.0;
+#pragma unroll
+            for (int c = 0; c < TB; c++) if (t == c) dinv = 1.0 / Lc[c];
+#pragma unroll
+            for (int c = TB - 1; c >= 0; c--) {
+                const double xc = __shfl_sync(0xffffffffu, v * dinv, c);
+                if (t == c) v = xc;
+                else if (t < c) v = fma(-Lc[c], xc, v);
+            }
+            y[b * TB + t] = v;
         }
         __syncthreads();
     }
