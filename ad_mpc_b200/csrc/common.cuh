@@ -77,6 +77,21 @@ struct Params {
 
 void admpc_set_error(const char *what, const char *msg);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: remember the largest size configured on each
+// device of the process (handles on several GPUs in one process are legal).
+struct SmemGuard {
+    size_t done[64] = {};
+    bool need(size_t bytes)
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (bytes <= done[d]) return false;
+        done[d] = bytes;
+        return true;
+    }
+};
+
 // kernel launchers (defined in the .cu files)
 void launch_prepare(const Params &P, cudaStream_t s);
 void launch_qp(const Params &P, cudaStream_t s);

@@ -651,10 +651,9 @@ void launch_prepare_dense(const Params &P, cudaStream_t s)
     dim3 grid((P.B + 127) / 128, P.o.N + 1);
     if (P.o.gp_enabled) {
         const size_t sm = (size_t)P.gp.bytes;
-        static size_t configured = 0;
-        if (sm > configured) {
+        static SmemGuard configured;
+        if (configured.need(sm)) {
             cudaFuncSetAttribute(prepare_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            configured = sm;
         }
         prepare_dense_kernel<true><<<grid, 128, sm, s>>>(P);
     } else {

@@ -200,11 +200,10 @@ void launch_prepare(const Params &P, cudaStream_t s)
         const size_t sm = (size_t)P.gp.bytes;
 #define LAUNCH_PREP(BOUND, MINB, BLK)                                                                                    \
     do {                                                                                                                \
-        static size_t configured = 0;                                                                                   \
-        if (sm > configured) {                                                                                          \
+        static SmemGuard configured;                                                                                   \
+        if (configured.need(sm)) {                                                                                          \
             cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
             cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-            configured = sm;                                                                                            \
         }                                                                                                               \
         dim3 grid((P.Bp + (BLK) - 1) / (BLK), P.o.N + 1);                                                               \
         if (P.gp.n_models > 1) prepare_kernel<true, BOUND, MINB, true><<<grid, (BLK), sm, s>>>(P);                      \

@@ -654,10 +654,9 @@ bool launch_qp_smem(const Params &P, cudaStream_t s)
 {
     const size_t sm = qp_smem_bytes(P.o.N);
     if (sm > 227 * 1024) return false;
-    static size_t configured = 0;
-    if (sm > configured) {
+    static SmemGuard configured;
+    if (configured.need(sm)) {
         cudaFuncSetAttribute(qp_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        configured = sm;
     }
     qp_smem_kernel<<<P.Bp / 4, 32, sm, s>>>(P);
     return true;

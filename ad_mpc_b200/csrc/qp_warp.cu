@@ -754,18 +754,16 @@ bool launch_qp_warp(const Params &P, cudaStream_t s)
     if (N > 63) return false;
     if (N <= 31) {
         const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE) * sizeof(double);
-        static size_t configured = 0;
-        if (sm > configured) {
+        static SmemGuard configured;
+        if (configured.need(sm)) {
             cudaFuncSetAttribute(qp_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            configured = sm;
         }
         qp_warp_kernel<1><<<P.B, 32, sm, s>>>(P);
     } else {
         const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE + XCH_SIZE) * sizeof(double);
-        static size_t configured2 = 0;
-        if (sm > configured2) {
+        static SmemGuard configured2;
+        if (configured2.need(sm)) {
             cudaFuncSetAttribute(qp_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            configured2 = sm;
         }
         qp_warp_kernel<2><<<P.B, 64, sm, s>>>(P);
     }

@@ -474,3 +474,24 @@ def test_acados_shim_sqp_mode():
     u = np.stack([cap.get(j, "u") for j in range(N)])
     assert mixed_err(u, r["u"][0]) <= TOL
     cap.free() if hasattr(cap, "free") else None
+
+
+def test_two_devices_in_one_process():
+    """Handles on different GPUs of one process (per-device kernel attributes, per-handle streams); skipped on 1-GPU boxes."""
+    from ad_mpc_b200 import _lib
+    if _lib.load().admpc_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    B, N = 40, 40
+    batch = wl.make_batch(B, N, seed=55, p=1.0)
+    model = wl.make_gp(M=1500, seed=9)                      # > 48 KB of dynamic shared memory on both devices
+    opts = default_opts(N)
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    r = oracle_batch(o, batch, gp=gp)
+    for dev in (0, 1, 0):
+        s = BatchSolver(B, opts, device=dev)
+        s.set_gp(model)
+        g = _gpu_step(s, batch)
+        _compare(g, r)
+        s.close()
