@@ -119,8 +119,8 @@ struct admpc_batch {
     size_t track_cap = 0;
     int track_L = 0, track_H = 0, track_stop = 0, track_anchor = 0;
     double track_dt = 0.0;
-    cudaEvent_t ev[8];
-    cudaEvent_t tm0, tm1;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     bool profiling = false;
     bool gps_set = false;
     int qp_variant = 0;      // 0 auto(=4), 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu)
@@ -137,6 +137,13 @@ static size_t gp_stride(int M, int dz) { return rup((size_t)M * (dz + 2) + dz + 
 // whole blob: nout outputs, then the 2^(j/GP_TAB) table of the device exp2 (model.cuh)
 static size_t gp_blob_doubles(int nout, int M, int dz) { return gp_stride(M, dz) * nout + GP_TAB; }
 
+extern "C" int admpc_batch_free(admpc_batch *h);
+// inside create: a failed CUDA call releases what was allocated so far
+#define CREATE_CK(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) { admpc_set_error(#call, cudaGetErrorString(e_)); admpc_batch_free(h); return ADMPC_E_CUDA; } \
+    } while (0)
 extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, admpc_batch **out)
 {
     if (!opts || !out || B <= 0 || opts->N < 2 || opts->N > ADMPC_NMAX) { admpc_set_error("admpc_batch_create", "bad argument"); return ADMPC_E_ARG; }
@@ -156,10 +163,10 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     P.B = B;
     P.Bp = (int)rup((size_t)B, 32);
     const size_t Bp = P.Bp;
-    CUDA_CHECK_RET(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (auto &e : h->ev) CUDA_CHECK_RET(cudaEventCreate(&e));
-    CUDA_CHECK_RET(cudaEventCreate(&h->tm0));
-    CUDA_CHECK_RET(cudaEventCreate(&h->tm1));
+    CREATE_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev) CREATE_CK(cudaEventCreate(&e));
+    CREATE_CK(cudaEventCreate(&h->tm0));
+    CREATE_CK(cudaEventCreate(&h->tm1));
 
     // carve the pool
     struct Item { double **p; size_t rows; };
@@ -191,40 +198,43 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     }
     size_t rows = 0;
     for (auto &it : items) rows += it.rows;
-    CUDA_CHECK_RET(cudaMalloc(&h->pool, rows * Bp * sizeof(double)));
-    CUDA_CHECK_RET(cudaMemsetAsync(h->pool, 0, rows * Bp * sizeof(double), h->stream));
+    CREATE_CK(cudaMalloc(&h->pool, rows * Bp * sizeof(double)));
+    CREATE_CK(cudaMemsetAsync(h->pool, 0, rows * Bp * sizeof(double), h->stream));
     size_t off = 0;
     for (auto &it : items) { *it.p = h->pool + off * Bp; off += it.rows; }
     P.x0 = x0; P.yref = yref; P.p = pp; P.gps = gps; P.kappa = kap;
-    CUDA_CHECK_RET(cudaMalloc(&h->ipool, (7 * Bp + 32) * sizeof(int)));
-    CUDA_CHECK_RET(cudaMemsetAsync(h->ipool, 0, (7 * Bp + 32) * sizeof(int), h->stream));
+    CREATE_CK(cudaMalloc(&h->ipool, (7 * Bp + 32) * sizeof(int)));
+    CREATE_CK(cudaMemsetAsync(h->ipool, 0, (7 * Bp + 32) * sizeof(int), h->stream));
     P.status = h->ipool; P.qp_status = h->ipool + Bp; P.qp_iter = h->ipool + 2 * Bp; P.lin_bad = h->ipool + 3 * Bp;
     P.sqp_status = h->ipool + 4 * Bp; P.sqp_iter = h->ipool + 5 * Bp;
     h->gp_sel = h->ipool + 6 * Bp; P.gp_sel = h->gp_sel;
     h->sqp_active = h->ipool + 7 * Bp;                       // per-iteration counters of still-running instances
     // instance-major staging areas
     const size_t in_rows = (size_t)N * 49 > (size_t)N * 9 + 7 ? (size_t)N * 49 : (size_t)N * 9 + 7;
-    CUDA_CHECK_RET(cudaMalloc(&h->stage_in, in_rows * Bp * sizeof(double)));
-    CUDA_CHECK_RET(cudaMalloc(&h->stage_u, nU * Bp * sizeof(double)));
-    CUDA_CHECK_RET(cudaMalloc(&h->stage_x, nX * Bp * sizeof(double)));
-    CUDA_CHECK_RET(cudaMalloc(&h->stage_misc, (size_t)N * 49 * Bp * sizeof(double)));
-    CUDA_CHECK_RET(cudaMalloc(&h->stage_status, 3 * Bp * sizeof(int)));
-    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    CREATE_CK(cudaMalloc(&h->stage_in, in_rows * Bp * sizeof(double)));
+    CREATE_CK(cudaMalloc(&h->stage_u, nU * Bp * sizeof(double)));
+    CREATE_CK(cudaMalloc(&h->stage_x, nX * Bp * sizeof(double)));
+    CREATE_CK(cudaMalloc(&h->stage_misc, (size_t)N * 49 * Bp * sizeof(double)));
+    CREATE_CK(cudaMalloc(&h->stage_status, 3 * Bp * sizeof(int)));
+    CREATE_CK(cudaStreamSynchronize(h->stream));
     *out = h;
     return 0;
 }
+#undef CREATE_CK
 
 extern "C" int admpc_batch_free(admpc_batch *h)
 {
     if (!h) return ADMPC_E_ARG;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
     cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack);
-    for (auto &e : h->ev) cudaEventDestroy(e);
-    cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
-    cudaStreamDestroy(h->stream);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->tm0) cudaEventDestroy(h->tm0);
+    if (h->tm1) cudaEventDestroy(h->tm1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();          // a partially created handle may have produced benign errors above: do not leave them behind
     delete h;
     return 0;
 }
