@@ -1030,6 +1030,7 @@ struct sim_car_solver_capsule {
     int N = 0;
     std::vector<double> x0, yref, p, kappa, x, u, pi, lam, t, sl, su;
     bool iterate_dirty = false, duals_stale = false;
+    double *hio = nullptr, *dio = nullptr;      // pinned host / device staging blocks of the single-instance fast path
     int status = 0, qp_status = 0, qp_iter = 0, sqp_iter = 1;
     bool nlp_sqp = false;            // nlp_solver_type: false "SQP_RTI" (shipped), true "SQP" (point-reference mode)
     int nlp_max_iter = 100;          // sim_car_acados_ocp.json:868
@@ -1117,6 +1118,8 @@ extern "C" int sim_car_acados_reset(sim_car_solver_capsule *c, int)
 extern "C" int sim_car_acados_free(sim_car_solver_capsule *c)
 {
     if (!c) return ADMPC_E_ARG;
+    if (c->hio) { cudaFreeHost(c->hio); c->hio = nullptr; }
+    if (c->dio) { cudaFree(c->dio); c->dio = nullptr; }
     int r = c->h ? admpc_batch_free(c->h) : 0;
     c->h = nullptr;
     return r;
@@ -1161,6 +1164,45 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
     if (!c || !c->h) { admpc_set_error("sim_car_acados_solve", "solver not created"); return ADMPC_E_STATE; }
     admpc_batch *h = c->h;
     int r;
+    if (!c->nlp_sqp) {
+        // RTI fast path: ONE packed host->device block, ONE packed device->host block, one synchronisation
+        const int N = c->N, nyr = 9 * N + 7, nx = (N + 1) * 7, nu = 2 * N;
+        const size_t nin = (size_t)7 + nyr + N + N + nx + nu, nout = (size_t)nx + nu + 7;
+        if (!c->hio) {
+            CUDA_CHECK_RET(cudaSetDevice(h->device));
+            CUDA_CHECK_RET(cudaHostAlloc((void **)&c->hio, (nin + nout) * sizeof(double), cudaHostAllocDefault));
+            CUDA_CHECK_RET(cudaMalloc(&c->dio, (nin + nout) * sizeof(double)));
+        }
+        double *hi = c->hio, *ho = c->hio + nin;
+        memcpy(hi, c->x0.data(), 7 * sizeof(double));
+        memcpy(hi + 7, c->yref.data(), nyr * sizeof(double));
+        memcpy(hi + 7 + nyr, c->p.data(), N * sizeof(double));
+        memcpy(hi + 7 + nyr + N, c->kappa.data(), N * sizeof(double));
+        const bool wit = c->iterate_dirty;
+        if (wit) {
+            memcpy(hi + 7 + nyr + 2 * N, c->x.data(), nx * sizeof(double));
+            memcpy(hi + 7 + nyr + 2 * N + nx, c->u.data(), nu * sizeof(double));
+        }
+        CUDA_CHECK_RET(cudaSetDevice(h->device));
+        if ((r = admpc_batch_timer_start(h))) return r;
+        CUDA_CHECK_RET(cudaMemcpyAsync(c->dio, hi, (wit ? nin : (size_t)7 + nyr + 2 * N) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_capsule_scatter(h->P, c->dio, c->opts.model_variant == 1, wit, h->stream);
+        c->iterate_dirty = false;
+        if ((r = admpc_batch_solve(h))) return r;
+        launch_capsule_gather(h->P, c->dio + nin, h->stream);
+        h->launches += 2;
+        CUDA_CHECK_RET(cudaMemcpyAsync(ho, c->dio + nin, nout * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        float ms = 0;
+        if ((r = admpc_batch_timer_stop(h, &ms))) return r;          // synchronises the stream
+        c->time_tot = ms * 1e-3;
+        memcpy(c->x.data(), ho, nx * sizeof(double));
+        memcpy(c->u.data(), ho + nx, nu * sizeof(double));
+        memcpy(c->res, ho + nx + nu, 4 * sizeof(double));
+        c->status = (int)ho[nx + nu + 4]; c->qp_status = (int)ho[nx + nu + 5]; c->qp_iter = (int)ho[nx + nu + 6];
+        c->duals_stale = true;
+        c->sqp_iter = 1;
+        return c->status;
+    }
     if ((r = admpc_batch_timer_start(h))) return r;
     if ((r = admpc_batch_set_x0(h, c->x0.data()))) return r;
     if ((r = admpc_batch_set_yref(h, c->yref.data()))) return r;

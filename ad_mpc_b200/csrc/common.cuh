@@ -105,6 +105,8 @@ void launch_update(const Params &P, cudaStream_t s);
 void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
 double run_fp64_peak(int device, int nint);
 void launch_prepare_dense(const Params &P, cudaStream_t s);
+void launch_capsule_scatter(const Params &P, const double *in, int with_kappa, int with_iterate, cudaStream_t s);
+void launch_capsule_gather(const Params &P, double *out, cudaStream_t s);
 void launch_gp_select(const Params &P, const double *xq, const double *uq, int *sel, cudaStream_t s);
 void launch_qp_dense(const Params &P, cudaStream_t s);
 void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);

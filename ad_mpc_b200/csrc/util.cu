@@ -68,6 +68,51 @@ void launch_fill(double *dst, size_t n, double v, cudaStream_t s)
     fill_kernel<<<148 * 8, 256, 0, s>>>(dst, n, v);
 }
 
+// ---- single-instance fast path of the acados shim: one packed block in, one packed block out ------------------------
+// in : [x0 7 | yref 9N+7 | p N | kappa N | x (N+1)*7 | u 2N]   (kappa / iterate sections used on demand)
+// out: [x (N+1)*7 | u 2N | res 4 | status qp_status qp_iter (as doubles)]
+__global__ void capsule_scatter_kernel(const Params P, const double *__restrict__ in, int with_kappa, int with_iterate)
+{
+    const int N = P.o.N, Bp = P.Bp;
+    const int nyr = 9 * N + 7, nx = (N + 1) * 7, nu = 2 * N;
+    const int tot = 7 + nyr + N + N + nx + nu;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        int r = e;
+        if (r < 7) { ((double *)P.x0)[(size_t)r * Bp] = in[e]; continue; }
+        r -= 7;
+        if (r < nyr) { ((double *)P.yref)[(size_t)r * Bp] = in[e]; continue; }
+        r -= nyr;
+        if (r < N) { ((double *)P.p)[(size_t)r * Bp] = in[e]; continue; }
+        r -= N;
+        if (r < N) { if (with_kappa) ((double *)P.kappa)[(size_t)r * Bp] = in[e]; continue; }
+        r -= N;
+        if (!with_iterate) continue;
+        if (r < nx) { P.xb[(size_t)r * Bp] = in[e]; continue; }
+        r -= nx;
+        P.ub[(size_t)r * Bp] = in[e];
+    }
+}
+__global__ void capsule_gather_kernel(const Params P, double *__restrict__ out)
+{
+    const int N = P.o.N, Bp = P.Bp;
+    const int nx = (N + 1) * 7, nu = 2 * N;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nx + nu + 7; e += gridDim.x * blockDim.x) {
+        int r = e;
+        if (r < nx) { out[e] = P.xb[(size_t)r * Bp]; continue; }
+        r -= nx;
+        if (r < nu) { out[e] = P.ub[(size_t)r * Bp]; continue; }
+        r -= nu;
+        if (r < 4) { out[e] = P.res_out[(size_t)r * Bp]; continue; }
+        r -= 4;
+        out[e] = (double)((r == 0) ? P.status[0] : (r == 1) ? P.qp_status[0] : P.qp_iter[0]);
+    }
+}
+void launch_capsule_scatter(const Params &P, const double *in, int with_kappa, int with_iterate, cudaStream_t s)
+{
+    capsule_scatter_kernel<<<4, 256, 0, s>>>(P, in, with_kappa, with_iterate);
+}
+void launch_capsule_gather(const Params &P, double *out, cudaStream_t s) { capsule_gather_kernel<<<2, 256, 0, s>>>(P, out); }
+
 // ---- GP ensemble: nearest-centroid model choice per instance (GPEnsemble.select_gp, model_fitting/gp.py:738-770) -----
 // z = B_z [x; u] from the query state / input (SoA rows), distance sqrt(sum (z - c)^2) like the reference, first minimum
 __global__ void gp_select_kernel(const Params P, const double *__restrict__ xq, const double *__restrict__ uq, int *sel)
