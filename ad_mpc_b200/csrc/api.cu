@@ -441,7 +441,14 @@ extern "C" int admpc_batch_reset(admpc_batch *h)
 static int launch_feedback(admpc_batch *h)
 {
     const Params &P = h->P;
-    if (P.o.model_variant == 1) {        // Frenet variant: dense stage matrices, generic kernel + separate update
+    if (P.o.model_variant == 1) {
+        // Frenet variant: warp-per-instance kernel on the 6x8 stage structure (N <= 63, fused update), else / on request
+        // (ADMPC_QP_VARIANT=1) the dense thread-per-instance kernel + separate update
+        if (h->qp_variant != 1 && launch_qp_warp_f(P, h->stream)) {
+            if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
+            h->launches += 1;
+            return 0;
+        }
         launch_qp_dense(P, h->stream);
         if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
         launch_update(P, h->stream);

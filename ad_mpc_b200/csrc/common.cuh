@@ -109,6 +109,7 @@ void launch_capsule_scatter(const Params &P, const double *in, int with_kappa, i
 void launch_capsule_gather(const Params &P, double *out, cudaStream_t s);
 void launch_gp_select(const Params &P, const double *xq, const double *uq, int *sel, cudaStream_t s);
 void launch_qp_dense(const Params &P, cudaStream_t s);
+bool launch_qp_warp_f(const Params &P, cudaStream_t s);   // Frenet structure, false: N > 63
 void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_sqp_finalize(const Params &P, cudaStream_t s);

@@ -140,7 +140,7 @@ int admpc_batch_set_p(admpc_batch *h, const double *p /*[B][N]*/);
 int admpc_batch_set_p_scalar(admpc_batch *h, const double *p /*[B]*/);      /* same switch on all stages (:449-450) */
 /* Frenet variant only (opts.model_variant == 1): path curvature kappa[B][N] at every shooting node (default 0; the
  * reference evaluates a B-spline kappa(s) inside the model, fren_ad_3d_optimizer bytecode).  With kappa = 0 the variant
- * coincides with the Cartesian model.  The variant runs dense, unstructured kernels (csrc/frenet.cu), full SQP mode
+ * coincides with the Cartesian model.  Kernels: csrc/frenet.cu (preparation) and csrc/qp_warp_f.cu (feedback), full SQP mode
  * included; the device reference generator and the closed-loop plant are Cartesian-only (ADMPC_E_UNSUPPORTED). */
 int admpc_batch_set_kappa(admpc_batch *h, const double *kappa);
 int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state /*[B][7] or NULL = x0*/);

@@ -119,3 +119,56 @@ def test_frenet_through_the_acados_shim():
     r = orc.rti_batch(mirror_opts(opts), b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"], kappa=b["kappa"])
     u = np.stack([cap.get(j, "u") for j in range(N)])
     assert mixed_err(u, r["u"][0]) <= TOL
+
+
+def test_frenet_kernel_variants_agree(monkeypatch):
+    """The warp-per-instance Frenet kernel (6x8 stage structure, default for N <= 63) and the dense thread-per-instance
+    kernel (ADMPC_QP_VARIANT=1, also the N > 63 fallback) are independent implementations: same statuses / iteration
+    counts, 1e-8 agreement, on a batch with active bounds; and the long-horizon fallback against the oracle."""
+    B, N = 64, 20
+    batch = wl.make_batch_frenet(B, N, seed=350, p=0.7, perturb=5.0)
+    rng = np.random.default_rng(1)
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([1.5, 0.5])
+    out = {}
+    for v in (4, 1):
+        monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
+        s = BatchSolver(B, default_opts(N, model_variant=1, lbu=[-3.0, -1.0], ubu=[2.0, 1.0]))
+        out[v] = _step(s, batch, kappa=batch["kappa"])
+        s.close()
+    assert np.array_equal(out[1]["qp_iter"], out[4]["qp_iter"]) and np.array_equal(out[1]["status"], out[4]["status"])
+    assert mixed_err(out[1]["u"], out[4]["u"]) <= TOL and mixed_err(out[1]["x"], out[4]["x"]) <= TOL
+    monkeypatch.delenv("ADMPC_QP_VARIANT")
+    for Nl in (31, 32, 63, 70):
+        bl = wl.make_batch_frenet(10, Nl, seed=360 + Nl, p=1.0, perturb=2.0)
+        opts = default_opts(Nl, model_variant=1)
+        s = BatchSolver(10, opts)
+        g = _step(s, bl, kappa=bl["kappa"])
+        r = orc.rti_batch(mirror_opts(opts), bl["x0"], bl["yref"], bl["p"], bl["x_init"], bl["u_init"], kappa=bl["kappa"])
+        assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_iter"], r["qp_iter"]), Nl
+        assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL, Nl
+        s.close()
+
+
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_frenet_random_settings(seed):
+    """Randomised weights / bounds / horizon / curvature on the Frenet variant (see test_gpu_fuzz.py for the Cartesian twin)."""
+    rng = np.random.default_rng(9500 + seed)
+    N = int(rng.choice([6, 20, 31, 40, 66]))
+    q = list(rng.choice([0.0, 1.0, 10.0, 100.0], size=7))
+    kw = dict(dt=float(rng.choice([0.02, 0.05, 0.1])), W=q + list(rng.choice([0.1, 10.0], size=2)), We=[0.01 * v for v in q],
+              lbu=[-float(rng.uniform(0.5, 10)), -float(rng.uniform(0.2, 3))], ubu=[float(rng.uniform(0.5, 5)), float(rng.uniform(0.2, 3))],
+              lbx=-float(rng.uniform(0.05, 0.6)), ubx=float(rng.uniform(0.05, 0.6)), iter_max=int(rng.choice([3, 50])),
+              model_variant=1)
+    B = 20
+    batch = wl.make_batch_frenet(B, N, seed=200 + seed, dt=kw["dt"], p=float(rng.choice([0.0, 1.0])), perturb=float(rng.choice([1.0, 6.0])),
+                                 radius=float(rng.choice([15.0, 50.0, 400.0])))
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([0.5, 0.1])
+    opts = default_opts(N, **kw)
+    s = BatchSolver(B, opts)
+    g = _step(s, batch, kappa=batch["kappa"])
+    r = orc.rti_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=batch["kappa"])
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_status"], r["qp_status"])
+    assert np.array_equal(g["qp_iter"], r["qp_iter"])
+    ok = r["status"] == 0
+    assert mixed_err(g["u"][ok], r["u"][ok]) <= TOL and mixed_err(g["x"][ok], r["x"][ok]) <= TOL
+    s.close()
