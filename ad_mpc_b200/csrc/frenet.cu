@@ -68,7 +68,7 @@ __device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *g
 __device__ __forceinline__ uint32_t fr_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool GP>
-__global__ void __launch_bounds__(128) prepare_dense_kernel(const Params P)
+__global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
