@@ -314,6 +314,30 @@ def run_ours(args):
     e2e_pose = B / (sum(pose_ms) / len(pose_ms) * 1e-3)
     ps.close()
 
+    # ---- the same step on the Frenet-frame model variant (SURVEY 8a A2'; rank 0, reported beside the headline) --------
+    frenet = None
+    if rank == 0:
+        from ad_mpc_b200 import workload as wlf
+        fb = wlf.make_batch_frenet(B, N, seed=20263, p=1.0)
+        fs = BatchSolver(B, default_opts(N, model_variant=1), device=local)
+        fs.set_gp(model)
+        fs.set_x0(fb["x0"]); fs.set_yref(fb["yref"]); fs.set_p(fb["p"]); fs.set_kappa(fb["kappa"])
+        f_ms = []
+        for it in range(3 + args.steps):
+            fs.set_iterate(fb["x_init"], fb["u_init"])
+            fs.flush_l2()
+            fs.timer_start()
+            fs.solve()
+            ms = fs.timer_stop()
+            if it >= 3:
+                f_ms.append(ms)
+        fst = fs.get_status()[0]
+        frenet = {"value": B / (statistics.mean(f_ms) * 1e-3), "unit": "solves/s", "ms_per_step": statistics.mean(f_ms),
+                  "ok": bool((fst == 0).all()),
+                  "note": "Frenet-frame model variant (model_variant=1, curvature per node), same batch size / horizon / GP, "
+                          "device-resident inputs, one GPU"}
+        fs.close()
+
     # ---- single-instance latency through the acados-shim symbols (cfg 1: nominal, N=20, B=1) ---------------------
     single_ms = []
     if rank == 0:
@@ -389,7 +413,7 @@ def run_ours(args):
                                               "note": "same call with the reference generated on the device from "
                                                       "vehicle states (refgen_kernel, anchored mode); rank 0"}},
                 "gpu_launches": counted, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "wall_s_timed_region": wall,
+                "wall_s_timed_region": wall, "frenet_variant": frenet,
                 "latency": {"p50_ms_per_batch_solve": sorted(step_ms)[len(step_ms) // 2], "batch": B,
                             "p99_ms_per_batch_solve": sorted(step_ms)[min(len(step_ms) - 1, int(0.99 * len(step_ms)))],
                             "single_instance_p50_ms": single_ms[len(single_ms) // 2] if single_ms else None,
