@@ -325,6 +325,28 @@ class PipelinedSolver:
         for s, (lo, hi) in zip(self.parts, self.ranges):
             s.set_iterate(None if x is None else x[lo:hi], None if u is None else u[lo:hi])
 
+    def set_gp_ensemble(self, models, centroids=None, stage0_trigger=1):
+        return [s.set_gp_ensemble(models, centroids=centroids, stage0_trigger=stage0_trigger) for s in self.parts][0]
+
+    def select_gp(self, x=None, u=None):
+        return np.concatenate([s.select_gp(None if x is None else x[lo:hi], None if u is None else u[lo:hi])
+                               for s, (lo, hi) in zip(self.parts, self.ranges)])
+
+    def set_gp_index(self, idx):
+        idx = np.broadcast_to(np.asarray(idx, dtype=np.int32).reshape(-1), (self.B,))
+        for s, (lo, hi) in zip(self.parts, self.ranges):
+            s.set_gp_index(idx[lo:hi])
+
+    def set_gp_state(self, gp_state):
+        for s, (lo, hi) in zip(self.parts, self.ranges):
+            s.set_gp_state(None if gp_state is None else gp_state[lo:hi])
+
+    def set_kappa(self, kappa):
+        """Frenet variant: kappa [B, N] (or [B])."""
+        k = np.asarray(kappa, dtype=np.float64)
+        for s, (lo, hi) in zip(self.parts, self.ranges):
+            s.set_kappa(k[lo:hi])
+
     def wait(self):
         for s in self.parts:
             s.wait()

@@ -172,3 +172,19 @@ def test_frenet_random_settings(seed):
     ok = r["status"] == 0
     assert mixed_err(g["u"][ok], r["u"][ok]) <= TOL and mixed_err(g["x"][ok], r["x"][ok]) <= TOL
     s.close()
+
+
+def test_frenet_through_the_pipelined_host_call():
+    """PipelinedSolver (the public batched call with host buffers) on the Frenet variant == resident BatchSolver."""
+    from ad_mpc_b200 import PipelinedSolver
+    B, N = 300, 20
+    batch = wl.make_batch_frenet(B, N, seed=370, p=1.0, perturb=2.0)
+    opts = default_opts(N, model_variant=1)
+    ps = PipelinedSolver(B, opts, chunks=3)
+    ps.set_iterate(batch["x_init"], batch["u_init"]); ps.set_kappa(batch["kappa"])
+    u, x, st = np.empty((B, N, 2)), np.empty((B, N + 1, 7)), np.empty(B, dtype=np.int32)
+    ps.solve_batch(np.ascontiguousarray(batch["x0"]), np.ascontiguousarray(batch["yref"]), np.ascontiguousarray(batch["p"][:, 0]), u, x, st)
+    s = BatchSolver(B, opts)
+    g = _step(s, batch, kappa=batch["kappa"])
+    assert np.array_equal(st, g["status"]) and np.array_equal(u, g["u"]) and np.array_equal(x, g["x"])
+    ps.close(); s.close()
