@@ -427,11 +427,20 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
         return;                                  // 2: finished instance of the full-SQP loop, nothing to do
     }
     // ---- stage M into shared memory ------------------------------------------------------------------------------------
-    for (int e = threadIdx.x; e < 42 * N; e += 32 * NW) {
-        const int k = e / 42, w = e - k * 42;
-        const int cc = w / 6, r = w - cc * 6;
-        const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp;
-        sm[k * R_STRIDE + R_M + w] = (cc < 2) ? ATS(lin, LIN_B + r * 2 + cc) : ATS(lin, LIN_A + r * 5 + (cc - 2));
+    // entry w = cc*6 + r of a stage (cc < 2: B(r,cc), else A(r,cc)) on lane w and lane w - 32; the source row of each lane
+    // is fixed, the loop over the stages is two loads + two stores with pointer increments (all loads in flight at once)
+    {
+        const int w0 = l, w1 = (l + 32 < 42) ? l + 32 : 41;
+        const int c0 = w0 / 6, r0 = w0 - c0 * 6, c1 = w1 / 6, r1 = w1 - c1 * 6;
+        const int s0 = (c0 < 2) ? LIN_B + r0 * 2 + c0 : LIN_A + r0 * 5 + (c0 - 2);
+        const int s1 = (c1 < 2) ? LIN_B + r1 * 2 + c1 : LIN_A + r1 * 5 + (c1 - 2);
+        const double *g0 = P.lin + (size_t)s0 * Bp + i, *g1 = P.lin + (size_t)s1 * Bp + i;
+        const size_t gstep = (size_t)LIN_ROWS * Bp;
+        for (int k = wrp; k < N; k += NW) {
+            const double v0 = g0[(size_t)k * gstep], v1 = g1[(size_t)k * gstep];
+            sm[k * R_STRIDE + R_M + w0] = v0;
+            if (l < 10) sm[k * R_STRIDE + R_M + w1] = v1;
+        }
     }
     // ---- stage role: load this node's data, cold start ---------------------------------------------------------------------
     const int k = threadIdx.x;

@@ -434,12 +434,20 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_f_kernel(const Param
         return;                                  // 2: finished instance of the full-SQP loop, nothing to do
     }
     // ---- stage M into shared memory ------------------------------------------------------------------------------------
-    for (int e = threadIdx.x; e < 48 * N; e += 32 * NW) {
-        const int k = e / 48, w = e - k * 48;
-        const int cc = w / 6, r = w - cc * 6;
-        const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
-        // M-column cc: 0,1 -> B(:,cc) ; 2..7 -> A(:, cc-1), i.e. the state columns e_y .. delta
-        sm[k * R_STRIDE + R_M + w] = (cc < 2) ? ATS(lin, DL_B + r * 2 + cc) : ATS(lin, DL_A + r * 7 + (cc - 1));
+    // entry w = cc*6 + r of a stage (M-column cc: 0,1 -> B(:,cc) ; 2..7 -> A(:, cc-1), the state columns e_y .. delta) on
+    // lane w and lane w - 32; fixed source rows per lane, the stage loop is two loads + two stores
+    {
+        const int w0 = l, w1 = (l + 32 < 48) ? l + 32 : 47;
+        const int c0 = w0 / 6, r0 = w0 - c0 * 6, c1 = w1 / 6, r1 = w1 - c1 * 6;
+        const int s0 = (c0 < 2) ? DL_B + r0 * 2 + c0 : DL_A + r0 * 7 + (c0 - 1);
+        const int s1 = (c1 < 2) ? DL_B + r1 * 2 + c1 : DL_A + r1 * 7 + (c1 - 1);
+        const double *g0 = P.lin_d + (size_t)s0 * Bp + i, *g1 = P.lin_d + (size_t)s1 * Bp + i;
+        const size_t gstep = (size_t)DL_ROWS * Bp;
+        for (int k = wrp; k < N; k += NW) {
+            const double v0 = g0[(size_t)k * gstep], v1 = g1[(size_t)k * gstep];
+            sm[k * R_STRIDE + R_M + w0] = v0;
+            if (l < 16) sm[k * R_STRIDE + R_M + w1] = v1;
+        }
     }
     // ---- stage role: load this node's data, cold start ---------------------------------------------------------------------
     const int k = threadIdx.x;
