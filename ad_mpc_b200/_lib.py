@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libadmpc_b200.so")
+SO_PATH = os.environ.get("ADMPC_LIB") or os.path.join(HERE, "libadmpc_b200.so")   # ADMPC_LIB: kernel-variant builds (scripts/)
 
 DZMAX, GPOUT_MAX = 8, 2
 
