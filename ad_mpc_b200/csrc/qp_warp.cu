@@ -149,6 +149,15 @@ __device__ __forceinline__ double dot6(const double *a, const double *b)
     v = fma(a2.x, b2.x, v); w = fma(a2.y, b2.y, w);
     return v + w;
 }
+// the same with the first operand already in registers (shared by several dot products of the lane)
+__device__ __forceinline__ double dot6r(double2 a0, double2 a1, double2 a2, const double *b)
+{
+    const double2 b0 = ld2(b), b1 = ld2(b + 2), b2 = ld2(b + 4);
+    double v = a0.x * b0.x, w = a0.y * b0.y;
+    v = fma(a1.x, b1.x, v); w = fma(a1.y, b1.y, w);
+    v = fma(a2.x, b2.x, v); w = fma(a2.y, b2.y, w);
+    return v + w;
+}
 
 // ---- sequential backward sweep (matrix role) -----------------------------------------------------------------------
 // Uniform instruction stream: every lane runs the same code on per-lane shared-memory pointers set up once before the
@@ -160,15 +169,16 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
 
     const double Ts = o.dt, hdt = o.dt;
-    // phase 1: entries e = cc*7 + a of W = P [M | rb]
-    const int e0 = l, e1 = (l + 32 < 56) ? l + 32 : 55;
-    const int cc0 = e0 / 7, a0 = e0 - cc0 * 7, cc1 = e1 / 7, a1 = e1 - cc1 * 7;
-    const double *p1P0 = xs + X_PS + a0 * PSS, *p1P1 = xs + X_PS + a1 * PSS;
+    // phase 1: W = P [M | rb], entry (a, cc) at cc*PSS + a.  Lane l < 28 owns row a = l % 7 of P for the two columns
+    // cc0 = l / 7 and cc0 + 4: the row of P is fetched once for both dot products (lanes 28..31 shadow lane 27)
+    const int lw = (l < 28) ? l : 27;
+    const int cc0 = lw / 7, a0 = lw - cc0 * 7, cc1 = cc0 + 4, a1 = a0;
+    const double *p1P0 = xs + X_PS + a0 * PSS;
     const int p1c0 = (cc0 < 7) ? R_M + cc0 * 6 : R_RB, p1c1 = (cc1 < 7) ? R_M + cc1 * 6 : R_RB;
     const double m6c0 = (cc0 == 1) ? hdt : (cc0 == 6) ? 1.0 : 0.0, m6r0 = (cc0 == 7) ? 1.0 : 0.0;
     const double m6c1 = (cc1 == 1) ? hdt : (cc1 == 6) ? 1.0 : 0.0, m6r1 = (cc1 == 7) ? 1.0 : 0.0;
     double *p1o0 = xs + X_WS + cc0 * PSS + a0, *p1o1 = xs + X_WS + cc1 * PSS + a1;
-    const bool v70 = (cc0 == 7), v71 = (cc1 == 7);
+    const bool v71 = (cc1 == 7);
     // phases 2 and 3: packed lower-triangle pair (ta >= tb); lanes 28..31 shadow lane 27
     const int lt = (l < 28) ? l : 27;
     const int ta = (lt >= 21) ? 6 : (lt >= 15) ? 5 : (lt >= 10) ? 4 : (lt >= 6) ? 3 : (lt >= 3) ? 2 : (lt >= 1) ? 1 : 0;
@@ -180,12 +190,11 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     const double p2dm = (dg && (ta < 2 || ta == 6)) ? 1.0 : 0.0;                 // diagonal term read from the record
     const double p2dc = (dg && ta >= 2 && ta < 6) ? Ts * sel7(o.W, ta) : 0.0;    // or a constant weight
     const int p2dOff = R_BAR + ((ta == 6) ? 2 : (ta == 1) ? 1 : 0);
-    // gradient vector g (lanes 0..8 as a second job of phase 2): v < 7 -> M-column v ; v = 7,8 -> x0, x1
-    const bool isG = (l < 9);
-    const int gv = isG ? l : 0;
+    // gradient vector g as a second job of phase 2: entry v < 7 (M-column v) on the lane with (ta, tb) = (v, 0), which
+    // already holds M(:, v) in registers for its Gram entry ; v = 7, 8 (x0, x1: no dot product) on lanes 28, 29
+    const bool isG = (l < 28) ? (tb == 0) : (l < 30);
+    const int gv = (l < 28) ? ta : (l < 30) ? l - 21 : 0;
     const int p3gb = (gv < 2) ? R_BAR + 3 + gv : (gv < 7) ? R_GX + gv : R_GX + (gv - 7);
-    const int p3M = R_M + ((gv < 7) ? gv : 0) * 6;
-    const double p3m6 = (gv == 1) ? hdt : (gv == 6) ? 1.0 : 0.0;
     const double p3gm = (gv < 7) ? 1.0 : 0.0, p3gh = (gv < 7) ? 0.0 : 1.0;
     const int p3h = (gv < 7) ? 0 : gv - 7;
     // phase 3: gains (lanes 0..13: j = l/7, x = l%7), Schur entry (ta, tb), k_ff (lanes 28, 29), p_k (lanes 0..6)
@@ -202,8 +211,6 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     double *p4o0 = xs + X_PS + ta * PSS + tb, *p4o1 = xs + X_PS + tb * PSS + ta;
     const int l7 = (l < 7) ? l : 6;
     const double *p4gx = xs + X_GV + ((l7 < 2) ? 7 + l7 : l7);
-    const double *p5c0 = (l7 < 2) ? xs + X_WS + 0 * PSS + l7 : xs + X_GS + tri_rt(l7, 0);   // G[u0][x_l]
-    const double *p5c1 = (l7 < 2) ? xs + X_WS + 1 * PSS + l7 : xs + X_GS + tri_rt(l7, 1);
     const bool kfj = (l == 29);
 
     // terminal: P_N = diag(We), p_N = r_x,N
@@ -219,30 +226,25 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
             // ---- phase 1: W = P_{k+1} [M | rb] ; P rb ; h = P rb + p ------------------------------------------------------
             const double rb6 = st[R_RB + 6];
             {
-                const double v = fma(p1P0[6], fma(m6r0, rb6, m6c0), dot6(p1P0, st + p1c0));
+                const double2 r01 = ld2(p1P0), r23 = ld2(p1P0 + 2), r45 = ld2(p1P0 + 4);
+                const double r6 = p1P0[6];
+                const double v = fma(r6, fma(m6r0, rb6, m6c0), dot6r(r01, r23, r45, st + p1c0));
                 *p1o0 = v;
-                if (v70) { st[R_PB + a0] = v; xs[X_HV + a0] = v + xs[X_PV + a0]; }
-            }
-            {
-                const double v = fma(p1P1[6], fma(m6r1, rb6, m6c1), dot6(p1P1, st + p1c1));
-                *p1o1 = v;
-                if (v71) { st[R_PB + a1] = v; xs[X_HV + a1] = v + xs[X_PV + a1]; }
+                const double w = fma(r6, fma(m6r1, rb6, m6c1), dot6r(r01, r23, r45, st + p1c1));
+                *p1o1 = w;
+                if (v71) { st[R_PB + a1] = w; xs[X_HV + a1] = w + xs[X_PV + a1]; }
             }
             __syncwarp();
             // ---- phase 2: Gram block G[ta][tb] = M(:,ta)^T W(:,tb) + diagonal ; gradient vector g ---------------------------
             {
-                double v = fma(p2m6, p2W[6], dot6(st + p2M, p2W));
+                const double2 m01 = ld2(st + p2M), m23 = ld2(st + p2M + 2), m45 = ld2(st + p2M + 4);
+                double v = fma(p2m6, p2W[6], dot6r(m01, m23, m45, p2W));
                 v += fma(p2dm, st[p2dOff], p2dc);
                 xs[X_GS + lt] = v;
+                const double d = fma(p2m6, xs[X_HV + 6], dot6r(m01, m23, m45, xs + X_HV));
+                const double g = st[p3gb] + fma(p3gm, d, p3gh * xs[X_HV + p3h]);
+                if (isG) xs[X_GV + gv] = g;
             }
-        } else {
-            if (l < 7) xs[X_HV + l] = st[R_PB + l] + xs[X_PV + l];
-            __syncwarp();
-        }
-        {
-            const double d = fma(p3m6, xs[X_HV + 6], dot6(st + p3M, xs + X_HV));
-            const double g = st[p3gb] + fma(p3gm, d, p3gh * xs[X_HV + p3h]);
-            if (isG) xs[X_GV + gv] = g;
         }
         __syncwarp();
         // ---- phase 3: 2x2 pivot, gains, Schur complement, k_ff, p_k -----------------------------------------------------------
@@ -251,9 +253,10 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
             const double g00 = xs[X_GS + 0] + o.reg, g01 = xs[X_GS + 1], g11 = xs[X_GS + 2] + o.reg;
             const double idet = rcp_nr(g00 * g11 - g01 * g01);
             gi00 = g11 * idet; gi01 = -g01 * idet; gi11 = g00 * idet;
+            const double a0v = *p3a0, a1v = *p3a1;       // G[u0][x_kx], G[u1][x_kx] (kx = l on lanes 0..6: reused for p_k below)
             {
                 const double c0 = kj ? gi01 : gi00, c1 = kj ? gi11 : gi01;
-                const double kval = -(c0 * (*p3a0) + c1 * (*p3a1));
+                const double kval = -(c0 * a0v + c1 * a1v);
                 if (isK) st[(kj ? R_K1 : R_K0) + kx] = kval;
             }
             if (l == 31) { st[R_GI + 0] = gi00; st[R_GI + 1] = gi01; st[R_GI + 2] = gi11; }
@@ -264,15 +267,10 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
                 *p4o0 = pn; *p4o1 = pn;
             }
             {   // p_k[l] = g_x[l] + K(:, x_l) . g_u
-                const double c0 = *p5c0, c1 = *p5c1;
-                const double k0 = -(gi00 * c0 + gi01 * c1), k1 = -(gi01 * c0 + gi11 * c1);
+                const double k0 = -(gi00 * a0v + gi01 * a1v), k1 = -(gi01 * a0v + gi11 * a1v);
                 const double pvv = *p4gx + k0 * gu0 + k1 * gu1;
                 if (l < 7) xs[X_PV + l] = pvv;
             }
-        } else {
-            gi00 = st[R_GI + 0]; gi01 = st[R_GI + 1]; gi11 = st[R_GI + 2];
-            const double pvv = *p4gx + st[R_K0 + l7] * gu0 + st[R_K1 + l7] * gu1;
-            if (l < 7) xs[X_PV + l] = pvv;
         }
         {
             const double c0 = kfj ? gi01 : gi00, c1 = kfj ? gi11 : gi01;
