@@ -325,51 +325,54 @@ __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, 
     }
 }
 
-// ---- sequential forward roll-out (matrix role: lane r < 7 carries ddx_k[r]) -------------------------------------------
-// The state is broadcast through a double-buffered 8-double slot (1 STS + LDS.128s + one __syncwarp per stage).
+// ---- sequential forward roll-out (matrix role) -------------------------------------------------------------------------
+// One uniform "row . x" stream per stage: lanes 0..5 own row l of M = [B | A(:,2:7)] (ddx_{k+1}[l]), lane 6 the trivial
+// delta row, lanes 7 / 8 the gain rows K0 / K1 (ddu_k).  The five state terms c = 2..6 multiply the same x_c on every
+// lane; the gain lanes add K(:,0:1) . x_{0:1} + k_ff, two shuffles hand ddu to the state lanes, which add B . ddu.  Each
+// lane fetches only ITS row (8 per-lane LDS.64) instead of all of K (the roll-outs were 40 % of the kernel's
+// shared-memory wavefronts).  The state is broadcast through a double-buffered 8-double slot (one __syncwarp per stage).
 template <bool ADJ>
 __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
     asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
 
     const double hdt = o.dt, Ts = o.dt;
-    const int l7 = (l < 7) ? l : 6, l6 = (l < 6) ? l : 5;
+    const int l7 = (l < 7) ? l : 6;
     const double wq_l = Ts * sel7(o.W, l7), we_l = sel7(o.We, l7);
     const double cself = (l < 2 || l == 6) ? 1.0 : 0.0, cdt = (l == 6) ? hdt : 0.0, mB = (l < 6) ? 1.0 : 0.0;
     const double is6 = (l == 6) ? 1.0 : 0.0;
+    const int job = (l < 9) ? l : 8;                       // lanes 9..31 shadow lane 8
+    const bool isK = (job >= 7);
+    const int rbase = isK ? ((job == 7) ? R_K0 : R_K1) : R_M + ((job < 6) ? job : 5);
+    const int rstr = isK ? 1 : 6;                          // element c of the lane's row at rbase + c * rstr
+    const double *row = sm + rbase;
+    const double *offp = sm + (isK ? R_KF + (job - 7) : R_RB + l7);     // k_ff,j or rb[l]
+    const int o1 = rstr, o2 = 2 * rstr, o3 = 3 * rstr, o4 = 4 * rstr, o5 = 5 * rstr, o6 = 6 * rstr;
     double dxr = 0.0;
     double *st = sm;
-    for (int k = 0; k < N; k++, st += R_STRIDE) {
+    for (int k = 0; k < N; k++, st += R_STRIDE, row += R_STRIDE, offp += R_STRIDE) {
         double *bx = xs + X_DX + (k & 1) * 8;
         if (l < 8) bx[l] = dxr;                        // lane 7 writes the zero pad
         __syncwarp();
         const double2 x01 = ld2(bx), x23 = ld2(bx + 2), x45 = ld2(bx + 4);
         const double x6 = bx[6];
-        const double2 ka = ld2(st + R_K0), kb = ld2(st + R_K0 + 2), kc = ld2(st + R_K0 + 4);
-        const double2 kd = ld2(st + R_K1), ke = ld2(st + R_K1 + 2), kg = ld2(st + R_K1 + 4);
-        const double2 kf = ld2(st + R_KF);
-        double du0 = fma(ka.x, x01.x, kf.x), t0 = ka.y * x01.y;
-        du0 = fma(kb.x, x23.x, du0); t0 = fma(kb.y, x23.y, t0);
-        du0 = fma(kc.x, x45.x, du0); t0 = fma(kc.y, x45.y, t0);
-        du0 = fma(st[R_K0 + 6], x6, du0) + t0;
-        double du1 = fma(kd.x, x01.x, kf.y), t1 = kd.y * x01.y;
-        du1 = fma(ke.x, x23.x, du1); t1 = fma(ke.y, x23.y, t1);
-        du1 = fma(kg.x, x45.x, du1); t1 = fma(kg.y, x45.y, t1);
-        du1 = fma(st[R_K1 + 6], x6, du1) + t1;
+        // state terms (every lane)
+        double ta = row[o2] * x23.x, tb = row[o3] * x23.y;
+        ta = fma(row[o4], x45.x, ta); tb = fma(row[o5], x45.y, tb);
+        ta = fma(row[o6], x6, ta);
+        const double e0 = row[0], e1 = row[o1], off = *offp;
+        // gain lanes: ddu_j = K_j . x + k_ff,j
+        const double duj = fma(e0, x01.x, off) + fma(e1, x01.y, tb) + ta;
+        const double du0 = __shfl_sync(FULL, duj, 7), du1 = __shfl_sync(FULL, duj, 8);
         if (l == 7) { st[R_DD + 0] = du0; st[R_DD + 1] = du1; st[R_DD + 2] = x6; }
         if (ADJ && k >= 1) {
             const double Qd = fma(is6, st[R_BAR + 2] - wq_l, wq_l);
             const double nb = fma(Qd, dxr, st[R_GX + l7]);
             if (l < 7) st[R_GX + l] = nb;
         }
-        const double *mr = st + R_M + l6;        // row l of M: element (l, c) at c*6
-        // state terms first: they do not wait for the du dot products (shorter dependent chain per stage)
-        double d = mr[12] * x23.x, d2 = mr[18] * x23.y;
-        d = fma(mr[24], x45.x, d); d2 = fma(mr[30], x45.y, d2);
-        d = fma(mr[36], x6, d);
-        d = fma(mr[0], du0, d); d2 = fma(mr[6], du1, d2);
-        d += d2;
-        double v = st[R_RB + l7] + fma(cself, dxr, cdt * du1);
+        // state lanes: ddx_{k+1}[l] = rb[l] + (A ddx)[l] + (B ddu)[l]
+        const double d = fma(e0, du0, ta) + fma(e1, du1, tb);
+        double v = off + fma(cself, dxr, cdt * du1);
         v = fma(mB, d, v);
         dxr = (l < 7) ? v : 0.0;
         if (ADJ && l < 7) st[R_RB + l] = dxr;           // ddx_{k+1}
