@@ -281,9 +281,9 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     }
 }
 
-// ---- corrector backward sweep: vector part only, ONE __syncwarp per stage --------------------------------------------
-// Every g-lane rebuilds h = P rb + p itself from the record and the published p_{k+1}; g_u reaches the p-lanes by two
-// shuffles; p_k is published in the other half of a double buffer for the next stage.
+// ---- corrector backward sweep: vector part only, NO shared-memory round trip in the recursion ------------------------
+// p_{k+1} is carried in registers (entry c on lane 7, 8, 2..6 for c = 0, 1, 2..6); the owner adds (P rb)[c] and seven
+// shuffles hand h = P rb + p to the g-lanes; g_u reaches the p-lanes by two more shuffles.
 __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
     asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
@@ -295,18 +295,16 @@ __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, 
     const double m6 = (v == 1) ? hdt : (v == 6) ? 1.0 : 0.0;
     const double gm = (v < 7) ? 1.0 : 0.0, gh = (v < 7) ? 0.0 : 1.0;
     const bool h1sel = (v == 8);
-    const int sx = (v >= 2 && v < 7) ? v : (v == 8) ? 1 : 0;    // state index of the p entry this lane produces
-    const bool isP = (l >= 2 && l < 9);
+    const int sx = (v >= 2 && v < 7) ? v : (v == 8) ? 1 : 0;    // state index of the p entry this lane carries
     const bool kfj = (l == 10);
-    double *pva = xs + X_PV, *pvb = xs + X_HV;
-    if (l < 7) pva[l] = sm[N * R_STRIDE + l];
-    __syncwarp();
+    const int gio = R_GI + (kfj ? 1 : 0);
+    double pown = sm[N * R_STRIDE + sx];                        // p_N = r_x,N
     double *st = sm + (N - 1) * R_STRIDE;
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
-        const double2 b01 = ld2(st + R_PB), b23 = ld2(st + R_PB + 2), b45 = ld2(st + R_PB + 4);
-        const double2 p01 = ld2(pva), p23 = ld2(pva + 2), p45 = ld2(pva + 4);
-        const double h0 = b01.x + p01.x, h1 = b01.y + p01.y, h2 = b23.x + p23.x, h3 = b23.y + p23.y;
-        const double h4 = b45.x + p45.x, h5 = b45.y + p45.y, h6 = st[R_PB + 6] + pva[6];
+        const double hown = st[R_PB + sx] + pown;
+        const double h0 = __shfl_sync(FULL, hown, 7), h1 = __shfl_sync(FULL, hown, 8), h2 = __shfl_sync(FULL, hown, 2);
+        const double h3 = __shfl_sync(FULL, hown, 3), h4 = __shfl_sync(FULL, hown, 4), h5 = __shfl_sync(FULL, hown, 5);
+        const double h6 = __shfl_sync(FULL, hown, 6);
         const double2 m01 = ld2(st + mOff), m23 = ld2(st + mOff + 2), m45 = ld2(st + mOff + 4);
         double d = m6 * h6, d2 = m01.x * h0;
         d = fma(m01.y, h1, d); d2 = fma(m23.x, h2, d2);
@@ -314,15 +312,12 @@ __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, 
         d = fma(m45.y, h5, d) + d2;
         const double g = st[gb] + fma(gm, d, gh * (h1sel ? h1 : h0));
         const double gu0 = __shfl_sync(FULL, g, 0), gu1 = __shfl_sync(FULL, g, 1);
-        const double gi00 = st[R_GI + 0], gi01 = st[R_GI + 1], gi11 = st[R_GI + 2];
-        const double c0 = kfj ? gi01 : gi00, c1 = kfj ? gi11 : gi01;
+        const double c0 = st[gio], c1 = st[gio + 1];             // lane 9: (gi00, gi01) ; lane 10: (gi01, gi11)
         const double kf = -(c0 * gu0 + c1 * gu1);
         if (l == 9 || l == 10) st[R_KF + (l - 9)] = kf;
-        const double pvv = g + st[R_K0 + sx] * gu0 + st[R_K1 + sx] * gu1;
-        if (isP) pvb[sx] = pvv;
-        __syncwarp();
-        double *t = pva; pva = pvb; pvb = t;
+        pown = g + st[R_K0 + sx] * gu0 + st[R_K1 + sx] * gu1;
     }
+    __syncwarp();
 }
 
 // ---- sequential forward roll-out (matrix role) -------------------------------------------------------------------------
@@ -382,6 +377,7 @@ __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, doubl
 }
 
 // ---- sequential adjoint sweep: dpi_{k-1} = base_k + A_k^T dpi_k ; leaves dpi_k in the P rb slot ----------------------
+// dpi_k stays on lanes 0..6; rows 0..5 reach the M-column lanes by shuffles (the store into the record is off the chain).
 __device__ __forceinline__ void w_adjoint(double *sm, double *xs, int N, int l)
 {
     asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
@@ -394,8 +390,14 @@ __device__ __forceinline__ void w_adjoint(double *sm, double *xs, int N, int l)
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
         if (l < 7) st[R_PB + l] = dpr;
         if (k == 0) break;
-        __syncwarp();
-        const double d = dot6(st + R_M + lc * 6, st + R_PB);      // rows 0..5 of dpi_k, just published in the record
+        const double q0 = __shfl_sync(FULL, dpr, 0), q1 = __shfl_sync(FULL, dpr, 1), q2 = __shfl_sync(FULL, dpr, 2);
+        const double q3 = __shfl_sync(FULL, dpr, 3), q4 = __shfl_sync(FULL, dpr, 4), q5 = __shfl_sync(FULL, dpr, 5);
+        const double *mc = st + R_M + lc * 6;
+        const double2 a0 = ld2(mc), a1 = ld2(mc + 2), a2 = ld2(mc + 4);
+        double d = a0.x * q0, w = a0.y * q1;
+        d = fma(a1.x, q2, d); w = fma(a1.y, q3, w);
+        d = fma(a2.x, q4, d); w = fma(a2.y, q5, w);
+        d += w;
         const double v = st[R_GX + l7] + fma(cself, dpr, mA * d);  // A(:,0..1) = e0,e1 ; A[6][6] = 1
         dpr = (l < 7) ? v : 0.0;
     }
