@@ -145,6 +145,15 @@ __device__ __forceinline__ double dot6(const double *a, const double *b)
     v = fma(a2.x, b2.x, v); w = fma(a2.y, b2.y, w);
     return v + w;
 }
+// the same with the first operand already in registers (shared by several dot products of the lane)
+__device__ __forceinline__ double dot6r(double2 a0, double2 a1, double2 a2, const double *b)
+{
+    const double2 b0 = ld2(b), b1 = ld2(b + 2), b2 = ld2(b + 4);
+    double v = a0.x * b0.x, w = a0.y * b0.y;
+    v = fma(a1.x, b1.x, v); w = fma(a1.y, b1.y, w);
+    v = fma(a2.x, b2.x, v); w = fma(a2.y, b2.y, w);
+    return v + w;
+}
 
 // ---- sequential backward sweep (matrix role) -----------------------------------------------------------------------
 // Uniform instruction stream: every lane runs the same code on per-lane shared-memory pointers set up once before the
@@ -180,12 +189,11 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     const double p2dc0 = (dg0 && ga0 >= 2 && ga0 < 7) ? Ts * sel7(o.W, ga0 - 1) : 0.0;
     const int p2dOff0 = R_BAR + ((ga0 == 7) ? 2 : (ga0 == 1) ? 1 : 0), p2dOff1 = R_BAR + 2;
     const bool g1on = (l < 4);
-    // gradient vector g (lanes 0..8 as a second job of phase 2): v < 8 -> M-column v ; v = 8 -> x0
-    const bool isG = (l < 9);
-    const int gv = isG ? l : 0;
+    // gradient vector g as a second job of phase 2: entry v < 8 (M-column v) on the lane whose first Gram entry is
+    // (v, 0) -- it already holds M(:, v) in registers ; v = 8 (x0: no dot product) on lane 31
+    const bool isG = (gb0 == 0) || (l == 31);
+    const int gv = (l == 31) ? 8 : ga0;
     const int p3gb = (gv < 2) ? R_BAR + 3 + gv : (gv < 8) ? R_GX + (gv - 1) : R_GX + 0;
-    const int p3M = R_M + ((gv < 8) ? gv : 0) * 6;
-    const double p3m6 = (gv == 1) ? hdt : (gv == 7) ? 1.0 : 0.0;
     const double p3gm = (gv < 8) ? 1.0 : 0.0, p3gh = (gv < 8) ? 0.0 : 1.0;
     // phase 3: gains (lanes 0..13: j = l/7, x = l%7), Schur entry (ta, tb) over STATE pairs (28 entries; lanes 28..31
     // shadow lane 27), k_ff (lanes 28, 29), p_k (lanes 0..6).  M-index of state a >= 1 is a + 1.
@@ -235,21 +243,17 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
             __syncwarp();
             // ---- phase 2: Gram block G[ta][tb] = M(:,ta)^T W(:,tb) + diagonal ; gradient vector g ---------------------------
             {
-                double v = fma(p2m60, p2W0[6], dot6(st + p2M0, p2W0));
+                const double2 m01 = ld2(st + p2M0), m23 = ld2(st + p2M0 + 2), m45 = ld2(st + p2M0 + 4);
+                double v = fma(p2m60, p2W0[6], dot6r(m01, m23, m45, p2W0));
                 v += fma(p2dm0, st[p2dOff0], p2dc0);
                 xs[X_GS + gt0] = v;
                 double w = fma(p2m61, p2W1[6], dot6(st + p2M1, p2W1));
                 w += p2dm1 * st[p2dOff1];
                 if (g1on) xs[X_GS + gt1] = w;
+                const double d = fma(p2m60, xs[X_HV + 6], dot6r(m01, m23, m45, xs + X_HV));
+                const double g = st[p3gb] + fma(p3gm, d, p3gh * xs[X_HV + 0]);
+                if (isG) xs[X_GV + gv] = g;
             }
-        } else {
-            if (l < 7) xs[X_HV + l] = st[R_PB + l] + xs[X_PV + l];
-            __syncwarp();
-        }
-        {
-            const double d = fma(p3m6, xs[X_HV + 6], dot6(st + p3M, xs + X_HV));
-            const double g = st[p3gb] + fma(p3gm, d, p3gh * xs[X_HV + 0]);
-            if (isG) xs[X_GV + gv] = g;
         }
         __syncwarp();
         // ---- phase 3: 2x2 pivot, gains, Schur complement, k_ff, p_k -----------------------------------------------------------
@@ -276,10 +280,6 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
                 const double pvv = *p4gx + k0 * gu0 + k1 * gu1;
                 if (l < 7) xs[X_PV + l] = pvv;
             }
-        } else {
-            gi00 = st[R_GI + 0]; gi01 = st[R_GI + 1]; gi11 = st[R_GI + 2];
-            const double pvv = *p4gx + st[R_K0 + l7] * gu0 + st[R_K1 + l7] * gu1;
-            if (l < 7) xs[X_PV + l] = pvv;
         }
         {
             const double c0 = kfj ? gi01 : gi00, c1 = kfj ? gi11 : gi01;
@@ -290,9 +290,9 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     }
 }
 
-// ---- corrector backward sweep: vector part only, ONE __syncwarp per stage --------------------------------------------
-// Every g-lane rebuilds h = P rb + p itself from the record and the published p_{k+1}; g_u reaches the p-lanes by two
-// shuffles; p_k is published in the other half of a double buffer for the next stage.
+// ---- corrector backward sweep: vector part only, NO shared-memory round trip in the recursion ------------------------
+// p_{k+1} is carried in registers (entry c on lane 8 for c = 0, lane c + 1 for c = 1..6); the owner adds (P rb)[c] and
+// seven shuffles hand h = P rb + p to the g-lanes; g_u reaches the p-lanes by two more shuffles.
 __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
     asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
@@ -303,82 +303,77 @@ __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, 
     const int mOff = R_M + ((v < 8) ? v : 0) * 6;
     const double m6 = (v == 1) ? hdt : (v == 7) ? 1.0 : 0.0;
     const double gm = (v < 8) ? 1.0 : 0.0, gh = (v < 8) ? 0.0 : 1.0;
-    const bool h1sel = false;
-    const int sx = (v >= 2 && v < 8) ? v - 1 : 0;               // state index of the p entry this lane produces (v = 8 -> x0)
-    const bool isP = (l >= 2 && l < 9);
+    const int sx = (v >= 2 && v < 8) ? v - 1 : 0;               // state index of the p entry this lane carries (v = 8 -> x0)
     const bool kfj = (l == 10);
-    double *pva = xs + X_PV, *pvb = xs + X_HV;
-    if (l < 7) pva[l] = sm[N * R_STRIDE + l];
-    __syncwarp();
+    const int gio = R_GI + (kfj ? 1 : 0);
+    double pown = sm[N * R_STRIDE + sx];                        // p_N = r_x,N
     double *st = sm + (N - 1) * R_STRIDE;
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
-        const double2 b01 = ld2(st + R_PB), b23 = ld2(st + R_PB + 2), b45 = ld2(st + R_PB + 4);
-        const double2 p01 = ld2(pva), p23 = ld2(pva + 2), p45 = ld2(pva + 4);
-        const double h0 = b01.x + p01.x, h1 = b01.y + p01.y, h2 = b23.x + p23.x, h3 = b23.y + p23.y;
-        const double h4 = b45.x + p45.x, h5 = b45.y + p45.y, h6 = st[R_PB + 6] + pva[6];
+        const double hown = st[R_PB + sx] + pown;
+        const double h0 = __shfl_sync(FULL, hown, 8), h1 = __shfl_sync(FULL, hown, 2), h2 = __shfl_sync(FULL, hown, 3);
+        const double h3 = __shfl_sync(FULL, hown, 4), h4 = __shfl_sync(FULL, hown, 5), h5 = __shfl_sync(FULL, hown, 6);
+        const double h6 = __shfl_sync(FULL, hown, 7);
         const double2 m01 = ld2(st + mOff), m23 = ld2(st + mOff + 2), m45 = ld2(st + mOff + 4);
         double d = m6 * h6, d2 = m01.x * h0;
         d = fma(m01.y, h1, d); d2 = fma(m23.x, h2, d2);
         d = fma(m23.y, h3, d); d2 = fma(m45.x, h4, d2);
         d = fma(m45.y, h5, d) + d2;
-        const double g = st[gb] + fma(gm, d, gh * (h1sel ? h1 : h0));
+        const double g = st[gb] + fma(gm, d, gh * h0);
         const double gu0 = __shfl_sync(FULL, g, 0), gu1 = __shfl_sync(FULL, g, 1);
-        const double gi00 = st[R_GI + 0], gi01 = st[R_GI + 1], gi11 = st[R_GI + 2];
-        const double c0 = kfj ? gi01 : gi00, c1 = kfj ? gi11 : gi01;
+        const double c0 = st[gio], c1 = st[gio + 1];             // lane 9: (gi00, gi01) ; lane 10: (gi01, gi11)
         const double kf = -(c0 * gu0 + c1 * gu1);
         if (l == 9 || l == 10) st[R_KF + (l - 9)] = kf;
-        const double pvv = g + st[R_K0 + sx] * gu0 + st[R_K1 + sx] * gu1;
-        if (isP) pvb[sx] = pvv;
-        __syncwarp();
-        double *t = pva; pva = pvb; pvb = t;
+        pown = g + st[R_K0 + sx] * gu0 + st[R_K1 + sx] * gu1;
     }
+    __syncwarp();
 }
 
-// ---- sequential forward roll-out (matrix role: lane r < 7 carries ddx_k[r]) -------------------------------------------
-// The state is broadcast through a double-buffered 8-double slot (1 STS + LDS.128s + one __syncwarp per stage).
+// ---- sequential forward roll-out (matrix role) -------------------------------------------------------------------------
+// One uniform "row . x" stream per stage (see qp_warp.cu): lanes 0..5 own row l of M = [B | A(:,1:7)], lane 6 the
+// trivial delta row, lanes 7 / 8 the gain rows K0 / K1.  The six state terms x_1..x_6 are common to every lane; the gain
+// lanes add K(:,0) x_0 + k_ff, two shuffles hand ddu to the state lanes, which add B . ddu.
 template <bool ADJ>
 __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, double *xs, int N, int l)
 {
     asm volatile("" : "+r"(l));      // per-lane role constants are rebuilt per sweep, not kept live across the stage role
 
     const double hdt = o.dt, Ts = o.dt;
-    const int l7 = (l < 7) ? l : 6, l6 = (l < 6) ? l : 5;
+    const int l7 = (l < 7) ? l : 6;
     const double wq_l = Ts * sel7(o.W, l7), we_l = sel7(o.We, l7);
     const double cself = (l < 1 || l == 6) ? 1.0 : 0.0, cdt = (l == 6) ? hdt : 0.0, mB = (l < 6) ? 1.0 : 0.0;
     const double is6 = (l == 6) ? 1.0 : 0.0;
+    const int job = (l < 9) ? l : 8;                       // lanes 9..31 shadow lane 8
+    const bool isK = (job >= 7);
+    // coefficient of x_i (i = 1..6) at xb + i * rstr ; first entries e0 (du0 | x0) and e1 (du1 | unused on the gain lanes)
+    const int xb = isK ? ((job == 7) ? R_K0 : R_K1) : R_M + ((job < 6) ? job : 5) + 6;
+    const int rstr = isK ? 1 : 6;
+    const double *row = sm + xb;
+    const int oe0 = isK ? 0 : -6, oe1 = 0;
+    const double e1on = isK ? 0.0 : 1.0;
+    const double *offp = sm + (isK ? R_KF + (job - 7) : R_RB + l7);     // k_ff,j or rb[l]
+    const int o1 = rstr, o2 = 2 * rstr, o3 = 3 * rstr, o4 = 4 * rstr, o5 = 5 * rstr, o6 = 6 * rstr;
     double dxr = 0.0;
     double *st = sm;
-    for (int k = 0; k < N; k++, st += R_STRIDE) {
+    for (int k = 0; k < N; k++, st += R_STRIDE, row += R_STRIDE, offp += R_STRIDE) {
         double *bx = xs + X_DX + (k & 1) * 8;
         if (l < 8) bx[l] = dxr;                        // lane 7 writes the zero pad
         __syncwarp();
         const double2 x01 = ld2(bx), x23 = ld2(bx + 2), x45 = ld2(bx + 4);
         const double x6 = bx[6];
-        const double2 ka = ld2(st + R_K0), kb = ld2(st + R_K0 + 2), kc = ld2(st + R_K0 + 4);
-        const double2 kd = ld2(st + R_K1), ke = ld2(st + R_K1 + 2), kg = ld2(st + R_K1 + 4);
-        const double2 kf = ld2(st + R_KF);
-        double du0 = fma(ka.x, x01.x, kf.x), t0 = ka.y * x01.y;
-        du0 = fma(kb.x, x23.x, du0); t0 = fma(kb.y, x23.y, t0);
-        du0 = fma(kc.x, x45.x, du0); t0 = fma(kc.y, x45.y, t0);
-        du0 = fma(st[R_K0 + 6], x6, du0) + t0;
-        double du1 = fma(kd.x, x01.x, kf.y), t1 = kd.y * x01.y;
-        du1 = fma(ke.x, x23.x, du1); t1 = fma(ke.y, x23.y, t1);
-        du1 = fma(kg.x, x45.x, du1); t1 = fma(kg.y, x45.y, t1);
-        du1 = fma(st[R_K1 + 6], x6, du1) + t1;
+        double ta = row[o1] * x01.y, tb = row[o2] * x23.x;
+        ta = fma(row[o3], x23.y, ta); tb = fma(row[o4], x45.x, tb);
+        ta = fma(row[o5], x45.y, ta); tb = fma(row[o6], x6, tb);
+        const double e0 = row[oe0], e1 = e1on * row[oe1], off = *offp;
+        const double duj = fma(e0, x01.x, off) + (ta + tb);       // gain lanes: ddu_j = K_j . x + k_ff,j
+        const double du0 = __shfl_sync(FULL, duj, 7), du1 = __shfl_sync(FULL, duj, 8);
         if (l == 7) { st[R_DD + 0] = du0; st[R_DD + 1] = du1; st[R_DD + 2] = x6; }
         if (ADJ && k >= 1) {
             const double Qd = fma(is6, st[R_BAR + 2] - wq_l, wq_l);
             const double nb = fma(Qd, dxr, st[R_GX + l7]);
             if (l < 7) st[R_GX + l] = nb;
         }
-        const double *mr = st + R_M + l6;        // row l of M: element (l, c) at c*6
-        // state terms first: they do not wait for the du dot products (shorter dependent chain per stage)
-        double d = mr[12] * x01.y, d2 = mr[18] * x23.x;
-        d = fma(mr[24], x23.y, d); d2 = fma(mr[30], x45.x, d2);
-        d = fma(mr[36], x45.y, d); d2 = fma(mr[42], x6, d2);
-        d = fma(mr[0], du0, d); d2 = fma(mr[6], du1, d2);
-        d += d2;
-        double v = st[R_RB + l7] + fma(cself, dxr, cdt * du1);
+        const double d = fma(e0, du0, ta) + fma(e1, du1, tb);
+        double v = off + fma(cself, dxr, cdt * du1);
         v = fma(mB, d, v);
         dxr = (l < 7) ? v : 0.0;
         if (ADJ && l < 7) st[R_RB + l] = dxr;           // ddx_{k+1}
