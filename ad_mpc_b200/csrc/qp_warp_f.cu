@@ -9,6 +9,22 @@
 #include "common.cuh"
 
 #define FULL 0xffffffffu
+// unroll factors of the horizon loops of the sweeps (the recursion is serial, but unrolling lets ptxas hoist the next
+// stage's operand loads above the current stage's dependent chain): factor sweep / vector sweeps
+#ifndef QPW_UB
+#define QPW_UB 1
+#endif
+#ifndef QPW_UVEC
+#define QPW_UVEC 2
+#endif
+#ifndef QPW_UFWD
+#define QPW_UFWD 2
+#endif
+#ifndef QPW_UADJ
+#define QPW_UADJ 2
+#endif
+#define QPW_PRAGMA_(x) _Pragma(#x)
+#define QPW_UNROLL(n) QPW_PRAGMA_(unroll n)
 #define ATS(arr, row) (arr)[(size_t)(row) * Bp + i]      // SoA interface arrays [row][Bp]
 
 // stage record in shared memory (doubles).  Every vector-loaded block starts at an even offset and the stride is
@@ -225,6 +241,7 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     if (FACTOR && l < 7) xs[X_PS + l * PSS + l] = sel7(o.We, l);
     __syncwarp();
     double *st = sm + (N - 1) * R_STRIDE;
+QPW_UNROLL(QPW_UB)
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
         double gi00, gi01, gi11;
         if (FACTOR) {
@@ -308,6 +325,7 @@ __device__ __forceinline__ void w_backward_vec(const admpc_opts &o, double *sm, 
     const int gio = R_GI + (kfj ? 1 : 0);
     double pown = sm[N * R_STRIDE + sx];                        // p_N = r_x,N
     double *st = sm + (N - 1) * R_STRIDE;
+QPW_UNROLL(QPW_UVEC)
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
         const double hown = st[R_PB + sx] + pown;
         const double h0 = __shfl_sync(FULL, hown, 8), h1 = __shfl_sync(FULL, hown, 2), h2 = __shfl_sync(FULL, hown, 3);
@@ -354,6 +372,7 @@ __device__ __forceinline__ void w_forward(const admpc_opts &o, double *sm, doubl
     const int o1 = rstr, o2 = 2 * rstr, o3 = 3 * rstr, o4 = 4 * rstr, o5 = 5 * rstr, o6 = 6 * rstr;
     double dxr = 0.0;
     double *st = sm;
+QPW_UNROLL(QPW_UFWD)
     for (int k = 0; k < N; k++, st += R_STRIDE, row += R_STRIDE, offp += R_STRIDE) {
         double *bx = xs + X_DX + (k & 1) * 8;
         if (l < 8) bx[l] = dxr;                        // lane 7 writes the zero pad
@@ -392,6 +411,7 @@ __device__ __forceinline__ void w_adjoint(double *sm, double *xs, int N, int l)
     const double cself = (l < 1 || l == 6) ? 1.0 : 0.0, mA = (l >= 1 && l < 7) ? 1.0 : 0.0;
     double dpr = (l < 7) ? sm[N * R_STRIDE + l] : 0.0;       // dpi_{N-1} = We dx_N + r_x,N
     double *st = sm + (N - 1) * R_STRIDE;
+QPW_UNROLL(QPW_UADJ)
     for (int k = N - 1; k >= 0; k--, st -= R_STRIDE) {
         if (l < 7) st[R_PB + l] = dpr;
         if (k == 0) break;
