@@ -97,6 +97,7 @@ SYMBOLS = {
     "admpc_batch_bcast_gp": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int]),
     "admpc_batch_gather": (C.c_int, [_vp, C.c_int, _dp, _dp, _ip]),
     "admpc_batch_get_gathered": (C.c_int, [_vp, _dp, _dp, _ip]),
+    "admpc_batch_gather_enable": (C.c_int, [_vp, C.c_int]),
     "admpc_batch_barrier": (C.c_int, [_vp]),
     "admpc_gp_fit": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_float)]),
     "admpc_gp_predict": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, _dp,

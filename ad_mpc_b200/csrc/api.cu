@@ -127,11 +127,23 @@ struct admpc_batch {
     long long launches = 0;
     float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
     char *pack = nullptr, *gpack = nullptr;     // packed [u | x | status] block of this rank / of all ranks (root)
+    // fused gather (admpc_batch_gather_enable): every rank writes its block straight into the root's gpack -- peer memory
+    // opened through CUDA IPC -- from the epilogue of the QP kernel; admpc_batch_gather is then only the completion barrier
+    char *gpack_peer = nullptr;                 // non-root: the root's gpack mapped into this process
+    bool gat_on = false, gat_fresh = false;     // fused path active / block written by the last feedback kernel
+    int gat_root = -1;
+    int *bar_buf = nullptr;                     // 4-byte all-reduce scratch of the completion barrier
     nccl_comm comm = nullptr;
     int rank = 0, nranks = 1;
 };
 
 static size_t rup(size_t v, size_t m) { return (v + m - 1) / m * m; }
+// bytes of one rank's packed [u | x | status] block (16-byte multiple so that every rank's slice stays aligned)
+static size_t gather_block_bytes(const Params &P)
+{
+    const size_t nu = (size_t)P.B * P.o.N * 2, nx = (size_t)P.B * (P.o.N + 1) * 7;
+    return rup((nu + nx) * sizeof(double) + (size_t)P.B * sizeof(int), 16);
+}
 // doubles per GP output in the packed blob: M points x (dz + 2) + tail (dz inverse squared length scales, y_mean)
 static size_t gp_stride(int M, int dz) { return rup((size_t)M * (dz + 2) + dz + 1, 2); }
 // whole blob: nout outputs, then the 2^(j/GP_TAB) table of the device exp2 (model.cuh)
@@ -227,9 +239,10 @@ extern "C" int admpc_batch_free(admpc_batch *h)
     if (!h) return ADMPC_E_ARG;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->gpack_peer) cudaIpcCloseMemHandle(h->gpack_peer);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
-    cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack);
+    cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack); cudaFree(h->bar_buf);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->tm0) cudaEventDestroy(h->tm0);
     if (h->tm1) cudaEventDestroy(h->tm1);
@@ -422,6 +435,7 @@ extern "C" int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state)
 extern "C" int admpc_batch_set_iterate(admpc_batch *h, const double *x, const double *u)
 {
     int r = 0;
+    if (h) h->gat_fresh = false;
     if (x) r = put_rows(h, x, h->P.xb, (h->P.o.N + 1) * 7);
     if (r == 0 && u) r = put_rows(h, u, h->P.ub, h->P.o.N * 2);
     return r;
@@ -433,6 +447,7 @@ extern "C" int admpc_batch_reset(admpc_batch *h)
     const Params &P = h->P;
     // iterate arrays are contiguous in the pool: xb .. sub
     const size_t n = (size_t)((P.sub + (size_t)P.o.N * 2 * P.Bp) - P.xb);
+    h->gat_fresh = false;
     CUDA_CHECK_RET(cudaMemsetAsync(P.xb, 0, n * sizeof(double), h->stream));
     return 0;
 }
@@ -441,12 +456,14 @@ extern "C" int admpc_batch_reset(admpc_batch *h)
 static int launch_feedback(admpc_batch *h)
 {
     const Params &P = h->P;
+    h->gat_fresh = false;
     if (P.o.model_variant == 1) {
         // Frenet variant: warp-per-instance kernel on the 6x8 stage structure (N <= 63, fused update), else / on request
         // (ADMPC_QP_VARIANT=1) the dense thread-per-instance kernel + separate update
         if (h->qp_variant != 1 && launch_qp_warp_f(P, h->stream)) {
             if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
             h->launches += 1;
+            h->gat_fresh = h->gat_on;
             return 0;
         }
         launch_qp_dense(P, h->stream);
@@ -460,7 +477,7 @@ static int launch_feedback(admpc_batch *h)
     // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
     const int variant = h->qp_variant ? h->qp_variant : 4;
     bool fused = false;
-    if (variant == 4) fused = launch_qp_warp(P, h->stream);        // one / two warps per instance, N <= 63
+    if (variant == 4) { fused = launch_qp_warp(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // one / two warps per instance, N <= 63
     if (!fused && variant >= 3 && P.ws) fused = launch_qp_smem(P, h->stream);
     if (!fused) {
         if (!P.dx) { admpc_set_error("admpc_batch_solve", "QP workspace for this kernel variant was not allocated at create"); return ADMPC_E_STATE; }
@@ -493,7 +510,7 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
 // Full SQP (nlp_solver_type "SQP", create_ros_ad_mpc.py:47-51): repeat { prepare; NLP residual check; QP; full step }
 // until every instance has converged / failed or max_iter is reached.  Synchronous: the host reads one counter per
 // iteration (how many instances are still running).  Per-instance results: admpc_batch_get_sqp_info.
-extern "C" int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double *tol4, int *iterations_run)
+static int solve_sqp_impl(admpc_batch *h, int max_iter, const double *tol4, int *iterations_run)
 {
     if (!h || max_iter < 0) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
@@ -527,6 +544,12 @@ extern "C" int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double 
     CUDA_CHECK_RET(cudaGetLastError());
     if (iterations_run) *iterations_run = it;
     return 0;
+}
+extern "C" int admpc_batch_solve_sqp(admpc_batch *h, int max_iter, const double *tol4, int *iterations_run)
+{
+    const int r = solve_sqp_impl(h, max_iter, tol4, iterations_run);
+    if (h) h->gat_fresh = false;      // the iterate moved after the last fused-gather epilogue
+    return r;
 }
 
 // per-instance outcome of the last admpc_batch_solve_sqp: acados status {0 converged, 1 NaN, 2 max_iter, 4 QP failure},
@@ -837,7 +860,7 @@ static int loop_alloc(admpc_batch *h)
 }
 
 // validity check + backup control + safety counter (+ plant step when advance != 0) for the last solve
-extern "C" int admpc_batch_postsolve(admpc_batch *h, int advance, int safe_threshold)
+static int postsolve_impl(admpc_batch *h, int advance, int safe_threshold)
 {
     if (h && h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_postsolve", "Cartesian model only (the Frenet variant takes its reference in path coordinates)"); return ADMPC_E_UNSUPPORTED; }
     if (!h) return ADMPC_E_ARG;
@@ -850,10 +873,16 @@ extern "C" int admpc_batch_postsolve(admpc_batch *h, int advance, int safe_thres
     CUDA_CHECK_RET(cudaGetLastError());
     return 0;
 }
+extern "C" int admpc_batch_postsolve(admpc_batch *h, int advance, int safe_threshold)
+{
+    const int r = postsolve_impl(h, advance, safe_threshold);
+    if (h) h->gat_fresh = false;      // the iterate moved after the last fused-gather epilogue
+    return r;
+}
 
 // `steps` closed-loop control steps entirely on the device: [make_yref] -> solve -> postsolve(advance) ...
 // log_x: optional host buffer [steps+1][B][7] receiving the plant state before every step and after the last one.
-extern "C" int admpc_batch_closed_loop(admpc_batch *h, int steps, int use_track, int safe_threshold, double *log_x)
+static int closed_loop_impl(admpc_batch *h, int steps, int use_track, int safe_threshold, double *log_x)
 {
     if (h && h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_closed_loop", "Cartesian model only (the Frenet variant takes its reference in path coordinates)"); return ADMPC_E_UNSUPPORTED; }
     if (!h || steps < 1) return ADMPC_E_ARG;
@@ -881,6 +910,12 @@ extern "C" int admpc_batch_closed_loop(admpc_batch *h, int steps, int use_track,
     if (r) return r;
     if (e != cudaSuccess) { admpc_set_error("admpc_batch_closed_loop", cudaGetErrorString(e)); return ADMPC_E_CUDA; }
     return 0;
+}
+extern "C" int admpc_batch_closed_loop(admpc_batch *h, int steps, int use_track, int safe_threshold, double *log_x)
+{
+    const int r = closed_loop_impl(h, steps, use_track, safe_threshold, log_x);
+    if (h) h->gat_fresh = false;      // the iterate moved after the last fused-gather epilogue
+    return r;
 }
 
 extern "C" int admpc_batch_get_loop_info(admpc_batch *h, int *valid, int *safe_count, int *cmd_ok, double *u_apply, double *x0)
@@ -916,6 +951,7 @@ extern "C" int admpc_batch_comm_init(admpc_batch *h, const void *id128, int rank
     memcpy(&id, id128, sizeof id);
     NCCL_CHECK_RET(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank; h->nranks = nranks;
+    if (!h->bar_buf) { CUDA_CHECK_RET(cudaMalloc(&h->bar_buf, 16)); CUDA_CHECK_RET(cudaMemset(h->bar_buf, 0, 16)); }
     return 0;
 }
 extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, const int *feat, const int *rows,
@@ -968,7 +1004,7 @@ extern "C" int admpc_batch_get_gathered(admpc_batch *h, double *u_all, double *x
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     const Params &P = h->P;
     const size_t nu = (size_t)P.B * P.o.N * 2, nx = (size_t)P.B * (P.o.N + 1) * 7;
-    const size_t bytes = (nu + nx) * sizeof(double) + (size_t)P.B * sizeof(int);
+    const size_t bytes = gather_block_bytes(P);
     for (int r = 0; r < h->nranks; r++) {
         const char *blk = h->gpack + (size_t)r * bytes;
         if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all + (size_t)r * nu, blk, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -979,6 +1015,59 @@ extern "C" int admpc_batch_get_gathered(admpc_batch *h, double *u_all, double *x
     return 0;
 }
 
+// Collective.  Sets up the FUSED gather towards `root`: the root allocates the gathered block and exports it through
+// CUDA IPC (the 64-byte handle travels by ncclBroadcast), every other rank maps it; from then on the epilogue of the QP
+// warp kernels writes each instance's [u | x | status] straight into the rank's slice of the root's block (stores over
+// NVLink, overlapped with the solve) and admpc_batch_gather shrinks to a 4-byte all-reduce = the stream-ordered
+// completion barrier.  Returns 1 when the fused path is active on all ranks, 0 when the NCCL send/recv path stays
+// (IPC unavailable, ADMPC_GATHER=nccl), < 0 on error.
+extern "C" int admpc_batch_gather_enable(admpc_batch *h, int root)
+{
+    if (!h || !h->comm) { admpc_set_error("admpc_batch_gather_enable", "communicator not initialised"); return ADMPC_E_STATE; }
+    if (root < 0 || root >= h->nranks) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    Params &P = h->P;
+    const size_t bytes = gather_block_bytes(P);
+    const char *env = getenv("ADMPC_GATHER");
+    struct { cudaIpcMemHandle_t hd; int ok; int pad[3]; } msg;
+    memset(&msg, 0, sizeof msg);
+    msg.ok = !(env && !strcmp(env, "nccl"));
+    if (h->rank == root) {
+        if (!h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, bytes * h->nranks));
+        if (msg.ok && cudaIpcGetMemHandle(&msg.hd, h->gpack) != cudaSuccess) { cudaGetLastError(); msg.ok = 0; }
+    }
+    char *d = nullptr;
+    CUDA_CHECK_RET(cudaMalloc(&d, sizeof msg));
+    CUDA_CHECK_RET(cudaMemcpyAsync(d, &msg, sizeof msg, cudaMemcpyHostToDevice, h->stream));
+    NCCL_CHECK_RET(g_nccl.Broadcast(d, d, sizeof msg, NCCL_INT8, root, h->comm, h->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(&msg, d, sizeof msg, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    int mine = msg.ok;
+    if (mine && h->rank != root && !h->gpack_peer) {
+        void *pp = nullptr;
+        if (cudaIpcOpenMemHandle(&pp, msg.hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine = 0; }
+        else h->gpack_peer = (char *)pp;
+    }
+    // everybody or nobody
+    CUDA_CHECK_RET(cudaMemcpyAsync(d, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    NCCL_CHECK_RET(g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_SUM, h->comm, h->stream));
+    int total = 0;
+    CUDA_CHECK_RET(cudaMemcpyAsync(&total, d, sizeof total, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    if (total != h->nranks) {
+        if (h->gpack_peer) { cudaIpcCloseMemHandle(h->gpack_peer); h->gpack_peer = nullptr; }
+        h->gat_on = false; h->gat_fresh = false;
+        P.gat_u = nullptr; P.gat_x = nullptr; P.gat_st = nullptr;
+        return 0;
+    }
+    const size_t nu = (size_t)P.B * P.o.N * 2, nx = (size_t)P.B * (P.o.N + 1) * 7;
+    char *slice = ((h->rank == root) ? h->gpack : h->gpack_peer) + (size_t)h->rank * bytes;
+    P.gat_u = (double *)slice; P.gat_x = P.gat_u + nu; P.gat_st = (int *)(P.gat_x + nx);
+    h->gat_on = true; h->gat_fresh = false; h->gat_root = root;
+    return 1;
+}
+
 extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, double *x_all, int *status_all)
 {
     if (!h || !h->comm) { admpc_set_error("admpc_batch_gather", "communicator not initialised"); return ADMPC_E_STATE; }
@@ -986,35 +1075,49 @@ extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, doubl
     const Params &P = h->P;
     const int N = P.o.N, B = P.B;
     const size_t nu = (size_t)B * N * 2, nx = (size_t)B * (N + 1) * 7;
-    const size_t bytes = (nu + nx) * sizeof(double) + (size_t)B * sizeof(int);      // one packed block per rank
-    if (!h->pack) CUDA_CHECK_RET(cudaMalloc(&h->pack, bytes));
-    if (h->rank == root && !h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, bytes * h->nranks));
-    // instance-major [u | x | status] block, then ONE send per rank and one receive per peer on the root
-    double *pu = (double *)h->pack, *px = pu + nu;
-    int *pst = (int *)(px + nx);
-    launch_transpose_out(P.ub, pu, B, P.Bp, N * 2, h->stream);
-    launch_transpose_out(P.xb, px, B, P.Bp, (N + 1) * 7, h->stream);
-    h->launches += 2;
-    CUDA_CHECK_RET(cudaGetLastError());
-    CUDA_CHECK_RET(cudaMemcpyAsync(pst, P.status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
-    NCCL_CHECK_RET(g_nccl.GroupStart());
-    if (h->rank != root) NCCL_CHECK_RET(g_nccl.Send(h->pack, bytes, NCCL_INT8, root, h->comm, h->stream));
-    else {
-        for (int r = 0; r < h->nranks; r++)
-            if (r != root) NCCL_CHECK_RET(g_nccl.Recv(h->gpack + (size_t)r * bytes, bytes, NCCL_INT8, r, h->comm, h->stream));
-    }
-    NCCL_CHECK_RET(g_nccl.GroupEnd());
-    if (h->rank == root) {
-        CUDA_CHECK_RET(cudaMemcpyAsync(h->gpack + (size_t)root * bytes, h->pack, bytes, cudaMemcpyDeviceToDevice, h->stream));
-        if (u_all || x_all || status_all) {
-            for (int r = 0; r < h->nranks; r++) {
-                const char *blk = h->gpack + (size_t)r * bytes;
-                if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all + (size_t)r * nu, blk, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all + (size_t)r * nx, blk + nu * sizeof(double), nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all + (size_t)r * B, blk + (nu + nx) * sizeof(double), (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-            }
-            CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    const size_t bytes = gather_block_bytes(P);                                      // one packed block per rank
+    const bool fused = h->gat_on && root == h->gat_root;
+    if (fused) {
+        // the QP kernel has already written this rank's slice of the root's block; if the iterate changed since (or a
+        // kernel variant without the fused epilogue ran), pack it now -- same destination, plain stores over NVLink
+        if (!h->gat_fresh) {
+            launch_transpose_out(P.ub, P.gat_u, B, P.Bp, N * 2, h->stream);
+            launch_transpose_out(P.xb, P.gat_x, B, P.Bp, (N + 1) * 7, h->stream);
+            h->launches += 2;
+            CUDA_CHECK_RET(cudaGetLastError());
+            CUDA_CHECK_RET(cudaMemcpyAsync(P.gat_st, P.status, (size_t)B * sizeof(int), cudaMemcpyDefault, h->stream));
         }
+        // stream-ordered completion: every rank enqueues the all-reduce after its stores, so once it has run on the
+        // root's stream all slices have landed
+        NCCL_CHECK_RET(g_nccl.AllReduce(h->bar_buf, h->bar_buf, 1, NCCL_INT32, NCCL_SUM, h->comm, h->stream));
+    } else {
+        if (!h->pack) CUDA_CHECK_RET(cudaMalloc(&h->pack, bytes));
+        if (h->rank == root && !h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, bytes * h->nranks));
+        // instance-major [u | x | status] block, then ONE send per rank and one receive per peer on the root
+        double *pu = (double *)h->pack, *px = pu + nu;
+        int *pst = (int *)(px + nx);
+        launch_transpose_out(P.ub, pu, B, P.Bp, N * 2, h->stream);
+        launch_transpose_out(P.xb, px, B, P.Bp, (N + 1) * 7, h->stream);
+        h->launches += 2;
+        CUDA_CHECK_RET(cudaGetLastError());
+        CUDA_CHECK_RET(cudaMemcpyAsync(pst, P.status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+        NCCL_CHECK_RET(g_nccl.GroupStart());
+        if (h->rank != root) NCCL_CHECK_RET(g_nccl.Send(h->pack, bytes, NCCL_INT8, root, h->comm, h->stream));
+        else {
+            for (int r = 0; r < h->nranks; r++)
+                if (r != root) NCCL_CHECK_RET(g_nccl.Recv(h->gpack + (size_t)r * bytes, bytes, NCCL_INT8, r, h->comm, h->stream));
+        }
+        NCCL_CHECK_RET(g_nccl.GroupEnd());
+        if (h->rank == root) CUDA_CHECK_RET(cudaMemcpyAsync(h->gpack + (size_t)root * bytes, h->pack, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (h->rank == root && (u_all || x_all || status_all)) {
+        for (int r = 0; r < h->nranks; r++) {
+            const char *blk = h->gpack + (size_t)r * bytes;
+            if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all + (size_t)r * nu, blk, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all + (size_t)r * nx, blk + nu * sizeof(double), nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all + (size_t)r * B, blk + (nu + nx) * sizeof(double), (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        }
+        CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     }
     return 0;       // stream-ordered: admpc_batch_wait (or the next synchronising call) completes it
 }

@@ -67,6 +67,10 @@ struct Params {
     int *sqp_status, *sqp_iter;
     const int *gp_sel;   // [Bp] cluster model of every instance (GP ensemble; zeros for a single model)
     double *nlp_res;     // [4][Bp] NLP KKT residual norms of the last check
+    // fused solution gather (multi-GPU): instance-major u [B][2N], x [B][7(N+1)], status [B] of this rank inside the
+    // root's gathered block (peer memory when the root is another GPU); null = off
+    double *gat_u, *gat_x;
+    int *gat_st;
 };
 
 #define CUDA_CHECK_RET(call)                                                         \

@@ -447,6 +447,14 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
     const double Ts = o.dt, hdt = o.dt;
     if (const int flag = P.lin_bad[i]) {         // 1: NaN/Inf in the linearisation: ACADOS_FAILURE, iterate untouched
         if (threadIdx.x == 0 && flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+        if (P.gat_x) {                           // fused gather: the (untouched) iterate still goes to the root's block
+            const int kk = threadIdx.x;
+            if (kk <= N) {
+                for (int a = 0; a < 7; a++) P.gat_x[((size_t)i * (N + 1) + kk) * 7 + a] = ATS(P.xb, kk * 7 + a);
+                if (kk < N) for (int j = 0; j < 2; j++) P.gat_u[((size_t)i * N + kk) * 2 + j] = ATS(P.ub, kk * 2 + j);
+            }
+            if (kk == 0) P.gat_st[i] = (flag == 1) ? 1 : P.status[i];
+        }
         return;                                  // 2: finished instance of the full-SQP loop, nothing to do
     }
     // ---- stage M into shared memory ------------------------------------------------------------------------------------
@@ -757,6 +765,18 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
     if (threadIdx.x == 0) {
         P.qp_status[i] = qps; P.qp_iter[i] = iter; P.status[i] = nlp_status;
         ATS(P.res_out, 0) = res0; ATS(P.res_out, 1) = res1; ATS(P.res_out, 2) = res2; ATS(P.res_out, 3) = res3;
+    }
+    // fused solution gather (multi-GPU): the updated [u | x | status] of the instance also goes, instance-major, to
+    // this rank's slice of the root's block -- peer memory over NVLink when the root is another GPU (api.cu)
+    if (P.gat_x && (isst || isterm)) {
+        const bool upd = (nlp_status == 0);
+#pragma unroll
+        for (int a = 0; a < 7; a++) P.gat_x[((size_t)i * (N + 1) + k) * 7 + a] = upd ? ATS(P.xb, k * 7 + a) + S.dx[a] : ATS(P.xb, k * 7 + a);
+        if (isst) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) P.gat_u[((size_t)i * N + k) * 2 + j] = upd ? ATS(P.ub, k * 2 + j) + S.du[j] : ATS(P.ub, k * 2 + j);
+        }
+        if (k == 0) P.gat_st[i] = nlp_status;
     }
     if (nlp_status == 0 && (isst || isterm)) {
 #pragma unroll

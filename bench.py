@@ -192,6 +192,8 @@ def run_ours(args):
         dist.broadcast_object_list(obj, src=0)
         uid = (C.c_char * 128).from_buffer_copy(obj[0])
         _lib.check(L.admpc_batch_comm_init(s.h, uid, rank, world), "comm_init")
+        gather_mode = L.admpc_batch_gather_enable(s.h, 0)       # 1: fused peer-memory gather, 0: NCCL send/recv
+        _lib.check(gather_mode, "gather_enable")
         # GP model lives on rank 0 and is broadcast over NVLink
         X = np.ascontiguousarray(model["X"]); al = np.ascontiguousarray(model["alpha"]); ell = np.ascontiguousarray(model["ell"])
         sf = np.ascontiguousarray(model["sigma_f"]); ym = np.ascontiguousarray(model["y_mean"])
@@ -405,7 +407,7 @@ def run_ours(args):
         line = {"metric": "SQP-RTI MPC solves/sec (N=20, GP-augmented)", "value": value, "unit": "solves/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config_dict(world),
+                "config": dict(config_dict(world), **({"gather": ("fused: QP-kernel epilogue stores into the root's block over NVLink peer memory (CUDA IPC) + 4-byte all-reduce" if gather_mode == 1 else "NCCL grouped send/recv of packed blocks")} if world > 1 else {})),
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "p50_ms_per_batch_call": e2e_sorted[len(e2e_sorted) // 2],
                         "p99_ms_per_batch_call": e2e_sorted[min(len(e2e_sorted) - 1, int(0.99 * len(e2e_sorted)))],

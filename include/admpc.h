@@ -219,6 +219,12 @@ int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, cons
                          const double *X, const double *alpha, const double *ell, const double *sigma_f,
                          const double *y_mean, int stage0_trigger);
 int admpc_batch_gather(admpc_batch *h, int root, double *u_all /*[nranks*B][N*2]*/, double *x_all, int *status_all);
+/* collective, optional: FUSED gather towards root.  The root exports its gathered block through CUDA IPC, every rank maps
+ * it, and from then on the QP kernels' epilogue writes each instance's [u | x | status] straight into the rank's slice
+ * of the root's block (NVLink peer stores overlapped with the solve); admpc_batch_gather becomes a 4-byte all-reduce
+ * (stream-ordered completion barrier).  Returns 1 = fused path active on all ranks, 0 = stays on NCCL send/recv
+ * (IPC unavailable or ADMPC_GATHER=nccl), < 0 error. */
+int admpc_batch_gather_enable(admpc_batch *h, int root);
 /* host copy of what the last gather left on the root's device (rank-major blocks); root only */
 int admpc_batch_get_gathered(admpc_batch *h, double *u_all, double *x_all, int *status_all);
 int admpc_batch_barrier(admpc_batch *h);

@@ -38,4 +38,30 @@ if rank == 0:
     _lib.check(L.admpc_batch_get_gathered(s.h, u2.ctypes.data_as(dp), x2.ctypes.data_as(dp), st2.ctypes.data_as(ip)), "get_gathered")
     assert np.array_equal(u2, u_all) and np.array_equal(x2, x_all) and np.array_equal(st2, st_all)
     print("GET_GATHERED_OK")
+# ---- fused gather: the QP kernel's epilogue writes straight into the root's block (CUDA IPC peer memory) ------------------
+mode = L.admpc_batch_gather_enable(s.h, 0)
+_lib.check(mode, "gather_enable")
+def check(tag):
+    u_all[:] = 0; x_all[:] = 0; st_all[:] = -1
+    _lib.check(L.admpc_batch_gather(s.h, 0, u_all.ctypes.data_as(dp), x_all.ctypes.data_as(dp), st_all.ctypes.data_as(ip)), "gather")
+    mine = (s.get_u(), s.get_x(), s.get_status()[0])
+    blocks = [None] * world if rank == 0 else None
+    dist.gather_object(mine, blocks, dst=0)
+    if rank == 0:
+        for r in range(world):
+            assert np.array_equal(u_all[r * B:(r + 1) * B], blocks[r][0]), tag
+            assert np.array_equal(x_all[r * B:(r + 1) * B], blocks[r][1]), tag
+            assert np.array_equal(st_all[r * B:(r + 1) * B], blocks[r][2]), tag
+        print("FUSED_GATHER_OK mode=%d %s" % (mode, tag))
+batch = wl.make_batch(B, N, seed=300 + rank, p=1.0)
+s.set_iterate(batch["x_init"], batch["u_init"]); s.set_x0(batch["x0"]); s.set_yref(batch["yref"])
+s.solve(); check("after solve (written by the kernel epilogue)")
+s.solve(); s.solve(); check("after two more RTI steps")
+s.set_iterate(batch["x_init"], batch["u_init"]); check("after set_iterate (explicit pack into the peer block)")
+x0bad = batch["x0"].copy(); x0bad[3, 0] = np.nan          # one NaN instance: early-exit path of the kernel
+s.set_x0(x0bad); s.solve(); check("with a failed instance")
+for rep in range(3):
+    s.set_x0(batch["x0"]); s.set_iterate(batch["x_init"], batch["u_init"])
+    s.timer_start(); s.solve(); _lib.check(L.admpc_batch_gather(s.h, 0, None, None, None), "gather"); ms = s.timer_stop()
+if rank == 0: print("solve+gather %.3f ms (mode %d)" % (ms, mode))
 s.close(); dist.destroy_process_group()
