@@ -765,25 +765,30 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_f_kernel(const Param
         P.qp_status[i] = qps; P.qp_iter[i] = iter; P.status[i] = nlp_status;
         ATS(P.res_out, 0) = res0; ATS(P.res_out, 1) = res1; ATS(P.res_out, 2) = res2; ATS(P.res_out, 3) = res3;
     }
-    // fused solution gather (multi-GPU): the updated [u | x | status] of the instance also goes, instance-major, to
-    // this rank's slice of the root's block -- peer memory over NVLink when the root is another GPU (api.cu)
-    if (P.gat_x && (isst || isterm)) {
-        const bool upd = (nlp_status == 0);
+    // fused RTI update + fused solution gather (multi-GPU): the new [u | x | status] of the instance also goes,
+    // instance-major, to this rank's slice of the root's block -- peer memory over NVLink when the root is another GPU
+    const bool upd = (nlp_status == 0);
+    if ((upd || P.gat_x) && (isst || isterm)) {
 #pragma unroll
-        for (int a = 0; a < 7; a++) P.gat_x[((size_t)i * (N + 1) + k) * 7 + a] = upd ? ATS(P.xb, k * 7 + a) + S.dx[a] : ATS(P.xb, k * 7 + a);
-        if (isst) {
-#pragma unroll
-            for (int j = 0; j < 2; j++) P.gat_u[((size_t)i * N + k) * 2 + j] = upd ? ATS(P.ub, k * 2 + j) + S.du[j] : ATS(P.ub, k * 2 + j);
+        for (int a = 0; a < 7; a++) {
+            double v = ATS(P.xb, k * 7 + a);
+            if (upd) { v += S.dx[a]; ATS(P.xb, k * 7 + a) = v; }
+            if (P.gat_x) P.gat_x[((size_t)i * (N + 1) + k) * 7 + a] = v;
         }
-        if (k == 0) P.gat_st[i] = nlp_status;
-    }
-    if (nlp_status == 0 && (isst || isterm)) {
-#pragma unroll
-        for (int a = 0; a < 7; a++) ATS(P.xb, k * 7 + a) += S.dx[a];
         if (isst) {
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                ATS(P.ub, k * 2 + j) += S.du[j];
+                double v = ATS(P.ub, k * 2 + j);
+                if (upd) { v += S.du[j]; ATS(P.ub, k * 2 + j) = v; }
+                if (P.gat_x) P.gat_u[((size_t)i * N + k) * 2 + j] = v;
+            }
+        }
+        if (k == 0 && P.gat_x) P.gat_st[i] = nlp_status;
+    }
+    if (upd && (isst || isterm)) {
+        if (isst) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
                 ATS(P.slb, k * 2 + j) = S.sl[j];
                 ATS(P.sub, k * 2 + j) = S.su[j];
             }
