@@ -36,6 +36,9 @@
 #ifndef QPW_PSHFL
 #define QPW_PSHFL 0     // 1: P_{k+1} stays in registers across the phase-3 -> phase-1 edge of the factor sweep (shuffles)
 #endif
+#ifndef QPW_PADS
+#define QPW_PADS 0      // 1: b_k[0..5] and r_k live in the 8 unused doubles of the stage record instead of being re-read from L2
+#endif
 #define QPW_PRAGMA_(x) _Pragma(#x)
 #define QPW_UNROLL(n) QPW_PRAGMA_(unroll n)
 #define ATS(arr, row) (arr)[(size_t)(row) * Bp + i]      // SoA interface arrays [row][Bp]
@@ -523,6 +526,15 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
             for (int a = 0; a < 7; a++) S.dx[a] = ATS(P.x0, a) - ATS(P.xb, a);     // x0 eliminated (nbxe_0 = 7)
         }
     }
+#if QPW_PADS
+    if (isst) {     // record pads 49, 57, 65, 69, 77, 85, 93, 97 (never written by the sweeps): b_k[0..5], r_k
+        const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp;
+        double *stp = sm + k * R_STRIDE;
+        stp[49] = ATS(lin, LIN_b + 0); stp[57] = ATS(lin, LIN_b + 1); stp[65] = ATS(lin, LIN_b + 2);
+        stp[69] = ATS(lin, LIN_b + 3); stp[77] = ATS(lin, LIN_b + 4); stp[85] = ATS(lin, LIN_b + 5);
+        stp[93] = ATS(lin, LIN_r + 0); stp[97] = ATS(lin, LIN_r + 1);
+    }
+#endif
     if (isst) {
         // cold start: primal 0 pushed thr0 inside its box, t from the box, lam = mu0 / t
 #pragma unroll
@@ -557,9 +569,18 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
         double lb[7], lq[7], lr[2];
         {
             const double *lin = P.lin + (size_t)((isst || isterm) ? k : 0) * LIN_ROWS * Bp;
+#if QPW_PADS
+            const double *stp = sm + (isst ? k : 0) * R_STRIDE;
+#pragma unroll
+            for (int a = 0; a < 7; a++) lq[a] = ATS(lin, LIN_q + a);
+            lb[0] = stp[49]; lb[1] = stp[57]; lb[2] = stp[65]; lb[3] = stp[69]; lb[4] = stp[77]; lb[5] = stp[85];
+            lb[6] = ATS(lin, LIN_b + 6);
+            lr[0] = stp[93]; lr[1] = stp[97];
+#else
 #pragma unroll
             for (int a = 0; a < 7; a++) { lq[a] = ATS(lin, LIN_q + a); lb[a] = ATS(lin, LIN_b + a); }
             lr[0] = ATS(lin, LIN_r + 0); lr[1] = ATS(lin, LIN_r + 1);
+#endif
         }
         if (NW == 1) {
 #pragma unroll
