@@ -37,7 +37,8 @@
 #define QPW_PSHFL 0     // 1: P_{k+1} stays in registers across the phase-3 -> phase-1 edge of the factor sweep (shuffles)
 #endif
 #ifndef QPW_PADS
-#define QPW_PADS 0      // 1: b_k[0..5] and r_k live in the 8 unused doubles of the stage record instead of being re-read from L2
+#define QPW_PADS 1      // 1: b_k[0..5] and r_k live in the 8 unused doubles of the stage record instead of being re-read from L2 every
+                        //    IPM iteration (uncoalesced reads: one sector per lane).  Four more slots for q_k did not pay (3.11 vs 3.10 ms)
 #endif
 #define QPW_PRAGMA_(x) _Pragma(#x)
 #define QPW_UNROLL(n) QPW_PRAGMA_(unroll n)
@@ -56,6 +57,7 @@
 #define R_GX 86     // 7   rgx0..rgx5, qt6 ; corrector roll-out leaves the adjoint base vector here
 #define R_DD 94     // 3   ddu0 ddu1 ddx_k[6]
 #define R_STRIDE 98
+#define R_TERM 8    // terminal record: r_x,N (7) | pad
 // scratch after the N stage records and the 8-double terminal record
 #define PSS 10      // row stride of P / column stride of W: even (LDS.128) and conflict-free over 7 rows (80 B)
 #define X_PS 0      // 72  P_{k+1}, full symmetric, row a at a*PSS
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
     const bool sweeper = (NW == 1) || wrp == 0;
     const int i = blockIdx.x;                    // one instance per CTA
     double *sm = smw;
-    double *xs = smw + N * R_STRIDE + 8;
+    double *xs = smw + N * R_STRIDE + R_TERM;
     double *xc = xs + X_SIZE;                    // NW == 2 only: exchange window [64][XCH_STRIDE] + 48 reduction slots
     double *red = xc + 64 * XCH_STRIDE;
     const double Ts = o.dt, hdt = o.dt;
@@ -855,14 +857,14 @@ bool launch_qp_warp(const Params &P, cudaStream_t s)
     const int N = P.o.N;
     if (N > 63) return false;
     if (N <= 31) {
-        const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE) * sizeof(double);
+        const size_t sm = (size_t)(N * R_STRIDE + R_TERM + X_SIZE) * sizeof(double);
         static SmemGuard configured;
         if (configured.need(sm)) {
             cudaFuncSetAttribute(qp_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         }
         qp_warp_kernel<1><<<P.B, 32, sm, s>>>(P);
     } else {
-        const size_t sm = (size_t)(N * R_STRIDE + 8 + X_SIZE + XCH_SIZE) * sizeof(double);
+        const size_t sm = (size_t)(N * R_STRIDE + R_TERM + X_SIZE + XCH_SIZE) * sizeof(double);
         static SmemGuard configured2;
         if (configured2.need(sm)) {
             cudaFuncSetAttribute(qp_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
