@@ -498,6 +498,13 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_f_kernel(const Param
             for (int a = 0; a < 7; a++) S.dx[a] = ATS(P.x0, a) - ATS(P.xb, a);     // x0 eliminated (nbxe_0 = 7)
         }
     }
+    if (isst) {     // record pads 55, 63, 71, 75, 83, 91, 99, 103 (never written by the sweeps): b_k[0..5], r_k
+        const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+        double *stp = sm + k * R_STRIDE;
+        stp[55] = ATS(lin, DL_b + 0); stp[63] = ATS(lin, DL_b + 1); stp[71] = ATS(lin, DL_b + 2);
+        stp[75] = ATS(lin, DL_b + 3); stp[83] = ATS(lin, DL_b + 4); stp[91] = ATS(lin, DL_b + 5);
+        stp[99] = ATS(lin, DL_r + 0); stp[103] = ATS(lin, DL_r + 1);
+    }
     if (isst) {
         // cold start: primal 0 pushed thr0 inside its box, t from the box, lam = mu0 / t
 #pragma unroll
@@ -532,9 +539,13 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_f_kernel(const Param
         double lb[7], lq[7], lr[2];
         {
             const double *lin = P.lin_d + (size_t)((isst || isterm) ? k : 0) * DL_ROWS * Bp;
+            // b_k[0..5] and r_k come from the 8 unused doubles of the stage record (staged once, see qp_warp.cu QPW_PADS)
+            const double *stp = sm + (isst ? k : 0) * R_STRIDE;
 #pragma unroll
-            for (int a = 0; a < 7; a++) { lq[a] = ATS(lin, DL_q + a); lb[a] = ATS(lin, DL_b + a); }
-            lr[0] = ATS(lin, DL_r + 0); lr[1] = ATS(lin, DL_r + 1);
+            for (int a = 0; a < 7; a++) lq[a] = ATS(lin, DL_q + a);
+            lb[0] = stp[55]; lb[1] = stp[63]; lb[2] = stp[71]; lb[3] = stp[75]; lb[4] = stp[83]; lb[5] = stp[91];
+            lb[6] = ATS(lin, DL_b + 6);
+            lr[0] = stp[99]; lr[1] = stp[103];
         }
         if (NW == 1) {
 #pragma unroll
