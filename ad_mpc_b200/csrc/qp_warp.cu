@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) qp_warp_kernel(const Params 
     for (iter = 0;; iter++) {
         // ================= residuals of the current point (stage role) ===================================================
         double pim[7], dxn[7], it[NC];
-        // b_k, q_k, r_k are re-read each iteration (L2-resident) instead of occupying 32 registers for the whole solve
+        // q_k and b_k[6] are re-read each iteration (L2-resident) instead of occupying registers for the whole solve;
+        // b_k[0..5] and r_k sit in the unused doubles of the stage record
         double lb[7], lq[7], lr[2];
         {
             const double *lin = P.lin + (size_t)((isst || isterm) ? k : 0) * LIN_ROWS * Bp;
