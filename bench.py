@@ -238,6 +238,10 @@ def run_ours(args):
     for _ in range(args.steps):
         s.set_iterate(x_init, u_init)       # same warm start every step (untimed restore of the iterate)
         s.flush_l2()
+        if world > 1:
+            # untimed alignment: the fused gather ends in an all-reduce, so without it a step would also time the other
+            # ranks' (untimed) restore / L2-flush work of the previous iteration
+            _lib.check(L.admpc_batch_barrier(s.h), "barrier")
         l0 = s.kernel_launches()
         s.timer_start()
         device_step()
