@@ -1,5 +1,5 @@
 #!/bin/bash
-# build_variant.sh NAME "-DQPW_MINB=8 ..." : links ad_mpc_b200/variants/NAME.so = the in-tree objects with qp_warp.cu
+# build_variant.sh NAME "-DQPW_UVEC=1 -DQPW_PADS=0 ..." : links ad_mpc_b200/variants/NAME.so = the in-tree objects with qp_warp.cu
 # (and qp_warp_f.cu) recompiled under the given macros.  Select it at run time with ADMPC_LIB=<path>.
 set -e
 cd "$(dirname "$0")/../ad_mpc_b200"
