@@ -24,21 +24,34 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile(src, verbose):
+    obj = src[:-3] + ".o"
+    cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed on " + src)
+    with open(obj + ".ptxas.log", "w") as f:
+        f.write(r.stderr)
+    return obj
+
+
 def build(force=False, verbose=False):
     if not (force or stale()):
         return SO
-    objs = []
+    # headers newer than an object invalidate every object; otherwise only the sources that changed are recompiled
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "admpc.h")]
+    th = max(os.path.getmtime(h) for h in hdrs)
+    todo, objs = [], []
     for src in sources():
         obj = src[:-3] + ".o"
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed on " + src)
-        with open(obj + ".ptxas.log", "w") as f:
-            f.write(r.stderr)
         objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(th, os.path.getmtime(src)):
+            todo.append(src)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        list(ex.map(lambda s: _compile(s, verbose), todo))
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", SO] + objs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -477,7 +477,8 @@ static int launch_feedback(admpc_batch *h)
     // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
     const int variant = h->qp_variant ? h->qp_variant : 4;
     bool fused = false;
-    if (variant == 4) { fused = launch_qp_warp(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // one / two warps per instance, N <= 63
+    if (variant == 5) { fused = launch_qp_half(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // half a warp per instance
+    if (!fused && variant >= 4) { fused = launch_qp_warp(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // one / two warps per instance, N <= 63
     if (!fused && variant >= 3 && P.ws) fused = launch_qp_smem(P, h->stream);
     if (!fused) {
         if (!P.dx) { admpc_set_error("admpc_batch_solve", "QP workspace for this kernel variant was not allocated at create"); return ADMPC_E_STATE; }

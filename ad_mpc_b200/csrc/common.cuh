@@ -102,6 +102,7 @@ void launch_qp(const Params &P, cudaStream_t s);
 bool launch_qp_smem(const Params &P, cudaStream_t s);   // false: horizon too long for the shared-memory variant
 int qp_smem_ws_rows(int N);
 bool launch_qp_warp(const Params &P, cudaStream_t s);   // false: N > 31
+bool launch_qp_half(const Params &P, cudaStream_t s);   // half a warp per instance, false: horizon too long for shared memory
 void launch_transpose_in(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);   // [B][F] -> [F][Bp]
 void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);  // [F][Bp] -> [B][F]
 void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]
