@@ -13,7 +13,7 @@ class AdmpcOpts(C.Structure):
     _fields_ = [
         ("N", C.c_int), ("iter_max", C.c_int), ("gp_enabled", C.c_int), ("gp_nout", C.c_int), ("gp_M", C.c_int),
         ("gp_dz", C.c_int), ("gp_stage0_trigger", C.c_int), ("model_variant", C.c_int),
-        ("gp_feat", C.c_int * DZMAX), ("gp_row", C.c_int * GPOUT_MAX),
+        ("gp_feat", C.c_int * DZMAX), ("gp_row", C.c_int * GPOUT_MAX), ("gp_precision", C.c_int), ("reserved_", C.c_int),
         ("dt", C.c_double), ("W", C.c_double * 9), ("We", C.c_double * 7),
         ("zl", C.c_double * 2), ("zu", C.c_double * 2), ("Zl", C.c_double * 2), ("Zu", C.c_double * 2),
         ("lbu", C.c_double * 2), ("ubu", C.c_double * 2), ("lbx", C.c_double), ("ubx", C.c_double),
@@ -21,7 +21,7 @@ class AdmpcOpts(C.Structure):
         ("cr2", C.c_double),
         ("mu0", C.c_double), ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double),
         ("tol_comp", C.c_double), ("alpha_min", C.c_double), ("lam_min", C.c_double), ("t_min", C.c_double),
-        ("thr0", C.c_double), ("reg", C.c_double),
+        ("thr0", C.c_double), ("reg", C.c_double), ("blend_min", C.c_double), ("blend_max", C.c_double),
     ]
 
 
@@ -62,6 +62,8 @@ SYMBOLS = {
     "admpc_batch_set_kappa": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_gp_state": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_iterate": (C.c_int, [_vp, _dp, _dp]),
+    "admpc_batch_set_duals": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "sim_car_acados_update_qp_solver_cond_N": (C.c_int, [_vp, C.c_int]),
     "admpc_batch_reset": (C.c_int, [_vp]),
     "admpc_batch_solve": (C.c_int, [_vp]),
     "admpc_batch_wait": (C.c_int, [_vp]),
@@ -75,6 +77,18 @@ SYMBOLS = {
     "admpc_batch_get_lin": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "admpc_batch_solve_host": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip]),
     "admpc_batch_solve_host_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "admpc_pipe_create": (C.c_int, [_op, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "admpc_pipe_free": (C.c_int, [_vp]),
+    "admpc_pipe_chunks": (C.c_int, [_vp]),
+    "admpc_pipe_chunk": (_vp, [_vp, C.c_int, _ip, _ip]),
+    "admpc_pipe_set_gp": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "admpc_pipe_set_iterate": (C.c_int, [_vp, _dp, _dp]),
+    "admpc_pipe_set_track": (C.c_int, [_vp, C.c_int, _dp, C.c_int, C.c_double, C.c_int]),
+    "admpc_pipe_solve_host": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "admpc_pipe_solve_host_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "admpc_pipe_solve_pose": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip]),
+    "admpc_pipe_wait": (C.c_int, [_vp]),
+    "admpc_pipe_kernel_launches": (C.c_longlong, [_vp]),
     "admpc_batch_set_track": (C.c_int, [_vp, C.c_int, _dp, C.c_int, C.c_double]),
     "admpc_batch_set_track_anchor": (C.c_int, [_vp, C.c_int]),
     "admpc_batch_make_yref": (C.c_int, [_vp]),

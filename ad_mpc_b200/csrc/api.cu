@@ -95,7 +95,7 @@ static int nccl_load()
         int r_ = (call);                                                                                  \
         if (r_ != 0) { admpc_set_error(#call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); return ADMPC_E_NCCL; } \
     } while (0)
-enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 
 // ---------------------------------------------------------------------------------------------- batch handle ----
 struct admpc_batch {
@@ -132,6 +132,11 @@ struct admpc_batch {
     char *gpack_peer = nullptr;                 // non-root: the root's gpack mapped into this process
     bool gat_on = false, gat_fresh = false;     // fused path active / block written by the last feedback kernel
     int gat_root = -1;
+    // The root's block is DOUBLE-BUFFERED: writes (kernel epilogue or explicit pack) go to half gat_par, every gather call
+    // flips it, so a rank that runs ahead never overwrites the half the root is still copying out (the all-reduce of the
+    // NEXT gather orders the write after that: it cannot complete before the root has passed its previous D2H copies).
+    int gat_par = 0, gat_last = 0;
+    bool b_uniform = true;                      // every rank of the communicator holds the same number of instances
     int *bar_buf = nullptr;                     // 4-byte all-reduce scratch of the completion barrier
     nccl_comm comm = nullptr;
     int rank = 0, nranks = 1;
@@ -303,6 +308,8 @@ static int upload_gp(admpc_batch *h, int K, int nout, int M, int dz, const int *
     const size_t cbytes = (size_t)K * dz * sizeof(double);
     if (bytes + cbytes > h->gp_blob_cap) {
         cudaFree(h->gp_blob);
+        h->gp_blob = nullptr; h->gp_blob_cap = 0;                   // nothing may keep pointing at the freed block
+        P.gp.blob = nullptr; P.o.gp_enabled = 0;
         CUDA_CHECK_RET(cudaMalloc(&h->gp_blob, bytes + cbytes));
         h->gp_blob_cap = bytes + cbytes;
     }
@@ -400,14 +407,15 @@ static int put_rows(admpc_batch *h, const double *host, double *dst, int F)
 
 extern "C" int admpc_batch_set_x0(admpc_batch *h, const double *x0)
 {
+    if (!h) return ADMPC_E_ARG;
     int r = put_rows(h, x0, (double *)h->P.x0, 7);
     if (r == 0 && !h->gps_set) {   // gp_state defaults to the initial state (quad_3d_optimizer.py:549)
         CUDA_CHECK_RET(cudaMemcpyAsync((void *)h->P.gps, h->P.x0, (size_t)7 * h->P.Bp * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
     return r;
 }
-extern "C" int admpc_batch_set_yref(admpc_batch *h, const double *yref) { return put_rows(h, yref, (double *)h->P.yref, h->P.o.N * 9 + 7); }
-extern "C" int admpc_batch_set_p(admpc_batch *h, const double *p) { return put_rows(h, p, (double *)h->P.p, h->P.o.N); }
+extern "C" int admpc_batch_set_yref(admpc_batch *h, const double *yref) { return h ? put_rows(h, yref, (double *)h->P.yref, h->P.o.N * 9 + 7) : ADMPC_E_ARG; }
+extern "C" int admpc_batch_set_p(admpc_batch *h, const double *p) { return h ? put_rows(h, p, (double *)h->P.p, h->P.o.N) : ADMPC_E_ARG; }
 extern "C" int admpc_batch_set_kappa(admpc_batch *h, const double *kappa)
 {
     if (!h) return ADMPC_E_ARG;
@@ -434,10 +442,27 @@ extern "C" int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state)
 }
 extern "C" int admpc_batch_set_iterate(admpc_batch *h, const double *x, const double *u)
 {
+    if (!h) return ADMPC_E_ARG;
     int r = 0;
-    if (h) h->gat_fresh = false;
+    h->gat_fresh = false;
     if (x) r = put_rows(h, x, h->P.xb, (h->P.o.N + 1) * 7);
     if (r == 0 && u) r = put_rows(h, u, h->P.ub, h->P.o.N * 2);
+    return r;
+}
+// multipliers and slacks of the iterate (acados load_iterate restores all of x, u, pi, lam, t, sl, su:
+// ad_3d_optimizer.py:454).  The RTI step overwrites them with the QP's; the full-SQP loop's first KKT check reads them.
+// Host layouts [B][N*7], [B][N*10], [B][N*10], [B][N*2], [B][N*2]; any pointer may be NULL (left unchanged).
+extern "C" int admpc_batch_set_duals(admpc_batch *h, const double *pi, const double *lam, const double *t, const double *sl,
+                                     const double *su)
+{
+    if (!h) return ADMPC_E_ARG;
+    const int N = h->P.o.N;
+    int r = 0;
+    if (pi) r = put_rows(h, pi, h->P.pib, N * 7);
+    if (r == 0 && lam) r = put_rows(h, lam, h->P.lamb, N * NC);
+    if (r == 0 && t) r = put_rows(h, t, h->P.tb, N * NC);
+    if (r == 0 && sl) r = put_rows(h, sl, h->P.slb, N * 2);
+    if (r == 0 && su) r = put_rows(h, su, h->P.sub, N * 2);
     return r;
 }
 extern "C" int admpc_batch_reset(admpc_batch *h)
@@ -596,13 +621,14 @@ static int get_rows(admpc_batch *h, const double *src, double *host, int F)
     CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     return 0;
 }
-extern "C" int admpc_batch_get_u(admpc_batch *h, double *u) { return get_rows(h, h->P.ub, u, h->P.o.N * 2); }
-extern "C" int admpc_batch_get_x(admpc_batch *h, double *x) { return get_rows(h, h->P.xb, x, (h->P.o.N + 1) * 7); }
-extern "C" int admpc_batch_get_pi(admpc_batch *h, double *pi) { return get_rows(h, h->P.pib, pi, h->P.o.N * 7); }
-extern "C" int admpc_batch_get_lam(admpc_batch *h, double *lam) { return get_rows(h, h->P.lamb, lam, h->P.o.N * NC); }
-extern "C" int admpc_batch_get_t(admpc_batch *h, double *t) { return get_rows(h, h->P.tb, t, h->P.o.N * NC); }
+extern "C" int admpc_batch_get_u(admpc_batch *h, double *u) { return h ? get_rows(h, h->P.ub, u, h->P.o.N * 2) : ADMPC_E_ARG; }
+extern "C" int admpc_batch_get_x(admpc_batch *h, double *x) { return h ? get_rows(h, h->P.xb, x, (h->P.o.N + 1) * 7) : ADMPC_E_ARG; }
+extern "C" int admpc_batch_get_pi(admpc_batch *h, double *pi) { return h ? get_rows(h, h->P.pib, pi, h->P.o.N * 7) : ADMPC_E_ARG; }
+extern "C" int admpc_batch_get_lam(admpc_batch *h, double *lam) { return h ? get_rows(h, h->P.lamb, lam, h->P.o.N * NC) : ADMPC_E_ARG; }
+extern "C" int admpc_batch_get_t(admpc_batch *h, double *t) { return h ? get_rows(h, h->P.tb, t, h->P.o.N * NC) : ADMPC_E_ARG; }
 extern "C" int admpc_batch_get_slacks(admpc_batch *h, double *sl, double *su)
 {
+    if (!h) return ADMPC_E_ARG;
     int r = 0;
     if (sl) r = get_rows(h, h->P.slb, sl, h->P.o.N * 2);
     if (r == 0 && su) r = get_rows(h, h->P.sub, su, h->P.o.N * 2);
@@ -783,6 +809,7 @@ extern "C" int admpc_batch_set_track(admpc_batch *h, int L, const double *traj, 
     if (h && h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_set_track", "Cartesian model only (the Frenet variant takes its reference in path coordinates)"); return ADMPC_E_UNSUPPORTED; }
     if (!h) return ADMPC_E_ARG;
     if (H < h->P.o.N) { admpc_set_error("admpc_batch_set_track", "reference horizon H must be >= N (gp_ad_mpc_node.py:172-175 single-point branch is not supported)"); return ADMPC_E_UNSUPPORTED; }
+    if (h->track_anchor && H > 64) { admpc_set_error("admpc_batch_set_track", "anchored mode supports H <= 64"); return ADMPC_E_UNSUPPORTED; }
     TrackHost T;
     int r = refgen_build_track(L, traj, H, traj_dt, T);
     if (r) { admpc_set_error("admpc_batch_set_track", "bad track (need L >= 2 rows of [vel,x,y,psi,cdist,curv], H >= 4)"); return r; }
@@ -812,6 +839,7 @@ extern "C" int admpc_batch_make_yref(admpc_batch *h)
 {
     if (!h) return ADMPC_E_ARG;
     if (!h->track) { admpc_set_error("admpc_batch_make_yref", "no track set"); return ADMPC_E_STATE; }
+    if (h->track_anchor && h->track_H > 64) { admpc_set_error("admpc_batch_make_yref", "anchored mode supports H <= 64"); return ADMPC_E_UNSUPPORTED; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     launch_refgen(h->P, h->track, h->track_L, h->track_H, h->track_dt, h->track_anchor, h->track_info, h->stream);
     h->launches++;
@@ -826,7 +854,11 @@ extern "C" int admpc_batch_solve_pose_async(admpc_batch *h, const double *x0, co
     if (!h || !x0) return ADMPC_E_ARG;
     int r;
     if ((r = admpc_batch_set_x0(h, x0))) return r;
-    if (p_scalar && (r = admpc_batch_set_p_scalar(h, p_scalar))) return r;
+    if (p_scalar) { if ((r = admpc_batch_set_p_scalar(h, p_scalar))) return r; }
+    else if (h->P.o.blend_max > h->P.o.blend_min) {        // no p from the host: blend from the measured v_x on the device
+        launch_blend(h->P, h->stream);
+        h->launches++;
+    }
     if ((r = admpc_batch_make_yref(h))) return r;
     return solve_host_enqueue(h, nullptr, nullptr, nullptr, u_out, x_out, status_out);
 }
@@ -953,6 +985,13 @@ extern "C" int admpc_batch_comm_init(admpc_batch *h, const void *id128, int rank
     NCCL_CHECK_RET(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank; h->nranks = nranks;
     if (!h->bar_buf) { CUDA_CHECK_RET(cudaMalloc(&h->bar_buf, 16)); CUDA_CHECK_RET(cudaMemset(h->bar_buf, 0, 16)); }
+    // the gathered layout is rank * block: every rank must hold the same number of instances (max B == min B)
+    int bb[2] = {h->P.B, -h->P.B};
+    CUDA_CHECK_RET(cudaMemcpyAsync(h->bar_buf + 2, bb, sizeof bb, cudaMemcpyHostToDevice, h->stream));
+    NCCL_CHECK_RET(g_nccl.AllReduce(h->bar_buf + 2, h->bar_buf + 2, 2, NCCL_INT32, NCCL_MAX, h->comm, h->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(bb, h->bar_buf + 2, sizeof bb, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    h->b_uniform = (bb[0] == -bb[1]);
     return 0;
 }
 extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, const int *feat, const int *rows,
@@ -960,15 +999,20 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
                                     const double *y_mean, int stage0_trigger)
 {
     if (!h || !h->comm) { admpc_set_error("admpc_batch_bcast_gp", "communicator not initialised"); return ADMPC_E_STATE; }
+    if (root < 0 || root >= h->nranks) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
-    // header (sizes, feature map) first, then the packed blob, both over NCCL on the handle's stream
-    int hdr[4 + ADMPC_DZMAX + ADMPC_GPOUT_MAX] = {0};
+    // A collective: whatever happens locally, every rank takes part in the header broadcast, the agreement all-reduce
+    // and (only if all ranks are fine) the blob broadcast, so that a local failure can never leave the peers blocked.
+    int hdr[5 + ADMPC_DZMAX + ADMPC_GPOUT_MAX] = {0};
+    int rc = 0;
     if (h->rank == root) {
-        int r = upload_gp(h, 1, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, nullptr, stage0_trigger);   // single model
-        if (r) return r;
-        hdr[0] = nout; hdr[1] = M; hdr[2] = dz; hdr[3] = stage0_trigger;
-        for (int d = 0; d < dz; d++) hdr[4 + d] = feat[d];
-        for (int j = 0; j < nout; j++) hdr[4 + ADMPC_DZMAX + j] = rows[j];
+        rc = upload_gp(h, 1, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, nullptr, stage0_trigger);   // single model
+        hdr[0] = (rc == 0);
+        if (rc == 0) {
+            hdr[1] = nout; hdr[2] = M; hdr[3] = dz; hdr[4] = stage0_trigger;
+            for (int d = 0; d < dz; d++) hdr[5 + d] = feat[d];
+            for (int j = 0; j < nout; j++) hdr[5 + ADMPC_DZMAX + j] = rows[j];
+        }
     }
     int *dh = h->stage_status;
     CUDA_CHECK_RET(cudaMemcpyAsync(dh, hdr, sizeof hdr, cudaMemcpyHostToDevice, h->stream));
@@ -976,23 +1020,51 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
     CUDA_CHECK_RET(cudaMemcpyAsync(hdr, dh, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     Params &P = h->P;
-    if (h->rank != root) {
-        nout = hdr[0]; M = hdr[1]; dz = hdr[2];
-        const size_t stride = gp_stride(M, dz);
-        const size_t bytes = gp_blob_doubles(nout, M, dz) * sizeof(double);
-        if (bytes > h->gp_blob_cap) {
-            cudaFree(h->gp_blob);
-            CUDA_CHECK_RET(cudaMalloc(&h->gp_blob, bytes));
-            h->gp_blob_cap = bytes;
+    int bad = hdr[0] ? 0 : 1;
+    if (h->rank != root && hdr[0]) {
+        // the same checks upload_gp applies on the root, on the sizes that arrived
+        nout = hdr[1]; M = hdr[2]; dz = hdr[3];
+        bool okv = nout >= 0 && nout <= ADMPC_GPOUT_MAX && (nout == 0 || (M > 0 && dz > 0 && dz <= ADMPC_DZMAX));
+        for (int d = 0; okv && nout > 0 && d < dz; d++) okv = hdr[5 + d] >= 2 && hdr[5 + d] <= 8;
+        for (int j = 0; okv && j < nout; j++) okv = hdr[5 + ADMPC_DZMAX + j] >= 3 && hdr[5 + ADMPC_DZMAX + j] <= 5;
+        const size_t bytes = okv && nout > 0 ? gp_blob_doubles(nout, M, dz) * sizeof(double) : 0;
+        if (okv && bytes > 220 * 1024) okv = false;
+        if (!okv) { admpc_set_error("admpc_batch_bcast_gp", "received GP header is invalid / exceeds the 220 KB staging budget"); bad = 1; rc = ADMPC_E_UNSUPPORTED; }
+        else if (nout == 0) { P.o.gp_enabled = 0; }
+        else {
+            if (bytes > h->gp_blob_cap) {
+                cudaFree(h->gp_blob);
+                h->gp_blob = nullptr; h->gp_blob_cap = 0; P.gp.blob = nullptr; P.o.gp_enabled = 0;
+                if (cudaMalloc(&h->gp_blob, bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    h->gp_blob = nullptr;
+                    admpc_set_error("admpc_batch_bcast_gp", "cudaMalloc of the GP blob failed");
+                    bad = 1; rc = ADMPC_E_CUDA;
+                } else h->gp_blob_cap = bytes;
+            }
+            if (!bad) {
+                const size_t stride = gp_stride(M, dz);
+                P.gp.blob = h->gp_blob; P.gp.bytes = (int)bytes; P.gp.stride_out = (int)stride;
+                P.gp.n_models = 1; P.gp.model_doubles = (int)(stride * nout); P.gp.centroids = nullptr;
+                CUDA_CHECK_RET(cudaMemsetAsync(h->gp_sel, 0, (size_t)P.Bp * sizeof(int), h->stream));
+                P.o.gp_enabled = 1; P.o.gp_nout = nout; P.o.gp_M = M; P.o.gp_dz = dz; P.o.gp_stage0_trigger = hdr[4];
+                for (int d = 0; d < dz; d++) P.o.gp_feat[d] = hdr[5 + d];
+                for (int j = 0; j < nout; j++) P.o.gp_row[j] = hdr[5 + ADMPC_DZMAX + j];
+            }
         }
-        P.gp.blob = h->gp_blob; P.gp.bytes = (int)bytes; P.gp.stride_out = (int)stride;
-        P.gp.n_models = 1; P.gp.model_doubles = (int)(stride * nout); P.gp.centroids = nullptr;
-        CUDA_CHECK_RET(cudaMemsetAsync(h->gp_sel, 0, (size_t)P.Bp * sizeof(int), h->stream));
-        P.o.gp_enabled = nout > 0; P.o.gp_nout = nout; P.o.gp_M = M; P.o.gp_dz = dz; P.o.gp_stage0_trigger = hdr[3];
-        for (int d = 0; d < dz; d++) P.o.gp_feat[d] = hdr[4 + d];
-        for (int j = 0; j < nout; j++) P.o.gp_row[j] = hdr[4 + ADMPC_DZMAX + j];
     }
-    if (P.gp.bytes > 0)
+    // everybody or nobody
+    CUDA_CHECK_RET(cudaMemcpyAsync(h->bar_buf + 1, &bad, sizeof bad, cudaMemcpyHostToDevice, h->stream));
+    NCCL_CHECK_RET(g_nccl.AllReduce(h->bar_buf + 1, h->bar_buf + 1, 1, NCCL_INT32, NCCL_SUM, h->comm, h->stream));
+    int nbad = 0;
+    CUDA_CHECK_RET(cudaMemcpyAsync(&nbad, h->bar_buf + 1, sizeof nbad, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    if (nbad) {
+        P.o.gp_enabled = 0;
+        if (rc == 0) { admpc_set_error("admpc_batch_bcast_gp", "another rank could not take the GP model"); rc = ADMPC_E_STATE; }
+        return rc;
+    }
+    if (P.o.gp_enabled && P.gp.bytes > 0)
         NCCL_CHECK_RET(g_nccl.Broadcast(h->gp_blob, h->gp_blob, (size_t)P.gp.bytes / sizeof(double), NCCL_FLOAT64, root, h->comm, h->stream));
     CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1007,13 +1079,23 @@ extern "C" int admpc_batch_get_gathered(admpc_batch *h, double *u_all, double *x
     const size_t nu = (size_t)P.B * P.o.N * 2, nx = (size_t)P.B * (P.o.N + 1) * 7;
     const size_t bytes = gather_block_bytes(P);
     for (int r = 0; r < h->nranks; r++) {
-        const char *blk = h->gpack + (size_t)r * bytes;
+        const char *blk = h->gpack + ((size_t)h->gat_last * h->nranks + r) * bytes;
         if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all + (size_t)r * nu, blk, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all + (size_t)r * nx, blk + nu * sizeof(double), nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all + (size_t)r * P.B, blk + (nu + nx) * sizeof(double), (size_t)P.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     }
     CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// this rank's slice of the half of the root's block that is written next
+static void gather_point(admpc_batch *h)
+{
+    Params &P = h->P;
+    const size_t bytes = gather_block_bytes(P);
+    const size_t nu = (size_t)P.B * P.o.N * 2, nx = (size_t)P.B * (P.o.N + 1) * 7;
+    char *slice = ((h->rank == h->gat_root) ? h->gpack : h->gpack_peer) + ((size_t)h->gat_par * h->nranks + h->rank) * bytes;
+    P.gat_u = (double *)slice; P.gat_x = P.gat_u + nu; P.gat_st = (int *)(P.gat_x + nx);
 }
 
 // Collective.  Sets up the FUSED gather towards `root`: the root allocates the gathered block and exports it through
@@ -1026,6 +1108,7 @@ extern "C" int admpc_batch_gather_enable(admpc_batch *h, int root)
 {
     if (!h || !h->comm) { admpc_set_error("admpc_batch_gather_enable", "communicator not initialised"); return ADMPC_E_STATE; }
     if (root < 0 || root >= h->nranks) return ADMPC_E_ARG;
+    if (!h->b_uniform) { admpc_set_error("admpc_batch_gather_enable", "ranks hold different numbers of instances (pad the batch to a multiple of the rank count)"); return ADMPC_E_UNSUPPORTED; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     Params &P = h->P;
     const size_t bytes = gather_block_bytes(P);
@@ -1034,7 +1117,7 @@ extern "C" int admpc_batch_gather_enable(admpc_batch *h, int root)
     memset(&msg, 0, sizeof msg);
     msg.ok = !(env && !strcmp(env, "nccl"));
     if (h->rank == root) {
-        if (!h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, bytes * h->nranks));
+        if (!h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, 2 * bytes * h->nranks));       // two halves, see gat_par
         if (msg.ok && cudaIpcGetMemHandle(&msg.hd, h->gpack) != cudaSuccess) { cudaGetLastError(); msg.ok = 0; }
     }
     char *d = nullptr;
@@ -1062,19 +1145,19 @@ extern "C" int admpc_batch_gather_enable(admpc_batch *h, int root)
         P.gat_u = nullptr; P.gat_x = nullptr; P.gat_st = nullptr;
         return 0;
     }
-    const size_t nu = (size_t)P.B * P.o.N * 2, nx = (size_t)P.B * (P.o.N + 1) * 7;
-    char *slice = ((h->rank == root) ? h->gpack : h->gpack_peer) + (size_t)h->rank * bytes;
-    P.gat_u = (double *)slice; P.gat_x = P.gat_u + nu; P.gat_st = (int *)(P.gat_x + nx);
-    h->gat_on = true; h->gat_fresh = false; h->gat_root = root;
+    h->gat_on = true; h->gat_fresh = false; h->gat_root = root; h->gat_par = 0; h->gat_last = 0;
+    gather_point(h);
     return 1;
 }
 
 extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, double *x_all, int *status_all)
 {
     if (!h || !h->comm) { admpc_set_error("admpc_batch_gather", "communicator not initialised"); return ADMPC_E_STATE; }
+    if (!h->b_uniform) { admpc_set_error("admpc_batch_gather", "ranks hold different numbers of instances (pad the batch to a multiple of the rank count)"); return ADMPC_E_UNSUPPORTED; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     const Params &P = h->P;
     const int N = P.o.N, B = P.B;
+    int half = 0;                                  // which half of the root's block this call delivers
     const size_t nu = (size_t)B * N * 2, nx = (size_t)B * (N + 1) * 7;
     const size_t bytes = gather_block_bytes(P);                                      // one packed block per rank
     const bool fused = h->gat_on && root == h->gat_root;
@@ -1091,9 +1174,14 @@ extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, doubl
         // stream-ordered completion: every rank enqueues the all-reduce after its stores, so once it has run on the
         // root's stream all slices have landed
         NCCL_CHECK_RET(g_nccl.AllReduce(h->bar_buf, h->bar_buf, 1, NCCL_INT32, NCCL_SUM, h->comm, h->stream));
+        // later writes of this rank go to the other half (the half just delivered may still be read out by the root)
+        half = h->gat_par;
+        h->gat_par ^= 1;
+        h->gat_fresh = false;
+        gather_point(h);
     } else {
         if (!h->pack) CUDA_CHECK_RET(cudaMalloc(&h->pack, bytes));
-        if (h->rank == root && !h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, bytes * h->nranks));
+        if (h->rank == root && !h->gpack) CUDA_CHECK_RET(cudaMalloc(&h->gpack, 2 * bytes * h->nranks));
         // instance-major [u | x | status] block, then ONE send per rank and one receive per peer on the root
         double *pu = (double *)h->pack, *px = pu + nu;
         int *pst = (int *)(px + nx);
@@ -1111,9 +1199,10 @@ extern "C" int admpc_batch_gather(admpc_batch *h, int root, double *u_all, doubl
         NCCL_CHECK_RET(g_nccl.GroupEnd());
         if (h->rank == root) CUDA_CHECK_RET(cudaMemcpyAsync(h->gpack + (size_t)root * bytes, h->pack, bytes, cudaMemcpyDeviceToDevice, h->stream));
     }
+    h->gat_last = half;
     if (h->rank == root && (u_all || x_all || status_all)) {
         for (int r = 0; r < h->nranks; r++) {
-            const char *blk = h->gpack + (size_t)r * bytes;
+            const char *blk = h->gpack + ((size_t)half * h->nranks + r) * bytes;
             if (u_all) CUDA_CHECK_RET(cudaMemcpyAsync(u_all + (size_t)r * nu, blk, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             if (x_all) CUDA_CHECK_RET(cudaMemcpyAsync(x_all + (size_t)r * nx, blk + nu * sizeof(double), nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             if (status_all) CUDA_CHECK_RET(cudaMemcpyAsync(status_all + (size_t)r * B, blk + (nu + nx) * sizeof(double), (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1140,7 +1229,7 @@ struct sim_car_solver_capsule {
     admpc_batch *h = nullptr;
     int N = 0;
     std::vector<double> x0, yref, p, kappa, x, u, pi, lam, t, sl, su;
-    bool iterate_dirty = false, duals_stale = false;
+    bool iterate_dirty = false, duals_stale = false, duals_dirty = false;
     double *hio = nullptr, *dio = nullptr;      // pinned host / device staging blocks of the single-instance fast path
     int status = 0, qp_status = 0, qp_iter = 0, sqp_iter = 1;
     bool nlp_sqp = false;            // nlp_solver_type: false "SQP_RTI" (shipped), true "SQP" (point-reference mode)
@@ -1209,6 +1298,14 @@ extern "C" int sim_car_acados_update_time_steps(sim_car_solver_capsule *c, int N
     c->opts.dt = ts[0];
     return 0;
 }
+// acados_solver_sim_car.h:137.  The reference's generated body prints "no partial condensing solver is used" and exits
+// (.c:810-816: the shipped solver is FULL_CONDENSING_HPIPM); this library never condenses (OCP-structured Riccati IPM),
+// so the call is accepted and ignored.
+extern "C" int sim_car_acados_update_qp_solver_cond_N(sim_car_solver_capsule *c, int qp_solver_cond_N)
+{
+    (void)qp_solver_cond_N;
+    return c ? 0 : ADMPC_E_ARG;
+}
 extern "C" int sim_car_acados_update_params(sim_car_solver_capsule *c, int stage, double *value, int np)
 {
     if (!c || !c->h || !value) return ADMPC_E_ARG;
@@ -1266,6 +1363,33 @@ extern "C" int sim_car_acados_set(sim_car_solver_capsule *c, int stage, const ch
         if (n != 2 || stage >= N) return ADMPC_E_ARG;
         memcpy(&c->u[(size_t)stage * 2], v, sizeof(double) * 2); c->iterate_dirty = true; return 0;
     }
+    // multipliers / slacks of the iterate (acados load_iterate, ad_3d_optimizer.py:454): same layouts as sim_car_acados_get
+    if (!strcmp(field, "pi") || !strcmp(field, "sl") || !strcmp(field, "su") || !strcmp(field, "lam") || !strcmp(field, "t")) {
+        if (stage >= N) return n == 0 ? 0 : ADMPC_E_ARG;               // nothing lives at the terminal node
+        if (c->duals_stale) {                                           // start from what the device holds
+            int r;
+            if ((r = admpc_batch_get_pi(c->h, c->pi.data()))) return r;
+            if ((r = admpc_batch_get_lam(c->h, c->lam.data()))) return r;
+            if ((r = admpc_batch_get_t(c->h, c->t.data()))) return r;
+            if ((r = admpc_batch_get_slacks(c->h, c->sl.data(), c->su.data()))) return r;
+            c->duals_stale = false;
+        }
+        if (!strcmp(field, "pi")) { if (n != 7) return ADMPC_E_ARG; memcpy(&c->pi[(size_t)stage * 7], v, 56); }
+        else if (!strcmp(field, "sl")) { if (n != 2) return ADMPC_E_ARG; memcpy(&c->sl[(size_t)stage * 2], v, 16); }
+        else if (!strcmp(field, "su")) { if (n != 2) return ADMPC_E_ARG; memcpy(&c->su[(size_t)stage * 2], v, 16); }
+        else {
+            double *d = ((field[0] == 'l') ? c->lam : c->t).data() + (size_t)stage * NC;
+            if (stage >= 1) { if (n != NC) return ADMPC_E_ARG; memcpy(d, v, sizeof(double) * NC); }
+            else {      // stage 0 arrives in the acados layout [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(2) | us(2)]
+                if (n != 22) return ADMPC_E_ARG;
+                d[0] = v[0]; d[1] = v[1]; d[3] = v[9]; d[4] = v[10];
+                for (int j = 0; j < 4; j++) d[6 + j] = v[18 + j];
+                d[2] = (field[0] == 'l') ? 0.0 : 1.0; d[5] = d[2];        // no state bound at stage 0 (x0 is eliminated)
+            }
+        }
+        c->duals_dirty = true;
+        return 0;
+    }
     admpc_set_error("sim_car_acados_set", "unknown field");
     return ADMPC_E_ARG;
 }
@@ -1275,6 +1399,10 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
     if (!c || !c->h) { admpc_set_error("sim_car_acados_solve", "solver not created"); return ADMPC_E_STATE; }
     admpc_batch *h = c->h;
     int r;
+    if (c->duals_dirty) {       // multipliers set by the caller (load_iterate): ship them before the solve
+        if ((r = admpc_batch_set_duals(h, c->pi.data(), c->lam.data(), c->t.data(), c->sl.data(), c->su.data()))) return r;
+        c->duals_dirty = false;
+    }
     if (!c->nlp_sqp) {
         // RTI fast path: ONE packed host->device block, ONE packed device->host block, one synchronisation
         const int N = c->N, nyr = 9 * N + 7, nx = (N + 1) * 7, nu = 2 * N;

@@ -83,14 +83,34 @@ __global__ void __launch_bounds__(128) postsolve_kernel(const Params P, const Lo
 #pragma unroll
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
     }
+    double vx_next = 0.0;
 #pragma unroll
     for (int c = 0; c < 7; c++) {
         const double xn = fma(h, ax[c], x[c]);
+        if (c == 3) vx_next = xn;
         Lp.x_next[(size_t)c * Bp + i] = xn;
         ((double *)P.x0)[(size_t)c * Bp + i] = xn;
         ((double *)P.gps)[(size_t)c * Bp + i] = xn;        // gp_state follows the measured state (quad_3d_optimizer.py:549)
     }
+    // the reference recomputes the kinematic/dynamic blend from the measured v_x before every solve
+    // (ad_3d_optimizer.py:443-450): the next solve (and the next plant step) of this vehicle uses it on all stages
+    if (o.blend_max > o.blend_min) {
+        const double pn = fmin(fmax((vx_next - o.blend_min) / (o.blend_max - o.blend_min), 0.0), 1.0);
+        for (int k = 0; k < N; k++) ((double *)P.p)[(size_t)k * Bp + i] = pn;
+    }
 }
+
+// p of every stage from the current x0 (pose-only step without a p from the host), ad_3d_optimizer.py:443-450
+__global__ void __launch_bounds__(128) blend_kernel(const Params P)
+{
+    const admpc_opts &o = P.o;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.B) return;
+    const double vx = P.x0[(size_t)3 * P.Bp + i];
+    const double pn = fmin(fmax((vx - o.blend_min) / (o.blend_max - o.blend_min), 0.0), 1.0);
+    for (int k = 0; k < o.N; k++) ((double *)P.p)[(size_t)k * P.Bp + i] = pn;
+}
+void launch_blend(const Params &P, cudaStream_t s) { blend_kernel<<<(P.B + 127) / 128, 128, 0, s>>>(P); }
 
 void launch_postsolve(const Params &P, double *prev_u, int *ibuf, double *u_apply, double *x_next, int threshold, int advance, cudaStream_t s)
 {

@@ -108,6 +108,7 @@ void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, 
 void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]
 void launch_update(const Params &P, cudaStream_t s);
 void launch_fill(double *dst, size_t n, double v, cudaStream_t s);
+void launch_blend(const Params &P, cudaStream_t s);     // p of every stage from x0's v_x (opts.blend_min / blend_max)
 double run_fp64_peak(int device, int nint);
 void launch_prepare_dense(const Params &P, cudaStream_t s);
 void launch_capsule_scatter(const Params &P, const double *in, int with_kappa, int with_iterate, cudaStream_t s);

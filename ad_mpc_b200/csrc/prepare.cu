@@ -215,14 +215,20 @@ void launch_prepare(const Params &P, cudaStream_t s)
             LAUNCH_PREP(128, 4, 128);
         } else {
             // One CTA per SM by shared memory.  All CTAs of the N working grid rows take the same time, so the run time is
-            // (number of waves over the 148 SMs) x (CTA width): pick the width, in warps, that minimises it; wider CTAs
+            // (number of waves over the device's SMs) x (CTA width): pick the width, in warps, that minimises it; wider CTAs
             // run with a lower register cap (more resident warps, slightly better latency hiding).
+            static int sm_count[64] = {};                        // SMs of the device this launch goes to (cached per device)
+            int dev = 0;
+            cudaGetDevice(&dev);
+            dev &= 63;
+            if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+            const int nsm = sm_count[dev] > 0 ? sm_count[dev] : 148;
             int best = 512;
             double best_cost = 1e300;
             for (int blk = 1024; blk >= 256; blk -= 32) {
                 const long ctas = (long)((P.Bp + blk - 1) / blk) * P.o.N;
                 const double eff = blk > 768 ? 1.02 : blk > 640 ? 0.96 : blk > 512 ? 0.98 : 1.0;   // measured per-thread cost
-                const double cost = (double)((ctas + 147) / 148) * blk * eff;
+                const double cost = (double)((ctas + nsm - 1) / nsm) * blk * eff;
                 if (cost < best_cost) { best_cost = cost; best = blk; }
             }
             if (best <= 512) LAUNCH_PREP(512, 1, best);

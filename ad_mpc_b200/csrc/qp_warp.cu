@@ -33,9 +33,6 @@
 #ifndef QPW_UADJ
 #define QPW_UADJ 2
 #endif
-#ifndef QPW_PSHFL
-#define QPW_PSHFL 0     // 1: P_{k+1} stays in registers across the phase-3 -> phase-1 edge of the factor sweep (shuffles)
-#endif
 #ifndef QPW_PADS
 #define QPW_PADS 1      // 1: b_k[0..5] and r_k live in the 8 unused doubles of the stage record instead of being re-read from L2 every
                         //    IPM iteration (uncoalesced reads: one sector per lane).  Four more slots for q_k did not pay (3.11 vs 3.10 ms)
@@ -236,14 +233,6 @@ __device__ __forceinline__ void w_backward(const admpc_opts &o, double *sm, doub
     const int l7 = (l < 7) ? l : 6;
     const double *p4gx = xs + X_GV + ((l7 < 2) ? 7 + l7 : l7);
     const bool kfj = (l == 29);
-#if QPW_PSHFL
-    // P[a0][c] lives on the lane of the packed pair (max, min): source lanes of this lane's row of P
-    const int s0 = tri_rt(a0, 0), s1 = tri_rt(a0, 1), s2 = tri_rt(a0, 2), s3 = tri_rt(a0, 3), s4 = tri_rt(a0, 4);
-    const int s5 = tri_rt(a0, 5), s6 = tri_rt(a0, 6);
-    const bool p4own = (ta < 2);                                  // Gxx of the (x0, x1) block is P_{k+1} itself
-    const double *p4gs = p4own ? xs + X_GS + lt : p4g;
-    double pn = dg ? sel7(o.We, ta) : 0.0;                        // P_N = diag(We)
-#endif
 
     // terminal: P_N = diag(We), p_N = r_x,N
     if (FACTOR) { xs[X_PS + l] = 0.0; xs[X_PS + 32 + l] = 0.0; if (l < 8) xs[X_PS + 64 + l] = 0.0; }
@@ -259,16 +248,8 @@ QPW_UNROLL(QPW_UB)
             // ---- phase 1: W = P_{k+1} [M | rb] ; P rb ; h = P rb + p ------------------------------------------------------
             const double rb6 = st[R_RB + 6];
             {
-#if QPW_PSHFL
-                double2 r01, r23, r45;
-                r01.x = __shfl_sync(FULL, pn, s0); r01.y = __shfl_sync(FULL, pn, s1);
-                r23.x = __shfl_sync(FULL, pn, s2); r23.y = __shfl_sync(FULL, pn, s3);
-                r45.x = __shfl_sync(FULL, pn, s4); r45.y = __shfl_sync(FULL, pn, s5);
-                const double r6 = __shfl_sync(FULL, pn, s6);
-#else
                 const double2 r01 = ld2(p1P0), r23 = ld2(p1P0 + 2), r45 = ld2(p1P0 + 4);
                 const double r6 = p1P0[6];
-#endif
                 const double v = fma(r6, fma(m6r0, rb6, m6c0), dot6r(r01, r23, r45, st + p1c0));
                 *p1o0 = v;
                 const double w = fma(r6, fma(m6r1, rb6, m6c1), dot6r(r01, r23, r45, st + p1c1));
@@ -304,13 +285,8 @@ QPW_UNROLL(QPW_UB)
             {   // P_k[ta][tb] = Gxx + G[x_ta][u] K(:, x_tb)
                 const double b0 = *p4b0, b1 = *p4b1;
                 const double kb0 = -(gi00 * b0 + gi01 * b1), kb1 = -(gi01 * b0 + gi11 * b1);
-#if QPW_PSHFL
-                const double gxx = p4own ? pn : *p4gs;
-                pn = (gxx + p4add) + (*p4a0) * kb0 + (*p4a1) * kb1;
-#else
                 const double pn = (*p4g + p4add) + (*p4a0) * kb0 + (*p4a1) * kb1;
                 *p4o0 = pn; *p4o1 = pn;
-#endif
             }
             {   // p_k[l] = g_x[l] + K(:, x_l) . g_u
                 const double k0 = -(gi00 * a0v + gi01 * a1v), k1 = -(gi01 * a0v + gi11 * a1v);

@@ -79,11 +79,24 @@ class BatchSolver:
         h = C.c_void_p()
         check(self.L.admpc_batch_create(C.byref(self.opts), self.B, int(device), C.byref(h)), "admpc_batch_create")
         self.h = h
+        self._owner = True
         self._keep = []
+
+    @classmethod
+    def _view(cls, handle, B, opts):
+        """Non-owning wrapper of a chunk handle that lives inside an admpc_pipe."""
+        self = cls.__new__(cls)
+        self.L = _lib.load()
+        self.opts, self.B, self.N = opts, int(B), int(opts.N)
+        self.h = C.c_void_p(handle)
+        self._owner = False
+        self._keep = []
+        return self
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.admpc_batch_free(self.h)
+            if self._owner:
+                self.L.admpc_batch_free(self.h)
             self.h = None
 
     def __del__(self):
@@ -168,6 +181,12 @@ class BatchSolver:
     def set_iterate(self, x=None, u=None):
         check(self.L.admpc_batch_set_iterate(self.h, None if x is None else _dp(_f64(x, (self.B, (self.N + 1) * 7))),
                                              None if u is None else _dp(_f64(u, (self.B, self.N * 2)))), "set_iterate")
+
+    def set_duals(self, pi=None, lam=None, t=None, sl=None, su=None):
+        """Multipliers / slacks of the iterate (the other five fields of acados' load_iterate)."""
+        B, N = self.B, self.N
+        a = [None if v is None else _f64(v, (B, N * w)) for v, w in ((pi, 7), (lam, NC), (t, NC), (sl, 2), (su, 2))]
+        check(self.L.admpc_batch_set_duals(self.h, *[_dp(v) for v in a]), "set_duals")
 
     def reset(self):
         check(self.L.admpc_batch_reset(self.h), "reset")
@@ -306,24 +325,41 @@ class BatchSolver:
 
 
 class PipelinedSolver:
-    """B instances split into `chunks` BatchSolver handles (one CUDA stream each): the H2D copy of chunk c+1, the solve
-    of chunk c and the D2H copy of chunk c-1 overlap.  Host buffers should be pinned (PinnedArray) for real overlap."""
+    """B instances behind ONE C handle (admpc_pipe, csrc/pipe.cu) that owns `chunks` chunk handles, one CUDA stream each:
+    the H2D copy of chunk c+1, the solve of chunk c and the D2H copy of chunk c-1 overlap.  Host buffers should be pinned
+    (PinnedArray) for real overlap.  `parts` are non-owning views of the chunk handles for per-chunk settings."""
 
     def __init__(self, B, opts=None, device=0, N=None, chunks=8):
-        from .shard import shard_range
-        self.B = int(B)
-        self.ranges = [shard_range(self.B, c, chunks) for c in range(chunks) if shard_range(self.B, c, chunks)[1] > shard_range(self.B, c, chunks)[0]]
-        self.parts = [BatchSolver(hi - lo, opts=opts, device=device, N=N) for lo, hi in self.ranges]
-        self.N = self.parts[0].N
-        self.L = self.parts[0].L
+        self.L = _lib.load()
+        self.opts = opts if opts is not None else default_opts(N or 20)
+        if N is not None:
+            self.opts.N = N
+        self.B, self.N = int(B), int(self.opts.N)
+        p = C.c_void_p()
+        check(self.L.admpc_pipe_create(C.byref(self.opts), self.B, int(device), int(chunks), C.byref(p)), "admpc_pipe_create")
+        self.p = p
+        self.parts, self.ranges = [], []
+        for c in range(self.L.admpc_pipe_chunks(self.p)):
+            lo, hi = C.c_int(), C.c_int()
+            h = self.L.admpc_pipe_chunk(self.p, c, C.byref(lo), C.byref(hi))
+            self.ranges.append((lo.value, hi.value))
+            self.parts.append(BatchSolver._view(h, hi.value - lo.value, self.opts))
 
     def set_gp(self, model, stage0_trigger=1):
-        for s in self.parts:
-            s.set_gp(model, stage0_trigger)
+        if model is None:
+            check(self.L.admpc_pipe_set_gp(self.p, 0, 0, 0, None, None, None, None, None, None, None, 0), "pipe_set_gp")
+            return
+        X = _f64(model["X"])
+        nout, M, dz = X.shape
+        feat = np.ascontiguousarray(model.get("feat", (3, 4, 5, 6)[:dz]), dtype=np.int32)
+        rows = np.ascontiguousarray(model.get("rows", (4, 5)[:nout]), dtype=np.int32)
+        check(self.L.admpc_pipe_set_gp(self.p, nout, M, dz, _ip(feat), _ip(rows), _dp(X), _dp(_f64(model["alpha"])),
+                                       _dp(_f64(model["ell"])), _dp(_f64(model["sigma_f"])), _dp(_f64(model["y_mean"])),
+                                       int(stage0_trigger)), "admpc_pipe_set_gp")
 
     def set_iterate(self, x=None, u=None):
-        for s, (lo, hi) in zip(self.parts, self.ranges):
-            s.set_iterate(None if x is None else x[lo:hi], None if u is None else u[lo:hi])
+        check(self.L.admpc_pipe_set_iterate(self.p, None if x is None else _dp(_f64(x, (self.B, (self.N + 1) * 7))),
+                                            None if u is None else _dp(_f64(u, (self.B, self.N * 2)))), "pipe_set_iterate")
 
     def set_gp_ensemble(self, models, centroids=None, stage0_trigger=1):
         return [s.set_gp_ensemble(models, centroids=centroids, stage0_trigger=stage0_trigger) for s in self.parts][0]
@@ -348,35 +384,49 @@ class PipelinedSolver:
             s.set_kappa(k[lo:hi])
 
     def wait(self):
-        for s in self.parts:
-            s.wait()
+        check(self.L.admpc_pipe_wait(self.p), "pipe_wait")
+
+    @staticmethod
+    def _c(a, dtype=np.float64):
+        assert a.flags["C_CONTIGUOUS"] and a.dtype == dtype, "host buffers must be C-contiguous %s" % dtype
+        return a
 
     def solve_batch(self, x0, yref, p, u_out, x_out, status_out):
-        """x0[B,7] yref[B,N*9+7] p[B] -> u_out[B,N,2] x_out[B,N+1,7] status_out[B] (all C-contiguous float64/int32)."""
-        for s, (lo, hi) in zip(self.parts, self.ranges):
-            check(self.L.admpc_batch_solve_host_async(s.h, _dp(x0[lo:hi]), _dp(yref[lo:hi]), _dp(p[lo:hi]), _dp(u_out[lo:hi]),
-                                                     _dp(x_out[lo:hi]), _ip(status_out[lo:hi])), "solve_host_async")
-        self.wait()
+        """x0[B,7] yref[B,N*9+7] p[B] -> u_out[B,N,2] x_out[B,N+1,7] status_out[B] (all C-contiguous float64/int32).
+        One C call (admpc_pipe_solve_host): every chunk is enqueued on its stream, then all are awaited."""
+        c = self._c
+        check(self.L.admpc_pipe_solve_host(self.p, _dp(_f64(x0)), _dp(_f64(yref)), _dp(_f64(p)), _dp(c(u_out)), _dp(c(x_out)),
+                                           _ip(c(status_out, np.int32))), "pipe_solve_host")
         return u_out, x_out, status_out
 
     def set_track(self, traj, H=None, traj_dt=None, anchor=False):
-        for s in self.parts:
-            s.set_track(traj, H=H, traj_dt=traj_dt, anchor=anchor)
+        traj = _f64(traj)
+        H = int(H if H is not None else self.N)
+        dt = float(traj_dt if traj_dt is not None else self.opts.dt)
+        check(self.L.admpc_pipe_set_track(self.p, traj.shape[0], _dp(traj), H, dt, int(anchor)), "pipe_set_track")
 
     def solve_from_pose(self, x0, p, u_out, x_out, status_out):
         """Control step from vehicle states only: reference generation, solve and read-back per chunk, pipelined."""
-        for s, (lo, hi) in zip(self.parts, self.ranges):
-            check(self.L.admpc_batch_solve_pose_async(s.h, _dp(x0[lo:hi]), _dp(p[lo:hi]), _dp(u_out[lo:hi]), _dp(x_out[lo:hi]),
-                                                     _ip(status_out[lo:hi])), "solve_pose_async")
-        self.wait()
+        c = self._c
+        check(self.L.admpc_pipe_solve_pose(self.p, _dp(_f64(x0)), _dp(_f64(p)), _dp(c(u_out)), _dp(c(x_out)),
+                                           _ip(c(status_out, np.int32))), "pipe_solve_pose")
         return u_out, x_out, status_out
 
     def kernel_launches(self):
-        return sum(s.kernel_launches() for s in self.parts)
+        return int(self.L.admpc_pipe_kernel_launches(self.p))
 
     def close(self):
-        for s in self.parts:
-            s.close()
+        if getattr(self, "p", None):
+            for s in self.parts:
+                s.close()
+            self.L.admpc_pipe_free(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class AcadosOcpSolverB200:
@@ -447,6 +497,9 @@ class AcadosOcpSolverB200:
             self.set(k, "x", d["x_%d" % k])
             if k < self.N:
                 self.set(k, "u", d["u_%d" % k])
+                for f in ("pi", "lam", "t", "sl", "su"):          # acados restores all seven fields (ad_3d_optimizer.py:454)
+                    if d.get("%s_%d" % (f, k)):
+                        self.set(k, f, d["%s_%d" % (f, k)])
 
     def __del__(self):
         try:

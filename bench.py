@@ -94,8 +94,18 @@ def dist_env():
     return rank, world, local
 
 
+def _workload_module():
+    """ad_mpc_b200/workload.py is numpy-only; load it by path so that the reference arm never imports the product package
+    (and therefore never loads libadmpc_b200.so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("admpc_workload", os.path.join(ROOT, "ad_mpc_b200", "workload.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_workload(rank, B=None):
-    from ad_mpc_b200 import workload as wl
+    wl = _workload_module()
     B = B or CFG["B"]
     batch = wl.make_batch(B, CFG["N"], dt=CFG["dt"], seed=20263 + 1000 * rank, p=CFG["p"])
     model = wl.make_gp(M=CFG["M"], seed=20263, n_out=CFG["n_out"], dz=CFG["dz"])
@@ -111,23 +121,42 @@ def config_dict(world):
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline -------
-def cpu_oracle_rate(sample, nthreads=0, gp=True, reps=1):
-    """Times the oracle port (CPU restatement of the reference path; acados itself is not buildable here) on a
-    bounded sample of the same workload.  Returns (solves/s, seconds, threads)."""
+_ORC_FLAGS = None
+
+
+def _oracle():
+    """The CPU restatement, rebuilt -O3 -march=native on this machine; test infrastructure, timed here as
+    the reported CPU baseline only."""
+    global _ORC_FLAGS
     from oracle import oracle as orc
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from util_parity import mirror_opts
-    from ad_mpc_b200 import default_opts
-    batch, model = make_workload(0, B=sample)
-    po = default_opts(CFG["N"])
-    po.dt = CFG["dt"]
-    o = mirror_opts(po)             # same options as the CUDA arm, field by field
+    if _ORC_FLAGS is None:
+        _ORC_FLAGS = orc.use_native()
+    return orc
+
+
+def _oracle_opts(orc, N):
+    """Oracle options = its own defaults (tests/test_host_cpu.py checks they equal the product's field by field)."""
+    o = orc.default_opts(N=N)
+    o.dt = CFG["dt"]
+    return o
+
+
+def cpu_oracle_rate(sample, nthreads=0, gp=True, reps=1, N=None, M=None, p=None):
+    """Times the oracle port (CPU restatement of the reference path; acados itself is not buildable here) on a
+    bounded sample of the workload.  Returns (solves/s, seconds, threads)."""
+    orc = _oracle()
+    wl = _workload_module()
+    N = N or CFG["N"]
+    batch = wl.make_batch(sample, N, dt=CFG["dt"], seed=20263, p=CFG["p"] if p is None else p)
+    o = _oracle_opts(orc, N)
     g = None
     if gp:
+        model = wl.make_gp(M=M or CFG["M"], seed=20263, n_out=CFG["n_out"], dz=CFG["dz"])
         g = orc.Gp(model)
         g.apply(o, feat=model["feat"], rows=model["rows"])
     cores = nthreads or (os.cpu_count() or 1)
-    orc.rti_batch(o, batch["x0"][:64], batch["yref"][:64], batch["p"][:64], batch["x_init"][:64], batch["u_init"][:64],
+    w = min(64, sample)
+    orc.rti_batch(o, batch["x0"][:w], batch["yref"][:w], batch["p"][:w], batch["x_init"][:w], batch["u_init"][:w],
                   gp=g, nthreads=cores)   # warm-up (page-in, thread pool)
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -137,11 +166,31 @@ def cpu_oracle_rate(sample, nthreads=0, gp=True, reps=1):
     return sample * reps / dt, dt, cores
 
 
+def cpu_single_latency(steps=50):
+    """cfg 1 on ONE host thread: nominal model, N=20, B=1, cold iterate then `steps` closed-loop RTI steps (plant =
+    model prediction), per-step latency of the CPU restatement (the quantity the GPU single-instance number sits beside)."""
+    orc = _oracle()
+    wl = _workload_module()
+    N = CFG["N"]
+    b1 = wl.make_batch(1, N, seed=20261, p=0.0)
+    o = _oracle_opts(orc, N)
+    x0, xi, ui = b1["x0"].copy(), b1["x_init"].copy(), b1["u_init"].copy()
+    ms = []
+    for it in range(5 + steps):
+        t0 = time.perf_counter()
+        r = orc.rti_batch(o, x0, b1["yref"], b1["p"], xi, ui, nthreads=1)
+        ms.append((time.perf_counter() - t0) * 1e3)
+        xi, ui = r["x"], r["u"]
+        x0 = r["x"][:, 1, :].copy()
+    ms = sorted(ms[5:])
+    return ms[len(ms) // 2], ms[min(len(ms) - 1, int(0.99 * len(ms)))]
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    sample = 4096
+    sample = CFG["B"]                        # the full per-GPU batch of the config, every step
     cores = os.cpu_count() or 1
     times = []
     for s in range(args.warmup + args.steps):
@@ -153,13 +202,39 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "SQP-RTI MPC solves/sec (N=20, GP-augmented)", "value": value, "unit": "solves/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(config_dict(world), reference_note="CPU restatement of the acados path (acados/HPIPM are "
-                           "un-vendored dependencies and cannot be built here); each step = %d-instance sample" % sample),
+            "config": config_dict(world),
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
-                             "sample": "%d instances of the cfg3 workload per step, OpenMP over instances" % sample},
+                             "sample": "the full %d-instance cfg3 batch per step, OpenMP over instances, oracle built %s "
+                                       "(CPU restatement of the acados path; acados/HPIPM are un-vendored and cannot be "
+                                       "built here)" % (sample, _ORC_FLAGS)},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def bind_numa(local):
+    """Best effort: pin this rank's host thread (and therefore its pinned allocations, first touch) to the NUMA node of
+    its GPU.  Returns a short description for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "gpu numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return "node %d has no allowed cpu (allowed %d cpus)" % (node, len(allowed))
+        os.sched_setaffinity(0, use)
+        return "node %d, %d cpus" % (node, len(use))
+    except Exception as e:           # noqa: BLE001 -- reporting only
+        return "not bound (%s)" % type(e).__name__
 
 
 # ------------------------------------------------------------------------------------------ our arm ------------
@@ -177,6 +252,7 @@ def run_ours(args):
         import torch.distributed as dist          # plumbing only: rendezvous, barrier, max over ranks
         dist.init_process_group(backend="gloo")
     L = _lib.load()
+    numa = bind_numa(local)
     B, N = CFG["B"], CFG["N"]
     opts = default_opts(N)
     opts.dt = CFG["dt"]
@@ -254,6 +330,22 @@ def run_ours(args):
     clocks = sampler.stop()
     st, qs, qi = s.get_status()
     assert (st == 0).all(), "solver failures in the benchmark batch"
+    # ---- multi-rank correctness of the gather: every rank's slice of the root's block == that rank's own result ----
+    gather_check = None
+    if world > 1:
+        own_u, own_x = s.get_u(), s.get_x()
+        mine = (float(own_u.sum()), float(np.abs(own_x).sum()), int(st.sum()), own_u[::997].tobytes())
+        sums = [None] * world if rank == 0 else None
+        dist.gather_object(mine, sums, dst=0)
+        if rank == 0:
+            ua = np.empty((world * B, N, 2)); xa = np.empty((world * B, N + 1, 7)); sa = np.empty(world * B, dtype=np.int32)
+            dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+            _lib.check(L.admpc_batch_get_gathered(s.h, ua.ctypes.data_as(dp), xa.ctypes.data_as(dp), sa.ctypes.data_as(ip)), "get_gathered")
+            for r in range(world):
+                blk = slice(r * B, (r + 1) * B)
+                got = (float(ua[blk].sum()), float(np.abs(xa[blk]).sum()), int(sa[blk].sum()), ua[blk][::997].tobytes())
+                assert got == sums[r], "gathered block of rank %d differs from the rank's own result" % r
+            gather_check = "root's gathered block == every rank's own (u, x, status): checksums + sampled rows, %d ranks" % world
     n_ipm = float(qi.mean())
     t_local = sum(step_ms)
     if dist is not None:
@@ -386,7 +478,8 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        roofline = {"bound": "fp64", "kernel": {"prepare": "prepare_kernel<GP>", "qp": "qp_warp_kernel"}[dom],
+        qp_name = "qp_half_kernel" if os.environ.get("ADMPC_QP_VARIANT", "") in ("", "0", "5") and N <= 31 else "qp_warp_kernel"
+        roofline = {"bound": "fp64", "kernel": {"prepare": "prepare_kernel<GP>", "qp": qp_name}[dom],
                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,
                     "peak_source": "DFMA microbenchmark admpc_measure_fp64_peak run in this process (MEASURED_PEAKS.json "
@@ -402,10 +495,21 @@ def run_ours(args):
         if world == 1:                                                       # reported at N=1 only
             sample = 8192
             rate0, secs0, cores = cpu_oracle_rate(1024)                      # calibrate, then size the sample to ~12 s
-            reps = max(1, min(80, int(24.0 * rate0 / sample)))
+            reps = max(1, min(80, int(12.0 * rate0 / sample)))
             rate, secs, cores = cpu_oracle_rate(sample, reps=reps)
+            # the other BASELINE.md 2 numbers: single-thread latency on cfg1, all-core throughput on cfg2 and cfg4
+            l50, l99 = cpu_single_latency(50)
+            r2, s2, _ = cpu_oracle_rate(4096, gp=False, p=0.0)
+            r4a, _, _ = cpu_oracle_rate(64, N=40, M=2000)                     # calibrate cfg4 (about 20x the work per solve)
+            n4 = int(max(64, min(4096, 4.0 * r4a)))
+            r4, s4, _ = cpu_oracle_rate(n4, N=40, M=2000)
             cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                    "sample": "%d instances of the cfg3 workload x%d, OpenMP over instances, %.1f s" % (sample, reps, secs),
+                   "build": _ORC_FLAGS,
+                   "cfg1_single_thread_latency_ms": {"p50": l50, "p99": l99, "cores": 1,
+                                                     "sample": "nominal N=20, B=1, 50 closed-loop RTI steps after 5 warm-up"},
+                   "cfg2_nominal_B4096": {"value": r2, "unit": "solves/s", "cores": cores, "sample": "4096 instances, %.2f s" % s2},
+                   "cfg4_gp2000_N40": {"value": r4, "unit": "solves/s", "cores": cores, "sample": "%d instances, %.2f s" % (n4, s4)},
                    "note": "CPU restatement of the acados path (oracle/); acados itself cannot be built here"}
         e2e_sorted = sorted(e2e_ms)
         line = {"metric": "SQP-RTI MPC solves/sec (N=20, GP-augmented)", "value": value, "unit": "solves/s",
@@ -419,6 +523,8 @@ def run_ours(args):
                                               "note": "same call with the reference generated on the device from "
                                                       "vehicle states (refgen_kernel, anchored mode); rank 0"}},
                 "gpu_launches": counted, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "host": {"numa_binding": numa, "e2e_entry": "admpc_pipe_solve_host (one C call, 8 chunk streams inside the library)"},
+                "gather_check": gather_check,
                 "wall_s_timed_region": wall, "frenet_variant": frenet,
                 "latency": {"p50_ms_per_batch_solve": sorted(step_ms)[len(step_ms) // 2], "batch": B,
                             "p99_ms_per_batch_solve": sorted(step_ms)[min(len(step_ms) - 1, int(0.99 * len(step_ms)))],

@@ -57,12 +57,20 @@ typedef struct admpc_opts {
                               path curvature per shooting node via admpc_batch_set_kappa) */
     int gp_feat[ADMPC_DZMAX];      /* feature indices into [x(7);u(2)] (B_z, model_fitting/gp.py:609-630); >= 2 */
     int gp_row[ADMPC_GPOUT_MAX];   /* state rows receiving the GP outputs (B_x, utils/utils.py:773-786); in {3,4,5} */
+    int gp_precision;      /* 0 (default): FP64 RBF kernel values; 1: opt-in FP32 exponential (ex2.approx on the fractional
+                              part of the FP64 exponent, FP64 accumulation): relative error of every kernel value <= 2^-22,
+                              see DESIGN.md 5 for the bound on A, B, b (model_fitting/gp.py:117-138) */
+    int reserved_;
     double dt;
     double W[9], We[7];
     double zl[2], zu[2], Zl[2], Zu[2];
     double lbu[2], ubu[2], lbx, ubx;
     double mass, lf, lr, iz, cf2, cr2;
     double mu0, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, lam_min, t_min, thr0, reg;
+    double blend_min, blend_max;   /* kinematic/dynamic blend window on v_x: p = clamp((v_x - blend_min)/(blend_max - blend_min), 0, 1)
+                                      ($A/ad_3d_optimizer.py:443, $A/ad_3d.py:62-64 = 100 / 110).  Used where the library
+                                      itself produces the next solve's p (device closed loop, pose-only step without p);
+                                      blend_max <= blend_min (default 0 / 0) keeps the p that was uploaded. */
 } admpc_opts;
 
 void admpc_default_opts(admpc_opts *o);
@@ -80,6 +88,8 @@ int sim_car_acados_create(sim_car_solver_capsule *capsule);                     
 int sim_car_acados_create_with_discretization(sim_car_solver_capsule *capsule, int n_time_steps,
                                               double *new_time_steps);            /* .h:128 (uniform steps only) */
 int sim_car_acados_update_time_steps(sim_car_solver_capsule *capsule, int N, double *new_time_steps); /* .h:133 */
+int sim_car_acados_update_qp_solver_cond_N(sim_car_solver_capsule *capsule, int qp_solver_cond_N);   /* .h:137: accepted
+                                                              and ignored (no condensing here; the reference's own body exits) */
 int sim_car_acados_update_params(sim_car_solver_capsule *capsule, int stage, double *value, int np);  /* .h:138 */
 int sim_car_acados_solve(sim_car_solver_capsule *capsule);                        /* .h:139 */
 int sim_car_acados_reset(sim_car_solver_capsule *capsule, int reset_qp_solver_mem); /* .h:121 */
@@ -93,7 +103,10 @@ int sim_car_acados_set_opts(sim_car_solver_capsule *capsule, const admpc_opts *o
 int sim_car_acados_set_nlp_solver(sim_car_solver_capsule *capsule, const char *type, int max_iter, const double *tol4);
 /* flat field access replacing ocp_nlp_{cost_model,constraints_model,out}_set / ocp_nlp_out_get / ocp_nlp_get.
  * set fields: "yref" (9, or 7 at stage N), "lbx"/"ubx" (stage 0: 7 = x0; stages 1..N-1: 1), "p" (1), "x" (7), "u" (2),
+ *             "pi" (7), "lam" / "t" (10, stage 0: 22), "sl" / "su" (2)  -- all seven fields of acados' load_iterate,
  *             "kappa" (1; Frenet variant only: path curvature at the node)
+ * The typed getters of the reference (sim_car_acados_get_nlp_in/out/solver/config/opts/dims/plan, .h:143-150) return
+ * libacados structs; they are replaced by this flat string-keyed access and are deliberately NOT exported.
  * get fields: "x" (7), "u" (2), "pi" (7), "lam" (10, stage 0: 22), "t" (same), "sl" (2), "su" (2)
  * stats: "sqp_iter"(int) "qp_iter"(int) "qp_stat"(int) "status"(int) "time_tot"(double, s) "kkt_norm_inf"(double) */
 int sim_car_acados_set(sim_car_solver_capsule *capsule, int stage, const char *field, const double *value, int n);
@@ -146,6 +159,11 @@ int admpc_batch_set_kappa(admpc_batch *h, const double *kappa);
 int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state /*[B][7] or NULL = x0*/);
 /* iterate (initial guess / warm start).  reset zeroes it like $G/acados_solver_sim_car.c:819-852. */
 int admpc_batch_set_iterate(admpc_batch *h, const double *x /*[B][(N+1)*7]*/, const double *u /*[B][N*2]*/);
+/* multipliers and slacks of the iterate: together with set_iterate the seven fields acados' load_iterate restores
+ * ($A/ad_3d_optimizer.py:454; layouts as in the getters below).  The RTI step replaces them by the QP's; the full-SQP
+ * loop's first KKT check reads them.  Any pointer may be NULL (left unchanged). */
+int admpc_batch_set_duals(admpc_batch *h, const double *pi /*[B][N*7]*/, const double *lam /*[B][N*10]*/,
+                          const double *t /*[B][N*10]*/, const double *sl /*[B][N*2]*/, const double *su /*[B][N*2]*/);
 int admpc_batch_reset(admpc_batch *h);
 
 int admpc_batch_solve(admpc_batch *h);   /* one SQP-RTI iteration for all B instances (async launch) */
@@ -170,6 +188,29 @@ int admpc_batch_solve_host(admpc_batch *h, const double *x0, const double *yref,
  * asynchrony); complete with admpc_batch_wait.  Several handles (one stream each) pipeline H2D / solve / D2H. */
 int admpc_batch_solve_host_async(admpc_batch *h, const double *x0, const double *yref, const double *p_scalar,
                                  double *u_out, double *x_out, int *status_out);
+
+/* The same call with the chunk pipeline INSIDE the library: one handle owning `chunks` chunk handles (contiguous blocks of
+ * the batch, one CUDA stream each), so that the H2D copy of chunk c+1, the solve of chunk c and the D2H copy of chunk c-1
+ * overlap.  One call from one host thread; host buffers should be pinned (admpc_host_alloc) for real overlap.  This is
+ * the end-to-end entry bench.py times ("e2e").  admpc_pipe_chunk exposes a chunk's handle ([lo, hi) = its instances)
+ * for per-chunk settings that have no pipe-level call (GP ensembles, curvature, gp_state, getters). */
+typedef struct admpc_pipe admpc_pipe;
+int admpc_pipe_create(const admpc_opts *opts, int B, int device, int chunks, admpc_pipe **out);
+int admpc_pipe_free(admpc_pipe *p);
+int admpc_pipe_chunks(const admpc_pipe *p);
+admpc_batch *admpc_pipe_chunk(admpc_pipe *p, int c, int *lo, int *hi);
+int admpc_pipe_set_gp(admpc_pipe *p, int nout, int M, int dz, const int *feat, const int *rows, const double *X,
+                      const double *alpha, const double *ell, const double *sigma_f, const double *y_mean, int stage0_trigger);
+int admpc_pipe_set_iterate(admpc_pipe *p, const double *x /*[B][(N+1)*7]*/, const double *u /*[B][N*2]*/);
+int admpc_pipe_set_track(admpc_pipe *p, int L, const double *traj, int H, double traj_dt, int anchor_at_closest);
+int admpc_pipe_solve_host(admpc_pipe *p, const double *x0, const double *yref, const double *p_scalar,
+                          double *u_out, double *x_out, int *status_out);          /* blocking */
+int admpc_pipe_solve_host_async(admpc_pipe *p, const double *x0, const double *yref, const double *p_scalar,
+                                double *u_out, double *x_out, int *status_out);    /* complete with admpc_pipe_wait */
+int admpc_pipe_solve_pose(admpc_pipe *p, const double *x0, const double *p_scalar, double *u_out, double *x_out,
+                          int *status_out);                                        /* refgen + solve per chunk, blocking */
+int admpc_pipe_wait(admpc_pipe *p);
+long long admpc_pipe_kernel_launches(const admpc_pipe *p);
 
 /* Reference generation on the device (ad_mpc/ref_traj.py:89-171 + nodes/gp_ad_mpc_node.py:180-187 +
  * ad_mpc/ad_3d_optimizer.py:343-345,420-438): set_track takes the table RefTrajectory.set_traj builds
@@ -212,7 +253,10 @@ int admpc_host_free(void *p);
 
 /* multi-GPU plumbing (one process per GPU).  The NCCL library is dlopen'ed; unique id bytes (128) are exchanged by
  * the caller's launcher (torch.distributed / MPI / file).  Broadcast ships the GP model from root to every rank's
- * handle; gather collects [u | x | status] blocks on root. */
+ * handle; gather collects [u | x | status] blocks on root.  Every rank must hold the SAME number of instances (checked
+ * in comm_init; gather / gather_enable return ADMPC_E_UNSUPPORTED otherwise -- pad the batch to a multiple of nranks).
+ * bcast_gp is safe against local failures: the root's verdict travels in the header and all ranks agree (one 4-byte
+ * all-reduce) before the blob moves, so either every rank has the model or every rank returns an error. */
 int admpc_nccl_unique_id(void *id128);
 int admpc_batch_comm_init(admpc_batch *h, const void *id128, int rank, int nranks);
 int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, int dz, const int *feat, const int *rows,
@@ -222,8 +266,11 @@ int admpc_batch_gather(admpc_batch *h, int root, double *u_all /*[nranks*B][N*2]
 /* collective, optional: FUSED gather towards root.  The root exports its gathered block through CUDA IPC, every rank maps
  * it, and from then on the QP kernels' epilogue writes each instance's [u | x | status] straight into the rank's slice
  * of the root's block (NVLink peer stores overlapped with the solve); admpc_batch_gather becomes a 4-byte all-reduce
- * (stream-ordered completion barrier).  Returns 1 = fused path active on all ranks, 0 = stays on NCCL send/recv
- * (IPC unavailable or ADMPC_GATHER=nccl), < 0 error. */
+ * (stream-ordered completion barrier).  The root's block is double-buffered: each gather call delivers one half and
+ * flips the half later solves write to, so a rank that runs ahead never overwrites a block the root is still copying
+ * out -- PROVIDED every rank calls admpc_batch_gather between two solves whose results are to be gathered (ranks that
+ * solve twice or more without a gather must separate them from the root's read-out with admpc_batch_barrier).
+ * Returns 1 = fused path active on all ranks, 0 = stays on NCCL send/recv (IPC unavailable or ADMPC_GATHER=nccl), < 0 error. */
 int admpc_batch_gather_enable(admpc_batch *h, int root);
 /* host copy of what the last gather left on the root's device (rank-major blocks); root only */
 int admpc_batch_get_gathered(admpc_batch *h, double *u_all, double *x_all, int *status_all);

@@ -19,8 +19,9 @@ def is_valid_command(x_opt, ref):                      # ad_3d_optimizer.py:385-
     return bool(np.mean(tmp) < 3.0 and np.cov(tmp) < 2 and np.max(tmp) < 4)
 
 
-def closed_loop(o, traj, H, traj_dt, x0, p, x_init, u_init, steps, threshold=10, anchor=False):
-    """Returns (log[steps+1,B,7], info dict of the last step)."""
+def closed_loop(o, traj, H, traj_dt, x0, p, x_init, u_init, steps, threshold=10, anchor=False, blend=None):
+    """Returns (log[steps+1,B,7], info dict of the last step).  blend = (blend_min, blend_max): the kinematic/dynamic
+    switch is recomputed from the measured v_x before every solve after the first (ad_3d_optimizer.py:443-450)."""
     B, N = x0.shape[0], o.N
     x0 = x0.copy()
     xit, uit = x_init.copy(), u_init.copy()
@@ -50,6 +51,8 @@ def closed_loop(o, traj, H, traj_dt, x0, p, x_init, u_init, steps, threshold=10,
             ua[b] = w[:2]
             u = np.array([w[0], min(max(w[1], o.lbu[1]), o.ubu[1])])
             x0[b] = orc.rk4_sens(o, x0[b], u, pfull[b, 0])[0]
+            if blend is not None:
+                pfull[b, :] = min(max((x0[b, 3] - blend[0]) / (blend[1] - blend[0]), 0.0), 1.0)
         log.append(x0.copy())
         info = dict(valid=valid, safe_count=cnt.copy(), cmd_ok=cmd_ok, u_apply=ua, status=r["status"])
     return np.array(log), info

@@ -69,12 +69,32 @@ def build(force=False):
 
 
 _lib = None
+_so_override = None
+
+
+def use_native():
+    """bench.py's CPU legs only: rebuild the restatement with -O3 -march=native ON THE MACHINE THAT RUNS IT (the shipped
+    liboracle.so is built -march=x86-64-v3 in the build container so that it loads on any box).  The result lives in
+    oracle/_native/ (git- and gpurun-ignored: it must never travel).  Returns the flags in use."""
+    global _lib, _so_override
+    d = os.path.join(_HERE, "_native")
+    so = os.path.join(d, "liboracle_native.so")
+    flags = "-O3 -march=native"
+    try:
+        os.makedirs(d, exist_ok=True)
+        subprocess.check_call(["/usr/bin/gcc"] + flags.split() + ["-fPIC", "-fopenmp", "-std=c11", "-shared", "-o", so,
+                               os.path.join(_HERE, "rti_oracle.c"), "-lm", "-ldl"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+    except Exception:
+        return "-O3 -march=x86-64-v3 (native rebuild failed; shipped build)"
+    _so_override, _lib = so, None
+    return flags
 
 
 def lib():
     global _lib
     if _lib is None:
-        so = build()
+        so = _so_override or build()
         L = C.CDLL(so)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.orc_default_opts.argtypes = [C.POINTER(OrcOpts)]

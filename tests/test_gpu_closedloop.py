@@ -75,6 +75,27 @@ def test_closed_loop_tracks_the_reference_and_matches_oracle():
     s.close()
 
 
+def test_closed_loop_refreshes_the_blend_parameter():
+    """opts.blend_min / blend_max: the kinematic/dynamic switch p follows the measured v_x between control steps
+    (ad_3d_optimizer.py:443-450) -- with a window around the cruise speed every vehicle gets its own, changing p."""
+    B, N, T = 40, 20, 6
+    traj, x0, x_init, u_init = _setup(B, N, 8, spread=0.3)
+    blend = (7.0, 9.0)
+    opts = default_opts(N, blend_min=blend[0], blend_max=blend[1])
+    o = mirror_opts(opts)
+    p0 = np.clip((x0[:, 3] - blend[0]) / (blend[1] - blend[0]), 0.0, 1.0)
+    s = BatchSolver(B, opts)
+    s.set_track(traj, H=N, traj_dt=opts.dt, anchor=True)
+    s.set_iterate(x_init, u_init); s.set_x0(x0); s.set_p(p0)
+    log = s.closed_loop(T, use_track=True, log=True)
+    rlog, r = clo.closed_loop(o, traj, N, opts.dt, x0, p0, x_init, u_init, T, anchor=True, blend=blend)
+    err = np.abs(log - rlog) / np.maximum(1.0, np.abs(rlog))
+    assert err.max() < 1e-7, err.max()
+    frozen, _ = clo.closed_loop(o, traj, N, opts.dt, x0, p0, x_init, u_init, T, anchor=True)
+    assert np.abs(frozen - rlog).max() > 1e-4        # the refresh matters on this scenario
+    s.close()
+
+
 def test_closed_loop_full_size_runs_on_device():
     """B = 16384 closed loops x 5 steps: no failures, all predictions healthy, timing printed."""
     B, N, T = 16384, 20, 5

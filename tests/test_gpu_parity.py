@@ -213,6 +213,67 @@ def test_golden_fixed_point_on_gpu(golden_dir):
     s.close()
 
 
+def test_load_iterate_restores_duals_and_sqp_sees_convergence(golden_dir, tmp_path):
+    """acados' load_iterate restores x, u, pi, lam, t, sl, su (ad_3d_optimizer.py:454).  The reference's own converged
+    iterate (sim_car_iterate.json, N = 40), written back in the acados JSON layout and loaded through the shim, must
+    test as converged in SQP mode without a single QP (it would not if the multipliers were dropped)."""
+    import json
+    from test_oracle_golden import _golden_lam, _golden_lin, _recover_yref
+    g = np.load(os.path.join(golden_dir, "sim_car_iterate.npz"))
+    N = 40
+    We = np.array([10.0, 10.0, 100.0, 0, 0, 0, 0])
+    opts = default_opts(N, We=We)
+    o = mirror_opts(opts)
+    A, B, _ = _golden_lin(g, o)
+    lam, t = _golden_lam(g)
+    yref = _recover_yref(g, o, A, lam, We)
+    d = {}
+    for k in range(N + 1):
+        d["x_%d" % k] = g["x"][k].tolist()
+        d["z_%d" % k] = []
+        if k < N:
+            d["u_%d" % k] = g["u"][k].tolist(); d["pi_%d" % k] = g["pi"][k].tolist()
+            d["lam_%d" % k] = (g["lam0"] if k == 0 else g["lam"][k - 1]).tolist()
+            d["t_%d" % k] = (g["t0"] if k == 0 else g["t"][k - 1]).tolist()
+            d["sl_%d" % k] = g["sl"][k].tolist(); d["su_%d" % k] = g["su"][k].tolist()
+        else:
+            for f in ("u", "lam", "t", "sl", "su"):
+                d["%s_%d" % (f, k)] = []
+    fn = str(tmp_path / "iterate.json")
+    with open(fn, "w") as fh:
+        json.dump(d, fh)
+
+    def run(with_duals):
+        cap = AcadosOcpSolverB200(opts, nlp_solver_type="SQP")
+        for j in range(N):
+            cap.set(j, "yref", yref[j * 9:(j + 1) * 9]); cap.set(j, "p", np.zeros(1))
+        cap.set(N, "yref", yref[N * 9:])
+        cap.set(0, "lbx", g["x"][0]); cap.set(0, "ubx", g["x"][0])
+        if with_duals:
+            cap.load_iterate(fn)
+        else:
+            for k in range(N + 1):
+                cap.set(k, "x", g["x"][k])
+                if k < N:
+                    cap.set(k, "u", g["u"][k])
+        st = cap.solve()
+        return st, cap.get_stats("sqp_iter"), cap
+    st, it, cap = run(True)
+    assert st == 0 and it == 0, (st, it)
+    # what was loaded comes back through the getters (stage-0 acados layout included)
+    assert np.abs(cap.get(3, "pi") - g["pi"][3]).max() == 0 and np.abs(cap.get(5, "lam") - g["lam"][4]).max() == 0
+    assert np.abs(cap.get(0, "lam")[[0, 1, 9, 10, 18, 19, 20, 21]] - g["lam0"][[0, 1, 9, 10, 18, 19, 20, 21]]).max() == 0
+    st2, it2, _ = run(False)
+    assert st2 == 0 and it2 >= 1            # without the multipliers the same point does not pass the KKT test
+
+
+def test_cond_N_update_is_accepted():
+    """acados_solver_sim_car.h:137 is exported; there is nothing to re-condense here, so it is a no-op returning 0."""
+    from ad_mpc_b200 import _lib
+    cap = AcadosOcpSolverB200(default_opts(20))
+    assert _lib.load().sim_car_acados_update_qp_solver_cond_N(cap.c, 5) == 0
+
+
 def test_nan_linearisation_status():
     """NaN in the iterate -> ACADOS_FAILURE (1) for that instance only; others unaffected."""
     B, N = 40, 20
@@ -474,6 +535,53 @@ def test_acados_shim_sqp_mode():
     u = np.stack([cap.get(j, "u") for j in range(N)])
     assert mixed_err(u, r["u"][0]) <= TOL
     cap.free() if hasattr(cap, "free") else None
+
+
+@pytest.mark.parametrize("B,N,M", [
+    (24, 40, 2000),      # BASELINE cfg4 (launch/gp_ad_mpc.launch:6-7 horizon, model_fitting/gp.py:403-430 at M = 2000):
+                         # 193 KB GP blob -> one wide CTA per SM in the preparation kernel, two-warp QP kernel
+    (48, 20, 450),       # 44 KB blob: the 36..54 KB launch regime of the preparation kernel
+    (40, 20, 700),       # 68 KB blob: smallest one-CTA-per-SM case
+])
+def test_large_gp_model_parity(B, N, M):
+    """Every launch regime of the GP preparation kernel on ONE device: linearisation to 1e-10, the whole RTI step to
+    1e-8, statuses / QP iteration counts identical."""
+    batch = wl.make_batch(B, N, seed=4000 + M, p=1.0)
+    rng = np.random.default_rng(M)
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([0.5, 0.1])
+    model = wl.make_gp(M=M, seed=9)
+    opts = default_opts(N)
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    s = BatchSolver(B, opts)
+    s.set_gp(model)
+    g = _gpu_step(s, batch)
+    lin = s.get_lin()
+    for i in range(0, B, 5):
+        it = orc.make_iterate(o, batch["x_init"][i], batch["u_init"][i])
+        ref = orc.prepare(o, it, batch["yref"][i], batch["p"][i], gp=gp, gp_state=batch["x0"][i])
+        for key in ("A", "B", "b", "q", "r"):
+            assert mixed_err(lin[key][i], ref[key]) <= 1e-10, key
+    r = oracle_batch(o, batch, gp=gp)
+    assert (r["status"] == 0).all()
+    _compare(g, r)
+    s.close()
+
+
+def test_two_rank_gather_when_two_gpus():
+    """Two ranks, two GPUs: the gathered blocks on the root equal the per-rank results for the NCCL send/recv path and for
+    the fused peer-memory path (scripts/gather_check.py under torchrun).  Skipped on a one-GPU box."""
+    import subprocess, sys
+    from ad_mpc_b200 import _lib
+    if _lib.load().admpc_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "scripts", "gather_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "GATHER_OK world=2" in out.stdout and out.stdout.count("FUSED_GATHER_OK") >= 4, out.stdout[-1500:]
 
 
 def test_two_devices_in_one_process():

@@ -300,3 +300,33 @@ def test_optimizer_marshalling_matches_the_reference_loops():
     prev = np.arange(40.0)
     w = AD3DOptimizerB200._backup(prev)
     assert w.shape == (40,) and np.array_equal(w[:39], np.concatenate((prev[2:-1], prev[-3:-1])))
+
+
+def test_oracle_defaults_equal_product_defaults():
+    """bench.py's reference arm builds its options from the oracle's own defaults (it must not import the product):
+    they have to be the product's defaults, field by field."""
+    from ad_mpc_b200 import default_opts
+    from oracle import oracle as orc
+    from util_parity import OPT_FIELDS
+    for N in (20, 40):
+        po, oo = default_opts(N), orc.default_opts(N=N)
+        for f in OPT_FIELDS:
+            a, b = getattr(po, f), getattr(oo, f)
+            if hasattr(a, "__len__"):
+                assert list(a) == list(b)[:len(a)], f
+            else:
+                assert a == b, f
+
+
+def test_reference_arm_never_loads_the_product():
+    """`bench.py --impl reference` runs the CPU restatement only: no ad_mpc_b200 import, no libadmpc_b200.so in the process."""
+    code = ("import sys, json, io, contextlib; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0'];"
+            "import bench; bench.CFG['B']=64;"
+            "buf=io.StringIO();\n"
+            "with contextlib.redirect_stdout(buf): bench.main()\n"
+            "line=json.loads(buf.getvalue().strip().splitlines()[-1]);"
+            "assert line['impl']=='reference' and line['value']>0 and 'reference_note' not in line['config'];"
+            "assert 'ad_mpc_b200' not in sys.modules;"
+            "assert 'libadmpc_b200' not in open('/proc/self/maps').read(); print('OK')")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-500:] + out.stderr[-1500:]
