@@ -111,6 +111,8 @@ struct admpc_batch {
     int *sqp_active_host = nullptr;  // pinned
     double *gp_blob = nullptr;
     size_t gp_blob_cap = 0;
+    double *gp_res = nullptr;        // per-stage GP results handed from gp_sweep_kernel to prepare_kernel
+    size_t gp_res_cap = 0;
     double *l2_scratch = nullptr;
     size_t l2_bytes = 0;
     double *loop_prev_u = nullptr;      // [2N prev_u | 2 u_apply | 7 x_next][Bp]
@@ -123,7 +125,7 @@ struct admpc_batch {
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     bool profiling = false;
     bool gps_set = false;
-    int qp_variant = 0;      // 0 auto(=4), 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu)
+    int qp_variant = 0;      // 0 auto, 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu), 6 resident warp (qp_rw.cu)
     long long launches = 0;
     float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
     char *pack = nullptr, *gpack = nullptr;     // packed [u | x | status] block of this rank / of all ranks (root)
@@ -192,8 +194,8 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     // Interface arrays always; QP workspaces only for the kernel variant this handle will run: the warp-per-instance
     // kernel (N <= 63) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
     // thread-per-instance kernel streams a 35 KB/instance SoA workspace.
-    const int variant = h->qp_variant ? h->qp_variant : (N <= 63 ? 4 : 3);
-    const bool need_ws3 = (variant == 3 || (variant == 4 && N > 63)) && N <= 80;
+    const int variant = h->qp_variant ? h->qp_variant : (N <= 31 ? 6 : (N <= 63 ? 4 : 3));
+    const bool need_ws3 = (variant == 3 || (variant >= 4 && N > 63)) && N <= 80;
     const bool frenet = h->P.o.model_variant == 1;
     const bool need_ws1 = (variant == 1) || N > 80 || frenet;
     std::vector<Item> items = {
@@ -247,7 +249,7 @@ extern "C" int admpc_batch_free(admpc_batch *h)
     if (h->gpack_peer) cudaIpcCloseMemHandle(h->gpack_peer);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
-    cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack); cudaFree(h->bar_buf);
+    cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->gp_res); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack); cudaFree(h->bar_buf);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->tm0) cudaEventDestroy(h->tm0);
     if (h->tm1) cudaEventDestroy(h->tm1);
@@ -330,12 +332,34 @@ static int upload_gp(admpc_batch *h, int K, int nout, int M, int dz, const int *
     return 0;
 }
 
+// (re)allocates the stage-result buffer of the two-pass GP preparation for the model now configured in P.o
+static int gp_res_alloc(admpc_batch *h)
+{
+    Params &P = h->P;
+    if (!P.o.gp_enabled || P.o.model_variant != 0) return 0;          // the Frenet variant keeps its fused preparation kernel
+    const size_t need = (size_t)P.o.N * 4 * P.o.gp_nout * (1 + P.o.gp_dz) * P.Bp * sizeof(double);
+    if (need > h->gp_res_cap) {
+        cudaFree(h->gp_res);
+        h->gp_res = nullptr; h->gp_res_cap = 0; P.gpr = nullptr;
+        if (cudaMalloc(&h->gp_res, need) != cudaSuccess) {
+            cudaGetLastError();
+            P.o.gp_enabled = 0;
+            admpc_set_error("GP stage-result buffer", "cudaMalloc failed");
+            return ADMPC_E_CUDA;
+        }
+        h->gp_res_cap = need;
+    }
+    P.gpr = h->gp_res;
+    return 0;
+}
+
 extern "C" int admpc_batch_set_gp(admpc_batch *h, int nout, int M, int dz, const int *feat, const int *rows,
                                   const double *X, const double *alpha, const double *ell, const double *sigma_f,
                                   const double *y_mean, int stage0_trigger)
 {
     if (!h) return ADMPC_E_ARG;
-    return upload_gp(h, 1, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, nullptr, stage0_trigger);
+    const int r = upload_gp(h, 1, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, nullptr, stage0_trigger);
+    return r ? r : gp_res_alloc(h);
 }
 
 // GP ensemble (GPEnsemble, gp.py:536-770; homogeneous case: the same K clusters for every output dimension):
@@ -346,7 +370,8 @@ extern "C" int admpc_batch_set_gp_ensemble(admpc_batch *h, int K, int nout, int 
                                            const double *y_mean, const double *centroids, int stage0_trigger)
 {
     if (!h) return ADMPC_E_ARG;
-    return upload_gp(h, K, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, centroids, stage0_trigger);
+    const int r = upload_gp(h, K, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, centroids, stage0_trigger);
+    return r ? r : gp_res_alloc(h);
 }
 
 // nearest-centroid choice per instance from the query state xq [B][7] (NULL: the current x0) and input uq [B][2]
@@ -497,12 +522,13 @@ static int launch_feedback(admpc_batch *h)
         h->launches += 2;
         return 0;
     }
-    // QP variant: 4 (default) warp per instance, register-resident IPM state; 3 shared-memory-resident octets
-    // (horizons 64..80);
-    // 1 one thread per instance.  3 falls back to 1 when the horizon does not fit in shared memory.
-    const int variant = h->qp_variant ? h->qp_variant : 4;
+    // QP variant (0 = auto): 6 warp per instance with the whole solve resident in shared memory (qp_rw.cu, default for
+    // N <= 31); 4 warp(s) per instance with register-resident IPM state (qp_warp.cu, default for 32 <= N <= 63: its
+    // two-warp form); 3 shared-memory octets (horizons 64..80); 1 one thread per instance.  A variant that cannot take
+    // the horizon falls through to the next one.
+    const int variant = h->qp_variant ? h->qp_variant : (P.o.N <= 31 ? 6 : 4);
     bool fused = false;
-    if (variant == 5) { fused = launch_qp_half(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // half a warp per instance
+    if (variant == 6) { fused = launch_qp_rw(P, h->stream); h->gat_fresh = fused && h->gat_on; }     // warp per instance, shared-memory resident
     if (!fused && variant >= 4) { fused = launch_qp_warp(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // one / two warps per instance, N <= 63
     if (!fused && variant >= 3 && P.ws) fused = launch_qp_smem(P, h->stream);
     if (!fused) {
@@ -525,7 +551,7 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
     if (P.o.model_variant == 1) launch_prepare_dense(P, h->stream);
     else launch_prepare(P, h->stream);
-    h->launches += 1;
+    h->launches += (P.o.model_variant == 0 && P.o.gp_enabled) ? 2 : 1;      // GP: sweep kernel + sensitivity kernel
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
     if (int r = launch_feedback(h)) return r;
     CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
@@ -554,7 +580,7 @@ static int solve_sqp_impl(admpc_batch *h, int max_iter, const double *tol4, int 
         CUDA_CHECK_RET(cudaMemsetAsync(ctr, 0, sizeof(int), h->stream));
         if (P.o.model_variant == 1) { launch_prepare_dense(P, h->stream); launch_nlp_res_dense(P, it, tol, ctr, h->stream); }
         else { launch_prepare(P, h->stream); launch_nlp_res(P, it, tol, ctr, h->stream); }
-        h->launches += 2;
+        h->launches += (P.o.model_variant == 0 && P.o.gp_enabled) ? 3 : 2;
         CUDA_CHECK_RET(cudaMemcpyAsync(h->sqp_active_host, ctr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
         running = h->sqp_active_host[0];
@@ -1007,6 +1033,7 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
     int rc = 0;
     if (h->rank == root) {
         rc = upload_gp(h, 1, nout, M, dz, feat, rows, X, alpha, ell, sigma_f, y_mean, nullptr, stage0_trigger);   // single model
+        if (rc == 0) rc = gp_res_alloc(h);
         hdr[0] = (rc == 0);
         if (rc == 0) {
             hdr[1] = nout; hdr[2] = M; hdr[3] = dz; hdr[4] = stage0_trigger;
@@ -1050,6 +1077,7 @@ extern "C" int admpc_batch_bcast_gp(admpc_batch *h, int root, int nout, int M, i
                 P.o.gp_enabled = 1; P.o.gp_nout = nout; P.o.gp_M = M; P.o.gp_dz = dz; P.o.gp_stage0_trigger = hdr[4];
                 for (int d = 0; d < dz; d++) P.o.gp_feat[d] = hdr[5 + d];
                 for (int j = 0; j < nout; j++) P.o.gp_row[j] = hdr[5 + ADMPC_DZMAX + j];
+                if ((rc = gp_res_alloc(h))) bad = 1;
             }
         }
     }

@@ -52,6 +52,7 @@ struct Params {
     double *xb, *ub, *pib, *lamb, *tb, *slb, *sub;
     // linearisation
     double *lin;
+    double *gpr;         // GP mean / feature gradient at the 4 RK4 stage points of every interval: [N*4*nout*(1+dz)][Bp] (prepare.cu)
     // QP solution (delta form) + workspace
     double *dx, *du, *pi, *lam, *t, *sl, *su;
     double *rgu, *rgx, *rgsl, *rgsu, *rb, *rd, *rm;
@@ -102,7 +103,7 @@ void launch_qp(const Params &P, cudaStream_t s);
 bool launch_qp_smem(const Params &P, cudaStream_t s);   // false: horizon too long for the shared-memory variant
 int qp_smem_ws_rows(int N);
 bool launch_qp_warp(const Params &P, cudaStream_t s);   // false: N > 31
-bool launch_qp_half(const Params &P, cudaStream_t s);   // half a warp per instance, false: horizon too long for shared memory
+bool launch_qp_rw(const Params &P, cudaStream_t s);     // one warp per instance, whole solve resident in shared memory, false: N > 63
 void launch_transpose_in(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);   // [B][F] -> [F][Bp]
 void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);  // [F][Bp] -> [B][F]
 void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]

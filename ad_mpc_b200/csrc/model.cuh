@@ -153,6 +153,137 @@ struct Jac {
     double ju[3][2];
 };
 
+
+// GP posterior mean and its gradient w.r.t. the features, per output (model_fitting/gp.py:117-165,446-460)
+struct GpOut { double m[ADMPC_GPOUT_MAX]; double g[ADMPC_GPOUT_MAX][ADMPC_DZMAX]; };
+
+// 2^t for t <= 0 with the FP32 special-function unit (opt-in, admpc_opts.gp_precision = 1): t = n + f, n = rint(t) exact in
+// FP64, 2^f by ex2.approx.ftz.f32 on the FP32 copy of f (|f| <= 1/2: input rounding 3e-8 * ln2 relative, MUFU.EX2 error
+// <= 2 ulp of FP32), 2^n through the FP64 exponent field.  Relative error <= 2^-22 for every argument; 3 FP64-pipe
+// instructions instead of 10.
+__device__ __forceinline__ double exp2_neg_f32(double t)
+{
+    const bool far = (unsigned)__double2hiint(t) > 0xC08F4000u;      // t < -1000
+    const double SHIFT = 6755399441055744.0;                         // 1.5 * 2^52
+    const double tt = t + SHIFT;
+    const int n = __double2loint(tt);
+    const float ff = (float)(t - (tt - SHIFT));
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ff));
+    const double r = (double)e;
+    return __hiloint2double(__double2hiint(r) + (far ? -1000 * (1 << 20) : (n << 20)), __double2loint(r));
+}
+
+// PREC 0: FP64 table-driven exp2 (default) ; 1: FP32 exponential, FP64 everything else
+template <int PREC>
+__device__ __forceinline__ double gp_exp2(double t, uint32_t tab) { return PREC ? exp2_neg_f32(t) : exp2_neg_tab(t, tab); }
+
+// gpsm: shared-memory copy of THIS instance's cluster model (nout output blocks); tab: shared-space address of the
+// 2^(j/GP_TAB) table of the device exp2
+template <int PREC>
+__device__ __forceinline__ void gp_eval(const admpc_opts &o, const double *__restrict__ gpsm, int gp_stride, uint32_t tab,
+                                        const double x[7], const double u[2], const double gpx[7], double trig, GpOut &O)
+{
+    const int dz = o.gp_dz, M = o.gp_M;
+    const double u0 = u[0], u1 = u[1];
+    double z[ADMPC_DZMAX];
+#pragma unroll
+    for (int d = 0; d < ADMPC_DZMAX; d++) {
+        if (d < dz) {
+            const int fi = o.gp_feat[d];
+            double v = 0.0;
+            // feature select without dynamic register indexing
+#pragma unroll
+            for (int s = 2; s < 7; s++) if (fi == s) v = gpx[s] * trig + x[s] * (1.0 - trig);
+            if (fi == 7) v = u0;
+            if (fi == 8) v = u1;
+            z[d] = v;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
+        O.m[j] = 0.0;
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) O.g[j][d] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
+        if (j >= o.gp_nout) continue;
+        // blob per output: M points of {a_0..a_{dz-1}, c, sigma_f*alpha} with a_d = log2(e) X_d / ell_d^2 and
+        // c = -0.5 log2(e) sum_d X_d^2/ell_d^2, so that  log2 k(z, X_i) = q + c_i + a_i . z,
+        // q = -0.5 log2(e) sum_d z_d^2/ell_d^2  (expanded square: 4 FMAs per point instead of 12 ops; the
+        // cancellation costs ~1e-15 absolute in the exponent).  Tail: 1/ell_d^2 (dz values), y_mean.
+        const double *blk = gpsm + (size_t)j * gp_stride;
+        const double *w = blk + (size_t)M * (dz + 2);
+        double wv[ADMPC_DZMAX];
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) wv[d] = (d < dz) ? w[d] : 0.0;
+        double q = 0.0;
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) q = fma(z[d] * wv[d], z[d], q);
+        q *= -0.5 * 1.4426950408889634;
+        double m = 0.0, G2[ADMPC_DZMAX];
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) G2[d] = 0.0;
+        if (dz == 4) {
+            // hot case: 4 features -> 48 B per point, three LDS.128.  (Two-point interleaving and software
+            // pipelining in the source were both tried: ptxas re-serialises the chains, no gain.)
+#pragma unroll 4
+            for (int i = 0; i < M; i++) {
+                const double2 *pt = reinterpret_cast<const double2 *>(blk + (size_t)i * 6);
+                const double2 a01 = pt[0], a23 = pt[1], ca = pt[2];
+                const double t = fma(a23.y, z[3], fma(a23.x, z[2], fma(a01.y, z[1], fma(a01.x, z[0], q + ca.x))));
+                const double ka = gp_exp2<PREC>(t, tab) * ca.y;
+                m += ka;
+                G2[0] = fma(ka, a01.x, G2[0]); G2[1] = fma(ka, a01.y, G2[1]);
+                G2[2] = fma(ka, a23.x, G2[2]); G2[3] = fma(ka, a23.y, G2[3]);
+            }
+        } else {
+            for (int i = 0; i < M; i++) {
+                const double *pt = blk + (size_t)i * (dz + 2);
+                double t = q + pt[dz];
+#pragma unroll
+                for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) t = fma(pt[d], z[d], t);
+                const double ka = gp_exp2<PREC>(t, tab) * pt[dz + 1];
+                m += ka;
+#pragma unroll
+                for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G2[d] = fma(ka, pt[d], G2[d]);
+            }
+        }
+        // d mu / d z_d = -sum_i ka_i (z_d - X_id)/ell_d^2 = -(z_d/ell_d^2 * m - ln2 * G2_d)
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) O.g[j][d] = fma(0.6931471805599453, G2[d], -(z[d] * wv[d]) * m);
+        O.m[j] = m + w[dz];   // + y_mean
+    }
+}
+
+// f + B_x mu(z) and its Jacobian rows (quad_mpc/quad_3d_optimizer.py:295,315; utils/utils.py:773-808)
+__device__ __forceinline__ void gp_apply(const admpc_opts &o, double trig, const GpOut &O, double f[7], Jac &J)
+{
+    const int dz = o.gp_dz;
+#pragma unroll
+    for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
+        if (j >= o.gp_nout) continue;
+        const int row = o.gp_row[j] - 3;       // 0..2
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            if (rr == row) {
+                f[3 + rr] += O.m[j];
+#pragma unroll
+                for (int d = 0; d < ADMPC_DZMAX; d++) {
+                    if (d < dz) {
+                        const int fi = o.gp_feat[d];
+#pragma unroll
+                        for (int s = 2; s < 7; s++) if (fi == s) J.jr[rr][s - 2] += (1.0 - trig) * O.g[j][d];
+                        if (fi == 7) J.ju[rr][0] += O.g[j][d];
+                        if (fi == 8) J.ju[rr][1] += O.g[j][d];
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <bool GP>
 // gpsm: shared-memory copy of THIS instance's cluster model (nout output blocks); tab: shared-space address of the
 // 2^(j/GP_TAB) table of the device exp2
@@ -210,85 +341,8 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
     J.ju[2][0] = q * dl * iL; J.ju[2][1] = q * vx * iL;
 
     if (GP) {
-        const int dz = o.gp_dz, M = o.gp_M;
-        double z[ADMPC_DZMAX];
-#pragma unroll
-        for (int d = 0; d < ADMPC_DZMAX; d++) {
-            if (d < dz) {
-                const int fi = o.gp_feat[d];
-                double v = 0.0;
-                // feature select without dynamic register indexing
-#pragma unroll
-                for (int s = 2; s < 7; s++) if (fi == s) v = gpx[s] * trig + x[s] * (1.0 - trig);
-                if (fi == 7) v = u0;
-                if (fi == 8) v = u1;
-                z[d] = v;
-            }
-        }
-        for (int j = 0; j < o.gp_nout; j++) {
-            // blob per output: M points of {a_0..a_{dz-1}, c, sigma_f*alpha} with a_d = log2(e) X_d / ell_d^2 and
-            // c = -0.5 log2(e) sum_d X_d^2/ell_d^2, so that  log2 k(z, X_i) = q + c_i + a_i . z,
-            // q = -0.5 log2(e) sum_d z_d^2/ell_d^2  (expanded square: 4 FMAs per point instead of 12 ops; the
-            // cancellation costs ~1e-15 absolute in the exponent).  Tail: 1/ell_d^2 (dz values), y_mean.
-            const double *blk = gpsm + (size_t)j * gp_stride;
-            const double *w = blk + (size_t)M * (dz + 2);
-            double wv[ADMPC_DZMAX];
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) wv[d] = (d < dz) ? w[d] : 0.0;
-            double q = 0.0;
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) q = fma(z[d] * wv[d], z[d], q);
-            q *= -0.5 * 1.4426950408889634;
-            double m = 0.0, g[ADMPC_DZMAX], G2[ADMPC_DZMAX];
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) { g[d] = 0.0; G2[d] = 0.0; }
-            if (dz == 4) {
-                // hot case: 4 features -> 48 B per point, three LDS.128.  (Two-point interleaving and software
-                // pipelining in the source were both tried: ptxas re-serialises the chains, no gain.)
-#pragma unroll 4
-                for (int i = 0; i < M; i++) {
-                    const double2 *pt = reinterpret_cast<const double2 *>(blk + (size_t)i * 6);
-                    const double2 a01 = pt[0], a23 = pt[1], ca = pt[2];
-                    const double t = fma(a23.y, z[3], fma(a23.x, z[2], fma(a01.y, z[1], fma(a01.x, z[0], q + ca.x))));
-                    const double ka = exp2_neg_tab(t, tab) * ca.y;
-                    m += ka;
-                    G2[0] = fma(ka, a01.x, G2[0]); G2[1] = fma(ka, a01.y, G2[1]);
-                    G2[2] = fma(ka, a23.x, G2[2]); G2[3] = fma(ka, a23.y, G2[3]);
-                }
-            } else {
-                for (int i = 0; i < M; i++) {
-                    const double *pt = blk + (size_t)i * (dz + 2);
-                    double t = q + pt[dz];
-#pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) t = fma(pt[d], z[d], t);
-                    const double ka = exp2_neg_tab(t, tab) * pt[dz + 1];
-                    m += ka;
-#pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G2[d] = fma(ka, pt[d], G2[d]);
-                }
-            }
-            // d mu / d z_d = -sum_i ka_i (z_d - X_id)/ell_d^2 = -(z_d/ell_d^2 * m - ln2 * G2_d)
-#pragma unroll
-            for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) g[d] = fma(0.6931471805599453, G2[d], -(z[d] * wv[d]) * m);
-            m += w[dz];   // y_mean
-            const int row = o.gp_row[j] - 3;       // 0..2
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
-                if (rr == row) {
-                    f[3 + rr] += m;
-#pragma unroll
-                    for (int d = 0; d < ADMPC_DZMAX; d++) {
-                        if (d < dz) {
-                            const int fi = o.gp_feat[d];
-#pragma unroll
-                            for (int s = 2; s < 7; s++) if (fi == s) J.jr[rr][s - 2] += (1.0 - trig) * g[d];
-                            if (fi == 7) J.ju[rr][0] += g[d];
-                            if (fi == 8) J.ju[rr][1] += g[d];
-                        }
-                    }
-                }
-            }
-        }
+        GpOut G;
+        gp_eval<0>(o, gpsm, gp_stride, tab, x, u, gpx, trig, G);
+        gp_apply(o, trig, G, f, J);
     }
 }
-

@@ -6,8 +6,10 @@
 //     here the Jacobian is hand-derived and only its structurally non-zero entries are touched:
 //     columns p_x,p_y of J_x are zero and row delta is trivial, so S keeps [e0 e1 | 6x5 block] + 6x2 input block.
 //   * optional GP residual f + B_x mu(z) and its Jacobian (model_fitting/gp.py:117-165,446-460;
-//     quad_mpc/quad_3d_optimizer.py:295,315): training set staged into shared memory once per CTA with a TMA bulk
-//     copy (cp.async.bulk + mbarrier), every thread then sweeps the M points with broadcast LDS.
+//     quad_mpc/quad_3d_optimizer.py:295,315) in TWO passes: gp_sweep_kernel evaluates mean and feature gradient at the
+//     four RK4 stage points (training set staged into shared memory once per CTA with a TMA bulk copy, cp.async.bulk +
+//     mbarrier; every thread sweeps the M points with broadcast LDS), prepare_kernel<true> then propagates the
+//     sensitivities with those terms read back -- the stage points do not depend on the sensitivities.
 //   * LINEAR_LS gradient and multiple-shooting residual (acados_solver_sim_car.c:378-485).
 // Output: lin[k][58][Bp] (A 6x5, B 6x2, b 7, q 7, r 2), SoA, coalesced.
 #include "common.cuh"
@@ -40,80 +42,126 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 #include "model.cuh"
 
-// One RK4 step with forward sensitivities. Sensitivity state: rows 0..5 x 7 columns [x2..x6 | u0 u1];
-// row 6 (delta) is analytic: d delta / d delta = 1, d delta / d u1 = t.
+// GP results of one RK4 stage, SoA rows of gpr: [(k*4 + s) * R + j*(1+dz) + {0: mean, 1+d: d mean / d z_d}][Bp], R = nout*(1+dz)
+__device__ __forceinline__ int gpr_rows(const admpc_opts &o) { return o.gp_nout * (1 + o.gp_dz); }
+
+// ---- pass 1 of the GP-augmented preparation: the GP sweeps -----------------------------------------------------------------
+// One thread per (instance, shooting interval) walks the four RK4 stages of the STATE only (the stage points do not depend
+// on the sensitivities) and evaluates the GP mean and its feature gradient at each of them: 4 sweeps over the M training
+// points staged in shared memory by one TMA bulk copy per CTA.  The 84-double sensitivity state is not alive here, so the
+// kernel runs at 24 warps per SM without pushing it through local memory around every sweep (the fused kernel moved
+// 2.8 GB of DRAM traffic per launch that way); the results (10 doubles per stage at d_z = 4, two outputs) go to gpr.
 // ENS: GP ensemble -- the cluster model is chosen per instance, so the training-set loads use per-thread addresses; a
 // single model keeps warp-uniform addresses (uniform-register LDS), which is measurably cheaper.
-template <bool GP, int BLOCK, int MINB, bool ENS = false>
-__global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
+template <int BLOCK, int MINB, bool ENS, int PREC>
+__global__ void __launch_bounds__(BLOCK, MINB) gp_sweep_kernel(const Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    const double *gpsm = nullptr;
-    if (GP) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, (uint32_t)P.gp.bytes);
-            // TMA bulk copies, <= 64 KB each
-            uint32_t off = 0;
-            while (off < (uint32_t)P.gp.bytes) {
-                uint32_t n = min((uint32_t)P.gp.bytes - off, 65536u);
-                tma_bulk_g2s(smem_raw + off, (const unsigned char *)P.gp.blob + off, n, &bar);
-                off += n;
-            }
-        }
-        gpsm = reinterpret_cast<const double *>(smem_raw);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)P.gp.bytes);
+        uint32_t off = 0;                      // TMA bulk copies, <= 64 KB each
+        while (off < (uint32_t)P.gp.bytes) {
+            uint32_t n = min((uint32_t)P.gp.bytes - off, 65536u);
+            tma_bulk_g2s(smem_raw + off, (const unsigned char *)P.gp.blob + off, n, &bar);
+            off += n;
+        }
+    }
+    const double *gpsm = reinterpret_cast<const double *>(smem_raw);
+    const admpc_opts &o = P.o;
+    const int Bp = P.Bp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;                                   // k < N
+    const double h = o.dt;
+    const bool active = (i < P.B) && (P.lin_bad[i] != 2);      // 2: finished instance of the full-SQP loop (sqp.cu)
+    const bool trg = (o.gp_stage0_trigger && k == 0);
+    const double trig = trg ? 1.0 : 0.0;
+    mbar_wait(&bar, 0);
+    if (!active) return;
+    const double *gpm = ENS ? gpsm + (size_t)P.gp_sel[i] * P.gp.model_doubles : gpsm;   // this instance's cluster model
+    const uint32_t tab = (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)P.gp.n_models * P.gp.model_doubles);
+    const int R = gpr_rows(o), dz = o.gp_dz;
+    double kx[7];
+#pragma unroll
+    for (int c = 0; c < 7; c++) kx[c] = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {
+        const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
+        const double ha = h * as;
+        // x, u, p, gp_state are re-read per stage (coalesced, L1/L2 hits) instead of being kept alive across the sweep
+        double xs[7], u[2], gpx[7], f[7];
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            xs[c] = fma(ha, kx[c], P.xb[(size_t)(k * 7 + c) * Bp + i]);
+            gpx[c] = trg ? P.gps[(size_t)c * Bp + i] : 0.0;
+        }
+        u[0] = P.ub[(size_t)(k * 2 + 0) * Bp + i]; u[1] = P.ub[(size_t)(k * 2 + 1) * Bp + i];
+        const double pk = P.p[(size_t)k * Bp + i];
+        GpOut G;
+        gp_eval<PREC>(o, gpm, P.gp.stride_out, tab, xs, u, gpx, trig, G);
+        double *out = P.gpr + (size_t)(k * 4 + s) * R * Bp + i;
+#pragma unroll
+        for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
+            if (j >= o.gp_nout) continue;
+            out[(size_t)(j * (1 + dz)) * Bp] = G.m[j];
+#pragma unroll
+            for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) out[(size_t)(j * (1 + dz) + 1 + d) * Bp] = G.g[j][d];
+        }
+        if (s == 3) break;
+        Jac J;
+        model_eval<false>(o, nullptr, 0, 0u, xs, u, pk, gpx, trig, f, J);        // nominal f (its Jacobian is dead code here)
+        gp_apply(o, trig, G, f, J);
+#pragma unroll
+        for (int c = 0; c < 7; c++) kx[c] = f[c];
+    }
+}
+
+// ---- pass 2 / nominal preparation: one RK4 step with forward sensitivities --------------------------------------------------
+// Sensitivity state: rows 0..5 x 7 columns [x2..x6 | u0 u1]; row 6 (delta) is analytic: d delta / d delta = 1,
+// d delta / d u1 = t.  GPR: the GP mean / gradient of every RK4 stage come from gpr (written by gp_sweep_kernel).
+template <bool GPR>
+__global__ void __launch_bounds__(128) prepare_kernel(const Params P)
+{
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     const double h = o.dt;
-    const bool active = (i < P.B) && (P.lin_bad[i] != 2);      // 2: finished instance of the full-SQP loop (sqp.cu)
+    if (!((i < P.B) && (P.lin_bad[i] != 2))) return;           // 2: finished instance of the full-SQP loop (sqp.cu)
 
     double x[7], u[2], xn[7], yr[9];
     double pk = 0.0;
-    if (active) {
 #pragma unroll
-        for (int c = 0; c < 7; c++) x[c] = P.xb[(size_t)(k * 7 + c) * Bp + i];
-        if (k < N) {
+    for (int c = 0; c < 7; c++) x[c] = P.xb[(size_t)(k * 7 + c) * Bp + i];
+    if (k < N) {
 #pragma unroll
-            for (int c = 0; c < 7; c++) xn[c] = P.xb[(size_t)((k + 1) * 7 + c) * Bp + i];
+        for (int c = 0; c < 7; c++) xn[c] = P.xb[(size_t)((k + 1) * 7 + c) * Bp + i];
 #pragma unroll
-            for (int c = 0; c < 2; c++) u[c] = P.ub[(size_t)(k * 2 + c) * Bp + i];
+        for (int c = 0; c < 2; c++) u[c] = P.ub[(size_t)(k * 2 + c) * Bp + i];
 #pragma unroll
-            for (int c = 0; c < 9; c++) yr[c] = P.yref[(size_t)(k * 9 + c) * Bp + i];
-            pk = P.p[(size_t)k * Bp + i];
-        } else {
+        for (int c = 0; c < 9; c++) yr[c] = P.yref[(size_t)(k * 9 + c) * Bp + i];
+        pk = P.p[(size_t)k * Bp + i];
+    } else {
 #pragma unroll
-            for (int c = 0; c < 7; c++) yr[c] = P.yref[(size_t)(N * 9 + c) * Bp + i];
-        }
+        for (int c = 0; c < 7; c++) yr[c] = P.yref[(size_t)(N * 9 + c) * Bp + i];
     }
     double *lin = P.lin + (size_t)k * LIN_ROWS * Bp + i;
     if (k == N) {
         // terminal cost gradient, scaling 1
-        if (active) {
 #pragma unroll
-            for (int c = 0; c < 7; c++) lin[(size_t)(LIN_q + c) * Bp] = o.We[c] * (x[c] - yr[c]);
-        }
-        if (GP) mbar_wait(&bar, 0);   // do not exit with the bulk copy in flight
+        for (int c = 0; c < 7; c++) lin[(size_t)(LIN_q + c) * Bp] = o.We[c] * (x[c] - yr[c]);
         return;
     }
     double gpx[7];
-    double trig = 0.0;
-    if (GP) {
-        trig = (o.gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
 #pragma unroll
-        for (int c = 0; c < 7; c++) gpx[c] = (active && k == 0 && o.gp_stage0_trigger) ? P.gps[(size_t)c * Bp + i] : 0.0;
-        mbar_wait(&bar, 0);
-    }
-    if (!active) return;
-    const double *gpm = (GP && ENS) ? gpsm + (size_t)P.gp_sel[i] * P.gp.model_doubles : gpsm;   // this instance's cluster model
-    const uint32_t tab = GP ? (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)P.gp.n_models * P.gp.model_doubles) : 0u;
+    for (int c = 0; c < 7; c++) gpx[c] = 0.0;
+    const double trig = (GPR && o.gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
+    const int R = GPR ? gpr_rows(o) : 0, dz = o.gp_dz;
 
     // K = current stage derivative of the sensitivity block, acc = weighted sum (rows 0..5 x 7 cols)
     double K[6][7], acc[6][7];
@@ -126,7 +174,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
     for (int c = 0; c < 7; c++) { kx[c] = 0.0; ax[c] = 0.0; }
 
 #pragma unroll 1
-    for (int s = 0; s < 4; s++) {          // not unrolled: 4 copies of the GP sweep would not fit the instruction cache
+    for (int s = 0; s < 4; s++) {
         const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
         const double bs = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
         const double ha = h * as;
@@ -134,7 +182,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
 #pragma unroll
         for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
         Jac J;
-        model_eval<GP>(o, gpm, P.gp.stride_out, tab, xs, u, pk, gpx, trig, f, J);
+        model_eval<false>(o, nullptr, 0, 0u, xs, u, pk, gpx, trig, f, J);
+        if (GPR) {
+            GpOut G;
+            const double *in = P.gpr + (size_t)(k * 4 + s) * R * Bp + i;
+#pragma unroll
+            for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
+                G.m[j] = 0.0;
+#pragma unroll
+                for (int d = 0; d < ADMPC_DZMAX; d++) G.g[j][d] = 0.0;
+                if (j >= o.gp_nout) continue;
+                G.m[j] = in[(size_t)(j * (1 + dz)) * Bp];
+#pragma unroll
+                for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G.g[j][d] = in[(size_t)(j * (1 + dz) + 1 + d) * Bp];
+            }
+            gp_apply(o, trig, G, f, J);
+        }
 #pragma unroll
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
         // sensitivity columns: c = 0..4 <-> x2..x6, c = 5,6 <-> u0,u1
@@ -193,51 +256,55 @@ __global__ void __launch_bounds__(BLOCK, MINB) prepare_kernel(const Params P)
 
 void launch_prepare(const Params &P, cudaStream_t s)
 {
-    if (P.o.gp_enabled) {
-        // register budget capped at 80 (24 warps/SM) or 128 (16 warps/SM): the GP sweep itself needs ~60 registers, the
-        // RK4 sensitivity state is spilled around it (once per RK4 stage, negligible against the M-point loop).
-        // Small models: 6 CTAs x 128 threads per SM; large models (one CTA per SM by shared memory): 512 / 768 threads.
-        const size_t sm = (size_t)P.gp.bytes;
-#define LAUNCH_PREP(BOUND, MINB, BLK)                                                                                    \
+    dim3 gridB((P.Bp + 127) / 128, P.o.N + 1);
+    if (!P.o.gp_enabled) {
+        prepare_kernel<false><<<gridB, 128, 0, s>>>(P);
+        return;
+    }
+    // pass 1: the GP sweeps.  Register budget capped at 80 (24 warps/SM) for small models; models above 36 KB run
+    // 4 CTAs x 128 registers, models above 54 KB one CTA per SM whose width is picked below.
+    const size_t sm = (size_t)P.gp.bytes;
+    const bool ens = P.gp.n_models > 1;
+    const int prec = P.o.gp_precision ? 1 : 0;
+#define LAUNCH_GP1(BOUND, MINB, BLK, ENS, PREC)                                                                          \
     do {                                                                                                                \
         static SmemGuard configured;                                                                                   \
-        if (configured.need(sm)) {                                                                                          \
-            cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-            cudaFuncSetAttribute(prepare_kernel<true, BOUND, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        }                                                                                                               \
-        dim3 grid((P.Bp + (BLK) - 1) / (BLK), P.o.N + 1);                                                               \
-        if (P.gp.n_models > 1) prepare_kernel<true, BOUND, MINB, true><<<grid, (BLK), sm, s>>>(P);                      \
-        else prepare_kernel<true, BOUND, MINB, false><<<grid, (BLK), sm, s>>>(P);                                       \
+        if (configured.need(sm))                                                                                        \
+            cudaFuncSetAttribute(gp_sweep_kernel<BOUND, MINB, ENS, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        dim3 grid((P.Bp + (BLK) - 1) / (BLK), P.o.N);                                                                   \
+        gp_sweep_kernel<BOUND, MINB, ENS, PREC><<<grid, (BLK), sm, s>>>(P);                                             \
     } while (0)
-        if (sm <= 36 * 1024) {
-            LAUNCH_PREP(128, 6, 128);       // 80 registers, 24 warps/SM
-        } else if (sm <= 54 * 1024) {
-            LAUNCH_PREP(128, 4, 128);
-        } else {
-            // One CTA per SM by shared memory.  All CTAs of the N working grid rows take the same time, so the run time is
-            // (number of waves over the device's SMs) x (CTA width): pick the width, in warps, that minimises it; wider CTAs
-            // run with a lower register cap (more resident warps, slightly better latency hiding).
-            static int sm_count[64] = {};                        // SMs of the device this launch goes to (cached per device)
-            int dev = 0;
-            cudaGetDevice(&dev);
-            dev &= 63;
-            if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-            const int nsm = sm_count[dev] > 0 ? sm_count[dev] : 148;
-            int best = 512;
-            double best_cost = 1e300;
-            for (int blk = 1024; blk >= 256; blk -= 32) {
-                const long ctas = (long)((P.Bp + blk - 1) / blk) * P.o.N;
-                const double eff = blk > 768 ? 1.02 : blk > 640 ? 0.96 : blk > 512 ? 0.98 : 1.0;   // measured per-thread cost
-                const double cost = (double)((ctas + nsm - 1) / nsm) * blk * eff;
-                if (cost < best_cost) { best_cost = cost; best = blk; }
-            }
-            if (best <= 512) LAUNCH_PREP(512, 1, best);
-            else if (best <= 640) LAUNCH_PREP(640, 1, best);
-            else if (best <= 768) LAUNCH_PREP(768, 1, best);
-            else LAUNCH_PREP(1024, 1, best);
-        }
+#define LAUNCH_GP(BOUND, MINB, BLK)                                                                                      \
+    do {                                                                                                                \
+        if (ens) { if (prec) LAUNCH_GP1(BOUND, MINB, BLK, true, 1); else LAUNCH_GP1(BOUND, MINB, BLK, true, 0); }       \
+        else { if (prec) LAUNCH_GP1(BOUND, MINB, BLK, false, 1); else LAUNCH_GP1(BOUND, MINB, BLK, false, 0); }         \
+    } while (0)
+    if (sm <= 36 * 1024) {
+        LAUNCH_GP(128, 6, 128);       // 80 registers, 24 warps/SM
+    } else if (sm <= 54 * 1024) {
+        LAUNCH_GP(128, 4, 128);
     } else {
-        dim3 grid((P.Bp + 127) / 128, P.o.N + 1);
-        prepare_kernel<false, 128, 1><<<grid, 128, 0, s>>>(P);
+        // One CTA per SM by shared memory.  All CTAs of the N grid rows take the same time, so the run time is
+        // (number of waves over the device's SMs) x (CTA width): pick the width, in warps, that minimises it; wider CTAs
+        // run with a lower register cap (more resident warps, slightly better latency hiding).
+        static int sm_count[64] = {};                        // SMs of the device this launch goes to (cached per device)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        const int nsm = sm_count[dev] > 0 ? sm_count[dev] : 148;
+        int best = 512;
+        double best_cost = 1e300;
+        for (int blk = 1024; blk >= 256; blk -= 32) {
+            const long ctas = (long)((P.Bp + blk - 1) / blk) * P.o.N;
+            const double cost = (double)((ctas + nsm - 1) / nsm) * blk;
+            if (cost < best_cost) { best_cost = cost; best = blk; }
+        }
+        if (best <= 512) LAUNCH_GP(512, 1, best);
+        else if (best <= 640) LAUNCH_GP(640, 1, best);
+        else if (best <= 768) LAUNCH_GP(768, 1, best);
+        else LAUNCH_GP(1024, 1, best);
     }
+    // pass 2: RK4 + forward sensitivities with the stored GP terms
+    prepare_kernel<true><<<gridB, 128, 0, s>>>(P);
 }

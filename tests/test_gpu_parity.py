@@ -361,8 +361,9 @@ def test_scale_invariance_full_size():
 
 
 def test_long_horizon_fallback_variants():
-    """Horizon dispatch of the feedback kernel: N <= 31 one warp per instance, 32..63 two warps per instance, 64..80 the
-    shared-memory octet kernel, above that one thread per instance -- same parity bar on both sides of every edge."""
+    """Horizon dispatch of the feedback kernel: N <= 31 the shared-memory-resident warp kernel (qp_rw), 32..63 two warps
+    per instance (qp_warp), 64..80 the shared-memory octet kernel, above that one thread per instance -- same parity bar
+    on both sides of every edge."""
     for N, B in ((31, 16), (32, 16), (40, 24), (63, 12), (64, 12), (90, 12)):
         batch = wl.make_batch(B, N, seed=31, p=1.0, perturb=3.0 if N in (32, 63) else 1.0)
         opts = default_opts(N)
@@ -390,19 +391,19 @@ def test_two_warp_kernel_matches_octet_kernel(monkeypatch):
 
 
 def test_qp_variants_agree(monkeypatch):
-    """The three QP kernels are independent implementations of the same algorithm: identical statuses / iteration
+    """The four QP kernels are independent implementations of the same algorithm: identical statuses / iteration
     counts and 1e-8 agreement on a batch with active bounds."""
     B, N = 128, 20
     batch = wl.make_batch(B, N, seed=77, p=0.5, perturb=5.0)
     out = {}
-    for v in (1, 3, 4):
+    for v in (1, 3, 4, 6):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, default_opts(N))
         out[v] = _gpu_step(s, batch)
         s.close()
-    for v in (1, 3):
-        assert np.array_equal(out[v]["qp_iter"], out[4]["qp_iter"]) and np.array_equal(out[v]["status"], out[4]["status"])
-        assert mixed_err(out[v]["u"], out[4]["u"]) <= TOL and mixed_err(out[v]["x"], out[4]["x"]) <= TOL
+    for v in (1, 3, 4):
+        assert np.array_equal(out[v]["qp_iter"], out[6]["qp_iter"]) and np.array_equal(out[v]["status"], out[6]["status"])
+        assert mixed_err(out[v]["u"], out[6]["u"]) <= TOL and mixed_err(out[v]["x"], out[6]["x"]) <= TOL
 
 
 def test_non_default_weights_and_quadratic_slack_penalty():
@@ -505,7 +506,7 @@ def test_sqp_mode_with_gp_and_other_qp_kernels(monkeypatch):
     gp = orc.Gp(model)
     gp.apply(o, feat=model["feat"], rows=model["rows"])
     r = orc.sqp_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=gp, gp_state=batch["x0"])
-    for v in (4, 3, 1):
+    for v in (6, 4, 3, 1):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, opts)
         s.set_gp(model)
