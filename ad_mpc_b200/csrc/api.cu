@@ -198,12 +198,15 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     const bool need_ws3 = (variant == 3 || (variant >= 4 && N > 63)) && N <= 80;
     const bool frenet = h->P.o.model_variant == 1;
     const bool need_ws1 = (variant == 1) || N > 80 || frenet;
+    // the shared-memory-resident warp kernel (variant 6) stages instance-major linearisation records by TMA; every other
+    // feedback kernel reads the SoA rows.  Exactly one of the two layouts exists per handle.
+    const bool use_im = (variant == 6) && N <= 63 && !frenet;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
         {&P.nlp_res, 4},
         {&P.lin_d, frenet ? (size_t)(N + 1) * DL_ROWS : 0}, {&kap, frenet ? (size_t)N : 0},
-        {&P.lin, (size_t)(N + 1) * LIN_ROWS}, {&P.res_out, 4},
+        {&P.lin, use_im ? 0 : (size_t)(N + 1) * LIN_ROWS}, {&P.lin_im, use_im ? (size_t)(N + 1) * LIM_STRIDE : 0}, {&P.res_out, 4},
     };
     if (need_ws3) items.push_back({&P.ws, (size_t)qp_smem_ws_rows(N)});
     if (need_ws1) {
@@ -220,7 +223,7 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     CREATE_CK(cudaMalloc(&h->pool, rows * Bp * sizeof(double)));
     CREATE_CK(cudaMemsetAsync(h->pool, 0, rows * Bp * sizeof(double), h->stream));
     size_t off = 0;
-    for (auto &it : items) { *it.p = h->pool + off * Bp; off += it.rows; }
+    for (auto &it : items) { *it.p = it.rows ? h->pool + off * Bp : nullptr; off += it.rows; }
     P.x0 = x0; P.yref = yref; P.p = pp; P.gps = gps; P.kappa = kap;
     CREATE_CK(cudaMalloc(&h->ipool, (7 * Bp + 32) * sizeof(int)));
     CREATE_CK(cudaMemsetAsync(h->ipool, 0, (7 * Bp + 32) * sizeof(int), h->stream));
@@ -676,9 +679,8 @@ extern "C" int admpc_batch_get_status(admpc_batch *h, int *status, int *qp_statu
 __global__ void expand_lin_kernel(const Params P, double *A, double *Bm, double *b, double *q, double *r)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-    const int N = P.o.N, Bp = P.Bp;
+    const int N = P.o.N;
     if (i >= P.B) return;
-    const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp + i;
     if (k < N) {
         double *Ao = A + ((size_t)i * N + k) * 49, *Bo = Bm + ((size_t)i * N + k) * 14;
         for (int rr = 0; rr < 7; rr++)
@@ -686,15 +688,15 @@ __global__ void expand_lin_kernel(const Params P, double *A, double *Bm, double 
                 double v;
                 if (c < 2) v = (rr == c) ? 1.0 : 0.0;
                 else if (rr == 6) v = (c == 6) ? 1.0 : 0.0;
-                else v = lin[(size_t)(LIN_A + rr * 5 + (c - 2)) * Bp];
+                else v = lin_get(P, k, LIN_A + rr * 5 + (c - 2), i);
                 Ao[rr * 7 + c] = v;
             }
         for (int rr = 0; rr < 7; rr++)
-            for (int c = 0; c < 2; c++) Bo[rr * 2 + c] = (rr == 6) ? ((c == 1) ? P.o.dt : 0.0) : lin[(size_t)(LIN_B + rr * 2 + c) * Bp];
-        for (int c = 0; c < 7; c++) b[((size_t)i * N + k) * 7 + c] = lin[(size_t)(LIN_b + c) * Bp];
-        for (int c = 0; c < 2; c++) r[((size_t)i * N + k) * 2 + c] = lin[(size_t)(LIN_r + c) * Bp];
+            for (int c = 0; c < 2; c++) Bo[rr * 2 + c] = (rr == 6) ? ((c == 1) ? P.o.dt : 0.0) : lin_get(P, k, LIN_B + rr * 2 + c, i);
+        for (int c = 0; c < 7; c++) b[((size_t)i * N + k) * 7 + c] = lin_get(P, k, LIN_b + c, i);
+        for (int c = 0; c < 2; c++) r[((size_t)i * N + k) * 2 + c] = lin_get(P, k, LIN_r + c, i);
     }
-    for (int c = 0; c < 7; c++) q[((size_t)i * (N + 1) + k) * 7 + c] = lin[(size_t)(LIN_q + c) * Bp];
+    for (int c = 0; c < 7; c++) q[((size_t)i * (N + 1) + k) * 7 + c] = lin_get(P, k, LIN_q + c, i);
 }
 
 extern "C" int admpc_batch_get_lin(admpc_batch *h, double *A, double *Bm, double *b, double *q, double *r)

@@ -21,6 +21,19 @@
 #define LIN_q 49
 #define LIN_r 56
 #define LIN_ROWS 58
+// instance-major twin of the block, lin_im[k][i][LIM_STRIDE] (one 544-byte record per instance and stage, pulled into shared
+// memory by one TMA bulk copy): M = [B | A(:,2:7)] column-major c*6 + r, then b, q, r and the linearisation point x_k, u_k
+#define LIM_M 0
+#define LIM_B 42
+#define LIM_Q 49
+#define LIM_R 56
+#define LIM_X 58
+#define LIM_U 65
+#define LIM_STRIDE 68
+__host__ __device__ __forceinline__ constexpr int lim_of_row(int row)      // SoA row -> offset inside the record
+{
+    return (row < LIN_B) ? (2 + row % 5) * 6 + row / 5 : (row < LIN_b) ? ((row - LIN_B) % 2) * 6 + (row - LIN_B) / 2 : row;
+}
 
 // entries of the 2^(j/GP_TAB) table of the device exp2 (model.cuh), stored behind the last GP output in the blob
 #ifndef GP_TAB_BITS
@@ -50,8 +63,9 @@ struct Params {
     const double *x0, *yref, *p, *gps;
     // iterate
     double *xb, *ub, *pib, *lamb, *tb, *slb, *sub;
-    // linearisation
+    // linearisation: SoA rows (lin) or instance-major records (lin_im), exactly one of them per handle
     double *lin;
+    double *lin_im;
     double *gpr;         // GP mean / feature gradient at the 4 RK4 stage points of every interval: [N*4*nout*(1+dz)][Bp] (prepare.cu)
     // QP solution (delta form) + workspace
     double *dx, *du, *pi, *lam, *t, *sl, *su;
@@ -73,6 +87,12 @@ struct Params {
     double *gat_u, *gat_x;
     int *gat_st;
 };
+
+// one entry of the linearisation of stage k, whichever layout the handle uses (kernels off the hot path)
+__device__ __forceinline__ double lin_get(const Params &P, int k, int row, int i)
+{
+    return P.lin_im ? P.lin_im[((size_t)k * P.Bp + i) * LIM_STRIDE + lim_of_row(row)] : P.lin[((size_t)k * LIN_ROWS + row) * P.Bp + i];
+}
 
 #define CUDA_CHECK_RET(call)                                                         \
     do {                                                                             \

@@ -14,31 +14,7 @@
 // Output: lin[k][58][Bp] (A 6x5, B 6x2, b 7, q 7, r 2), SoA, coalesced.
 #include "common.cuh"
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n .reg .pred p;\n WAIT_%=:\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+#include "tma.cuh"
 
 #include "model.cuh"
 
@@ -124,15 +100,47 @@ __global__ void __launch_bounds__(BLOCK, MINB) gp_sweep_kernel(const Params P)
 // ---- pass 2 / nominal preparation: one RK4 step with forward sensitivities --------------------------------------------------
 // Sensitivity state: rows 0..5 x 7 columns [x2..x6 | u0 u1]; row 6 (delta) is analytic: d delta / d delta = 1,
 // d delta / d u1 = t.  GPR: the GP mean / gradient of every RK4 stage come from gpr (written by gp_sweep_kernel).
-template <bool GPR>
+// IM: the linearisation goes to the instance-major records lin_im[k][i][LIM_STRIDE] = {M, b, q, r, x, u} that the
+// shared-memory-resident QP kernel pulls in with one TMA bulk copy per stage; otherwise to the SoA rows lin[k][58][Bp].
+template <bool GPR, bool IM>
+__device__ __forceinline__ void prepare_body(const Params &P, int i, int k, double *lin);
+
+#define LIM_PAD (LIM_STRIDE + 1)      // row stride of the staging tile: odd, so that a column of the tile hits 32 banks
+template <bool GPR, bool IM>
 __global__ void __launch_bounds__(128) prepare_kernel(const Params P)
 {
+    extern __shared__ __align__(16) double tile[];              // IM: [128][LIM_PAD] records of this CTA, written out coalesced
+    __shared__ int act[128];
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     const double h = o.dt;
-    if (!((i < P.B) && (P.lin_bad[i] != 2))) return;           // 2: finished instance of the full-SQP loop (sqp.cu)
+    const bool active = (i < P.B) && (P.lin_bad[i] != 2);      // 2: finished instance of the full-SQP loop (sqp.cu)
+    if (IM && k < N) {
+        act[threadIdx.x] = active ? 1 : 0;
+        if (active) prepare_body<GPR, IM>(P, i, k, tile + (size_t)threadIdx.x * LIM_PAD);
+        __syncthreads();
+        // the 128 records of this CTA are one contiguous block of lin_im[k]: coalesced 8-byte stores
+        double *dst = P.lin_im + ((size_t)k * Bp + (size_t)blockIdx.x * blockDim.x) * LIM_STRIDE;
+        const int nrec = min((int)blockDim.x, Bp - (int)(blockIdx.x * blockDim.x));
+        for (int e = threadIdx.x; e < nrec * LIM_STRIDE; e += blockDim.x) {
+            const int r = e / LIM_STRIDE, c = e - r * LIM_STRIDE;
+            if (act[r]) dst[e] = tile[(size_t)r * LIM_PAD + c];
+        }
+        return;
+    }
+    if (!active) return;
+    prepare_body<GPR, IM>(P, i, k, IM ? P.lin_im + ((size_t)k * Bp + i) * LIM_STRIDE : P.lin + (size_t)k * LIN_ROWS * Bp + i);
+}
+
+// body of one (instance, interval): `lin` is the record to fill (IM: LIM_* offsets, contiguous; else SoA rows, stride Bp)
+template <bool GPR, bool IM>
+__device__ __forceinline__ void prepare_body(const Params &P, int i, int k, double *lin)
+{
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp;
+    const double h = o.dt;
 
     double x[7], u[2], xn[7], yr[9];
     double pk = 0.0;
@@ -150,11 +158,16 @@ __global__ void __launch_bounds__(128) prepare_kernel(const Params P)
 #pragma unroll
         for (int c = 0; c < 7; c++) yr[c] = P.yref[(size_t)(N * 9 + c) * Bp + i];
     }
-    double *lin = P.lin + (size_t)k * LIN_ROWS * Bp + i;
+#define LIN_PUT(row, v) do { if (IM) lin[lim_of_row(row)] = (v); else lin[(size_t)(row) * Bp] = (v); } while (0)
+    if (IM) {            // linearisation point: the QP kernel forms bounds / the full step from it without touching HBM again
+#pragma unroll
+        for (int c = 0; c < 7; c++) lin[LIM_X + c] = x[c];
+        if (k < N) { lin[LIM_U] = u[0]; lin[LIM_U + 1] = u[1]; }
+    }
     if (k == N) {
         // terminal cost gradient, scaling 1
 #pragma unroll
-        for (int c = 0; c < 7; c++) lin[(size_t)(LIN_q + c) * Bp] = o.We[c] * (x[c] - yr[c]);
+        for (int c = 0; c < 7; c++) LIN_PUT(LIN_q + c, o.We[c] * (x[c] - yr[c]));
         return;
     }
     double gpx[7];
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(128) prepare_kernel(const Params P)
     for (int c = 0; c < 7; c++) {
         const double xp = fma(h, ax[c], x[c]);
         bad |= !isfinite(xp);
-        lin[(size_t)(LIN_b + c) * Bp] = xp - xn[c];
+        LIN_PUT(LIN_b + c, xp - xn[c]);
     }
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -237,28 +250,37 @@ __global__ void __launch_bounds__(128) prepare_kernel(const Params P)
         for (int c = 0; c < 5; c++) {
             const double v = h * acc[r][c] + ((r == 2 + c) ? 1.0 : 0.0);
             bad |= !isfinite(v);
-            lin[(size_t)(LIN_A + r * 5 + c) * Bp] = v;
+            LIN_PUT(LIN_A + r * 5 + c, v);
         }
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const double v = h * acc[r][5 + c];
             bad |= !isfinite(v);
-            lin[(size_t)(LIN_B + r * 2 + c) * Bp] = v;
+            LIN_PUT(LIN_B + r * 2 + c, v);
         }
     }
     const double Ts = o.dt;
 #pragma unroll
-    for (int c = 0; c < 7; c++) lin[(size_t)(LIN_q + c) * Bp] = Ts * o.W[c] * (x[c] - yr[c]);
+    for (int c = 0; c < 7; c++) LIN_PUT(LIN_q + c, Ts * o.W[c] * (x[c] - yr[c]));
 #pragma unroll
-    for (int c = 0; c < 2; c++) lin[(size_t)(LIN_r + c) * Bp] = Ts * o.W[7 + c] * (u[c] - yr[7 + c]);
+    for (int c = 0; c < 2; c++) LIN_PUT(LIN_r + c, Ts * o.W[7 + c] * (u[c] - yr[7 + c]));
     if (bad) P.lin_bad[i] = 1;
 }
 
 void launch_prepare(const Params &P, cudaStream_t s)
 {
     dim3 gridB((P.Bp + 127) / 128, P.o.N + 1);
+    const size_t tile_bytes = (size_t)128 * LIM_PAD * sizeof(double);       // 70.7 KB: needs the opt-in attribute
+    if (P.lin_im) {
+        static SmemGuard cfg;
+        if (cfg.need(tile_bytes)) {
+            cudaFuncSetAttribute(prepare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
+            cudaFuncSetAttribute(prepare_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
+        }
+    }
     if (!P.o.gp_enabled) {
-        prepare_kernel<false><<<gridB, 128, 0, s>>>(P);
+        if (P.lin_im) prepare_kernel<false, true><<<gridB, 128, tile_bytes, s>>>(P);
+        else prepare_kernel<false, false><<<gridB, 128, 0, s>>>(P);
         return;
     }
     // pass 1: the GP sweeps.  Register budget capped at 80 (24 warps/SM) for small models; models above 36 KB run
@@ -306,5 +328,6 @@ void launch_prepare(const Params &P, cudaStream_t s)
         else LAUNCH_GP(1024, 1, best);
     }
     // pass 2: RK4 + forward sensitivities with the stored GP terms
-    prepare_kernel<true><<<gridB, 128, 0, s>>>(P);
+    if (P.lin_im) prepare_kernel<true, true><<<gridB, 128, tile_bytes, s>>>(P);
+    else prepare_kernel<true, false><<<gridB, 128, 0, s>>>(P);
 }

@@ -24,40 +24,46 @@
 // orc_qp_solve), results differ by rounding only.  The corrector's barrier gradient is formed as predictor value + the
 // change caused by the complementarity right-hand side.
 #include "common.cuh"
+#include "tma.cuh"
 
 #define FULL 0xffffffffu
 #define ATS(arr, row) (arr)[(size_t)(row) * Bp + i]      // SoA interface arrays [row][Bp]
 
-// ---- node record (doubles).  7-vectors start at even offsets (16-byte loads), the odd slots between them hold scalars.
+// ---- node record (doubles).  The first LIM_STRIDE doubles are the instance-major linearisation record written by the
+// preparation kernel (common.cuh LIM_*), pulled in by ONE TMA bulk copy per stage.  7-vectors start at even offsets
+// (16-byte loads), the odd slots between them hold scalars.
 #define W_M 0       // 42  column c (0,1 = u0,u1 ; 2..6 = x2..x6) at c*6 + r, r < 6
-#define W_K0 42     // 7   first row of the gain K over the states x0..x6
-#define W_GI0 49    //     Guu^-1 (0,0)
-#define W_K1 50     // 7   second row
-#define W_GI1 57    //     Guu^-1 (0,1)
-#define W_RB 58     // 7   dynamics residual ; the corrector roll-out leaves ddx_{k+1} here
-#define W_GI2 65    //     Guu^-1 (1,1)
-#define W_PB 66     // 7   P_{k+1} rb_k ; the adjoint sweep leaves dpi_k here
-#define W_KF0 73    //     k_ff
-#define W_GX 74     // 7   rgx0..rgx5, qt6 ; the corrector roll-out leaves the adjoint base vector here
-#define W_KF1 81
-#define W_BAR 82    // 5   Rt0 Rt1 | rt0 rt1 | Qt6 ; the corrector roll-out leaves its ddu in rt0, rt1
-#define W_DD 87     // 3   affine ddu0 ddu1 ddx_k[6]
-#define W_DX 90     // 7   iterate: dx_k
-#define W_PI 97     // 7   iterate: pi_k   (dx, pi = 14 contiguous doubles from an even offset)
-#define W_LAM 104   // 10  iterate: lam
-#define W_T 114     // 10  iterate: t
-#define W_DU 124    // 2
-#define W_SL 126    // 2
-#define W_SU 128    // 2
-#define W_LB 130    // 7   b_k   (cold linearisation vectors: staged once, read once per IPM iteration)
-#define W_LQ 137    // 7   q_k
-#define W_LR 144    // 2   r_k
-#define W_RS 146    // record stride (even; 16-byte node-parallel accesses are conflict-free: 2*W_RS mod 32 = 4)
+#define W_LB 42     // 7   b_k   (b, q, r: 16 contiguous doubles, read once per IPM iteration)
+#define W_LQ 49     // 7   q_k
+#define W_LR 56     // 2   r_k
+#define W_XB 58     // 7   linearisation point x_k (bounds in delta form, full step of the epilogue)
+#define W_UB 65     // 2   linearisation point u_k
+#define W_K0 68     // 7   first row of the gain K over the states x0..x6
+#define W_GI0 75    //     Guu^-1 (0,0)
+#define W_K1 76     // 7   second row
+#define W_GI1 83    //     Guu^-1 (0,1)
+#define W_RB 84     // 7   dynamics residual ; the corrector roll-out leaves ddx_{k+1} here
+#define W_GI2 91    //     Guu^-1 (1,1)
+#define W_PB 92     // 7   P_{k+1} rb_k ; the adjoint sweep leaves dpi_k here
+#define W_KF0 99    //     k_ff
+#define W_GX 100    // 7   rgx0..rgx5, qt6 ; the corrector roll-out leaves the adjoint base vector here
+#define W_KF1 107
+#define W_BAR 108   // 5   Rt0 Rt1 | rt0 rt1 | Qt6 ; the corrector roll-out leaves its ddu in rt0, rt1
+#define W_DD 113    // 3   affine ddu0 ddu1 ddx_k[6]
+#define W_DX 116    // 7   iterate: dx_k
+#define W_PI 123    // 7   iterate: pi_k   (dx, pi = 14 contiguous doubles from an even offset)
+#define W_LAM 130   // 10  iterate: lam
+#define W_T 140     // 10  iterate: t
+#define W_DU 150    // 2
+#define W_SL 152    // 2
+#define W_SU 154    // 2
+#define W_RS 158    // record stride (even; 16-byte node-parallel accesses are conflict-free: 2*W_RS mod 32 = 28)
 // terminal record
 #define T_DX 0      // 7
 #define T_GX 8      // 7   r_x,N ; later We dx_N + r_x,N (adjoint start)
 #define T_LQ 16     // 7   q_N
-#define T_SIZE 24
+#define T_XB 24     // 7   x_N of the linearisation point
+#define T_SIZE 32
 // scratch of one instance.  Row stride 10 doubles (80 B): the four row pairs of a broadcast load fall on distinct banks.
 #define XS 10
 #define X_P 0       // 80  P_{k+1}, full symmetric, row a at a*XS (row 7 / column 7 padding) ; pads of rows 0, 1: the
@@ -111,8 +117,9 @@ struct NCon {
     double lam[NC], t[NC], sl[2], su[2], du[2], dx6;
     double lo[2], hi[2], lox, hix;
 };
-__device__ __forceinline__ void load_ncon(const admpc_opts &o, const double *st, double ub0, double ub1, double xb6, NCon &C)
+__device__ __forceinline__ void load_ncon(const admpc_opts &o, const double *st, NCon &C)
 {
+    const double ub0 = st[W_UB], ub1 = st[W_UB + 1], xb6 = st[W_XB + 6];
 #pragma unroll
     for (int c = 0; c < NC; c += 2) {
         const double2 l = ldv(st + W_LAM + c), t = ldv(st + W_T + c);
@@ -238,7 +245,10 @@ __device__ __forceinline__ void rw_factor(const admpc_opts &o, double *rec, doub
     const double *pr0 = xs + X_P + a0 * XS, *pr1 = xs + X_P + a1 * XS;
     double *wst = xs + X_W + c * XS + 2 * qd;
     const double *wld = xs + X_W + c * XS;
-    const int mo0 = W_M + 6 * a0, mo1 = W_M + 6 * a1;      // a1 = 7 (qd = 3) reads the first gain row: a padding entry
+    const int mo0 = W_M + 6 * a0, mo1 = W_M + 6 * a1;      // a1 = 7 (qd = 3) reads b_k: a padding entry
+    // broadcast pad holding (G[u0][a], G[u1][a]) of row a: the states x0, x1 in the pads of P, the M-columns 2..6 in the pads of W
+    const int roff0 = (a0 < 2) ? X_P + a0 * XS + 8 : X_W + a0 * XS + 8;
+    const int roff1 = (a1 < 2) ? X_P + a1 * XS + 8 : X_W + ((a1 < 7) ? a1 : 6) * XS + 8;
 
     // terminal: P_N = diag(We), p_N = r_x,N
     xs[X_P + l] = 0.0; xs[X_P + 32 + l] = 0.0;
@@ -285,25 +295,25 @@ __device__ __forceinline__ void rw_factor(const admpc_opts &o, double *rec, doub
         if (q0) stv(xs + X_W + c * XS + 8, fma(vm, rt.x, G0), fma(vm, rt.y, G1));      // vector column: g_u = rt + B^T h
         if (st_w01) { xs[X_P + 8 + c] = w01.x; xs[X_P + XS + 8 + c] = w01.y; }           // G[u_c][x0], G[u_c][x1]
         __syncwarp();
-        // ---- 5. 2x2 pivot, gains ------------------------------------------------------------------------------------------------
+        // ---- 5. 2x2 pivot, gains, Schur complement P_k(a, x_c) = base + G[u][a]^T K(:, c) ; vector column: p_k(a) ---------------
+        // (G[u][a] of this lane's two rows comes from the same broadcast pads as G[u][c]: no round trip through the gains)
         const double2 gA = ldv(xs + X_W + 8), gB = ldv(xs + X_W + XS + 8);           // G00 G10 | G01 G11
         const double2 gc = ldv(xs + goff);                                           // (G[u0][.], G[u1][.]) of this lane's column
+        const double2 ga0 = ldv(xs + roff0), ga1 = ldv(xs + roff1);                  // ... of this lane's two rows
+        const double2 gx = ldv(st + W_GX + a0);
         const double g00 = gA.x + o.reg, g01 = gA.y, g11 = gB.y + o.reg;
         const double idet = rcp_w(g00 * g11 - g01 * g01);
         const double gi00 = g11 * idet, gi01 = -g01 * idet, gi11 = g00 * idet;
         const double K0c = -(gi00 * gc.x + gi01 * gc.y), K1c = -(gi01 * gc.x + gi11 * gc.y);
         if (q0) { st[kidx0] = K0c; st[kidx1] = K1c; }
         if (st_gi) { st[W_GI0] = gi00; st[W_GI1] = gi01; st[W_GI2] = gi11; }
-        __syncwarp();
-        // ---- 6. Schur complement P_k(a, x_c) = base + K(:, a)^T G[u][x_c] ; vector column: p_k(a) --------------------------------
         {
-            const double2 k0 = ldv(st + W_K0 + a0), k1 = ldv(st + W_K1 + a0), gx = ldv(st + W_GX + a0);
             double b0 = useW ? w01.x : (useP ? pold0 + pd0 : G0);
             double b1 = useW ? w01.y : (useP ? pold1 + pd1 : G1);
             b0 = fma(vm, gx.x, b0);
             b1 = fma(vm, gx.y, b1);
-            const double v0 = fma(k1.x, gc.y, fma(k0.x, gc.x, b0));
-            const double v1 = fma(k1.y, gc.y, fma(k0.y, gc.x, b1));
+            const double v0 = fma(ga0.y, K1c, fma(ga0.x, K0c, b0));
+            const double v1 = fma(ga1.y, K1c, fma(ga1.x, K0c, b1));
             if (st_col) stv(xs + X_P + c * XS + a0, v0, v1);
             if (st_row) { xs[X_P + c] = v0; xs[X_P + XS + c] = v1; }
             pv0 = v0; pv1 = v1;
@@ -317,6 +327,11 @@ __device__ __forceinline__ void rw_factor(const admpc_opts &o, double *rec, doub
 #ifndef RW_VEC16
 #define RW_VEC16 1
 #endif
+#ifndef RW_UV
+#define RW_UV 2         // unroll factor of the horizon loops of the vector sweeps
+#endif
+#define RW_PRAGMA_(x) _Pragma(#x)
+#define RW_UNROLL(n) RW_PRAGMA_(unroll n)
 #if RW_VEC16
 #define VMASK 0x0000ffffu
 #define VEC_ONLY if (l < 16)
@@ -344,7 +359,7 @@ __device__ __forceinline__ void rw_backward_vec(const admpc_opts &o, double *rec
     double pown = term[T_GX + sx];                              // p_N = r_x,N
     double *st = rec + (size_t)(N - 1) * W_RS;
     VEC_ONLY
-#pragma unroll 2
+RW_UNROLL(RW_UV)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         double *hb = xs + X_HV + (k & 1) * 8;
         const double hown = st[W_PB + sx] + pown;
@@ -386,7 +401,7 @@ __device__ __forceinline__ void rw_forward(const admpc_opts &o, double *rec, dou
     double dxr = 0.0;
     double *st = rec;
     VEC_ONLY
-#pragma unroll 2
+RW_UNROLL(RW_UV)
     for (int k = 0; k < N; k++, st += W_RS) {
         const double *row = st + rbase;
         double *bx = xs + X_HV + (k & 1) * 8;
@@ -430,7 +445,7 @@ __device__ __forceinline__ void rw_adjoint(double *rec, double *term, double *xs
     double dpr = (l < 7) ? term[T_GX + l] : 0.0;             // dpi_{N-1} = We dx_N + r_x,N
     double *st = rec + (size_t)(N - 1) * W_RS;
     VEC_ONLY
-#pragma unroll 2
+RW_UNROLL(RW_UV)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         double *hb = xs + X_HV + (k & 1) * 8;
         if (l < 7) { st[W_PB + l] = dpr; hb[l] = dpr; }
@@ -474,48 +489,34 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
         return;
     }
 
-    // ---- stage the linearisation and the cold start ---------------------------------------------------------------------------
-    // M: entry w = cc*6 + r of a stage (cc < 2: B(r,cc), else A(r,cc-2)) on lane w and lane w - 32
-    {
-        const int w0 = l, w1 = (l + 32 < 42) ? l + 32 : 41;
-        const int c0 = w0 / 6, r0 = w0 - c0 * 6, c1 = w1 / 6, r1 = w1 - c1 * 6;
-        const int s0 = (c0 < 2) ? LIN_B + r0 * 2 + c0 : LIN_A + r0 * 5 + (c0 - 2);
-        const int s1 = (c1 < 2) ? LIN_B + r1 * 2 + c1 : LIN_A + r1 * 5 + (c1 - 2);
-        const double *g0 = P.lin + (size_t)s0 * Bp + i, *g1 = P.lin + (size_t)s1 * Bp + i;
-        const size_t gstep = (size_t)LIN_ROWS * Bp;
-        for (int k = 0; k < N; k++) {
-            const double v0 = g0[(size_t)k * gstep], v1 = g1[(size_t)k * gstep];
-            rec[(size_t)k * W_RS + W_M + w0] = v0;
-            if (l < 10) rec[(size_t)k * W_RS + W_M + w1] = v1;
-        }
+    // ---- stage the linearisation: one TMA bulk copy per stage record (M, b, q, r, x, u = 544 B), one mbarrier ---------------
+    __shared__ uint64_t bar;
+    if (l == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&bar, (uint32_t)(N * LIM_STRIDE * sizeof(double)));
     }
-    for (int k = l; k <= N; k += 32) {               // b_k, q_k, r_k of this lane's nodes
-        const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp;
-        double *st = rec + (size_t)k * W_RS;
-        if (k == N) {
-#pragma unroll
-            for (int a = 0; a < 7; a++) term[T_LQ + a] = ATS(lin, LIN_q + a);
-        } else {
-#pragma unroll
-            for (int a = 0; a < 7; a++) { st[W_LB + a] = ATS(lin, LIN_b + a); st[W_LQ + a] = ATS(lin, LIN_q + a); }
-            st[W_LR] = ATS(lin, LIN_r + 0); st[W_LR + 1] = ATS(lin, LIN_r + 1);
-        }
+    __syncwarp();
+    for (int k = l; k < N; k += 32)
+        tma_bulk_g2s(rec + (size_t)k * W_RS, P.lin_im + ((size_t)k * Bp + i) * LIM_STRIDE, LIM_STRIDE * sizeof(double), &bar);
+    if (l < 7) {                                     // terminal node: q_N and x_N only
+        const double *rn = P.lin_im + ((size_t)N * Bp + i) * LIM_STRIDE;
+        term[T_LQ + l] = rn[LIM_Q + l]; term[T_XB + l] = rn[LIM_X + l]; term[T_DX + l] = 0.0;
     }
-    double ub0[NS], ub1[NS], xb6[NS];                // linearisation point of this lane's nodes (bounds in delta form)
+    double x0v[7];
+#pragma unroll
+    for (int a = 0; a < 7; a++) x0v[a] = (l == 0) ? ATS(P.x0, a) : 0.0;
+    mbar_wait(&bar, 0);
+    // ---- cold start ------------------------------------------------------------------------------------------------------------
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         const int k = l + 32 * s;
-        ub0[s] = 0.0; ub1[s] = 0.0; xb6[s] = 0.0;
-        if (k == N) {
-#pragma unroll
-            for (int a = 0; a < 7; a++) term[T_DX + a] = 0.0;
-        }
         if (k >= N) continue;
         double *st = rec + (size_t)k * W_RS;
-        ub0[s] = ATS(P.ub, k * 2 + 0); ub1[s] = ATS(P.ub, k * 2 + 1); xb6[s] = ATS(P.xb, k * 7 + 6);
+        const double ub0 = st[W_UB], ub1 = st[W_UB + 1], xb6 = st[W_XB + 6];
         double dx[7];
 #pragma unroll
-        for (int a = 0; a < 7; a++) dx[a] = (k == 0) ? ATS(P.x0, a) - ATS(P.xb, a) : 0.0;     // x0 eliminated (nbxe_0 = 7)
+        for (int a = 0; a < 7; a++) dx[a] = (k == 0) ? x0v[a] - st[W_XB + a] : 0.0;     // x0 eliminated (nbxe_0 = 7)
         double du[2] = {0.0, 0.0}, lam[NC], t[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) { lam[c] = 0.0; t[c] = 1.0; }
@@ -523,8 +524,8 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
 #pragma unroll
         for (int jj = 0; jj < 3; jj++) {
             if (jj == 2 && k == 0) continue;
-            const double lo = (jj == 0) ? o.lbu[0] - ub0[s] : (jj == 1) ? o.lbu[1] - ub1[s] : o.lbx - xb6[s];
-            const double hi = (jj == 0) ? o.ubu[0] - ub0[s] : (jj == 1) ? o.ubu[1] - ub1[s] : o.ubx - xb6[s];
+            const double lo = (jj == 0) ? o.lbu[0] - ub0 : (jj == 1) ? o.lbu[1] - ub1 : o.lbx - xb6;
+            const double hi = (jj == 0) ? o.ubu[0] - ub0 : (jj == 1) ? o.ubu[1] - ub1 : o.ubx - xb6;
             double v = 0.0;
             if (v - lo < o.thr0) {
                 if (hi - v < o.thr0) v = 0.5 * (lo + hi);
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
                 lr[0] = v[14]; lr[1] = v[15];
             }
             NCon C;
-            load_ncon(o, st, ub0[s], ub1[s], xb6[s], C);
+            load_ncon(o, st, C);
             double pi[7], dx[7];
             {
                 double xp[14];
@@ -693,7 +694,7 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
             for (int c = 0; c < 3; c++) { fa[s][c] = 0.0; fb[s][c] = 0.0; }
             if (k >= N) continue;
             const double *st = rec + (size_t)k * W_RS;
-            NCon C; load_ncon(o, st, ub0[s], ub1[s], xb6[s], C);
+            NCon C; load_ncon(o, st, C);
             NRes R; node_res_w(o, k >= 1, C, R);
             NScal S; node_scal_w(o, C, S);
             double rm[NC];
@@ -752,7 +753,7 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
             const int k = l + 32 * s;
             if (k >= N) continue;
             const double *st = rec + (size_t)k * W_RS;
-            load_ncon(o, st, ub0[s], ub1[s], xb6[s], Cs[s]);
+            load_ncon(o, st, Cs[s]);
             NRes R; node_res_w(o, k >= 1, Cs[s], R);
             NScal S; node_scal_w(o, Cs[s], S);
             double rm[NC];
@@ -821,17 +822,18 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
     for (int k = l; k <= N; k += 32) {
         const double *st = rec + (size_t)k * W_RS;
         const double *dxs = (k < N) ? st + W_DX : term + T_DX;
+        const double *xbs = (k < N) ? st + W_XB : term + T_XB;       // linearisation point: came in with the stage record
         if (upd || P.gat_x) {
 #pragma unroll
             for (int a = 0; a < 7; a++) {
-                double v = ATS(P.xb, k * 7 + a);
+                double v = xbs[a];
                 if (upd) { v += dxs[a]; ATS(P.xb, k * 7 + a) = v; }
                 if (P.gat_x) P.gat_x[((size_t)i * (N + 1) + k) * 7 + a] = v;
             }
             if (k < N) {
 #pragma unroll
                 for (int jj = 0; jj < 2; jj++) {
-                    double v = ATS(P.ub, k * 2 + jj);
+                    double v = st[W_UB + jj];
                     if (upd) { v += st[W_DU + jj]; ATS(P.ub, k * 2 + jj) = v; }
                     if (P.gat_x) P.gat_u[((size_t)i * N + k) * 2 + jj] = v;
                 }
@@ -860,7 +862,7 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
 bool launch_qp_rw(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
-    if (N > 63) return false;
+    if (N > 63 || !P.lin_im) return false;
     const size_t sm = ((size_t)N * W_RS + T_SIZE + X_SIZE) * sizeof(double);
     if (N <= 31) {
         static SmemGuard configured;

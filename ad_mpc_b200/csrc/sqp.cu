@@ -32,7 +32,6 @@ __global__ void __launch_bounds__(128) nlp_res_kernel(const Params P, int it, do
 #pragma unroll
     for (int a = 0; a < 7; a++) { pim[a] = 0.0; nb = nmx(nb, fabs(ATS(P.x0, a) - ATS(P.xb, a))); }
     for (int k = 0; k < N; k++) {
-        const double *lin = P.lin + (size_t)k * LIN_ROWS * Bp;
         double pi[7], lam[NC], t[NC];
 #pragma unroll
         for (int a = 0; a < 7; a++) pi[a] = ATS(P.pib, k * 7 + a);
@@ -40,9 +39,9 @@ __global__ void __launch_bounds__(128) nlp_res_kernel(const Params P, int it, do
         for (int c = 0; c < NC; c++) { lam[c] = ATS(P.lamb, k * NC + c); t[c] = ATS(P.tb, k * NC + c); }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            double g = ATS(lin, LIN_r + j);
+            double g = lin_get(P, k, LIN_r + j, i);
 #pragma unroll
-            for (int r = 0; r < 6; r++) g += ATS(lin, LIN_B + r * 2 + j) * pi[r];
+            for (int r = 0; r < 6; r++) g += lin_get(P, k, LIN_B + r * 2 + j, i) * pi[r];
             if (j == 1) g += hdt * pi[6];
             g += -lam[j] + lam[3 + j];
             const double sl = ATS(P.slb, k * 2 + j), su = ATS(P.sub, k * 2 + j), u = ATS(P.ub, k * 2 + j);
@@ -61,7 +60,7 @@ __global__ void __launch_bounds__(128) nlp_res_kernel(const Params P, int it, do
             nd = nmx(nd, fabs(t[5] - ((o.ubx - x6) - 0.0)));
         }
 #pragma unroll
-        for (int a = 0; a < 7; a++) nb = nmx(nb, fabs(ATS(lin, LIN_b + a)));
+        for (int a = 0; a < 7; a++) nb = nmx(nb, fabs(lin_get(P, k, LIN_b + a, i)));
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             if ((c == 2 || c == 5) && k == 0) continue;
@@ -70,11 +69,11 @@ __global__ void __launch_bounds__(128) nlp_res_kernel(const Params P, int it, do
         if (k >= 1) {
 #pragma unroll
             for (int a = 0; a < 7; a++) {
-                double g = ATS(lin, LIN_q + a) - pim[a];
+                double g = lin_get(P, k, LIN_q + a, i) - pim[a];
                 if (a < 2) g += pi[a];
                 else {
 #pragma unroll
-                    for (int r = 0; r < 6; r++) g += ATS(lin, LIN_A + r * 5 + (a - 2)) * pi[r];
+                    for (int r = 0; r < 6; r++) g += lin_get(P, k, LIN_A + r * 5 + (a - 2), i) * pi[r];
                     if (a == 6) g += pi[6] - lam[2] + lam[5];
                 }
                 ng = nmx(ng, fabs(g));
@@ -84,9 +83,8 @@ __global__ void __launch_bounds__(128) nlp_res_kernel(const Params P, int it, do
         for (int a = 0; a < 7; a++) pim[a] = pi[a];
     }
     {
-        const double *lin = P.lin + (size_t)N * LIN_ROWS * Bp;
 #pragma unroll
-        for (int a = 0; a < 7; a++) ng = nmx(ng, fabs(ATS(lin, LIN_q + a) - pim[a]));
+        for (int a = 0; a < 7; a++) ng = nmx(ng, fabs(lin_get(P, N, LIN_q + a, i) - pim[a]));
     }
     ATS(P.nlp_res, 0) = ng; ATS(P.nlp_res, 1) = nb; ATS(P.nlp_res, 2) = nd; ATS(P.nlp_res, 3) = nm;
     if (ng < tol0 && nb < tol1 && nd < tol2 && nm < tol3) {

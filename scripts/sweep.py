@@ -4,10 +4,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ad_mpc_b200 import BatchSolver, default_opts, workload as wl
 
-def run(B, N, gpM, variant, p=1.0, reps=5):
+def run(B, N, gpM, variant, p=1.0, reps=5, **optkw):
     os.environ["ADMPC_QP_VARIANT"] = str(variant)
     batch = wl.make_batch(B, N, seed=1, p=p)
-    s = BatchSolver(B, default_opts(N))
+    s = BatchSolver(B, default_opts(N, **optkw))
     if gpM:
         s.set_gp(wl.make_gp(M=gpM, seed=2))
     s.set_profiling(True)
@@ -30,3 +30,6 @@ if __name__ == "__main__":
             run(B, 20, 0, v)
     run(16384, 20, 200, variants[-1])
     run(4096, 40, 2000, variants[-1], reps=2)
+    print("# opt-in FP32-exponent GP (gp_precision = 1)")
+    run(16384, 20, 200, variants[-1], gp_precision=1)
+    run(4096, 40, 2000, variants[-1], reps=2, gp_precision=1)

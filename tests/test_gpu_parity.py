@@ -570,6 +570,51 @@ def test_large_gp_model_parity(B, N, M):
     s.close()
 
 
+@pytest.mark.parametrize("M,N", [(200, 20), (2000, 40)])
+def test_gp_fp32_exponent_option_within_stated_bound(M, N):
+    """admpc_opts.gp_precision = 1 (opt-in): the RBF exponential runs on the FP32 special-function unit, everything else
+    stays FP64.  Stated bound: every kernel value is off by <= 2^-22 relative, so the GP mean is off by
+    <= 2^-22 * S, S = sum_i |sigma_f alpha_i k(z, X_i)| (no cancellation credit), and so are, to first order, the entries
+    of A, B, b (the GP term enters them times h-weighted O(1) factors).  Checked here: linearisation error <= 2 * 2^-22 * S
+    with S evaluated on the batch, statuses and QP iteration counts unchanged, solution within 10x that of the FP64
+    oracle.  The default (0) keeps the 1e-10 / 1e-8 bars."""
+    B = 32
+    batch = wl.make_batch(B, N, seed=5100 + M, p=1.0)
+    rng = np.random.default_rng(M + 1)
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([0.5, 0.1])
+    model = wl.make_gp(M=M, seed=10)
+    opts = default_opts(N, gp_precision=1)
+    o = mirror_opts(default_opts(N))
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    s = BatchSolver(B, opts)
+    s.set_gp(model)
+    g = _gpu_step(s, batch)
+    lin = s.get_lin()
+    worst = 0.0
+    for i in range(0, B, 4):
+        it = orc.make_iterate(o, batch["x_init"][i], batch["u_init"][i])
+        ref = orc.prepare(o, it, batch["yref"][i], batch["p"][i], gp=gp, gp_state=batch["x0"][i])
+        for key in ("A", "B", "b"):
+            worst = max(worst, mixed_err(lin[key][i], ref[key]))
+    # S on the batch: features = states 3..6 of the linearisation points
+    z = batch["x_init"][::4, :, 3:7].reshape(-1, 4)
+    S = 0.0
+    for j in range(model["X"].shape[0]):
+        d = (z[:, None, :] - model["X"][j][None, :, :]) / model["ell"][j]
+        kk = model["sigma_f"][j] * np.exp(-0.5 * (d * d).sum(axis=2))
+        S = max(S, float((np.abs(model["alpha"][j])[None, :] * kk).sum(axis=1).max()))
+    bound = 2.0 * 2.0 ** -22 * S
+    assert 1e-13 < worst <= bound, (worst, bound)  # really the reduced-precision path, and inside its bound
+    assert worst <= 2e-5                           # what the synthetic benchmark models actually show (errors do not add up coherently)
+    r = oracle_batch(o, batch, gp=gp)
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_iter"], r["qp_iter"])
+    eu = max(mixed_err(g["u"], r["u"]), mixed_err(g["x"], r["x"]))
+    assert eu <= 10 * bound, (eu, bound)
+    print("fp32-exponent GP, M=%d N=%d: S = %.3g, bound %.2e, max lin err %.2e, max solution err %.2e" % (M, N, S, bound, worst, eu))
+    s.close()
+
+
 def test_two_rank_gather_when_two_gpus():
     """Two ranks, two GPUs: the gathered blocks on the root equal the per-rank results for the NCCL send/recv path and for
     the fused peer-memory path (scripts/gather_check.py under torchrun).  Skipped on a one-GPU box."""
