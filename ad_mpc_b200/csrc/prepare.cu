@@ -106,8 +106,11 @@ template <bool GPR, bool IM>
 __device__ __forceinline__ void prepare_body(const Params &P, int i, int k, double *lin);
 
 #define LIM_PAD (LIM_STRIDE + 1)      // row stride of the staging tile: odd, so that a column of the tile hits 32 banks
+#ifndef PREP_MINB
+#define PREP_MINB 2
+#endif
 template <bool GPR, bool IM>
-__global__ void __launch_bounds__(128) prepare_kernel(const Params P)
+__global__ void __launch_bounds__(128, PREP_MINB) prepare_kernel(const Params P)
 {
     extern __shared__ __align__(16) double tile[];              // IM: [128][LIM_PAD] records of this CTA, written out coalesced
     __shared__ int act[128];
@@ -132,6 +135,22 @@ __global__ void __launch_bounds__(128) prepare_kernel(const Params P)
     }
     if (!active) return;
     prepare_body<GPR, IM>(P, i, k, IM ? P.lin_im + ((size_t)k * Bp + i) * LIM_STRIDE : P.lin + (size_t)k * LIN_ROWS * Bp + i);
+}
+
+// GP results of one RK4 stage (rows row0 .. row0 + R - 1 of gpr) of instance i
+__device__ __forceinline__ void gpr_load(const Params &P, const admpc_opts &o, int row0, int dz, int i, GpOut &G)
+{
+    const double *in = P.gpr + (size_t)row0 * P.Bp + i;
+#pragma unroll
+    for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
+        G.m[j] = 0.0;
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) G.g[j][d] = 0.0;
+        if (j >= o.gp_nout) continue;
+        G.m[j] = in[(size_t)(j * (1 + dz)) * P.Bp];
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G.g[j][d] = in[(size_t)(j * (1 + dz) + 1 + d) * P.Bp];
+    }
 }
 
 // body of one (instance, interval): `lin` is the record to fill (IM: LIM_* offsets, contiguous; else SoA rows, stride Bp)
@@ -186,6 +205,8 @@ __device__ __forceinline__ void prepare_body(const Params &P, int i, int k, doub
 #pragma unroll
     for (int c = 0; c < 7; c++) { kx[c] = 0.0; ax[c] = 0.0; }
 
+    GpOut Gn;
+    if (GPR) gpr_load(P, o, (k * 4) * R, dz, i, Gn);
 #pragma unroll 1
     for (int s = 0; s < 4; s++) {
         const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
@@ -197,18 +218,8 @@ __device__ __forceinline__ void prepare_body(const Params &P, int i, int k, doub
         Jac J;
         model_eval<false>(o, nullptr, 0, 0u, xs, u, pk, gpx, trig, f, J);
         if (GPR) {
-            GpOut G;
-            const double *in = P.gpr + (size_t)(k * 4 + s) * R * Bp + i;
-#pragma unroll
-            for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
-                G.m[j] = 0.0;
-#pragma unroll
-                for (int d = 0; d < ADMPC_DZMAX; d++) G.g[j][d] = 0.0;
-                if (j >= o.gp_nout) continue;
-                G.m[j] = in[(size_t)(j * (1 + dz)) * Bp];
-#pragma unroll
-                for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G.g[j][d] = in[(size_t)(j * (1 + dz) + 1 + d) * Bp];
-            }
+            const GpOut G = Gn;                      // loaded one stage ahead: its latency hides behind the model evaluation
+            if (s < 3) gpr_load(P, o, (k * 4 + s + 1) * R, dz, i, Gn);
             gp_apply(o, trig, G, f, J);
         }
 #pragma unroll

@@ -499,7 +499,7 @@ def run_ours(args):
             rate, secs, cores = cpu_oracle_rate(sample, reps=reps)
             # the other BASELINE.md 2 numbers: single-thread latency on cfg1, all-core throughput on cfg2 and cfg4
             l50, l99 = cpu_single_latency(50)
-            r2, s2, _ = cpu_oracle_rate(4096, gp=False, p=0.0)
+            r2, s2, _ = cpu_oracle_rate(4096, gp=False, p=0.0, reps=40)
             r4a, _, _ = cpu_oracle_rate(64, N=40, M=2000)                     # calibrate cfg4 (about 20x the work per solve)
             n4 = int(max(64, min(4096, 4.0 * r4a)))
             r4, s4, _ = cpu_oracle_rate(n4, N=40, M=2000)
@@ -508,7 +508,7 @@ def run_ours(args):
                    "build": _ORC_FLAGS,
                    "cfg1_single_thread_latency_ms": {"p50": l50, "p99": l99, "cores": 1,
                                                      "sample": "nominal N=20, B=1, 50 closed-loop RTI steps after 5 warm-up"},
-                   "cfg2_nominal_B4096": {"value": r2, "unit": "solves/s", "cores": cores, "sample": "4096 instances, %.2f s" % s2},
+                   "cfg2_nominal_B4096": {"value": r2, "unit": "solves/s", "cores": cores, "sample": "4096 instances x40, %.2f s" % s2},
                    "cfg4_gp2000_N40": {"value": r4, "unit": "solves/s", "cores": cores, "sample": "%d instances, %.2f s" % (n4, s4)},
                    "note": "CPU restatement of the acados path (oracle/); acados itself cannot be built here"}
         e2e_sorted = sorted(e2e_ms)

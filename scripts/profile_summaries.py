@@ -84,8 +84,10 @@ def kernels(src, dst, cmd):
             v, u = d[k]
             x = float(v.replace(",", ""))
             return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-        key = "prepare" if "prepare" in name else ("qp" if "qp_" in name else name)
+        key = "prepare_sens" if "prepare" in name else ("gp_sweep" if "gp_sweep" in name else ("qp" if "qp_" in name else name))
         traffic[key] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+    if "gp_sweep" in traffic or "prepare_sens" in traffic:          # the preparation phase = both of its kernels
+        traffic["prepare"] = traffic.get("gp_sweep", 0.0) + traffic.get("prepare_sens", 0.0)
     traffic["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, %s (profiles/%s)" % (cmd, os.path.basename(dst))
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     print(open(dst).read())
@@ -94,3 +96,6 @@ def kernels(src, dst, cmd):
 
 if __name__ == "__main__":
     {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    if len(sys.argv) > 5:            # round tag for the headers (default r01)
+        txt = open(sys.argv[3]).read().replace("# r01 ", "# %s " % sys.argv[5], 1)
+        open(sys.argv[3], "w").write(txt)
