@@ -60,6 +60,7 @@ SYMBOLS = {
     "admpc_batch_set_p": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_p_scalar": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_kappa": (C.c_int, [_vp, _dp]),
+    "admpc_batch_set_kappa_spline": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "admpc_batch_set_gp_state": (C.c_int, [_vp, _dp]),
     "admpc_batch_set_iterate": (C.c_int, [_vp, _dp, _dp]),
     "admpc_batch_set_duals": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),

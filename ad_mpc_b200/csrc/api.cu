@@ -111,6 +111,8 @@ struct admpc_batch {
     int *sqp_active_host = nullptr;  // pinned
     double *gp_blob = nullptr;
     size_t gp_blob_cap = 0;
+    double *kap_sp = nullptr;        // Frenet variant: spline curvature table
+    size_t kap_sp_cap = 0;
     double *gp_res = nullptr;        // per-stage GP results handed from gp_sweep_kernel to prepare_kernel
     size_t gp_res_cap = 0;
     double *l2_scratch = nullptr;
@@ -252,7 +254,7 @@ extern "C" int admpc_batch_free(admpc_batch *h)
     if (h->gpack_peer) cudaIpcCloseMemHandle(h->gpack_peer);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->pool); cudaFree(h->ipool); cudaFree(h->stage_in); cudaFree(h->stage_u); cudaFree(h->stage_x);
-    cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->gp_res); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack); cudaFree(h->bar_buf);
+    cudaFreeHost(h->sqp_active_host); cudaFree(h->stage_misc); cudaFree(h->stage_status); cudaFree(h->gp_blob); cudaFree(h->kap_sp); cudaFree(h->gp_res); cudaFree(h->l2_scratch); cudaFree(h->track); cudaFree(h->track_info); cudaFree(h->loop_prev_u); cudaFree(h->loop_i); cudaFree(h->pack); cudaFree(h->gpack); cudaFree(h->bar_buf);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->tm0) cudaEventDestroy(h->tm0);
     if (h->tm1) cudaEventDestroy(h->tm1);
@@ -450,6 +452,38 @@ extern "C" int admpc_batch_set_kappa(admpc_batch *h, const double *kappa)
     if (h->P.o.model_variant != 1) { admpc_set_error("admpc_batch_set_kappa", "handle was not created with model_variant = 1 (Frenet)"); return ADMPC_E_STATE; }
     return put_rows(h, kappa, (double *)h->P.kappa, h->P.o.N);
 }
+// Frenet variant: kappa(s) as a per-instance piecewise cubic (K pieces: breaks[B][K+1], coef[B][K][4], lowest power first),
+// evaluated inside the model at every RK4 sub-stage with its d kappa / d s Jacobian column -- the reference's
+// interpolant('kapparef_s', 'bspline', ...) semantics (fren_ad_3d_optimizer bytecode) for any spline brought to
+// piecewise-polynomial form.  K = 0 / NULL switches back to the per-node constants of admpc_batch_set_kappa.
+extern "C" int admpc_batch_set_kappa_spline(admpc_batch *h, int K, const double *breaks, const double *coef)
+{
+    if (!h) return ADMPC_E_ARG;
+    Params &P = h->P;
+    if (P.o.model_variant != 1) { admpc_set_error("admpc_batch_set_kappa_spline", "handle was not created with model_variant = 1 (Frenet)"); return ADMPC_E_STATE; }
+    if (K <= 0 || !breaks || !coef) { P.kap_K = 0; return 0; }
+    if (K > 64) { admpc_set_error("admpc_batch_set_kappa_spline", "at most 64 pieces"); return ADMPC_E_UNSUPPORTED; }
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    const size_t rows = (size_t)(K + 1) + 4 * (size_t)K, need = rows * P.Bp * sizeof(double);
+    if (need > h->kap_sp_cap) {
+        cudaFree(h->kap_sp);
+        h->kap_sp = nullptr; h->kap_sp_cap = 0; P.kap_K = 0; P.kap_sp = nullptr;
+        CUDA_CHECK_RET(cudaMalloc(&h->kap_sp, need));
+        h->kap_sp_cap = need;
+    }
+    // host [B][K+1] and [B][K*4] -> SoA rows, through the staging area in two transposes
+    double *tmp = nullptr;
+    CUDA_CHECK_RET(cudaMalloc(&tmp, (size_t)P.B * (4 * K) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(tmp, breaks, (size_t)P.B * (K + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) { launch_transpose_in(tmp, h->kap_sp, P.B, P.Bp, K + 1, h->stream); e = cudaStreamSynchronize(h->stream); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, coef, (size_t)P.B * 4 * K * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) { launch_transpose_in(tmp, h->kap_sp + (size_t)(K + 1) * P.Bp, P.B, P.Bp, 4 * K, h->stream); e = cudaStreamSynchronize(h->stream); }
+    cudaFree(tmp);
+    h->launches += 2;
+    if (e != cudaSuccess) { admpc_set_error("admpc_batch_set_kappa_spline", cudaGetErrorString(e)); return ADMPC_E_CUDA; }
+    P.kap_sp = h->kap_sp; P.kap_K = K;
+    return 0;
+}
 extern "C" int admpc_batch_set_p_scalar(admpc_batch *h, const double *p)
 {
     if (!h || !p) return ADMPC_E_ARG;
@@ -513,7 +547,8 @@ static int launch_feedback(admpc_batch *h)
     if (P.o.model_variant == 1) {
         // Frenet variant: warp-per-instance kernel on the 6x8 stage structure (N <= 63, fused update), else / on request
         // (ADMPC_QP_VARIANT=1) the dense thread-per-instance kernel + separate update
-        if (h->qp_variant != 1 && launch_qp_warp_f(P, h->stream)) {
+        // (a spline curvature makes the column of s dense: A(:,0) != e0, outside the structure qp_warp_f exploits)
+        if (h->qp_variant != 1 && P.kap_K == 0 && launch_qp_warp_f(P, h->stream)) {
             if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
             h->launches += 1;
             h->gat_fresh = h->gat_on;

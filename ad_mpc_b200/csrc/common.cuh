@@ -79,6 +79,8 @@ struct Params {
     // Frenet variant (frenet.cu): dense linearisation [k][DL_ROWS][Bp] (A 49, B 14, b 7, q 7, r 2), curvature [N][Bp]
     double *lin_d;
     const double *kappa;
+    const double *kap_sp;    // Frenet variant: kappa(s) as piecewise cubics [(K+1) breaks | K x 4 coefficients][Bp], kap_K pieces (0: off)
+    int kap_K;
     int *sqp_status, *sqp_iter;
     const int *gp_sel;   // [Bp] cluster model of every instance (GP ensemble; zeros for a single model)
     double *nlp_res;     // [4][Bp] NLP KKT residual norms of the last check

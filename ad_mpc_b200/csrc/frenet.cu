@@ -6,8 +6,12 @@
 //     s'     = (v_x cos e_psi - v_y sin e_psi) / (1 - e_y kappa)
 //     e_y'   =  v_x sin e_psi + v_y cos e_psi
 //     e_psi' =  r - e_y kappa s'                         (literal bytecode form, including the e_y*kappa factor)
-// The reference evaluates a B-spline kappa(s) inside the model (compiled with placeholder knots); here kappa is a
-// per-instance, per-shooting-node parameter (admpc_batch_set_kappa), i.e. d/ds = 0 inside one linearisation.
+// The reference evaluates a B-spline kappa(s) inside the model (compiled with placeholder knots).  Two forms here:
+//   * admpc_batch_set_kappa_spline: kappa(s) as a per-instance piecewise cubic evaluated at every RK4 sub-stage, with the
+//     d kappa / d s column in the Jacobian (the reference's semantics; A(:,0) is then dense, so the feedback phase runs the
+//     dense kernel below);
+//   * admpc_batch_set_kappa: a per-instance, per-shooting-node constant (d/ds = 0 inside one linearisation), which keeps
+//     the column of s trivial and lets the structured warp kernel qp_warp_f run.
 // With kappa = 0 the model IS the Cartesian one; tests pin this variant to the (reference-pinned) Cartesian path that
 // way.  The variant's own OCP (soft e_y bound, hard steering-rate bound) is not restated: the constraint set stays
 // the shipped one (both inputs soft, delta hard); weights / bounds / tyre factors are options.
@@ -32,7 +36,7 @@ __device__ __forceinline__ double nmaxd(double a, double b) { return (a > b || a
 // dense f, Jx (7x7), Ju (7x2) of the Frenet variant at (x, u); rows 3..6 (+ GP) from the shared model code
 template <bool GP>
 __device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *gpsm, int gp_stride, uint32_t tab, const double x[7],
-                                            const double u[2], double p, double kap, const double gpx[7], double trig,
+                                            const double u[2], double p, double kap, double dkap, const double gpx[7], double trig,
                                             double f[7], double Jx[7][7], double Ju[7][2])
 {
     Jac J;
@@ -63,6 +67,24 @@ __device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *g
     Jx[2][3] = -ey * kap * Jx[0][3];
     Jx[2][4] = -ey * kap * Jx[0][4];
     Jx[2][5] = 1.0;
+    // d / d s through kappa(s) (spline curvature evaluated inside the model); zero for a per-node constant
+    Jx[0][0] = sd0 * ey * dkap / den;
+    Jx[2][0] = -ey * dkap * sd0 - ey * kap * Jx[0][0];
+}
+
+// kappa(s) of instance i: piecewise cubic, SoA rows [breaks (K+1) | coef (K x 4, lowest power first)][Bp]; the end pieces
+// extrapolate.  The reference evaluates CasADi's interpolant('kapparef_s', 'bspline', ...) at this place.
+__device__ __forceinline__ void kappa_spline(const Params &P, int i, double s, double &kap, double &dkap)
+{
+    const int K = P.kap_K, Bp = P.Bp;
+    const double *sp = P.kap_sp + i;
+    int j = 0;
+    while (j + 1 < K && s >= sp[(size_t)(j + 1) * Bp]) j++;
+    const double t = s - sp[(size_t)j * Bp];
+    const double *c = sp + (size_t)(K + 1 + 4 * j) * Bp;
+    const double c0 = c[0], c1 = c[(size_t)Bp], c2 = c[(size_t)2 * Bp], c3 = c[(size_t)3 * Bp];
+    kap = ((c3 * t + c2) * t + c1) * t + c0;
+    dkap = (3.0 * c3 * t + 2.0 * c2) * t + c1;
 }
 
 __device__ __forceinline__ uint32_t fr_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,7 +139,8 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
     }
     double u[2], gpx[7];
     u[0] = AT(P.ub, k * 2 + 0); u[1] = AT(P.ub, k * 2 + 1);
-    const double pk = AT(P.p, k), kap = AT(P.kappa, k);
+    const double pk = AT(P.p, k);
+    double kap = AT(P.kappa, k), dkap = 0.0;
     const double trig = (GP && o.gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
 #pragma unroll
     for (int c = 0; c < 7; c++) gpx[c] = (trig != 0.0) ? AT(P.gps, c) : 0.0;
@@ -138,7 +161,8 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
         double xs[7], f[7], Jx[7][7], Ju[7][2];
 #pragma unroll
         for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
-        frenet_eval<GP>(o, gpm, P.gp.stride_out, tab, xs, u, pk, kap, gpx, trig, f, Jx, Ju);
+        if (P.kap_K > 0) kappa_spline(P, i, xs[0], kap, dkap);      // curvature at this sub-stage's own arc length
+        frenet_eval<GP>(o, gpm, P.gp.stride_out, tab, xs, u, pk, kap, dkap, gpx, trig, f, Jx, Ju);
 #pragma unroll
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
 #pragma unroll

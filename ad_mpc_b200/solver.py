@@ -49,6 +49,15 @@ def _f64(a, shape=None):
     return a
 
 
+def kappa_pp_from_knots(s_knots, curv):
+    """Piecewise-cubic form (breaks[K+1], coef[K,4] lowest power first) of the not-a-knot cubic spline through
+    (s_knots, curv) -- the degree-3 interpolating spline CasADi's interpolant(..., 'bspline', ...) builds from the same
+    data.  Host-side helper for BatchSolver.set_kappa_spline."""
+    from scipy.interpolate import CubicSpline
+    cs = CubicSpline(np.asarray(s_knots, dtype=np.float64), np.asarray(curv, dtype=np.float64), bc_type="not-a-knot")
+    return cs.x.copy(), np.ascontiguousarray(cs.c[::-1].T)
+
+
 class PinnedArray:
     """float64/int32 numpy view over cudaHostAlloc'ed memory (truly asynchronous H2D/D2H)."""
 
@@ -174,6 +183,19 @@ class BatchSolver:
         if k.size == self.B:
             k = np.repeat(k.reshape(self.B, 1), self.N, axis=1)
         check(self.L.admpc_batch_set_kappa(self.h, _dp(_f64(k, (self.B, self.N)))), "set_kappa")
+
+    def set_kappa_spline(self, breaks=None, coef=None):
+        """Frenet variant: kappa(s) as per-instance piecewise cubics, breaks[B,K+1] (or [K+1]), coef[B,K,4] (or [K,4]),
+        lowest power first -- evaluated inside the model with its d kappa / d s column (the reference's bspline
+        interpolant semantics).  None switches back to the per-node constants.  `kappa_pp_from_knots` builds the arrays."""
+        if breaks is None:
+            check(self.L.admpc_batch_set_kappa_spline(self.h, 0, None, None), "set_kappa_spline")
+            return
+        c = np.asarray(coef, dtype=np.float64)
+        K = c.shape[-2]
+        b = _f64(np.broadcast_to(np.asarray(breaks, dtype=np.float64), (self.B, K + 1)))
+        c = _f64(np.broadcast_to(c, (self.B, K, 4)))
+        check(self.L.admpc_batch_set_kappa_spline(self.h, K, _dp(b), _dp(c)), "set_kappa_spline")
 
     def set_gp_state(self, gp_state):
         check(self.L.admpc_batch_set_gp_state(self.h, None if gp_state is None else _dp(_f64(gp_state, (self.B, 7)))), "set_gp_state")

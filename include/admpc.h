@@ -156,6 +156,13 @@ int admpc_batch_set_p_scalar(admpc_batch *h, const double *p /*[B]*/);      /* s
  * coincides with the Cartesian model.  Kernels: csrc/frenet.cu (preparation) and csrc/qp_warp_f.cu (feedback), full SQP mode
  * included; the device reference generator and the closed-loop plant are Cartesian-only (ADMPC_E_UNSUPPORTED). */
 int admpc_batch_set_kappa(admpc_batch *h, const double *kappa);
+/* Frenet variant, the reference's own semantics: kappa(s) as a spline of the arc length evaluated INSIDE the model at every
+ * RK4 sub-stage, the Jacobian gaining its d kappa / d s column (bytecode: interpolant('kapparef_s', 'bspline', s_knots,
+ * curv)).  Any spline is passed in piecewise-polynomial form: K cubic pieces per instance, breaks[B][K+1], coef[B][K][4]
+ * with kappa(s) = c0 + c1 t + c2 t^2 + c3 t^3, t = s - breaks[j] (end pieces extrapolate); K <= 64.  K = 0 / NULL returns
+ * to the per-node constants.  With a spline the column of s in A_k is dense and the feedback phase runs the dense
+ * thread-per-instance kernel (qp_dense_kernel) instead of the structured warp kernel. */
+int admpc_batch_set_kappa_spline(admpc_batch *h, int K, const double *breaks, const double *coef);
 int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state /*[B][7] or NULL = x0*/);
 /* iterate (initial guess / warm start).  reset zeroes it like $G/acados_solver_sim_car.c:819-852. */
 int admpc_batch_set_iterate(admpc_batch *h, const double *x /*[B][(N+1)*7]*/, const double *u /*[B][N*2]*/);

@@ -107,6 +107,8 @@ def lib():
         L.orc_rti_step.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, dp, dp, C.POINTER(OrcIterate), C.POINTER(OrcStats)]
         L.orc_rti_batch.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, dp, ip, ip, ip, C.c_int]
         L.orc_set_kappa.argtypes = [C.c_double]
+        L.orc_set_kappa_spline.argtypes = [C.c_int, dp, dp]
+        L.orc_set_batch_kappa_spline.argtypes = [C.c_int, dp, dp]
         L.orc_rti_batch_frenet.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip,
                                            ip, C.c_int]
         L.orc_sqp_batch_frenet.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), C.c_int, dp, dp, dp, dp, dp, dp, dp, C.c_int, dp,
@@ -170,6 +172,33 @@ class Gp:
             o.gp_row[i] = r
         o.gp_stage0_trigger = stage0_trigger
         return o
+
+
+_spline_keep = []
+
+
+def set_kappa_spline(breaks=None, coef=None):
+    """Direct calls (model_jac / rk4_sens on this thread): kappa(s) = piecewise cubic, breaks[K+1], coef[K,4] (lowest power
+    first); None switches back to the per-node constant."""
+    global _spline_keep
+    if breaks is None:
+        lib().orc_set_kappa_spline(0, None, None)
+        _spline_keep = []
+        return
+    b = np.ascontiguousarray(breaks, dtype=np.float64); c = np.ascontiguousarray(coef, dtype=np.float64)
+    _spline_keep = [b, c]
+    lib().orc_set_kappa_spline(c.shape[0], _dp(b), _dp(c))
+
+
+def set_batch_kappa_spline(breaks=None, coef=None):
+    """Batch entry points (rti_batch / sqp_batch with the Frenet backend): per-instance splines breaks[B,K+1], coef[B,K,4]."""
+    global _spline_keep
+    if breaks is None:
+        lib().orc_set_batch_kappa_spline(0, None, None)
+        return
+    b = np.ascontiguousarray(breaks, dtype=np.float64); c = np.ascontiguousarray(coef, dtype=np.float64)
+    _spline_keep = [b, c]
+    lib().orc_set_batch_kappa_spline(c.shape[1], _dp(b), _dp(c))
 
 
 def model_jac(o, x, u, p, gp=None, gp_state=None, trigger=0.0, kappa=0.0):

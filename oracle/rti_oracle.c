@@ -113,6 +113,38 @@ void orc_gp_predict(const orc_opts *o, const orc_gp *gp, const double *z, double
  * preparation loop (the reference evaluates a B-spline kappa(s) inside the model). */
 static _Thread_local double tls_kappa = 0.0;
 void orc_set_kappa(double kappa) { tls_kappa = kappa; }
+/* kappa(s) as the reference has it: a spline of the arc length evaluated INSIDE the model (CasADi
+ * interpolant('kapparef_s', 'bspline', [s_knots], curv) in the bytecode), so that every RK4 sub-stage sees the
+ * curvature at its own s and the Jacobian gains a d kappa / d s column.  Any spline reaches this code in piecewise-
+ * polynomial form: K cubic pieces, breaks[K+1], coef[K][4] with kappa(s) = c0 + c1 t + c2 t^2 + c3 t^3, t = s - breaks[j];
+ * outside [breaks[0], breaks[K]] the end pieces extrapolate.  Thread-local (one instance per thread); the batch entry
+ * points install the instance's spline from the table set by orc_set_batch_kappa_spline. */
+static _Thread_local int tls_sp_K = 0;
+static _Thread_local const double *tls_sp_breaks = 0, *tls_sp_coef = 0;
+void orc_set_kappa_spline(int K, const double *breaks, const double *coef)
+{
+    tls_sp_K = (breaks && coef) ? K : 0; tls_sp_breaks = breaks; tls_sp_coef = coef;
+}
+static int g_sp_K = 0;
+static const double *g_sp_breaks = 0, *g_sp_coef = 0;          /* [B][K+1], [B][K][4] */
+void orc_set_batch_kappa_spline(int K, const double *breaks, const double *coef)
+{
+    g_sp_K = (breaks && coef) ? K : 0; g_sp_breaks = breaks; g_sp_coef = coef;
+}
+static void batch_spline_install(int b)
+{
+    if (g_sp_K > 0) orc_set_kappa_spline(g_sp_K, g_sp_breaks + (size_t)b * (g_sp_K + 1), g_sp_coef + (size_t)b * g_sp_K * 4);
+    else orc_set_kappa_spline(0, 0, 0);
+}
+static void kappa_eval(double s, double *kap, double *dkap)
+{
+    if (tls_sp_K <= 0) { *kap = tls_kappa; *dkap = 0.0; return; }
+    int j = 0;
+    while (j + 1 < tls_sp_K && s >= tls_sp_breaks[j + 1]) j++;
+    const double t = s - tls_sp_breaks[j], *c = tls_sp_coef + 4 * j;
+    *kap = ((c[3] * t + c[2]) * t + c[1]) * t + c[0];
+    *dkap = (3.0 * c[3] * t + 2.0 * c[2]) * t + c[1];
+}
 
 void orc_model_jac(const orc_opts *o, const orc_gp *gp, const double *x, const double *u, double p,
                    const double *gp_state, double trigger, double *f, double *Jx, double *Ju)
@@ -166,7 +198,9 @@ void orc_model_jac(const orc_opts *o, const orc_gp *gp, const double *x, const d
          *   s'     = (vx cos e_psi - vy sin e_psi) / (1 - e_y kappa)
          *   e_y'   =  vx sin e_psi + vy cos e_psi
          *   e_psi' =  r - e_y kappa s'                                                             */
-        const double kap = tls_kappa, ey = x[1];
+        double kap, dkap;
+        kappa_eval(x[0], &kap, &dkap);
+        const double ey = x[1];
         const double vt = vx * cp - vy * sp, vn = vx * sp + vy * cp, den = 1.0 - ey * kap;
         const double sd0 = vt / den;
         f[0] = sd0; f[1] = vn; f[2] = r - ey * kap * sd0;
@@ -178,6 +212,9 @@ void orc_model_jac(const orc_opts *o, const orc_gp *gp, const double *x, const d
         JX(2, 3) = -ey * kap * JX(0, 3);
         JX(2, 4) = -ey * kap * JX(0, 4);
         JX(2, 5) = 1.0;
+        /* d / d s through kappa(s): zero for a per-node constant curvature */
+        JX(0, 0) = sd0 * ey * dkap / den;
+        JX(2, 0) = -ey * dkap * sd0 - ey * kap * JX(0, 0);
     }
     if (o->gp_enabled && gp) {
         /* gp_x = gp_state*trigger + x*(1-trigger)   quad_3d_optimizer.py:295 ; z = B_z [x;u]  gp.py:609-630 */
@@ -794,6 +831,7 @@ int orc_sqp_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const doubl
             memcpy(it->u, uit + (size_t)b * N * 2, sizeof(double) * N * 2);
             int si = 0;
             double r4[4];
+            batch_spline_install(b);
             int stt = sqp_solve_impl(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N, kappa ? kappa + (size_t)b * N : 0,
                                      gp_state ? gp_state + (size_t)b * 7 : 0, it, max_iter, tol, &si, r4);
             memcpy(xit + (size_t)b * (N + 1) * 7, it->x, sizeof(double) * (N + 1) * 7);
@@ -835,6 +873,7 @@ int orc_rti_batch_frenet(const orc_opts *o, const orc_gp *gp, int B, const doubl
             memcpy(it->x, xit + (size_t)b * (N + 1) * 7, sizeof(double) * (N + 1) * 7);
             memcpy(it->u, uit + (size_t)b * N * 2, sizeof(double) * N * 2);
             orc_stats st;
+            batch_spline_install(b);
             rti_step_impl(o, gp, x0 + (size_t)b * 7, yref + b * ny, p + (size_t)b * N, kappa ? kappa + (size_t)b * N : 0,
                           gp_state ? gp_state + (size_t)b * 7 : 0, it, &st);
             memcpy(xit + (size_t)b * (N + 1) * 7, it->x, sizeof(double) * (N + 1) * 7);

@@ -139,6 +139,10 @@ int orc_sqp_batch(const orc_opts *o, const orc_gp *gp, int B, const double *x0, 
 
 /* Frenet variant (model_backend = 2): kappa[N] per instance = path curvature at every shooting node */
 void orc_set_kappa(double kappa);      /* for direct orc_model_jac / orc_rk4_sens calls (thread-local) */
+/* kappa(s) as a piecewise cubic (K pieces, breaks[K+1], coef[K][4], lowest power first) evaluated inside the model at every
+ * RK4 sub-stage, with its d kappa / d s Jacobian column; NULL / K = 0 switches back to the per-node constant */
+void orc_set_kappa_spline(int K, const double *breaks, const double *coef);            /* thread-local, direct calls */
+void orc_set_batch_kappa_spline(int K, const double *breaks, const double *coef);      /* [B][K+1], [B][K][4]: batch entry points */
 int orc_prepare_frenet(const orc_opts *o, const orc_gp *gp, const orc_iterate *it, const double *yref,
                        const double *p, const double *kappa, const double *gp_state, orc_lin *lin);
 int orc_rti_step_frenet(const orc_opts *o, const orc_gp *gp, const double *x0, const double *yref,

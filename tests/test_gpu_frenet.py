@@ -188,3 +188,56 @@ def test_frenet_through_the_pipelined_host_call():
     g = _step(s, batch, kappa=batch["kappa"])
     assert np.array_equal(st, g["status"]) and np.array_equal(u, g["u"]) and np.array_equal(x, g["x"])
     ps.close(); s.close()
+
+
+def _spline_batch(B, N, seed):
+    """Curvature that really varies along the horizon: kappa(s) = 0.02 + 0.012 sin(s / 9 + phase_i), sampled at knots
+    every 4 m around each vehicle and turned into the not-a-knot cubic the reference's bspline interpolant builds."""
+    from ad_mpc_b200 import kappa_pp_from_knots
+    batch = wl.make_batch_frenet(B, N, seed=seed, p=1.0, perturb=2.0)
+    rng = np.random.default_rng(seed + 1)
+    phase = rng.uniform(0, 6.28, size=B)
+    K = 12
+    breaks, coef = np.zeros((B, K + 1)), np.zeros((B, K, 4))
+    for i in range(B):
+        kn = batch["x0"][i, 0] - 6.0 + 4.0 * np.arange(K + 1)
+        breaks[i], coef[i] = kappa_pp_from_knots(kn, 0.02 + 0.012 * np.sin(kn / 9.0 + phase[i]))
+    return batch, breaks, coef
+
+
+@pytest.mark.parametrize("B,N", [(48, 20), (20, 40)])
+def test_frenet_spline_curvature_inside_the_model(B, N):
+    """kappa(s) as a spline evaluated inside the model at every RK4 sub-stage, with the d kappa / d s column of the
+    Jacobian (the reference's bspline-interpolant semantics): linearisation and RTI step against the oracle."""
+    batch, breaks, coef = _spline_batch(B, N, 420 + N)
+    opts = default_opts(N, model_variant=1)
+    o = mirror_opts(opts)
+    s = BatchSolver(B, opts)
+    s.set_kappa_spline(breaks, coef)
+    g = _step(s, batch)
+    orc.set_batch_kappa_spline(breaks, coef)
+    try:
+        r = orc.rti_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=np.zeros((B, N)))
+    finally:
+        orc.set_batch_kappa_spline(None)
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_iter"], r["qp_iter"])
+    assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL
+    # the column of s is really there: the same spline frozen at the nodes (d kappa / d s dropped) gives another answer
+    kap_nodes = np.zeros((B, N))
+    for i in range(B):
+        for k in range(N):
+            sk = batch["x_init"][i, k, 0]
+            j = int(np.clip(np.searchsorted(breaks[i], sk, side="right") - 1, 0, coef.shape[1] - 1))
+            t = sk - breaks[i, j]
+            kap_nodes[i, k] = coef[i, j] @ np.array([1.0, t, t * t, t ** 3])
+    s.set_kappa_spline(None)
+    g2 = _step(s, batch, kappa=kap_nodes)
+    assert mixed_err(g2["u"], g["u"]) > 1e-7
+    # constant spline == per-node constant (both Jacobian forms coincide)
+    cb = np.tile(np.array([-1e3, 1e3]), (B, 1)); cc = np.zeros((B, 1, 4)); cc[:, 0, 0] = 0.02
+    s.set_kappa_spline(cb, cc)
+    g3 = _step(s, batch)
+    s.set_kappa_spline(None)
+    g4 = _step(s, batch, kappa=np.full((B, N), 0.02))
+    assert np.array_equal(g3["qp_iter"], g4["qp_iter"]) and mixed_err(g3["u"], g4["u"]) <= TOL
+    s.close()

@@ -215,3 +215,34 @@ def test_frenet_variant_oracle_consistency():
     rf = orc.rti_batch(of, bf["x0"], bf["yref"], bf["p"], bf["x_init"], bf["u_init"], kappa=bf["kappa"])
     assert (rf["status"] == 0).all() and (rf["qp_status"] == 0).all()
     assert np.abs(rf["x"][:, -1, 1]).mean() < np.abs(bf["x0"][:, 1]).mean()
+
+
+def test_frenet_spline_curvature_jacobian_matches_finite_differences():
+    """Frenet backend with kappa(s) evaluated inside the model: the analytic Jacobian (including the d kappa / d s column)
+    against central differences of f, and the RK4 sensitivities against differences of the RK4 map."""
+    o = orc.default_opts(N=20)
+    o.model_backend = 2
+    kn = np.linspace(-5.0, 45.0, 11)
+    from scipy.interpolate import CubicSpline
+    cs = CubicSpline(kn, 0.03 * np.sin(kn / 7.0) + 0.01, bc_type="not-a-knot")
+    breaks, coef = cs.x.copy(), np.ascontiguousarray(cs.c[::-1].T)
+    orc.set_kappa_spline(breaks, coef)
+    try:
+        rng = np.random.default_rng(3)
+        for _ in range(20):
+            x = np.array([rng.uniform(0, 40), rng.normal() * 0.5, rng.normal() * 0.1, 8 + rng.normal(), rng.normal() * 0.3,
+                          rng.normal() * 0.2, rng.normal() * 0.1])
+            u = rng.normal(size=2) * np.array([1.0, 0.2])
+            f, Jx, Ju = orc.model_jac(o, x, u, 1.0)
+            assert abs(Jx[0, 0]) > 1e-6          # the column is live
+            for j in range(7):
+                e = np.zeros(7); e[j] = 1e-6
+                fp = orc.model_jac(o, x + e, u, 1.0)[0]; fm = orc.model_jac(o, x - e, u, 1.0)[0]
+                assert np.abs((fp - fm) / 2e-6 - Jx[:, j]).max() < 1e-6 * max(1.0, np.abs(Jx[:, j]).max())
+            A = orc.rk4_sens(o, x, u, 1.0)[1]
+            for j in range(7):
+                e = np.zeros(7); e[j] = 1e-6
+                d = (orc.rk4_sens(o, x + e, u, 1.0)[0] - orc.rk4_sens(o, x - e, u, 1.0)[0]) / 2e-6
+                assert np.abs(d - A[:, j]).max() < 1e-6
+    finally:
+        orc.set_kappa_spline(None)
