@@ -96,6 +96,22 @@ __device__ __forceinline__ double lin_get(const Params &P, int k, int row, int i
     return P.lin_im ? P.lin_im[((size_t)k * P.Bp + i) * LIM_STRIDE + lim_of_row(row)] : P.lin[((size_t)k * LIN_ROWS + row) * P.Bp + i];
 }
 
+// -DADMPC_DEBUG: device-side bounds asserts on the SoA / record indexing (compute-sanitizer is closed on the GPU pool, this
+// build is its substitute; scripts/debug_build.sh, the parity suite runs under it with ADMPC_LIB=...).  A failed assert
+// prints file:line and traps, which the host sees as a CUDA error on the next synchronisation.
+#ifdef ADMPC_DEBUG
+#include <stdio.h>
+#define ADMPC_ASSERT(c) do { if (!(c)) { printf("ADMPC_ASSERT failed %s:%d: %s\n", __FILE__, __LINE__, #c); __trap(); } } while (0)
+#else
+#define ADMPC_ASSERT(c) ((void)0)
+#endif
+// checked element of an SoA interface array [rows][Bp]: row within the array's row count, instance within the padded batch
+__device__ __forceinline__ size_t soa_at(int row, int rows, int i, int Bp)
+{
+    ADMPC_ASSERT(row >= 0 && row < rows && i >= 0 && i < Bp);
+    return (size_t)row * Bp + i;
+}
+
 #define CUDA_CHECK_RET(call)                                                         \
     do {                                                                             \
         cudaError_t e_ = (call);                                                     \

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gp_sweep_kernel(const Params P)
         const double pk = P.p[(size_t)k * Bp + i];
         GpOut G;
         gp_eval<PREC>(o, gpm, P.gp.stride_out, tab, xs, u, gpx, trig, G);
+        ADMPC_ASSERT(k < o.N && soa_at((k * 4 + s) * R + R - 1, o.N * 4 * R, i, Bp) < (size_t)o.N * 4 * R * Bp);
         double *out = P.gpr + (size_t)(k * 4 + s) * R * Bp + i;
 #pragma unroll
         for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(128, PREP_MINB) prepare_kernel(const Params P)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     const double h = o.dt;
+    ADMPC_ASSERT(k <= N);                                     // (threads past the batch are masked by `active` below)
     const bool active = (i < P.B) && (P.lin_bad[i] != 2);      // 2: finished instance of the full-SQP loop (sqp.cu)
     if (IM && k < N) {
         act[threadIdx.x] = active ? 1 : 0;

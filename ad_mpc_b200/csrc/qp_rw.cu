@@ -259,6 +259,7 @@ __device__ __forceinline__ void rw_factor(const admpc_opts &o, double *rec, doub
     __syncwarp();
     double *st = rec + (size_t)(N - 1) * W_RS;
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
+        ADMPC_ASSERT(st == rec + (size_t)k * W_RS && st + mo1 + 5 < rec + (size_t)N * W_RS + T_SIZE + X_SIZE);
         // ---- 1. W(a, c) = P(a, :) col_c for the two rows of this lane ----------------------------------------------------
         const double2 c01 = ldv(st + colOff), c23 = ldv(st + colOff + 2), c45 = ldv(st + colOff + 4);
         const double rb6 = st[W_RB + 6];
@@ -476,6 +477,15 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
     double *term = rec + (size_t)N * W_RS;
     double *xs = term + T_SIZE;
     const double Ts = o.dt, hdt = o.dt;
+#ifdef ADMPC_DEBUG
+    {
+        unsigned dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        ADMPC_ASSERT((size_t)dyn >= ((size_t)N * W_RS + T_SIZE + X_SIZE) * sizeof(double));
+        ADMPC_ASSERT(i < P.B && N >= 2 && N <= 32 * NS - 1 && P.lin_im != nullptr);
+        ADMPC_ASSERT((((size_t)(P.lin_im + ((size_t)0 * Bp + i) * LIM_STRIDE)) & 15) == 0);
+    }
+#endif
     const int flag = P.lin_bad[i];                   // 1: NaN/Inf in the linearisation ; 2: finished instance of the SQP loop
     if (flag) {
         if (l == 0 && flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
@@ -820,6 +830,7 @@ __global__ void __launch_bounds__(32, (NS == 1) ? RW_MINB : 5) qp_rw_kernel(cons
     }
     const bool upd = (nlp_status == 0);
     for (int k = l; k <= N; k += 32) {
+        ADMPC_ASSERT(k >= 0 && k <= N && soa_at(k * 7 + 6, (N + 1) * 7, i, Bp) < (size_t)(N + 1) * 7 * Bp);
         const double *st = rec + (size_t)k * W_RS;
         const double *dxs = (k < N) ? st + W_DX : term + T_DX;
         const double *xbs = (k < N) ? st + W_XB : term + T_XB;       // linearisation point: came in with the stage record

@@ -15,7 +15,7 @@ for f in $FILES; do
   OBJS="$OBJS variants/$NAME.$b.o"
   EXCL="$EXCL|csrc/$b.o"
 done
-REST=$(ls csrc/*.o | grep -v -E "^(${EXCL:1})$")
+REST=$(ls csrc/*.o | grep -v -E "^(${EXCL:1})$" || true)
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -o variants/$NAME.so $REST $OBJS -ldl
 grep -h "registers\|spill" variants/$NAME.*.log | paste - - | sed 's/ptxas info    ://g' | head -4
 echo variants/$NAME.so
