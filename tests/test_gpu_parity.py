@@ -391,19 +391,19 @@ def test_two_warp_kernel_matches_octet_kernel(monkeypatch):
 
 
 def test_qp_variants_agree(monkeypatch):
-    """The four QP kernels are independent implementations of the same algorithm: identical statuses / iteration
-    counts and 1e-8 agreement on a batch with active bounds."""
+    """The five QP kernels are independent implementations of the same algorithm: identical statuses / iteration
+    counts and 1e-8 agreement on a batch with active bounds (7 = tensor-core sweeps, the default; 6 = its hand-distributed twin)."""
     B, N = 128, 20
     batch = wl.make_batch(B, N, seed=77, p=0.5, perturb=5.0)
     out = {}
-    for v in (1, 3, 4, 6):
+    for v in (1, 3, 4, 6, 7):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, default_opts(N))
         out[v] = _gpu_step(s, batch)
         s.close()
-    for v in (1, 3, 4):
-        assert np.array_equal(out[v]["qp_iter"], out[6]["qp_iter"]) and np.array_equal(out[v]["status"], out[6]["status"])
-        assert mixed_err(out[v]["u"], out[6]["u"]) <= TOL and mixed_err(out[v]["x"], out[6]["x"]) <= TOL
+    for v in (1, 3, 4, 6):
+        assert np.array_equal(out[v]["qp_iter"], out[7]["qp_iter"]) and np.array_equal(out[v]["status"], out[7]["status"]), v
+        assert mixed_err(out[v]["u"], out[7]["u"]) <= TOL and mixed_err(out[v]["x"], out[7]["x"]) <= TOL, v
 
 
 def test_non_default_weights_and_quadratic_slack_penalty():
@@ -506,7 +506,7 @@ def test_sqp_mode_with_gp_and_other_qp_kernels(monkeypatch):
     gp = orc.Gp(model)
     gp.apply(o, feat=model["feat"], rows=model["rows"])
     r = orc.sqp_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=gp, gp_state=batch["x0"])
-    for v in (6, 4, 3, 1):
+    for v in (7, 6, 4, 3, 1):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, opts)
         s.set_gp(model)
