@@ -82,6 +82,20 @@ __device__ __forceinline__ void mm8(double &d0, double &d1, double ax, double ay
     dmma(d0, d1, ay, by, e0, e1);
 }
 __device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(FULL, v, src); }
+// reciprocal of the pivot's determinant.  MMA_RCP1 = 1: one Newton step on the hardware seed (A/B switch, see profiles)
+#ifndef MMA_RCP1
+#define MMA_RCP1 0
+#endif
+__device__ __forceinline__ double rcp_piv(double x)
+{
+#if MMA_RCP1
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+#else
+    return rcp_w(x);
+#endif
+}
 
 // ---- operand fragments of one stage, straight from the column-major 6x7 block M = [B | A(:,2:7)] of the record ---------------
 // cl(Mh^T): lane (g, t) holds Mh[2t][g], Mh[2t+1][g] ; Mh = [[M7, rb], [0, 1]], M7 = M with the delta row (0, dt, 0, .., 0, 1)
@@ -143,7 +157,7 @@ __device__ __forceinline__ void mma_factor(const admpc_opts &o, double *rec, con
     const int g = l >> 2, t = l & 3;
     const double Ts = o.dt, hdt = o.dt;
     const MtFrag mf(g, t, hdt);
-    const bool g7 = (g == 7), t0 = (t == 0), t3 = (t == 3), glow = (g < 2);
+    const bool g7 = (g == 7), g0 = (g == 0), t0 = (t == 0), t3 = (t == 3), glow = (g < 2);
     // H[g][2t..2t+1] = base + add.  base: own P (states x0, x1 among themselves), W handed over by the lanes (2t, 0), (2t+1, 0)
     // (rows x0, x1), own W (columns x0, x1), own G (the rest).  add: diagonal weights, gradient on the vector row / column.
     const bool catA = glow && t0, catB = glow && !t0, catD = !glow && !t0;
@@ -157,6 +171,7 @@ __device__ __forceinline__ void mma_factor(const admpc_opts &o, double *rec, con
     // G[u][.] on the lanes t = 0: the input rows of G (states x2.., vector column), W[a][u] for the states x0, x1
     const double dmU = glow ? 0.0 : 1.0, mrt = g7 ? 1.0 : 0.0;
     const int src0 = l & ~3;                                       // lane (g, 0)
+    const bool tlow = (t < 2);
     const int kst = W_K0 + 8 * (t & 1) + g;
     const double reg = o.reg;
     // terminal: P_N = diag(We), p_N = r_x,N
@@ -189,13 +204,18 @@ __device__ __forceinline__ void mma_factor(const admpc_opts &o, double *rec, con
         double Gx, Gy;
         mm8(Gx, Gy, mx, my, wx, wy, 0.0, 0.0);
         // (meanwhile, from W alone)  P rb for the corrector ; rows / columns of the states x0, x1: G[u][x_a] = W[a][u], H[x_a][c] = W[a][c]
-        if (g7) stv(sw + W_PB + 2 * t, wx - px, wy - py);
-        const double rcv = __shfl_xor_sync(FULL, (g == 0) ? wy : wx, 4);
-        const double upx = glow ? ((g == 0) ? wx : rcv) : ur0, upy = glow ? ((g == 0) ? rcv : wy) : ur1;
-        const double sx = wx + addx, sy = wy + addy;
+        const double pbx = wx - px, pby = wy - py;
+        if (g7) stv(sw + W_PB + 2 * t, pbx, pby);
+        const double rcv = __shfl_xor_sync(FULL, g0 ? wy : wx, 4);
+        const double ua = g0 ? wx : rcv, ub = g0 ? rcv : wy;
+        const double upx = glow ? ua : ur0, upy = glow ? ub : ur1;
+        const double sx = wx + addx, sy = wy + addy, pax = px + addx, pay = py + addy;
         const double r0x = shf(sx, 8 * t), r1x = shf(sx, 8 * t + 4), r0y = shf(sy, 8 * t), r1y = shf(sy, 8 * t + 4);
-        const double hpx = catD ? addx : (catA ? px + addx : (catB ? ((g == 0) ? r0x : r0y) : sx));
-        const double hpy = catD ? addy : (catA ? py + addy : (catB ? ((g == 0) ? r1x : r1y) : sy));
+        // (flat selects on values computed for every lane: no divergent code inside the sweep)
+        const double rbx = g0 ? r0x : r0y, rby = g0 ? r1x : r1y;
+        double hpx = catB ? rbx : sx, hpy = catB ? rby : sy;
+        hpx = catA ? pax : hpx; hpy = catA ? pay : hpy;
+        hpx = catD ? addx : hpx; hpy = catD ? addy : hpy;
         // next stage's operands
         const double *sn = (k > 0) ? st - W_RS : st;
         mf.load(sn, mx, my);
@@ -204,16 +224,18 @@ __device__ __forceinline__ void mma_factor(const admpc_opts &o, double *rec, con
         // ---- 3. 2x2 pivot -------------------------------------------------------------------------------------------------------------
         const double g00 = shf(Gx, 0) + r00, g01 = shf(Gy, 0), g11 = shf(Gy, 4) + r11;
         const double gu0 = shf(fma(dmU, Gx, upx), src0), gu1 = shf(fma(dmU, Gy, upy), src0);
-        const double kt = t0 ? fma(g11, gu0, -g01 * gu1) : fma(g00, gu1, -g01 * gu0);      // rows of adj(Guu) Gu
+        const double kta = fma(g11, gu0, -g01 * gu1), ktb = fma(g00, gu1, -g01 * gu0);      // rows of adj(Guu) Gu
+        const double kt = t0 ? kta : ktb, gut = t0 ? gu0 : gu1;
         double Dx, Dy;
-        dmma(Dx, Dy, t0 ? gu0 : ((t == 1) ? gu1 : 0.0), (t < 2) ? kt : 0.0, 0.0, 0.0);     // Gu^T adj(Guu) Gu
-        const double idet = rcp_w(fma(g00, g11, -g01 * g01));
+        dmma(Dx, Dy, tlow ? gut : 0.0, tlow ? kt : 0.0, 0.0, 0.0);                          // Gu^T adj(Guu) Gu
+        const double idet = rcp_piv(fma(g00, g11, -g01 * g01));
         // ---- 4. Schur complement --------------------------------------------------------------------------------------------------------
         px = fma(-idet, Dx, fma(dmG, Gx, hpx));
         py = fma(-idet, Dy, fma(dmG, Gy, hpy));
         // gains (K | k_ff) = -Guu^-1 Gu and Guu^-1 for the corrector
-        if (t < 2) sw[kst] = -idet * kt;
-        if (l == 2) { sw[W_GI0] = g11 * idet; sw[W_GI1] = -g01 * idet; sw[W_GI2] = g00 * idet; }
+        const double kout = -idet * kt, gi0 = g11 * idet, gi1 = -g01 * idet, gi2 = g00 * idet;
+        if (tlow) sw[kst] = kout;
+        if (l == 2) { sw[W_GI0] = gi0; sw[W_GI1] = gi1; sw[W_GI2] = gi2; }
     }
     __syncwarp();
 }
@@ -234,23 +256,28 @@ __device__ __forceinline__ void mma_forward(const admpc_opts &o, double *rec, in
     const double c0y = (t0 && g == 1) ? 1.0 : 0.0;
     const bool l0x = lo && !t0, l0y = (lo && !t0) || t3;
     const bool row0 = (g == 0);
-    double xx = 0.0, xy = (l == 3) ? 1.0 : 0.0;                  // ddx_0 = 0 (x0 is eliminated), homogeneous 1
+    double xx = 0.0, xy = (l == 3) ? 1.0 : 0.0;                  // ddx_0 = 0 (x0 is eliminated), homogeneous 1 ; rows g > 0 stay 0
     double *st = rec;
-    double bm, kh, a0x, a0y;
+    double bm, kh, a0x, a0y, acx, acy;
     cf.load(st, bm, kh);
     { const double u = st[a0o], v = st[a1o]; a0x = l0x ? u : c0x; a0y = l0y ? v : c0y; }
+    dmma(acx, acy, bm, kh, a0x, a0y);                              // cl(Acl) = Bh Kh + A0 of stage 0
+    {
+        const double *sn = st + W_RS;
+        cf.load(sn, bm, kh);
+        const double u = sn[a0o], v = sn[a1o];
+        a0x = l0x ? u : c0x; a0y = l0y ? v : c0y;
+    }
 #pragma unroll 2
     for (int k = 0; k < N; k++, st += W_RS) {
-        double acx, acy;
-        dmma(acx, acy, bm, kh, a0x, a0y);                          // cl(Acl) = Bh Kh + A0
+        mm8(xx, xy, xx, xy, acx, acy, 0.0, 0.0);                   // the chain: two dependent DMMAs per stage
+        dmma(acx, acy, bm, kh, a0x, a0y);                          // closed-loop matrix of stage k + 1, off the chain
         {
-            const double *sn = (k + 1 < N) ? st + W_RS : st;
+            const double *sn = (k + 2 < N) ? st + 2 * W_RS : st;
             cf.load(sn, bm, kh);
             const double u = sn[a0o], v = sn[a1o];
             a0x = l0x ? u : c0x; a0y = l0y ? v : c0y;
         }
-        mm8(xx, xy, xx, xy, acx, acy, 0.0, 0.0);
-        if (!row0) { xx = 0.0; xy = 0.0; }
         if (l < 4) stv(st + W_XA + 2 * t, xx, xy);
     }
     __syncwarp();
@@ -269,25 +296,25 @@ __device__ __forceinline__ void mma_backward(const admpc_opts &o, double *rec, c
     double px, py;
     { const double2 tg = ldv(term + T_GX + 2 * t); px = m0 * tg.x; py = m0 * tg.y; }                   // p_N = r_x,N
     double *st = rec + (size_t)(N - 1) * W_RS;
-    double bm, kh, atx, aty;
+    double bm, kh, atx, aty, ctx, cty;
     cf.load(st, bm, kh); af.load(st, atx, aty);
+    dmma(ctx, cty, kh, bm, atx, aty);                              // cl(Acl^T) = Kh^T Bh^T + A0^T of stage N-1 (row / column 7 never used)
+    cf.load(st - W_RS, bm, kh); af.load(st - W_RS, atx, aty);
     double2 pb = ldv(st + W_PB + 2 * t), gx = ldv(st + W_GX + 2 * t), k0 = ldv(st + W_K0 + 2 * t), k1 = ldv(st + W_K1 + 2 * t);
     double2 rt = ldv(st + W_BAR + 2);
 #pragma unroll 2
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
-        double ctx, cty;
-        dmma(ctx, cty, kh, bm, atx, aty);                          // cl(Acl^T) = Kh^T Bh^T + A0^T (row / column 7 never used)
         const double cx = m0 * fma(k1.x, rt.y, fma(k0.x, rt.x, gx.x)), cy = m0 * fma(k1.y, rt.y, fma(k0.y, rt.x, gx.y));
-        const double hx = fma(m0, pb.x, px), hy = fma(m0, pb.y, py);
+        const double hx = fma(m0, pb.x, px), hy = fma(m0, pb.y, py);           // rows g > 0 stay 0
+        mm8(px, py, hx, hy, ctx, cty, cx, cy);
+        dmma(ctx, cty, kh, bm, atx, aty);                          // stage k - 1, off the chain
         if (l < 4) stv(st + W_PB + 2 * t, hx, hy);
         {
-            const double *sn = (k > 0) ? st - W_RS : st;
-            cf.load(sn, bm, kh); af.load(sn, atx, aty);
+            const double *sn = (k > 0) ? st - W_RS : st, *s2 = (k > 1) ? st - 2 * W_RS : st;
+            cf.load(s2, bm, kh); af.load(s2, atx, aty);
             pb = ldv(sn + W_PB + 2 * t); gx = ldv(sn + W_GX + 2 * t); k0 = ldv(sn + W_K0 + 2 * t); k1 = ldv(sn + W_K1 + 2 * t);
             rt = ldv(sn + W_BAR + 2);
         }
-        mm8(px, py, hx, hy, ctx, cty, cx, cy);
-        if (!row0) { px = 0.0; py = 0.0; }
     }
     __syncwarp();
 }
@@ -315,8 +342,7 @@ __device__ __forceinline__ void mma_adjoint(double *rec, const double *term, int
             const double *sn = (k > 0) ? st - W_RS : st;
             af.load(sn, atx, aty); gx = ldv(sn + W_GX + 2 * t);
         }
-        mm8(px, py, px, py, bx, by, cx, cy);                       // (the product of stage 0 is not used)
-        if (!row0) { px = 0.0; py = 0.0; }
+        mm8(px, py, px, py, bx, by, cx, cy);                       // (the product of stage 0 is not used ; rows g > 0 stay 0)
     }
     __syncwarp();
 }

@@ -478,7 +478,8 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        qp_name = "qp_rw_kernel<1>" if os.environ.get("ADMPC_QP_VARIANT", "") in ("", "0", "6") and N <= 31 else "qp_warp_kernel"
+        _v = os.environ.get("ADMPC_QP_VARIANT", "")
+        qp_name = ("qp_mma_kernel" if _v in ("", "0", "7") else "qp_rw_kernel<1>" if _v == "6" else "qp_warp_kernel") if N <= 31 else "qp_warp_kernel"
         roofline = {"bound": "fp64", "kernel": {"prepare": "gp_sweep_kernel + prepare_kernel<GP>", "qp": qp_name}[dom],
                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,
