@@ -81,12 +81,29 @@ __device__ __forceinline__ void mm8(double &d0, double &d1, double ax, double ay
     dmma(e0, e1, ax, bx, c0, c1);
     dmma(d0, d1, ay, by, e0, e1);
 }
+#ifndef MMA_UF
+#define MMA_UF 1        // unroll factor of the factor sweep
+#endif
+#ifndef MMA_UV
+#define MMA_UV 2        // unroll factor of the vector sweeps
+#endif
+#define MMA_PRAGMA_(x) _Pragma(#x)
+#define MMA_UNROLL(n) MMA_PRAGMA_(unroll n)
+__device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(FULL, v, src); }
+#ifndef MMA_UF
+#define MMA_UF 1        // unroll factor of the factor sweep
+#endif
+#ifndef MMA_UV
+#define MMA_UV 2        // unroll factor of the vector sweeps
+#endif
+#define MMA_PRAGMA_(x) _Pragma(#x)
+#define MMA_UNROLL(n) MMA_PRAGMA_(unroll n)
 __device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(FULL, v, src); }
 // reciprocal of the pivot's determinant.  MMA_RCP1 = 1: one Newton step on the hardware seed (A/B switch, see profiles)
 #ifndef MMA_RCP1
 #define MMA_RCP1 0
 #endif
-__device__ __forceinline__ double rcp_piv(double x)
+__device__ __forceinline__ double rcp_w(double x)
 {
 #if MMA_RCP1
     double r;
@@ -187,7 +204,7 @@ __device__ __forceinline__ void mma_factor(const admpc_opts &o, double *rec, con
     mf.load(st, mx, my);
     double2 bar01 = ldv(st + W_BAR), bar23 = ldv(st + W_BAR + 2), gxp = ldv(st + gxo);
     double qt6 = st[W_BAR + 4];
-#pragma unroll 1
+MMA_UNROLL(MMA_UF)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         ADMPC_ASSERT(st == rec + (size_t)k * W_RS);
         double *sw = const_cast<double *>(st);
@@ -228,7 +245,7 @@ __device__ __forceinline__ void mma_factor(const admpc_opts &o, double *rec, con
         const double kt = t0 ? kta : ktb, gut = t0 ? gu0 : gu1;
         double Dx, Dy;
         dmma(Dx, Dy, tlow ? gut : 0.0, tlow ? kt : 0.0, 0.0, 0.0);                          // Gu^T adj(Guu) Gu
-        const double idet = rcp_piv(fma(g00, g11, -g01 * g01));
+        const double idet = rcp_w(fma(g00, g11, -g01 * g01));
         // ---- 4. Schur complement --------------------------------------------------------------------------------------------------------
         px = fma(-idet, Dx, fma(dmG, Gx, hpx));
         py = fma(-idet, Dy, fma(dmG, Gy, hpy));
@@ -268,7 +285,7 @@ __device__ __forceinline__ void mma_forward(const admpc_opts &o, double *rec, in
         const double u = sn[a0o], v = sn[a1o];
         a0x = l0x ? u : c0x; a0y = l0y ? v : c0y;
     }
-#pragma unroll 2
+MMA_UNROLL(MMA_UV)
     for (int k = 0; k < N; k++, st += W_RS) {
         mm8(xx, xy, xx, xy, acx, acy, 0.0, 0.0);                   // the chain: two dependent DMMAs per stage
         dmma(acx, acy, bm, kh, a0x, a0y);                          // closed-loop matrix of stage k + 1, off the chain
@@ -302,7 +319,7 @@ __device__ __forceinline__ void mma_backward(const admpc_opts &o, double *rec, c
     cf.load(st - W_RS, bm, kh); af.load(st - W_RS, atx, aty);
     double2 pb = ldv(st + W_PB + 2 * t), gx = ldv(st + W_GX + 2 * t), k0 = ldv(st + W_K0 + 2 * t), k1 = ldv(st + W_K1 + 2 * t);
     double2 rt = ldv(st + W_BAR + 2);
-#pragma unroll 2
+MMA_UNROLL(MMA_UV)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         const double cx = m0 * fma(k1.x, rt.y, fma(k0.x, rt.x, gx.x)), cy = m0 * fma(k1.y, rt.y, fma(k0.y, rt.x, gx.y));
         const double hx = fma(m0, pb.x, px), hy = fma(m0, pb.y, py);           // rows g > 0 stay 0
@@ -333,7 +350,7 @@ __device__ __forceinline__ void mma_adjoint(double *rec, const double *term, int
     double atx, aty;
     af.load(st, atx, aty);
     double2 gx = ldv(st + W_GX + 2 * t);
-#pragma unroll 2
+MMA_UNROLL(MMA_UV)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         if (l < 4) stv(st + W_PB + 2 * t, px, py);
         const double cx = m0 * gx.x, cy = m0 * gx.y;
