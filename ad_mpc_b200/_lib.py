@@ -13,10 +13,10 @@ class AdmpcOpts(C.Structure):
     _fields_ = [
         ("N", C.c_int), ("iter_max", C.c_int), ("gp_enabled", C.c_int), ("gp_nout", C.c_int), ("gp_M", C.c_int),
         ("gp_dz", C.c_int), ("gp_stage0_trigger", C.c_int), ("model_variant", C.c_int),
-        ("gp_feat", C.c_int * DZMAX), ("gp_row", C.c_int * GPOUT_MAX), ("gp_precision", C.c_int), ("reserved_", C.c_int),
+        ("gp_feat", C.c_int * DZMAX), ("gp_row", C.c_int * GPOUT_MAX), ("gp_precision", C.c_int), ("con_set", C.c_int),
         ("dt", C.c_double), ("W", C.c_double * 9), ("We", C.c_double * 7),
         ("zl", C.c_double * 2), ("zu", C.c_double * 2), ("Zl", C.c_double * 2), ("Zu", C.c_double * 2),
-        ("lbu", C.c_double * 2), ("ubu", C.c_double * 2), ("lbx", C.c_double), ("ubx", C.c_double),
+        ("lbu", C.c_double * 2), ("ubu", C.c_double * 2), ("lbx", C.c_double), ("ubx", C.c_double), ("lbx2", C.c_double), ("ubx2", C.c_double),
         ("mass", C.c_double), ("lf", C.c_double), ("lr", C.c_double), ("iz", C.c_double), ("cf2", C.c_double),
         ("cr2", C.c_double),
         ("mu0", C.c_double), ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double),

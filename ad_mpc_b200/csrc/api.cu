@@ -35,6 +35,7 @@ extern "C" void admpc_default_opts(admpc_opts *o)
     for (int j = 0; j < 2; j++) { o->zl[j] = o->zu[j] = 10.0; o->Zl[j] = o->Zu[j] = 0.0; }
     o->lbu[0] = -10; o->ubu[0] = 5; o->lbu[1] = -3; o->ubu[1] = 3;
     o->lbx = -0.52; o->ubx = 0.52;
+    o->con_set = 0; o->lbx2 = -2.0; o->ubx2 = 2.0;
     // ad_3d.py:47-60 evaluated literally (the reference's pi literal is 3.14195)
     const double mass = 1500, f_mass = 900, r_mass = mass - f_mass, L = 2.7;
     o->mass = mass;
@@ -169,6 +170,11 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
 {
     if (!opts || !out || B <= 0 || opts->N < 2 || opts->N > ADMPC_NMAX) { admpc_set_error("admpc_batch_create", "bad argument"); return ADMPC_E_ARG; }
     if (opts->model_variant != 0 && opts->model_variant != 1) { admpc_set_error("admpc_batch_create", "model_variant must be 0 (Cartesian) or 1 (Frenet)"); return ADMPC_E_ARG; }
+    if (opts->con_set != 0 && opts->con_set != 1) { admpc_set_error("admpc_batch_create", "con_set must be 0 or 1"); return ADMPC_E_ARG; }
+    if (opts->con_set == 1 && opts->model_variant != 1) {
+        admpc_set_error("admpc_batch_create", "con_set = 1 (the Frenet variant's constraint set) needs model_variant = 1");
+        return ADMPC_E_UNSUPPORTED;
+    }
     int ndev = 0;
     CUDA_CHECK_RET(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { admpc_set_error("admpc_batch_create", "no such CUDA device"); return ADMPC_E_CUDA; }
@@ -191,7 +197,7 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
 
     // carve the pool
     struct Item { double **p; size_t rows; };
-    const size_t nX = (size_t)(N + 1) * 7, nU = (size_t)N * 2, nPi = (size_t)N * 7, nC = (size_t)N * NC;
+    const size_t nX = (size_t)(N + 1) * 7, nU = (size_t)N * 2, nPi = (size_t)N * 7, nC = (size_t)N * con_rows(h->P.o);
     double *x0, *yref, *pp, *gps, *kap = nullptr;
     // Interface arrays always; QP workspaces only for the kernel variant this handle will run: the warp-per-instance
     // kernel (N <= 63) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
@@ -522,8 +528,8 @@ extern "C" int admpc_batch_set_duals(admpc_batch *h, const double *pi, const dou
     const int N = h->P.o.N;
     int r = 0;
     if (pi) r = put_rows(h, pi, h->P.pib, N * 7);
-    if (r == 0 && lam) r = put_rows(h, lam, h->P.lamb, N * NC);
-    if (r == 0 && t) r = put_rows(h, t, h->P.tb, N * NC);
+    if (r == 0 && lam) r = put_rows(h, lam, h->P.lamb, N * con_rows(h->P.o));
+    if (r == 0 && t) r = put_rows(h, t, h->P.tb, N * con_rows(h->P.o));
     if (r == 0 && sl) r = put_rows(h, sl, h->P.slb, N * 2);
     if (r == 0 && su) r = put_rows(h, su, h->P.sub, N * 2);
     return r;
@@ -549,7 +555,8 @@ static int launch_feedback(admpc_batch *h)
         // Frenet variant: warp-per-instance kernel on the 6x8 stage structure (N <= 63, fused update), else / on request
         // (ADMPC_QP_VARIANT=1) the dense thread-per-instance kernel + separate update
         // (a spline curvature makes the column of s dense: A(:,0) != e0, outside the structure qp_warp_f exploits)
-        if (h->qp_variant != 1 && P.kap_K == 0 && launch_qp_warp_f(P, h->stream)) {
+        // (the variant's own constraint set, con_set = 1, is implemented by the dense kernel only)
+        if (h->qp_variant != 1 && P.kap_K == 0 && P.o.con_set == 0 && launch_qp_warp_f(P, h->stream)) {
             if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
             h->launches += 1;
             h->gat_fresh = h->gat_on;
@@ -691,8 +698,8 @@ static int get_rows(admpc_batch *h, const double *src, double *host, int F)
 extern "C" int admpc_batch_get_u(admpc_batch *h, double *u) { return h ? get_rows(h, h->P.ub, u, h->P.o.N * 2) : ADMPC_E_ARG; }
 extern "C" int admpc_batch_get_x(admpc_batch *h, double *x) { return h ? get_rows(h, h->P.xb, x, (h->P.o.N + 1) * 7) : ADMPC_E_ARG; }
 extern "C" int admpc_batch_get_pi(admpc_batch *h, double *pi) { return h ? get_rows(h, h->P.pib, pi, h->P.o.N * 7) : ADMPC_E_ARG; }
-extern "C" int admpc_batch_get_lam(admpc_batch *h, double *lam) { return h ? get_rows(h, h->P.lamb, lam, h->P.o.N * NC) : ADMPC_E_ARG; }
-extern "C" int admpc_batch_get_t(admpc_batch *h, double *t) { return h ? get_rows(h, h->P.tb, t, h->P.o.N * NC) : ADMPC_E_ARG; }
+extern "C" int admpc_batch_get_lam(admpc_batch *h, double *lam) { return h ? get_rows(h, h->P.lamb, lam, h->P.o.N * con_rows(h->P.o)) : ADMPC_E_ARG; }
+extern "C" int admpc_batch_get_t(admpc_batch *h, double *t) { return h ? get_rows(h, h->P.tb, t, h->P.o.N * con_rows(h->P.o)) : ADMPC_E_ARG; }
 extern "C" int admpc_batch_get_slacks(admpc_batch *h, double *sl, double *su)
 {
     if (!h) return ADMPC_E_ARG;

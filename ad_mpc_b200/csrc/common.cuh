@@ -54,6 +54,9 @@ struct GpDev {
     const double *centroids;
 };
 
+// inequality rows per stage of the configured constraint set = stride of lam / t (admpc.h con_set)
+__host__ __device__ __forceinline__ int con_rows(const admpc_opts &o) { return o.con_set == 1 ? 12 : NC; }
+
 #define DL_ROWS 79
 struct Params {
     admpc_opts o;

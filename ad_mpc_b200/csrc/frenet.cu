@@ -211,51 +211,120 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
 }
 
 // ---------------------------------------------------------------------------------------------- dense IPM ---------
-__device__ __forceinline__ bool con_on(int k, int c) { return !((c == 2 || c == 5) && k == 0); }
+// Constraint sets (twin of oracle/rti_oracle.c con_get): bounded quantities q = 0..nb-1 of z = [u0 u1 | x0..x6], each hard
+// (two rows) or soft (slack id soft[q], two more rows); row order [lb(q) | ub(q) | ls(s) | us(s)] as in the reference's iterate
+// dumps.  con_set 0: u0, u1 soft + delta hard (10 rows) ; con_set 1, the Frenet variant's own set (structure pinned by
+// ad_mpc/debug.json): u0 soft, u1 hard, e_y = x[1] hard, delta soft (12 rows).  State bounds and their slacks do not exist at
+// stage 0 (x0 is eliminated).
+#define NCD 12
+struct ConDesc {
+    int nb, ns, nc;
+    int idx[4], soft[4];
+    double lo[4], hi[4];
+};
+__device__ __forceinline__ void con_get(const admpc_opts &o, ConDesc &d)
+{
+    d.ns = 2;
+    d.idx[0] = 0; d.idx[1] = 1;
+    d.lo[0] = o.lbu[0]; d.hi[0] = o.ubu[0]; d.lo[1] = o.lbu[1]; d.hi[1] = o.ubu[1];
+    if (o.con_set == 1) {
+        d.nb = 4;
+        d.idx[2] = 3; d.idx[3] = 8;
+        d.soft[0] = 0; d.soft[1] = -1; d.soft[2] = -1; d.soft[3] = 1;
+        d.lo[2] = o.lbx2; d.hi[2] = o.ubx2; d.lo[3] = o.lbx; d.hi[3] = o.ubx;
+    } else {
+        d.nb = 3;
+        d.idx[2] = 8; d.idx[3] = 8;
+        d.soft[0] = 0; d.soft[1] = 1; d.soft[2] = -1; d.soft[3] = -1;
+        d.lo[2] = o.lbx; d.hi[2] = o.ubx; d.lo[3] = 0.0; d.hi[3] = 0.0;
+    }
+    d.nc = 2 * d.nb + 2 * d.ns;
+}
+__device__ __forceinline__ bool q_on(const ConDesc &d, int k, int q) { return d.idx[q] < 2 || k >= 1; }
+__device__ __forceinline__ int row_q(const ConDesc &d, int c)
+{
+    if (c < d.nb) return c;
+    if (c < 2 * d.nb) return c - d.nb;
+    const int s = (c < 2 * d.nb + d.ns) ? c - 2 * d.nb : c - 2 * d.nb - d.ns;
+    for (int q = 0; q < d.nb; q++) if (d.soft[q] == s) return q;
+    return 0;
+}
+__device__ __forceinline__ bool con_on(const ConDesc &d, int k, int c) { return q_on(d, k, row_q(d, c)); }
+#define RL(q) (q)
+#define RU(q) (d.nb + (q))
+#define RLS(s) (2 * d.nb + (s))
+#define RUS(s) (2 * d.nb + d.ns + (s))
 __device__ __forceinline__ constexpr int sy(int a, int b) { return (a >= b) ? (a * (a + 1) / 2 + b) : (b * (b + 1) / 2 + a); }
-
-// residuals of the current point: fills rgu, rgx, rgsl, rgsu, rb, rd, rm; returns the four norms and mu
-__device__ void dn_residuals(const Params &P, int i, double res[4], double &summ)
+// current value of the iterate entry a bounded quantity refers to, and of a delta vector [du | dx] of stage k
+__device__ __forceinline__ double q_bar(const Params &P, const ConDesc &d, int q, int k, int i)
+{
+    const int Bp = P.Bp;
+    return (d.idx[q] < 2) ? AT(P.ub, k * 2 + d.idx[q]) : AT(P.xb, k * 7 + d.idx[q] - 2);
+}
+struct QScal { double Sl, Su, Dl, Du; };
+__device__ __forceinline__ void q_scaling(const Params &P, const ConDesc &d, int q, int k, int i, QScal &S)
 {
     const admpc_opts &o = P.o;
-    const int N = o.N, Bp = P.Bp;
+    const int Bp = P.Bp, nc = d.nc;
+    const double Ts = o.dt;
+    const int sq = d.soft[q];
+    S.Sl = AT(P.lam, k * nc + RL(q)) / AT(P.t, k * nc + RL(q));
+    S.Su = AT(P.lam, k * nc + RU(q)) / AT(P.t, k * nc + RU(q));
+    if (sq >= 0) {
+        const double Ssl = AT(P.lam, k * nc + RLS(sq)) / AT(P.t, k * nc + RLS(sq)), Ssu = AT(P.lam, k * nc + RUS(sq)) / AT(P.t, k * nc + RUS(sq));
+        S.Dl = Ts * o.Zl[sq] + S.Sl + Ssl; S.Du = Ts * o.Zu[sq] + S.Su + Ssu;
+    } else { S.Dl = 0.0; S.Du = 0.0; }
+}
+
+// residuals of the current point: fills rgu, rgx, rgsl, rgsu, rb, rd, rm; returns the four norms and the sum of lam t
+__device__ void dn_residuals(const Params &P, const ConDesc &d, int i, double res[4], double &summ, int &ncon)
+{
+    const admpc_opts &o = P.o;
+    const int N = o.N, Bp = P.Bp, nc = d.nc;
     const double Ts = o.dt;
     double ng = 0, nb = 0, nd = 0, nm = 0;
-    summ = 0;
+    summ = 0; ncon = 0;
     for (int k = 0; k <= N; k++) {
         const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
         double dx[7];
 #pragma unroll
         for (int a = 0; a < 7; a++) dx[a] = AT(P.dx, k * 7 + a);
         if (k < N) {
-            double du[2], pi[7], lam[NC], t[NC];
+            double du[2], pi[7];
             du[0] = AT(P.du, k * 2); du[1] = AT(P.du, k * 2 + 1);
 #pragma unroll
             for (int a = 0; a < 7; a++) pi[a] = AT(P.pi, k * 7 + a);
-#pragma unroll
-            for (int c = 0; c < NC; c++) { lam[c] = AT(P.lam, k * NC + c); t[c] = AT(P.t, k * NC + c); }
-            double rd[NC];
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 double g = Ts * o.W[7 + j] * du[j] + AT(lin, DL_r + j);
 #pragma unroll
                 for (int l = 0; l < 7; l++) g += AT(lin, DL_B + l * 2 + j) * pi[l];
-                g += -lam[j] + lam[3 + j];
-                const double sl = AT(P.sl, k * 2 + j), su = AT(P.su, k * 2 + j), ub = AT(P.ub, k * 2 + j);
-                const double gsl = Ts * o.zl[j] + Ts * o.Zl[j] * sl - lam[j] - lam[6 + j];
-                const double gsu = Ts * o.zu[j] + Ts * o.Zu[j] * su - lam[3 + j] - lam[8 + j];
-                AT(P.rgu, k * 2 + j) = g; AT(P.rgsl, k * 2 + j) = gsl; AT(P.rgsu, k * 2 + j) = gsu;
-                rd[j] = t[j] - (du[j] - (o.lbu[j] - ub) + sl);
-                rd[3 + j] = t[3 + j] - ((o.ubu[j] - ub) - du[j] + su);
-                rd[6 + j] = t[6 + j] - sl;
-                rd[8 + j] = t[8 + j] - su;
-                ng = nmaxd(ng, nmaxd(fabs(g), nmaxd(fabs(gsl), fabs(gsu))));
+                for (int q = 0; q < d.nb; q++) if (d.idx[q] == j) g += -AT(P.lam, k * nc + RL(q)) + AT(P.lam, k * nc + RU(q));
+                AT(P.rgu, k * 2 + j) = g;
+                ng = nmaxd(ng, fabs(g));
             }
-            if (k >= 1) {
-                const double x6 = AT(P.xb, k * 7 + 6);
-                rd[2] = t[2] - (dx[6] - (o.lbx - x6));
-                rd[5] = t[5] - ((o.ubx - x6) - dx[6]);
-            } else { rd[2] = 0.0; rd[5] = 0.0; }
+            for (int c = 0; c < nc; c++) AT(P.rd, k * nc + c) = 0.0;
+            for (int q = 0; q < d.nb; q++) {
+                if (!q_on(d, k, q)) continue;
+                const double v = (d.idx[q] < 2) ? ((d.idx[q] == 0) ? du[0] : du[1]) : AT(P.dx, k * 7 + d.idx[q] - 2);
+                const double bar = q_bar(P, d, q, k, i);
+                const double lo = d.lo[q] - bar, hi = d.hi[q] - bar;
+                const int sq = d.soft[q];
+                if (sq >= 0) {
+                    const double sl = AT(P.sl, k * 2 + sq), su = AT(P.su, k * 2 + sq);
+                    const double gsl = Ts * o.zl[sq] + Ts * o.Zl[sq] * sl - AT(P.lam, k * nc + RL(q)) - AT(P.lam, k * nc + RLS(sq));
+                    const double gsu = Ts * o.zu[sq] + Ts * o.Zu[sq] * su - AT(P.lam, k * nc + RU(q)) - AT(P.lam, k * nc + RUS(sq));
+                    AT(P.rgsl, k * 2 + sq) = gsl; AT(P.rgsu, k * 2 + sq) = gsu;
+                    AT(P.rd, k * nc + RL(q)) = AT(P.t, k * nc + RL(q)) - (v - lo + sl);
+                    AT(P.rd, k * nc + RU(q)) = AT(P.t, k * nc + RU(q)) - (hi - v + su);
+                    AT(P.rd, k * nc + RLS(sq)) = AT(P.t, k * nc + RLS(sq)) - sl;
+                    AT(P.rd, k * nc + RUS(sq)) = AT(P.t, k * nc + RUS(sq)) - su;
+                    ng = nmaxd(ng, nmaxd(fabs(gsl), fabs(gsu)));
+                } else {
+                    AT(P.rd, k * nc + RL(q)) = AT(P.t, k * nc + RL(q)) - (v - lo);
+                    AT(P.rd, k * nc + RU(q)) = AT(P.t, k * nc + RU(q)) - (hi - v);
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 7; r++) {
                 double v = AT(lin, DL_b + r) - AT(P.dx, (k + 1) * 7 + r);
@@ -266,15 +335,14 @@ __device__ void dn_residuals(const Params &P, int i, double res[4], double &summ
                 AT(P.rb, k * 7 + r) = v;
                 nb = nmaxd(nb, fabs(v));
             }
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                AT(P.rd, k * NC + c) = rd[c];
-                if (!con_on(k, c)) { AT(P.rm, k * NC + c) = 0.0; continue; }
-                const double rm = lam[c] * t[c];
-                AT(P.rm, k * NC + c) = rm;
-                nd = nmaxd(nd, fabs(rd[c]));
+            for (int c = 0; c < nc; c++) {
+                if (!con_on(d, k, c)) { AT(P.rm, k * nc + c) = 0.0; continue; }
+                const double rm = AT(P.lam, k * nc + c) * AT(P.t, k * nc + c);
+                AT(P.rm, k * nc + c) = rm;
+                nd = nmaxd(nd, fabs(AT(P.rd, k * nc + c)));
                 nm = nmaxd(nm, fabs(rm));
                 summ += rm;
+                ncon++;
             }
         }
         if (k >= 1) {
@@ -285,7 +353,8 @@ __device__ void dn_residuals(const Params &P, int i, double res[4], double &summ
                 if (k < N) {
 #pragma unroll
                     for (int l = 0; l < 7; l++) g += AT(lin, DL_A + l * 7 + a) * AT(P.pi, k * 7 + l);
-                    if (a == 6) g += -AT(P.lam, k * NC + 2) + AT(P.lam, k * NC + 5);
+                    for (int q = 0; q < d.nb; q++)
+                        if (d.idx[q] == 2 + a) g += -AT(P.lam, k * nc + RL(q)) + AT(P.lam, k * nc + RU(q));
                 }
                 AT(P.rgx, k * 7 + a) = g;
                 ng = nmaxd(ng, fabs(g));
@@ -296,7 +365,7 @@ __device__ void dn_residuals(const Params &P, int i, double res[4], double &summ
 }
 
 // Riccati factorisation of the barrier-modified Hessian (matrix part): K, Luu (in Ginv), P (packed symmetric)
-__device__ void dn_factor(const Params &P, int i)
+__device__ void dn_factor(const Params &P, const ConDesc &d, int i)
 {
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
@@ -310,15 +379,18 @@ __device__ void dn_factor(const Params &P, int i)
     for (int a = 0; a < 28; a++) AT(P.P, N * 28 + a) = Pn[a];
     for (int k = N - 1; k >= 0; k--) {
         const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
-        double Rt[2];
+        // barrier-modified diagonal of the stage Hessian over z = [u; x] (soft-bound slacks eliminated)
+        double Hd[9];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const double Sl = AT(P.lam, k * NC + j) / AT(P.t, k * NC + j), Su = AT(P.lam, k * NC + 3 + j) / AT(P.t, k * NC + 3 + j);
-            const double Ssl = AT(P.lam, k * NC + 6 + j) / AT(P.t, k * NC + 6 + j), Ssu = AT(P.lam, k * NC + 8 + j) / AT(P.t, k * NC + 8 + j);
-            const double Dl = Ts * o.Zl[j] + Sl + Ssl, Du = Ts * o.Zu[j] + Su + Ssu;
-            Rt[j] = Ts * o.W[7 + j] + Sl * (1.0 - Sl / Dl) + Su * (1.0 - Su / Du);
+        for (int z = 0; z < 9; z++) Hd[z] = (z < 2) ? Ts * o.W[7 + z] : Ts * o.W[z - 2];
+        for (int q = 0; q < d.nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            QScal S; q_scaling(P, d, q, k, i, S);
+            const double add2 = (d.soft[q] >= 0) ? S.Su * (1.0 - S.Su / S.Du) : 0.0;
+            const double add1 = (d.soft[q] >= 0) ? S.Sl * (1.0 - S.Sl / S.Dl) : (S.Sl + S.Su);
+#pragma unroll
+            for (int z = 0; z < 9; z++) if (z == d.idx[q]) Hd[z] = Hd[z] + add1 + add2;
         }
-        const double Qt6 = Ts * o.W[6] + (k >= 1 ? AT(P.lam, k * NC + 2) / AT(P.t, k * NC + 2) + AT(P.lam, k * NC + 5) / AT(P.t, k * NC + 5) : 0.0);
         double BA[7][9], PBA[7][9], G[45];
 #pragma unroll
         for (int r = 0; r < 7; r++) {
@@ -344,9 +416,8 @@ __device__ void dn_factor(const Params &P, int i)
                 for (int l = 0; l < 7; l++) v += BA[l][a] * PBA[l][c];
                 G[sy(a, c)] = v;
             }
-        G[sy(0, 0)] += Rt[0]; G[sy(1, 1)] += Rt[1];
 #pragma unroll
-        for (int a = 0; a < 7; a++) G[sy(2 + a, 2 + a)] += (a == 6) ? Qt6 : Ts * o.W[a];
+        for (int z = 0; z < 9; z++) G[sy(z, z)] += Hd[z];
         const double l00 = sqrt(G[sy(0, 0)] + o.reg), l10 = G[sy(1, 0)] / l00, l11 = sqrt(G[sy(1, 1)] + o.reg - l10 * l10);
         AT(P.Ginv, k * 3 + 0) = l00; AT(P.Ginv, k * 3 + 1) = l10; AT(P.Ginv, k * 3 + 2) = l11;
         double K0[7], K1[7];
@@ -371,32 +442,53 @@ __device__ void dn_factor(const Params &P, int i)
     }
 }
 
+// barrier gradient of stage k: gl per row, the modified gradients rt (inputs) / qx (states), cl / cu per slack
+__device__ __forceinline__ void dn_stage_grad(const Params &P, const ConDesc &d, int i, int k, double gl[NCD], double rt[2], double qx[7],
+                                               double cl[2], double cu[2], QScal S[4])
+{
+    const int Bp = P.Bp, nc = d.nc;
+    for (int c = 0; c < nc; c++)
+        gl[c] = con_on(d, k, c) ? (AT(P.rm, k * nc + c) - AT(P.lam, k * nc + c) * AT(P.rd, k * nc + c)) / AT(P.t, k * nc + c) : 0.0;
+    rt[0] = AT(P.rgu, k * 2); rt[1] = AT(P.rgu, k * 2 + 1);
+#pragma unroll
+    for (int a = 0; a < 7; a++) qx[a] = (k >= 1) ? AT(P.rgx, k * 7 + a) : 0.0;
+    cl[0] = cl[1] = cu[0] = cu[1] = 0.0;
+    for (int q = 0; q < d.nb; q++) {
+        if (!q_on(d, k, q)) continue;
+        q_scaling(P, d, q, k, i, S[q]);
+        const int sq = d.soft[q];
+        double add;
+        double base = 0.0;
+#pragma unroll
+        for (int z = 0; z < 9; z++) if (z == d.idx[q]) base = (z < 2) ? rt[z & 1] : qx[(z >= 2) ? z - 2 : 0];
+        if (sq >= 0) {
+            const double c_l = AT(P.rgsl, k * 2 + sq) + gl[RL(q)] + gl[RLS(sq)];
+            const double c_u = AT(P.rgsu, k * 2 + sq) + gl[RU(q)] + gl[RUS(sq)];
+            if (sq == 0) { cl[0] = c_l; cu[0] = c_u; } else { cl[1] = c_l; cu[1] = c_u; }
+            add = base + (gl[RL(q)] - S[q].Sl * c_l / S[q].Dl) - (gl[RU(q)] - S[q].Su * c_u / S[q].Du);
+        } else {
+            add = base + gl[RL(q)] - gl[RU(q)];
+        }
+#pragma unroll
+        for (int z = 0; z < 9; z++) if (z == d.idx[q]) { if (z < 2) rt[z & 1] = add; else qx[(z >= 2) ? z - 2 : 0] = add; }
+    }
+}
+
 // Newton step for the complementarity right-hand side in P.rm: ddu, ddx, dpi, dsl, dsu, dt, dlam; returns the
 // fraction-to-boundary step and the two sums of the Mehrotra centering estimate
-__device__ void dn_solve(const Params &P, int i, double &alpha, double &s1, double &s2)
+__device__ void dn_solve(const Params &P, const ConDesc &d, int i, double &alpha, double &s1, double &s2)
 {
     const admpc_opts &o = P.o;
-    const int N = o.N, Bp = P.Bp;
-    const double Ts = o.dt;
+    const int N = o.N, Bp = P.Bp, nc = d.nc;
     double pv[7];
 #pragma unroll
     for (int a = 0; a < 7; a++) { pv[a] = AT(P.rgx, N * 7 + a); AT(P.pv, N * 7 + a) = pv[a]; }
-    // backward vector recursion (stage barrier quantities recomputed, rt / qt6 not stored)
+    // backward vector recursion (stage barrier quantities recomputed, rt / qx not stored)
     for (int k = N - 1; k >= 0; k--) {
         const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
-        double gl[NC], rt[2];
-#pragma unroll
-        for (int c = 0; c < NC; c++)
-            gl[c] = con_on(k, c) ? (AT(P.rm, k * NC + c) - AT(P.lam, k * NC + c) * AT(P.rd, k * NC + c)) / AT(P.t, k * NC + c) : 0.0;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const double Sl = AT(P.lam, k * NC + j) / AT(P.t, k * NC + j), Su = AT(P.lam, k * NC + 3 + j) / AT(P.t, k * NC + 3 + j);
-            const double Ssl = AT(P.lam, k * NC + 6 + j) / AT(P.t, k * NC + 6 + j), Ssu = AT(P.lam, k * NC + 8 + j) / AT(P.t, k * NC + 8 + j);
-            const double Dl = Ts * o.Zl[j] + Sl + Ssl, Du = Ts * o.Zu[j] + Su + Ssu;
-            const double cl = AT(P.rgsl, k * 2 + j) + gl[j] + gl[6 + j], cu = AT(P.rgsu, k * 2 + j) + gl[3 + j] + gl[8 + j];
-            rt[j] = AT(P.rgu, k * 2 + j) + (gl[j] - Sl * cl / Dl) - (gl[3 + j] - Su * cu / Du);
-        }
-        const double qt6 = (k >= 1) ? AT(P.rgx, k * 7 + 6) + gl[2] - gl[5] : 0.0;
+        double gl[NCD], rt[2], qx[7], cl[2], cu[2];
+        QScal S[4];
+        dn_stage_grad(P, d, i, k, gl, rt, qx, cl, cu, S);
         double Pn[28], hv[7], gu[2], gx[7];
 #pragma unroll
         for (int a = 0; a < 28; a++) Pn[a] = AT(P.P, (k + 1) * 28 + a);
@@ -416,7 +508,7 @@ __device__ void dn_solve(const Params &P, int i, double &alpha, double &s1, doub
         }
 #pragma unroll
         for (int a = 0; a < 7; a++) {
-            double v = (k >= 1) ? ((a == 6) ? qt6 : AT(P.rgx, k * 7 + a)) : 0.0;
+            double v = qx[a];
 #pragma unroll
             for (int l = 0; l < 7; l++) v += AT(lin, DL_A + l * 7 + a) * hv[l];
             gx[a] = v;
@@ -447,33 +539,38 @@ __device__ void dn_solve(const Params &P, int i, double &alpha, double &s1, doub
             ddu[j] = v;
             AT(P.ddu, k * 2 + j) = v;
         }
-        // slack / t / lambda steps of this stage (need ddu_k and ddx_k[6])
+        // slack / t / lambda steps of this stage (need ddu_k and ddx_k)
         {
-            double gl[NC], dt[NC];
+            double gl[NCD], rt[2], qx[7], cl[2], cu[2], dt[NCD];
+            QScal S[4];
+            dn_stage_grad(P, d, i, k, gl, rt, qx, cl, cu, S);
+            for (int c = 0; c < nc; c++) dt[c] = 0.0;
+            AT(P.dsl, k * 2) = 0.0; AT(P.dsl, k * 2 + 1) = 0.0; AT(P.dsu, k * 2) = 0.0; AT(P.dsu, k * 2 + 1) = 0.0;
+            for (int q = 0; q < d.nb; q++) {
+                if (!q_on(d, k, q)) continue;
+                double dv = 0.0;
 #pragma unroll
-            for (int c = 0; c < NC; c++)
-                gl[c] = con_on(k, c) ? (AT(P.rm, k * NC + c) - AT(P.lam, k * NC + c) * AT(P.rd, k * NC + c)) / AT(P.t, k * NC + c) : 0.0;
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const double Sl = AT(P.lam, k * NC + j) / AT(P.t, k * NC + j), Su = AT(P.lam, k * NC + 3 + j) / AT(P.t, k * NC + 3 + j);
-                const double Ssl = AT(P.lam, k * NC + 6 + j) / AT(P.t, k * NC + 6 + j), Ssu = AT(P.lam, k * NC + 8 + j) / AT(P.t, k * NC + 8 + j);
-                const double Dl = Ts * o.Zl[j] + Sl + Ssl, Du = Ts * o.Zu[j] + Su + Ssu;
-                const double cl = AT(P.rgsl, k * 2 + j) + gl[j] + gl[6 + j], cu = AT(P.rgsu, k * 2 + j) + gl[3 + j] + gl[8 + j];
-                const double dsl = -(cl + Sl * ddu[j]) / Dl, dsu = -(cu - Su * ddu[j]) / Du;
-                AT(P.dsl, k * 2 + j) = dsl; AT(P.dsu, k * 2 + j) = dsu;
-                dt[j] = ddu[j] + dsl - AT(P.rd, k * NC + j);
-                dt[3 + j] = -ddu[j] + dsu - AT(P.rd, k * NC + 3 + j);
-                dt[6 + j] = dsl - AT(P.rd, k * NC + 6 + j);
-                dt[8 + j] = dsu - AT(P.rd, k * NC + 8 + j);
+                for (int z = 0; z < 9; z++) if (z == d.idx[q]) dv = (z < 2) ? ddu[z & 1] : ddx[(z >= 2) ? z - 2 : 0];
+                const int sq = d.soft[q];
+                if (sq >= 0) {
+                    const double c_l = (sq == 0) ? cl[0] : cl[1], c_u = (sq == 0) ? cu[0] : cu[1];
+                    const double dsl = -(c_l + S[q].Sl * dv) / S[q].Dl, dsu = -(c_u - S[q].Su * dv) / S[q].Du;
+                    AT(P.dsl, k * 2 + sq) = dsl; AT(P.dsu, k * 2 + sq) = dsu;
+                    dt[RL(q)] = dv + dsl - AT(P.rd, k * nc + RL(q));
+                    dt[RU(q)] = -dv + dsu - AT(P.rd, k * nc + RU(q));
+                    dt[RLS(sq)] = dsl - AT(P.rd, k * nc + RLS(sq));
+                    dt[RUS(sq)] = dsu - AT(P.rd, k * nc + RUS(sq));
+                } else {
+                    dt[RL(q)] = dv - AT(P.rd, k * nc + RL(q));
+                    dt[RU(q)] = -dv - AT(P.rd, k * nc + RU(q));
+                }
             }
-            if (k >= 1) { dt[2] = ddx[6] - AT(P.rd, k * NC + 2); dt[5] = -ddx[6] - AT(P.rd, k * NC + 5); }
-            else { dt[2] = 0.0; dt[5] = 0.0; }
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const double lam = AT(P.lam, k * NC + c), t = AT(P.t, k * NC + c);
-                const double dl = con_on(k, c) ? -(AT(P.rm, k * NC + c) + lam * dt[c]) / t : 0.0;
-                AT(P.dt, k * NC + c) = dt[c]; AT(P.dlam, k * NC + c) = dl;
-                if (!con_on(k, c)) continue;
+            for (int c = 0; c < nc; c++) {
+                const double lam = AT(P.lam, k * nc + c), t = AT(P.t, k * nc + c);
+                const bool on = con_on(d, k, c);
+                const double dl = on ? -(AT(P.rm, k * nc + c) + lam * dt[c]) / t : 0.0;
+                AT(P.dt, k * nc + c) = dt[c]; AT(P.dlam, k * nc + c) = dl;
+                if (!on) continue;
                 if (dl < 0 && -lam / dl < alpha) alpha = -lam / dl;
                 if (dt[c] < 0 && -t / dt[c] < alpha) alpha = -t / dt[c];
                 s1 += lam * dt[c] + t * dl;
@@ -511,57 +608,57 @@ __global__ void __launch_bounds__(64) qp_dense_kernel(const Params P)
         if (flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
         return;
     }
-    // cold start (identical to qp_ipm.cu)
+    ConDesc d;
+    con_get(o, d);
+    const int nc = d.nc;
+    // cold start (identical to qp_ipm.cu): primal 0 pushed thr0 inside its box, t from the box, lam = mu0 / t
 #pragma unroll
     for (int a = 0; a < 7; a++) AT(P.dx, a) = AT(P.x0, a) - AT(P.xb, a);
     for (int k = 0; k < N; k++) {
-        for (int j = 0; j < 3; j++) {
-            if (j == 2 && k == 0) {
-                AT(P.t, 2) = 1.0; AT(P.t, 5) = 1.0; AT(P.lam, 2) = 0.0; AT(P.lam, 5) = 0.0;
-                continue;
-            }
-            const double cur = (j < 2) ? AT(P.ub, k * 2 + j) : AT(P.xb, k * 7 + 6);
-            const double lo = ((j < 2) ? o.lbu[j] : o.lbx) - cur, hi = ((j < 2) ? o.ubu[j] : o.ubx) - cur;
+        for (int a = 0; a < 7; a++) { AT(P.pi, k * 7 + a) = 0.0; AT(P.dx, (k + 1) * 7 + a) = 0.0; }
+        AT(P.du, k * 2) = 0.0; AT(P.du, k * 2 + 1) = 0.0;
+        AT(P.sl, k * 2) = 0.0; AT(P.sl, k * 2 + 1) = 0.0; AT(P.su, k * 2) = 0.0; AT(P.su, k * 2 + 1) = 0.0;
+    }
+    for (int k = 0; k < N; k++) {
+        for (int c = 0; c < nc; c++) { AT(P.t, k * nc + c) = 1.0; AT(P.lam, k * nc + c) = 0.0; }
+        for (int q = 0; q < d.nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            const double bar = q_bar(P, d, q, k, i);
+            const double lo = d.lo[q] - bar, hi = d.hi[q] - bar;
             double v = 0.0;
             if (v - lo < o.thr0) {
                 if (hi - v < o.thr0) v = 0.5 * (lo + hi);
                 else v = lo + o.thr0;
             } else if (hi - v < o.thr0) v = hi - o.thr0;
-            if (j < 2) AT(P.du, k * 2 + j) = v; else AT(P.dx, k * 7 + 6) = v;
-            const double tl = fmax(o.thr0, v - lo), tu = fmax(o.thr0, hi - v);
-            AT(P.t, k * NC + j) = tl; AT(P.t, k * NC + 3 + j) = tu;
-            AT(P.lam, k * NC + j) = o.mu0 / tl; AT(P.lam, k * NC + 3 + j) = o.mu0 / tu;
+            if (d.idx[q] < 2) AT(P.du, k * 2 + d.idx[q]) = v; else AT(P.dx, k * 7 + d.idx[q] - 2) = v;
+            AT(P.t, k * nc + RL(q)) = fmax(o.thr0, v - lo);
+            AT(P.t, k * nc + RU(q)) = fmax(o.thr0, hi - v);
+            if (d.soft[q] >= 0) { AT(P.t, k * nc + RLS(d.soft[q])) = o.thr0; AT(P.t, k * nc + RUS(d.soft[q])) = o.thr0; }
         }
-        for (int j = 0; j < 2; j++) {
-            AT(P.t, k * NC + 6 + j) = o.thr0; AT(P.t, k * NC + 8 + j) = o.thr0;
-            AT(P.lam, k * NC + 6 + j) = o.mu0 / o.thr0; AT(P.lam, k * NC + 8 + j) = o.mu0 / o.thr0;
-            AT(P.sl, k * 2 + j) = 0.0; AT(P.su, k * 2 + j) = 0.0;
-        }
-        for (int a = 0; a < 7; a++) AT(P.pi, k * 7 + a) = 0.0;
-        for (int a = 0; a < 6; a++) AT(P.dx, (k + 1) * 7 + a) = 0.0;
-        if (k + 1 == N) AT(P.dx, N * 7 + 6) = 0.0;
+        for (int c = 0; c < nc; c++) if (con_on(d, k, c)) AT(P.lam, k * nc + c) = o.mu0 / AT(P.t, k * nc + c);
     }
-    const double inv_nc = 1.0 / (double)(NC * N - 2);
     int status = 1, iter = 0;
     double res[4] = {0, 0, 0, 0};
     for (iter = 0;; iter++) {
         double summ;
-        dn_residuals(P, i, res, summ);
+        int ncon;
+        dn_residuals(P, d, i, res, summ, ncon);
         if (!(isfinite(res[0]) && isfinite(res[1]) && isfinite(res[2]) && isfinite(res[3]))) { status = 3; break; }
         if (res[0] < o.tol_stat && res[1] < o.tol_eq && res[2] < o.tol_ineq && res[3] < o.tol_comp) { status = 0; break; }
         if (iter >= o.iter_max) { status = 1; break; }
+        const double inv_nc = 1.0 / (double)ncon;
         const double mu = summ * inv_nc;
         double a_aff, s1, s2, alpha;
-        dn_factor(P, i);
-        dn_solve(P, i, a_aff, s1, s2);
+        dn_factor(P, d, i);
+        dn_solve(P, d, i, a_aff, s1, s2);
         const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
         double sigma = mu_aff / mu;
         sigma = sigma * sigma * sigma;
         for (int k = 0; k < N; k++)
-            for (int c = 0; c < NC; c++)
-                if (con_on(k, c))
-                    AT(P.rm, k * NC + c) = AT(P.lam, k * NC + c) * AT(P.t, k * NC + c) + AT(P.dlam, k * NC + c) * AT(P.dt, k * NC + c) - sigma * mu;
-        dn_solve(P, i, alpha, s1, s2);
+            for (int c = 0; c < nc; c++)
+                if (con_on(d, k, c))
+                    AT(P.rm, k * nc + c) = AT(P.lam, k * nc + c) * AT(P.t, k * nc + c) + AT(P.dlam, k * nc + c) * AT(P.dt, k * nc + c) - sigma * mu;
+        dn_solve(P, d, i, alpha, s1, s2);
         if (alpha < o.alpha_min) { status = 2; break; }
         if (alpha < 1.0) alpha *= 0.995;
         for (int k = 0; k < N; k++) {
@@ -574,10 +671,10 @@ __global__ void __launch_bounds__(64) qp_dense_kernel(const Params P)
                 AT(P.dx, (k + 1) * 7 + a) += alpha * AT(P.ddx, (k + 1) * 7 + a);
                 AT(P.pi, k * 7 + a) += alpha * AT(P.dpi, k * 7 + a);
             }
-            for (int c = 0; c < NC; c++) {
-                if (!con_on(k, c)) continue;
-                AT(P.lam, k * NC + c) = fmax(AT(P.lam, k * NC + c) + alpha * AT(P.dlam, k * NC + c), o.lam_min);
-                AT(P.t, k * NC + c) = fmax(AT(P.t, k * NC + c) + alpha * AT(P.dt, k * NC + c), o.t_min);
+            for (int c = 0; c < nc; c++) {
+                if (!con_on(d, k, c)) continue;
+                AT(P.lam, k * nc + c) = fmax(AT(P.lam, k * nc + c) + alpha * AT(P.dlam, k * nc + c), o.lam_min);
+                AT(P.t, k * nc + c) = fmax(AT(P.t, k * nc + c) + alpha * AT(P.dt, k * nc + c), o.t_min);
             }
         }
     }
@@ -600,6 +697,9 @@ __global__ void __launch_bounds__(128) nlp_res_dense_kernel(const Params P, int 
     if (flag == 2) return;
     if (it > 0 && P.status[i] != 0) { P.sqp_status[i] = P.status[i]; P.sqp_iter[i] = it - 1; P.lin_bad[i] = 2; return; }
     if (flag == 1) { P.sqp_status[i] = 1; P.status[i] = 1; P.sqp_iter[i] = it; P.lin_bad[i] = 2; return; }
+    ConDesc d;
+    con_get(o, d);
+    const int nc = d.nc;
     const double Ts = o.dt;
     double ng = 0, nb = 0, nd = 0, nm = 0;
     double pim[7];
@@ -607,48 +707,52 @@ __global__ void __launch_bounds__(128) nlp_res_dense_kernel(const Params P, int 
     for (int a = 0; a < 7; a++) { pim[a] = 0.0; nb = nmaxd(nb, fabs(AT(P.x0, a) - AT(P.xb, a))); }
     for (int k = 0; k < N; k++) {
         const double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
-        double pi[7], lam[NC], t[NC];
+        double pi[7], gu[2], gx[7];
 #pragma unroll
         for (int a = 0; a < 7; a++) pi[a] = AT(P.pib, k * 7 + a);
-#pragma unroll
-        for (int c = 0; c < NC; c++) { lam[c] = AT(P.lamb, k * NC + c); t[c] = AT(P.tb, k * NC + c); }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             double g = AT(lin, DL_r + j);
 #pragma unroll
             for (int l = 0; l < 7; l++) g += AT(lin, DL_B + l * 2 + j) * pi[l];
-            g += -lam[j] + lam[3 + j];
-            const double sl = AT(P.slb, k * 2 + j), su = AT(P.sub, k * 2 + j), u = AT(P.ub, k * 2 + j);
-            const double gsl = Ts * o.zl[j] + Ts * o.Zl[j] * sl - lam[j] - lam[6 + j];
-            const double gsu = Ts * o.zu[j] + Ts * o.Zu[j] * su - lam[3 + j] - lam[8 + j];
-            ng = nmaxd(ng, nmaxd(fabs(g), nmaxd(fabs(gsl), fabs(gsu))));
-            nd = nmaxd(nd, fabs(t[j] - (0.0 - (o.lbu[j] - u) + sl)));
-            nd = nmaxd(nd, fabs(t[3 + j] - ((o.ubu[j] - u) - 0.0 + su)));
-            nd = nmaxd(nd, fabs(t[6 + j] - sl));
-            nd = nmaxd(nd, fabs(t[8 + j] - su));
+            gu[j] = g;
         }
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            double g = AT(lin, DL_q + a) - pim[a];
+#pragma unroll
+            for (int l = 0; l < 7; l++) g += AT(lin, DL_A + l * 7 + a) * pi[l];
+            gx[a] = g;
+        }
+        for (int q = 0; q < d.nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            const double ll = AT(P.lamb, k * nc + RL(q)), lu = AT(P.lamb, k * nc + RU(q));
+            const double tl = AT(P.tb, k * nc + RL(q)), tu = AT(P.tb, k * nc + RU(q));
+            const double bar = q_bar(P, d, q, k, i);
+#pragma unroll
+            for (int z = 0; z < 9; z++) if (z == d.idx[q]) { if (z < 2) gu[z & 1] += -ll + lu; else gx[(z >= 2) ? z - 2 : 0] += -ll + lu; }
+            const int sq = d.soft[q];
+            double sl = 0.0, su = 0.0;
+            if (sq >= 0) {
+                sl = AT(P.slb, k * 2 + sq); su = AT(P.sub, k * 2 + sq);
+                const double lls = AT(P.lamb, k * nc + RLS(sq)), lus = AT(P.lamb, k * nc + RUS(sq));
+                const double gsl = Ts * o.zl[sq] + Ts * o.Zl[sq] * sl - ll - lls;
+                const double gsu = Ts * o.zu[sq] + Ts * o.Zu[sq] * su - lu - lus;
+                ng = nmaxd(ng, nmaxd(fabs(gsl), fabs(gsu)));
+                nd = nmaxd(nd, nmaxd(fabs(AT(P.tb, k * nc + RLS(sq)) - sl), fabs(AT(P.tb, k * nc + RUS(sq)) - su)));
+                nm = nmaxd(nm, nmaxd(fabs(lls * AT(P.tb, k * nc + RLS(sq))), fabs(lus * AT(P.tb, k * nc + RUS(sq)))));
+            }
+            nd = nmaxd(nd, fabs(tl - (0.0 - (d.lo[q] - bar) + sl)));
+            nd = nmaxd(nd, fabs(tu - ((d.hi[q] - bar) - 0.0 + su)));
+            nm = nmaxd(nm, nmaxd(fabs(ll * tl), fabs(lu * tu)));
+        }
+        ng = nmaxd(ng, nmaxd(fabs(gu[0]), fabs(gu[1])));
         if (k >= 1) {
-            const double x6 = AT(P.xb, k * 7 + 6);
-            nd = nmaxd(nd, fabs(t[2] - (0.0 - (o.lbx - x6))));
-            nd = nmaxd(nd, fabs(t[5] - ((o.ubx - x6) - 0.0)));
+#pragma unroll
+            for (int a = 0; a < 7; a++) ng = nmaxd(ng, fabs(gx[a]));
         }
 #pragma unroll
         for (int a = 0; a < 7; a++) nb = nmaxd(nb, fabs(AT(lin, DL_b + a)));
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            if (!con_on(k, c)) continue;
-            nm = nmaxd(nm, fabs(lam[c] * t[c]));
-        }
-        if (k >= 1) {
-#pragma unroll
-            for (int a = 0; a < 7; a++) {
-                double g = AT(lin, DL_q + a) - pim[a];
-#pragma unroll
-                for (int l = 0; l < 7; l++) g += AT(lin, DL_A + l * 7 + a) * pi[l];
-                if (a == 6) g += -lam[2] + lam[5];
-                ng = nmaxd(ng, fabs(g));
-            }
-        }
 #pragma unroll
         for (int a = 0; a < 7; a++) pim[a] = pi[a];
     }

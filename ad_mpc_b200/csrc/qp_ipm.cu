@@ -510,7 +510,7 @@ __global__ void update_kernel(const Params P)
         AT(P.sub, row) = AT(P.su, row);
     }
     if (row < N * 7) AT(P.pib, row) = AT(P.pi, row);
-    if (row < N * NC) { AT(P.lamb, row) = AT(P.lam, row); AT(P.tb, row) = AT(P.t, row); }
+    if (row < N * con_rows(P.o)) { AT(P.lamb, row) = AT(P.lam, row); AT(P.tb, row) = AT(P.t, row); }
 }
 
 void launch_qp(const Params &P, cudaStream_t s)
@@ -521,7 +521,7 @@ void launch_qp(const Params &P, cudaStream_t s)
 void launch_update(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
-    int rows = N * NC;
+    int rows = N * con_rows(P.o);
     if ((N + 1) * 7 > rows) rows = (N + 1) * 7;
     dim3 grid((P.B + 127) / 128, rows);
     update_kernel<<<grid, 128, 0, s>>>(P);

@@ -85,6 +85,7 @@ class BatchSolver:
         if N is not None:
             self.opts.N = N
         self.B, self.N = int(B), int(self.opts.N)
+        self.nc = 12 if self.opts.con_set == 1 else NC      # inequality rows per stage (stride of lam / t)
         h = C.c_void_p()
         check(self.L.admpc_batch_create(C.byref(self.opts), self.B, int(device), C.byref(h)), "admpc_batch_create")
         self.h = h
@@ -97,6 +98,7 @@ class BatchSolver:
         self = cls.__new__(cls)
         self.L = _lib.load()
         self.opts, self.B, self.N = opts, int(B), int(opts.N)
+        self.nc = 12 if opts.con_set == 1 else NC
         self.h = C.c_void_p(handle)
         self._owner = False
         self._keep = []
@@ -207,7 +209,7 @@ class BatchSolver:
     def set_duals(self, pi=None, lam=None, t=None, sl=None, su=None):
         """Multipliers / slacks of the iterate (the other five fields of acados' load_iterate)."""
         B, N = self.B, self.N
-        a = [None if v is None else _f64(v, (B, N * w)) for v, w in ((pi, 7), (lam, NC), (t, NC), (sl, 2), (su, 2))]
+        a = [None if v is None else _f64(v, (B, N * w)) for v, w in ((pi, 7), (lam, self.nc), (t, self.nc), (sl, 2), (su, 2))]
         check(self.L.admpc_batch_set_duals(self.h, *[_dp(v) for v in a]), "set_duals")
 
     def reset(self):
@@ -286,10 +288,10 @@ class BatchSolver:
         return self._get(self.L.admpc_batch_get_pi, self.N * 7).reshape(self.B, self.N, 7)
 
     def get_lam(self):
-        return self._get(self.L.admpc_batch_get_lam, self.N * NC).reshape(self.B, self.N, NC)
+        return self._get(self.L.admpc_batch_get_lam, self.N * self.nc).reshape(self.B, self.N, self.nc)
 
     def get_t(self):
-        return self._get(self.L.admpc_batch_get_t, self.N * NC).reshape(self.B, self.N, NC)
+        return self._get(self.L.admpc_batch_get_t, self.N * self.nc).reshape(self.B, self.N, self.nc)
 
     def get_slacks(self):
         sl, su = np.empty((self.B, self.N * 2)), np.empty((self.B, self.N * 2))

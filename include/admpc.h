@@ -60,11 +60,16 @@ typedef struct admpc_opts {
     int gp_precision;      /* 0 (default): FP64 RBF kernel values; 1: opt-in FP32 exponential (ex2.approx on the fractional
                               part of the FP64 exponent, FP64 accumulation): relative error of every kernel value <= 2^-22,
                               see DESIGN.md 5 for the bound on A, B, b (model_fitting/gp.py:117-138) */
-    int reserved_;
+    int con_set;           /* inequality set: 0 = u0, u1 soft + steering angle hard ($A/ad_3d_optimizer.py:165-199, 10 rows per stage);
+                              1 = the Frenet variant's own set (fren_ad_3d_optimizer pyc; structure pinned by $A/debug.json: 12
+                              multipliers, 2 + 2 slacks per stage): u0 soft, u1 hard, e_y = x[1] in [lbx2, ubx2] hard, steering
+                              angle soft with the penalties zl[1], zu[1].  Rows [lbu0 lbu1 lbx_ey lbx_delta | ub.. | ls0 ls1 |
+                              us0 us1].  Needs model_variant = 1; solved by the dense thread-per-instance kernel */
     double dt;
     double W[9], We[7];
     double zl[2], zu[2], Zl[2], Zu[2];
     double lbu[2], ubu[2], lbx, ubx;
+    double lbx2, ubx2;     /* con_set = 1: hard bound on e_y, stages 1..N-1 (default -2 / 2) */
     double mass, lf, lr, iz, cf2, cr2;
     double mu0, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, lam_min, t_min, thr0, reg;
     double blend_min, blend_max;   /* kinematic/dynamic blend window on v_x: p = clamp((v_x - blend_min)/(blend_max - blend_min), 0, 1)

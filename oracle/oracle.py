@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 NX, NU, NC, NMAX, DZMAX, GPOUT_MAX = 7, 2, 10, 128, 8, 4
+NCS = 12      # storage rows per stage (ORC_NC); rows in use / stride = con_rows(o): 10 Cartesian set, 12 Frenet set
 
 
 class OrcOpts(C.Structure):
@@ -26,6 +27,7 @@ class OrcOpts(C.Structure):
         ("mu0", C.c_double), ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double),
         ("tol_comp", C.c_double), ("alpha_min", C.c_double), ("lam_min", C.c_double), ("t_min", C.c_double),
         ("thr0", C.c_double), ("reg", C.c_double),
+        ("con_set", C.c_int), ("lbx2", C.c_double), ("ubx2", C.c_double),
     ]
 
 
@@ -36,8 +38,8 @@ class OrcGp(C.Structure):
 
 class OrcIterate(C.Structure):
     _fields_ = [("x", C.c_double * ((NMAX + 1) * NX)), ("u", C.c_double * (NMAX * NU)),
-                ("pi", C.c_double * (NMAX * NX)), ("lam", C.c_double * (NMAX * NC)),
-                ("t", C.c_double * (NMAX * NC)), ("sl", C.c_double * (NMAX * NU)), ("su", C.c_double * (NMAX * NU))]
+                ("pi", C.c_double * (NMAX * NX)), ("lam", C.c_double * (NMAX * NCS)),
+                ("t", C.c_double * (NMAX * NCS)), ("sl", C.c_double * (NMAX * NU)), ("su", C.c_double * (NMAX * NU))]
 
 
 class OrcLin(C.Structure):
@@ -52,7 +54,7 @@ class OrcStats(C.Structure):
 
 class OrcQpSol(C.Structure):
     _fields_ = [("dx", C.c_double * ((NMAX + 1) * 7)), ("du", C.c_double * (NMAX * 2)), ("pi", C.c_double * (NMAX * 7)),
-                ("lam", C.c_double * (NMAX * NC)), ("t", C.c_double * (NMAX * NC)),
+                ("lam", C.c_double * (NMAX * NCS)), ("t", C.c_double * (NMAX * NCS)),
                 ("sl", C.c_double * (NMAX * 2)), ("su", C.c_double * (NMAX * 2))]
 
 
@@ -98,6 +100,7 @@ def lib():
         L = C.CDLL(so)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.orc_default_opts.argtypes = [C.POINTER(OrcOpts)]
+        L.orc_con_rows.argtypes = [C.POINTER(OrcOpts)]
         L.orc_model_jac.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, C.c_double, dp, C.c_double, dp, dp, dp]
         L.orc_gp_predict.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, dp]
         L.orc_rk4_sens.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, C.c_double, dp, C.c_double, dp, dp, dp]
@@ -134,6 +137,11 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+def con_rows(o):
+    """Inequality rows per stage of the configured constraint set (stride of lam / t)."""
+    return lib().orc_con_rows(C.byref(o))
 
 
 def default_opts(N=20, **kw):
@@ -244,7 +252,7 @@ def make_iterate(o, x=None, u=None):
 def iterate_arrays(o, it):
     N = o.N
     g = lambda f, n, w: np.array(f[:n * w]).reshape(n, w)
-    return dict(x=g(it.x, N + 1, 7), u=g(it.u, N, 2), pi=g(it.pi, N, 7), lam=g(it.lam, N, NC), t=g(it.t, N, NC),
+    return dict(x=g(it.x, N + 1, 7), u=g(it.u, N, 2), pi=g(it.pi, N, 7), lam=g(it.lam, N, con_rows(o)), t=g(it.t, N, con_rows(o)),
                 sl=g(it.sl, N, 2), su=g(it.su, N, 2))
 
 
@@ -266,8 +274,8 @@ def qp_solve(o, lin_c, it, x0):
     lib().orc_qp_solve(C.byref(o), C.byref(lin_c), C.byref(it), _dp(x0), C.byref(sol), C.byref(st))
     N = o.N
     g = lambda f, n, w: np.array(f[:n * w]).reshape(n, w)
-    return dict(dx=g(sol.dx, N + 1, 7), du=g(sol.du, N, 2), pi=g(sol.pi, N, 7), lam=g(sol.lam, N, NC),
-                t=g(sol.t, N, NC), sl=g(sol.sl, N, 2), su=g(sol.su, N, 2), qp_status=st.qp_status, qp_iter=st.qp_iter,
+    return dict(dx=g(sol.dx, N + 1, 7), du=g(sol.du, N, 2), pi=g(sol.pi, N, 7), lam=g(sol.lam, N, con_rows(o)),
+                t=g(sol.t, N, con_rows(o)), sl=g(sol.sl, N, 2), su=g(sol.su, N, 2), qp_status=st.qp_status, qp_iter=st.qp_iter,
                 res=np.array(st.res[:]))
 
 

@@ -49,6 +49,7 @@ void orc_default_opts(orc_opts *o)
     for (int j = 0; j < 2; j++) { o->zl[j] = 10; o->zu[j] = 10; o->Zl[j] = 0; o->Zu[j] = 0; }
     o->lbu[0] = -10; o->ubu[0] = 5; o->lbu[1] = -3; o->ubu[1] = 3;
     o->lbx = -0.52; o->ubx = 0.52;
+    o->con_set = 0; o->lbx2 = -2.0; o->ubx2 = 2.0;      /* e_y bound of the Frenet variant's set (con_set = 1) */
     /* ad_3d.py:47-60, evaluated literally (note the reference's 3.14195) */
     double mass = 1500, f_mass = 900, r_mass = mass - f_mass, L = 2.7;
     o->mass = mass;
@@ -349,52 +350,112 @@ static int prepare_impl(const orc_opts *o, const orc_gp *gp, const orc_iterate *
 }
 
 /* ------------------------------------------------------------------------------------------ QP (IPM) ------- */
+/* ---- constraint sets ------------------------------------------------------------------------------------------
+ * Bounded quantities q = 0..nb-1 of the stage vector z = [u0 u1 | x0..x6] (index idx[q]), each hard (two rows) or soft
+ * (slack id soft[q]: two more rows).  Row order per stage = acados / HPIPM order, as in the reference's iterate dumps:
+ *     [ lb(q = 0..nb-1) | ub(q = 0..nb-1) | ls(s = 0..ns-1) | us(s = 0..ns-1) ]
+ *   con_set 0 (ad_3d_optimizer.py:165-199, sim_car_iterate.json): u0 soft, u1 soft, x6 (delta) hard           -> 10 rows
+ *   con_set 1 (fren_ad_3d_optimizer pyc; ad_mpc/debug.json: 12 multipliers and 2 + 2 slacks per stage, lam_ls1 + lam_lbx_delta
+ *              = Ts zl at an active steering bound, lam_ubu1 active with no slack row): u0 soft, u1 hard, x1 (e_y) hard,
+ *              x6 (delta) soft                                                                                 -> 12 rows
+ * Bounds on states do not exist at stage 0 (x0 is eliminated), nor do their slacks; no terminal constraints. */
+typedef struct { int nb, ns, nc; int idx[4], soft[4]; double lo[4], hi[4]; } con_desc;
+static void con_get(const orc_opts *o, con_desc *d)
+{
+    memset(d, 0, sizeof(*d));
+    if (o->con_set == 1) {
+        d->nb = 4; d->ns = 2;
+        d->idx[0] = 0; d->idx[1] = 1; d->idx[2] = 3; d->idx[3] = 8;
+        d->soft[0] = 0; d->soft[1] = -1; d->soft[2] = -1; d->soft[3] = 1;
+        d->lo[0] = o->lbu[0]; d->hi[0] = o->ubu[0]; d->lo[1] = o->lbu[1]; d->hi[1] = o->ubu[1];
+        d->lo[2] = o->lbx2; d->hi[2] = o->ubx2; d->lo[3] = o->lbx; d->hi[3] = o->ubx;
+    } else {
+        d->nb = 3; d->ns = 2;
+        d->idx[0] = 0; d->idx[1] = 1; d->idx[2] = 8;
+        d->soft[0] = 0; d->soft[1] = 1; d->soft[2] = -1;
+        d->lo[0] = o->lbu[0]; d->hi[0] = o->ubu[0]; d->lo[1] = o->lbu[1]; d->hi[1] = o->ubu[1];
+        d->lo[2] = o->lbx; d->hi[2] = o->ubx;
+    }
+    d->nc = 2 * d->nb + 2 * d->ns;
+}
+int orc_con_rows(const orc_opts *o) { con_desc d; con_get(o, &d); return d.nc; }
+static inline int q_on(const con_desc *d, int k, int q) { return d->idx[q] < 2 || k >= 1; }
+/* quantity a row belongs to */
+static inline int row_q(const con_desc *d, int c)
+{
+    if (c < d->nb) return c;
+    if (c < 2 * d->nb) return c - d->nb;
+    int s = (c < 2 * d->nb + d->ns) ? c - 2 * d->nb : c - 2 * d->nb - d->ns;
+    for (int q = 0; q < d->nb; q++) if (d->soft[q] == s) return q;
+    return 0;
+}
+static inline int con_on(const con_desc *d, int k, int c) { return q_on(d, k, row_q(d, c)); }
+#define RL(q) (q)
+#define RU(q) (d->nb + (q))
+#define RLS(s) (2 * d->nb + (s))
+#define RUS(s) (2 * d->nb + d->ns + (s))
+
 typedef struct {
     /* Newton-step right-hand sides */
     double rgu[ORC_NMAX][2], rgx[ORC_NMAX + 1][7], rgsl[ORC_NMAX][2], rgsu[ORC_NMAX][2];
-    double rb[ORC_NMAX][7], rd[ORC_NMAX][NC], rm[ORC_NMAX][NC];
-    /* factorisation */
-    double Rt[ORC_NMAX][2], Qt6[ORC_NMAX + 1];
+    double rb[ORC_NMAX][7], rd[ORC_NMAX][ORC_NC], rm[ORC_NMAX][ORC_NC];
+    /* factorisation: barrier-modified diagonal of the stage Hessian over z = [u; x] */
+    double Hd[ORC_NMAX][9];
     double K[ORC_NMAX][14], Luu[ORC_NMAX][3], P[ORC_NMAX + 1][49];
     /* step */
-    double ddu[ORC_NMAX][2], ddx[ORC_NMAX + 1][7], dpi[ORC_NMAX][7], dlam[ORC_NMAX][NC], dt[ORC_NMAX][NC],
+    double ddu[ORC_NMAX][2], ddx[ORC_NMAX + 1][7], dpi[ORC_NMAX][7], dlam[ORC_NMAX][ORC_NC], dt[ORC_NMAX][ORC_NC],
         dsl[ORC_NMAX][2], dsu[ORC_NMAX][2];
 } ipm_ws;
 
-/* constraint activity mask: stage 0 has no state bound (x0 is eliminated, nbxe_0 = 7) */
-static inline int con_on(int k, int c) { return !((c == 2 || c == 5) && k == 0); }
-
-static void ipm_residuals(const orc_opts *o, const orc_lin *lin, const double *dlu, const double *duu,
-                          const double *dlx, const double *dux, const orc_qpsol *s, ipm_ws *w, double res[4],
-                          double *mu)
+/* value of the bounded quantity q of stage k in the current delta point */
+static inline double q_val(const con_desc *d, int q, const double *du, const double *dx)
 {
-    const int N = o->N;
+    return (d->idx[q] < 2) ? du[d->idx[q]] : dx[d->idx[q] - 2];
+}
+/* its linearisation point */
+static inline double q_bar(const con_desc *d, int q, const orc_iterate *it, int k)
+{
+    return (d->idx[q] < 2) ? it->u[k * 2 + d->idx[q]] : it->x[k * 7 + d->idx[q] - 2];
+}
+
+/* dlo / dhi [k][q]: bounds in delta form around the iterate */
+static void ipm_residuals(const orc_opts *o, const con_desc *d, const orc_lin *lin, const double (*dlo)[4],
+                          const double (*dhi)[4], const orc_qpsol *s, ipm_ws *w, double res[4], double *mu)
+{
+    const int N = o->N, nc = d->nc;
     const double Ts = o->dt;
     double ng = 0, nb = 0, nd = 0, nm = 0, summ = 0;
-    int nc = 0;
+    int ncon = 0;
     for (int k = 0; k <= N; k++) {
         const double *dx = s->dx + k * 7;
         if (k < N) {
             const double *A = lin->A + k * 49, *B = lin->B + k * 14;
-            const double *du = s->du + k * 2, *pi = s->pi + k * 7, *lam = s->lam + k * NC, *t = s->t + k * NC;
+            const double *du = s->du + k * 2, *pi = s->pi + k * 7, *lam = s->lam + k * nc, *t = s->t + k * nc;
             for (int j = 0; j < 2; j++) {
                 double g = Ts * o->W[7 + j] * du[j] + lin->r[k * 2 + j];
                 for (int l = 0; l < 7; l++) g += B[l * 2 + j] * pi[l];
-                g += -lam[j] + lam[3 + j];
+                for (int q = 0; q < d->nb; q++) if (d->idx[q] == j) g += -lam[RL(q)] + lam[RU(q)];
                 w->rgu[k][j] = g;
-                w->rgsl[k][j] = Ts * o->zl[j] + Ts * o->Zl[j] * s->sl[k * 2 + j] - lam[j] - lam[6 + j];
-                w->rgsu[k][j] = Ts * o->zu[j] + Ts * o->Zu[j] * s->su[k * 2 + j] - lam[3 + j] - lam[8 + j];
-                w->rd[k][j] = t[j] - (du[j] - dlu[k * 2 + j] + s->sl[k * 2 + j]);
-                w->rd[k][3 + j] = t[3 + j] - (duu[k * 2 + j] - du[j] + s->su[k * 2 + j]);
-                w->rd[k][6 + j] = t[6 + j] - s->sl[k * 2 + j];
-                w->rd[k][8 + j] = t[8 + j] - s->su[k * 2 + j];
-                ng = nanmax(ng, nanmax(fabs(g), nanmax(fabs(w->rgsl[k][j]), fabs(w->rgsu[k][j]))));
+                ng = nanmax(ng, fabs(g));
             }
-            if (k >= 1) {
-                w->rd[k][2] = t[2] - (dx[6] - dlx[k]);
-                w->rd[k][5] = t[5] - (dux[k] - dx[6]);
-            } else {
-                w->rd[k][2] = w->rd[k][5] = 0.0;
+            for (int c = 0; c < nc; c++) w->rd[k][c] = 0.0;
+            for (int q = 0; q < d->nb; q++) {
+                if (!q_on(d, k, q)) continue;
+                const double v = q_val(d, q, du, dx);
+                const int sq = d->soft[q];
+                if (sq >= 0) {
+                    const double sl = s->sl[k * 2 + sq], su = s->su[k * 2 + sq];
+                    w->rgsl[k][sq] = Ts * o->zl[sq] + Ts * o->Zl[sq] * sl - lam[RL(q)] - lam[RLS(sq)];
+                    w->rgsu[k][sq] = Ts * o->zu[sq] + Ts * o->Zu[sq] * su - lam[RU(q)] - lam[RUS(sq)];
+                    w->rd[k][RL(q)] = t[RL(q)] - (v - dlo[k][q] + sl);
+                    w->rd[k][RU(q)] = t[RU(q)] - (dhi[k][q] - v + su);
+                    w->rd[k][RLS(sq)] = t[RLS(sq)] - sl;
+                    w->rd[k][RUS(sq)] = t[RUS(sq)] - su;
+                    ng = nanmax(ng, nanmax(fabs(w->rgsl[k][sq]), fabs(w->rgsu[k][sq])));
+                } else {
+                    w->rd[k][RL(q)] = t[RL(q)] - (v - dlo[k][q]);
+                    w->rd[k][RU(q)] = t[RU(q)] - (dhi[k][q] - v);
+                }
             }
             for (int i = 0; i < 7; i++) {
                 double v = lin->b[k * 7 + i] - s->dx[(k + 1) * 7 + i];
@@ -403,25 +464,24 @@ static void ipm_residuals(const orc_opts *o, const orc_lin *lin, const double *d
                 w->rb[k][i] = v;
                 nb = nanmax(nb, fabs(v));
             }
-            for (int c = 0; c < NC; c++) {
-                if (!con_on(k, c)) { w->rm[k][c] = 0; continue; }
+            for (int c = 0; c < nc; c++) {
+                if (!con_on(d, k, c)) { w->rm[k][c] = 0; continue; }
                 w->rm[k][c] = lam[c] * t[c];
                 nd = nanmax(nd, fabs(w->rd[k][c]));
                 nm = nanmax(nm, fabs(w->rm[k][c]));
                 summ += w->rm[k][c];
-                nc++;
+                ncon++;
             }
         }
         if (k >= 1) {
-            const double Qk6 = (k < N) ? Ts * o->W[6] : o->We[6];
-            (void)Qk6;
             for (int i = 0; i < 7; i++) {
                 double Qd = (k < N) ? Ts * o->W[i] : o->We[i];
                 double g = Qd * dx[i] + lin->q[k * 7 + i] - s->pi[(k - 1) * 7 + i];
                 if (k < N) {
                     const double *A = lin->A + k * 49, *pi = s->pi + k * 7;
                     for (int l = 0; l < 7; l++) g += A[l * 7 + i] * pi[l];
-                    if (i == 6) g += -s->lam[k * NC + 2] + s->lam[k * NC + 5];
+                    for (int q = 0; q < d->nb; q++)
+                        if (d->idx[q] == 2 + i) g += -s->lam[k * nc + RL(q)] + s->lam[k * nc + RU(q)];
                 }
                 w->rgx[k][i] = g;
                 ng = nanmax(ng, fabs(g));
@@ -429,29 +489,41 @@ static void ipm_residuals(const orc_opts *o, const orc_lin *lin, const double *d
         }
     }
     res[0] = ng; res[1] = nb; res[2] = nd; res[3] = nm;
-    *mu = summ / nc;
+    *mu = summ / ncon;
+}
+
+/* barrier scalings of one bounded quantity */
+typedef struct { double Sl, Su, Dl, Du; } q_scal;
+static inline void q_scaling(const orc_opts *o, const con_desc *d, int q, const double *lam, const double *t, q_scal *S)
+{
+    const double Ts = o->dt;
+    const int sq = d->soft[q];
+    S->Sl = lam[RL(q)] / t[RL(q)]; S->Su = lam[RU(q)] / t[RU(q)];
+    if (sq >= 0) {
+        const double Ssl = lam[RLS(sq)] / t[RLS(sq)], Ssu = lam[RUS(sq)] / t[RUS(sq)];
+        S->Dl = Ts * o->Zl[sq] + S->Sl + Ssl; S->Du = Ts * o->Zu[sq] + S->Su + Ssu;
+    } else { S->Dl = 0; S->Du = 0; }
 }
 
 /* Riccati factorisation for the barrier-modified Hessian (matrix part only). */
-static void ipm_factor(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
+static void ipm_factor(const orc_opts *o, const con_desc *d, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
 {
-    const int N = o->N;
+    const int N = o->N, nc = d->nc;
     const double Ts = o->dt;
     /* barrier terms with soft-bound slacks eliminated */
     for (int k = 0; k < N; k++) {
-        const double *lam = s->lam + k * NC, *t = s->t + k * NC;
-        for (int j = 0; j < 2; j++) {
-            double Sl = lam[j] / t[j], Su = lam[3 + j] / t[3 + j], Ssl = lam[6 + j] / t[6 + j],
-                   Ssu = lam[8 + j] / t[8 + j];
-            double Dl = Ts * o->Zl[j] + Sl + Ssl, Du = Ts * o->Zu[j] + Su + Ssu;
-            w->Rt[k][j] = Ts * o->W[7 + j] + Sl * (1.0 - Sl / Dl) + Su * (1.0 - Su / Du);
+        const double *lam = s->lam + k * nc, *t = s->t + k * nc;
+        for (int z = 0; z < 9; z++) w->Hd[k][z] = (z < 2) ? Ts * o->W[7 + z] : Ts * o->W[z - 2];
+        for (int q = 0; q < d->nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            q_scal S; q_scaling(o, d, q, lam, t, &S);
+            if (d->soft[q] >= 0) w->Hd[k][d->idx[q]] = w->Hd[k][d->idx[q]] + S.Sl * (1.0 - S.Sl / S.Dl) + S.Su * (1.0 - S.Su / S.Du);
+            else w->Hd[k][d->idx[q]] = w->Hd[k][d->idx[q]] + (S.Sl + S.Su);
         }
-        w->Qt6[k] = Ts * o->W[6] + (k >= 1 ? lam[2] / t[2] + lam[5] / t[5] : 0.0);
     }
-    w->Qt6[N] = o->We[6];
     double *P = w->P[N];
     memset(P, 0, 49 * sizeof(double));
-    for (int i = 0; i < 7; i++) P[i * 7 + i] = (i == 6) ? w->Qt6[N] : o->We[i];
+    for (int i = 0; i < 7; i++) P[i * 7 + i] = o->We[i];
     for (int k = N - 1; k >= 0; k--) {
         const double *A = lin->A + k * 49, *B = lin->B + k * 14;
         const double *Pn = w->P[k + 1];
@@ -470,8 +542,7 @@ static void ipm_factor(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s
             for (int l = 0; l < 7; l++) v += BA[l][a] * PBA[l][c];
             G[a][c] = v;
         }
-        G[0][0] += w->Rt[k][0]; G[1][1] += w->Rt[k][1];
-        for (int i = 0; i < 7; i++) G[2 + i][2 + i] += (i == 6) ? w->Qt6[k] : Ts * o->W[i];
+        for (int z = 0; z < 9; z++) G[z][z] += w->Hd[k][z];
         /* Cholesky of the 2x2 input block */
         double l00 = sqrt(G[0][0] + o->reg), l10 = G[1][0] / l00, l11 = sqrt(G[1][1] + o->reg - l10 * l10);
         w->Luu[k][0] = l00; w->Luu[k][1] = l10; w->Luu[k][2] = l11;
@@ -492,25 +563,29 @@ static void ipm_factor(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s
 }
 
 /* Solve for the Newton step given the complementarity right-hand side w->rm (vector part of the Riccati). */
-static void ipm_solve(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
+static void ipm_solve(const orc_opts *o, const con_desc *d, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
 {
-    const int N = o->N;
-    const double Ts = o->dt;
-    double gl[ORC_NMAX][NC], rt[ORC_NMAX][2], qt6[ORC_NMAX], cl[ORC_NMAX][2], cu[ORC_NMAX][2],
-        Dl[ORC_NMAX][2], Du[ORC_NMAX][2];
+    const int N = o->N, nc = d->nc;
+    double gl[ORC_NMAX][ORC_NC], rt[ORC_NMAX][2], qx[ORC_NMAX][7], cl[ORC_NMAX][2], cu[ORC_NMAX][2];
+    q_scal S[ORC_NMAX][4];
     for (int k = 0; k < N; k++) {
-        const double *lam = s->lam + k * NC, *t = s->t + k * NC;
-        for (int c = 0; c < NC; c++) gl[k][c] = con_on(k, c) ? (w->rm[k][c] - lam[c] * w->rd[k][c]) / t[c] : 0.0;
-        for (int j = 0; j < 2; j++) {
-            double Sl = lam[j] / t[j], Su = lam[3 + j] / t[3 + j], Ssl = lam[6 + j] / t[6 + j],
-                   Ssu = lam[8 + j] / t[8 + j];
-            Dl[k][j] = Ts * o->Zl[j] + Sl + Ssl;
-            Du[k][j] = Ts * o->Zu[j] + Su + Ssu;
-            cl[k][j] = w->rgsl[k][j] + gl[k][j] + gl[k][6 + j];
-            cu[k][j] = w->rgsu[k][j] + gl[k][3 + j] + gl[k][8 + j];
-            rt[k][j] = w->rgu[k][j] + (gl[k][j] - Sl * cl[k][j] / Dl[k][j]) - (gl[k][3 + j] - Su * cu[k][j] / Du[k][j]);
+        const double *lam = s->lam + k * nc, *t = s->t + k * nc;
+        for (int c = 0; c < nc; c++) gl[k][c] = con_on(d, k, c) ? (w->rm[k][c] - lam[c] * w->rd[k][c]) / t[c] : 0.0;
+        for (int j = 0; j < 2; j++) rt[k][j] = w->rgu[k][j];
+        for (int i = 0; i < 7; i++) qx[k][i] = (k >= 1) ? w->rgx[k][i] : 0.0;
+        for (int q = 0; q < d->nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            q_scaling(o, d, q, lam, t, &S[k][q]);
+            double *gq = (d->idx[q] < 2) ? &rt[k][d->idx[q]] : &qx[k][d->idx[q] - 2];
+            const int sq = d->soft[q];
+            if (sq >= 0) {
+                cl[k][sq] = w->rgsl[k][sq] + gl[k][RL(q)] + gl[k][RLS(sq)];
+                cu[k][sq] = w->rgsu[k][sq] + gl[k][RU(q)] + gl[k][RUS(sq)];
+                *gq = *gq + (gl[k][RL(q)] - S[k][q].Sl * cl[k][sq] / S[k][q].Dl) - (gl[k][RU(q)] - S[k][q].Su * cu[k][sq] / S[k][q].Du);
+            } else {
+                *gq = *gq + gl[k][RL(q)] - gl[k][RU(q)];
+            }
         }
-        qt6[k] = (k >= 1) ? w->rgx[k][6] + gl[k][2] - gl[k][5] : 0.0;
     }
     /* backward vector recursion */
     double pv[ORC_NMAX + 1][7], kf[ORC_NMAX][2];
@@ -529,7 +604,7 @@ static void ipm_solve(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s,
             gu[j] = v;
         }
         for (int i = 0; i < 7; i++) {
-            double v = (k >= 1) ? ((i == 6) ? qt6[k] : w->rgx[k][i]) : 0.0;
+            double v = qx[k][i];
             for (int l = 0; l < 7; l++) v += A[l * 7 + i] * h[l];
             gx[i] = v;
         }
@@ -563,99 +638,108 @@ static void ipm_solve(const orc_opts *o, const orc_lin *lin, const orc_qpsol *s,
     }
     /* recover slack, t and lambda steps */
     for (int k = 0; k < N; k++) {
-        const double *lam = s->lam + k * NC, *t = s->t + k * NC;
-        for (int j = 0; j < 2; j++) {
-            double Sl = lam[j] / t[j], Su = lam[3 + j] / t[3 + j];
-            w->dsl[k][j] = -(cl[k][j] + Sl * w->ddu[k][j]) / Dl[k][j];
-            w->dsu[k][j] = -(cu[k][j] - Su * w->ddu[k][j]) / Du[k][j];
-            w->dt[k][j] = w->ddu[k][j] + w->dsl[k][j] - w->rd[k][j];
-            w->dt[k][3 + j] = -w->ddu[k][j] + w->dsu[k][j] - w->rd[k][3 + j];
-            w->dt[k][6 + j] = w->dsl[k][j] - w->rd[k][6 + j];
-            w->dt[k][8 + j] = w->dsu[k][j] - w->rd[k][8 + j];
+        const double *lam = s->lam + k * nc, *t = s->t + k * nc;
+        for (int c = 0; c < nc; c++) w->dt[k][c] = 0.0;
+        for (int sq = 0; sq < 2; sq++) { w->dsl[k][sq] = 0.0; w->dsu[k][sq] = 0.0; }
+        for (int q = 0; q < d->nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            const double dv = q_val(d, q, w->ddu[k], w->ddx[k]);
+            const int sq = d->soft[q];
+            if (sq >= 0) {
+                w->dsl[k][sq] = -(cl[k][sq] + S[k][q].Sl * dv) / S[k][q].Dl;
+                w->dsu[k][sq] = -(cu[k][sq] - S[k][q].Su * dv) / S[k][q].Du;
+                w->dt[k][RL(q)] = dv + w->dsl[k][sq] - w->rd[k][RL(q)];
+                w->dt[k][RU(q)] = -dv + w->dsu[k][sq] - w->rd[k][RU(q)];
+                w->dt[k][RLS(sq)] = w->dsl[k][sq] - w->rd[k][RLS(sq)];
+                w->dt[k][RUS(sq)] = w->dsu[k][sq] - w->rd[k][RUS(sq)];
+            } else {
+                w->dt[k][RL(q)] = dv - w->rd[k][RL(q)];
+                w->dt[k][RU(q)] = -dv - w->rd[k][RU(q)];
+            }
         }
-        if (k >= 1) {
-            w->dt[k][2] = w->ddx[k][6] - w->rd[k][2];
-            w->dt[k][5] = -w->ddx[k][6] - w->rd[k][5];
-        } else {
-            w->dt[k][2] = w->dt[k][5] = 0.0;
-        }
-        for (int c = 0; c < NC; c++)
-            w->dlam[k][c] = con_on(k, c) ? -(w->rm[k][c] + lam[c] * w->dt[k][c]) / t[c] : 0.0;
+        for (int c = 0; c < nc; c++)
+            w->dlam[k][c] = con_on(d, k, c) ? -(w->rm[k][c] + lam[c] * w->dt[k][c]) / t[c] : 0.0;
     }
 }
 
-static double ipm_alpha(const orc_opts *o, const orc_qpsol *s, const ipm_ws *w)
+static double ipm_alpha(const orc_opts *o, const con_desc *d, const orc_qpsol *s, const ipm_ws *w)
 {
+    const int nc = d->nc;
     double a = 1.0;
-    for (int k = 0; k < o->N; k++) for (int c = 0; c < NC; c++) {
-        if (!con_on(k, c)) continue;
-        double l = s->lam[k * NC + c], t = s->t[k * NC + c], dl = w->dlam[k][c], dt = w->dt[k][c];
+    for (int k = 0; k < o->N; k++) for (int c = 0; c < nc; c++) {
+        if (!con_on(d, k, c)) continue;
+        double l = s->lam[k * nc + c], t = s->t[k * nc + c], dl = w->dlam[k][c], dt = w->dt[k][c];
         if (dl < 0 && -l / dl < a) a = -l / dl;
         if (dt < 0 && -t / dt < a) a = -t / dt;
     }
     return a;
 }
 
+static void delta_bounds(const con_desc *d, const orc_iterate *it, int N, double (*dlo)[4], double (*dhi)[4])
+{
+    for (int k = 0; k < N; k++) for (int q = 0; q < d->nb; q++) {
+        const double bar = q_bar(d, q, it, k);
+        dlo[k][q] = d->lo[q] - bar;
+        dhi[k][q] = d->hi[q] - bar;
+    }
+}
+
 int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0,
                  orc_qpsol *s, orc_stats *st)
 {
     const int N = o->N;
+    con_desc dd; con_get(o, &dd);
+    const con_desc *d = &dd;
+    const int nc = d->nc;
     ipm_ws *w = (ipm_ws *)malloc(sizeof(ipm_ws));
-    double dlu[ORC_NMAX * 2], duu[ORC_NMAX * 2], dlx[ORC_NMAX], dux[ORC_NMAX];
+    double dlo[ORC_NMAX][4], dhi[ORC_NMAX][4];
     memset(s, 0, sizeof(*s));
-    /* bounds in delta form around the iterate */
-    for (int k = 0; k < N; k++) {
-        for (int j = 0; j < 2; j++) {
-            dlu[k * 2 + j] = o->lbu[j] - it->u[k * 2 + j];
-            duu[k * 2 + j] = o->ubu[j] - it->u[k * 2 + j];
-        }
-        dlx[k] = o->lbx - it->x[k * 7 + 6];
-        dux[k] = o->ubx - it->x[k * 7 + 6];
-    }
+    delta_bounds(d, it, N, dlo, dhi);            /* bounds in delta form around the iterate */
     /* cold start (qp_solver_warm_start 0, sim_car_acados_ocp.json:885): primal 0 pushed thr0 inside its box */
     for (int i = 0; i < 7; i++) s->dx[i] = x0[i] - it->x[i];     /* lbx_0 = ubx_0 = x0, eliminated (nbxe_0) */
     for (int k = 0; k < N; k++) {
-        double *t = s->t + k * NC, *lam = s->lam + k * NC;
-        for (int j = 0; j < 3; j++) {
-            if (j == 2 && k == 0) { t[2] = t[5] = 1.0; lam[2] = lam[5] = 0.0; continue; }
-            double lo = (j < 2) ? dlu[k * 2 + j] : dlx[k], hi = (j < 2) ? duu[k * 2 + j] : dux[k];
+        double *t = s->t + k * nc, *lam = s->lam + k * nc;
+        for (int c = 0; c < nc; c++) { t[c] = 1.0; lam[c] = 0.0; }
+        for (int q = 0; q < d->nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            double lo = dlo[k][q], hi = dhi[k][q];
             double v = 0.0;
             if (v - lo < o->thr0) {
                 if (hi - v < o->thr0) v = 0.5 * (lo + hi);
                 else v = lo + o->thr0;
             } else if (hi - v < o->thr0) v = hi - o->thr0;
-            if (j < 2) s->du[k * 2 + j] = v; else s->dx[k * 7 + 6] = v;
-            t[j] = fmax(o->thr0, v - lo);
-            t[3 + j] = fmax(o->thr0, hi - v);
+            if (d->idx[q] < 2) s->du[k * 2 + d->idx[q]] = v; else s->dx[k * 7 + d->idx[q] - 2] = v;
+            t[RL(q)] = fmax(o->thr0, v - lo);
+            t[RU(q)] = fmax(o->thr0, hi - v);
+            if (d->soft[q] >= 0) { t[RLS(d->soft[q])] = o->thr0; t[RUS(d->soft[q])] = o->thr0; }
         }
-        for (int j = 0; j < 2; j++) { t[6 + j] = o->thr0; t[8 + j] = o->thr0; }
-        for (int c = 0; c < NC; c++) if (con_on(k, c)) lam[c] = o->mu0 / t[c];
+        for (int c = 0; c < nc; c++) if (con_on(d, k, c)) lam[c] = o->mu0 / t[c];
     }
     int status = 1, iter = 0;
     double res[4] = {0}, mu = 0;
     for (iter = 0;; iter++) {
-        ipm_residuals(o, lin, dlu, duu, dlx, dux, s, w, res, &mu);
+        ipm_residuals(o, d, lin, dlo, dhi, s, w, res, &mu);
         if (!(isfinite(res[0]) && isfinite(res[1]) && isfinite(res[2]) && isfinite(res[3]))) { status = 3; break; }
         if (res[0] < o->tol_stat && res[1] < o->tol_eq && res[2] < o->tol_ineq && res[3] < o->tol_comp) {
             status = 0; break;
         }
         if (iter >= o->iter_max) { status = 1; break; }
         /* predictor (affine scaling) */
-        ipm_factor(o, lin, s, w);
-        ipm_solve(o, lin, s, w);
-        double a_aff = ipm_alpha(o, s, w);
-        double mu_aff = 0; int nc = 0;
-        for (int k = 0; k < N; k++) for (int c = 0; c < NC; c++) if (con_on(k, c)) {
-            mu_aff += (s->lam[k * NC + c] + a_aff * w->dlam[k][c]) * (s->t[k * NC + c] + a_aff * w->dt[k][c]);
-            nc++;
+        ipm_factor(o, d, lin, s, w);
+        ipm_solve(o, d, lin, s, w);
+        double a_aff = ipm_alpha(o, d, s, w);
+        double mu_aff = 0; int ncon = 0;
+        for (int k = 0; k < N; k++) for (int c = 0; c < nc; c++) if (con_on(d, k, c)) {
+            mu_aff += (s->lam[k * nc + c] + a_aff * w->dlam[k][c]) * (s->t[k * nc + c] + a_aff * w->dt[k][c]);
+            ncon++;
         }
-        mu_aff /= nc;
+        mu_aff /= ncon;
         double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
         /* corrector */
-        for (int k = 0; k < N; k++) for (int c = 0; c < NC; c++) if (con_on(k, c))
-            w->rm[k][c] = s->lam[k * NC + c] * s->t[k * NC + c] + w->dlam[k][c] * w->dt[k][c] - sigma * mu;
-        ipm_solve(o, lin, s, w);
-        double alpha = ipm_alpha(o, s, w);
+        for (int k = 0; k < N; k++) for (int c = 0; c < nc; c++) if (con_on(d, k, c))
+            w->rm[k][c] = s->lam[k * nc + c] * s->t[k * nc + c] + w->dlam[k][c] * w->dt[k][c] - sigma * mu;
+        ipm_solve(o, d, lin, s, w);
+        double alpha = ipm_alpha(o, d, s, w);
         if (alpha < o->alpha_min) { status = 2; break; }
         if (alpha < 1.0) alpha *= 0.995;
         for (int k = 0; k < N; k++) {
@@ -668,9 +752,9 @@ int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, c
                 s->dx[(k + 1) * 7 + i] += alpha * w->ddx[k + 1][i];
                 s->pi[k * 7 + i] += alpha * w->dpi[k][i];
             }
-            for (int c = 0; c < NC; c++) if (con_on(k, c)) {
-                s->lam[k * NC + c] = fmax(s->lam[k * NC + c] + alpha * w->dlam[k][c], o->lam_min);
-                s->t[k * NC + c] = fmax(s->t[k * NC + c] + alpha * w->dt[k][c], o->t_min);
+            for (int c = 0; c < nc; c++) if (con_on(d, k, c)) {
+                s->lam[k * nc + c] = fmax(s->lam[k * nc + c] + alpha * w->dlam[k][c], o->lam_min);
+                s->t[k * nc + c] = fmax(s->t[k * nc + c] + alpha * w->dt[k][c], o->t_min);
             }
         }
     }
@@ -722,8 +806,8 @@ static int rti_step_impl(const orc_opts *o, const orc_gp *gp, const double *x0, 
         for (int i = 0; i < (N + 1) * 7; i++) it->x[i] += sol->dx[i];
         for (int i = 0; i < N * 2; i++) it->u[i] += sol->du[i];
         memcpy(it->pi, sol->pi, sizeof(double) * N * 7);
-        memcpy(it->lam, sol->lam, sizeof(double) * N * NC);
-        memcpy(it->t, sol->t, sizeof(double) * N * NC);
+        memcpy(it->lam, sol->lam, sizeof(double) * N * orc_con_rows(o));
+        memcpy(it->t, sol->t, sizeof(double) * N * orc_con_rows(o));
         memcpy(it->sl, sol->sl, sizeof(double) * N * 2);
         memcpy(it->su, sol->su, sizeof(double) * N * 2);
     }
@@ -738,23 +822,18 @@ static int rti_step_impl(const orc_opts *o, const orc_gp *gp, const double *x0, 
 void orc_nlp_residuals(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0, double res[4])
 {
     const int N = o->N;
+    con_desc dd; con_get(o, &dd);
+    const con_desc *d = &dd;
     ipm_ws *w = (ipm_ws *)malloc(sizeof(ipm_ws));
     orc_qpsol *s = (orc_qpsol *)calloc(1, sizeof(orc_qpsol));
-    double dlu[ORC_NMAX * 2], duu[ORC_NMAX * 2], dlx[ORC_NMAX], dux[ORC_NMAX], mu;
-    for (int k = 0; k < N; k++) {
-        for (int j = 0; j < 2; j++) {
-            dlu[k * 2 + j] = o->lbu[j] - it->u[k * 2 + j];
-            duu[k * 2 + j] = o->ubu[j] - it->u[k * 2 + j];
-        }
-        dlx[k] = o->lbx - it->x[k * 7 + 6];
-        dux[k] = o->ubx - it->x[k * 7 + 6];
-    }
+    double dlo[ORC_NMAX][4], dhi[ORC_NMAX][4], mu;
+    delta_bounds(d, it, N, dlo, dhi);
     memcpy(s->pi, it->pi, sizeof(double) * N * 7);
-    memcpy(s->lam, it->lam, sizeof(double) * N * NC);
-    memcpy(s->t, it->t, sizeof(double) * N * NC);
+    memcpy(s->lam, it->lam, sizeof(double) * N * d->nc);
+    memcpy(s->t, it->t, sizeof(double) * N * d->nc);
     memcpy(s->sl, it->sl, sizeof(double) * N * 2);
     memcpy(s->su, it->su, sizeof(double) * N * 2);
-    ipm_residuals(o, lin, dlu, duu, dlx, dux, s, w, res, &mu);
+    ipm_residuals(o, d, lin, dlo, dhi, s, w, res, &mu);
     /* the initial-state mismatch is an equality residual of the NLP (x_0 = x0 is a constraint of the OCP) */
     for (int i = 0; i < 7; i++) res[1] = nanmax(res[1], fabs(x0[i] - it->x[i]));
     free(w); free(s);
@@ -792,8 +871,8 @@ static int sqp_solve_impl(const orc_opts *o, const orc_gp *gp, const double *x0,
         for (int i = 0; i < (N + 1) * 7; i++) it->x[i] += sol->dx[i];
         for (int i = 0; i < N * 2; i++) it->u[i] += sol->du[i];
         memcpy(it->pi, sol->pi, sizeof(double) * N * 7);
-        memcpy(it->lam, sol->lam, sizeof(double) * N * NC);
-        memcpy(it->t, sol->t, sizeof(double) * N * NC);
+        memcpy(it->lam, sol->lam, sizeof(double) * N * orc_con_rows(o));
+        memcpy(it->t, sol->t, sizeof(double) * N * orc_con_rows(o));
         memcpy(it->sl, sol->sl, sizeof(double) * N * 2);
         memcpy(it->su, sol->su, sizeof(double) * N * 2);
     }

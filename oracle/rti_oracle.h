@@ -27,7 +27,8 @@ extern "C" {
 
 #define ORC_NX 7
 #define ORC_NU 2
-#define ORC_NC 10      /* per-stage inequality rows: [lbu0 lbu1 lbx | ubu0 ubu1 ubx | ls0 ls1 | us0 us1] */
+#define ORC_NC 12      /* storage rows per stage; the rows in use and their stride = orc_con_rows(): 10 for the Cartesian set
+                          [lbu0 lbu1 lbx | ubu0 ubu1 ubx | ls0 ls1 | us0 us1], 12 for the Frenet set (rti_oracle.c con_get) */
 #define ORC_NMAX 128   /* max horizon */
 #define ORC_DZMAX 8
 #define ORC_GPOUT_MAX 4
@@ -52,6 +53,9 @@ typedef struct orc_opts {
     double lbx, ubx;                     /* hard bound on x[6], stages 1..N-1        .c:595-596 */
     double mass, lf, lr, iz, cf2, cr2;   /* vehicle: m, L_F, L_R, Iz, 2Cf, 2Cr       ad_3d.py:47-60 */
     double mu0, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, lam_min, t_min, thr0, reg;
+    int con_set;          /* 0: u0, u1 soft + delta hard (ad_3d_optimizer.py:165-199) ; 1: the Frenet variant's set: u0 soft, u1 hard,
+                             e_y = x[1] in [lbx2, ubx2] hard, delta soft (fren_ad_3d_optimizer pyc, structure pinned by ad_mpc/debug.json) */
+    double lbx2, ubx2;
 } orc_opts;
 
 /* GP model, one per output j (gp.py:495-508 pickle schema: x_train, k_inv_y, kernel_params{l,sigma_f}, y_mean):
@@ -92,6 +96,7 @@ typedef struct orc_stats {
 } orc_stats;
 
 void orc_default_opts(orc_opts *o);
+int orc_con_rows(const orc_opts *o);   /* inequality rows per stage of the configured constraint set = stride of lam / t */
 
 /* model */
 void orc_ode(const orc_opts *o, const orc_gp *gp, const double *x, const double *u, double p,

@@ -241,3 +241,90 @@ def test_frenet_spline_curvature_inside_the_model(B, N):
     g4 = _step(s, batch, kappa=np.full((B, N), 0.02))
     assert np.array_equal(g3["qp_iter"], g4["qp_iter"]) and mixed_err(g3["u"], g4["u"]) <= TOL
     s.close()
+
+
+def _frenet_own_opts(N, **kw):
+    """The Frenet variant's own OCP (SURVEY 8a A2' + ad_mpc/debug.json): weights q = [0,10,10,10,10,1,0.1], r = [10,10],
+    W_e = 0.01 Q, steering rate in [-2, 2] hard, acceleration soft, e_y in [-2, 2] hard, steering angle soft, zl = zu = 100."""
+    q = [0.0, 10.0, 10.0, 10.0, 10.0, 1.0, 0.1]
+    return default_opts(N, model_variant=1, con_set=1, W=q + [10.0, 10.0], We=[0.01 * v for v in q], zl=[100.0, 100.0],
+                        zu=[100.0, 100.0], lbu=[-10.0, -2.0], ubu=[5.0, 2.0], lbx=-0.52, ubx=0.52, lbx2=-2.0, ubx2=2.0, **kw)
+
+
+@pytest.mark.parametrize("B,N,tight", [(48, 20, False), (40, 20, True), (17, 40, True)])
+def test_frenet_own_constraint_set_parity(B, N, tight):
+    """con_set = 1: u0 soft, u1 hard, e_y hard, steering angle soft (12 rows per stage), against the oracle's generic
+    constraint-set IPM; `tight` shrinks the boxes so that the hard e_y bound, the hard steering-rate bound and the soft
+    steering-angle bound are all active somewhere in the batch."""
+    batch = wl.make_batch_frenet(B, N, seed=360 + B, p=1.0, perturb=3.0)
+    kw = dict(lbx2=-0.6, ubx2=0.6, lbu=[-2.0, -0.5], ubu=[1.5, 0.5], lbx=-0.08, ubx=0.08) if tight else {}
+    opts = _frenet_own_opts(N)
+    for k, v in kw.items():
+        cur = getattr(opts, k)
+        if hasattr(cur, "__len__"):
+            for i, vi in enumerate(v):
+                cur[i] = vi
+        else:
+            setattr(opts, k, v)
+    if tight:                                           # iterate inside the hard boxes (an interior point exists)
+        batch["x_init"][:, :, 1] = np.clip(batch["x_init"][:, :, 1], -0.5, 0.5)
+        batch["x0"][:, 1] = np.clip(batch["x0"][:, 1], -0.5, 0.5)
+    s = BatchSolver(B, opts)
+    g = _step(s, batch, kappa=batch["kappa"])
+    r = orc.rti_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=batch["kappa"])
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_status"], r["qp_status"])
+    good = r["status"] == 0             # (an infeasible instance ends in a minimum-step failure after a rounding-dependent count)
+    assert np.array_equal(g["qp_iter"][good], r["qp_iter"][good])
+    assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL
+    assert mixed_err(g["pi"][good], r["pi"][good]) <= 1e-6
+    lam, t = s.get_lam(), s.get_t()
+    assert lam.shape == (B, N, 12) and t.shape == (B, N, 12)
+    ok = g["status"] == 0
+    assert ok.any()
+    if tight:
+        # hard rows active: steering rate (rows 1 / 5) and e_y (rows 2 / 6) ; soft steering angle: lam_ls1 + lam_lbx_delta = Ts zl
+        assert (lam[ok][:, :, [1, 5]] > 1e-3).any() and (lam[ok][:, 1:, [2, 6]] > 1e-3).any()
+        assert (lam[ok][:, 1:, [3, 7]] > 1e-3).any()
+    Tz = opts.dt * 100.0
+    assert np.abs(lam[ok][:, 1:, 3] + lam[ok][:, 1:, 9] - Tz).max() < 1e-6      # slack stationarity of the soft steering angle
+    assert np.abs(lam[ok][:, :, 0] + lam[ok][:, :, 8] - Tz).max() < 1e-6       # ... of the soft acceleration
+    # second (warm) step from the updated iterate
+    s.solve()
+    r2 = orc.rti_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], r["x"], r["u"], kappa=batch["kappa"])
+    assert np.array_equal(s.get_status()[0], r2["status"])
+    assert mixed_err(s.get_u(), r2["u"]) <= TOL
+    s.close()
+
+
+def test_frenet_own_constraint_set_full_sqp_and_spline_curvature():
+    """The variant as the reference defines it end to end: kappa(s) spline inside the model + its own constraint set, SQP mode."""
+    from ad_mpc_b200.solver import kappa_pp_from_knots
+    B, N = 24, 20
+    batch = wl.make_batch_frenet(B, N, seed=371, p=1.0, perturb=2.0)
+    opts = _frenet_own_opts(N)
+    s_knots = np.linspace(-50.0, 450.0, 26)
+    rng = np.random.default_rng(5)
+    brk, cf = [], []
+    for b in range(B):
+        bb, cc = kappa_pp_from_knots(s_knots, 0.02 + 0.01 * np.sin(0.03 * s_knots + rng.uniform(0, 6.28)))
+        brk.append(bb); cf.append(cc)
+    brk, cf = np.stack(brk), np.stack(cf)
+    s = BatchSolver(B, opts)
+    s.set_iterate(batch["x_init"], batch["u_init"])
+    s.set_x0(batch["x0"]); s.set_yref(batch["yref"]); s.set_p(batch["p"]); s.set_kappa(batch["kappa"])
+    s.set_kappa_spline(brk, cf)
+    g = s.solve_sqp()
+    orc.set_batch_kappa_spline(brk, cf)
+    try:
+        r = orc.sqp_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=batch["kappa"])
+    finally:
+        orc.set_batch_kappa_spline(None)
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["sqp_iter"], r["sqp_iter"])
+    assert mixed_err(s.get_u(), r["u"]) <= TOL and mixed_err(s.get_x(), r["x"]) <= TOL
+    s.close()
+
+
+def test_con_set_1_needs_the_frenet_model():
+    from ad_mpc_b200 import _lib
+    with pytest.raises(_lib.AdmpcError):
+        BatchSolver(4, default_opts(20, con_set=1))

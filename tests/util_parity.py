@@ -5,7 +5,7 @@ from oracle import oracle as orc
 
 OPT_FIELDS = ["N", "iter_max", "dt", "W", "We", "zl", "zu", "Zl", "Zu", "lbu", "ubu", "lbx", "ubx", "mass", "lf", "lr",
               "iz", "cf2", "cr2", "mu0", "tol_stat", "tol_eq", "tol_ineq", "tol_comp", "alpha_min", "lam_min", "t_min",
-              "thr0", "reg"]
+              "thr0", "reg", "con_set", "lbx2", "ubx2"]
 
 
 def mirror_opts(gpu_opts):
