@@ -101,6 +101,7 @@ def lib():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.orc_default_opts.argtypes = [C.POINTER(OrcOpts)]
         L.orc_con_rows.argtypes = [C.POINTER(OrcOpts)]
+        L.orc_con_check.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcIterate), dp]
         L.orc_model_jac.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, C.c_double, dp, C.c_double, dp, dp, dp]
         L.orc_gp_predict.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, dp]
         L.orc_rk4_sens.argtypes = [C.POINTER(OrcOpts), C.POINTER(OrcGp), dp, dp, C.c_double, dp, C.c_double, dp, dp, dp]
@@ -247,6 +248,22 @@ def make_iterate(o, x=None, u=None):
     if u is not None:
         it.u[:N * 2] = list(np.asarray(u, dtype=np.float64).reshape(-1))
     return it
+
+
+def set_iterate_duals(o, it, lam=None, t=None, sl=None, su=None, pi=None):
+    """Fill the dual part of an iterate: lam, t [N, con_rows(o)], sl, su [N, 2], pi [N, 7]."""
+    N = o.N
+    for name, a, w in (("lam", lam, con_rows(o)), ("t", t, con_rows(o)), ("sl", sl, 2), ("su", su, 2), ("pi", pi, 7)):
+        if a is not None:
+            getattr(it, name)[:N * w] = list(np.asarray(a, dtype=np.float64).reshape(N * w))
+    return it
+
+
+def con_check(o, it):
+    """(max |t - constraint function|, max |slack stationarity|, max |lam t|) of an iterate, model-independent."""
+    out = np.zeros(3)
+    lib().orc_con_check(C.byref(o), C.byref(it), _dp(out))
+    return out
 
 
 def iterate_arrays(o, it):

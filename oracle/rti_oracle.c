@@ -684,6 +684,37 @@ static void delta_bounds(const con_desc *d, const orc_iterate *it, int N, double
     }
 }
 
+/* Constraint-side KKT relations of an iterate, model-independent (used to pin the row order / softness mapping of a constraint
+ * set against the reference's own iterate dumps): out[0] = max |t - constraint function| over the rows in use,
+ * out[1] = max |stationarity w.r.t. the slacks| (Ts z + Ts Z s - lam_bound - lam_slack), out[2] = max |lam t|. */
+void orc_con_check(const orc_opts *o, const orc_iterate *it, double out[3])
+{
+    con_desc dd; con_get(o, &dd);
+    const con_desc *d = &dd;
+    const int N = o->N, nc = d->nc;
+    const double Ts = o->dt;
+    double e0 = 0, e1 = 0, e2 = 0;
+    for (int k = 0; k < N; k++) {
+        const double *lam = it->lam + k * nc, *t = it->t + k * nc;
+        for (int q = 0; q < d->nb; q++) {
+            if (!q_on(d, k, q)) continue;
+            const double v = q_bar(d, q, it, k);
+            const int sq = d->soft[q];
+            const double sl = (sq >= 0) ? it->sl[k * 2 + sq] : 0.0, su = (sq >= 0) ? it->su[k * 2 + sq] : 0.0;
+            e0 = nanmax(e0, fabs(t[RL(q)] - (v - d->lo[q] + sl)));
+            e0 = nanmax(e0, fabs(t[RU(q)] - (d->hi[q] - v + su)));
+            e2 = nanmax(e2, nanmax(fabs(lam[RL(q)] * t[RL(q)]), fabs(lam[RU(q)] * t[RU(q)])));
+            if (sq >= 0) {
+                e0 = nanmax(e0, nanmax(fabs(t[RLS(sq)] - sl), fabs(t[RUS(sq)] - su)));
+                e1 = nanmax(e1, fabs(Ts * o->zl[sq] + Ts * o->Zl[sq] * sl - lam[RL(q)] - lam[RLS(sq)]));
+                e1 = nanmax(e1, fabs(Ts * o->zu[sq] + Ts * o->Zu[sq] * su - lam[RU(q)] - lam[RUS(sq)]));
+                e2 = nanmax(e2, nanmax(fabs(lam[RLS(sq)] * t[RLS(sq)]), fabs(lam[RUS(sq)] * t[RUS(sq)])));
+            }
+        }
+    }
+    out[0] = e0; out[1] = e1; out[2] = e2;
+}
+
 int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0,
                  orc_qpsol *s, orc_stats *st)
 {

@@ -97,6 +97,8 @@ typedef struct orc_stats {
 
 void orc_default_opts(orc_opts *o);
 int orc_con_rows(const orc_opts *o);   /* inequality rows per stage of the configured constraint set = stride of lam / t */
+/* constraint-side KKT relations of an iterate: max |t - constraint function|, max |slack stationarity|, max |lam t| */
+void orc_con_check(const orc_opts *o, const struct orc_iterate *it, double out[3]);
 
 /* model */
 void orc_ode(const orc_opts *o, const orc_gp *gp, const double *x, const double *u, double p,

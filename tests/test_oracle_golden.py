@@ -246,3 +246,42 @@ def test_frenet_spline_curvature_jacobian_matches_finite_differences():
                 assert np.abs(d - A[:, j]).max() < 1e-6
     finally:
         orc.set_kappa_spline(None)
+
+
+def test_frenet_constraint_set_matches_the_reference_iterate_dump(golden_dir):
+    """ad_mpc/debug.json is an acados store_iterate dump of the Frenet variant (N = 40, a failed solve): it pins the STRUCTURE of
+    that variant's inequality set -- 12 multipliers [lbu0 lbu1 lbx_ey lbx_delta | ub.. | ls0 ls1 | us0 us1] and 2 + 2 slacks per
+    stage, 20 / 1 + 1 at stage 0 (initial state as bounds), none at the terminal node -- and, through the t-vector definitions and
+    the slack stationarity lam_bound + lam_slack = Ts z, WHICH rows are soft (acceleration and steering angle) and the bounds
+    (u0 in [-10, 5], u1 in [-2, 2], e_y in [-2, 2], delta in [-0.52, 0.52], zl = zu = 100).  The oracle's con_set = 1 must
+    reproduce all of that from the dump's own x, u, lam, t, sl, su."""
+    g = _load(golden_dir, "frenet_debug.npz")
+    N = 40
+    assert g["lam"].shape == (N - 1, 12) and g["sl"].shape == (N - 1, 2) and g["lam0"].shape == (20,) and g["sl0"].shape == (1,)
+    o = orc.default_opts(N, con_set=1, model_backend=2, zl=[100.0, 100.0], zu=[100.0, 100.0], lbu=[-10.0, -2.0], ubu=[5.0, 2.0],
+                         lbx=-0.52, ubx=0.52, lbx2=-2.0, ubx2=2.0)
+    assert orc.con_rows(o) == 12
+    lam, t = np.zeros((N, 12)), np.ones((N, 12))
+    lam[1:], t[1:] = g["lam"], g["t"]
+    # stage 0 of the dump: [lbu0 lbu1 lbx(7) | ubu0 ubu1 ubx(7) | ls0 | us0] ; this repo eliminates x0, the input rows remain
+    for ours, theirs in ((0, 0), (1, 1), (4, 9), (5, 10), (8, 18), (10, 19)):
+        lam[0, ours], t[0, ours] = g["lam0"][theirs], g["t0"][theirs]
+    sl, su = np.zeros((N, 2)), np.zeros((N, 2))
+    sl[1:], su[1:] = g["sl"], g["su"]
+    sl[0, 0], su[0, 0] = g["sl0"][0], g["su0"][0]
+    it = orc.make_iterate(o, g["x"], g["u"])
+    orc.set_iterate_duals(o, it, lam=lam, t=t, sl=sl, su=su)
+    e_t, e_s, e_c = orc.con_check(o, it)
+    assert e_t < 1e-12, e_t                  # t = v - lo + sl, hi - v + su, sl, su with this row order and these bounds
+    assert e_s < 1e-12, e_s                  # Ts z - lam_bound - lam_slack = 0: slack 0 <-> u0 rows, slack 1 <-> steering-angle rows
+    assert e_c < 1e-8                        # the dump is complementary (lam t <= 7e-10)
+    # the mapping is the only one that fits: with the soft state bound on e_y instead (SURVEY's first reading) stage 11 of
+    # the dump (active lower steering bound, lam = 3.59, lam_ls1 = 1.41) violates the slack stationarity
+    assert g["lam"][10, 3] > 3.0 and abs(g["lam"][10, 3] + g["lam"][10, 9] - 5.0) < 1e-12
+    # and the hard rows carry multipliers with no slack partner (steering rate at its upper bound, stages 12..19)
+    assert (g["lam"][11:19, 5] > 0.05).all()
+    # Cartesian set on the same data must NOT fit (10 rows, different softness): guards against a vacuous check
+    o0 = orc.default_opts(N, model_backend=2, zl=[100.0, 100.0], zu=[100.0, 100.0], lbu=[-10.0, -2.0], ubu=[5.0, 2.0])
+    it0 = orc.make_iterate(o0, g["x"], g["u"])
+    orc.set_iterate_duals(o0, it0, lam=lam[:, [0, 1, 3, 4, 5, 7, 8, 9, 10, 11]], t=t[:, [0, 1, 3, 4, 5, 7, 8, 9, 10, 11]], sl=sl, su=su)
+    assert orc.con_check(o0, it0)[1] > 1.0
