@@ -268,6 +268,7 @@ MMA_UNROLL(MMA_UV)
         dmma(acx, acy, bm, kh, a0x, a0y);                          // closed-loop matrix of stage k + 1, off the chain
         {
             const double *sn = (k + 2 < N) ? st + 2 * W_RS : st;
+            ADMPC_ASSERT(sn >= rec && sn + W_RS <= rec + (size_t)N * W_RS);
             cf.load(sn, bm, kh);
             const double u = sn[a0o], v = sn[a1o];
             a0x = l0x ? u : c0x; a0y = l0y ? v : c0y;
@@ -305,6 +306,7 @@ MMA_UNROLL(MMA_UV)
         if (l < 4) stv(st + W_PB + 2 * t, hx, hy);
         {
             const double *sn = (k > 0) ? st - W_RS : st, *s2 = (k > 1) ? st - 2 * W_RS : st;
+            ADMPC_ASSERT(s2 >= rec && sn >= rec && st + W_RS <= rec + (size_t)N * W_RS);
             cf.load(s2, bm, kh); af.load(s2, atx, aty);
             pb = ldv(sn + W_PB + 2 * t); gx = ldv(sn + W_GX + 2 * t); k0 = ldv(sn + W_K0 + 2 * t); k1 = ldv(sn + W_K1 + 2 * t);
             rt = ldv(sn + W_BAR + 2);
