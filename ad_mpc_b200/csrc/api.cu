@@ -128,7 +128,7 @@ struct admpc_batch {
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     bool profiling = false;
     bool gps_set = false;
-    int qp_variant = 0;      // 0 auto, 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu), 6 resident warp (qp_rw.cu), 7 resident warp + DMMA sweeps (qp_mma.cu)
+    int qp_variant = 0;      // 0 auto, 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu), 7 resident warp(s) + DMMA sweeps (qp_mma.cu)
     long long launches = 0;
     float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
     char *pack = nullptr, *gpack = nullptr;     // packed [u | x | status] block of this rank / of all ranks (root)
@@ -202,14 +202,14 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     // Interface arrays always; QP workspaces only for the kernel variant this handle will run: the warp-per-instance
     // kernel (N <= 63) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
     // thread-per-instance kernel streams a 35 KB/instance SoA workspace.
-    int variant = h->qp_variant ? h->qp_variant : (N <= 31 ? 7 : (N <= 63 ? 4 : 3));
-    if (variant == 7 && N > 31) variant = (N <= 63) ? 4 : 3;       // the tensor-core kernel takes one node per lane
+    int variant = h->qp_variant ? h->qp_variant : (N <= 63 ? 7 : 3);
+    if (variant == 7 && N > 63) variant = 3;                       // the tensor-core kernel takes one node per thread of one or two warps
     const bool need_ws3 = (variant == 3 || (variant >= 4 && N > 63)) && N <= 80;
     const bool frenet = h->P.o.model_variant == 1;
     const bool need_ws1 = (variant == 1) || N > 80 || frenet;
-    // the shared-memory-resident warp kernel (variant 6) stages instance-major linearisation records by TMA; every other
+    // the shared-memory-resident warp kernel (variant 7) stages instance-major linearisation records by TMA; every other
     // feedback kernel reads the SoA rows.  Exactly one of the two layouts exists per handle.
-    const bool use_im = (variant == 6 || variant == 7) && N <= 63 && !frenet;
+    const bool use_im = (variant == 7) && N <= 63 && !frenet;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
@@ -568,15 +568,14 @@ static int launch_feedback(admpc_batch *h)
         h->launches += 2;
         return 0;
     }
-    // QP variant (0 = auto): 7 warp per instance, shared-memory resident, Riccati sweeps as FP64 tensor-core fragments
-    // (qp_mma.cu, default for N <= 31); 6 the same with hand-distributed sweeps (qp_rw.cu); 4 warp(s) per instance with register-resident IPM state (qp_warp.cu, default for 32 <= N <= 63: its
-    // two-warp form); 3 shared-memory octets (horizons 64..80); 1 one thread per instance.  A variant that cannot take
-    // the horizon falls through to the next one.
-    int variant = h->qp_variant ? h->qp_variant : (P.o.N <= 31 ? 7 : 4);
-    if (variant == 7 && P.o.N > 31) variant = 4;
+    // QP variant (0 = auto): 7 one / two warps per instance, shared-memory resident, Riccati sweeps as FP64 tensor-core
+    // fragments (qp_mma.cu, default for N <= 63); 4 warp(s) per instance with register-resident IPM state (qp_warp.cu, the
+    // round-1 kernel, kept as an independent implementation); 3 shared-memory octets (horizons 64..80); 1 one thread per
+    // instance.  A variant that cannot take the horizon falls through to the next one.
+    int variant = h->qp_variant ? h->qp_variant : 7;
+    if (variant == 7 && P.o.N > 63) variant = 4;
     bool fused = false;
     if (variant == 7) { fused = launch_qp_mma(P, h->stream); h->gat_fresh = fused && h->gat_on; }    // warp per instance, sweeps on the FP64 tensor cores
-    if (variant == 6) { fused = launch_qp_rw(P, h->stream); h->gat_fresh = fused && h->gat_on; }     // warp per instance, shared-memory resident
     if (!fused && variant >= 4) { fused = launch_qp_warp(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // one / two warps per instance, N <= 63
     if (!fused && variant >= 3 && P.ws) fused = launch_qp_smem(P, h->stream);
     if (!fused) {

@@ -144,8 +144,7 @@ void launch_qp(const Params &P, cudaStream_t s);
 bool launch_qp_smem(const Params &P, cudaStream_t s);   // false: horizon too long for the shared-memory variant
 int qp_smem_ws_rows(int N);
 bool launch_qp_warp(const Params &P, cudaStream_t s);   // false: N > 31
-bool launch_qp_mma(const Params &P, cudaStream_t s);    // one warp per instance, sweeps on the FP64 tensor cores (DMMA), false: N > 31
-bool launch_qp_rw(const Params &P, cudaStream_t s);     // one warp per instance, whole solve resident in shared memory, false: N > 63
+bool launch_qp_mma(const Params &P, cudaStream_t s);    // one / two warps per instance, whole solve resident in shared memory, sweeps on the FP64 tensor cores (DMMA), false: N > 63
 void launch_transpose_in(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);   // [B][F] -> [F][Bp]
 void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);  // [F][Bp] -> [B][F]
 void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]

@@ -1,7 +1,7 @@
-// qp_mma.cu -- feedback phase, v7: ONE WARP PER MPC INSTANCE, the horizon-sequential Riccati sweeps on the FP64 TENSOR CORES
-// (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4), N <= 31.
+// qp_mma.cu -- feedback phase, v7: ONE (N <= 31) OR TWO (N <= 63) WARPS PER MPC INSTANCE, the whole solve resident in shared
+// memory, the horizon-sequential Riccati sweeps on the FP64 TENSOR CORES (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).
 //
-// Why: the v6 kernel (qp_rw.cu) spends 70 % of its time in five sweeps per IPM iteration whose 7x7 products are spread over the
+// Why: the v6 kernel (same residency, hand-distributed sweeps; profiles/r02_qp_rw_summary.md) spent 70 % of its time in five sweeps per IPM iteration whose 7x7 products are spread over the
 // lanes by hand: every operand a lane does not own is a shared-memory broadcast or a shuffle (103 shared-memory wavefronts per
 // factor stage, three round trips per stage on the critical path; the LSU pipe, not the FP64 pipe, is the busiest unit).  An
 // m8n8k4 DMMA moves the operands inside the tensor core instead.  With nx = 7 (+1 homogeneous coordinate) everything is 8 x 8:
@@ -22,8 +22,8 @@
 // Measured on B200 (scripts/dmma_probe.cu): DMMA.8x8x4 26 cycles dependent, 0.25 / clk / SM (= the DFMA pipe: 37 TFLOP/s), so a
 // padded 8x8x8 product costs what the hand-distributed one cost in pipe time, minus all of its operand traffic.
 //
-// Node role (lane k owns node k: residuals, barrier terms, step lengths, update), record layout, staging by TMA bulk copies and
-// the epilogue are those of qp_rw.cu.  Algorithm: HPIPM-style Mehrotra predictor-corrector IPM on the OCP-structured QP [EXT],
+// Node role: thread k owns node k (residuals, barrier terms, step lengths, update: shared memory -> registers -> shared memory
+// with 16-byte accesses, one pass per phase); staging: one TMA bulk copy per instance-major stage record.  Algorithm: HPIPM-style Mehrotra predictor-corrector IPM on the OCP-structured QP [EXT],
 // replacing FULL_CONDENSING_HPIPM (acados_solver_sim_car.c:145,688-693); identical maths to oracle/rti_oracle.c orc_qp_solve,
 // results differ by rounding only.
 #include "common.cuh"
@@ -369,12 +369,18 @@ __device__ __forceinline__ void node_dir(const double *st, int k, double ddx[7],
 #ifndef MMA_MINB
 #define MMA_MINB 8
 #endif
-__global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
+// NW warps per instance: thread k owns node k in the node role (N <= 32 NW - 1); the sweeps run on warp 0 while the others wait
+// at the CTA barrier.  NW = 1: N <= 31, 8 instances per SM ; NW = 2: N <= 63, 4 instances per SM (BASELINE cfg4: N = 40).
+template <int NW> __device__ __forceinline__ void bsync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kernel(const Params P)
 {
     extern __shared__ __align__(16) double smr[];
+    __shared__ double red[16];                       // cross-warp reductions (NW = 2)
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
-    const int l = threadIdx.x;
+    const int tid = threadIdx.x, l = tid & 31, wid = tid >> 5;
+    const bool sweeper = (NW == 1) || wid == 0;
     const int i = blockIdx.x;                        // one instance per CTA
     double *rec = smr;
     double *term = rec + (size_t)N * W_RS;
@@ -384,45 +390,45 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
         unsigned dyn;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
         ADMPC_ASSERT((size_t)dyn >= ((size_t)N * W_RS + T_SIZE) * sizeof(double));
-        ADMPC_ASSERT(i < P.B && N >= 2 && N <= 31 && P.lin_im != nullptr);
+        ADMPC_ASSERT(i < P.B && N >= 2 && N <= 32 * NW - 1 && P.lin_im != nullptr);
         ADMPC_ASSERT((((size_t)(P.lin_im + ((size_t)0 * Bp + i) * LIM_STRIDE)) & 15) == 0);
     }
 #endif
     const int flag = P.lin_bad[i];                   // 1: NaN/Inf in the linearisation ; 2: finished instance of the SQP loop
     if (flag) {
-        if (l == 0 && flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
+        if (tid == 0 && flag == 1) { P.status[i] = 1; P.qp_status[i] = 0; P.qp_iter[i] = 0; }
         if (P.gat_x) {                               // fused gather: the (untouched) iterate still goes to the root's block
-            for (int k = l; k <= N; k += 32) {
+            for (int k = tid; k <= N; k += 32 * NW) {
                 for (int a = 0; a < 7; a++) P.gat_x[((size_t)i * (N + 1) + k) * 7 + a] = ATS(P.xb, k * 7 + a);
                 if (k < N) for (int jj = 0; jj < 2; jj++) P.gat_u[((size_t)i * N + k) * 2 + jj] = ATS(P.ub, k * 2 + jj);
             }
-            if (l == 0) P.gat_st[i] = (flag == 1) ? 1 : P.status[i];
+            if (tid == 0) P.gat_st[i] = (flag == 1) ? 1 : P.status[i];
         }
         return;
     }
 
     // ---- stage the linearisation: one TMA bulk copy per stage record (M, b, q, r, x, u = 544 B), one mbarrier ---------------
     __shared__ uint64_t bar;
-    if (l == 0) {
+    if (tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&bar, (uint32_t)(N * LIM_STRIDE * sizeof(double)));
     }
-    __syncwarp();
-    for (int k = l; k < N; k += 32)
+    bsync<NW>();
+    for (int k = tid; k < N; k += 32 * NW)
         tma_bulk_g2s(rec + (size_t)k * W_RS, P.lin_im + ((size_t)k * Bp + i) * LIM_STRIDE, LIM_STRIDE * sizeof(double), &bar);
-    if (l < 7) {                                     // terminal node: q_N and x_N only
+    if (tid < 7) {                                   // terminal node: q_N and x_N only
         const double *rn = P.lin_im + ((size_t)N * Bp + i) * LIM_STRIDE;
-        term[T_LQ + l] = rn[LIM_Q + l]; term[T_XB + l] = rn[LIM_X + l]; term[T_DX + l] = 0.0;
-        if (l == 0) term[T_GX + 7] = 0.0;
+        term[T_LQ + tid] = rn[LIM_Q + tid]; term[T_XB + tid] = rn[LIM_X + tid]; term[T_DX + tid] = 0.0;
+        if (tid == 0) term[T_GX + 7] = 0.0;
     }
     double x0v[7];
 #pragma unroll
-    for (int a = 0; a < 7; a++) x0v[a] = (l == 0) ? ATS(P.x0, a) : 0.0;
+    for (int a = 0; a < 7; a++) x0v[a] = (tid == 0) ? ATS(P.x0, a) : 0.0;
     mbar_wait(&bar, 0);
     // ---- cold start ------------------------------------------------------------------------------------------------------------
     {
-        const int k = l;
+        const int k = tid;
         if (k < N) {
             double *st = rec + (size_t)k * W_RS;
             const double ub0 = st[W_UB], ub1 = st[W_UB + 1], xb6 = st[W_XB + 6];
@@ -462,10 +468,10 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
             st[W_RB + 7] = 1.0; st[W_GX + 7] = 0.0;          // homogeneous coordinate / padding of the fragment rows
         }
     }
-    __syncwarp();
+    bsync<NW>();
 
     const double inv_nc = 1.0 / (double)(NC * N - 2);
-    const int k = l;                                 // node of this lane
+    const int k = tid;                               // node of this thread
     int status = 1, iter = 0;
     double res0 = 0, res1 = 0, res2 = 0, res3 = 0;
     for (iter = 0;; iter++) {
@@ -581,19 +587,27 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
             st[W_GX + 6] = gx[6];
         }
         ng = wmax32(ng); nb = wmax32(nb); nd = wmax32(nd); nm = wmax32(nm); summ = wsum32(summ);
+        if (NW == 2) {
+            if (l == 0) { red[wid * 8] = ng; red[wid * 8 + 1] = nb; red[wid * 8 + 2] = nd; red[wid * 8 + 3] = nm; red[wid * 8 + 4] = summ; }
+            __syncthreads();
+            ng = nmx(red[0], red[8]); nb = nmx(red[1], red[9]); nd = nmx(red[2], red[10]); nm = nmx(red[3], red[11]); summ = red[4] + red[12];
+            __syncthreads();
+        }
         res0 = ng; res1 = nb; res2 = nd; res3 = nm;
         if (!(isfinite(ng) && isfinite(nb) && isfinite(nd) && isfinite(nm))) { status = 3; break; }
         if (ng < o.tol_stat && nb < o.tol_eq && nd < o.tol_ineq && nm < o.tol_comp) { status = 0; break; }
         if (iter >= o.iter_max) { status = 1; break; }
         const double mu = summ * inv_nc;
-        __syncwarp();
+        bsync<NW>();
 
         // ================= predictor ========================================================================================
-        mma_factor(o, rec, term, N, l);
-        mma_forward(o, rec, N, l);
+        if (sweeper) mma_factor(o, rec, term, N, l);
+        bsync<NW>();
+        if (sweeper) mma_forward(o, rec, N, l);
+        bsync<NW>();
         // affine step: step length, mu_aff ; the complementarity products and the two linear functionals the corrected
         // barrier gradient needs stay in registers of the node's lane
-        double an = 1.0, ad = 1.0, s1 = 0.0, s2 = 0.0;
+        double an = 1.0, ad = 1.0, s1 = 0.0, s2 = 0.0, m_aff = 1.0;
         double pr[NC], fa[3], fb[3];
 #pragma unroll
         for (int c = 0; c < NC; c++) pr[c] = 0.0;
@@ -611,7 +625,7 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
             node_dir(st, k, ddx, ddu);
             NStep D;
             node_step_w(k >= 1, C, R, S, rm, ddu[0], ddu[1], ddx[6], D);
-            node_ratio_w(k >= 1, C, D, an, ad);
+            m_aff = node_ratio_aff(k >= 1, S, D, m_aff);
             double ea[NC], eb[NC];       // change of g = (rm - lam rd)/t caused by rm -> rm + dlam dt - sigma mu: ea - sigma mu eb
 #pragma unroll
             for (int c = 0; c < NC; c++) {
@@ -632,9 +646,15 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
             fa[2] = ea[2] - ea[5];
             fb[2] = eb[2] - eb[5];
         }
-        warp_ratio(an, ad);
+        m_aff = wmaxf32(m_aff);
         s1 = wsum32(s1); s2 = wsum32(s2);
-        const double a_aff = an * rcp_w(ad);
+        if (NW == 2) {
+            if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
+            __syncthreads();
+            m_aff = fmax(red[0], red[8]); s1 = red[1] + red[9]; s2 = red[2] + red[10];
+            __syncthreads();
+        }
+        const double a_aff = rcp_w(m_aff);               // min(1, min ratio) = 1 / max(1, max of the inverse ratios)
         const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
         double sigma = mu_aff * rcp_w(mu);
         sigma = sigma * sigma * sigma;
@@ -645,9 +665,10 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
             stv(st + W_BAR + 2, rt.x + fma(-sigmu, fb[0], fa[0]), rt.y + fma(-sigmu, fb[1], fa[1]));
             if (k >= 1) st[W_GX + 6] += fma(-sigmu, fb[2], fa[2]);
         }
-        __syncwarp();
+        bsync<NW>();
         // ================= corrector ========================================================================================
-        mma_backward(o, rec, term, N, l);
+        if (sweeper) mma_backward(o, rec, term, N, l);
+        bsync<NW>();
         // k_ff of the corrector: -Guu^-1 (rt + B^T h_k), node-parallel
         if (k < N) {
             double *st = rec + (size_t)k * W_RS;
@@ -660,8 +681,9 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
             st[W_KF0] = -(gi00 * gu0 + gi01 * gu1);
             st[W_KF1] = -(gi01 * gu0 + gi11 * gu1);
         }
-        __syncwarp();
-        mma_forward(o, rec, N, l);
+        bsync<NW>();
+        if (sweeper) mma_forward(o, rec, N, l);
+        bsync<NW>();
         // final step: step length, then the update of the constraint part of the iterate from the same registers
         an = 1.0; ad = 1.0;
         NCon Cs;
@@ -690,9 +712,18 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
                 st[W_GX + 6] = nbv[6];
             }
             node_step_w(k >= 1, Cs, R, S, rm, duc[0], duc[1], ddx[6], Ds);
-            node_ratio_w(k >= 1, Cs, Ds, an, ad);
+            node_ratio_lam(k >= 1, Cs, Ds, an, ad);
+            const double mt = node_ratio_t(k >= 1, S, Ds, 1.0);
+            if (ad < an * mt) { an = 1.0; ad = mt; }
         }
         warp_ratio(an, ad);
+        if (NW == 2) {
+            if (l == 0) { red[wid * 8] = an; red[wid * 8 + 1] = ad; }
+            __syncthreads();
+            an = red[0]; ad = red[1];
+            if (red[8] * ad < an * red[9]) { an = red[8]; ad = red[9]; }
+            __syncthreads();
+        }
         double alpha = an * rcp_w(ad);
         if (alpha < o.alpha_min) { status = 2; break; }
         if (alpha < 1.0) alpha *= 0.995;
@@ -713,9 +744,10 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
 #pragma unroll
             for (int c = 0; c < NC; c += 2) { stv(st + W_LAM + c, ln[c], ln[c + 1]); stv(st + W_T + c, tn[c], tn[c + 1]); }
         }
-        __syncwarp();
+        bsync<NW>();
         // pi and dx wait for the adjoint sweep
-        mma_adjoint(rec, term, N, l);
+        if (sweeper) mma_adjoint(rec, term, N, l);
+        bsync<NW>();
         if (k <= N) {
             if (k < N) {
                 double *st = rec + (size_t)k * W_RS;
@@ -729,13 +761,13 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
                 for (int a = 0; a < 7; a++) dst[a] += alpha * prev[W_XA + a];
             }
         }
-        __syncwarp();
+        bsync<NW>();
     }
 
     // ---- epilogue: statuses + fused RTI update (full step; duals <- QP duals) --------------------------------------------
     const int qps = (status == 0) ? 0 : ((status == 1) ? 2 : ((status == 2) ? 3 : 1));   // hpipm -> acados numbering
     const int nlp_status = (qps == 0 || qps == 2) ? 0 : 4;
-    if (l == 0) {
+    if (tid == 0) {
         P.qp_status[i] = qps; P.qp_iter[i] = iter; P.status[i] = nlp_status;
         ATS(P.res_out, 0) = res0; ATS(P.res_out, 1) = res1; ATS(P.res_out, 2) = res2; ATS(P.res_out, 3) = res3;
     }
@@ -784,10 +816,16 @@ __global__ void __launch_bounds__(32, MMA_MINB) qp_mma_kernel(const Params P)
 bool launch_qp_mma(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
-    if (N > 31 || !P.lin_im) return false;
+    if (N > 63 || !P.lin_im) return false;
     const size_t sm = ((size_t)N * W_RS + T_SIZE) * sizeof(double);
-    static SmemGuard configured;
-    if (configured.need(sm)) cudaFuncSetAttribute(qp_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    qp_mma_kernel<<<P.B, 32, sm, s>>>(P);
+    if (N <= 31) {
+        static SmemGuard configured;
+        if (configured.need(sm)) cudaFuncSetAttribute(qp_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        qp_mma_kernel<1><<<P.B, 32, sm, s>>>(P);
+    } else {
+        static SmemGuard configured2;
+        if (configured2.need(sm)) cudaFuncSetAttribute(qp_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        qp_mma_kernel<2><<<P.B, 64, sm, s>>>(P);
+    }
     return true;
 }

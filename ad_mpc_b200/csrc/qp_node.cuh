@@ -1,4 +1,4 @@
-// qp_node.cuh -- node-role arithmetic of the warp-per-instance IPM kernels (qp_rw.cu, qp_mma.cu): constraint data of one shooting
+// qp_node.cuh -- node-role arithmetic of the warp-per-instance IPM kernel (qp_mma.cu): constraint data of one shooting
 // node streamed from its shared-memory record, residuals, barrier scalings, slack / t / lambda steps, division-free ratio test,
 // warp reductions.  Include AFTER the record layout (W_* offsets) of the kernel has been defined.
 #pragma once
@@ -141,6 +141,48 @@ __device__ __forceinline__ void node_ratio_w(bool k_ge1, const NCon &C, const NS
             if (D.dtv[c] < 0.0 && C.t[c] * ad < an * (-D.dtv[c])) { an = C.t[c]; ad = -D.dtv[c]; }
         }
     }
+}
+// Ratio test through the reciprocals the barrier terms already hold: t / (-dt) = 1 / (-dt it), so the t rows contribute
+// max_c(-dt_c it_c) to m and the step bound is 1 / max(1, m): one multiply and one max per row, no serial (num, den) chain.
+__device__ __forceinline__ double node_ratio_t(bool k_ge1, const NScal &S, const NStep &D, double m)
+{
+    double w[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const bool on = !((c == 2 || c == 5) && !k_ge1);
+        w[c] = on ? -D.dtv[c] * S.it[c] : 0.0;
+    }
+    const double a = fmax(fmax(w[0], w[1]), fmax(w[2], w[3])), b = fmax(fmax(w[4], w[5]), fmax(w[6], w[7]));
+    return fmax(m, fmax(fmax(a, b), fmax(w[8], w[9])));
+}
+// Affine step only (rm = lam t): dlam = -lam (1 + dt / t), so lam / (-dlam) = 1 / (1 + dt it) and both halves of the test come
+// from w_c = dt_c it_c: m = max_c max(-w_c, 1 + w_c).
+__device__ __forceinline__ double node_ratio_aff(bool k_ge1, const NScal &S, const NStep &D, double m)
+{
+    double w[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const bool on = !((c == 2 || c == 5) && !k_ge1);
+        const double q = D.dtv[c] * S.it[c];
+        w[c] = on ? fmax(-q, 1.0 + q) : 0.0;
+    }
+    const double a = fmax(fmax(w[0], w[1]), fmax(w[2], w[3])), b = fmax(fmax(w[4], w[5]), fmax(w[6], w[7]));
+    return fmax(m, fmax(fmax(a, b), fmax(w[8], w[9])));
+}
+// lam rows of the final step: division-free (num, den) pair as in node_ratio_w
+__device__ __forceinline__ void node_ratio_lam(bool k_ge1, const NCon &C, const NStep &D, double &an, double &ad)
+{
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const bool on = !((c == 2 || c == 5) && !k_ge1);
+        if (on && D.dlv[c] < 0.0 && C.lam[c] * ad < an * (-D.dlv[c])) { an = C.lam[c]; ad = -D.dlv[c]; }
+    }
+}
+__device__ __forceinline__ double wmaxf32(double v)       // plain max (no NaN propagation needed: NaNs are caught by the residual norms)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
 }
 __device__ __forceinline__ void warp_ratio(double &an, double &ad)
 {

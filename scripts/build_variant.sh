@@ -1,11 +1,11 @@
 #!/bin/bash
 # build_variant.sh NAME "-DMACRO=... ..." [file.cu ...] : links ad_mpc_b200/variants/NAME.so = the in-tree objects with the given
-# sources (default: qp_rw.cu) recompiled under the given macros.  Select it at run time with ADMPC_LIB=<path>.
+# sources (default: qp_mma.cu) recompiled under the given macros.  Select it at run time with ADMPC_LIB=<path>.
 set -e
 cd "$(dirname "$0")/../ad_mpc_b200"
 mkdir -p variants
 NAME=$1; MACROS=$2; shift 2 || true
-FILES=${@:-qp_rw.cu}
+FILES=${@:-qp_mma.cu}
 F="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ -I csrc -I ../include -Xptxas -v"
 EXCL=""
 OBJS=""

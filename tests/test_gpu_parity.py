@@ -361,8 +361,8 @@ def test_scale_invariance_full_size():
 
 
 def test_long_horizon_fallback_variants():
-    """Horizon dispatch of the feedback kernel: N <= 31 the shared-memory-resident warp kernel (qp_rw), 32..63 two warps
-    per instance (qp_warp), 64..80 the shared-memory octet kernel, above that one thread per instance -- same parity bar
+    """Horizon dispatch of the feedback kernel: N <= 31 the tensor-core kernel with one warp per instance (qp_mma<1>), 32..63
+    with two (qp_mma<2>), 64..80 the shared-memory octet kernel, above that one thread per instance -- same parity bar
     on both sides of every edge."""
     for N, B in ((31, 16), (32, 16), (40, 24), (63, 12), (64, 12), (90, 12)):
         batch = wl.make_batch(B, N, seed=31, p=1.0, perturb=3.0 if N in (32, 63) else 1.0)
@@ -375,33 +375,35 @@ def test_long_horizon_fallback_variants():
 
 
 def test_two_warp_kernel_matches_octet_kernel(monkeypatch):
-    """N = 40 with active bounds: the two-warps-per-instance kernel (default) against the octet kernel (variant 3)."""
+    """N = 40 with active bounds: the two-warps-per-instance tensor-core kernel (default, 7) against the register-resident
+    two-warp kernel (4) and the octet kernel (3)."""
     B, N = 96, 40
     batch = wl.make_batch(B, N, seed=78, p=0.5, perturb=5.0)
     out = {}
-    for v in (3, 4):
+    for v in (3, 4, 7):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, default_opts(N))
         out[v] = _gpu_step(s, batch)
         s.close()
-    assert np.array_equal(out[3]["qp_iter"], out[4]["qp_iter"]) and np.array_equal(out[3]["status"], out[4]["status"])
-    assert mixed_err(out[3]["u"], out[4]["u"]) <= TOL and mixed_err(out[3]["x"], out[4]["x"]) <= TOL
+    for v in (3, 4):
+        assert np.array_equal(out[v]["qp_iter"], out[7]["qp_iter"]) and np.array_equal(out[v]["status"], out[7]["status"])
+        assert mixed_err(out[v]["u"], out[7]["u"]) <= TOL and mixed_err(out[v]["x"], out[7]["x"]) <= TOL
     r = oracle_batch(mirror_opts(default_opts(N)), batch)
-    _compare(out[4], r)
+    _compare(out[7], r)
 
 
 def test_qp_variants_agree(monkeypatch):
-    """The five QP kernels are independent implementations of the same algorithm: identical statuses / iteration
-    counts and 1e-8 agreement on a batch with active bounds (7 = tensor-core sweeps, the default; 6 = its hand-distributed twin)."""
+    """The four QP kernels are independent implementations of the same algorithm: identical statuses / iteration
+    counts and 1e-8 agreement on a batch with active bounds (7 = tensor-core sweeps, the default)."""
     B, N = 128, 20
     batch = wl.make_batch(B, N, seed=77, p=0.5, perturb=5.0)
     out = {}
-    for v in (1, 3, 4, 6, 7):
+    for v in (1, 3, 4, 7):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, default_opts(N))
         out[v] = _gpu_step(s, batch)
         s.close()
-    for v in (1, 3, 4, 6):
+    for v in (1, 3, 4):
         assert np.array_equal(out[v]["qp_iter"], out[7]["qp_iter"]) and np.array_equal(out[v]["status"], out[7]["status"]), v
         assert mixed_err(out[v]["u"], out[7]["u"]) <= TOL and mixed_err(out[v]["x"], out[7]["x"]) <= TOL, v
 
@@ -506,7 +508,7 @@ def test_sqp_mode_with_gp_and_other_qp_kernels(monkeypatch):
     gp = orc.Gp(model)
     gp.apply(o, feat=model["feat"], rows=model["rows"])
     r = orc.sqp_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=gp, gp_state=batch["x0"])
-    for v in (7, 6, 4, 3, 1):
+    for v in (7, 4, 3, 1):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, opts)
         s.set_gp(model)
