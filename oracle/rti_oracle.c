@@ -359,8 +359,19 @@ static int prepare_impl(const orc_opts *o, const orc_gp *gp, const orc_iterate *
  *              = Ts zl at an active steering bound, lam_ubu1 active with no slack row): u0 soft, u1 hard, x1 (e_y) hard,
  *              x6 (delta) soft                                                                                 -> 12 rows
  * Bounds on states do not exist at stage 0 (x0 is eliminated), nor do their slacks; no terminal constraints. */
-typedef struct { int nb, ns, nc; int idx[4], soft[4]; double lo[4], hi[4]; } con_desc;
-static void con_get(const orc_opts *o, con_desc *d)
+typedef struct { int nb, ns, nc; int idx[4], soft[4]; double lo[4], hi[4]; int on0[ORC_NC]; } con_desc;
+static inline int q_on(const con_desc *d, int k, int q) { return d->idx[q] < 2 || k >= 1; }
+/* quantity a row belongs to */
+static inline int row_q(const con_desc *d, int c)
+{
+    if (c < d->nb) return c;
+    if (c < 2 * d->nb) return c - d->nb;
+    int s = (c < 2 * d->nb + d->ns) ? c - 2 * d->nb : c - 2 * d->nb - d->ns;
+    for (int q = 0; q < d->nb; q++) if (d->soft[q] == s) return q;
+    return 0;
+}
+static inline int con_on(const con_desc *d, int k, int c) { return k >= 1 || d->on0[c]; }     /* rows in use at stage k */
+static inline __attribute__((always_inline)) void con_get(const orc_opts *o, con_desc *d)
 {
     memset(d, 0, sizeof(*d));
     if (o->con_set == 1) {
@@ -377,19 +388,9 @@ static void con_get(const orc_opts *o, con_desc *d)
         d->lo[2] = o->lbx; d->hi[2] = o->ubx;
     }
     d->nc = 2 * d->nb + 2 * d->ns;
+    for (int c = 0; c < d->nc; c++) d->on0[c] = q_on(d, 0, row_q(d, c));
 }
 int orc_con_rows(const orc_opts *o) { con_desc d; con_get(o, &d); return d.nc; }
-static inline int q_on(const con_desc *d, int k, int q) { return d->idx[q] < 2 || k >= 1; }
-/* quantity a row belongs to */
-static inline int row_q(const con_desc *d, int c)
-{
-    if (c < d->nb) return c;
-    if (c < 2 * d->nb) return c - d->nb;
-    int s = (c < 2 * d->nb + d->ns) ? c - 2 * d->nb : c - 2 * d->nb - d->ns;
-    for (int q = 0; q < d->nb; q++) if (d->soft[q] == s) return q;
-    return 0;
-}
-static inline int con_on(const con_desc *d, int k, int c) { return q_on(d, k, row_q(d, c)); }
 #define RL(q) (q)
 #define RU(q) (d->nb + (q))
 #define RLS(s) (2 * d->nb + (s))
@@ -419,7 +420,7 @@ static inline double q_bar(const con_desc *d, int q, const orc_iterate *it, int 
 }
 
 /* dlo / dhi [k][q]: bounds in delta form around the iterate */
-static void ipm_residuals(const orc_opts *o, const con_desc *d, const orc_lin *lin, const double (*dlo)[4],
+static inline __attribute__((always_inline)) void ipm_residuals(const orc_opts *o, const con_desc *d, const orc_lin *lin, const double (*dlo)[4],
                           const double (*dhi)[4], const orc_qpsol *s, ipm_ws *w, double res[4], double *mu)
 {
     const int N = o->N, nc = d->nc;
@@ -506,7 +507,7 @@ static inline void q_scaling(const orc_opts *o, const con_desc *d, int q, const 
 }
 
 /* Riccati factorisation for the barrier-modified Hessian (matrix part only). */
-static void ipm_factor(const orc_opts *o, const con_desc *d, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
+static inline __attribute__((always_inline)) void ipm_factor(const orc_opts *o, const con_desc *d, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
 {
     const int N = o->N, nc = d->nc;
     const double Ts = o->dt;
@@ -563,7 +564,7 @@ static void ipm_factor(const orc_opts *o, const con_desc *d, const orc_lin *lin,
 }
 
 /* Solve for the Newton step given the complementarity right-hand side w->rm (vector part of the Riccati). */
-static void ipm_solve(const orc_opts *o, const con_desc *d, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
+static inline __attribute__((always_inline)) void ipm_solve(const orc_opts *o, const con_desc *d, const orc_lin *lin, const orc_qpsol *s, ipm_ws *w)
 {
     const int N = o->N, nc = d->nc;
     double gl[ORC_NMAX][ORC_NC], rt[ORC_NMAX][2], qx[ORC_NMAX][7], cl[ORC_NMAX][2], cu[ORC_NMAX][2];
@@ -662,7 +663,7 @@ static void ipm_solve(const orc_opts *o, const con_desc *d, const orc_lin *lin, 
     }
 }
 
-static double ipm_alpha(const orc_opts *o, const con_desc *d, const orc_qpsol *s, const ipm_ws *w)
+static inline __attribute__((always_inline)) double ipm_alpha(const orc_opts *o, const con_desc *d, const orc_qpsol *s, const ipm_ws *w)
 {
     const int nc = d->nc;
     double a = 1.0;
@@ -675,7 +676,7 @@ static double ipm_alpha(const orc_opts *o, const con_desc *d, const orc_qpsol *s
     return a;
 }
 
-static void delta_bounds(const con_desc *d, const orc_iterate *it, int N, double (*dlo)[4], double (*dhi)[4])
+static inline __attribute__((always_inline)) void delta_bounds(const con_desc *d, const orc_iterate *it, int N, double (*dlo)[4], double (*dhi)[4])
 {
     for (int k = 0; k < N; k++) for (int q = 0; q < d->nb; q++) {
         const double bar = q_bar(d, q, it, k);
@@ -715,12 +716,10 @@ void orc_con_check(const orc_opts *o, const orc_iterate *it, double out[3])
     out[0] = e0; out[1] = e1; out[2] = e2;
 }
 
-int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0,
-                 orc_qpsol *s, orc_stats *st)
+static inline __attribute__((always_inline)) int qp_solve_body(const orc_opts *o, const con_desc *d, const orc_lin *lin, const orc_iterate *it,
+                                                              const double *x0, orc_qpsol *s, orc_stats *st)
 {
     const int N = o->N;
-    con_desc dd; con_get(o, &dd);
-    const con_desc *d = &dd;
     const int nc = d->nc;
     ipm_ws *w = (ipm_ws *)malloc(sizeof(ipm_ws));
     double dlo[ORC_NMAX][4], dhi[ORC_NMAX][4];
@@ -802,6 +801,23 @@ int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, c
         st->step_inf = m;
     }
     return status;
+}
+/* one specialisation per constraint set: the descriptor's structure is a compile-time constant inside each (the generic code then
+ * costs what the hard-coded version did) */
+static int qp_solve_set0(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0, orc_qpsol *s, orc_stats *st)
+{
+    con_desc d; orc_opts oo = *o; oo.con_set = 0; con_get(&oo, &d);
+    return qp_solve_body(o, &d, lin, it, x0, s, st);
+}
+static int qp_solve_set1(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0, orc_qpsol *s, orc_stats *st)
+{
+    con_desc d; orc_opts oo = *o; oo.con_set = 1; con_get(&oo, &d);
+    return qp_solve_body(o, &d, lin, it, x0, s, st);
+}
+int orc_qp_solve(const orc_opts *o, const orc_lin *lin, const orc_iterate *it, const double *x0,
+                 orc_qpsol *s, orc_stats *st)
+{
+    return (o->con_set == 1) ? qp_solve_set1(o, lin, it, x0, s, st) : qp_solve_set0(o, lin, it, x0, s, st);
 }
 
 /* ------------------------------------------------------------------------------------------ RTI step ------- */
