@@ -1,31 +1,36 @@
 // qp_mma.cu -- feedback phase, v7: ONE (N <= 31) OR TWO (N <= 63) WARPS PER MPC INSTANCE, the whole solve resident in shared
 // memory, the horizon-sequential Riccati sweeps on the FP64 TENSOR CORES (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).
 //
-// Why: the v6 kernel (same residency, hand-distributed sweeps; profiles/r02_qp_rw_summary.md) spent 70 % of its time in five sweeps per IPM iteration whose 7x7 products are spread over the
-// lanes by hand: every operand a lane does not own is a shared-memory broadcast or a shuffle (103 shared-memory wavefronts per
-// factor stage, three round trips per stage on the critical path; the LSU pipe, not the FP64 pipe, is the busiest unit).  An
-// m8n8k4 DMMA moves the operands inside the tensor core instead.  With nx = 7 (+1 homogeneous coordinate) everything is 8 x 8:
+// Why: the v6 kernel (same residency, hand-distributed sweeps; profiles/r02_qp_rw_summary.md) spent 70 % of its time in five
+// sweeps per IPM iteration whose 7x7 products were spread over the lanes by hand: every operand a lane does not own is a
+// shared-memory broadcast or a shuffle (103 shared-memory wavefronts per factor stage, three round trips per stage on the
+// critical path; the LSU pipe, not the FP64 pipe, was the busiest unit).  An m8n8k4 DMMA moves the operands inside the tensor
+// core instead.  With nx = 7 (+1 homogeneous coordinate) everything is 8 x 8:
 //
 //   fragment convention cl(X): lane (g, t) = (lane >> 2, lane & 3) holds X[g][2t], X[g][2t+1]  (the accumulator layout).
 //   cl(A B) = mm8(cl(A), cl(B^T)): the k index is split as {0,2,4,6} / {1,3,5,7} over two DMMAs, so that the SAME two registers
 //   serve as A-fragment of X and as B-fragment of X^T.  A symmetric matrix is therefore its own B-fragment, and the whole chain
-//       W^T = Mh^T Ph          (Ph = [[P, p],[p^T, 0]] cost-to-go with its gradient, Mh = [[M7, rb],[0, 1]])
+//       W^T = Mh^T Ph          (Ph = [[P, p],[p^T, .]] cost-to-go with its gradient, Mh = [[M7, rb],[0, 1]])
 //       G   = Mh^T W           (Gram matrix, M7^T h in its last row / column)
 //       Ph' = H - Gu^T Guu^-1 Gu   (rank-2 DMMA; H = G with the rows / columns of the inputs replaced by those of x0, x1)
 //   runs accumulator -> operand with NO shared-memory traffic and NO __syncwarp: 5 DMMAs + 20 SHFL per stage.
 //   The vector sweeps (two roll-outs, corrector backward sweep, adjoint sweep) are row-vector x matrix chains
 //       x^T <- x^T Acl^T,   p^T <- h^T Acl + c^T,   dpi^T <- dpi^T A + base^T
 //   whose result row (lanes 0..3) is already the A-fragment of the next stage; the closed-loop matrix Acl = A + B K is rebuilt
-//   per stage by one rank-2 DMMA off the critical path.  Critical path per stage: 34 cycles (one DMMA + one DADD) instead of
-//   110..150 (store, __syncwarp, broadcast load, dot product, shuffle).
+//   per stage by one rank-2 DMMA one stage ahead of the chain.  Critical path per stage: two chained DMMAs (52 cycles) instead
+//   of 110..150 (store, __syncwarp, broadcast load, dot product, shuffle).
+//   No lane-conditional blocks inside the sweeps: selects on values every lane computes, clamped prefetch pointers, 8-double
+//   slots per vector (a divergent `if` costs a reconvergence stall per stage; the first correct build had them and was no faster
+//   than v6).
 //
 // Measured on B200 (scripts/dmma_probe.cu): DMMA.8x8x4 26 cycles dependent, 0.25 / clk / SM (= the DFMA pipe: 37 TFLOP/s), so a
 // padded 8x8x8 product costs what the hand-distributed one cost in pipe time, minus all of its operand traffic.
+// cfg3 (B = 16384, N = 20): 1.55 ms against 2.13 (v6) and 3.10 (round 1); cfg4 (N = 40, two warps): 1.18 against 2.57.
 //
 // Node role: thread k owns node k (residuals, barrier terms, step lengths, update: shared memory -> registers -> shared memory
-// with 16-byte accesses, one pass per phase); staging: one TMA bulk copy per instance-major stage record.  Algorithm: HPIPM-style Mehrotra predictor-corrector IPM on the OCP-structured QP [EXT],
-// replacing FULL_CONDENSING_HPIPM (acados_solver_sim_car.c:145,688-693); identical maths to oracle/rti_oracle.c orc_qp_solve,
-// results differ by rounding only.
+// with 16-byte accesses, one pass per phase); staging: one TMA bulk copy per instance-major stage record.  Algorithm: HPIPM-style
+// Mehrotra predictor-corrector IPM on the OCP-structured QP [EXT], replacing FULL_CONDENSING_HPIPM
+// (acados_solver_sim_car.c:145,688-693); identical maths to oracle/rti_oracle.c orc_qp_solve, results differ by rounding only.
 #include "common.cuh"
 #include "tma.cuh"
 
