@@ -210,12 +210,15 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     // the shared-memory-resident warp kernel (variant 7) stages instance-major linearisation records by TMA; every other
     // feedback kernel reads the SoA rows.  Exactly one of the two layouts exists per handle.
     const bool use_im = (variant == 7) && N <= 63 && !frenet;
+    // Frenet variant: the tensor-core kernel (qp_mma_f.cu) pulls 74-double instance-major records; written next to the dense
+    // SoA linearisation the SQP residual kernel and the dense QP kernel read
+    const bool use_im_f = frenet && (h->qp_variant == 0 || h->qp_variant == 7) && N <= 63 && h->P.o.con_set == 0;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
         {&P.nlp_res, 4},
         {&P.lin_d, frenet ? (size_t)(N + 1) * DL_ROWS : 0}, {&kap, frenet ? (size_t)N : 0},
-        {&P.lin, use_im ? 0 : (size_t)(N + 1) * LIN_ROWS}, {&P.lin_im, use_im ? (size_t)(N + 1) * LIM_STRIDE : 0}, {&P.res_out, 4},
+        {&P.lin, (use_im || frenet) ? 0 : (size_t)(N + 1) * LIN_ROWS}, {&P.lin_im, use_im ? (size_t)(N + 1) * LIM_STRIDE : (use_im_f ? (size_t)(N + 1) * 74 : 0)}, {&P.res_out, 4},
     };
     if (need_ws3) items.push_back({&P.ws, (size_t)qp_smem_ws_rows(N)});
     if (need_ws1) {
@@ -556,6 +559,12 @@ static int launch_feedback(admpc_batch *h)
         // (ADMPC_QP_VARIANT=1) the dense thread-per-instance kernel + separate update
         // (a spline curvature makes the column of s dense: A(:,0) != e0, outside the structure qp_warp_f exploits)
         // (the variant's own constraint set, con_set = 1, is implemented by the dense kernel only)
+        if ((h->qp_variant == 0 || h->qp_variant == 7) && P.kap_K == 0 && P.o.con_set == 0 && launch_qp_mma_f(P, h->stream)) {
+            if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
+            h->launches += 1;
+            h->gat_fresh = h->gat_on;
+            return 0;
+        }
         if (h->qp_variant != 1 && P.kap_K == 0 && P.o.con_set == 0 && launch_qp_warp_f(P, h->stream)) {
             if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
             h->launches += 1;
@@ -746,6 +755,7 @@ __global__ void expand_lin_kernel(const Params P, double *A, double *Bm, double 
 extern "C" int admpc_batch_get_lin(admpc_batch *h, double *A, double *Bm, double *b, double *q, double *r)
 {
     if (!h || !A || !Bm || !b || !q || !r) return ADMPC_E_ARG;
+    if (h->P.o.model_variant != 0) { admpc_set_error("admpc_batch_get_lin", "structured linearisation of the Cartesian model only"); return ADMPC_E_UNSUPPORTED; }
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     const int N = h->P.o.N, B = h->P.B;
     const size_t nA = (size_t)B * N * 49, nB = (size_t)B * N * 14, nb = (size_t)B * N * 7, nq = (size_t)B * (N + 1) * 7, nr = (size_t)B * N * 2;

@@ -158,6 +158,7 @@ void launch_capsule_gather(const Params &P, double *out, cudaStream_t s);
 void launch_gp_select(const Params &P, const double *xq, const double *uq, int *sel, cudaStream_t s);
 void launch_qp_dense(const Params &P, cudaStream_t s);
 bool launch_qp_warp_f(const Params &P, cudaStream_t s);   // Frenet structure, false: N > 63
+bool launch_qp_mma_f(const Params &P, cudaStream_t s);    // Frenet structure on the FP64 tensor cores, false: N > 63 or no instance-major records
 void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_sqp_finalize(const Params &P, cudaStream_t s);
