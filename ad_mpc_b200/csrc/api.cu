@@ -212,13 +212,15 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     const bool use_im = (variant == 7) && N <= 63 && !frenet;
     // Frenet variant: the tensor-core kernel (qp_mma_f.cu) pulls 74-double instance-major records; written next to the dense
     // SoA linearisation the SQP residual kernel and the dense QP kernel read
-    const bool use_im_f = frenet && (h->qp_variant == 0 || h->qp_variant == 7) && N <= 63 && h->P.o.con_set == 0;
+    // (80-double generic records when the column of s is dense or the variant's own constraint set is on: qp_mma_g.cu; which
+    // of the two formats a step writes is decided per solve, the curvature form can change between solves)
+    const bool use_im_f = frenet && (h->qp_variant == 0 || h->qp_variant == 7) && N <= 63;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
         {&P.nlp_res, 4},
         {&P.lin_d, frenet ? (size_t)(N + 1) * DL_ROWS : 0}, {&kap, frenet ? (size_t)N : 0},
-        {&P.lin, (use_im || frenet) ? 0 : (size_t)(N + 1) * LIN_ROWS}, {&P.lin_im, use_im ? (size_t)(N + 1) * LIM_STRIDE : (use_im_f ? (size_t)(N + 1) * 74 : 0)}, {&P.res_out, 4},
+        {&P.lin, (use_im || frenet) ? 0 : (size_t)(N + 1) * LIN_ROWS}, {&P.lin_im, use_im ? (size_t)(N + 1) * LIM_STRIDE : (use_im_f ? (size_t)(N + 1) * 80 : 0)}, {&P.res_out, 4},
     };
     if (need_ws3) items.push_back({&P.ws, (size_t)qp_smem_ws_rows(N)});
     if (need_ws1) {
@@ -549,6 +551,12 @@ extern "C" int admpc_batch_reset(admpc_batch *h)
     return 0;
 }
 
+// Frenet variant: record format of this solve (common.cuh Params::lim_fmt)
+static void frenet_record_format(admpc_batch *h)
+{
+    h->P.lim_fmt = (h->P.o.model_variant == 1 && (h->P.kap_K > 0 || h->P.o.con_set == 1)) ? 1 : 0;
+}
+
 // feedback phase + update of one iteration (shared by the RTI step and the full-SQP loop)
 static int launch_feedback(admpc_batch *h)
 {
@@ -558,7 +566,14 @@ static int launch_feedback(admpc_batch *h)
         // Frenet variant: warp-per-instance kernel on the 6x8 stage structure (N <= 63, fused update), else / on request
         // (ADMPC_QP_VARIANT=1) the dense thread-per-instance kernel + separate update
         // (a spline curvature makes the column of s dense: A(:,0) != e0, outside the structure qp_warp_f exploits)
-        // (the variant's own constraint set, con_set = 1, is implemented by the dense kernel only)
+        // -> the generic tensor-core kernel qp_mma_g (no trivial column assumed, both constraint sets), dense kernel as
+        // cross-check and N > 63 fallback
+        if ((h->qp_variant == 0 || h->qp_variant == 7) && P.lim_fmt == 1 && launch_qp_mma_g(P, h->stream)) {
+            if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
+            h->launches += 1;
+            h->gat_fresh = h->gat_on;
+            return 0;
+        }
         if ((h->qp_variant == 0 || h->qp_variant == 7) && P.kap_K == 0 && P.o.con_set == 0 && launch_qp_mma_f(P, h->stream)) {
             if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
             h->launches += 1;
@@ -601,6 +616,7 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
 {
     if (!h) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
+    frenet_record_format(h);
     const Params &P = h->P;
     CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
     CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
@@ -622,6 +638,7 @@ static int solve_sqp_impl(admpc_batch *h, int max_iter, const double *tol4, int 
 {
     if (!h || max_iter < 0) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
+    frenet_record_format(h);
     const Params &P = h->P;
     const double dflt[4] = {1e-6, 1e-6, 1e-6, 1e-6};            // sim_car_acados_ocp.json:870-873
     const double *tol = tol4 ? tol4 : dflt;

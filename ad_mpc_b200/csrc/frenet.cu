@@ -136,9 +136,11 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
 #pragma unroll
         for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = o.We[c] * (x[c] - AT(P.yref, N * 9 + c));
         if (P.lin_im) {
-            double *rec = P.lin_im + ((size_t)N * Bp + i) * 74;
+            // terminal record: q_N and x_N at the offsets of the stage records (74-double Frenet / 80-double generic format)
+            double *rec = P.lin_im + ((size_t)N * Bp + i) * (P.lim_fmt == 1 ? 80 : 74);
+            const int oq = (P.lim_fmt == 1) ? 61 : 55, ox = (P.lim_fmt == 1) ? 70 : 64;
 #pragma unroll
-            for (int c = 0; c < 7; c++) { rec[55 + c] = o.We[c] * (x[c] - AT(P.yref, N * 9 + c)); rec[64 + c] = x[c]; }
+            for (int c = 0; c < 7; c++) { rec[oq + c] = o.We[c] * (x[c] - AT(P.yref, N * 9 + c)); rec[ox + c] = x[c]; }
         }
         return;
     }
@@ -212,7 +214,30 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
     for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = Ts * o.W[c] * (x[c] - AT(P.yref, k * 9 + c));
 #pragma unroll
     for (int c = 0; c < 2; c++) AT(lin, DL_r + c) = Ts * o.W[7 + c] * (u[c] - AT(P.yref, k * 9 + 7 + c));
-    if (P.lin_im) {
+    if (P.lin_im && P.lim_fmt == 1) {
+        // generic instance-major record (qp_mma_g.cu): M = [B | A] rows 0..5 column-major (6 x 9, the column of s included: a
+        // spline curvature makes it dense), b, q, r, the linearisation point and one pad; 640 bytes per (stage, instance)
+        double *rec = P.lin_im + ((size_t)k * Bp + i) * 80;
+#pragma unroll
+        for (int c = 0; c < 9; c++)
+#pragma unroll
+            for (int r = 0; r < 6; r += 2) {
+                const double v0 = (c < 2) ? h * acc[r][7 + c] : h * acc[r][c - 2] + ((r == c - 2) ? 1.0 : 0.0);
+                const double v1 = (c < 2) ? h * acc[r + 1][7 + c] : h * acc[r + 1][c - 2] + ((r + 1 == c - 2) ? 1.0 : 0.0);
+                *reinterpret_cast<double2 *>(rec + c * 6 + r) = make_double2(v0, v1);
+            }
+        double tail[26];                       // b (7) q (7) r (2) x (7) u (2) pad
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            tail[c] = fma(h, ax[c], x[c]) - AT(P.xb, (k + 1) * 7 + c);
+            tail[7 + c] = Ts * o.W[c] * (x[c] - AT(P.yref, k * 9 + c));
+            tail[16 + c] = x[c];
+        }
+        tail[14] = Ts * o.W[7] * (u[0] - AT(P.yref, k * 9 + 7)); tail[15] = Ts * o.W[8] * (u[1] - AT(P.yref, k * 9 + 8));
+        tail[23] = u[0]; tail[24] = u[1]; tail[25] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 26; c += 2) *reinterpret_cast<double2 *>(rec + 54 + c) = make_double2(tail[c], tail[c + 1]);
+    } else if (P.lin_im) {
         // instance-major record for the tensor-core QP kernel (qp_mma_f.cu LIMF_*): M = [B | A(:,1:7)] rows 0..5 column-major,
         // b, q, r and the linearisation point; one contiguous 592-byte block per (stage, instance), pulled by one TMA bulk copy
         double *rec = P.lin_im + ((size_t)k * Bp + i) * 74;

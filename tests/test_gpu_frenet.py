@@ -324,6 +324,43 @@ def test_frenet_own_constraint_set_full_sqp_and_spline_curvature():
     s.close()
 
 
+@pytest.mark.parametrize("N,own_set,spline", [(20, True, True), (20, False, True), (20, True, False), (40, True, True)])
+def test_frenet_generic_tensor_core_kernel_agrees_with_the_dense_kernel(monkeypatch, N, own_set, spline):
+    """qp_mma_g (dense column of s and / or con_set = 1 on the FP64 tensor cores, the default for N <= 63) against the dense
+    thread-per-instance kernel (ADMPC_QP_VARIANT=1): independent implementations, same statuses / iteration counts, 1e-8
+    on the trajectories and 1e-6 on the multipliers; the launch count proves which kernel ran (fused update: 2 per step)."""
+    B = 40
+    batch, breaks, coef = _spline_batch(B, N, 500 + N)
+    opts = _frenet_own_opts(N) if own_set else default_opts(N, model_variant=1, lbu=[-3.0, -1.0], ubu=[2.0, 1.0])
+    if own_set:                                         # boxes tight enough that hard and soft rows are active
+        opts.lbx2, opts.ubx2, opts.lbx, opts.ubx = -0.6, 0.6, -0.08, 0.08
+        opts.lbu[0], opts.lbu[1], opts.ubu[0], opts.ubu[1] = -2.0, -0.5, 1.5, 0.5
+        batch["x_init"][:, :, 1] = np.clip(batch["x_init"][:, :, 1], -0.5, 0.5)
+        batch["x0"][:, 1] = np.clip(batch["x0"][:, 1], -0.5, 0.5)
+    out, launches = {}, {}
+    for v in (0, 1):
+        if v:
+            monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
+        s = BatchSolver(B, opts)
+        if spline:
+            s.set_kappa_spline(breaks, coef)
+        n0 = s.kernel_launches()
+        out[v] = _step(s, batch, kappa=None if spline else batch["kappa"])
+        launches[v] = s.kernel_launches() - n0
+        out[v]["lam"], out[v]["t"] = s.get_lam(), s.get_t()
+        out[v]["sl"], out[v]["su"] = s.get_slacks()
+        s.close()
+    monkeypatch.delenv("ADMPC_QP_VARIANT")
+    assert launches[1] - launches[0] == 1               # prepare + fused QP / update  vs  prepare + dense QP + update
+    a, b = out[0], out[1]
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["qp_status"], b["qp_status"])
+    good = b["status"] == 0
+    assert good.any() and np.array_equal(a["qp_iter"][good], b["qp_iter"][good])
+    assert mixed_err(a["u"], b["u"]) <= TOL and mixed_err(a["x"], b["x"]) <= TOL
+    for f in ("pi", "lam", "t", "sl", "su"):
+        assert mixed_err(a[f][good], b[f][good]) <= 1e-6, f
+
+
 def test_con_set_1_needs_the_frenet_model():
     from ad_mpc_b200 import _lib
     with pytest.raises(_lib.AdmpcError):
