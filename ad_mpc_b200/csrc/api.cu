@@ -210,10 +210,8 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     // the shared-memory-resident warp kernel (variant 7) stages instance-major linearisation records by TMA; every other
     // feedback kernel reads the SoA rows.  Exactly one of the two layouts exists per handle.
     const bool use_im = (variant == 7) && N <= 63 && !frenet;
-    // Frenet variant: the tensor-core kernel (qp_mma_f.cu) pulls 74-double instance-major records; written next to the dense
+    // Frenet variant: the tensor-core kernel (qp_mma_g.cu) pulls 80-double instance-major records; written next to the dense
     // SoA linearisation the SQP residual kernel and the dense QP kernel read
-    // (80-double generic records when the column of s is dense or the variant's own constraint set is on: qp_mma_g.cu; which
-    // of the two formats a step writes is decided per solve, the curvature form can change between solves)
     const bool use_im_f = frenet && (h->qp_variant == 0 || h->qp_variant == 7) && N <= 63;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
@@ -353,7 +351,7 @@ static int upload_gp(admpc_batch *h, int K, int nout, int M, int dz, const int *
 static int gp_res_alloc(admpc_batch *h)
 {
     Params &P = h->P;
-    if (!P.o.gp_enabled || P.o.model_variant != 0) return 0;          // the Frenet variant keeps its fused preparation kernel
+    if (!P.o.gp_enabled) return 0;
     const size_t need = (size_t)P.o.N * 4 * P.o.gp_nout * (1 + P.o.gp_dz) * P.Bp * sizeof(double);
     if (need > h->gp_res_cap) {
         cudaFree(h->gp_res);
@@ -551,30 +549,17 @@ extern "C" int admpc_batch_reset(admpc_batch *h)
     return 0;
 }
 
-// Frenet variant: record format of this solve (common.cuh Params::lim_fmt)
-static void frenet_record_format(admpc_batch *h)
-{
-    h->P.lim_fmt = (h->P.o.model_variant == 1 && (h->P.kap_K > 0 || h->P.o.con_set == 1)) ? 1 : 0;
-}
-
 // feedback phase + update of one iteration (shared by the RTI step and the full-SQP loop)
 static int launch_feedback(admpc_batch *h)
 {
     const Params &P = h->P;
     h->gat_fresh = false;
     if (P.o.model_variant == 1) {
-        // Frenet variant: warp-per-instance kernel on the 6x8 stage structure (N <= 63, fused update), else / on request
-        // (ADMPC_QP_VARIANT=1) the dense thread-per-instance kernel + separate update
-        // (a spline curvature makes the column of s dense: A(:,0) != e0, outside the structure qp_warp_f exploits)
-        // -> the generic tensor-core kernel qp_mma_g (no trivial column assumed, both constraint sets), dense kernel as
-        // cross-check and N > 63 fallback
-        if ((h->qp_variant == 0 || h->qp_variant == 7) && P.lim_fmt == 1 && launch_qp_mma_g(P, h->stream)) {
-            if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
-            h->launches += 1;
-            h->gat_fresh = h->gat_on;
-            return 0;
-        }
-        if ((h->qp_variant == 0 || h->qp_variant == 7) && P.kap_K == 0 && P.o.con_set == 0 && launch_qp_mma_f(P, h->stream)) {
+        // Frenet variant: the tensor-core kernel qp_mma_g (N <= 63, no trivial column assumed -- a spline curvature makes the
+        // column of s dense --, both constraint sets, fused update); on request the round-1 warp kernel on the 6x8 stage
+        // structure (ADMPC_QP_VARIANT=4: per-node curvature and con_set = 0 only) or the dense thread-per-instance kernel +
+        // separate update (ADMPC_QP_VARIANT=1, also the N > 63 fallback)
+        if ((h->qp_variant == 0 || h->qp_variant == 7) && launch_qp_mma_g(P, h->stream)) {
             if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
             h->launches += 1;
             h->gat_fresh = h->gat_on;
@@ -616,14 +601,13 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
 {
     if (!h) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
-    frenet_record_format(h);
     const Params &P = h->P;
     CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
     CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[1], h->stream));
     if (P.o.model_variant == 1) launch_prepare_dense(P, h->stream);
     else launch_prepare(P, h->stream);
-    h->launches += (P.o.model_variant == 0 && P.o.gp_enabled) ? 2 : 1;      // GP: sweep kernel + sensitivity kernel
+    h->launches += P.o.gp_enabled ? 2 : 1;      // GP: sweep kernel + sensitivity kernel
     if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[2], h->stream));
     if (int r = launch_feedback(h)) return r;
     CUDA_CHECK_RET(cudaEventRecord(h->ev[4], h->stream));
@@ -638,7 +622,6 @@ static int solve_sqp_impl(admpc_batch *h, int max_iter, const double *tol4, int 
 {
     if (!h || max_iter < 0) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
-    frenet_record_format(h);
     const Params &P = h->P;
     const double dflt[4] = {1e-6, 1e-6, 1e-6, 1e-6};            // sim_car_acados_ocp.json:870-873
     const double *tol = tol4 ? tol4 : dflt;
@@ -653,7 +636,7 @@ static int solve_sqp_impl(admpc_batch *h, int max_iter, const double *tol4, int 
         CUDA_CHECK_RET(cudaMemsetAsync(ctr, 0, sizeof(int), h->stream));
         if (P.o.model_variant == 1) { launch_prepare_dense(P, h->stream); launch_nlp_res_dense(P, it, tol, ctr, h->stream); }
         else { launch_prepare(P, h->stream); launch_nlp_res(P, it, tol, ctr, h->stream); }
-        h->launches += (P.o.model_variant == 0 && P.o.gp_enabled) ? 3 : 2;
+        h->launches += P.o.gp_enabled ? 3 : 2;
         CUDA_CHECK_RET(cudaMemcpyAsync(h->sqp_active_host, ctr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
         running = h->sqp_active_host[0];

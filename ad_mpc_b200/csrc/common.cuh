@@ -69,7 +69,6 @@ struct Params {
     // linearisation: SoA rows (lin) or instance-major records (lin_im), exactly one of them per handle
     double *lin;
     double *lin_im;
-    int lim_fmt;         // Frenet variant: 0 = 74-double records of qp_mma_f.cu (column of s trivial), 1 = 80-double generic records of qp_mma_g.cu
     double *gpr;         // GP mean / feature gradient at the 4 RK4 stage points of every interval: [N*4*nout*(1+dz)][Bp] (prepare.cu)
     // QP solution (delta form) + workspace
     double *dx, *du, *pi, *lam, *t, *sl, *su;
@@ -141,6 +140,7 @@ struct SmemGuard {
 
 // kernel launchers (defined in the .cu files)
 void launch_prepare(const Params &P, cudaStream_t s);
+void launch_gp_sweep(const Params &P, cudaStream_t s);   // pass 1 of a GP-augmented preparation: GP mean / gradient at the RK4 stage points -> gpr
 void launch_qp(const Params &P, cudaStream_t s);
 bool launch_qp_smem(const Params &P, cudaStream_t s);   // false: horizon too long for the shared-memory variant
 int qp_smem_ws_rows(int N);
@@ -159,8 +159,7 @@ void launch_capsule_gather(const Params &P, double *out, cudaStream_t s);
 void launch_gp_select(const Params &P, const double *xq, const double *uq, int *sel, cudaStream_t s);
 void launch_qp_dense(const Params &P, cudaStream_t s);
 bool launch_qp_warp_f(const Params &P, cudaStream_t s);   // Frenet structure, false: N > 63
-bool launch_qp_mma_g(const Params &P, cudaStream_t s);    // Frenet variant with a dense column of s (spline curvature) and / or con_set = 1, false: N > 63 or no generic records
-bool launch_qp_mma_f(const Params &P, cudaStream_t s);    // Frenet structure on the FP64 tensor cores, false: N > 63 or no instance-major records
+bool launch_qp_mma_g(const Params &P, cudaStream_t s);    // Frenet variant on the FP64 tensor cores (dense column of s, both constraint sets), false: N > 63 or no instance-major records
 void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_sqp_finalize(const Params &P, cudaStream_t s);

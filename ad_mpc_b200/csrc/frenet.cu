@@ -34,13 +34,15 @@
 __device__ __forceinline__ double nmaxd(double a, double b) { return (a > b || a != a) ? a : b; }
 
 // dense f, Jx (7x7), Ju (7x2) of the Frenet variant at (x, u); rows 3..6 (+ GP) from the shared model code
-template <bool GP>
-__device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *gpsm, int gp_stride, uint32_t tab, const double x[7],
+// GPR: the GP mean / feature gradient of this stage point come from the sweep kernel's results (prepare.cu gp_sweep_kernel<FR>)
+template <bool GPR>
+__device__ __forceinline__ void frenet_eval(const admpc_opts &o, const GpOut &G, const double x[7],
                                             const double u[2], double p, double kap, double dkap, const double gpx[7], double trig,
                                             double f[7], double Jx[7][7], double Ju[7][2])
 {
     Jac J;
-    model_eval<GP>(o, gpsm, gp_stride, tab, x, u, p, gpx, trig, f, J);
+    model_eval<false>(o, nullptr, 0, 0u, x, u, p, gpx, trig, f, J);
+    if (GPR) gp_apply(o, trig, G, f, J);
 #pragma unroll
     for (int r = 0; r < 7; r++) {
 #pragma unroll
@@ -72,62 +74,17 @@ __device__ __forceinline__ void frenet_eval(const admpc_opts &o, const double *g
     Jx[2][0] = -ey * dkap * sd0 - ey * kap * Jx[0][0];
 }
 
-// kappa(s) of instance i: piecewise cubic, SoA rows [breaks (K+1) | coef (K x 4, lowest power first)][Bp]; the end pieces
-// extrapolate.  The reference evaluates CasADi's interpolant('kapparef_s', 'bspline', ...) at this place.
-__device__ __forceinline__ void kappa_spline(const Params &P, int i, double s, double &kap, double &dkap)
-{
-    const int K = P.kap_K, Bp = P.Bp;
-    const double *sp = P.kap_sp + i;
-    int j = 0;
-    while (j + 1 < K && s >= sp[(size_t)(j + 1) * Bp]) j++;
-    const double t = s - sp[(size_t)j * Bp];
-    const double *c = sp + (size_t)(K + 1 + 4 * j) * Bp;
-    const double c0 = c[0], c1 = c[(size_t)Bp], c2 = c[(size_t)2 * Bp], c3 = c[(size_t)3 * Bp];
-    kap = ((c3 * t + c2) * t + c1) * t + c0;
-    dkap = (3.0 * c3 * t + 2.0 * c2) * t + c1;
-}
-
-__device__ __forceinline__ uint32_t fr_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
+// GP: pass 2 of the two-pass preparation -- the GP mean / feature gradient at the four RK4 stage points were written to gpr by
+// gp_sweep_kernel<.., FR = true> (prepare.cu); the 126-double sensitivity state never shares the SM with a sweep.
 template <bool GP>
-__global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Params P)
+__global__ void __launch_bounds__(128, 2) prepare_dense_kernel(const Params P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    const double *gpsm = nullptr;
-    if (GP) {
-        // GP blob staged by TMA bulk copies exactly as in prepare.cu
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fr_smem_u32(&bar)), "r"(1));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fr_smem_u32(&bar)), "r"((uint32_t)P.gp.bytes) : "memory");
-            uint32_t off = 0;
-            while (off < (uint32_t)P.gp.bytes) {
-                const uint32_t n = min((uint32_t)P.gp.bytes - off, 65536u);
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 fr_smem_u32(smem_raw + off)),
-                             "l"((const unsigned char *)P.gp.blob + off), "r"(n), "r"(fr_smem_u32(&bar))
-                             : "memory");
-                off += n;
-            }
-        }
-        gpsm = reinterpret_cast<const double *>(smem_raw);
-        asm volatile(
-            "{\n .reg .pred p;\n WAIT_%=:\n"
-            " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(fr_smem_u32(&bar)), "r"(0) : "memory");
-    }
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (i >= P.B || P.lin_bad[i] == 2) return;
     const double h = o.dt, Ts = o.dt;
-    const double *gpm = GP ? gpsm + (size_t)P.gp_sel[i] * P.gp.model_doubles : nullptr;      // this instance's cluster model
-    const uint32_t tab = GP ? (uint32_t)__cvta_generic_to_shared(gpsm + (size_t)P.gp.n_models * P.gp.model_doubles) : 0u;
     double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
     double x[7];
 #pragma unroll
@@ -136,11 +93,10 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
 #pragma unroll
         for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = o.We[c] * (x[c] - AT(P.yref, N * 9 + c));
         if (P.lin_im) {
-            // terminal record: q_N and x_N at the offsets of the stage records (74-double Frenet / 80-double generic format)
-            double *rec = P.lin_im + ((size_t)N * Bp + i) * (P.lim_fmt == 1 ? 80 : 74);
-            const int oq = (P.lim_fmt == 1) ? 61 : 55, ox = (P.lim_fmt == 1) ? 70 : 64;
+            // terminal record: q_N and x_N at the offsets of the stage records (qp_mma_g.cu W_LQ / W_XB)
+            double *rec = P.lin_im + ((size_t)N * Bp + i) * 80;
 #pragma unroll
-            for (int c = 0; c < 7; c++) { rec[oq + c] = o.We[c] * (x[c] - AT(P.yref, N * 9 + c)); rec[ox + c] = x[c]; }
+            for (int c = 0; c < 7; c++) { rec[61 + c] = o.We[c] * (x[c] - AT(P.yref, N * 9 + c)); rec[70 + c] = x[c]; }
         }
         return;
     }
@@ -150,7 +106,10 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
     double kap = AT(P.kappa, k), dkap = 0.0;
     const double trig = (GP && o.gp_stage0_trigger && k == 0) ? 1.0 : 0.0;
 #pragma unroll
-    for (int c = 0; c < 7; c++) gpx[c] = (trig != 0.0) ? AT(P.gps, c) : 0.0;
+    for (int c = 0; c < 7; c++) gpx[c] = 0.0;
+    const int R = GP ? gpr_rows(o) : 0, dz = o.gp_dz;
+    GpOut Gn;
+    if (GP) gpr_load(P, o, (k * 4) * R, dz, i, Gn);
 
     // classic RK4 on [x | S], S = [S_x (7x7) | S_u (7x2)], S(0) = [I 0]
     double K[7][9], acc[7][9], kx[7], ax[7];
@@ -169,7 +128,9 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
 #pragma unroll
         for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
         if (P.kap_K > 0) kappa_spline(P, i, xs[0], kap, dkap);      // curvature at this sub-stage's own arc length
-        frenet_eval<GP>(o, gpm, P.gp.stride_out, tab, xs, u, pk, kap, dkap, gpx, trig, f, Jx, Ju);
+        const GpOut G = Gn;                          // loaded one stage ahead
+        if (GP && s < 3) gpr_load(P, o, (k * 4 + s + 1) * R, dz, i, Gn);
+        frenet_eval<GP>(o, G, xs, u, pk, kap, dkap, gpx, trig, f, Jx, Ju);
 #pragma unroll
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
 #pragma unroll
@@ -214,8 +175,8 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
     for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = Ts * o.W[c] * (x[c] - AT(P.yref, k * 9 + c));
 #pragma unroll
     for (int c = 0; c < 2; c++) AT(lin, DL_r + c) = Ts * o.W[7 + c] * (u[c] - AT(P.yref, k * 9 + 7 + c));
-    if (P.lin_im && P.lim_fmt == 1) {
-        // generic instance-major record (qp_mma_g.cu): M = [B | A] rows 0..5 column-major (6 x 9, the column of s included: a
+    if (P.lin_im) {
+        // instance-major record of the tensor-core QP kernel (qp_mma_g.cu): M = [B | A] rows 0..5 column-major (6 x 9, the column of s included: a
         // spline curvature makes it dense), b, q, r, the linearisation point and one pad; 640 bytes per (stage, instance)
         double *rec = P.lin_im + ((size_t)k * Bp + i) * 80;
 #pragma unroll
@@ -237,30 +198,6 @@ __global__ void __launch_bounds__(128, GP ? 6 : 2) prepare_dense_kernel(const Pa
         tail[23] = u[0]; tail[24] = u[1]; tail[25] = 0.0;
 #pragma unroll
         for (int c = 0; c < 26; c += 2) *reinterpret_cast<double2 *>(rec + 54 + c) = make_double2(tail[c], tail[c + 1]);
-    } else if (P.lin_im) {
-        // instance-major record for the tensor-core QP kernel (qp_mma_f.cu LIMF_*): M = [B | A(:,1:7)] rows 0..5 column-major,
-        // b, q, r and the linearisation point; one contiguous 592-byte block per (stage, instance), pulled by one TMA bulk copy
-        double *rec = P.lin_im + ((size_t)k * Bp + i) * 74;
-        // 16-byte stores: a record is 37 aligned pairs
-#pragma unroll
-        for (int c = 0; c < 8; c++)
-#pragma unroll
-            for (int r = 0; r < 6; r += 2) {
-                const double v0 = (c < 2) ? h * acc[r][7 + c] : h * acc[r][c - 1] + ((r == c - 1) ? 1.0 : 0.0);
-                const double v1 = (c < 2) ? h * acc[r + 1][7 + c] : h * acc[r + 1][c - 1] + ((r + 1 == c - 1) ? 1.0 : 0.0);
-                *reinterpret_cast<double2 *>(rec + c * 6 + r) = make_double2(v0, v1);
-            }
-        double tail[26];                       // b (7) q (7) r (2) x (7) u (2) pad
-#pragma unroll
-        for (int c = 0; c < 7; c++) {
-            tail[c] = fma(h, ax[c], x[c]) - AT(P.xb, (k + 1) * 7 + c);
-            tail[7 + c] = Ts * o.W[c] * (x[c] - AT(P.yref, k * 9 + c));
-            tail[16 + c] = x[c];
-        }
-        tail[14] = Ts * o.W[7] * (u[0] - AT(P.yref, k * 9 + 7)); tail[15] = Ts * o.W[8] * (u[1] - AT(P.yref, k * 9 + 8));
-        tail[23] = u[0]; tail[24] = u[1]; tail[25] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 26; c += 2) *reinterpret_cast<double2 *>(rec + 48 + c) = make_double2(tail[c], tail[c + 1]);
     }
     if (bad) P.lin_bad[i] = 1;
 }
@@ -833,12 +770,8 @@ void launch_prepare_dense(const Params &P, cudaStream_t s)
 {
     dim3 grid((P.B + 127) / 128, P.o.N + 1);
     if (P.o.gp_enabled) {
-        const size_t sm = (size_t)P.gp.bytes;
-        static SmemGuard configured;
-        if (configured.need(sm)) {
-            cudaFuncSetAttribute(prepare_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        }
-        prepare_dense_kernel<true><<<grid, 128, sm, s>>>(P);
+        launch_gp_sweep(P, s);                 // pass 1: GP mean / gradient at the RK4 stage points (shared with the Cartesian model)
+        prepare_dense_kernel<true><<<grid, 128, 0, s>>>(P);
     } else {
         prepare_dense_kernel<false><<<grid, 128, 0, s>>>(P);
     }

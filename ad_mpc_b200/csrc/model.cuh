@@ -346,3 +346,49 @@ __device__ __forceinline__ void model_eval(const admpc_opts &o, const double *__
         gp_apply(o, trig, G, f, J);
     }
 }
+
+// ---- results of the GP sweep kernel (prepare.cu gp_sweep_kernel), read back by the sensitivity kernels of both model variants ------
+// GP results of one RK4 stage, SoA rows of gpr: [(k*4 + s) * R + j*(1+dz) + {0: mean, 1+d: d mean / d z_d}][Bp], R = nout*(1+dz)
+__device__ __forceinline__ int gpr_rows(const admpc_opts &o) { return o.gp_nout * (1 + o.gp_dz); }
+// GP results of one RK4 stage (rows row0 .. row0 + R - 1 of gpr) of instance i
+__device__ __forceinline__ void gpr_load(const Params &P, const admpc_opts &o, int row0, int dz, int i, GpOut &G)
+{
+    const double *in = P.gpr + (size_t)row0 * P.Bp + i;
+#pragma unroll
+    for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
+        G.m[j] = 0.0;
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) G.g[j][d] = 0.0;
+        if (j >= o.gp_nout) continue;
+        G.m[j] = in[(size_t)(j * (1 + dz)) * P.Bp];
+#pragma unroll
+        for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G.g[j][d] = in[(size_t)(j * (1 + dz) + 1 + d) * P.Bp];
+    }
+}
+
+// ---- Frenet variant (frenet.cu; shared with the GP sweep kernel of prepare.cu) --------------------------------------------------
+// kappa(s) of instance i: piecewise cubic, SoA rows [breaks (K+1) | coef (K x 4, lowest power first)][Bp]; the end pieces
+// extrapolate.  The reference evaluates CasADi's interpolant('kapparef_s', 'bspline', ...) at this place.
+__device__ __forceinline__ void kappa_spline(const Params &P, int i, double s, double &kap, double &dkap)
+{
+    const int K = P.kap_K, Bp = P.Bp;
+    const double *sp = P.kap_sp + i;
+    int j = 0;
+    while (j + 1 < K && s >= sp[(size_t)(j + 1) * Bp]) j++;
+    const double t = s - sp[(size_t)j * Bp];
+    const double *c = sp + (size_t)(K + 1 + 4 * j) * Bp;
+    const double c0 = c[0], c1 = c[(size_t)Bp], c2 = c[(size_t)2 * Bp], c3 = c[(size_t)3 * Bp];
+    kap = ((c3 * t + c2) * t + c1) * t + c0;
+    dkap = (3.0 * c3 * t + 2.0 * c2) * t + c1;
+}
+
+// pose rows of the Frenet model at (x, kappa): s', e_y', e_psi' (frenet.cu header); rows 3..6 are the Cartesian model's
+__device__ __forceinline__ void frenet_pose_rows(const double x[7], double kap, double f[7])
+{
+    double sp, cp;
+    sincos(x[2], &sp, &cp);
+    const double ey = x[1], vx = x[3], vy = x[4], r = x[5];
+    const double vt = vx * cp - vy * sp, vn = vx * sp + vy * cp, den = 1.0 - ey * kap;
+    const double sd0 = vt / den;
+    f[0] = sd0; f[1] = vn; f[2] = r - ey * kap * sd0;
+}

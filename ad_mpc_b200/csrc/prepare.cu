@@ -18,9 +18,6 @@
 
 #include "model.cuh"
 
-// GP results of one RK4 stage, SoA rows of gpr: [(k*4 + s) * R + j*(1+dz) + {0: mean, 1+d: d mean / d z_d}][Bp], R = nout*(1+dz)
-__device__ __forceinline__ int gpr_rows(const admpc_opts &o) { return o.gp_nout * (1 + o.gp_dz); }
-
 // ---- pass 1 of the GP-augmented preparation: the GP sweeps -----------------------------------------------------------------
 // One thread per (instance, shooting interval) walks the four RK4 stages of the STATE only (the stage points do not depend
 // on the sensitivities) and evaluates the GP mean and its feature gradient at each of them: 4 sweeps over the M training
@@ -29,7 +26,9 @@ __device__ __forceinline__ int gpr_rows(const admpc_opts &o) { return o.gp_nout 
 // 2.8 GB of DRAM traffic per launch that way); the results (10 doubles per stage at d_z = 4, two outputs) go to gpr.
 // ENS: GP ensemble -- the cluster model is chosen per instance, so the training-set loads use per-thread addresses; a
 // single model keeps warp-uniform addresses (uniform-register LDS), which is measurably cheaper.
-template <int BLOCK, int MINB, bool ENS, int PREC>
+// FR: Frenet variant -- the pose rows of f are the curvilinear ones (curvature per node or from the kappa(s) spline at the
+// sub-stage's own arc length); the GP terms and rows 3..6 are shared with the Cartesian model.
+template <int BLOCK, int MINB, bool ENS, int PREC, bool FR>
 __global__ void __launch_bounds__(BLOCK, MINB) gp_sweep_kernel(const Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -93,6 +92,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) gp_sweep_kernel(const Params P)
         Jac J;
         model_eval<false>(o, nullptr, 0, 0u, xs, u, pk, gpx, trig, f, J);        // nominal f (its Jacobian is dead code here)
         gp_apply(o, trig, G, f, J);
+        if (FR) {
+            double kap = P.kappa[(size_t)k * Bp + i], dkap;
+            if (P.kap_K > 0) kappa_spline(P, i, xs[0], kap, dkap);
+            frenet_pose_rows(xs, kap, f);
+        }
 #pragma unroll
         for (int c = 0; c < 7; c++) kx[c] = f[c];
     }
@@ -137,22 +141,6 @@ __global__ void __launch_bounds__(128, PREP_MINB) prepare_kernel(const Params P)
     }
     if (!active) return;
     prepare_body<GPR, IM>(P, i, k, IM ? P.lin_im + ((size_t)k * Bp + i) * LIM_STRIDE : P.lin + (size_t)k * LIN_ROWS * Bp + i);
-}
-
-// GP results of one RK4 stage (rows row0 .. row0 + R - 1 of gpr) of instance i
-__device__ __forceinline__ void gpr_load(const Params &P, const admpc_opts &o, int row0, int dz, int i, GpOut &G)
-{
-    const double *in = P.gpr + (size_t)row0 * P.Bp + i;
-#pragma unroll
-    for (int j = 0; j < ADMPC_GPOUT_MAX; j++) {
-        G.m[j] = 0.0;
-#pragma unroll
-        for (int d = 0; d < ADMPC_DZMAX; d++) G.g[j][d] = 0.0;
-        if (j >= o.gp_nout) continue;
-        G.m[j] = in[(size_t)(j * (1 + dz)) * P.Bp];
-#pragma unroll
-        for (int d = 0; d < ADMPC_DZMAX; d++) if (d < dz) G.g[j][d] = in[(size_t)(j * (1 + dz) + 1 + d) * P.Bp];
-    }
 }
 
 // body of one (instance, interval): `lin` is the record to fill (IM: LIM_* offsets, contiguous; else SoA rows, stride Bp)
@@ -280,40 +268,30 @@ __device__ __forceinline__ void prepare_body(const Params &P, int i, int k, doub
     if (bad) P.lin_bad[i] = 1;
 }
 
-void launch_prepare(const Params &P, cudaStream_t s)
+// pass 1 of a GP-augmented preparation (both model variants): the GP sweeps at the four RK4 stage points -> P.gpr
+void launch_gp_sweep(const Params &P, cudaStream_t s)
 {
-    dim3 gridB((P.Bp + 127) / 128, P.o.N + 1);
-    const size_t tile_bytes = (size_t)128 * LIM_PAD * sizeof(double);       // 70.7 KB: needs the opt-in attribute
-    if (P.lin_im) {
-        static SmemGuard cfg;
-        if (cfg.need(tile_bytes)) {
-            cudaFuncSetAttribute(prepare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
-            cudaFuncSetAttribute(prepare_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
-        }
-    }
-    if (!P.o.gp_enabled) {
-        if (P.lin_im) prepare_kernel<false, true><<<gridB, 128, tile_bytes, s>>>(P);
-        else prepare_kernel<false, false><<<gridB, 128, 0, s>>>(P);
-        return;
-    }
-    // pass 1: the GP sweeps.  Register budget capped at 80 (24 warps/SM) for small models; models above 36 KB run
-    // 4 CTAs x 128 registers, models above 54 KB one CTA per SM whose width is picked below.
+    const bool frenet = P.o.model_variant == 1;
     const size_t sm = (size_t)P.gp.bytes;
     const bool ens = P.gp.n_models > 1;
     const int prec = P.o.gp_precision ? 1 : 0;
-#define LAUNCH_GP1(BOUND, MINB, BLK, ENS, PREC)                                                                          \
+    // Register budget capped at 80 (24 warps/SM) for small models; models above 36 KB run 4 CTAs x 128 registers, models
+    // above 54 KB one CTA per SM whose width is picked below.
+#define LAUNCH_GP1(BOUND, MINB, BLK, ENS, PREC, FR)                                                                         \
     do {                                                                                                                \
         static SmemGuard configured;                                                                                   \
         if (configured.need(sm))                                                                                        \
-            cudaFuncSetAttribute(gp_sweep_kernel<BOUND, MINB, ENS, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            cudaFuncSetAttribute(gp_sweep_kernel<BOUND, MINB, ENS, PREC, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
         dim3 grid((P.Bp + (BLK) - 1) / (BLK), P.o.N);                                                                   \
-        gp_sweep_kernel<BOUND, MINB, ENS, PREC><<<grid, (BLK), sm, s>>>(P);                                             \
+        gp_sweep_kernel<BOUND, MINB, ENS, PREC, FR><<<grid, (BLK), sm, s>>>(P);                                             \
+    } while (0)
+#define LAUNCH_GP2(BOUND, MINB, BLK, FR)                                                                                 \
+    do {                                                                                                                \
+        if (ens) { if (prec) LAUNCH_GP1(BOUND, MINB, BLK, true, 1, FR); else LAUNCH_GP1(BOUND, MINB, BLK, true, 0, FR); } \
+        else { if (prec) LAUNCH_GP1(BOUND, MINB, BLK, false, 1, FR); else LAUNCH_GP1(BOUND, MINB, BLK, false, 0, FR); }   \
     } while (0)
 #define LAUNCH_GP(BOUND, MINB, BLK)                                                                                      \
-    do {                                                                                                                \
-        if (ens) { if (prec) LAUNCH_GP1(BOUND, MINB, BLK, true, 1); else LAUNCH_GP1(BOUND, MINB, BLK, true, 0); }       \
-        else { if (prec) LAUNCH_GP1(BOUND, MINB, BLK, false, 1); else LAUNCH_GP1(BOUND, MINB, BLK, false, 0); }         \
-    } while (0)
+    do { if (frenet) LAUNCH_GP2(BOUND, MINB, BLK, true); else LAUNCH_GP2(BOUND, MINB, BLK, false); } while (0)
     if (sm <= 36 * 1024) {
         LAUNCH_GP(128, 6, 128);       // 80 registers, 24 warps/SM
     } else if (sm <= 54 * 1024) {
@@ -340,6 +318,25 @@ void launch_prepare(const Params &P, cudaStream_t s)
         else if (best <= 768) LAUNCH_GP(768, 1, best);
         else LAUNCH_GP(1024, 1, best);
     }
+}
+
+void launch_prepare(const Params &P, cudaStream_t s)
+{
+    dim3 gridB((P.Bp + 127) / 128, P.o.N + 1);
+    const size_t tile_bytes = (size_t)128 * LIM_PAD * sizeof(double);       // 70.7 KB: needs the opt-in attribute
+    if (P.lin_im) {
+        static SmemGuard cfg;
+        if (cfg.need(tile_bytes)) {
+            cudaFuncSetAttribute(prepare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
+            cudaFuncSetAttribute(prepare_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
+        }
+    }
+    if (!P.o.gp_enabled) {
+        if (P.lin_im) prepare_kernel<false, true><<<gridB, 128, tile_bytes, s>>>(P);
+        else prepare_kernel<false, false><<<gridB, 128, 0, s>>>(P);
+        return;
+    }
+    launch_gp_sweep(P, s);
     // pass 2: RK4 + forward sensitivities with the stored GP terms
     if (P.lin_im) prepare_kernel<true, true><<<gridB, 128, tile_bytes, s>>>(P);
     else prepare_kernel<true, false><<<gridB, 128, 0, s>>>(P);

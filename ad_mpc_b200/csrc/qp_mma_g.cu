@@ -1,8 +1,9 @@
-// qp_mma_g.cu -- feedback phase of the FRENET model variant AS THE REFERENCE DEFINES IT (SURVEY 8a A2'): curvature as a spline
-// kappa(s) inside the model (the column of s in A_k is dense: nothing of A but the delta row is trivial) and / or the variant's
-// own constraint set (admpc.h con_set = 1: acceleration soft, steering rate hard, e_y hard, steering angle soft; structure
-// pinned by ad_mpc/debug.json).  ONE (N <= 31) OR TWO (N <= 63) WARPS PER INSTANCE, whole IPM solve resident in shared memory,
-// Riccati sweeps as FP64 DMMA fragment chains -- the design of qp_mma.cu / qp_mma_f.cu for a stage with no exploitable column.
+// qp_mma_g.cu -- feedback phase of the FRENET model variant (SURVEY 8a A2'): ONE (N <= 31) OR TWO (N <= 63) WARPS PER INSTANCE,
+// whole IPM solve resident in shared memory, Riccati sweeps as FP64 DMMA fragment chains -- the design of qp_mma.cu for a stage
+// with no exploitable column.  Covers the variant as the reference defines it: curvature as a spline kappa(s) inside the model
+// (the column of s in A_k is then dense; nothing of A but the delta row is trivial) and the variant's own constraint set
+// (admpc.h con_set = 1: acceleration soft, steering rate hard, e_y hard, steering angle soft; structure pinned by
+// ad_mpc/debug.json), as well as per-node curvature / the shipped constraint set (con_set = 0).
 //
 // Structure: x = [s, e_y, e_psi, v_x, v_y, r, delta], A 7x7 dense except the delta row (0 .. 0 1 | 0, dt), so the stage vector
 // z = (u0, u1, x0..x6) has NINE entries -- one more than a DMMA tile.  The state space (7 + one homogeneous coordinate for the
@@ -17,12 +18,15 @@
 // sweep are the row-vector chains of qp_mma.cu over (x0..x6, 1).  The node role is written over a compile-time descriptor of the
 // bounded quantities (twin of con_get in oracle/rti_oracle.c and frenet.cu), rows [lb(q) | ub(q) | ls(s) | us(s)].
 //
-// Replaces the dense thread-per-instance kernel (frenet.cu qp_dense_kernel, kept as cross-check and N > 63 fallback) on these
-// configurations; identical maths to oracle/rti_oracle.c with model_backend = 2, results differ by rounding only.
+// History: a first tensor-core kernel for this variant (qp_mma_f, z = (u, x1..x6) with the trivial column of s split off and a
+// permuted position layout) covered per-node curvature and con_set = 0 only and measured 2.00 ms at B = 16384, N = 20; this
+// kernel runs the same case in 1.89 ms and replaced it.  Cross-checks kept: qp_warp_f.cu (round-1 warp kernel, per-node
+// curvature, con_set = 0) and the dense thread-per-instance kernel of frenet.cu (everything, also the N > 63 fallback);
+// identical maths to oracle/rti_oracle.c with model_backend = 2, results differ by rounding only.
 #include "common.cuh"
 #include "tma.cuh"
 
-// instance-major linearisation record of the Frenet preparation kernel (frenet.cu, lim_fmt = 1): M = [B | A] rows 0..5
+// instance-major linearisation record of the Frenet preparation kernel (frenet.cu): M = [B | A] rows 0..5
 // column-major (6 x 9), b, q, r, x, u, one pad
 #define LIMG_STRIDE 80
 
@@ -972,11 +976,11 @@ template <int NW, int CS> static void launch_one(const Params &P, size_t sm, cud
     if (configured.need(sm)) cudaFuncSetAttribute(qp_mma_g_kernel<NW, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     qp_mma_g_kernel<NW, CS><<<P.B, 32 * NW, sm, s>>>(P);
 }
-// false: horizon outside the range of this kernel, or no generic instance-major records on this handle
+// false: horizon outside the range of this kernel, or no instance-major records on this handle
 bool launch_qp_mma_g(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
-    if (N > 63 || !P.lin_im || P.lim_fmt != 1) return false;
+    if (N > 63 || !P.lin_im) return false;
     const size_t sm = ((size_t)N * W_RS + T_SIZE) * sizeof(double);
     const bool cs1 = (P.o.con_set == 1);
     if (N <= 31) { if (cs1) launch_one<1, 1>(P, sm, s); else launch_one<1, 0>(P, sm, s); }
