@@ -601,6 +601,8 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
 {
     if (!h) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
+    // Frenet variant, RTI step through the tensor-core kernel: only the instance-major records are consumed
+    h->P.skip_lin_d = (h->P.o.model_variant == 1 && (h->qp_variant == 0 || h->qp_variant == 7) && h->P.o.N <= 63 && h->P.lin_im) ? 1 : 0;
     const Params &P = h->P;
     CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
     CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));
@@ -622,6 +624,7 @@ static int solve_sqp_impl(admpc_batch *h, int max_iter, const double *tol4, int 
 {
     if (!h || max_iter < 0) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
+    h->P.skip_lin_d = 0;                                     // the NLP residual kernel reads the SoA linearisation
     const Params &P = h->P;
     const double dflt[4] = {1e-6, 1e-6, 1e-6, 1e-6};            // sim_car_acados_ocp.json:870-873
     const double *tol = tol4 ? tol4 : dflt;

@@ -81,6 +81,7 @@ struct Params {
     // full SQP mode (sqp.cu): lin_bad == 2 marks an instance that has finished and is skipped by prepare / QP kernels
     // Frenet variant (frenet.cu): dense linearisation [k][DL_ROWS][Bp] (A 49, B 14, b 7, q 7, r 2), curvature [N][Bp]
     double *lin_d;
+    int skip_lin_d;      // 1: this solve runs the tensor-core QP kernel off the instance-major records, nothing reads the SoA rows
     const double *kappa;
     const double *kap_sp;    // Frenet variant: kappa(s) as piecewise cubics [(K+1) breaks | K x 4 coefficients][Bp], kap_K pieces (0: off)
     int kap_K;

@@ -86,12 +86,13 @@ __global__ void __launch_bounds__(128, 2) prepare_dense_kernel(const Params P)
     if (i >= P.B || P.lin_bad[i] == 2) return;
     const double h = o.dt, Ts = o.dt;
     double *lin = P.lin_d + (size_t)k * DL_ROWS * Bp;
+    const bool soa = (P.skip_lin_d == 0);      // the SoA rows feed the dense / warp QP kernels and the SQP residual kernel only
     double x[7];
 #pragma unroll
     for (int c = 0; c < 7; c++) x[c] = AT(P.xb, k * 7 + c);
     if (k == N) {
 #pragma unroll
-        for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = o.We[c] * (x[c] - AT(P.yref, N * 9 + c));
+        for (int c = 0; c < 7; c++) if (soa) AT(lin, DL_q + c) = o.We[c] * (x[c] - AT(P.yref, N * 9 + c));
         if (P.lin_im) {
             // terminal record: q_N and x_N at the offsets of the stage records (qp_mma_g.cu W_LQ / W_XB)
             double *rec = P.lin_im + ((size_t)N * Bp + i) * 80;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(128, 2) prepare_dense_kernel(const Params P)
 #pragma unroll
         for (int c = 0; c < 9; c++) { K[r][c] = 0.0; acc[r][c] = 0.0; }
     }
+    int kap_j = -1;                                  // spline piece of the previous sub-stage
 #pragma unroll 1
     for (int s = 0; s < 4; s++) {
         const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(128, 2) prepare_dense_kernel(const Params P)
         double xs[7], f[7], Jx[7][7], Ju[7][2];
 #pragma unroll
         for (int c = 0; c < 7; c++) xs[c] = fma(ha, kx[c], x[c]);
-        if (P.kap_K > 0) kappa_spline(P, i, xs[0], kap, dkap);      // curvature at this sub-stage's own arc length
+        if (P.kap_K > 0) kappa_spline(P, i, xs[0], kap, dkap, kap_j);      // curvature at this sub-stage's own arc length
         const GpOut G = Gn;                          // loaded one stage ahead
         if (GP && s < 3) gpr_load(P, o, (k * 4 + s + 1) * R, dz, i, Gn);
         frenet_eval<GP>(o, G, xs, u, pk, kap, dkap, gpx, trig, f, Jx, Ju);
@@ -135,26 +137,47 @@ __global__ void __launch_bounds__(128, 2) prepare_dense_kernel(const Params P)
         for (int c = 0; c < 7; c++) { kx[c] = f[c]; ax[c] = fma(bs, f[c], ax[c]); }
 #pragma unroll
         for (int c = 0; c < 9; c++) {
-            double sv[7], kn[7];
+            // Stage input S_in[:,c] = S0[:,c] + ha K[:,c].  Structure kept out of the arithmetic: the velocity rows 3..5 see
+            // x2..x6 and u only (their sensitivities w.r.t. s, e_y stay zero), the delta row is analytic, the pose rows do not
+            // see u or delta directly.  (Terms dropped are exact zeros: results are those of the dense recursion bit for bit.)
+            const bool vel = (c >= 2);
+            double sv[7];
 #pragma unroll
-            for (int r = 0; r < 7; r++) sv[r] = ha * K[r][c] + ((r == c) ? 1.0 : 0.0);
+            for (int r = 0; r < 3; r++) sv[r] = ha * K[r][c] + ((r == c) ? 1.0 : 0.0);
 #pragma unroll
-            for (int r = 0; r < 7; r++) {
-                double v = (c >= 7) ? Ju[r][c - 7] : 0.0;
-#pragma unroll
-                for (int l = 0; l < 7; l++) v = fma(Jx[r][l], sv[l], v);
-                kn[r] = v;
+            for (int r = 3; r < 6; r++) sv[r] = vel ? ha * K[r][c] + ((r == c) ? 1.0 : 0.0) : 0.0;
+            sv[6] = (c == 6) ? 1.0 : ((c == 8) ? ha : 0.0);
+            double kn[3];
+            kn[0] = fma(Jx[0][2], sv[2], fma(Jx[0][1], sv[1], Jx[0][0] * sv[0]));
+            kn[1] = Jx[1][2] * sv[2];
+            kn[2] = fma(Jx[2][2], sv[2], fma(Jx[2][1], sv[1], Jx[2][0] * sv[0]));
+            if (vel) {
+                kn[0] = fma(Jx[0][4], sv[4], fma(Jx[0][3], sv[3], kn[0]));
+                kn[1] = fma(Jx[1][4], sv[4], fma(Jx[1][3], sv[3], kn[1]));
+                kn[2] = fma(Jx[2][5], sv[5], fma(Jx[2][4], sv[4], fma(Jx[2][3], sv[3], kn[2])));
             }
 #pragma unroll
-            for (int r = 0; r < 7; r++) { K[r][c] = kn[r]; acc[r][c] = fma(bs, kn[r], acc[r][c]); }
+            for (int r = 0; r < 3; r++) { K[r][c] = kn[r]; acc[r][c] = fma(bs, kn[r], acc[r][c]); }
+            if (vel) {
+#pragma unroll
+                for (int r = 3; r < 6; r++) {
+                    double v = (c >= 7) ? Ju[r][c - 7] : 0.0;
+#pragma unroll
+                    for (int l = 2; l < 7; l++) v = fma(Jx[r][l], sv[l], v);
+                    K[r][c] = v; acc[r][c] = fma(bs, v, acc[r][c]);
+                }
+            }
         }
     }
+    // delta row: d delta+ / d delta = 1, d delta+ / d u1 = h (acc holds (A - I) / h, B / h)
+#pragma unroll
+    for (int c = 0; c < 9; c++) acc[6][c] = (c == 8) ? 1.0 : 0.0;
     bool bad = false;
 #pragma unroll
     for (int c = 0; c < 7; c++) {
         const double xp = fma(h, ax[c], x[c]);
         bad |= !isfinite(xp);
-        AT(lin, DL_b + c) = xp - AT(P.xb, (k + 1) * 7 + c);
+        if (soa) AT(lin, DL_b + c) = xp - AT(P.xb, (k + 1) * 7 + c);
     }
 #pragma unroll
     for (int r = 0; r < 7; r++) {
@@ -162,19 +185,19 @@ __global__ void __launch_bounds__(128, 2) prepare_dense_kernel(const Params P)
         for (int c = 0; c < 7; c++) {
             const double v = h * acc[r][c] + ((r == c) ? 1.0 : 0.0);
             bad |= !isfinite(v);
-            AT(lin, DL_A + r * 7 + c) = v;
+            if (soa) AT(lin, DL_A + r * 7 + c) = v;
         }
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const double v = h * acc[r][7 + c];
             bad |= !isfinite(v);
-            AT(lin, DL_B + r * 2 + c) = v;
+            if (soa) AT(lin, DL_B + r * 2 + c) = v;
         }
     }
 #pragma unroll
-    for (int c = 0; c < 7; c++) AT(lin, DL_q + c) = Ts * o.W[c] * (x[c] - AT(P.yref, k * 9 + c));
+    for (int c = 0; c < 7; c++) if (soa) AT(lin, DL_q + c) = Ts * o.W[c] * (x[c] - AT(P.yref, k * 9 + c));
 #pragma unroll
-    for (int c = 0; c < 2; c++) AT(lin, DL_r + c) = Ts * o.W[7 + c] * (u[c] - AT(P.yref, k * 9 + 7 + c));
+    for (int c = 0; c < 2; c++) if (soa) AT(lin, DL_r + c) = Ts * o.W[7 + c] * (u[c] - AT(P.yref, k * 9 + 7 + c));
     if (P.lin_im) {
         // instance-major record of the tensor-core QP kernel (qp_mma_g.cu): M = [B | A] rows 0..5 column-major (6 x 9, the column of s included: a
         // spline curvature makes it dense), b, q, r, the linearisation point and one pad; 640 bytes per (stage, instance)

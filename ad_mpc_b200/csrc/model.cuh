@@ -369,12 +369,23 @@ __device__ __forceinline__ void gpr_load(const Params &P, const admpc_opts &o, i
 // ---- Frenet variant (frenet.cu; shared with the GP sweep kernel of prepare.cu) --------------------------------------------------
 // kappa(s) of instance i: piecewise cubic, SoA rows [breaks (K+1) | coef (K x 4, lowest power first)][Bp]; the end pieces
 // extrapolate.  The reference evaluates CasADi's interpolant('kapparef_s', 'bspline', ...) at this place.
-__device__ __forceinline__ void kappa_spline(const Params &P, int i, double s, double &kap, double &dkap)
+// j: piece of the previous evaluation of this thread (-1: none yet -> bisection) ; the arc length moves by less than one piece
+// between the sub-stages of one interval, so every later call costs one or two break-point loads.
+__device__ __forceinline__ void kappa_spline(const Params &P, int i, double s, double &kap, double &dkap, int &j)
 {
     const int K = P.kap_K, Bp = P.Bp;
     const double *sp = P.kap_sp + i;
-    int j = 0;
-    while (j + 1 < K && s >= sp[(size_t)(j + 1) * Bp]) j++;
+    if (j < 0) {                                   // largest j with breaks[j] <= s, clamped to [0, K-1]
+        int lo = 0, hi = K - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s >= sp[(size_t)mid * Bp]) lo = mid; else hi = mid - 1;
+        }
+        j = lo;
+    } else {
+        while (j + 1 < K && s >= sp[(size_t)(j + 1) * Bp]) j++;
+        while (j > 0 && s < sp[(size_t)j * Bp]) j--;
+    }
     const double t = s - sp[(size_t)j * Bp];
     const double *c = sp + (size_t)(K + 1 + 4 * j) * Bp;
     const double c0 = c[0], c1 = c[(size_t)Bp], c2 = c[(size_t)2 * Bp], c3 = c[(size_t)3 * Bp];

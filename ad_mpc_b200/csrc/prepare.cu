@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gp_sweep_kernel(const Params P)
     double kx[7];
 #pragma unroll
     for (int c = 0; c < 7; c++) kx[c] = 0.0;
+    int kap_j = -1;                                             // FR: spline piece of the previous sub-stage
 #pragma unroll 1
     for (int s = 0; s < 4; s++) {
         const double as = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gp_sweep_kernel(const Params P)
         gp_apply(o, trig, G, f, J);
         if (FR) {
             double kap = P.kappa[(size_t)k * Bp + i], dkap;
-            if (P.kap_K > 0) kappa_spline(P, i, xs[0], kap, dkap);
+            if (P.kap_K > 0) kappa_spline(P, i, xs[0], kap, dkap, kap_j);
             frenet_pose_rows(xs, kap, f);
         }
 #pragma unroll
