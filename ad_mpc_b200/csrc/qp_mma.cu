@@ -822,7 +822,10 @@ bool launch_qp_mma(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
     if (N > 63 || !P.lin_im) return false;
-    const size_t sm = ((size_t)N * W_RS + T_SIZE) * sizeof(double);
+    size_t sm = ((size_t)N * W_RS + T_SIZE) * sizeof(double);
+#ifdef QPM_SMEM_PAD_ENV      // occupancy probe: ADMPC_SMEM_PAD = extra bytes of (unused) dynamic shared memory per CTA
+    if (const char *e = getenv("ADMPC_SMEM_PAD")) sm += (size_t)atoi(e);
+#endif
     if (N <= 31) {
         static SmemGuard configured;
         if (configured.need(sm)) cudaFuncSetAttribute(qp_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

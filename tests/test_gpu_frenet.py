@@ -361,6 +361,54 @@ def test_frenet_generic_tensor_core_kernel_agrees_with_the_dense_kernel(monkeypa
         assert mixed_err(a[f][good], b[f][good]) <= 1e-6, f
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_frenet_reference_defined_variant_random_settings(seed):
+    """Randomised weights / bounds / horizon / GP on the variant as the reference defines it -- kappa(s) spline inside the model,
+    own constraint set (con_set = 1) -- through the default kernels (gp_sweep_kernel<FR>, prepare_dense_kernel, qp_mma_g_kernel)
+    against the oracle: statuses, QP statuses, iteration counts of the solved instances, 1e-8 on the trajectories."""
+    rng = np.random.default_rng(9700 + seed)
+    N = int(rng.choice([5, 20, 31, 32, 48, 63]))
+    B = 24
+    q = [0.0] + list(rng.choice([0.1, 1.0, 10.0, 100.0], size=6))
+    opts = _frenet_own_opts(N, dt=float(rng.choice([0.02, 0.05, 0.1])), iter_max=int(rng.choice([4, 50])))
+    for i, v in enumerate(q + list(rng.choice([0.1, 10.0], size=2))):
+        opts.W[i] = v
+    for i, v in enumerate(q):
+        opts.We[i] = 0.01 * v
+    opts.lbu[0], opts.ubu[0] = -float(rng.uniform(0.5, 10)), float(rng.uniform(0.5, 5))
+    opts.lbu[1], opts.ubu[1] = -float(rng.uniform(0.3, 3)), float(rng.uniform(0.3, 3))
+    opts.lbx, opts.ubx = -float(rng.uniform(0.05, 0.6)), float(rng.uniform(0.05, 0.6))
+    opts.lbx2, opts.ubx2 = -float(rng.uniform(0.6, 3)), float(rng.uniform(0.6, 3))
+    for j in range(2):
+        opts.zl[j] = opts.zu[j] = float(rng.choice([10.0, 100.0, 1000.0]))
+    batch, breaks, coef = _spline_batch(B, N, 600 + seed)
+    batch["x_init"][:, :, 1] = np.clip(batch["x_init"][:, :, 1], -0.5, 0.5)      # inside the hard e_y box
+    batch["x0"][:, 1] = np.clip(batch["x0"][:, 1], -0.5, 0.5)
+    batch["u_init"] = rng.normal(size=(B, N, 2)) * np.array([0.5, 0.1])
+    s = BatchSolver(B, opts)
+    o = mirror_opts(opts)
+    gp = None
+    if seed % 2:
+        model = wl.make_gp(M=int(rng.choice([16, 100])), seed=30 + seed)
+        s.set_gp(model)
+        gp = orc.Gp(model)
+        gp.apply(o, feat=model["feat"], rows=model["rows"])
+    s.set_kappa_spline(breaks, coef)
+    g = _step(s, batch)
+    orc.set_batch_kappa_spline(breaks, coef)
+    try:
+        r = orc.rti_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=np.zeros((B, N)), gp=gp)
+    finally:
+        orc.set_batch_kappa_spline(None)
+    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_status"], r["qp_status"])
+    ok = r["status"] == 0
+    assert ok.any()
+    conv = ok & (r["qp_status"] == 0)
+    assert np.array_equal(g["qp_iter"][conv], r["qp_iter"][conv])
+    assert mixed_err(g["u"][ok], r["u"][ok]) <= TOL and mixed_err(g["x"][ok], r["x"][ok]) <= TOL
+    s.close()
+
+
 def test_con_set_1_needs_the_frenet_model():
     from ad_mpc_b200 import _lib
     with pytest.raises(_lib.AdmpcError):
