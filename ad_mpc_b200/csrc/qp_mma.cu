@@ -501,8 +501,6 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
                 for (int a = 0; a < 7; a++) { lb[a] = v[a]; lq[a] = v[7 + a]; }
                 lr[0] = v[14]; lr[1] = v[15];
             }
-            NCon C;
-            load_ncon(o, st, C);
             double pi[7], dx[7];
             {
                 double xp[14];
@@ -511,17 +509,14 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
 #pragma unroll
                 for (int a = 0; a < 7; a++) { dx[a] = xp[a]; pi[a] = xp[7 + a]; }
             }
-            NRes R;
-            node_res_w(o, k >= 1, C, R);
-            NScal S;
-            node_scal_w(o, C, S);
+            const double2 duv = ldv(st + W_DU);
             // stationarity w.r.t. u, dynamics residual, stationarity w.r.t. x: one pass over the columns of M
             double rgu[2], rgx[7], rbv[6];
             {
                 const double *dxn = (k + 1 < N) ? st + W_RS + W_DX : term + T_DX;
 #pragma unroll
                 for (int r = 0; r < 6; r++) rbv[r] = lb[r] - dxn[r] + ((r < 2) ? dx[r] : 0.0);
-                const double rb6 = lb[6] - dxn[6] + dx[6] + hdt * C.du[1];
+                const double rb6 = lb[6] - dxn[6] + dx[6] + hdt * duv.y;
                 st[W_RB + 6] = rb6;
                 nb = nmx(nb, fabs(rb6));
             }
@@ -529,7 +524,7 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
             for (int cc = 0; cc < 7; cc++) {
                 const double2 m01 = ldv(st + W_M + cc * 6), m23 = ldv(st + W_M + cc * 6 + 2), m45 = ldv(st + W_M + cc * 6 + 4);
                 const double mm[6] = {m01.x, m01.y, m23.x, m23.y, m45.x, m45.y};
-                const double xv = (cc < 2) ? C.du[cc] : dx[cc];
+                const double xv = (cc == 0) ? duv.x : (cc == 1) ? duv.y : dx[cc];
                 double gq = 0.0;
 #pragma unroll
                 for (int r = 0; r < 6; r++) { rbv[r] = fma(mm[r], xv, rbv[r]); gq = fma(mm[r], pi[r], gq); }
@@ -538,6 +533,13 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
             stv(st + W_RB, rbv[0], rbv[1]); stv(st + W_RB + 2, rbv[2], rbv[3]); stv(st + W_RB + 4, rbv[4], rbv[5]);
 #pragma unroll
             for (int r = 0; r < 6; r++) nb = nmx(nb, fabs(rbv[r]));
+            // constraint data only now: nothing of it is live across the pass over M
+            NCon C;
+            load_ncon(o, st, C);
+            NRes R;
+            node_res_w(o, k >= 1, C, R);
+            NScal S;
+            node_scal_w(o, C, S);
 #pragma unroll
             for (int jj = 0; jj < 2; jj++) {
                 double gq = Ts * o.W[7 + jj] * C.du[jj] + lr[jj] - C.lam[jj] + C.lam[3 + jj] + rgu[jj];

@@ -644,17 +644,14 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             }
         } else if (k < N) {
             double *st = rec + (size_t)k * W_RS;
-            double lq[7], lb[7], lr[2];
+            double lb[7];
             {
-                double v[16];                       // b (7) q (7) r (2): 16 contiguous doubles from an even offset
+                double v[8];                        // b (7) from an even offset (the eighth double is q[0])
 #pragma unroll
-                for (int a = 0; a < 16; a += 2) { const double2 t2 = ldv(st + W_LB + a); v[a] = t2.x; v[a + 1] = t2.y; }
+                for (int a = 0; a < 8; a += 2) { const double2 t2 = ldv(st + W_LB + a); v[a] = t2.x; v[a + 1] = t2.y; }
 #pragma unroll
-                for (int a = 0; a < 7; a++) { lb[a] = v[a]; lq[a] = v[7 + a]; }
-                lr[0] = v[14]; lr[1] = v[15];
+                for (int a = 0; a < 7; a++) lb[a] = v[a];
             }
-            GCon<CS> C;
-            load_gcon<CS>(o, st, C);
             double pi[7], dx[7];
             {
                 double xp[14];
@@ -665,10 +662,6 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             }
             const double2 duv = ldv(st + W_DU);
             const double du[2] = {duv.x, duv.y};
-            GRes<CS> R;
-            node_res_g<CS>(o, kge1, C, R);
-            GScal<CS> S;
-            node_scal_g<CS>(o, kge1, C, S);
             // stationarity w.r.t. u, dynamics residual, stationarity w.r.t. x: one pass over the columns of M
             double rgu[2], rgx[7], rbv[6], rb6s;
             {
@@ -694,6 +687,22 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             for (int r = 0; r < 6; r++) nb = nmx(nb, fabs(rbv[r]));
             rgx[6] += pi[6];
             rgu[1] = fma(hdt, pi[6], rgu[1]);
+            // cost gradients and constraint data only now: nothing of them is live across the pass over M
+            double lq[7], lr[2];
+            {
+                double v[10];                       // q (7) r (2) from the even offset before q
+#pragma unroll
+                for (int a = 0; a < 10; a += 2) { const double2 t2 = ldv(st + W_LQ - 1 + a); v[a] = t2.x; v[a + 1] = t2.y; }
+#pragma unroll
+                for (int a = 0; a < 7; a++) lq[a] = v[1 + a];
+                lr[0] = v[8]; lr[1] = v[9];
+            }
+            GCon<CS> C;
+            load_gcon<CS>(o, st, C);
+            GRes<CS> R;
+            node_res_g<CS>(o, kge1, C, R);
+            GScal<CS> S;
+            node_scal_g<CS>(o, kge1, C, S);
             // multipliers of the bounded quantities, complementarity, norms
             double rm[NR];
 #pragma unroll
