@@ -628,7 +628,8 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
 
     const double inv_nc = 1.0 / (double)((CS == 0) ? 10 * N - 2 : 12 * N - 6);
     const int k = tid;                               // node of this thread
-    const bool kge1 = (k >= 1);
+    const bool kge1 = (k >= 1), act = (k < N);
+    const int kc = act ? k : N - 1;                  // record the lanes without a node compute on (results masked)
     int status = 1, iter = 0;
     double res0 = 0, res1 = 0, res2 = 0, res3 = 0;
     for (iter = 0;; iter++) {
@@ -765,109 +766,113 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
         const double mu = summ * inv_nc;
         bsync<NW>();
 
-        // ================= predictor ========================================================================================
-        if (sweeper) mmag_factor(o, rec, term, N, l);
-        bsync<NW>();
-        if (sweeper) mmag_forward(o, rec, N, l);
-        bsync<NW>();
-        // affine step: step length, mu_aff ; the complementarity products and the two linear functionals the corrected
-        // barrier gradient needs stay in registers of the node's lane
-        double an = 1.0, ad = 1.0, s1 = 0.0, s2 = 0.0, m_aff = 1.0;
-        double pr[NR], fa[NQ], fb[NQ];
+        // ================= predictor (pass 0) and corrector (pass 1) ==========================================================
+        // One rolled loop: the node-role arithmetic both passes share (constraint data, residuals, scalings, step of the node for
+        // the direction the roll-out left) exists once in the instruction stream -- the iteration body is streamed from the
+        // instruction cache by every warp, its size is time.  pass 0 runs with pr = 0, sigma mu = 0: rm = lam t.
+        double an = 1.0, ad = 1.0, sigmu = 0.0;
+        double pr[NR];
 #pragma unroll
         for (int c = 0; c < NR; c++) pr[c] = 0.0;
-#pragma unroll
-        for (int q = 0; q < NQ; q++) { fa[q] = 0.0; fb[q] = 0.0; }
-        if (k < N) {
-            const double *st = rec + (size_t)k * W_RS;
-            GCon<CS> C; load_gcon<CS>(o, st, C);
-            GRes<CS> R; node_res_g<CS>(o, kge1, C, R);
-            GScal<CS> S; node_scal_g<CS>(o, kge1, C, S);
-            double rm[NR];
-#pragma unroll
-            for (int c = 0; c < NR; c++) rm[c] = row_on<CS>(c, kge1) ? C.lam[c] * C.t[c] : 0.0;
-            double ddx[7], ddu[2], dv[NQ];
-            node_dir_g(st, k, ddx, ddu);
-#pragma unroll
-            for (int q = 0; q < NQ; q++) { const int z = q_idx<CS>(q); dv[q] = (z < 2) ? ddu[z] : ddx[z - 2]; }
-            GStep<CS> D;
-            node_step_g<CS>(kge1, C, R, S, rm, dv, D);
-            m_aff = node_ratio_aff_g<CS>(kge1, S, D, m_aff);
-            double ea[NR], eb[NR];       // change of g = (rm - lam rd)/t caused by rm -> rm + dlam dt - sigma mu: ea - sigma mu eb
-#pragma unroll
-            for (int c = 0; c < NR; c++) {
-                const bool on = row_on<CS>(c, kge1);
-                pr[c] = on ? D.dlv[c] * D.dtv[c] : 0.0;
-                ea[c] = pr[c] * S.it[c];
-                eb[c] = on ? S.it[c] : 0.0;
-                if (on) {
-                    s1 += C.lam[c] * D.dtv[c] + C.t[c] * D.dlv[c];
-                    s2 += pr[c];
+        GCon<CS> Cs;
+        GScal<CS> Ss;
+        GStep<CS> Ds;
+        double duc[2] = {0.0, 0.0}, ddx[7];
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 0) {
+                if (sweeper) mmag_factor(o, rec, term, N, l);
+            } else {
+                if (sweeper) mmag_backward(o, rec, term, N, l);
+                bsync<NW>();
+                // k_ff of the corrector: -Guu^-1 (rt + B^T h_k), node-parallel
+                if (k < N) {
+                    double *st = rec + (size_t)k * W_RS;
+                    const double2 rt = ldv(st + W_BAR + 2);
+                    const double2 h01 = ldv(st + W_PB), h23 = ldv(st + W_PB + 2), h45 = ldv(st + W_PB + 4);
+                    const double h6 = st[W_PB + 6];
+                    const double gu0 = rt.x + dot6v(ldv(st + W_M), ldv(st + W_M + 2), ldv(st + W_M + 4), h01, h23, h45);
+                    const double gu1 = fma(hdt, h6, rt.y) + dot6v(ldv(st + W_M + 6), ldv(st + W_M + 8), ldv(st + W_M + 10), h01, h23, h45);
+                    const double gi00 = st[W_GI0], gi01 = st[W_GI1], gi11 = st[W_GI2];
+                    st[W_KF0] = -(gi00 * gu0 + gi01 * gu1);
+                    st[W_KF1] = -(gi01 * gu0 + gi11 * gu1);
                 }
             }
+            bsync<NW>();
+            if (sweeper) mmag_forward(o, rec, N, l);
+            bsync<NW>();
+            // step of this node along the direction of the roll-out.  Unconditional: the lanes without a node work on the last
+            // record and are masked where it matters (a conditional assignment would keep the previous pass's values of every
+            // one of these registers alive through the sweeps)
+            GRes<CS> R;
+            {
+                const double *st = rec + (size_t)kc * W_RS;
+                load_gcon<CS>(o, st, Cs);
+                node_res_g<CS>(o, kge1, Cs, R);
+                node_scal_g<CS>(o, kge1, Cs, Ss);
+                double rm[NR];
 #pragma unroll
-            for (int q = 0; q < NQ; q++) { fa[q] = q_grad<CS>(R, S, ea, q, 0.0); fb[q] = q_grad<CS>(R, S, eb, q, 0.0); }
-        }
-        m_aff = wmaxf32(m_aff);
-        s1 = wsum32(s1); s2 = wsum32(s2);
-        if (NW == 2) {
-            if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
-            __syncthreads();
-            m_aff = fmax(red[0], red[8]); s1 = red[1] + red[9]; s2 = red[2] + red[10];
-            __syncthreads();
-        }
-        const double a_aff = rcp_w(m_aff);               // min(1, min ratio) = 1 / max(1, max of the inverse ratios)
-        const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
-        double sigma = mu_aff * rcp_w(mu);
-        sigma = sigma * sigma * sigma;
-        const double sigmu = sigma * mu;
-        if (k < N) {
-            double *st = rec + (size_t)k * W_RS;
-            const double2 rt = ldv(st + W_BAR + 2);
-            stv(st + W_BAR + 2, rt.x + fma(-sigmu, fb[0], fa[0]), rt.y + fma(-sigmu, fb[1], fa[1]));
-            if (kge1) {
+                for (int c = 0; c < NR; c++) rm[c] = row_on<CS>(c, kge1) ? Cs.lam[c] * Cs.t[c] + pr[c] - sigmu : 0.0;
+                double dv[NQ];
+                node_dir_g(st, kc, ddx, duc);
 #pragma unroll
-                for (int q = 2; q < NQ; q++) st[W_GX + q_idx<CS>(q) - 2] += fma(-sigmu, fb[q], fa[q]);
+                for (int q = 0; q < NQ; q++) { const int z = q_idx<CS>(q); dv[q] = (z < 2) ? duc[z] : ddx[z - 2]; }
+                node_step_g<CS>(kge1, Cs, R, Ss, rm, dv, Ds);
+            }
+            if (pass == 0) {
+                // affine step: step length, mu_aff ; the complementarity products stay in registers of the node's lane, the two
+                // linear functionals the corrected barrier gradient needs go into the record
+                double s1 = 0.0, s2 = 0.0, m_aff = 1.0;
+                double fa[NQ], fb[NQ];
+                {
+                    m_aff = node_ratio_aff_g<CS>(kge1, Ss, Ds, m_aff);
+                    double ea[NR], eb[NR];   // change of g = (rm - lam rd)/t caused by rm -> rm + dlam dt - sigma mu: ea - sigma mu eb
+#pragma unroll
+                    for (int c = 0; c < NR; c++) {
+                        const bool on = row_on<CS>(c, kge1);
+                        pr[c] = on ? Ds.dlv[c] * Ds.dtv[c] : 0.0;
+                        ea[c] = pr[c] * Ss.it[c];
+                        eb[c] = on ? Ss.it[c] : 0.0;
+                        if (on) {
+                            s1 += Cs.lam[c] * Ds.dtv[c] + Cs.t[c] * Ds.dlv[c];
+                            s2 += pr[c];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) { fa[q] = q_grad<CS>(R, Ss, ea, q, 0.0); fb[q] = q_grad<CS>(R, Ss, eb, q, 0.0); }
+                }
+                m_aff = wmaxf32(act ? m_aff : 1.0);
+                s1 = wsum32(act ? s1 : 0.0); s2 = wsum32(act ? s2 : 0.0);
+                if (NW == 2) {
+                    if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
+                    __syncthreads();
+                    m_aff = fmax(red[0], red[8]); s1 = red[1] + red[9]; s2 = red[2] + red[10];
+                    __syncthreads();
+                }
+                const double a_aff = rcp_w(m_aff);           // min(1, min ratio) = 1 / max(1, max of the inverse ratios)
+                const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
+                double sigma = mu_aff * rcp_w(mu);
+                sigma = sigma * sigma * sigma;
+                sigmu = sigma * mu;
+                if (k < N) {
+                    double *st = rec + (size_t)k * W_RS;
+                    const double2 rt = ldv(st + W_BAR + 2);
+                    stv(st + W_BAR + 2, rt.x + fma(-sigmu, fb[0], fa[0]), rt.y + fma(-sigmu, fb[1], fa[1]));
+                    if (kge1) {
+#pragma unroll
+                        for (int q = 2; q < NQ; q++) st[W_GX + q_idx<CS>(q) - 2] += fma(-sigmu, fb[q], fa[q]);
+                    }
+                }
+                bsync<NW>();
             }
         }
-        bsync<NW>();
-        // ================= corrector ========================================================================================
-        if (sweeper) mmag_backward(o, rec, term, N, l);
-        bsync<NW>();
-        // k_ff of the corrector: -Guu^-1 (rt + B^T h_k), node-parallel
-        if (k < N) {
-            double *st = rec + (size_t)k * W_RS;
-            const double2 rt = ldv(st + W_BAR + 2);
-            const double2 h01 = ldv(st + W_PB), h23 = ldv(st + W_PB + 2), h45 = ldv(st + W_PB + 4);
-            const double h6 = st[W_PB + 6];
-            const double gu0 = rt.x + dot6v(ldv(st + W_M), ldv(st + W_M + 2), ldv(st + W_M + 4), h01, h23, h45);
-            const double gu1 = fma(hdt, h6, rt.y) + dot6v(ldv(st + W_M + 6), ldv(st + W_M + 8), ldv(st + W_M + 10), h01, h23, h45);
-            const double gi00 = st[W_GI0], gi01 = st[W_GI1], gi11 = st[W_GI2];
-            st[W_KF0] = -(gi00 * gu0 + gi01 * gu1);
-            st[W_KF1] = -(gi01 * gu0 + gi11 * gu1);
-        }
-        bsync<NW>();
-        if (sweeper) mmag_forward(o, rec, N, l);
-        bsync<NW>();
         // final step: step length, then the update of the constraint part of the iterate from the same registers
-        an = 1.0; ad = 1.0;
-        GCon<CS> Cs;
-        GStep<CS> Ds;
-        double duc[2] = {0.0, 0.0};
         if (k == N) {                                 // adjoint start: We ddx_N + r_x,N
             const double *pv = rec + (size_t)(N - 1) * W_RS + W_XA;
 #pragma unroll
             for (int a = 0; a < 7; a++) term[T_GX + a] = fma(o.We[a], pv[a], term[T_GX + a]);
         } else if (k < N) {
             double *st = rec + (size_t)k * W_RS;
-            load_gcon<CS>(o, st, Cs);
-            GRes<CS> R; node_res_g<CS>(o, kge1, Cs, R);
-            GScal<CS> S; node_scal_g<CS>(o, kge1, Cs, S);
-            double rm[NR];
-#pragma unroll
-            for (int c = 0; c < NR; c++) rm[c] = row_on<CS>(c, kge1) ? Cs.lam[c] * Cs.t[c] + pr[c] - sigmu : 0.0;
-            double ddx[7], dv[NQ];
-            node_dir_g(st, k, ddx, duc);
             if (kge1) {                               // adjoint base vector Qt_k ddx_k + gt_k
                 const double2 qt = ldv(st + W_BAR + 4);
                 double nbv[7];
@@ -875,11 +880,8 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
                 for (int a = 0; a < 7; a++) nbv[a] = fma((a == 1) ? qt.x : ((a == 6) ? qt.y : Ts * o.W[a]), ddx[a], st[W_GX + a]);
                 stv(st + W_GX, nbv[0], nbv[1]); stv(st + W_GX + 2, nbv[2], nbv[3]); stv(st + W_GX + 4, nbv[4], nbv[5]); st[W_GX + 6] = nbv[6];
             }
-#pragma unroll
-            for (int q = 0; q < NQ; q++) { const int z = q_idx<CS>(q); dv[q] = (z < 2) ? duc[z] : ddx[z - 2]; }
-            node_step_g<CS>(kge1, Cs, R, S, rm, dv, Ds);
             node_ratio_lam_g<CS>(kge1, Cs, Ds, an, ad);
-            const double mt = node_ratio_t_g<CS>(kge1, S, Ds, 1.0);
+            const double mt = node_ratio_t_g<CS>(kge1, Ss, Ds, 1.0);
             if (ad < an * mt) { an = 1.0; ad = mt; }
         }
         warp_ratio(an, ad);

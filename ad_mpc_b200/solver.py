@@ -407,6 +407,16 @@ class PipelinedSolver:
         for s, (lo, hi) in zip(self.parts, self.ranges):
             s.set_kappa(k[lo:hi])
 
+    def set_kappa_spline(self, breaks=None, coef=None):
+        """Frenet variant: kappa(s) spline inside the model (BatchSolver.set_kappa_spline), per instance or shared."""
+        b = None if breaks is None else np.asarray(breaks, dtype=np.float64)
+        c = None if coef is None else np.asarray(coef, dtype=np.float64)
+        for s, (lo, hi) in zip(self.parts, self.ranges):
+            if b is None:
+                s.set_kappa_spline(None)
+            else:
+                s.set_kappa_spline(b if b.ndim == 1 else b[lo:hi], c if c.ndim == 2 else c[lo:hi])
+
     def wait(self):
         check(self.L.admpc_pipe_wait(self.p), "pipe_wait")
 

@@ -190,6 +190,24 @@ def test_frenet_through_the_pipelined_host_call():
     ps.close(); s.close()
 
 
+def test_reference_defined_frenet_through_the_pipelined_host_call():
+    """The public batched call with host buffers on the variant as the reference defines it (spline + con_set = 1)."""
+    from ad_mpc_b200 import PipelinedSolver
+    B, N = 200, 20
+    batch, breaks, coef = _spline_batch(B, N, 377)
+    opts = _frenet_own_opts(N)
+    ps = PipelinedSolver(B, opts, chunks=3)
+    ps.set_iterate(batch["x_init"], batch["u_init"]); ps.set_kappa_spline(breaks, coef)
+    u, x, st = np.empty((B, N, 2)), np.empty((B, N + 1, 7)), np.empty(B, dtype=np.int32)
+    ps.solve_batch(np.ascontiguousarray(batch["x0"]), np.ascontiguousarray(batch["yref"]), np.ascontiguousarray(batch["p"][:, 0]), u, x, st)
+    s = BatchSolver(B, opts)
+    s.set_kappa_spline(breaks, coef)
+    g = _step(s, batch)
+    assert (g["status"] == 0).any()
+    assert np.array_equal(st, g["status"]) and np.array_equal(u, g["u"]) and np.array_equal(x, g["x"])
+    ps.close(); s.close()
+
+
 def _spline_batch(B, N, seed):
     """Curvature that really varies along the horizon: kappa(s) = 0.02 + 0.012 sin(s / 9 + phase_i), sampled at knots
     every 4 m around each vehicle and turned into the not-a-knot cubic the reference's bspline interpolant builds."""
