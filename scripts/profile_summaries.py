@@ -44,7 +44,7 @@ def launches(src, dst, cmd):
         a[0] += 1; a[1] += ms; n += 1
     tot = sum(v[1] for v in agg.values())
     with open(dst, "w") as f:
-        f.write("# r01 ncu launch list of `%s` (%d launches; --metrics gpu__time_duration.sum, --clock-control none)\n\n" % (cmd, n))
+        f.write("# r02 ncu launch list of `%s` (%d launches; --metrics gpu__time_duration.sum, --clock-control none)\n\n" % (cmd, n))
         f.write("Per-launch times are cold-cache and serialised by the profiler: compare SHARES, not absolutes.\n\n")
         f.write("| kernel | launches | total ms | mean ms | share |\n|---|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -60,7 +60,7 @@ def kernels(src, dst, cmd):
     for r in rows[2:]:
         cols.append((short(r[iK]), {h: (r[j], units[j]) for j, h in enumerate(hdr)}))
     with open(dst, "w") as f:
-        f.write("# r01 `ncu --set full --clock-control none` capture, %s\n\n" % cmd)
+        f.write("# r02 `ncu --set full --clock-control none` capture, %s\n\n" % cmd)
         f.write("| metric | " + " | ".join(c[0] for c in cols) + " |\n|---|" + "---|" * len(cols) + "\n")
         for k in KEYS:
             if k not in hdr:
