@@ -1,5 +1,5 @@
-// frenet.cu -- Frenet-frame model variant (SURVEY.md 8a row A2'): preparation and feedback kernels for a model whose
-// linearisation has no exploitable structure beyond "dense 7x7 / 7x2".
+// frenet.cu -- Frenet-frame model variant (SURVEY.md 8a row A2'): the model, pass 2 of its preparation, and the dense
+// thread-per-instance IPM that serves as cross-check and long-horizon fallback.
 //
 // Reference: ad_mpc/__pycache__/fren_ad_3d_optimizer.cpython-36.pyc (bytecode only; equations recovered in SURVEY 8a):
 // state x = [s, e_y, e_psi, v_x, v_y, r, delta];  rows 3..6 are the Cartesian model's (ad_3d_optimizer.py:286-310),
@@ -8,18 +8,21 @@
 //     e_psi' =  r - e_y kappa s'                         (literal bytecode form, including the e_y*kappa factor)
 // The reference evaluates a B-spline kappa(s) inside the model (compiled with placeholder knots).  Two forms here:
 //   * admpc_batch_set_kappa_spline: kappa(s) as a per-instance piecewise cubic evaluated at every RK4 sub-stage, with the
-//     d kappa / d s column in the Jacobian (the reference's semantics; A(:,0) is then dense, so the feedback phase runs the
-//     dense kernel below);
-//   * admpc_batch_set_kappa: a per-instance, per-shooting-node constant (d/ds = 0 inside one linearisation), which keeps
-//     the column of s trivial and lets the structured warp kernel qp_warp_f run.
-// With kappa = 0 the model IS the Cartesian one; tests pin this variant to the (reference-pinned) Cartesian path that
-// way.  The variant's own OCP (soft e_y bound, hard steering-rate bound) is not restated: the constraint set stays
-// the shipped one (both inputs soft, delta hard); weights / bounds / tyre factors are options.
+//     d kappa / d s column in the Jacobian (the reference's semantics; A(:,0) is then dense);
+//   * admpc_batch_set_kappa: a per-instance, per-shooting-node constant (d/ds = 0 inside one linearisation).
+// With kappa = 0 the model IS the Cartesian one; tests pin this variant to the (reference-pinned) Cartesian path that way.
+// Constraint sets: the shipped one (con_set = 0) and the variant's own (con_set = 1, structure pinned by ad_mpc/debug.json),
+// see the descriptor below.
 //
-// Kernels (first correct version, one thread per (instance, node) / per instance, no structure exploited):
-//   prepare_dense_kernel<GP>  RK4 + forward sensitivities with dense Jacobians, writes lin_d[k][79][Bp]
-//   qp_dense_kernel           the same Mehrotra / Riccati IPM as qp_ipm.cu on dense stage matrices
-// FP64-pipe bound like their structured twins; expect ~5-10x their run time.
+// Kernels:
+//   prepare_dense_kernel<GP>  RK4 + forward sensitivities on the structurally non-zero block of the Frenet Jacobian; GP terms
+//                             read back from gpr (pass 1 = gp_sweep_kernel<.., FR = true>, prepare.cu); writes the 80-double
+//                             instance-major records qp_mma_g.cu pulls by TMA and, when something reads them, the SoA rows
+//                             lin_d[k][79][Bp]
+//   qp_dense_kernel           the same Mehrotra / Riccati IPM on dense stage matrices, one thread per instance, workspace in HBM,
+//                             run-time constraint descriptor: independent cross-check (ADMPC_QP_VARIANT=1) and N > 63 fallback;
+//                             ~12x the run time of the default kernel (qp_mma_g.cu)
+//   nlp_res_dense_kernel      NLP KKT residuals of the full-SQP mode on the dense linearisation
 #include "common.cuh"
 
 #include "model.cuh"

@@ -6,6 +6,9 @@
 // matrix is M = [B | A(:,1:7)] (6 x 8) instead of [B | A(:,2:7)] (6 x 7): 63 entries of P [M | rb], a 36-entry Gram
 // block, and every index map between state indices and M-columns shifts by one.  Input: the dense linearisation of
 // prepare_dense_kernel (frenet.cu), of which column 0 of A is e0 and row 6 is [0..0 1 | 0 dt] exactly.
+// Round-1 design; the default for the variant is the tensor-core kernel qp_mma_g.cu (every curvature form, both constraint
+// sets).  Kept selectable (ADMPC_QP_VARIANT=4: per-node curvature, con_set = 0) as an independent implementation for
+// tests/test_gpu_frenet.py::test_frenet_kernel_variants_agree.
 #include "common.cuh"
 
 #define FULL 0xffffffffu
