@@ -9,7 +9,7 @@ pin = {k: PinnedArray(v.shape) for k, v in (("x0", batch["x0"]), ("yref", batch[
 pin["x0"].array[:] = batch["x0"]; pin["yref"].array[:] = batch["yref"]
 pp = PinnedArray((B,)); pp.array[:] = 1.0
 ou, ox, os_ = PinnedArray((B, N, 2)), PinnedArray((B, N + 1, 7)), PinnedArray((B,), dtype=np.int32)
-for chunks in (1, 2, 4, 6, 8, 10, 12, 16, 24):
+for chunks in [int(c) for c in os.environ.get("CHUNKS", "1,2,4,6,8,10,12,16,24").split(",")]:
     ps = PipelinedSolver(B, default_opts(N), chunks=chunks)
     ps.set_gp(model)
     ts = []
