@@ -26,37 +26,40 @@
 #include "common.cuh"
 #include "tma.cuh"
 
-// instance-major linearisation record of the Frenet preparation kernel (frenet.cu): M = [B | A] rows 0..5
-// column-major (6 x 9), b, q, r, x, u, one pad
+// instance-major linearisation record of the Frenet preparation kernel (frenet.cu): M = [B | A] rows 0..5 column-major (6 x 9),
+// b, q, r, x, u, one pad.  Only M is staged (one TMA bulk copy per stage); b, q, r are read once per IPM iteration and the
+// linearisation point twice per solve by the node lanes straight from this record (L2-resident: the CTA has just pulled it) --
+// 16 + 10 doubles less per stage in shared memory are the eighth resident instance per SM.
 #define LIMG_STRIDE 80
+#define G_LB 54     // 7   b_k
+#define G_LQ 61     // 7   q_k
+#define G_LR 68     // 2   r_k
+#define G_XB 70     // 7   linearisation point x_k
+#define G_UB 77     // 2   linearisation point u_k (+ 1 pad)
 
-// ---- node record (doubles); the first LIMG_STRIDE are pulled in by one TMA bulk copy per stage
-#define W_M 0       // 54  column c (0,1 = u0,u1 ; 2..8 = x0..x6) at c*6 + r, r < 6 (next states x0..x5)
-#define W_LB 54     // 7   b_k
-#define W_LQ 61     // 7   q_k
-#define W_LR 68     // 2   r_k
-#define W_XB 70     // 7   linearisation point x_k
-#define W_UB 77     // 2   linearisation point u_k (+ 1 pad)
-#define W_K0 80     // 8   first row of (K | k_ff)
-#define W_KF0 87
-#define W_K1 88     // 8   second row
-#define W_KF1 95
-#define W_RB 96     // 8   dynamics residual, slot 7 = 1.0 (homogeneous coordinate: never overwritten)
-#define W_PB 104    // 8   P_{k+1} rb_k ; corrector backward sweep: h_k ; adjoint sweep: dpi_k
-#define W_GX 112    // 8   gradient w.r.t. x (slot 7 = 0) ; after the corrector roll-out the adjoint base vector
-#define W_BAR 120   // 6   Rt0 Rt1 | rt0 rt1 | Qt1 Qt6
-#define W_GI0 126   // 3   Guu^-1 (0,0), (0,1), (1,1)
-#define W_GI1 127
-#define W_GI2 128
-#define W_DX 130    // 7   iterate: dx_k
-#define W_PI 137    // 7   iterate: pi_k
-#define W_LAM 144   // 12  iterate: lam (10 rows used by con_set 0)
-#define W_T 156     // 12  iterate: t
-#define W_DU 168    // 2
-#define W_SL 170    // 2
-#define W_SU 172    // 2
-#define W_XA 174    // 8   roll-out: [ddx_{k+1}, 1]
-#define W_RS 182    // record stride (W_RS / 2 odd: 16-byte node-parallel accesses are conflict-free)
+// ---- node record in shared memory (doubles)
+#define W_M 0       // 54  column c (0,1 = u0,u1 ; 2..8 = x0..x6) at c*6 + r, r < 6 (next states x0..x5) ; the TMA'd part
+#define W_BND 54    // 4   linearisation-point value of every bounded quantity (u0, u1, then the bounded states)
+#define W_K0 58     // 8   first row of (K | k_ff)
+#define W_KF0 65
+#define W_K1 66     // 8   second row
+#define W_KF1 73
+#define W_RB 74     // 8   dynamics residual, slot 7 = 1.0 (homogeneous coordinate: never overwritten)
+#define W_PB 82     // 8   P_{k+1} rb_k ; corrector backward sweep: h_k ; adjoint sweep: dpi_k
+#define W_GX 90     // 8   gradient w.r.t. x (slot 7 = 0) ; after the corrector roll-out the adjoint base vector
+#define W_BAR 98    // 6   Rt0 Rt1 | rt0 rt1 | Qt1 Qt6
+#define W_GI0 104   // 3   Guu^-1 (0,0), (0,1), (1,1)
+#define W_GI1 105
+#define W_GI2 106
+#define W_DX 108    // 7   iterate: dx_k
+#define W_PI 115    // 7   iterate: pi_k
+#define W_LAM 122   // 12  iterate: lam (10 rows used by con_set 0)
+#define W_T 134     // 12  iterate: t
+#define W_DU 146    // 2
+#define W_SL 148    // 2
+#define W_SU 150    // 2
+#define W_XA 152    // 8   roll-out: [ddx_{k+1}, 1]
+#define W_RS 162    // record stride (W_RS / 2 odd: 16-byte node-parallel accesses are conflict-free)
 // terminal record
 #define T_DX 0      // 7
 #define T_GX 8      // 8   r_x,N ; later We dx_N + r_x,N (adjoint start)
@@ -133,7 +136,7 @@ template <int CS> __device__ __forceinline__ void load_gcon(const admpc_opts &o,
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
         const int z = q_idx<CS>(q);
-        const double bar = (z < 2) ? st[W_UB + z] : st[W_XB + z - 2];
+        const double bar = st[W_BND + q];
         C.v[q] = (z == 0) ? du.x : (z == 1) ? du.y : st[W_DX + z - 2];
         C.lo[q] = q_lo<CS>(o, q) - bar; C.hi[q] = q_hi<CS>(o, q) - bar;
     }
@@ -524,13 +527,13 @@ __device__ __forceinline__ void node_dir_g(const double *st, int k, double ddx[7
 }
 
 #ifndef MMAG_MINB
-#define MMAG_MINB 7
+#define MMAG_MINB 8
 #endif
 // NW warps per instance: thread k owns node k in the node role (N <= 32 NW - 1); the sweeps run on warp 0 while the others wait
-// at the CTA barrier.  NW = 1: N <= 31, 7 instances per SM at N = 20 ; NW = 2: N <= 63.
+// at the CTA barrier.  NW = 1: N <= 31, 8 instances per SM at N = 20 ; NW = 2: N <= 63.
 template <int NW> __device__ __forceinline__ void bsync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
 template <int NW, int CS>
-__global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_kernel(const Params P)
+__global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 4) qp_mma_g_kernel(const Params P)
 {
     constexpr int NQ = CSet<CS>::NQ, NR = CSet<CS>::NR;
     extern __shared__ __align__(16) double smr[];
@@ -565,19 +568,19 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
         return;
     }
 
-    // ---- stage the linearisation: one TMA bulk copy per stage record (640 B), one mbarrier ---------------------------------
+    // ---- stage the stage matrices: one TMA bulk copy per stage (M, 432 B), one mbarrier ------------------------------------------
     __shared__ uint64_t bar;
     if (tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(&bar, (uint32_t)(N * LIMG_STRIDE * sizeof(double)));
+        mbar_expect_tx(&bar, (uint32_t)(N * G_LB * sizeof(double)));
     }
     bsync<NW>();
     for (int k = tid; k < N; k += 32 * NW)
-        tma_bulk_g2s(rec + (size_t)k * W_RS, P.lin_im + ((size_t)k * Bp + i) * LIMG_STRIDE, LIMG_STRIDE * sizeof(double), &bar);
+        tma_bulk_g2s(rec + (size_t)k * W_RS, P.lin_im + ((size_t)k * Bp + i) * LIMG_STRIDE, G_LB * sizeof(double), &bar);
     if (tid < 7) {                                   // terminal node: q_N and x_N only
         const double *rn = P.lin_im + ((size_t)N * Bp + i) * LIMG_STRIDE;
-        term[T_LQ + tid] = rn[W_LQ + tid]; term[T_XB + tid] = rn[W_XB + tid]; term[T_DX + tid] = 0.0;
+        term[T_LQ + tid] = rn[G_LQ + tid]; term[T_XB + tid] = rn[G_XB + tid]; term[T_DX + tid] = 0.0;
         if (tid == 0) term[T_GX + 7] = 0.0;
     }
     double x0v[7];
@@ -589,9 +592,19 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
         const int k = tid;
         if (k < N) {
             double *st = rec + (size_t)k * W_RS;
+            const double *gr = P.lin_im + ((size_t)k * Bp + i) * LIMG_STRIDE;               // this node's record in HBM / L2
+            double xbv[7], ubv[2];
+            {
+                double v[10];                       // x (7) u (2) pad from an even offset
+#pragma unroll
+                for (int a = 0; a < 10; a += 2) { const double2 t2 = ldv(gr + G_XB + a); v[a] = t2.x; v[a + 1] = t2.y; }
+#pragma unroll
+                for (int a = 0; a < 7; a++) xbv[a] = v[a];
+                ubv[0] = v[7]; ubv[1] = v[8];
+            }
             double dx[7];
 #pragma unroll
-            for (int a = 0; a < 7; a++) dx[a] = (k == 0) ? x0v[a] - st[W_XB + a] : 0.0;     // x0 eliminated (nbxe_0 = 7)
+            for (int a = 0; a < 7; a++) dx[a] = (k == 0) ? x0v[a] - xbv[a] : 0.0;           // x0 eliminated (nbxe_0 = 7)
             double du[2] = {0.0, 0.0}, lam[NR], t[NR];
 #pragma unroll
             for (int c = 0; c < NR; c++) { lam[c] = 0.0; t[c] = 1.0; }
@@ -599,7 +612,7 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             for (int q = 0; q < NQ; q++) {
                 const int z = q_idx<CS>(q), s = q_soft<CS>(q);
                 if (z >= 2 && k == 0) continue;
-                const double bar_ = (z < 2) ? st[W_UB + z] : st[W_XB + z - 2];
+                const double bar_ = (z < 2) ? ubv[z] : xbv[z - 2];
                 const double lo = q_lo<CS>(o, q) - bar_, hi = q_hi<CS>(o, q) - bar_;
                 double v = 0.0;
                 if (v - lo < o.thr0) {
@@ -621,6 +634,12 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             for (int c = 0; c < NR; c += 2) { stv(st + W_LAM + c, lam[c], lam[c + 1]); stv(st + W_T + c, t[c], t[c + 1]); }
             stv(st + W_DU, du[0], du[1]);
             stv(st + W_SL, 0.0, 0.0); stv(st + W_SU, 0.0, 0.0);
+            {
+                double bnd[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int q = 0; q < NQ; q++) { const int z = q_idx<CS>(q); bnd[q] = (z < 2) ? ubv[z] : xbv[z - 2]; }
+                stv(st + W_BND, bnd[0], bnd[1]); stv(st + W_BND + 2, bnd[2], bnd[3]);
+            }
             st[W_RB + 7] = 1.0; st[W_GX + 7] = 0.0; st[W_PB + 7] = 0.0;     // homogeneous coordinate / unused slot of the fragment rows
         }
     }
@@ -645,13 +664,16 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             }
         } else if (k < N) {
             double *st = rec + (size_t)k * W_RS;
-            double lb[7];
+            // b, q, r of this node from its global record (issued first: an L2 round trip that the pass over M covers)
+            const double *gr = P.lin_im + ((size_t)k * Bp + i) * LIMG_STRIDE;
+            double lb[7], lq[7], lr[2];
             {
-                double v[8];                        // b (7) from an even offset (the eighth double is q[0])
+                double v[16];                       // b (7) q (7) r (2): 16 contiguous doubles from an even offset
 #pragma unroll
-                for (int a = 0; a < 8; a += 2) { const double2 t2 = ldv(st + W_LB + a); v[a] = t2.x; v[a + 1] = t2.y; }
+                for (int a = 0; a < 16; a += 2) { const double2 t2 = ldv(gr + G_LB + a); v[a] = t2.x; v[a + 1] = t2.y; }
 #pragma unroll
-                for (int a = 0; a < 7; a++) lb[a] = v[a];
+                for (int a = 0; a < 7; a++) { lb[a] = v[a]; lq[a] = v[7 + a]; }
+                lr[0] = v[14]; lr[1] = v[15];
             }
             double pi[7], dx[7];
             {
@@ -668,10 +690,8 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             {
                 const double *dxn = (k + 1 < N) ? st + W_RS + W_DX : term + T_DX;
 #pragma unroll
-                for (int r = 0; r < 6; r++) rbv[r] = lb[r] - dxn[r];
-                const double rb6 = lb[6] - dxn[6] + dx[6] + hdt * du[1];
-                rb6s = rb6;
-                nb = nmx(nb, fabs(rb6));
+                for (int r = 0; r < 6; r++) rbv[r] = -dxn[r];
+                rb6s = dx[6] - dxn[6] + hdt * du[1];
             }
 #pragma unroll
             for (int cc = 0; cc < 9; cc++) {                  // columns u0, u1, x0..x6
@@ -683,21 +703,16 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
                 for (int r = 0; r < 6; r++) { rbv[r] = fma(mm[r], xv, rbv[r]); gq = fma(mm[r], pi[r], gq); }
                 if (cc < 2) rgu[cc] = gq; else rgx[(cc >= 2) ? cc - 2 : 0] = gq;
             }
+#pragma unroll
+            for (int r = 0; r < 6; r++) rbv[r] += lb[r];          // (b last: its load is the one that comes from L2)
+            rb6s += lb[6];
             stv(st + W_RB, rbv[0], rbv[1]); stv(st + W_RB + 2, rbv[2], rbv[3]); stv(st + W_RB + 4, rbv[4], rbv[5]); st[W_RB + 6] = rb6s;
 #pragma unroll
             for (int r = 0; r < 6; r++) nb = nmx(nb, fabs(rbv[r]));
+            nb = nmx(nb, fabs(rb6s));
             rgx[6] += pi[6];
             rgu[1] = fma(hdt, pi[6], rgu[1]);
-            // cost gradients and constraint data only now: nothing of them is live across the pass over M
-            double lq[7], lr[2];
-            {
-                double v[10];                       // q (7) r (2) from the even offset before q
-#pragma unroll
-                for (int a = 0; a < 10; a += 2) { const double2 t2 = ldv(st + W_LQ - 1 + a); v[a] = t2.x; v[a + 1] = t2.y; }
-#pragma unroll
-                for (int a = 0; a < 7; a++) lq[a] = v[1 + a];
-                lr[0] = v[8]; lr[1] = v[9];
-            }
+            // constraint data only now: nothing of it is live across the pass over M
             GCon<CS> C;
             load_gcon<CS>(o, st, C);
             GRes<CS> R;
@@ -945,7 +960,8 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
         ADMPC_ASSERT(soa_at(k * 7 + 6, (N + 1) * 7, i, Bp) < (size_t)(N + 1) * 7 * Bp);
         const double *st = rec + (size_t)k * W_RS;
         const double *dxs = (k < N) ? st + W_DX : term + T_DX;
-        const double *xbs = (k < N) ? st + W_XB : term + T_XB;       // linearisation point: came in with the stage record
+        const double *gr = P.lin_im + ((size_t)k * Bp + i) * LIMG_STRIDE;
+        const double *xbs = (k < N) ? gr + G_XB : term + T_XB;       // linearisation point: from the global record again
         if (upd || P.gat_x) {
 #pragma unroll
             for (int a = 0; a < 7; a++) {
@@ -956,7 +972,7 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 3) qp_mma_g_k
             if (k < N) {
 #pragma unroll
                 for (int jj = 0; jj < 2; jj++) {
-                    double v = st[W_UB + jj];
+                    double v = gr[G_UB + jj];
                     if (upd) { v += st[W_DU + jj]; ATS(P.ub, k * 2 + jj) = v; }
                     if (P.gat_x) P.gat_u[((size_t)i * N + k) * 2 + jj] = v;
                 }

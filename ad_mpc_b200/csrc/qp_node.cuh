@@ -52,6 +52,7 @@ struct NCon {
     double lam[NC], t[NC], sl[2], su[2], du[2], dx6;
     double lo[2], hi[2], lox, hix;
 };
+#ifdef W_XB      // (kernels that keep the linearisation point in the record; qp_mma_g.cu has its own descriptor-based loader)
 __device__ __forceinline__ void load_ncon(const admpc_opts &o, const double *st, NCon &C)
 {
     const double ub0 = st[W_UB], ub1 = st[W_UB + 1], xb6 = st[W_XB + 6];
@@ -67,6 +68,7 @@ __device__ __forceinline__ void load_ncon(const admpc_opts &o, const double *st,
     C.lo[1] = o.lbu[1] - ub1; C.hi[1] = o.ubu[1] - ub1;
     C.lox = o.lbx - xb6; C.hix = o.ubx - xb6;
 }
+#endif
 struct NRes { double rd[NC], rgsl[2], rgsu[2]; };
 __device__ __forceinline__ void node_res_w(const admpc_opts &o, bool k_ge1, const NCon &C, NRes &R)
 {
