@@ -427,6 +427,48 @@ def test_frenet_reference_defined_variant_random_settings(seed):
     s.close()
 
 
+def test_reference_defined_frenet_full_size(monkeypatch):
+    """BASELINE cfg-3 size (B = 16384, N = 20, GP M = 200) on the variant as the reference defines it: size-independent properties
+    instead of a 16k-instance oracle run -- (i) duplicated instances give bit-identical results wherever they sit in the batch,
+    (ii) a 128-instance sample matches the oracle, (iii) the dense thread-per-instance kernel (independent implementation) agrees
+    on the whole batch, (iv) every status is 0."""
+    B, N, S = 16384, 20, 128
+    base, breaks, coef = _spline_batch(S, N, 731)
+    base["x_init"][:, :, 1] = np.clip(base["x_init"][:, :, 1], -0.5, 0.5)
+    base["x0"][:, 1] = np.clip(base["x0"][:, 1], -0.5, 0.5)
+    reps = B // S
+    batch = {k: np.concatenate([v] * reps, axis=0) for k, v in base.items()}
+    bk, cf = np.concatenate([breaks] * reps, axis=0), np.concatenate([coef] * reps, axis=0)
+    model = wl.make_gp(M=200, seed=20263)
+    opts = _frenet_own_opts(N)
+    out = {}
+    for v in (0, 1):
+        if v:
+            monkeypatch.setenv("ADMPC_QP_VARIANT", "1")
+        s = BatchSolver(B, opts)
+        s.set_gp(model)
+        s.set_kappa_spline(bk, cf)
+        out[v] = _step(s, batch)
+        s.close()
+    monkeypatch.delenv("ADMPC_QP_VARIANT")
+    g = out[0]
+    assert (g["status"] == 0).all() and (g["qp_status"] == 0).all()
+    u = g["u"].reshape(reps, S, N, 2)
+    assert np.array_equal(u[0], u[-1]) and np.array_equal(u[0], u[reps // 2])
+    assert np.array_equal(g["qp_iter"], out[1]["qp_iter"]) and np.array_equal(g["status"], out[1]["status"])
+    assert mixed_err(g["u"], out[1]["u"]) <= TOL and mixed_err(g["x"], out[1]["x"]) <= TOL
+    o = mirror_opts(opts)
+    gp = orc.Gp(model)
+    gp.apply(o, feat=model["feat"], rows=model["rows"])
+    orc.set_batch_kappa_spline(breaks, coef)
+    try:
+        r = orc.rti_batch(o, base["x0"], base["yref"], base["p"], base["x_init"], base["u_init"], kappa=np.zeros((S, N)), gp=gp)
+    finally:
+        orc.set_batch_kappa_spline(None)
+    assert np.array_equal(g["qp_iter"][:S], r["qp_iter"]) and np.array_equal(g["status"][:S], r["status"])
+    assert mixed_err(u[0], r["u"]) <= TOL and mixed_err(g["x"][:S], r["x"]) <= TOL
+
+
 def test_con_set_1_needs_the_frenet_model():
     from ad_mpc_b200 import _lib
     with pytest.raises(_lib.AdmpcError):
