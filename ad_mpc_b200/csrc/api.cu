@@ -1318,6 +1318,16 @@ struct sim_car_solver_capsule {
     std::vector<double> x0, yref, p, kappa, x, u, pi, lam, t, sl, su;
     bool iterate_dirty = false, duals_stale = false, duals_dirty = false;
     double *hio = nullptr, *dio = nullptr;      // pinned host / device staging blocks of the single-instance fast path
+    double *hio_dev = nullptr;                  // device-side address of the pinned block (zero-copy)
+    bool zero_copy = false;
+    // the fast path as a CUDA graph (one launch instead of ~12 stream calls): [0] without / [1] with a new initial guess; a graph
+    // is replayed only while the kernel parameters it captured are byte-identical to the handle's current ones
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    Params gparams[2];
+    bool gprof[2] = {false, false};
+    long long glaunches[2] = {0, 0};
+    int rti_solves = 0;
+    bool graph_ok = true;
     int status = 0, qp_status = 0, qp_iter = 0, sqp_iter = 1;
     bool nlp_sqp = false;            // nlp_solver_type: false "SQP_RTI" (shipped), true "SQP" (point-reference mode)
     int nlp_max_iter = 100;          // sim_car_acados_ocp.json:868
@@ -1413,6 +1423,7 @@ extern "C" int sim_car_acados_reset(sim_car_solver_capsule *c, int)
 extern "C" int sim_car_acados_free(sim_car_solver_capsule *c)
 {
     if (!c) return ADMPC_E_ARG;
+    for (int g = 0; g < 2; g++) if (c->gexec[g]) { cudaGraphExecDestroy(c->gexec[g]); c->gexec[g] = nullptr; }
     if (c->hio) { cudaFreeHost(c->hio); c->hio = nullptr; }
     if (c->dio) { cudaFree(c->dio); c->dio = nullptr; }
     int r = c->h ? admpc_batch_free(c->h) : 0;
@@ -1496,8 +1507,10 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
         const size_t nin = (size_t)7 + nyr + N + N + nx + nu, nout = (size_t)nx + nu + 7;
         if (!c->hio) {
             CUDA_CHECK_RET(cudaSetDevice(h->device));
-            CUDA_CHECK_RET(cudaHostAlloc((void **)&c->hio, (nin + nout) * sizeof(double), cudaHostAllocDefault));
+            CUDA_CHECK_RET(cudaHostAlloc((void **)&c->hio, (nin + nout) * sizeof(double), cudaHostAllocMapped));
             CUDA_CHECK_RET(cudaMalloc(&c->dio, (nin + nout) * sizeof(double)));
+            c->zero_copy = !getenv("ADMPC_NO_ZEROCOPY") && cudaHostGetDevicePointer((void **)&c->hio_dev, c->hio, 0) == cudaSuccess;
+            if (!c->zero_copy) cudaGetLastError();
         }
         double *hi = c->hio, *ho = c->hio + nin;
         memcpy(hi, c->x0.data(), 7 * sizeof(double));
@@ -1511,13 +1524,52 @@ extern "C" int sim_car_acados_solve(sim_car_solver_capsule *c)
         }
         CUDA_CHECK_RET(cudaSetDevice(h->device));
         if ((r = admpc_batch_timer_start(h))) return r;
-        CUDA_CHECK_RET(cudaMemcpyAsync(c->dio, hi, (wit ? nin : (size_t)7 + nyr + 2 * N) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        launch_capsule_scatter(h->P, c->dio, c->opts.model_variant == 1, wit, h->stream);
+        // zero-copy: the pinned block is mapped into the device's address space (unified addressing), so the scatter kernel reads
+        // its 2 KB straight from host memory and the gather kernel writes its 1.5 KB straight back -- two copy operations (and
+        // their ~6 us each of launch latency) less on a path whose whole budget is 0.1 ms
+        const bool zc = c->zero_copy;
+        auto enqueue = [&]() -> int {
+            if (!zc) CUDA_CHECK_RET(cudaMemcpyAsync(c->dio, hi, (wit ? nin : (size_t)7 + nyr + 2 * N) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            launch_capsule_scatter(h->P, zc ? c->hio_dev : c->dio, c->opts.model_variant == 1, wit, h->stream);
+            if (int rr = admpc_batch_solve(h)) return rr;
+            launch_capsule_gather(h->P, zc ? c->hio_dev + nin : c->dio + nin, h->stream);
+            h->launches += 2;
+            if (!zc) CUDA_CHECK_RET(cudaMemcpyAsync(ho, c->dio + nin, nout * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            return 0;
+        };
         c->iterate_dirty = false;
-        if ((r = admpc_batch_solve(h))) return r;
-        launch_capsule_gather(h->P, c->dio + nin, h->stream);
-        h->launches += 2;
-        CUDA_CHECK_RET(cudaMemcpyAsync(ho, c->dio + nin, nout * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        const int gi = wit ? 1 : 0;
+        if (c->rti_solves == 0 && getenv("ADMPC_NO_GRAPH")) c->graph_ok = false;
+        if (c->gexec[gi] && (memcmp(&c->gparams[gi], &h->P, sizeof(Params)) != 0 || c->gprof[gi] != h->profiling)) {
+            cudaGraphExecDestroy(c->gexec[gi]);                 // something the kernels see has changed since the capture
+            c->gexec[gi] = nullptr;
+        }
+        if (c->gexec[gi]) {
+            CUDA_CHECK_RET(cudaGraphLaunch(c->gexec[gi], h->stream));
+            h->launches += c->glaunches[gi];
+        } else if (c->graph_ok && c->rti_solves >= 2) {         // (the first solves run eagerly: one-time kernel attributes, warm-up)
+            const long long l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            bool captured = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (captured) {
+                r = enqueue();
+                captured = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && r == 0 && graph != nullptr;
+            }
+            if (captured && cudaGraphInstantiate(&c->gexec[gi], graph, 0) == cudaSuccess) {
+                c->gparams[gi] = h->P; c->gprof[gi] = h->profiling; c->glaunches[gi] = h->launches - l0;
+                cudaGraphDestroy(graph);
+                CUDA_CHECK_RET(cudaGraphLaunch(c->gexec[gi], h->stream));
+            } else {                                            // capture not possible here: stay on the eager path for good
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                c->gexec[gi] = nullptr; c->graph_ok = false;
+                h->launches = l0;
+                if ((r = enqueue())) return r;
+            }
+        } else {
+            if ((r = enqueue())) return r;
+        }
+        c->rti_solves++;
         float ms = 0;
         if ((r = admpc_batch_timer_stop(h, &ms))) return r;          // synchronises the stream
         c->time_tot = ms * 1e-3;
