@@ -549,7 +549,7 @@ def run_ours(args):
                             "single_instance_p50_ms": single_ms[len(single_ms) // 2] if single_ms else None,
                             "single_instance_p99_ms": single_ms[min(len(single_ms) - 1, int(0.99 * len(single_ms)))] if single_ms else None,
                             "single_instance_note": "cfg1: nominal N=20, B=1, 50 closed-loop RTI steps through "
-                                                    "sim_car_acados_solve (host clock, includes H2D/D2H of the one instance)"}}
+                                                    "sim_car_acados_solve (host clock around the call: zero-copy pinned I/O block, the step replayed as one CUDA graph)"}}
         print(json.dumps(line), flush=True)
     barrier()
     s.close()
