@@ -82,6 +82,12 @@ __device__ __forceinline__ void mm8(double &d0, double &d1, double ax, double ay
     dmma(e0, e1, ax, bx, c0, c1);
     dmma(d0, d1, ay, by, e0, e1);
 }
+#ifndef MMAG_UF
+#define MMAG_UF 1        // unroll factor of the factor sweep
+#endif
+#ifndef MMAG_UV
+#define MMAG_UV 2        // unroll factor of the vector sweeps
+#endif
 #define MMAG_PRAGMA_(x) _Pragma(#x)
 #define MMAG_UNROLL(n) MMAG_PRAGMA_(unroll n)
 __device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -357,7 +363,7 @@ __device__ __forceinline__ void mmag_factor(const admpc_opts &o, double *rec, co
     double atx, aty, vx, vy, btx, bty;
     af.load(st, atx, aty); vf.load(st, vx, vy); bf.load(st, btx, bty);
     double2 bar01 = ldv(st + W_BAR), bar23 = ldv(st + W_BAR + 2), bar45 = ldv(st + W_BAR + 4), gxp = ldv(st + W_GX + 2 * t);
-MMAG_UNROLL(1)
+MMAG_UNROLL(MMAG_UF)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         ADMPC_ASSERT(st == rec + (size_t)k * W_RS);
         double *sw = const_cast<double *>(st);
@@ -427,7 +433,7 @@ __device__ __forceinline__ void mmag_forward(const admpc_opts &o, double *rec, i
         const double u = sn[a0o], v = sn[a1o];
         a0x = l0x ? u : c0x; a0y = l0y ? v : c0y;
     }
-MMAG_UNROLL(2)
+MMAG_UNROLL(MMAG_UV)
     for (int k = 0; k < N; k++, st += W_RS) {
         mm8(xx, xy, xx, xy, acx, acy, 0.0, 0.0);
         dmma(acx, acy, bm, kh, a0x, a0y);
@@ -460,7 +466,7 @@ __device__ __forceinline__ void mmag_backward(const admpc_opts &o, double *rec, 
     cf.load(st - W_RS, bm, kh); af.load(st - W_RS, atx, aty);
     double2 pb = ldv(st + W_PB + 2 * t), gx = ldv(st + W_GX + 2 * t), k0 = ldv(st + W_K0 + 2 * t), k1 = ldv(st + W_K1 + 2 * t);
     double2 rt = ldv(st + W_BAR + 2);
-MMAG_UNROLL(2)
+MMAG_UNROLL(MMAG_UV)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         const double cx = m0 * fma(k1.x, rt.y, fma(k0.x, rt.x, gx.x)), cy = m0y * fma(k1.y, rt.y, fma(k0.y, rt.x, gx.y));
         const double hx = fma(m0, pb.x, px), hy = fma(m0y, pb.y, py);
@@ -490,7 +496,7 @@ __device__ __forceinline__ void mmag_adjoint(double *rec, const double *term, in
     double atx, aty;
     af.load(st, atx, aty);
     double2 gx = ldv(st + W_GX + 2 * t);
-MMAG_UNROLL(2)
+MMAG_UNROLL(MMAG_UV)
     for (int k = N - 1; k >= 0; k--, st -= W_RS) {
         if (l < 4) stv(st + W_PB + 2 * t, px, py);
         const double cx = m0 * gx.x, cy = m0 * gx.y;
