@@ -62,3 +62,18 @@ f.solve()
 print("5. Frenet variant: %d ok, mean |e_y| at the end of the horizon %.3f m (start %.3f m)" % (
     (f.get_status()[0] == 0).sum(), np.abs(f.get_x()[:, -1, 1]).mean(), np.abs(fb["x0"][:, 1]).mean()))
 f.close()
+
+# 5b. the variant as the reference defines it: kappa(s) spline evaluated inside the model + its own constraint set
+from ad_mpc_b200 import kappa_pp_from_knots
+q = [0.0, 10.0, 10.0, 10.0, 10.0, 1.0, 0.1]
+own = default_opts(N, model_variant=1, con_set=1, W=q + [10.0, 10.0], We=[0.01 * v for v in q], zl=[100.0, 100.0], zu=[100.0, 100.0],
+                   lbu=[-10.0, -2.0], ubu=[5.0, 2.0], lbx=-0.52, ubx=0.52, lbx2=-2.0, ubx2=2.0)
+s_knots = np.linspace(-50.0, 450.0, 26)
+breaks, coef = kappa_pp_from_knots(s_knots, 0.02 + 0.01 * np.sin(0.03 * s_knots))     # what the reference hands to CasADi's bspline
+f = BatchSolver(B, own)
+f.set_kappa_spline(breaks, coef)                                                      # shared by all vehicles (or [B, ...] per vehicle)
+f.set_iterate(fb["x_init"], fb["u_init"]); f.set_x0(fb["x0"]); f.set_yref(fb["yref"]); f.set_p(fb["p"])
+f.solve()
+print("5b. Frenet variant, spline curvature + own constraint set: %d ok, %d inequality rows per stage" % (
+    (f.get_status()[0] == 0).sum(), f.get_lam().shape[-1]))
+f.close()
