@@ -158,15 +158,16 @@ int admpc_batch_set_p(admpc_batch *h, const double *p /*[B][N]*/);
 int admpc_batch_set_p_scalar(admpc_batch *h, const double *p /*[B]*/);      /* same switch on all stages (:449-450) */
 /* Frenet variant only (opts.model_variant == 1): path curvature kappa[B][N] at every shooting node (default 0; the
  * reference evaluates a B-spline kappa(s) inside the model, fren_ad_3d_optimizer bytecode).  With kappa = 0 the variant
- * coincides with the Cartesian model.  Kernels: csrc/frenet.cu (preparation) and csrc/qp_warp_f.cu (feedback), full SQP mode
+ * coincides with the Cartesian model.  Kernels: gp_sweep_kernel<FR> + csrc/frenet.cu (two-pass preparation) and csrc/qp_mma_g.cu
+ * (feedback on the FP64 tensor cores: both curvature forms, both constraint sets, N <= 63), full SQP mode
  * included; the device reference generator and the closed-loop plant are Cartesian-only (ADMPC_E_UNSUPPORTED). */
 int admpc_batch_set_kappa(admpc_batch *h, const double *kappa);
 /* Frenet variant, the reference's own semantics: kappa(s) as a spline of the arc length evaluated INSIDE the model at every
  * RK4 sub-stage, the Jacobian gaining its d kappa / d s column (bytecode: interpolant('kapparef_s', 'bspline', s_knots,
  * curv)).  Any spline is passed in piecewise-polynomial form: K cubic pieces per instance, breaks[B][K+1], coef[B][K][4]
  * with kappa(s) = c0 + c1 t + c2 t^2 + c3 t^3, t = s - breaks[j] (end pieces extrapolate); K <= 64.  K = 0 / NULL returns
- * to the per-node constants.  With a spline the column of s in A_k is dense and the feedback phase runs the dense
- * thread-per-instance kernel (qp_dense_kernel) instead of the structured warp kernel. */
+ * to the per-node constants.  With a spline the column of s in A_k is dense; the default feedback kernel (qp_mma_g.cu) assumes
+ * no trivial column, so both forms run at the same speed. */
 int admpc_batch_set_kappa_spline(admpc_batch *h, int K, const double *breaks, const double *coef);
 int admpc_batch_set_gp_state(admpc_batch *h, const double *gp_state /*[B][7] or NULL = x0*/);
 /* iterate (initial guess / warm start).  reset zeroes it like $G/acados_solver_sim_car.c:819-852. */
