@@ -1381,7 +1381,8 @@ extern "C" int sim_car_acados_create_with_discretization(sim_car_solver_capsule 
     c->N = N;
     c->x0.assign(7, 0.0); c->yref.assign((size_t)N * 9 + 7, 0.0); c->p.assign(N, 0.0); c->kappa.assign(N, 0.0);
     c->x.assign((size_t)(N + 1) * 7, 0.0); c->u.assign((size_t)N * 2, 0.0); c->pi.assign((size_t)N * 7, 0.0);
-    c->lam.assign((size_t)N * NC, 0.0); c->t.assign((size_t)N * NC, 0.0); c->sl.assign((size_t)N * 2, 0.0); c->su.assign((size_t)N * 2, 0.0);
+    const size_t nc = (size_t)con_rows(o);          // 10 rows per stage (shipped set) or 12 (the Frenet variant's own, con_set = 1)
+    c->lam.assign((size_t)N * nc, 0.0); c->t.assign((size_t)N * nc, 0.0); c->sl.assign((size_t)N * 2, 0.0); c->su.assign((size_t)N * 2, 0.0);
     return 0;
 }
 extern "C" int sim_car_acados_create(sim_car_solver_capsule *c) { return c ? sim_car_acados_create_with_discretization(c, c->opts.N, nullptr) : ADMPC_E_ARG; }
@@ -1472,17 +1473,26 @@ extern "C" int sim_car_acados_set(sim_car_solver_capsule *c, int stage, const ch
             if ((r = admpc_batch_get_slacks(c->h, c->sl.data(), c->su.data()))) return r;
             c->duals_stale = false;
         }
+        const int nc = con_rows(c->opts);
+        const bool own = (nc == 12);                // con_set = 1: rows [lb u0 u1 e_y delta | ub .. | ls0 ls1 | us0 us1], slack 1 belongs to delta
         if (!strcmp(field, "pi")) { if (n != 7) return ADMPC_E_ARG; memcpy(&c->pi[(size_t)stage * 7], v, 56); }
-        else if (!strcmp(field, "sl")) { if (n != 2) return ADMPC_E_ARG; memcpy(&c->sl[(size_t)stage * 2], v, 16); }
-        else if (!strcmp(field, "su")) { if (n != 2) return ADMPC_E_ARG; memcpy(&c->su[(size_t)stage * 2], v, 16); }
-        else {
-            double *d = ((field[0] == 'l') ? c->lam : c->t).data() + (size_t)stage * NC;
-            if (stage >= 1) { if (n != NC) return ADMPC_E_ARG; memcpy(d, v, sizeof(double) * NC); }
-            else {      // stage 0 arrives in the acados layout [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(2) | us(2)]
+        else if (!strcmp(field, "sl") || !strcmp(field, "su")) {
+            double *d = ((field[1] == 'l') ? c->sl : c->su).data() + (size_t)stage * 2;
+            if (own && stage == 0) { if (n != 1) return ADMPC_E_ARG; d[0] = v[0]; d[1] = 0.0; }      // no state slack at stage 0
+            else { if (n != 2) return ADMPC_E_ARG; memcpy(d, v, 16); }
+        } else {
+            double *d = ((field[0] == 'l') ? c->lam : c->t).data() + (size_t)stage * nc;
+            const double off = (field[0] == 'l') ? 0.0 : 1.0;             // rows that do not exist at stage 0 (x0 is eliminated)
+            if (stage >= 1) { if (n != nc) return ADMPC_E_ARG; memcpy(d, v, sizeof(double) * nc); }
+            else if (!own) {    // stage 0 arrives in the acados layout [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(2) | us(2)]
                 if (n != 22) return ADMPC_E_ARG;
                 d[0] = v[0]; d[1] = v[1]; d[3] = v[9]; d[4] = v[10];
                 for (int j = 0; j < 4; j++) d[6 + j] = v[18 + j];
-                d[2] = (field[0] == 'l') ? 0.0 : 1.0; d[5] = d[2];        // no state bound at stage 0 (x0 is eliminated)
+                d[2] = off; d[5] = off;
+            } else {            // con_set = 1, ad_mpc/debug.json lam_0: [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(1) | us(1)]
+                if (n != 20) return ADMPC_E_ARG;
+                d[0] = v[0]; d[1] = v[1]; d[4] = v[9]; d[5] = v[10]; d[8] = v[18]; d[10] = v[19];
+                d[2] = d[3] = d[6] = d[7] = d[9] = d[11] = off;
             }
         }
         c->duals_dirty = true;
@@ -1626,17 +1636,31 @@ extern "C" int sim_car_acados_get(sim_car_solver_capsule *c, int stage, const ch
         c->duals_stale = false;
     }
     if (!strcmp(field, "pi")) { if (n != 7) return ADMPC_E_ARG; memcpy(out, &c->pi[(size_t)stage * 7], 56); return 0; }
-    if (!strcmp(field, "sl")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->sl[(size_t)stage * 2], 16); return 0; }
-    if (!strcmp(field, "su")) { if (n != 2) return ADMPC_E_ARG; memcpy(out, &c->su[(size_t)stage * 2], 16); return 0; }
+    const int nc = con_rows(c->opts);
+    const bool own = (nc == 12);
+    if (!strcmp(field, "sl") || !strcmp(field, "su")) {
+        const double *s = ((field[1] == 'l') ? c->sl : c->su).data() + (size_t)stage * 2;
+        if (own && stage == 0) { if (n != 1) return ADMPC_E_ARG; out[0] = s[0]; return 0; }           // debug.json: sl_0 has one entry
+        if (n != 2) return ADMPC_E_ARG;
+        memcpy(out, s, 16);
+        return 0;
+    }
     if (!strcmp(field, "lam") || !strcmp(field, "t")) {
         const std::vector<double> &src = (field[0] == 'l') ? c->lam : c->t;
-        const double *s = &src[(size_t)stage * NC];
-        if (stage >= 1) { if (n != NC) return ADMPC_E_ARG; memcpy(out, s, sizeof(double) * NC); return 0; }
-        // stage 0 in acados layout: [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(2) | us(2)]  (sim_car_iterate.json lam_0)
-        if (n != 22) return ADMPC_E_ARG;
-        for (int j = 0; j < 22; j++) out[j] = 1e-16;
-        out[0] = s[0]; out[1] = s[1]; out[9] = s[3]; out[10] = s[4];
-        for (int j = 0; j < 4; j++) out[18 + j] = s[6 + j];
+        const double *s = &src[(size_t)stage * nc];
+        if (stage >= 1) { if (n != nc) return ADMPC_E_ARG; memcpy(out, s, sizeof(double) * nc); return 0; }
+        if (!own) {
+            // stage 0 in acados layout: [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(2) | us(2)]  (sim_car_iterate.json lam_0)
+            if (n != 22) return ADMPC_E_ARG;
+            for (int j = 0; j < 22; j++) out[j] = 1e-16;
+            out[0] = s[0]; out[1] = s[1]; out[9] = s[3]; out[10] = s[4];
+            for (int j = 0; j < 4; j++) out[18 + j] = s[6 + j];
+            return 0;
+        }
+        // con_set = 1: [lbu(2) lbx0(7) | ubu(2) ubx0(7) | ls(1) | us(1)]  (ad_mpc/debug.json lam_0, 20 entries)
+        if (n != 20) return ADMPC_E_ARG;
+        for (int j = 0; j < 20; j++) out[j] = 1e-16;
+        out[0] = s[0]; out[1] = s[1]; out[9] = s[4]; out[10] = s[5]; out[18] = s[8]; out[19] = s[10];
         return 0;
     }
     admpc_set_error("sim_car_acados_get", "unknown field");

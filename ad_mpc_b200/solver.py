@@ -479,6 +479,7 @@ class AcadosOcpSolverB200:
         check(self.L.sim_car_acados_create_with_discretization(self.c, int(n), None), "create")
         self.N = int(n)
         self.status = 0
+        self.own_set = bool(opts is not None and opts.con_set == 1)      # the Frenet variant's own constraint set: 12 rows per stage
 
     def set(self, stage, field, value):
         v = _f64(np.atleast_1d(value)).reshape(-1)
@@ -490,7 +491,10 @@ class AcadosOcpSolverB200:
         return self.status
 
     def get(self, stage, field):
-        n = {"x": 7, "u": 2, "pi": 7, "sl": 2, "su": 2}.get(field, 22 if stage == 0 else NC)
+        if self.own_set:        # ad_mpc/debug.json: 12 multipliers and 2 + 2 slacks per stage, 20 / 1 + 1 at stage 0
+            n = {"x": 7, "u": 2, "pi": 7, "sl": 1 if stage == 0 else 2, "su": 1 if stage == 0 else 2}.get(field, 20 if stage == 0 else 12)
+        else:
+            n = {"x": 7, "u": 2, "pi": 7, "sl": 2, "su": 2}.get(field, 22 if stage == 0 else NC)
         out = np.empty(n)
         check(self.L.sim_car_acados_get(self.c, int(stage), field.encode(), _dp(out), n), "get(%s)" % field)
         return out

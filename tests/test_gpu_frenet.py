@@ -121,6 +121,50 @@ def test_frenet_through_the_acados_shim():
     assert mixed_err(u, r["u"][0]) <= TOL
 
 
+def test_frenet_own_constraint_set_through_the_acados_shim(tmp_path):
+    """Single-instance shim with con_set = 1: multipliers / slacks in the layout of the reference's iterate dump of this variant
+    (ad_mpc/debug.json: 12 rows and 2 + 2 slacks per stage, 20 / 1 + 1 at stage 0), store_iterate / load_iterate round trip."""
+    from ad_mpc_b200 import AcadosOcpSolverB200
+    N = 20
+    b = wl.make_batch_frenet(1, N, seed=331, p=1.0, perturb=1.0)
+    b["x_init"][:, :, 1] = np.clip(b["x_init"][:, :, 1], -0.5, 0.5); b["x0"][:, 1] = np.clip(b["x0"][:, 1], -0.5, 0.5)
+    opts = _frenet_own_opts(N)
+
+    def fill(cap):
+        for j in range(N):
+            cap.set(j, "yref", b["yref"][0][j * 9:(j + 1) * 9])
+            cap.set(j, "p", b["p"][0][j])
+            cap.set(j, "kappa", b["kappa"][0][j])
+        cap.set(N, "yref", b["yref"][0][N * 9:])
+        cap.set(0, "lbx", b["x0"][0]); cap.set(0, "ubx", b["x0"][0])
+
+    cap = AcadosOcpSolverB200(opts)
+    fill(cap)
+    for j in range(N + 1):
+        cap.set(j, "x", b["x_init"][0, j])
+    assert cap.solve() == 0
+    r = orc.rti_batch(mirror_opts(opts), b["x0"], b["yref"], b["p"], b["x_init"], b["u_init"], kappa=b["kappa"])
+    u = np.stack([cap.get(j, "u") for j in range(N)])
+    assert mixed_err(u, r["u"][0]) <= TOL
+    assert cap.get(0, "lam").shape == (20,) and cap.get(3, "lam").shape == (12,) and cap.get(0, "sl").shape == (1,) and cap.get(3, "su").shape == (2,)
+    Tz = opts.dt * 100.0
+    lam3 = cap.get(3, "lam")
+    assert abs(lam3[0] + lam3[8] - Tz) < 1e-6 and abs(lam3[3] + lam3[9] - Tz) < 1e-6          # slack stationarity: u0 and delta are the soft rows
+    lam0 = cap.get(0, "lam")
+    assert abs(lam0[0] + lam0[18] - Tz) < 1e-6 and (lam0[2:9] == 1e-16).all()                # stage 0: u0's slack only, x0 rows eliminated
+    # round trip through the acados iterate file: a second solver loaded from it continues exactly like the first one
+    f = str(tmp_path / "iterate.json")
+    d = cap.store_iterate(f)
+    assert len(d["lam_0"]) == 20 and len(d["lam_1"]) == 12 and len(d["sl_0"]) == 1 and len(d["sl_1"]) == 2
+    cap2 = AcadosOcpSolverB200(opts)
+    fill(cap2)
+    cap2.load_iterate(f)
+    assert cap.solve() == 0 and cap2.solve() == 0
+    for j in (0, 5, N - 1):
+        assert np.array_equal(cap.get(j, "u"), cap2.get(j, "u"))
+        assert np.allclose(cap.get(j, "lam"), cap2.get(j, "lam"), rtol=0, atol=0)
+
+
 def test_frenet_kernel_variants_agree(monkeypatch):
     """The warp-per-instance Frenet kernel (6x8 stage structure, default for N <= 63) and the dense thread-per-instance
     kernel (ADMPC_QP_VARIANT=1, also the N > 63 fallback) are independent implementations: same statuses / iteration
