@@ -506,6 +506,7 @@ def run_ours(args):
                     "kernels_ms": kern,
                     "kernels_frac": {k: ops[k] * B / (kern[k] * 1e-3) / 1e12 / peak.value for k in kern},
                     "all_kernels_tflops": (ops["prepare"] + ops["qp"]) * B / ((kern["prepare"] + kern["qp"]) * 1e-3) / 1e12,
+                    "step_frac": (ops["prepare"] + ops["qp"]) * B / (ms_per_step * 1e-3) / 1e12 / peak.value,     # whole step, all kernels
                     "hbm": {"algorithmic_GBps": algorithmic_bytes(N) * B / (ms_per_step * 1e-3) / 1e9, "peak_GBps": hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
         # ---- CPU baseline on this box's host cores ----------------------------------------------------------
