@@ -128,7 +128,7 @@ struct admpc_batch {
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     bool profiling = false;
     bool gps_set = false;
-    int qp_variant = 0;      // 0 auto, 1 thread-per-instance (qp_ipm.cu), 3 smem octets (qp_smem.cu), 4 warp per instance (qp_warp.cu), 7 resident warp(s) + DMMA sweeps (qp_mma.cu)
+    int qp_variant = 0;      // 0 auto, 1 thread-per-instance (qp_ipm.cu), 4 warp(s) per instance, register-resident (qp_warp.cu, N <= 63), 7 resident warp(s) + DMMA sweeps (qp_mma.cu, N <= 127)
     long long launches = 0;
     float ms_solve = 0, ms_prepare = 0, ms_qp = 0;
     char *pack = nullptr, *gpack = nullptr;     // packed [u | x | status] block of this rank / of all ranks (root)
@@ -199,20 +199,20 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
     struct Item { double **p; size_t rows; };
     const size_t nX = (size_t)(N + 1) * 7, nU = (size_t)N * 2, nPi = (size_t)N * 7, nC = (size_t)N * con_rows(h->P.o);
     double *x0, *yref, *pp, *gps, *kap = nullptr;
-    // Interface arrays always; QP workspaces only for the kernel variant this handle will run: the warp-per-instance
-    // kernel (N <= 63) keeps its whole working set on chip, the octet kernel needs its scratch tiles, the
-    // thread-per-instance kernel streams a 35 KB/instance SoA workspace.
-    int variant = h->qp_variant ? h->qp_variant : (N <= 63 ? 7 : 3);
-    if (variant == 7 && N > 63) variant = 3;                       // the tensor-core kernel takes one node per thread of one or two warps
-    const bool need_ws3 = (variant == 3 || (variant >= 4 && N > 63)) && N <= 80;
+    // Interface arrays always; the QP workspace only for handles that run the thread-per-instance kernel (a 35 KB/instance SoA
+    // workspace streamed from HBM): the tensor-core kernels (variant 7, N <= 127) and the round-1 warp kernel (variant 4,
+    // N <= 63) keep their whole working set on chip.
+    int variant = h->qp_variant ? h->qp_variant : 7;
+    if (variant != 7 && variant != 4) variant = 1;
+    if ((variant == 7 && N > 127) || (variant == 4 && N > 63)) variant = 1;
     const bool frenet = h->P.o.model_variant == 1;
-    const bool need_ws1 = (variant == 1) || N > 80 || frenet;
-    // the shared-memory-resident warp kernel (variant 7) stages instance-major linearisation records by TMA; every other
+    const bool need_ws1 = (variant == 1) || frenet;
+    // the shared-memory-resident tensor-core kernel (variant 7) stages instance-major linearisation records by TMA; every other
     // feedback kernel reads the SoA rows.  Exactly one of the two layouts exists per handle.
-    const bool use_im = (variant == 7) && N <= 63 && !frenet;
+    const bool use_im = (variant == 7) && !frenet;
     // Frenet variant: the tensor-core kernel (qp_mma_g.cu) pulls 80-double instance-major records; written next to the dense
     // SoA linearisation the SQP residual kernel and the dense QP kernel read
-    const bool use_im_f = frenet && (h->qp_variant == 0 || h->qp_variant == 7) && N <= 63;
+    const bool use_im_f = frenet && (h->qp_variant == 0 || h->qp_variant == 7) && N <= 127;
     std::vector<Item> items = {
         {&x0, 7}, {&yref, (size_t)N * 9 + 7}, {&pp, (size_t)N}, {&gps, 7},
         {&P.xb, nX}, {&P.ub, nU}, {&P.pib, nPi}, {&P.lamb, nC}, {&P.tb, nC}, {&P.slb, nU}, {&P.sub, nU},
@@ -220,7 +220,6 @@ extern "C" int admpc_batch_create(const admpc_opts *opts, int B, int device, adm
         {&P.lin_d, frenet ? (size_t)(N + 1) * DL_ROWS : 0}, {&kap, frenet ? (size_t)N : 0},
         {&P.lin, (use_im || frenet) ? 0 : (size_t)(N + 1) * LIN_ROWS}, {&P.lin_im, use_im ? (size_t)(N + 1) * LIM_STRIDE : (use_im_f ? (size_t)(N + 1) * 80 : 0)}, {&P.res_out, 4},
     };
-    if (need_ws3) items.push_back({&P.ws, (size_t)qp_smem_ws_rows(N)});
     if (need_ws1) {
         std::vector<Item> w1 = {
             {&P.dx, nX}, {&P.du, nU}, {&P.pi, nPi}, {&P.lam, nC}, {&P.t, nC}, {&P.sl, nU}, {&P.su, nU},
@@ -555,10 +554,10 @@ static int launch_feedback(admpc_batch *h)
     const Params &P = h->P;
     h->gat_fresh = false;
     if (P.o.model_variant == 1) {
-        // Frenet variant: the tensor-core kernel qp_mma_g (N <= 63, no trivial column assumed -- a spline curvature makes the
+        // Frenet variant: the tensor-core kernel qp_mma_g (N <= 127, no trivial column assumed -- a spline curvature makes the
         // column of s dense --, both constraint sets, fused update); on request the round-1 warp kernel on the 6x8 stage
         // structure (ADMPC_QP_VARIANT=4: per-node curvature and con_set = 0 only) or the dense thread-per-instance kernel +
-        // separate update (ADMPC_QP_VARIANT=1, also the N > 63 fallback)
+        // separate update (ADMPC_QP_VARIANT=1, also the N > 127 fallback)
         if ((h->qp_variant == 0 || h->qp_variant == 7) && launch_qp_mma_g(P, h->stream)) {
             if (h->profiling) CUDA_CHECK_RET(cudaEventRecord(h->ev[3], h->stream));
             h->launches += 1;
@@ -577,16 +576,14 @@ static int launch_feedback(admpc_batch *h)
         h->launches += 2;
         return 0;
     }
-    // QP variant (0 = auto): 7 one / two warps per instance, shared-memory resident, Riccati sweeps as FP64 tensor-core
-    // fragments (qp_mma.cu, default for N <= 63); 4 warp(s) per instance with register-resident IPM state (qp_warp.cu, the
-    // round-1 kernel, kept as an independent implementation); 3 shared-memory octets (horizons 64..80); 1 one thread per
-    // instance.  A variant that cannot take the horizon falls through to the next one.
+    // QP variant (0 = auto): 7 one / two / four warps per instance, shared-memory resident, Riccati sweeps as FP64 tensor-core
+    // fragments (qp_mma.cu, default for N <= 127); 4 one / two warps per instance with register-resident IPM state (qp_warp.cu,
+    // the round-1 kernel, kept as an independent implementation, N <= 63); 1 one thread per instance (any horizon).  A variant
+    // that cannot take the horizon falls through to the thread-per-instance kernel.
     int variant = h->qp_variant ? h->qp_variant : 7;
-    if (variant == 7 && P.o.N > 63) variant = 4;
     bool fused = false;
-    if (variant == 7) { fused = launch_qp_mma(P, h->stream); h->gat_fresh = fused && h->gat_on; }    // warp per instance, sweeps on the FP64 tensor cores
-    if (!fused && variant >= 4) { fused = launch_qp_warp(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // one / two warps per instance, N <= 63
-    if (!fused && variant >= 3 && P.ws) fused = launch_qp_smem(P, h->stream);
+    if (variant == 7) { fused = launch_qp_mma(P, h->stream); h->gat_fresh = fused && h->gat_on; }    // sweeps on the FP64 tensor cores
+    if (!fused && variant == 4) { fused = launch_qp_warp(P, h->stream); h->gat_fresh = fused && h->gat_on; }   // N <= 63
     if (!fused) {
         if (!P.dx) { admpc_set_error("admpc_batch_solve", "QP workspace for this kernel variant was not allocated at create"); return ADMPC_E_STATE; }
         launch_qp(P, h->stream);
@@ -602,7 +599,7 @@ extern "C" int admpc_batch_solve(admpc_batch *h)
     if (!h) return ADMPC_E_ARG;
     CUDA_CHECK_RET(cudaSetDevice(h->device));
     // Frenet variant, RTI step through the tensor-core kernel: only the instance-major records are consumed
-    h->P.skip_lin_d = (h->P.o.model_variant == 1 && (h->qp_variant == 0 || h->qp_variant == 7) && h->P.o.N <= 63 && h->P.lin_im) ? 1 : 0;
+    h->P.skip_lin_d = (h->P.o.model_variant == 1 && (h->qp_variant == 0 || h->qp_variant == 7) && h->P.o.N <= 127 && h->P.lin_im) ? 1 : 0;
     const Params &P = h->P;
     CUDA_CHECK_RET(cudaEventRecord(h->ev[0], h->stream));
     CUDA_CHECK_RET(cudaMemsetAsync(P.lin_bad, 0, (size_t)P.Bp * sizeof(int), h->stream));

@@ -75,7 +75,6 @@ struct Params {
     double *rgu, *rgx, *rgsl, *rgsu, *rb, *rd, *rm;
     double *K, *Ginv, *P, *Pb, *kf, *pv;
     double *ddu, *ddx, *dpi, *dlam, *dt, *dsl, *dsu;
-    double *ws;          // qp_smem.cu: per-warp scratch tiles [Bp/4][rows][4]
     int *status, *qp_status, *qp_iter, *lin_bad;
     double *res_out;     // [4][Bp] final residual norms
     // full SQP mode (sqp.cu): lin_bad == 2 marks an instance that has finished and is skipped by prepare / QP kernels
@@ -143,10 +142,8 @@ struct SmemGuard {
 void launch_prepare(const Params &P, cudaStream_t s);
 void launch_gp_sweep(const Params &P, cudaStream_t s);   // pass 1 of a GP-augmented preparation: GP mean / gradient at the RK4 stage points -> gpr
 void launch_qp(const Params &P, cudaStream_t s);
-bool launch_qp_smem(const Params &P, cudaStream_t s);   // false: horizon too long for the shared-memory variant
-int qp_smem_ws_rows(int N);
 bool launch_qp_warp(const Params &P, cudaStream_t s);   // false: N > 31
-bool launch_qp_mma(const Params &P, cudaStream_t s);    // one / two warps per instance, whole solve resident in shared memory, sweeps on the FP64 tensor cores (DMMA), false: N > 63
+bool launch_qp_mma(const Params &P, cudaStream_t s);    // one / two / four warps per instance, whole solve resident in shared memory, sweeps on the FP64 tensor cores (DMMA), false: N > 127
 void launch_transpose_in(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);   // [B][F] -> [F][Bp]
 void launch_transpose_out(const double *src, double *dst, int B, int Bp, int F, cudaStream_t s);  // [F][Bp] -> [B][F]
 void launch_bcast_rows(const double *src, double *dst, int Bp, int F, cudaStream_t s);            // [Bp] -> [F][Bp]
@@ -160,7 +157,7 @@ void launch_capsule_gather(const Params &P, double *out, cudaStream_t s);
 void launch_gp_select(const Params &P, const double *xq, const double *uq, int *sel, cudaStream_t s);
 void launch_qp_dense(const Params &P, cudaStream_t s);
 bool launch_qp_warp_f(const Params &P, cudaStream_t s);   // Frenet structure, false: N > 63
-bool launch_qp_mma_g(const Params &P, cudaStream_t s);    // Frenet variant on the FP64 tensor cores (dense column of s, both constraint sets), false: N > 63 or no instance-major records
+bool launch_qp_mma_g(const Params &P, cudaStream_t s);    // Frenet variant on the FP64 tensor cores (dense column of s, both constraint sets), false: N > 127 or no instance-major records
 void launch_nlp_res_dense(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_nlp_res(const Params &P, int it, const double tol[4], int *active, cudaStream_t s);
 void launch_sqp_finalize(const Params &P, cudaStream_t s);

@@ -20,7 +20,7 @@
 //                             instance-major records qp_mma_g.cu pulls by TMA and, when something reads them, the SoA rows
 //                             lin_d[k][79][Bp]
 //   qp_dense_kernel           the same Mehrotra / Riccati IPM on dense stage matrices, one thread per instance, workspace in HBM,
-//                             run-time constraint descriptor: independent cross-check (ADMPC_QP_VARIANT=1) and N > 63 fallback;
+//                             run-time constraint descriptor: independent cross-check (ADMPC_QP_VARIANT=1) and N = 128 fallback;
 //                             ~12x the run time of the default kernel (qp_mma_g.cu)
 //   nlp_res_dense_kernel      NLP KKT residuals of the full-SQP mode on the dense linearisation
 #include "common.cuh"

@@ -1,4 +1,4 @@
-// qp_mma.cu -- feedback phase, v7: ONE (N <= 31) OR TWO (N <= 63) WARPS PER MPC INSTANCE, the whole solve resident in shared
+// qp_mma.cu -- feedback phase, v7: ONE (N <= 31), TWO (N <= 63) OR FOUR (N <= 127) WARPS PER MPC INSTANCE, the whole solve resident in shared
 // memory, the horizon-sequential Riccati sweeps on the FP64 TENSOR CORES (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).
 //
 // Why: the v6 kernel (same residency, hand-distributed sweeps; profiles/r02_qp_rw_summary.md) spent 70 % of its time in five
@@ -375,13 +375,14 @@ __device__ __forceinline__ void node_dir(const double *st, int k, double ddx[7],
 #define MMA_MINB 8
 #endif
 // NW warps per instance: thread k owns node k in the node role (N <= 32 NW - 1); the sweeps run on warp 0 while the others wait
-// at the CTA barrier.  NW = 1: N <= 31, 8 instances per SM ; NW = 2: N <= 63, 4 instances per SM (BASELINE cfg4: N = 40).
+// at the CTA barrier.  NW = 1: N <= 31, 8 instances per SM ; NW = 2: N <= 63, 4 instances per SM (BASELINE cfg4: N = 40) ;
+// NW = 4: N <= 127 (long horizons: one or two instances per SM by shared memory).
 template <int NW> __device__ __forceinline__ void bsync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
 template <int NW>
-__global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kernel(const Params P)
+__global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : (NW == 2) ? 4 : 1) qp_mma_kernel(const Params P)
 {
     extern __shared__ __align__(16) double smr[];
-    __shared__ double red[16];                       // cross-warp reductions (NW = 2)
+    __shared__ double red[8 * NW];                   // cross-warp reductions (NW > 1): 8 slots per warp
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
     const int tid = threadIdx.x, l = tid & 31, wid = tid >> 5;
@@ -594,10 +595,15 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
             st[W_GX + 6] = gx[6];
         }
         ng = wmax32(ng); nb = wmax32(nb); nd = wmax32(nd); nm = wmax32(nm); summ = wsum32(summ);
-        if (NW == 2) {
+        if (NW > 1) {
             if (l == 0) { red[wid * 8] = ng; red[wid * 8 + 1] = nb; red[wid * 8 + 2] = nd; red[wid * 8 + 3] = nm; red[wid * 8 + 4] = summ; }
             __syncthreads();
-            ng = nmx(red[0], red[8]); nb = nmx(red[1], red[9]); nd = nmx(red[2], red[10]); nm = nmx(red[3], red[11]); summ = red[4] + red[12];
+            ng = red[0]; nb = red[1]; nd = red[2]; nm = red[3]; summ = red[4];
+#pragma unroll
+            for (int w = 1; w < NW; w++) {
+                ng = nmx(ng, red[w * 8]); nb = nmx(nb, red[w * 8 + 1]); nd = nmx(nd, red[w * 8 + 2]); nm = nmx(nm, red[w * 8 + 3]);
+                summ += red[w * 8 + 4];
+            }
             __syncthreads();
         }
         res0 = ng; res1 = nb; res2 = nd; res3 = nm;
@@ -655,10 +661,12 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
         }
         m_aff = wmaxf32(m_aff);
         s1 = wsum32(s1); s2 = wsum32(s2);
-        if (NW == 2) {
+        if (NW > 1) {
             if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
             __syncthreads();
-            m_aff = fmax(red[0], red[8]); s1 = red[1] + red[9]; s2 = red[2] + red[10];
+            m_aff = red[0]; s1 = red[1]; s2 = red[2];
+#pragma unroll
+            for (int w = 1; w < NW; w++) { m_aff = fmax(m_aff, red[w * 8]); s1 += red[w * 8 + 1]; s2 += red[w * 8 + 2]; }
             __syncthreads();
         }
         const double a_aff = rcp_w(m_aff);               // min(1, min ratio) = 1 / max(1, max of the inverse ratios)
@@ -724,11 +732,12 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
             if (ad < an * mt) { an = 1.0; ad = mt; }
         }
         warp_ratio(an, ad);
-        if (NW == 2) {
+        if (NW > 1) {
             if (l == 0) { red[wid * 8] = an; red[wid * 8 + 1] = ad; }
             __syncthreads();
             an = red[0]; ad = red[1];
-            if (red[8] * ad < an * red[9]) { an = red[8]; ad = red[9]; }
+#pragma unroll
+            for (int w = 1; w < NW; w++) if (red[w * 8] * ad < an * red[w * 8 + 1]) { an = red[w * 8]; ad = red[w * 8 + 1]; }
             __syncthreads();
         }
         double alpha = an * rcp_w(ad);
@@ -823,7 +832,7 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : 4) qp_mma_kern
 bool launch_qp_mma(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
-    if (N > 63 || !P.lin_im) return false;
+    if (N > 127 || !P.lin_im) return false;
     size_t sm = ((size_t)N * W_RS + T_SIZE) * sizeof(double);
 #ifdef QPM_SMEM_PAD_ENV      // occupancy probe: ADMPC_SMEM_PAD = extra bytes of (unused) dynamic shared memory per CTA
     if (const char *e = getenv("ADMPC_SMEM_PAD")) sm += (size_t)atoi(e);
@@ -832,10 +841,14 @@ bool launch_qp_mma(const Params &P, cudaStream_t s)
         static SmemGuard configured;
         if (configured.need(sm)) cudaFuncSetAttribute(qp_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         qp_mma_kernel<1><<<P.B, 32, sm, s>>>(P);
-    } else {
+    } else if (N <= 63) {
         static SmemGuard configured2;
         if (configured2.need(sm)) cudaFuncSetAttribute(qp_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         qp_mma_kernel<2><<<P.B, 64, sm, s>>>(P);
+    } else {
+        static SmemGuard configured4;
+        if (configured4.need(sm)) cudaFuncSetAttribute(qp_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        qp_mma_kernel<4><<<P.B, 128, sm, s>>>(P);
     }
     return true;
 }

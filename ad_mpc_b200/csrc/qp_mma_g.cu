@@ -1,4 +1,4 @@
-// qp_mma_g.cu -- feedback phase of the FRENET model variant (SURVEY 8a A2'): ONE (N <= 31) OR TWO (N <= 63) WARPS PER INSTANCE,
+// qp_mma_g.cu -- feedback phase of the FRENET model variant (SURVEY 8a A2'): ONE (N <= 31), TWO (N <= 63) OR FOUR (N <= 127) WARPS PER INSTANCE,
 // whole IPM solve resident in shared memory, Riccati sweeps as FP64 DMMA fragment chains -- the design of qp_mma.cu for a stage
 // with no exploitable column.  Covers the variant as the reference defines it: curvature as a spline kappa(s) inside the model
 // (the column of s in A_k is then dense; nothing of A but the delta row is trivial) and the variant's own constraint set
@@ -21,7 +21,7 @@
 // History: a first tensor-core kernel for this variant (qp_mma_f, z = (u, x1..x6) with the trivial column of s split off and a
 // permuted position layout) covered per-node curvature and con_set = 0 only and measured 2.00 ms at B = 16384, N = 20; this
 // kernel runs the same case in 1.89 ms and replaced it.  Cross-checks kept: qp_warp_f.cu (round-1 warp kernel, per-node
-// curvature, con_set = 0) and the dense thread-per-instance kernel of frenet.cu (everything, also the N > 63 fallback);
+// curvature, con_set = 0) and the dense thread-per-instance kernel of frenet.cu (everything, also the N = 128 fallback);
 // identical maths to oracle/rti_oracle.c with model_backend = 2, results differ by rounding only.
 #include "common.cuh"
 #include "tma.cuh"
@@ -536,14 +536,14 @@ __device__ __forceinline__ void node_dir_g(const double *st, int k, double ddx[7
 #define MMAG_MINB 8
 #endif
 // NW warps per instance: thread k owns node k in the node role (N <= 32 NW - 1); the sweeps run on warp 0 while the others wait
-// at the CTA barrier.  NW = 1: N <= 31, 8 instances per SM at N = 20 ; NW = 2: N <= 63.
+// at the CTA barrier.  NW = 1: N <= 31, 8 instances per SM at N = 20 ; NW = 2: N <= 63 ; NW = 4: N <= 127.
 template <int NW> __device__ __forceinline__ void bsync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
 template <int NW, int CS>
-__global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 4) qp_mma_g_kernel(const Params P)
+__global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : (NW == 2) ? 4 : 1) qp_mma_g_kernel(const Params P)
 {
     constexpr int NQ = CSet<CS>::NQ, NR = CSet<CS>::NR;
     extern __shared__ __align__(16) double smr[];
-    __shared__ double red[16];                       // cross-warp reductions (NW = 2)
+    __shared__ double red[8 * NW];                   // cross-warp reductions (NW > 1): 8 slots per warp
     const admpc_opts &o = P.o;
     const int N = o.N, Bp = P.Bp;
     const int tid = threadIdx.x, l = tid & 31, wid = tid >> 5;
@@ -774,10 +774,15 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 4) qp_mma_g_k
             stv(st + W_GX, gx[0], gx[1]); stv(st + W_GX + 2, gx[2], gx[3]); stv(st + W_GX + 4, gx[4], gx[5]); st[W_GX + 6] = gx[6];
         }
         ng = wmax32(ng); nb = wmax32(nb); nd = wmax32(nd); nm = wmax32(nm); summ = wsum32(summ);
-        if (NW == 2) {
+        if (NW > 1) {
             if (l == 0) { red[wid * 8] = ng; red[wid * 8 + 1] = nb; red[wid * 8 + 2] = nd; red[wid * 8 + 3] = nm; red[wid * 8 + 4] = summ; }
             __syncthreads();
-            ng = nmx(red[0], red[8]); nb = nmx(red[1], red[9]); nd = nmx(red[2], red[10]); nm = nmx(red[3], red[11]); summ = red[4] + red[12];
+            ng = red[0]; nb = red[1]; nd = red[2]; nm = red[3]; summ = red[4];
+#pragma unroll
+            for (int w = 1; w < NW; w++) {
+                ng = nmx(ng, red[w * 8]); nb = nmx(nb, red[w * 8 + 1]); nd = nmx(nd, red[w * 8 + 2]); nm = nmx(nm, red[w * 8 + 3]);
+                summ += red[w * 8 + 4];
+            }
             __syncthreads();
         }
         res0 = ng; res1 = nb; res2 = nd; res3 = nm;
@@ -864,10 +869,12 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 4) qp_mma_g_k
                 }
                 m_aff = wmaxf32(act ? m_aff : 1.0);
                 s1 = wsum32(act ? s1 : 0.0); s2 = wsum32(act ? s2 : 0.0);
-                if (NW == 2) {
+                if (NW > 1) {
                     if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
                     __syncthreads();
-                    m_aff = fmax(red[0], red[8]); s1 = red[1] + red[9]; s2 = red[2] + red[10];
+                    m_aff = red[0]; s1 = red[1]; s2 = red[2];
+#pragma unroll
+                    for (int w = 1; w < NW; w++) { m_aff = fmax(m_aff, red[w * 8]); s1 += red[w * 8 + 1]; s2 += red[w * 8 + 2]; }
                     __syncthreads();
                 }
                 const double a_aff = rcp_w(m_aff);           // min(1, min ratio) = 1 / max(1, max of the inverse ratios)
@@ -906,11 +913,12 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : 4) qp_mma_g_k
             if (ad < an * mt) { an = 1.0; ad = mt; }
         }
         warp_ratio(an, ad);
-        if (NW == 2) {
+        if (NW > 1) {
             if (l == 0) { red[wid * 8] = an; red[wid * 8 + 1] = ad; }
             __syncthreads();
             an = red[0]; ad = red[1];
-            if (red[8] * ad < an * red[9]) { an = red[8]; ad = red[9]; }
+#pragma unroll
+            for (int w = 1; w < NW; w++) if (red[w * 8] * ad < an * red[w * 8 + 1]) { an = red[w * 8]; ad = red[w * 8 + 1]; }
             __syncthreads();
         }
         double alpha = an * rcp_w(ad);
@@ -1013,10 +1021,11 @@ template <int NW, int CS> static void launch_one(const Params &P, size_t sm, cud
 bool launch_qp_mma_g(const Params &P, cudaStream_t s)
 {
     const int N = P.o.N;
-    if (N > 63 || !P.lin_im) return false;
+    if (N > 127 || !P.lin_im) return false;
     const size_t sm = ((size_t)N * W_RS + T_SIZE) * sizeof(double);
     const bool cs1 = (P.o.con_set == 1);
     if (N <= 31) { if (cs1) launch_one<1, 1>(P, sm, s); else launch_one<1, 0>(P, sm, s); }
-    else { if (cs1) launch_one<2, 1>(P, sm, s); else launch_one<2, 0>(P, sm, s); }
+    else if (N <= 63) { if (cs1) launch_one<2, 1>(P, sm, s); else launch_one<2, 0>(P, sm, s); }
+    else { if (cs1) launch_one<4, 1>(P, sm, s); else launch_one<4, 0>(P, sm, s); }
     return true;
 }

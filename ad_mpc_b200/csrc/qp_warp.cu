@@ -13,7 +13,7 @@
 // write the updated iterate back (fused RTI update).
 //
 // Algorithm: HPIPM-style Mehrotra predictor-corrector IPM on the OCP-structured QP [EXT], replacing
-// FULL_CONDENSING_HPIPM (acados_solver_sim_car.c:145,688-693).  Same maths as qp_smem.cu / qp_ipm.cu; divisions by
+// FULL_CONDENSING_HPIPM (acados_solver_sim_car.c:145,688-693).  Same maths as qp_ipm.cu; divisions by
 // t are done as multiplications by 1/t and the ratio test keeps (num, den) pairs, so results differ from the other
 // variants by rounding only.
 #include "common.cuh"

@@ -496,7 +496,7 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         _v = os.environ.get("ADMPC_QP_VARIANT", "")
-        qp_name = "qp_mma_kernel<%d>" % (1 if N <= 31 else 2) if _v in ("", "0", "7") and N <= 63 else "qp_warp_kernel"
+        qp_name = "qp_mma_kernel<%d>" % (1 if N <= 31 else 2 if N <= 63 else 4) if _v in ("", "0", "7") and N <= 127 else "qp_warp_kernel"
         roofline = {"bound": "fp64", "kernel": {"prepare": "gp_sweep_kernel + prepare_kernel<GP>", "qp": qp_name}[dom],
                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,

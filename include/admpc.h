@@ -159,7 +159,7 @@ int admpc_batch_set_p_scalar(admpc_batch *h, const double *p /*[B]*/);      /* s
 /* Frenet variant only (opts.model_variant == 1): path curvature kappa[B][N] at every shooting node (default 0; the
  * reference evaluates a B-spline kappa(s) inside the model, fren_ad_3d_optimizer bytecode).  With kappa = 0 the variant
  * coincides with the Cartesian model.  Kernels: gp_sweep_kernel<FR> + csrc/frenet.cu (two-pass preparation) and csrc/qp_mma_g.cu
- * (feedback on the FP64 tensor cores: both curvature forms, both constraint sets, N <= 63), full SQP mode
+ * (feedback on the FP64 tensor cores: both curvature forms, both constraint sets, N <= 127), full SQP mode
  * included; the device reference generator and the closed-loop plant are Cartesian-only (ADMPC_E_UNSUPPORTED). */
 int admpc_batch_set_kappa(admpc_batch *h, const double *kappa);
 /* Frenet variant, the reference's own semantics: kappa(s) as a spline of the arc length evaluated INSIDE the model at every

@@ -3,7 +3,7 @@ import math, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ad_mpc_b200 import BatchSolver, default_opts, workload as wl
-for N, B, M, variant in ((20, 37, 24, "4"), (40, 9, 0, "3"), (20, 5, 0, "1")):
+for N, B, M, variant in ((20, 37, 24, "4"), (40, 9, 0, "7"), (20, 5, 0, "1")):
     os.environ["ADMPC_QP_VARIANT"] = variant
     batch = wl.make_batch(B, N, seed=1, p=1.0, perturb=3.0)
     s = BatchSolver(B, default_opts(N))

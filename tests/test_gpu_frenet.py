@@ -167,7 +167,7 @@ def test_frenet_own_constraint_set_through_the_acados_shim(tmp_path):
 
 def test_frenet_kernel_variants_agree(monkeypatch):
     """The warp-per-instance Frenet kernel (6x8 stage structure, default for N <= 63) and the dense thread-per-instance
-    kernel (ADMPC_QP_VARIANT=1, also the N > 63 fallback) are independent implementations: same statuses / iteration
+    kernel (ADMPC_QP_VARIANT=1, also the N > 127 fallback) are independent implementations: same statuses / iteration
     counts, 1e-8 agreement, on a batch with active bounds; and the long-horizon fallback against the oracle."""
     B, N = 64, 20
     batch = wl.make_batch_frenet(B, N, seed=350, p=0.7, perturb=5.0)
@@ -182,7 +182,7 @@ def test_frenet_kernel_variants_agree(monkeypatch):
     assert np.array_equal(out[1]["qp_iter"], out[4]["qp_iter"]) and np.array_equal(out[1]["status"], out[4]["status"])
     assert mixed_err(out[1]["u"], out[4]["u"]) <= TOL and mixed_err(out[1]["x"], out[4]["x"]) <= TOL
     monkeypatch.delenv("ADMPC_QP_VARIANT")
-    for Nl in (31, 32, 63, 70):
+    for Nl in (31, 32, 63, 64, 100, 127, 128):
         bl = wl.make_batch_frenet(10, Nl, seed=360 + Nl, p=1.0, perturb=2.0)
         opts = default_opts(Nl, model_variant=1)
         s = BatchSolver(10, opts)

@@ -362,48 +362,53 @@ def test_scale_invariance_full_size():
 
 def test_long_horizon_fallback_variants():
     """Horizon dispatch of the feedback kernel: N <= 31 the tensor-core kernel with one warp per instance (qp_mma<1>), 32..63
-    with two (qp_mma<2>), 64..80 the shared-memory octet kernel, above that one thread per instance -- same parity bar
-    on both sides of every edge."""
-    for N, B in ((31, 16), (32, 16), (40, 24), (63, 12), (64, 12), (90, 12)):
-        batch = wl.make_batch(B, N, seed=31, p=1.0, perturb=3.0 if N in (32, 63) else 1.0)
+    with two (qp_mma<2>), 64..127 with four (qp_mma<4>), above that one thread per instance -- same parity bar on both
+    sides of every edge."""
+    launches = {}
+    for N, B in ((31, 16), (32, 16), (40, 24), (63, 12), (64, 12), (90, 12), (127, 6), (128, 6)):
+        batch = wl.make_batch(B, N, seed=31, p=1.0, perturb=3.0 if N in (32, 63, 127) else 1.0)
         opts = default_opts(N)
         s = BatchSolver(B, opts)
+        n0 = s.kernel_launches()
         g = _gpu_step(s, batch)
+        launches[N] = s.kernel_launches() - n0
         r = oracle_batch(mirror_opts(opts), batch)
         _compare(g, r)
         s.close()
+    # the update is fused into the feedback kernel up to N = 127; the thread-per-instance kernel beyond needs one more launch
+    assert launches[31] == launches[64] == launches[127] and launches[128] == launches[127] + 1
 
 
-def test_two_warp_kernel_matches_octet_kernel(monkeypatch):
+def test_multi_warp_kernels_match_the_other_implementations(monkeypatch):
     """N = 40 with active bounds: the two-warps-per-instance tensor-core kernel (default, 7) against the register-resident
-    two-warp kernel (4) and the octet kernel (3)."""
-    B, N = 96, 40
-    batch = wl.make_batch(B, N, seed=78, p=0.5, perturb=5.0)
-    out = {}
-    for v in (3, 4, 7):
-        monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
-        s = BatchSolver(B, default_opts(N))
-        out[v] = _gpu_step(s, batch)
-        s.close()
-    for v in (3, 4):
-        assert np.array_equal(out[v]["qp_iter"], out[7]["qp_iter"]) and np.array_equal(out[v]["status"], out[7]["status"])
-        assert mixed_err(out[v]["u"], out[7]["u"]) <= TOL and mixed_err(out[v]["x"], out[7]["x"]) <= TOL
-    r = oracle_batch(mirror_opts(default_opts(N)), batch)
-    _compare(out[7], r)
+    two-warp kernel (4) and the thread-per-instance kernel (1); N = 90: four warps per instance (7) against (1)."""
+    for N, B, others in ((40, 96, (1, 4)), (90, 24, (1,))):
+        batch = wl.make_batch(B, N, seed=78, p=0.5, perturb=5.0)
+        out = {}
+        for v in others + (7,):
+            monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
+            s = BatchSolver(B, default_opts(N))
+            out[v] = _gpu_step(s, batch)
+            s.close()
+        for v in others:
+            assert np.array_equal(out[v]["qp_iter"], out[7]["qp_iter"]) and np.array_equal(out[v]["status"], out[7]["status"])
+            assert mixed_err(out[v]["u"], out[7]["u"]) <= TOL and mixed_err(out[v]["x"], out[7]["x"]) <= TOL
+        r = oracle_batch(mirror_opts(default_opts(N)), batch)
+        _compare(out[7], r)
 
 
 def test_qp_variants_agree(monkeypatch):
-    """The four QP kernels are independent implementations of the same algorithm: identical statuses / iteration
+    """The three QP kernels are independent implementations of the same algorithm: identical statuses / iteration
     counts and 1e-8 agreement on a batch with active bounds (7 = tensor-core sweeps, the default)."""
     B, N = 128, 20
     batch = wl.make_batch(B, N, seed=77, p=0.5, perturb=5.0)
     out = {}
-    for v in (1, 3, 4, 7):
+    for v in (1, 4, 7):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, default_opts(N))
         out[v] = _gpu_step(s, batch)
         s.close()
-    for v in (1, 3, 4):
+    for v in (1, 4):
         assert np.array_equal(out[v]["qp_iter"], out[7]["qp_iter"]) and np.array_equal(out[v]["status"], out[7]["status"]), v
         assert mixed_err(out[v]["u"], out[7]["u"]) <= TOL and mixed_err(out[v]["x"], out[7]["x"]) <= TOL, v
 
@@ -508,7 +513,7 @@ def test_sqp_mode_with_gp_and_other_qp_kernels(monkeypatch):
     gp = orc.Gp(model)
     gp.apply(o, feat=model["feat"], rows=model["rows"])
     r = orc.sqp_batch(o, batch["x0"], batch["yref"], batch["p"], batch["x_init"], batch["u_init"], gp=gp, gp_state=batch["x0"])
-    for v in (7, 4, 3, 1):
+    for v in (7, 4, 1):
         monkeypatch.setenv("ADMPC_QP_VARIANT", str(v))
         s = BatchSolver(B, opts)
         s.set_gp(model)
