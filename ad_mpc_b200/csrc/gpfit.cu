@@ -7,6 +7,8 @@
 // The hyper-parameter search stays a host loop (L-BFGS-B like the reference, ad_mpc_b200/gpfit.py); every NLL
 // evaluation and the final alpha run here.  FP64 throughout: K has condition ~ sigma_f M / sigma_n^2.
 //
+// The right-hand side is one more tile row below the matrix (augmented factorisation): the steps that factorise K leave
+// z = L^-1 y in it, the NLL needs no substitution (sum log L_ii + z^T z / 2), alpha one backward substitution.
 // Blocked right-looking Cholesky on 32x32 tiles of the padded matrix (row-major, lower triangle):
 //   potrf32 (one CTA)  ->  trsm32 (one CTA per tile below the diagonal)  ->  syrk32 (one CTA per trailing tile pair).
 // The trailing update is the dense GEMM of this path (M^3/3 flops, 2.7 GFLOP at M = 2000); B200 has no FP64 tcgen05
@@ -19,7 +21,7 @@
 #define TB 32
 
 // K build: one thread per (i, j) of the padded Mp x Mp matrix; padding = identity
-__global__ void gpfit_build_kernel(const double *__restrict__ Xs, int M, int Mp, int dz, double sigma_f, double sn2,
+__global__ void gpfit_build_kernel(const double *__restrict__ Xs, int M, int Mp, int ld, int dz, double sigma_f, double sn2,
                                    double *__restrict__ A)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
@@ -32,7 +34,14 @@ __global__ void gpfit_build_kernel(const double *__restrict__ Xs, int M, int Mp,
     } else {
         v = (i == j) ? 1.0 : 0.0;
     }
-    A[(size_t)i * Mp + j] = v;
+    A[(size_t)i * ld + j] = v;
+}
+// the right-hand side as one more row below the matrix (row Mp of the augmented factorisation): the same trsm32 / syrk32 steps
+// that factorise K leave z = L^-1 y in it -- the forward substitution comes for free
+__global__ void gpfit_aug_row_kernel(double *__restrict__ A, int ld, int Mp, int M, const double *__restrict__ y)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < Mp) A[(size_t)Mp * ld + j] = (j < M) ? y[j] : 0.0;
 }
 
 // Cholesky of the diagonal tile (j, j): ONE WARP, lane r owns row r of the tile in registers; the pivot column is
@@ -126,15 +135,17 @@ __global__ void __launch_bounds__(256) gpfit_syrk32(double *A, int Mp, int jb, i
 // 256-byte reads.  Backward: lane c owns column c of the current block column, the warps stride over the rows below it
 // (again one coalesced 256-byte read per row), partial sums meet in shared memory.  The 32x32 diagonal solves stay on
 // warp 0.  (the Mp x Mp factor may sit in the top-left corner of a larger matrix: row stride ldA)
+// do_fwd / do_bwd select the two substitutions (admpc_gp_fit gets z from the augmented factorisation and needs the backward one only,
+// and only when alpha is asked for)
 __global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restrict__ A, int M, int Mp, int ldA, double *y,
-                                                            const double *__restrict__ y0, double *out2)
+                                                            const double *__restrict__ y0, double *out2, int do_fwd, int do_bwd)
 {
     __shared__ double xb[TB];
     __shared__ double part[TB][TB + 1];
     __shared__ double red[32];
     const int nb = Mp / TB, t = threadIdx.x, w = t >> 5, l = t & 31;
     // forward: L z = y
-    for (int b = 0; b < nb; b++) {
+    for (int b = 0; b < (do_fwd ? nb : 0); b++) {
         {
             const double *row = A + (size_t)(b * TB + w) * ldA;
             double s = 0.0;
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(1024) gpfit_solve_kernel(const double *__restr
         __syncthreads();
     }
     // backward: L^T alpha = z
-    for (int b = nb - 1; b >= 0; b--) {
+    for (int b = (do_bwd ? nb - 1 : -1); b >= 0; b--) {
         {
             double s = 0.0;
             for (int i = (b + 1) * TB + w; i < Mp; i += 32) s = fma(A[(size_t)i * ldA + b * TB + l], y[i], s);
@@ -217,6 +228,7 @@ extern "C" int admpc_gp_fit(int device, int M, int dz, const double *X, const do
     if (device < 0 || device >= ndev) { admpc_set_error("admpc_gp_fit", "no such CUDA device"); return ADMPC_E_CUDA; }
     CUDA_CHECK_RET(cudaSetDevice(device));
     const int Mp = (M + TB - 1) / TB * TB, nb = Mp / TB;
+    const int Mt = Mp + TB, nbt = Mt / TB;          // one more tile row: the right-hand side (augmented factorisation)
     std::vector<double> Xs((size_t)M * dz), yp(Mp, 0.0);
     for (int i = 0; i < M; i++)
         for (int d = 0; d < dz; d++) Xs[(size_t)i * dz + d] = X[(size_t)i * dz + d] / ell[d];     // cdist(x/l, x/l), gp.py:103
@@ -231,7 +243,7 @@ extern "C" int admpc_gp_fit(int device, int M, int dz, const double *X, const do
     do {
 #define GP_TRY(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { admpc_set_error(#call, cudaGetErrorString(e_)); rc = ADMPC_E_CUDA; break; } }
         GP_TRY(cudaMalloc(&dXs, Xs.size() * sizeof(double)));
-        GP_TRY(cudaMalloc(&dA, (size_t)Mp * Mp * sizeof(double)));
+        GP_TRY(cudaMalloc(&dA, (size_t)Mt * Mt * sizeof(double)));
         GP_TRY(cudaMalloc(&dy, Mp * sizeof(double)));
         GP_TRY(cudaMalloc(&dy0, Mp * sizeof(double)));
         GP_TRY(cudaMalloc(&dout, 2 * sizeof(double)));
@@ -242,16 +254,18 @@ extern "C" int admpc_gp_fit(int device, int M, int dz, const double *X, const do
         GP_TRY(cudaMemsetAsync(dfail, 0, sizeof(int), s));
         GP_TRY(cudaEventRecord(e0, s));
         dim3 bb(16, 16), bg((Mp + 15) / 16, (Mp + 15) / 16);
-        gpfit_build_kernel<<<bg, bb, 0, s>>>(dXs, M, Mp, dz, sigma_f, sigma_n * sigma_n, dA);
-        for (int j = 0; j < nb; j++) {
-            gpfit_potrf32<<<1, 32, 0, s>>>(dA, Mp, j, dfail);
-            const int rem = nb - j - 1;
-            if (rem > 0) {
-                gpfit_trsm32<<<(rem + 3) / 4, 128, 0, s>>>(dA, Mp, j, nb);
-                gpfit_syrk32<<<dim3(rem, rem), dim3(16, 16), 0, s>>>(dA, Mp, j, nb);
-            }
+        GP_TRY(cudaMemsetAsync(dA + (size_t)Mp * Mt, 0, (size_t)TB * Mt * sizeof(double), s));     // the extra tile row
+        gpfit_build_kernel<<<bg, bb, 0, s>>>(dXs, M, Mp, Mt, dz, sigma_f, sigma_n * sigma_n, dA);
+        gpfit_aug_row_kernel<<<(Mp + 255) / 256, 256, 0, s>>>(dA, Mt, Mp, M, dy0);
+        for (int j = 0; j < nb; j++) {                       // the first Mp / 32 block columns: K = L L^T, row Mp <- (L^-1 y)^T
+            gpfit_potrf32<<<1, 32, 0, s>>>(dA, Mt, j, dfail);
+            const int rem = nbt - j - 1;
+            gpfit_trsm32<<<(rem + 3) / 4, 128, 0, s>>>(dA, Mt, j, nbt);
+            gpfit_syrk32<<<dim3(rem, rem), dim3(16, 16), 0, s>>>(dA, Mt, j, nbt);
         }
-        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, Mp, dy, dy0, dout);
+        // z = L^-1 y sits in row Mp; nll needs sum log L_ii + z^T z / 2, alpha (only when asked for) the backward substitution
+        GP_TRY(cudaMemcpyAsync(dy, dA + (size_t)Mp * Mt, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, Mt, dy, alpha_out ? dy0 : dy, dout, 0, alpha_out ? 1 : 0);
         GP_TRY(cudaEventRecord(e1, s));
         GP_TRY(cudaGetLastError());
         double out2[2];
@@ -372,7 +386,7 @@ extern "C" int admpc_gp_predict(int device, int M, int dz, const double *X, cons
             gpfit_trsm32<<<(rem + 3) / 4, 128, 0, s>>>(dA, Mt, j, nb);
             gpfit_syrk32<<<dim3(rem, rem), dim3(16, 16), 0, s>>>(dA, Mt, j, nb);
         }
-        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, Mt, dy, dy0, dout);        // alpha = K^-1 y
+        gpfit_solve_kernel<<<1, 1024, 0, s>>>(dA, M, Mp, Mt, dy, dy0, dout, 1, 1);  // alpha = K^-1 y
         gpfit_mean_kernel<<<(n * 32 + 127) / 128, 128, 0, s>>>(dXs, dXt, dy, M, n, dz, sigma_f, y_mean, dmu);
         dim3 cg((n + 15) / 16, (n + 15) / 16);
         gpfit_cov_out_kernel<<<cg, bb, 0, s>>>(dA, Mp, n, Mt, dvar, dcov);
