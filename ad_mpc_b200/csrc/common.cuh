@@ -37,7 +37,7 @@ __host__ __device__ __forceinline__ constexpr int lim_of_row(int row)      // So
 
 // entries of the 2^(j/GP_TAB) table of the device exp2 (model.cuh), stored behind the last GP output in the blob
 #ifndef GP_TAB_BITS
-#define GP_TAB_BITS 6
+#define GP_TAB_BITS 8
 #endif
 #define GP_TAB (1 << GP_TAB_BITS)
 struct GpDev {

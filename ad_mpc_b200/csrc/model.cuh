@@ -63,9 +63,10 @@ __device__ __forceinline__ double exp2_neg(double t)
 
 // 2^t for t <= 0, table-driven: t = n + j/GP_TAB + f with |f| <= 1/(2 GP_TAB); 2^(j/GP_TAB) from a GP_TAB-entry
 // shared-memory table (appended to the GP blob by the host), 2^f - 1 by a short Taylor/Horner polynomial (truncation
-// < 4e-18 relative), 2^n through the exponent field.  10 FP64-pipe instructions against 17 for exp2_neg; the clamp
-// (t < -1000 -> 2^-1000 = 1e-301 instead of a denormal/zero) is an integer compare.  With GP_TAB = 32 two lanes
-// conflict on a bank only when their indices differ by exactly 16.
+// < 4e-17 relative), 2^n through the exponent field.  GP_TAB = 256 (2 KB, the default): degree 4, 9 FP64-pipe instructions
+// against 17 for exp2_neg (GP_TAB = 64: degree 5, 10 instructions; measured 1.172 -> 1.131 ms for the cfg3 preparation, the
+// extra bank conflicts of the larger table do not show); the clamp (t < -1000 -> 2^-1000 = 1e-301 instead of a denormal /
+// zero) is an integer compare.
 struct Exp2Part { double f, T; int nsh; };
 // front half: range reduction, table fetch, exponent increment (already shifted into the high word)
 __device__ __forceinline__ Exp2Part exp2_front(double t, uint32_t tab)       // tab: shared-space address of the table
@@ -84,6 +85,9 @@ __device__ __forceinline__ Exp2Part exp2_front(double t, uint32_t tab)       // 
 __device__ __forceinline__ double exp2_back(const Exp2Part &e)
 {
     const double f = e.f;
+#if GP_TAB_BITS >= 8                                        // |f| <= 1/512: the f^5 term is below 4e-17 relative
+    double p = 9.61812910762847716e-03;
+#else
 #if GP_TAB_BITS == 6
     double p = 1.33335581464284434e-03;
 #elif GP_TAB_BITS == 5
@@ -95,6 +99,7 @@ __device__ __forceinline__ double exp2_back(const Exp2Part &e)
     p = fma(p, f, 1.33335581464284434e-03);
 #endif
     p = fma(p, f, 9.61812910762847716e-03);
+#endif
     p = fma(p, f, 5.55041086648215800e-02);
     p = fma(p, f, 2.40226506959100712e-01);
     p = fma(p, f, 6.93147180559945309e-01);
