@@ -67,6 +67,7 @@
 #define T_XB 24     // 7   x_N of the linearisation point
 #define T_SIZE 32
 
+#define NMX_INT      // residual-norm maxima as integer maxima (qp_node.cuh)
 #include "qp_node.cuh"
 
 // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor core: a = A[g][t], b = B[t][g], (c0, c1) = C[g][2t..2t+1]

@@ -24,7 +24,19 @@ __device__ __forceinline__ double rcp_w(double x)
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
-__device__ __forceinline__ double nmx(double a, double b) { return (a > b || a != a) ? a : b; }   // NaN-propagating
+// NaN-propagating maximum.  NMX_INT (qp_mma_g.cu): every use is nmx(running maximum, fabs(..)) or a reduction of such, i.e.
+// NON-NEGATIVE values; for sign bit 0 the IEEE order is the order of the bit patterns and a NaN is larger than every finite
+// pattern, so an integer maximum does it off the FP64 pipe (a DSETP pair per maximum otherwise).  Measured: qp_mma_g<1,1>
+// 1.777 -> 1.727 ms; qp_mma<1> 1.500 -> 1.519 ms (it starts to spill), which therefore keeps the floating-point form.
+#ifdef NMX_INT
+__device__ __forceinline__ double nmx(double a, double b)
+{
+    const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+    return __longlong_as_double(ia > ib ? ia : ib);
+}
+#else
+__device__ __forceinline__ double nmx(double a, double b) { return (a > b || a != a) ? a : b; }
+#endif
 __device__ __forceinline__ double wsum32(double v)
 {
 #pragma unroll
