@@ -70,6 +70,7 @@
 #define T_XB 24     // 7   x_N of the linearisation point
 #define T_SIZE 32
 
+#define NMX_INT
 #include "qp_node.cuh"
 
 // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor core: a = A[g][t], b = B[t][g], (c0, c1) = C[g][2t..2t+1]
@@ -478,6 +479,8 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : (NW == 2) ? 4 
 
     const double inv_nc = 1.0 / (double)(NC * N - 2);
     const int k = tid;                               // node of this thread
+    const bool act = (k < N);
+    const int kc = act ? k : N - 1;                  // record the lanes without a node compute on (results masked)
     int status = 1, iter = 0;
     double res0 = 0, res1 = 0, res2 = 0, res3 = 0;
     for (iter = 0;; iter++) {
@@ -613,111 +616,107 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : (NW == 2) ? 4 
         const double mu = summ * inv_nc;
         bsync<NW>();
 
-        // ================= predictor ========================================================================================
-        if (sweeper) mma_factor(o, rec, term, N, l);
-        bsync<NW>();
-        if (sweeper) mma_forward(o, rec, N, l);
-        bsync<NW>();
-        // affine step: step length, mu_aff ; the complementarity products and the two linear functionals the corrected
-        // barrier gradient needs stay in registers of the node's lane
-        double an = 1.0, ad = 1.0, s1 = 0.0, s2 = 0.0, m_aff = 1.0;
-        double pr[NC], fa[3], fb[3];
+        // ================= predictor (pass 0) and corrector (pass 1) ==========================================================
+        // One rolled loop: the node-role arithmetic both passes share (constraint data, residuals, scalings, step of the node for
+        // the direction the roll-out left) exists once in the instruction stream.  pass 0 runs with pr = 0, sigma mu = 0: rm = lam t.
+        double an = 1.0, ad = 1.0, sigmu = 0.0;
+        double pr[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) pr[c] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) { fa[c] = 0.0; fb[c] = 0.0; }
-        if (k < N) {
-            const double *st = rec + (size_t)k * W_RS;
-            NCon C; load_ncon(o, st, C);
-            NRes R; node_res_w(o, k >= 1, C, R);
-            NScal S; node_scal_w(o, C, S);
-            double rm[NC];
-#pragma unroll
-            for (int c = 0; c < NC; c++) rm[c] = ((c == 2 || c == 5) && k == 0) ? 0.0 : C.lam[c] * C.t[c];
-            double ddx[7], ddu[2];
-            node_dir(st, k, ddx, ddu);
-            NStep D;
-            node_step_w(k >= 1, C, R, S, rm, ddu[0], ddu[1], ddx[6], D);
-            m_aff = node_ratio_aff(k >= 1, S, D, m_aff);
-            double ea[NC], eb[NC];       // change of g = (rm - lam rd)/t caused by rm -> rm + dlam dt - sigma mu: ea - sigma mu eb
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const bool on = !((c == 2 || c == 5) && k == 0);
-                pr[c] = on ? D.dlv[c] * D.dtv[c] : 0.0;
-                ea[c] = pr[c] * S.it[c];
-                eb[c] = on ? S.it[c] : 0.0;
-                if (on) {
-                    s1 += C.lam[c] * D.dtv[c] + C.t[c] * D.dlv[c];
-                    s2 += pr[c];
+        NCon Cs;
+        NScal Ss;
+        NStep Ds;
+        double duc[2] = {0.0, 0.0}, ddx[7];
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 0) {
+                if (sweeper) mma_factor(o, rec, term, N, l);
+            } else {
+                if (sweeper) mma_backward(o, rec, term, N, l);
+                bsync<NW>();
+                // k_ff of the corrector: -Guu^-1 (rt + B^T h_k), node-parallel
+                if (k < N) {
+                    double *st = rec + (size_t)k * W_RS;
+                    const double2 rt = ldv(st + W_BAR + 2);
+                    const double2 h01 = ldv(st + W_PB), h23 = ldv(st + W_PB + 2), h45 = ldv(st + W_PB + 4);
+                    const double h6 = st[W_PB + 6];
+                    const double gu0 = rt.x + dot6v(ldv(st + W_M), ldv(st + W_M + 2), ldv(st + W_M + 4), h01, h23, h45);
+                    const double gu1 = fma(hdt, h6, rt.y) + dot6v(ldv(st + W_M + 6), ldv(st + W_M + 8), ldv(st + W_M + 10), h01, h23, h45);
+                    const double gi00 = st[W_GI0], gi01 = st[W_GI1], gi11 = st[W_GI2];
+                    st[W_KF0] = -(gi00 * gu0 + gi01 * gu1);
+                    st[W_KF1] = -(gi01 * gu0 + gi11 * gu1);
                 }
             }
+            bsync<NW>();
+            if (sweeper) mma_forward(o, rec, N, l);
+            bsync<NW>();
+            NRes R;
+            {
+                const double *st = rec + (size_t)kc * W_RS;
+                load_ncon(o, st, Cs);
+                node_res_w(o, kc >= 1, Cs, R);
+                node_scal_w(o, Cs, Ss);
+                double rm[NC];
 #pragma unroll
-            for (int jj = 0; jj < 2; jj++) {
-                fa[jj] = (ea[jj] - S.Sl[jj] * (ea[jj] + ea[6 + jj]) * S.iDl[jj]) - (ea[3 + jj] - S.Su[jj] * (ea[3 + jj] + ea[8 + jj]) * S.iDu[jj]);
-                fb[jj] = (eb[jj] - S.Sl[jj] * (eb[jj] + eb[6 + jj]) * S.iDl[jj]) - (eb[3 + jj] - S.Su[jj] * (eb[3 + jj] + eb[8 + jj]) * S.iDu[jj]);
+                for (int c = 0; c < NC; c++) rm[c] = ((c == 2 || c == 5) && kc == 0) ? 0.0 : Cs.lam[c] * Cs.t[c] + pr[c] - sigmu;
+                node_dir(st, kc, ddx, duc);
+                node_step_w(kc >= 1, Cs, R, Ss, rm, duc[0], duc[1], ddx[6], Ds);
             }
-            fa[2] = ea[2] - ea[5];
-            fb[2] = eb[2] - eb[5];
-        }
-        m_aff = wmaxf32(m_aff);
-        s1 = wsum32(s1); s2 = wsum32(s2);
-        if (NW > 1) {
-            if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
-            __syncthreads();
-            m_aff = red[0]; s1 = red[1]; s2 = red[2];
+            if (pass == 0) {
+                double s1 = 0.0, s2 = 0.0, m_aff = 1.0;
+                double fa[3], fb[3];
+                {
+                    m_aff = node_ratio_aff(kc >= 1, Ss, Ds, m_aff);
+                    double ea[NC], eb[NC];
 #pragma unroll
-            for (int w = 1; w < NW; w++) { m_aff = fmax(m_aff, red[w * 8]); s1 += red[w * 8 + 1]; s2 += red[w * 8 + 2]; }
-            __syncthreads();
+                    for (int c = 0; c < NC; c++) {
+                        const bool on = !((c == 2 || c == 5) && kc == 0);
+                        pr[c] = on ? Ds.dlv[c] * Ds.dtv[c] : 0.0;
+                        ea[c] = pr[c] * Ss.it[c];
+                        eb[c] = on ? Ss.it[c] : 0.0;
+                        if (on) {
+                            s1 += Cs.lam[c] * Ds.dtv[c] + Cs.t[c] * Ds.dlv[c];
+                            s2 += pr[c];
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++) {
+                        fa[jj] = (ea[jj] - Ss.Sl[jj] * (ea[jj] + ea[6 + jj]) * Ss.iDl[jj]) - (ea[3 + jj] - Ss.Su[jj] * (ea[3 + jj] + ea[8 + jj]) * Ss.iDu[jj]);
+                        fb[jj] = (eb[jj] - Ss.Sl[jj] * (eb[jj] + eb[6 + jj]) * Ss.iDl[jj]) - (eb[3 + jj] - Ss.Su[jj] * (eb[3 + jj] + eb[8 + jj]) * Ss.iDu[jj]);
+                    }
+                    fa[2] = ea[2] - ea[5];
+                    fb[2] = eb[2] - eb[5];
+                }
+                m_aff = wmaxf32(act ? m_aff : 1.0);
+                s1 = wsum32(act ? s1 : 0.0); s2 = wsum32(act ? s2 : 0.0);
+                if (NW > 1) {
+                    if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
+                    __syncthreads();
+                    m_aff = red[0]; s1 = red[1]; s2 = red[2];
+#pragma unroll
+                    for (int w = 1; w < NW; w++) { m_aff = fmax(m_aff, red[w * 8]); s1 += red[w * 8 + 1]; s2 += red[w * 8 + 2]; }
+                    __syncthreads();
+                }
+                const double a_aff = rcp_w(m_aff);
+                const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
+                double sigma = mu_aff * rcp_w(mu);
+                sigma = sigma * sigma * sigma;
+                sigmu = sigma * mu;
+                if (k < N) {
+                    double *st = rec + (size_t)k * W_RS;
+                    const double2 rt = ldv(st + W_BAR + 2);
+                    stv(st + W_BAR + 2, rt.x + fma(-sigmu, fb[0], fa[0]), rt.y + fma(-sigmu, fb[1], fa[1]));
+                    if (k >= 1) st[W_GX + 6] += fma(-sigmu, fb[2], fa[2]);
+                }
+                bsync<NW>();
+            }
         }
-        const double a_aff = rcp_w(m_aff);               // min(1, min ratio) = 1 / max(1, max of the inverse ratios)
-        const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
-        double sigma = mu_aff * rcp_w(mu);
-        sigma = sigma * sigma * sigma;
-        const double sigmu = sigma * mu;
-        if (k < N) {
-            double *st = rec + (size_t)k * W_RS;
-            const double2 rt = ldv(st + W_BAR + 2);
-            stv(st + W_BAR + 2, rt.x + fma(-sigmu, fb[0], fa[0]), rt.y + fma(-sigmu, fb[1], fa[1]));
-            if (k >= 1) st[W_GX + 6] += fma(-sigmu, fb[2], fa[2]);
-        }
-        bsync<NW>();
-        // ================= corrector ========================================================================================
-        if (sweeper) mma_backward(o, rec, term, N, l);
-        bsync<NW>();
-        // k_ff of the corrector: -Guu^-1 (rt + B^T h_k), node-parallel
-        if (k < N) {
-            double *st = rec + (size_t)k * W_RS;
-            const double2 rt = ldv(st + W_BAR + 2);
-            const double2 h01 = ldv(st + W_PB), h23 = ldv(st + W_PB + 2), h45 = ldv(st + W_PB + 4);
-            const double h6 = st[W_PB + 6];
-            const double gu0 = rt.x + dot6v(ldv(st + W_M), ldv(st + W_M + 2), ldv(st + W_M + 4), h01, h23, h45);
-            const double gu1 = fma(hdt, h6, rt.y) + dot6v(ldv(st + W_M + 6), ldv(st + W_M + 8), ldv(st + W_M + 10), h01, h23, h45);
-            const double gi00 = st[W_GI0], gi01 = st[W_GI1], gi11 = st[W_GI2];
-            st[W_KF0] = -(gi00 * gu0 + gi01 * gu1);
-            st[W_KF1] = -(gi01 * gu0 + gi11 * gu1);
-        }
-        bsync<NW>();
-        if (sweeper) mma_forward(o, rec, N, l);
-        bsync<NW>();
-        // final step: step length, then the update of the constraint part of the iterate from the same registers
-        an = 1.0; ad = 1.0;
-        NCon Cs;
-        NStep Ds;
-        double duc[2] = {0.0, 0.0};
         if (k == N) {                                 // adjoint start: We ddx_N + r_x,N
             const double *pv = rec + (size_t)(N - 1) * W_RS + W_XA;
 #pragma unroll
             for (int a = 0; a < 7; a++) term[T_GX + a] = fma(o.We[a], pv[a], term[T_GX + a]);
         } else if (k < N) {
             double *st = rec + (size_t)k * W_RS;
-            load_ncon(o, st, Cs);
-            NRes R; node_res_w(o, k >= 1, Cs, R);
-            NScal S; node_scal_w(o, Cs, S);
-            double rm[NC];
-#pragma unroll
-            for (int c = 0; c < NC; c++) rm[c] = ((c == 2 || c == 5) && k == 0) ? 0.0 : Cs.lam[c] * Cs.t[c] + pr[c] - sigmu;
-            double ddx[7];
-            node_dir(st, k, ddx, duc);
             if (k >= 1) {                             // adjoint base vector Qt_k ddx_k + gt_k
                 const double qt6 = st[W_BAR + 4];
                 double nbv[7];
@@ -726,9 +725,8 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMA_MINB : (NW == 2) ? 4 
                 stv(st + W_GX, nbv[0], nbv[1]); stv(st + W_GX + 2, nbv[2], nbv[3]); stv(st + W_GX + 4, nbv[4], nbv[5]);
                 st[W_GX + 6] = nbv[6];
             }
-            node_step_w(k >= 1, Cs, R, S, rm, duc[0], duc[1], ddx[6], Ds);
             node_ratio_lam(k >= 1, Cs, Ds, an, ad);
-            const double mt = node_ratio_t(k >= 1, S, Ds, 1.0);
+            const double mt = node_ratio_t(k >= 1, Ss, Ds, 1.0);
             if (ad < an * mt) { an = 1.0; ad = mt; }
         }
         warp_ratio(an, ad);

@@ -24,10 +24,11 @@ __device__ __forceinline__ double rcp_w(double x)
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
-// NaN-propagating maximum.  NMX_INT (qp_mma_g.cu): every use is nmx(running maximum, fabs(..)) or a reduction of such, i.e.
-// NON-NEGATIVE values; for sign bit 0 the IEEE order is the order of the bit patterns and a NaN is larger than every finite
-// pattern, so an integer maximum does it off the FP64 pipe (a DSETP pair per maximum otherwise).  Measured: qp_mma_g<1,1>
-// 1.777 -> 1.727 ms; qp_mma<1> 1.500 -> 1.519 ms (it starts to spill), which therefore keeps the floating-point form.
+// NaN-propagating maximum.  NMX_INT (qp_mma.cu, qp_mma_g.cu): every use is nmx(running maximum, fabs(..)) or a reduction of
+// such, i.e. NON-NEGATIVE values; for sign bit 0 the IEEE order is the order of the bit patterns and a NaN is larger than every
+// finite pattern, so an integer maximum does it off the FP64 pipe (a DSETP pair per maximum otherwise).  Measured: qp_mma_g<1,1>
+// 1.777 -> 1.727 ms; qp_mma<1> 1.500 -> 1.519 ms on the kernel with two separate passes (it started to spill), 1.506 -> 1.484 ms
+// together with the rolled two-pass loop (250 registers, no spills).
 #ifdef NMX_INT
 __device__ __forceinline__ double nmx(double a, double b)
 {
