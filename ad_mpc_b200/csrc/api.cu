@@ -536,6 +536,25 @@ extern "C" int admpc_batch_set_duals(admpc_batch *h, const double *pi, const dou
     if (r == 0 && su) r = put_rows(h, su, h->P.sub, N * 2);
     return r;
 }
+// internal (pipe.cu): give the handle's stream a scheduling priority (0 = highest level the device offers, larger = lower; clamped
+// to the device's range).  The chunk pipeline runs chunk c at a higher priority than chunk c + 1, so that the CTA scheduler
+// finishes the chunks in order and every read-back overlaps the next chunk's kernels.
+int admpc_batch_set_stream_level(admpc_batch *h, int level)
+{
+    if (!h) return ADMPC_E_ARG;
+    CUDA_CHECK_RET(cudaSetDevice(h->device));
+    int least = 0, greatest = 0;
+    CUDA_CHECK_RET(cudaDeviceGetStreamPriorityRange(&least, &greatest));      // numerically: greatest <= least
+    int prio = greatest + level;
+    if (prio > least) prio = least;
+    cudaStream_t ns = nullptr;
+    CUDA_CHECK_RET(cudaStreamCreateWithPriority(&ns, cudaStreamNonBlocking, prio));
+    CUDA_CHECK_RET(cudaStreamSynchronize(h->stream));
+    cudaStreamDestroy(h->stream);
+    h->stream = ns;
+    return 0;
+}
+
 extern "C" int admpc_batch_reset(admpc_batch *h)
 {
     if (!h) return ADMPC_E_ARG;

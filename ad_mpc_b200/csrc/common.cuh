@@ -138,6 +138,9 @@ struct SmemGuard {
     }
 };
 
+struct admpc_batch;
+int admpc_batch_set_stream_level(admpc_batch *h, int level);      // api.cu, used by the chunk pipeline (pipe.cu)
+
 // kernel launchers (defined in the .cu files)
 void launch_prepare(const Params &P, cudaStream_t s);
 void launch_gp_sweep(const Params &P, cudaStream_t s);   // pass 1 of a GP-augmented preparation: GP mean / gradient at the RK4 stage points -> gpr

@@ -4,6 +4,7 @@
 // for B vehicles with HOST buffers: the batch is cut into K contiguous chunks; the H2D copy of chunk c+1, the two solver
 // kernels of chunk c and the D2H copy of chunk c-1 overlap because every chunk owns a stream.  One call, one host
 // thread; a C caller reaches the same end-to-end rate as the Python wrapper (which is now a thin shell over this).
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -35,6 +36,12 @@ extern "C" int admpc_pipe_create(const admpc_opts *opts, int B, int device, int 
         const int r = admpc_batch_create(opts, n, device, &h);
         if (r) { admpc_pipe_free(p); return r; }
         p->parts.push_back(h); p->lo.push_back(lo); p->hi.push_back(lo + n);
+        // earlier chunks at higher stream priority: the chunks then finish in order instead of all together at the end, and the
+        // read-back of chunk c overlaps the kernels of chunk c + 1 (ADMPC_PIPE_FLAT=1: equal priorities, the first version)
+        if (!getenv("ADMPC_PIPE_FLAT")) {
+            const int rr = admpc_batch_set_stream_level(h, c);
+            if (rr) { admpc_pipe_free(p); return rr; }
+        }
     }
     *out = p;
     return 0;
