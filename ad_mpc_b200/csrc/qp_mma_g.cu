@@ -774,22 +774,33 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : (NW == 2) ? 4
             stv(st + W_BAR, Rt[0], Rt[1]); stv(st + W_BAR + 2, rtv[0], rtv[1]); stv(st + W_BAR + 4, Qt1, Qt6);
             stv(st + W_GX, gx[0], gx[1]); stv(st + W_GX + 2, gx[2], gx[3]); stv(st + W_GX + 4, gx[4], gx[5]); st[W_GX + 6] = gx[6];
         }
-        ng = wmax32(ng); nb = wmax32(nb); nd = wmax32(nd); nm = wmax32(nm); summ = wsum32(summ);
+        // Termination tests as warp votes on the lanes' own partial norms ("every partial maximum is finite / below its tolerance"
+        // is the same statement as the one about the maximum): the four norm reductions themselves are only needed for the
+        // report, i.e. in the iteration that leaves the loop.
+        summ = wsum32(summ);
+        bool fin = __all_sync(FULL, isfinite(ng) && isfinite(nb) && isfinite(nd) && isfinite(nm));
+        bool conv = __all_sync(FULL, ng < o.tol_stat && nb < o.tol_eq && nd < o.tol_ineq && nm < o.tol_comp);
         if (NW > 1) {
-            if (l == 0) { red[wid * 8] = ng; red[wid * 8 + 1] = nb; red[wid * 8 + 2] = nd; red[wid * 8 + 3] = nm; red[wid * 8 + 4] = summ; }
+            if (l == 0) { red[wid * 8 + 4] = summ; red[wid * 8 + 5] = fin ? 1.0 : 0.0; red[wid * 8 + 6] = conv ? 1.0 : 0.0; }
             __syncthreads();
-            ng = red[0]; nb = red[1]; nd = red[2]; nm = red[3]; summ = red[4];
+            summ = red[4]; fin = red[5] != 0.0; conv = red[6] != 0.0;
 #pragma unroll
-            for (int w = 1; w < NW; w++) {
-                ng = nmx(ng, red[w * 8]); nb = nmx(nb, red[w * 8 + 1]); nd = nmx(nd, red[w * 8 + 2]); nm = nmx(nm, red[w * 8 + 3]);
-                summ += red[w * 8 + 4];
-            }
+            for (int w = 1; w < NW; w++) { summ += red[w * 8 + 4]; fin = fin && red[w * 8 + 5] != 0.0; conv = conv && red[w * 8 + 6] != 0.0; }
             __syncthreads();
         }
-        res0 = ng; res1 = nb; res2 = nd; res3 = nm;
-        if (!(isfinite(ng) && isfinite(nb) && isfinite(nd) && isfinite(nm))) { status = 3; break; }
-        if (ng < o.tol_stat && nb < o.tol_eq && nd < o.tol_ineq && nm < o.tol_comp) { status = 0; break; }
-        if (iter >= o.iter_max) { status = 1; break; }
+        if (!fin || conv || iter >= o.iter_max) {
+            ng = wmax32(ng); nb = wmax32(nb); nd = wmax32(nd); nm = wmax32(nm);
+            if (NW > 1) {
+                if (l == 0) { red[wid * 8] = ng; red[wid * 8 + 1] = nb; red[wid * 8 + 2] = nd; red[wid * 8 + 3] = nm; }
+                __syncthreads();
+                ng = red[0]; nb = red[1]; nd = red[2]; nm = red[3];
+#pragma unroll
+                for (int w = 1; w < NW; w++) { ng = nmx(ng, red[w * 8]); nb = nmx(nb, red[w * 8 + 1]); nd = nmx(nd, red[w * 8 + 2]); nm = nmx(nm, red[w * 8 + 3]); }
+            }
+            res0 = ng; res1 = nb; res2 = nd; res3 = nm;
+            status = !fin ? 3 : (conv ? 0 : 1);
+            break;
+        }
         const double mu = summ * inv_nc;
         bsync<NW>();
 
