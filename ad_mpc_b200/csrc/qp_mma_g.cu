@@ -879,18 +879,27 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : (NW == 2) ? 4
 #pragma unroll
                     for (int q = 0; q < NQ; q++) { fa[q] = q_grad<CS>(R, Ss, ea, q, 0.0); fb[q] = q_grad<CS>(R, Ss, eb, q, 0.0); }
                 }
-                m_aff = wmaxf32(act ? m_aff : 1.0);
-                s1 = wsum32(act ? s1 : 0.0); s2 = wsum32(act ? s2 : 0.0);
+                // m_aff >= 1 on every lane: two REDUX instructions ; then ONE sum of the lanes' own a s1 + a^2 s2 instead of two sums
+                m_aff = wmax_pos(act ? m_aff : 1.0);
                 if (NW > 1) {
-                    if (l == 0) { red[wid * 8] = m_aff; red[wid * 8 + 1] = s1; red[wid * 8 + 2] = s2; }
+                    if (l == 0) red[wid * 8] = m_aff;
                     __syncthreads();
-                    m_aff = red[0]; s1 = red[1]; s2 = red[2];
+                    m_aff = red[0];
 #pragma unroll
-                    for (int w = 1; w < NW; w++) { m_aff = fmax(m_aff, red[w * 8]); s1 += red[w * 8 + 1]; s2 += red[w * 8 + 2]; }
+                    for (int w = 1; w < NW; w++) m_aff = fmax(m_aff, red[w * 8]);
                     __syncthreads();
                 }
                 const double a_aff = rcp_w(m_aff);           // min(1, min ratio) = 1 / max(1, max of the inverse ratios)
-                const double mu_aff = (summ + a_aff * s1 + a_aff * a_aff * s2) * inv_nc;
+                double s12 = wsum32(act ? a_aff * (s1 + a_aff * s2) : 0.0);
+                if (NW > 1) {
+                    if (l == 0) red[wid * 8 + 1] = s12;
+                    __syncthreads();
+                    s12 = red[1];
+#pragma unroll
+                    for (int w = 1; w < NW; w++) s12 += red[w * 8 + 1];
+                    __syncthreads();
+                }
+                const double mu_aff = (summ + s12) * inv_nc;
                 double sigma = mu_aff * rcp_w(mu);
                 sigma = sigma * sigma * sigma;
                 sigmu = sigma * mu;
@@ -924,16 +933,17 @@ __global__ void __launch_bounds__(32 * NW, (NW == 1) ? MMAG_MINB : (NW == 2) ? 4
             const double mt = node_ratio_t_g<CS>(kge1, Ss, Ds, 1.0);
             if (ad < an * mt) { an = 1.0; ad = mt; }
         }
-        warp_ratio(an, ad);
+        // every lane's own bound an / ad (1 for the lanes without a row that limits the step), then the minimum by two REDUX
+        // instructions instead of five shuffle rounds over (numerator, denominator) pairs
+        double alpha = wmin_pos(an * rcp_w(ad));
         if (NW > 1) {
-            if (l == 0) { red[wid * 8] = an; red[wid * 8 + 1] = ad; }
+            if (l == 0) red[wid * 8] = alpha;
             __syncthreads();
-            an = red[0]; ad = red[1];
+            alpha = red[0];
 #pragma unroll
-            for (int w = 1; w < NW; w++) if (red[w * 8] * ad < an * red[w * 8 + 1]) { an = red[w * 8]; ad = red[w * 8 + 1]; }
+            for (int w = 1; w < NW; w++) alpha = fmin(alpha, red[w * 8]);
             __syncthreads();
         }
-        double alpha = an * rcp_w(ad);
         if (alpha < o.alpha_min) { status = 2; break; }
         if (alpha < 1.0) alpha *= 0.995;
         if (k < N) {

@@ -193,6 +193,23 @@ __device__ __forceinline__ void node_ratio_lam(bool k_ge1, const NCon &C, const 
         if (on && D.dlv[c] < 0.0 && C.lam[c] * ad < an * (-D.dlv[c])) { an = C.lam[c]; ad = -D.dlv[c]; }
     }
 }
+// Warp maximum / minimum of POSITIVE doubles in two REDUX instructions instead of five shuffle rounds: for sign bit 0 the order of
+// the values is the order of the bit patterns, so reduce the high words, then the low words of the lanes that hold the winning
+// high word.  (A NaN has the largest pattern: it wins a maximum and loses a minimum.)
+__device__ __forceinline__ double wmax_pos(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, (hi == mh) ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double wmin_pos(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, (hi == mh) ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
+}
 __device__ __forceinline__ double wmaxf32(double v)       // plain max (no NaN propagation needed: NaNs are caught by the residual norms)
 {
 #pragma unroll
